@@ -1,0 +1,128 @@
+"""ctypes mirror of include/guac.h — the plain-C data contract of the pileup-and-call engine.
+
+Structure layouts follow include/guac.h field by field; tests/test_abi.py checks sizes and offsets against the
+compiled library (guac_abi_sizeof).  No torch types cross this boundary.
+"""
+import ctypes as C
+
+GUAC_ABI_VERSION = 1
+
+# guac_status
+OK = 0
+ERR_INVALID_ARGUMENT = 1
+ERR_UNSORTED_READS = 2
+ERR_CONTIG_ORDER = 3
+ERR_INVALID_CIGAR = 4
+ERR_MISSING_MD = 5
+ERR_MULTIPLE_REFERENCE_BASES = 6
+ERR_BAD_QUALITY = 7
+ERR_CUDA = 8
+ERR_OOM = 9
+ERR_NO_DEVICE = 10
+ERR_UNSUPPORTED = 11
+
+STATUS_NAMES = {
+    0: "GUAC_OK", 1: "GUAC_ERR_INVALID_ARGUMENT", 2: "GUAC_ERR_UNSORTED_READS", 3: "GUAC_ERR_CONTIG_ORDER",
+    4: "GUAC_ERR_INVALID_CIGAR", 5: "GUAC_ERR_MISSING_MD", 6: "GUAC_ERR_MULTIPLE_REFERENCE_BASES",
+    7: "GUAC_ERR_BAD_QUALITY", 8: "GUAC_ERR_CUDA", 9: "GUAC_ERR_OOM", 10: "GUAC_ERR_NO_DEVICE",
+    11: "GUAC_ERR_UNSUPPORTED",
+}
+
+READ_POSITIVE_STRAND = 0x01
+READ_DUPLICATE = 0x02
+READ_FAILED_QC = 0x04
+READ_HAS_MD = 0x08
+READ_PAIRED = 0x10
+
+CIGAR_OPS = "MIDNSHP=X"
+
+GT_REF, GT_ALT, GT_OTHER_ALT, GT_NO_CALL = 0, 1, 2, 3
+GT_NAMES = {0: "Ref", 1: "Alt", 2: "OtherAlt", 3: "NoCall"}
+
+
+class ReadBatchC(C.Structure):
+    _fields_ = [
+        ("n_reads", C.c_uint64),
+        ("n_contigs", C.c_uint32),
+        ("contig_length", C.POINTER(C.c_int64)),
+        ("contig", C.POINTER(C.c_int32)),
+        ("start", C.POINTER(C.c_int64)),
+        ("cigar_off", C.POINTER(C.c_uint64)),
+        ("cigar", C.POINTER(C.c_uint32)),
+        ("seq_off", C.POINTER(C.c_uint64)),
+        ("seq", C.POINTER(C.c_uint8)),
+        ("qual", C.POINTER(C.c_uint8)),
+        ("mapq", C.POINTER(C.c_uint8)),
+        ("flags", C.POINTER(C.c_uint8)),
+        ("sample", C.POINTER(C.c_int32)),
+        ("md_off", C.POINTER(C.c_uint64)),
+        ("md", C.c_char_p),
+    ]
+
+
+class ReferenceC(C.Structure):
+    _fields_ = [
+        ("n_contigs", C.c_uint32),
+        ("base_off", C.POINTER(C.c_uint64)),
+        ("bases", C.POINTER(C.c_uint8)),
+    ]
+
+
+class LocusRangeC(C.Structure):
+    _fields_ = [("contig", C.c_int32), ("task", C.c_int32), ("start", C.c_int64), ("end", C.c_int64)]
+
+
+class ThresholdParamsC(C.Structure):
+    _fields_ = [("threshold_percent", C.c_int32), ("emit_ref", C.c_int32), ("emit_no_call", C.c_int32),
+                ("skip_empty", C.c_int32)]
+
+
+class SomaticParamsC(C.Structure):
+    _fields_ = [("odds_threshold", C.c_int32), ("min_alignment_quality", C.c_int32),
+                ("filter_multi_allelic", C.c_int32), ("max_read_depth", C.c_int32), ("skip_empty", C.c_int32)]
+
+
+class ThresholdRecordC(C.Structure):
+    _fields_ = [("start", C.c_int64), ("contig", C.c_int32), ("sample", C.c_int32), ("ref_off", C.c_uint32),
+                ("alt_off", C.c_uint32), ("ref_len", C.c_uint16), ("alt_len", C.c_uint16), ("gt", C.c_uint8 * 2),
+                ("tie", C.c_uint8), ("pad_", C.c_uint8)]
+
+
+class AlleleEvidenceC(C.Structure):
+    _fields_ = [("likelihood", C.c_double), ("mean_mapping_quality", C.c_double),
+                ("median_mapping_quality", C.c_double), ("mean_base_quality", C.c_double),
+                ("median_base_quality", C.c_double), ("median_mismatches_per_read", C.c_double),
+                ("read_depth", C.c_int32), ("allele_read_depth", C.c_int32), ("forward_depth", C.c_int32),
+                ("allele_forward_depth", C.c_int32)]
+
+
+class SomaticRecordC(C.Structure):
+    _fields_ = [("start", C.c_int64), ("contig", C.c_int32), ("sample", C.c_int32), ("ref_off", C.c_uint32),
+                ("alt_off", C.c_uint32), ("ref_len", C.c_uint16), ("alt_len", C.c_uint16),
+                ("phred_scaled_somatic_likelihood", C.c_int32), ("somatic_log_odds", C.c_double),
+                ("tumor", AlleleEvidenceC), ("normal", AlleleEvidenceC)]
+
+
+class LocusCountsC(C.Structure):
+    _fields_ = [("locus", C.c_int64), ("contig", C.c_int32), ("depth", C.c_int32), ("positive_depth", C.c_int32),
+                ("reference_depth", C.c_int32), ("base_count", C.c_int32 * 4), ("other_count", C.c_int32),
+                ("reference_base", C.c_uint8), ("pad_", C.c_uint8 * 3)]
+
+
+class StatsC(C.Structure):
+    _fields_ = [("reads_total", C.c_uint64), ("reads_relevant", C.c_uint64), ("reads_expanded", C.c_uint64),
+                ("loci_requested", C.c_uint64), ("loci_visited", C.c_uint64), ("records", C.c_uint64),
+                ("tie_loci", C.c_uint64), ("order_sensitive_loci", C.c_uint64), ("kernel_ms", C.c_double),
+                ("kernel_launches", C.c_uint64)]
+
+
+def struct_to_dict(s):
+    out = {}
+    for name, _ in s._fields_:
+        v = getattr(s, name)
+        if isinstance(v, C.Structure):
+            v = struct_to_dict(v)
+        elif isinstance(v, C.Array):
+            v = list(v)
+        out[name] = v
+    return out

@@ -1,0 +1,246 @@
+/*
+ * guac.h — C ABI of the B200 pileup-and-call engine (libguac_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of the reference (MartijnAB/guacamole, Scala/Spark):
+ * "pileupFlatMap ∘ caller closure".  The reference has no FFI for this path; its boundary is the Scala
+ * closure API
+ *     DistributedUtil.pileupFlatMap[T](reads, lociPartitions, skipEmpty, Pileup => Iterator[T], reference)
+ *         (src/main/scala/org/hammerlab/guacamole/DistributedUtil.scala:288-306)
+ *     DistributedUtil.pileupFlatMapTwoRDDs[T](reads1, reads2, lociPartitions, skipEmpty, (Pileup,Pileup) => Iterator[T], ref)
+ *         (DistributedUtil.scala:316-335)
+ * A JVM closure cannot run on a GPU, so the ABI is cut one level up: one fused entry point per caller
+ * closure that the reference ships on this path:
+ *     GermlineThreshold.Caller.callVariantsAtLocus   (commands/GermlineThresholdCaller.scala:90-179)
+ *     SomaticStandard.Caller.findPotentialVariantAtLocus (commands/SomaticStandardCaller.scala:162-245)
+ * plus a generic per-locus histogram entry point for closures that only need counts
+ * (Pileup.depth / positiveDepth / referenceDepth, pileup/Pileup.scala:76-91).
+ *
+ * All functions are extern "C", take plain pointers and sizes, never call back into the host, never abort():
+ * they return a guac_status and leave a message retrievable with guac_last_error().
+ * INTEGRATION.md shows the Scala-side (Panama / JNI) binding a maintainer would add.
+ */
+#ifndef GUAC_H_
+#define GUAC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GUAC_ABI_VERSION 1
+
+/* ---- status codes.  Each maps to the Scala exception the reference throws on this path. -------------- */
+typedef enum guac_status {
+  GUAC_OK = 0,
+  GUAC_ERR_INVALID_ARGUMENT = 1,        /* null pointer, bad sizes, unsorted/overlapping loci ranges            */
+  GUAC_ERR_UNSORTED_READS = 2,          /* "Regions must be sorted by start locus" windowing/SlidingWindow.scala:56 */
+  GUAC_ERR_CONTIG_ORDER = 3,            /* "Regions are not sorted by contig" DistributedUtil.scala:662-664      */
+  GUAC_ERR_INVALID_CIGAR = 4,           /* InvalidCigarElementException pileup/PileupElement.scala:106,277;
+                                           deletion preceded by non-M/=/X (AssertionError :118-122); P operator  */
+  GUAC_ERR_MISSING_MD = 5,              /* ReferenceWithoutMDTagException reads/MappedRead.scala:58-59;
+                                           NoSuchElementException from mdTag.deletions(..) PileupElement.scala:112,117;
+                                           CigarMDTagMismatchException MappedRead.scala:63 */
+  GUAC_ERR_MULTIPLE_REFERENCE_BASES = 6,/* IllegalArgumentException commands/GermlineThresholdCaller.scala:171-174 */
+  GUAC_ERR_BAD_QUALITY = 7,             /* quality byte > 127 would index PhredUtils' table negatively            */
+  GUAC_ERR_CUDA = 8,                    /* any CUDA runtime error (message has the cudaError string)              */
+  GUAC_ERR_OOM = 9,                     /* host or device allocation failed                                       */
+  GUAC_ERR_NO_DEVICE = 10,              /* no CUDA device / kernels not built for it: there is NO CPU fallback    */
+  GUAC_ERR_UNSUPPORTED = 11             /* e.g. more than GUAC_MAX_SAMPLES samples in one read set                */
+} guac_status;
+
+/* ---- input: one columnar batch of MappedReads (reads/MappedRead.scala:35-48), caller-owned ------------- */
+/* flags bits (reads/Read.scala:227-232, 253-267) */
+#define GUAC_READ_POSITIVE_STRAND 0x01u  /* isPositiveStrand = !SAM flag 0x10 */
+#define GUAC_READ_DUPLICATE       0x02u  /* isDuplicate (SAM 0x400); informational — input filters run host-side */
+#define GUAC_READ_FAILED_QC       0x04u  /* failedVendorQualityChecks (SAM 0x200) */
+#define GUAC_READ_HAS_MD          0x08u  /* mdTagOpt.isDefined */
+#define GUAC_READ_PAIRED          0x10u
+
+/* CIGAR ops use the BAM encoding (len << 4 | op), op index into "MIDNSHP=X" (htsjdk CigarOperator). */
+#define GUAC_CIGAR_M 0u
+#define GUAC_CIGAR_I 1u
+#define GUAC_CIGAR_D 2u
+#define GUAC_CIGAR_N 3u
+#define GUAC_CIGAR_S 4u
+#define GUAC_CIGAR_H 5u
+#define GUAC_CIGAR_P 6u
+#define GUAC_CIGAR_EQ 7u
+#define GUAC_CIGAR_X 8u
+
+typedef struct guac_read_batch {
+  uint64_t n_reads;
+  uint32_t n_contigs;            /* contig indices are 0..n_contigs-1                                           */
+  const int64_t* contig_length;  /* [n_contigs] (may be NULL: then no upper bound is checked)                    */
+  const int32_t* contig;         /* [n] contig index; reads must be sorted by (contig, start)                    */
+  const int64_t* start;          /* [n] 0-based inclusive (MappedRead.start)                                     */
+  const uint64_t* cigar_off;     /* [n+1] offsets into cigar[]                                                   */
+  const uint32_t* cigar;         /* BAM-encoded ops                                                              */
+  const uint64_t* seq_off;       /* [n+1] offsets into seq[] and qual[] (sequence.length == baseQualities.length)*/
+  const uint8_t* seq;            /* ASCII bases, any byte allowed (Bases.scala)                                  */
+  const uint8_t* qual;           /* numeric phred (no +33), each <= 127                                          */
+  const uint8_t* mapq;           /* [n] alignmentQuality 0..255                                                  */
+  const uint8_t* flags;          /* [n] GUAC_READ_* bits                                                         */
+  const int32_t* sample;         /* [n] sample index (sampleName interned by the shim), or NULL = all sample 0   */
+  const uint64_t* md_off;        /* [n+1] offsets into md[]; empty string + !HAS_MD = no MD tag                  */
+  const char* md;                /* MD tag strings, not NUL-terminated                                           */
+} guac_read_batch;
+
+/* optional FASTA-derived reference (ReferenceGenome.getReferenceBase, DistributedUtil.scala:266) */
+typedef struct guac_reference {
+  uint32_t n_contigs;
+  const uint64_t* base_off;      /* [n_contigs+1] offsets into bases[] */
+  const uint8_t* bases;          /* ASCII, upper-case */
+} guac_reference;
+
+typedef struct guac_locus_range {
+  int32_t contig;
+  int32_t task;                  /* LociMap[Long] value = task / GPU shard id (informational on one GPU)        */
+  int64_t start;                 /* inclusive */
+  int64_t end;                   /* exclusive */
+} guac_locus_range;
+
+/* ---- parameters: 1:1 with the reference's args4j flags ------------------------------------------------- */
+typedef struct guac_threshold_params {   /* commands/GermlineThresholdCaller.scala:42-51 */
+  int32_t threshold_percent;     /* --threshold, default 8 */
+  int32_t emit_ref;              /* --emit-ref */
+  int32_t emit_no_call;          /* --emit-no-call */
+  int32_t skip_empty;            /* pileupFlatMap skipEmpty (the caller passes true) */
+} guac_threshold_params;
+
+typedef struct guac_somatic_params {     /* commands/SomaticStandardCaller.scala:49-60, filters/PileupFilter.scala:48-59 */
+  int32_t odds_threshold;        /* --odds, default 20 */
+  int32_t min_alignment_quality; /* --min-mapq, default 1 */
+  int32_t filter_multi_allelic;  /* --filter-multi-allelic */
+  int32_t max_read_depth;        /* --max-tumor-read-depth, default INT32_MAX */
+  int32_t skip_empty;
+} guac_somatic_params;
+
+/* ---- output records ------------------------------------------------------------------------------------ */
+/* bdg-formats GenotypeAllele */
+#define GUAC_GT_REF 0u
+#define GUAC_GT_ALT 1u
+#define GUAC_GT_OTHER_ALT 2u
+#define GUAC_GT_NO_CALL 3u
+
+/* One bdg-formats Genotype as built by GermlineThresholdCaller.scala:106-117.
+ * ref/alt bytes live in the result's byte pool at [ref_off, ref_off+ref_len) / [alt_off, ...). */
+typedef struct guac_threshold_record {
+  int64_t start;                 /* Variant.start = pileup.locus */
+  int32_t contig;
+  int32_t sample;
+  uint32_t ref_off;
+  uint32_t alt_off;
+  uint16_t ref_len;
+  uint16_t alt_len;
+  uint8_t gt[2];
+  uint8_t tie;                   /* 1 if an equal-count tie made the allele choice depend on Scala HashMap order */
+  uint8_t pad_;
+} guac_threshold_record;
+
+/* variants/AlleleEvidence.scala:41-50 */
+typedef struct guac_allele_evidence {
+  double likelihood;
+  double mean_mapping_quality;
+  double median_mapping_quality;
+  double mean_base_quality;
+  double median_base_quality;
+  double median_mismatches_per_read;
+  int32_t read_depth;
+  int32_t allele_read_depth;
+  int32_t forward_depth;
+  int32_t allele_forward_depth;
+} guac_allele_evidence;
+
+/* variants/CalledSomaticAllele.scala:36-51 + the fields AlleleConversions.scala:47-62 derives from it */
+typedef struct guac_somatic_record {
+  int64_t start;
+  int32_t contig;
+  int32_t sample;                /* tumorPileup.sampleName */
+  uint32_t ref_off;
+  uint32_t alt_off;
+  uint16_t ref_len;
+  uint16_t alt_len;
+  int32_t phred_scaled_somatic_likelihood;  /* genotypeQuality */
+  double somatic_log_odds;
+  guac_allele_evidence tumor;    /* tumorVariantEvidence */
+  guac_allele_evidence normal;   /* normalReferenceEvidence */
+} guac_somatic_record;
+
+/* per-locus histogram (guac_pileup_counts): one row per visited locus */
+typedef struct guac_locus_counts {
+  int64_t locus;
+  int32_t contig;
+  int32_t depth;                 /* Pileup.depth */
+  int32_t positive_depth;        /* Pileup.positiveDepth */
+  int32_t reference_depth;       /* Pileup.referenceDepth (Match elements only) */
+  int32_t base_count[4];         /* Match/Mismatch elements whose sequenced base is A,C,G,T */
+  int32_t other_count;           /* every other element: insertion / deletion / mid-deletion / clipped / non-ACGT base */
+  uint8_t reference_base;        /* Pileup.referenceBase (ASCII) */
+  uint8_t pad_[3];
+} guac_locus_counts;
+
+/* counters the reference keeps in Spark accumulators (DistributedUtil.scala:573-618) */
+typedef struct guac_stats {
+  uint64_t reads_total;
+  uint64_t reads_relevant;       /* overlap >= 1 requested locus */
+  uint64_t reads_expanded;       /* after duplication across task boundaries */
+  uint64_t loci_requested;
+  uint64_t loci_visited;         /* non-empty pileups when skip_empty */
+  uint64_t records;
+  uint64_t tie_loci;             /* SURVEY H1b */
+  uint64_t order_sensitive_loci; /* MD-derived reference bases disagree */
+  double kernel_ms;              /* device time of the pileup+call kernels of the last call (CUDA events) */
+  uint64_t kernel_launches;      /* number of kernels launched by the last call */
+} guac_stats;
+
+typedef struct guac_ctx guac_ctx;
+typedef struct guac_reads guac_reads;
+typedef struct guac_result guac_result;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------ */
+int guac_abi_version(void);
+guac_status guac_ctx_create(int device, guac_ctx** out);
+void guac_ctx_destroy(guac_ctx* ctx);
+const char* guac_last_error(const guac_ctx* ctx);   /* valid until the next call on ctx */
+const char* guac_status_string(guac_status s);
+
+/* Pack a host batch into the device SoA (copies; caller keeps ownership of `batch`).  Validates sortedness,
+ * CIGAR/MD consistency and quality range — the checks SlidingWindow / MappedRead do lazily. `ref` may be NULL
+ * (reference bases then come from MD tags, Pileup.referenceBaseAtLocus pileup/Pileup.scala:157-165). */
+guac_status guac_reads_pack(guac_ctx* ctx, const guac_read_batch* batch, const guac_reference* ref, guac_reads** out);
+void guac_reads_free(guac_reads* reads);
+uint64_t guac_reads_count(const guac_reads* reads);
+uint64_t guac_reads_device_bytes(const guac_reads* reads);
+
+/* ---- the hot path ---------------------------------------------------------------------------------------- */
+/* pileupFlatMap(reads, ranges, skip_empty, callVariantsAtLocus(_, threshold, emitRef, emitNoCall)) */
+guac_status guac_germline_threshold(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges,
+                                    size_t n_ranges, const guac_threshold_params* params, guac_result** out);
+/* pileupFlatMapTwoRDDs(tumor, normal, ranges, skip_empty, findPotentialVariantAtLocus(...)) */
+guac_status guac_somatic_standard(guac_ctx* ctx, const guac_reads* tumor, const guac_reads* normal,
+                                  const guac_locus_range* ranges, size_t n_ranges,
+                                  const guac_somatic_params* params, guac_result** out);
+/* pileupFlatMap(reads, ranges, skip_empty, p => (depth, positiveDepth, referenceDepth, base histogram)) */
+guac_status guac_pileup_counts(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges,
+                               size_t n_ranges, int skip_empty, guac_result** out);
+
+/* ---- results (library-owned; pointers valid until guac_result_free) -------------------------------------- */
+size_t guac_result_n(const guac_result* r);
+const guac_threshold_record* guac_result_threshold_records(const guac_result* r); /* NULL if other kind */
+const guac_somatic_record* guac_result_somatic_records(const guac_result* r);
+const guac_locus_counts* guac_result_counts(const guac_result* r);
+const uint8_t* guac_result_bytes(const guac_result* r, size_t* n_bytes);            /* allele byte pool */
+const guac_stats* guac_result_stats(const guac_result* r);
+void guac_result_free(guac_result* r);
+
+/* ---- LociPartitioning (host-side; DistributedUtil.scala:83-108). Writes at most max_out ranges (task set),
+ * returns the number produced through *n_out. ------------------------------------------------------------- */
+guac_status guac_partition_loci_uniformly(int64_t tasks, const guac_locus_range* loci, size_t n_loci,
+                                          guac_locus_range* out, size_t max_out, size_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GUAC_H_ */
