@@ -1,0 +1,79 @@
+"""Loads libguac_b200.so (the CUDA engine behind include/guac.h) and declares its C ABI for ctypes.
+
+There is no CPU fallback: if the library is missing the import of any caller fails loudly, and on a machine without
+a B200 `guac_ctx_create` returns GUAC_ERR_NO_DEVICE."""
+import ctypes as C
+import os
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libguac_b200.so")
+
+# every symbol include/guac.h declares (tests/test_abi.py checks the library exports them all)
+EXPORTED = [
+    "guac_abi_version", "guac_ctx_create", "guac_ctx_destroy", "guac_last_error", "guac_status_string",
+    "guac_reads_pack", "guac_reads_free", "guac_reads_count", "guac_reads_device_bytes",
+    "guac_reads_order_sensitive_loci", "guac_reads_pack_kernel_ms",
+    "guac_germline_threshold", "guac_somatic_standard", "guac_pileup_counts",
+    "guac_result_n", "guac_result_threshold_records", "guac_result_somatic_records", "guac_result_counts",
+    "guac_result_bytes", "guac_result_stats", "guac_result_free", "guac_partition_loci_uniformly",
+]
+
+_lib = None
+
+
+class GuacError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{abi.STATUS_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(guacamole_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.guac_abi_version.restype = C.c_int
+    L.guac_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.guac_ctx_destroy.argtypes = [vp]
+    L.guac_ctx_destroy.restype = None
+    L.guac_last_error.argtypes = [vp]
+    L.guac_last_error.restype = C.c_char_p
+    L.guac_status_string.argtypes = [C.c_int]
+    L.guac_status_string.restype = C.c_char_p
+    L.guac_reads_pack.argtypes = [vp, C.POINTER(abi.ReadBatchC), C.POINTER(abi.ReferenceC), C.POINTER(vp)]
+    L.guac_reads_free.argtypes = [vp]
+    L.guac_reads_free.restype = None
+    for f in ("guac_reads_count", "guac_reads_device_bytes", "guac_reads_order_sensitive_loci"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = C.c_uint64
+    L.guac_reads_pack_kernel_ms.argtypes = [vp]
+    L.guac_reads_pack_kernel_ms.restype = C.c_double
+    L.guac_germline_threshold.argtypes = [vp, vp, C.POINTER(abi.LocusRangeC), C.c_size_t,
+                                          C.POINTER(abi.ThresholdParamsC), C.POINTER(vp)]
+    L.guac_somatic_standard.argtypes = [vp, vp, vp, C.POINTER(abi.LocusRangeC), C.c_size_t,
+                                        C.POINTER(abi.SomaticParamsC), C.POINTER(vp)]
+    L.guac_pileup_counts.argtypes = [vp, vp, C.POINTER(abi.LocusRangeC), C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.guac_result_n.argtypes = [vp]
+    L.guac_result_n.restype = C.c_size_t
+    L.guac_result_threshold_records.argtypes = [vp]
+    L.guac_result_threshold_records.restype = C.POINTER(abi.ThresholdRecordC)
+    L.guac_result_somatic_records.argtypes = [vp]
+    L.guac_result_somatic_records.restype = C.POINTER(abi.SomaticRecordC)
+    L.guac_result_counts.argtypes = [vp]
+    L.guac_result_counts.restype = C.POINTER(abi.LocusCountsC)
+    L.guac_result_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.guac_result_bytes.restype = C.POINTER(C.c_uint8)
+    L.guac_result_stats.argtypes = [vp]
+    L.guac_result_stats.restype = C.POINTER(abi.StatsC)
+    L.guac_result_free.argtypes = [vp]
+    L.guac_result_free.restype = None
+    L.guac_partition_loci_uniformly.argtypes = [C.c_int64, C.POINTER(abi.LocusRangeC), C.c_size_t,
+                                                C.POINTER(abi.LocusRangeC), C.c_size_t, C.POINTER(C.c_size_t)]
+    _lib = L
+    return L

@@ -1,0 +1,197 @@
+"""Host-side mirror of the reference's caller interface for the pileup-and-call path.
+
+    reference (Scala)                                                       here
+    ---------------------------------------------------------------------  -----------------------------------------
+    DistributedUtil.pileupFlatMap(reads, lociPartitions, skipEmpty,          germline_threshold(ctx, reads, loci, ...)
+        GermlineThreshold.Caller.callVariantsAtLocus(_, threshold, ...))      (commands/GermlineThresholdCaller.scala:73-81)
+    DistributedUtil.pileupFlatMapTwoRDDs(tumor, normal, lociPartitions,      somatic_standard(ctx, tumor, normal, loci, ...)
+        skipEmpty, SomaticStandard.Caller.findPotentialVariantAtLocus(...))   (commands/SomaticStandardCaller.scala:103-119)
+    pileupFlatMap(reads, loci, skipEmpty, p => (depth, ...))                 pileup_counts(ctx, reads, loci, skip_empty)
+
+Everything goes through the C ABI of include/guac.h (libguac_b200.so); nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import abi
+from ._lib import GuacError, lib
+from .loci import ranges_to_c
+from .reads import ReadBatch
+
+COUNTS_DTYPE = np.dtype([("locus", "<i8"), ("contig", "<i4"), ("depth", "<i4"), ("positive_depth", "<i4"),
+                         ("reference_depth", "<i4"), ("base_count", "<i4", 4), ("other_count", "<i4"),
+                         ("reference_base", "u1"), ("pad_", "u1", 3)])
+THRESHOLD_DTYPE = np.dtype([("start", "<i8"), ("contig", "<i4"), ("sample", "<i4"), ("ref_off", "<u4"),
+                            ("alt_off", "<u4"), ("ref_len", "<u2"), ("alt_len", "<u2"), ("gt", "u1", 2), ("tie", "u1"),
+                            ("pad_", "u1")])
+_EVIDENCE = [("likelihood", "<f8"), ("mean_mapping_quality", "<f8"), ("median_mapping_quality", "<f8"),
+             ("mean_base_quality", "<f8"), ("median_base_quality", "<f8"), ("median_mismatches_per_read", "<f8"),
+             ("read_depth", "<i4"), ("allele_read_depth", "<i4"), ("forward_depth", "<i4"),
+             ("allele_forward_depth", "<i4")]
+SOMATIC_DTYPE = np.dtype([("start", "<i8"), ("contig", "<i4"), ("sample", "<i4"), ("ref_off", "<u4"),
+                          ("alt_off", "<u4"), ("ref_len", "<u2"), ("alt_len", "<u2"),
+                          ("phred_scaled_somatic_likelihood", "<i4"), ("somatic_log_odds", "<f8"),
+                          ("tumor", _EVIDENCE), ("normal", _EVIDENCE)])
+assert COUNTS_DTYPE.itemsize == C.sizeof(abi.LocusCountsC)
+assert THRESHOLD_DTYPE.itemsize == C.sizeof(abi.ThresholdRecordC)
+assert SOMATIC_DTYPE.itemsize == C.sizeof(abi.SomaticRecordC)
+
+
+class Context:
+    """guac_ctx: one CUDA device + stream.  Single-threaded; use one per thread / rank."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().guac_ctx_create(device, C.byref(self._h))
+        if rc != 0:
+            raise GuacError(rc, "guac_ctx_create failed (no CUDA device of compute capability 10.x?)")
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GuacError(rc, lib().guac_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().guac_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def pack(self, batch: ReadBatch, reference: Optional[Sequence[bytes]] = None) -> "PackedReads":
+        return PackedReads(self, batch, reference)
+
+
+class PackedReads:
+    """guac_reads: one sample's start-sorted reads packed into the device SoA (guac_reads_pack)."""
+
+    def __init__(self, ctx: Context, batch: ReadBatch, reference: Optional[Sequence[bytes]] = None):
+        self.ctx = ctx
+        self.contig_names = list(batch.contig_names)
+        self.sample_names = list(batch.sample_names)
+        self._h = C.c_void_p()
+        b = batch.to_c()
+        ref = None
+        if reference is not None:
+            offs = np.zeros(len(reference) + 1, np.uint64)
+            offs[1:] = np.cumsum([len(x) for x in reference])
+            data = np.frombuffer(b"".join(reference) or b"\0", dtype=np.uint8).copy()
+            ref = abi.ReferenceC(len(reference), offs.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                 data.ctypes.data_as(C.POINTER(C.c_uint8)))
+        ctx._check(lib().guac_reads_pack(ctx._h, C.byref(b), C.byref(ref) if ref is not None else None,
+                                         C.byref(self._h)))
+
+    @property
+    def n_reads(self) -> int:
+        return int(lib().guac_reads_count(self._h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(lib().guac_reads_device_bytes(self._h))
+
+    @property
+    def order_sensitive_loci(self) -> int:
+        return int(lib().guac_reads_order_sensitive_loci(self._h))
+
+    @property
+    def pack_kernel_ms(self) -> float:
+        return float(lib().guac_reads_pack_kernel_ms(self._h))
+
+    def free(self):
+        if self._h:
+            lib().guac_reads_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Result:
+    """guac_result copied into numpy structured arrays + the allele byte pool."""
+
+    def __init__(self, handle, kind: str):
+        L = lib()
+        self.kind = kind
+        n = L.guac_result_n(handle)
+        nb = C.c_size_t()
+        bp = L.guac_result_bytes(handle, C.byref(nb))
+        self.bytes = C.string_at(bp, nb.value) if nb.value else b""
+        self.stats = abi.struct_to_dict(L.guac_result_stats(handle).contents)
+        if kind == "threshold":
+            p, dt = L.guac_result_threshold_records(handle), THRESHOLD_DTYPE
+        elif kind == "somatic":
+            p, dt = L.guac_result_somatic_records(handle), SOMATIC_DTYPE
+        else:
+            p, dt = L.guac_result_counts(handle), COUNTS_DTYPE
+        self.records = np.frombuffer(C.string_at(p, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dt)
+        L.guac_result_free(handle)
+
+    def __len__(self):
+        return len(self.records)
+
+    def _s(self, off, ln):
+        return self.bytes[int(off):int(off) + int(ln)].decode("latin1")
+
+    def genotypes(self) -> List[dict]:
+        """Records as the fields of the bdg-formats Genotype the reference builds
+        (GermlineThresholdCaller.scala:106-117, AlleleConversions.scala:47-62)."""
+        out = []
+        for r in self.records:
+            d = dict(contig=int(r["contig"]), start=int(r["start"]), sample=int(r["sample"]),
+                     ref=self._s(r["ref_off"], r["ref_len"]), alt=self._s(r["alt_off"], r["alt_len"]))
+            if self.kind == "threshold":
+                d["gt"] = (int(r["gt"][0]), int(r["gt"][1]))
+                d["tie"] = int(r["tie"])
+            else:
+                d["gt"] = (abi.GT_REF, abi.GT_ALT)
+                d["phred"] = int(r["phred_scaled_somatic_likelihood"])
+                d["somatic_log_odds"] = float(r["somatic_log_odds"])
+                for side in ("tumor", "normal"):
+                    d[side] = {k: (float(r[side][k]) if k[0] == "m" or k == "likelihood" else int(r[side][k]))
+                               for k, _ in _EVIDENCE}
+            out.append(d)
+        return out
+
+
+def _ranges(loci):
+    return ranges_to_c(loci), len(loci)
+
+
+def germline_threshold(ctx: Context, reads: PackedReads, loci_partitions, threshold: int = 8, emit_ref: bool = False,
+                       emit_no_call: bool = False, skip_empty: bool = True) -> Result:
+    """pileupFlatMap(reads, lociPartitions, skipEmpty, callVariantsAtLocus(_, threshold, emitRef, emitNoCall))."""
+    arr, n = _ranges(loci_partitions)
+    prm = abi.ThresholdParamsC(threshold, int(emit_ref), int(emit_no_call), int(skip_empty))
+    h = C.c_void_p()
+    ctx._check(lib().guac_germline_threshold(ctx._h, reads._h, arr, n, C.byref(prm), C.byref(h)))
+    return Result(h, "threshold")
+
+
+def somatic_standard(ctx: Context, tumor: PackedReads, normal: PackedReads, loci_partitions, odds_threshold: int = 20,
+                     min_alignment_quality: int = 1, filter_multi_allelic: bool = False,
+                     max_read_depth: int = 2 ** 31 - 1, skip_empty: bool = True) -> Result:
+    """pileupFlatMapTwoRDDs(tumor, normal, lociPartitions, skipEmpty, findPotentialVariantAtLocus(...))."""
+    arr, n = _ranges(loci_partitions)
+    prm = abi.SomaticParamsC(odds_threshold, min_alignment_quality, int(filter_multi_allelic), max_read_depth,
+                             int(skip_empty))
+    h = C.c_void_p()
+    ctx._check(lib().guac_somatic_standard(ctx._h, tumor._h, normal._h, arr, n, C.byref(prm), C.byref(h)))
+    return Result(h, "somatic")
+
+
+def pileup_counts(ctx: Context, reads: PackedReads, loci_partitions, skip_empty: bool = True) -> Result:
+    """pileupFlatMap(reads, lociPartitions, skipEmpty, p => depth / positiveDepth / referenceDepth / base counts)."""
+    arr, n = _ranges(loci_partitions)
+    h = C.c_void_p()
+    ctx._check(lib().guac_pileup_counts(ctx._h, reads._h, arr, n, int(skip_empty), C.byref(h)))
+    return Result(h, "counts")

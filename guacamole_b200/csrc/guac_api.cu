@@ -1,0 +1,583 @@
+// guac_api.cu — host side of libguac_b200.so: the C ABI of include/guac.h over the CUDA kernels (sm_100a).
+// There is NO CPU fallback: without a CUDA device every entry point fails with GUAC_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "guac_host.cuh"
+#include "guac_pack.cuh"
+#include "guac_pileup.cuh"
+#include "guac_somatic.cuh"
+
+namespace {
+
+void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* ref, guac_reads& out) {
+  if (!b) fail(GUAC_ERR_INVALID_ARGUMENT, "null batch");
+  const uint64_t n = b->n_reads;
+  if (n >= 0xFFFFFFF0ull) fail(GUAC_ERR_UNSUPPORTED, "more than 2^32 reads in one read set: shard it");
+  if (n && (!b->contig || !b->start || !b->cigar_off || !b->seq_off || !b->seq || !b->qual || !b->mapq || !b->flags || !b->md_off))
+    fail(GUAC_ERR_INVALID_ARGUMENT, "null column in read batch");
+  out.ctx = ctx;
+  out.n = n;
+  out.n_contigs = b->n_contigs;
+  if (ref && ref->n_contigs != b->n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "reference and batch disagree on the number of contigs");
+
+  // ---- host pass over the read headers: O(reads + cigar ops); everything per-base happens on the device
+  std::vector<ReadRec> rec(n + 1);
+  std::vector<uint32_t> cig_off(n + 1), md_off(n + 1), read_contig(n);
+  std::vector<int64_t> contig_end(b->n_contigs, 0);
+  std::vector<uint64_t> contig_first(b->n_contigs, ~0ull), contig_last(b->n_contigs, 0);
+  uint64_t pair_total = 0;
+  int32_t prev_contig = -1;
+  int64_t prev_start = 0;
+  std::vector<char> contig_seen(b->n_contigs, 0);
+  if (b->cigar_off[n] >= 0xFFFFFFFFull || b->md_off[n] >= 0xFFFFFFFFull) fail(GUAC_ERR_UNSUPPORTED, "cigar / MD columns too large: shard the read set");
+  out.sample = n ? (b->sample ? b->sample[0] : 0) : 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    const int32_t c = b->contig[i];
+    if (c < 0 || (uint32_t)c >= b->n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "read %llu: contig index %d out of range", (unsigned long long)i, c);
+    if (c != prev_contig) {
+      if (contig_seen[c]) fail(GUAC_ERR_CONTIG_ORDER, "Regions are not sorted by contig (read %llu)", (unsigned long long)i);
+      contig_seen[c] = 1;
+      prev_contig = c;
+      prev_start = 0;
+      contig_first[c] = i;
+    }
+    contig_last[c] = i + 1;
+    const int64_t start = b->start[i];
+    if (start < prev_start) fail(GUAC_ERR_UNSORTED_READS, "Regions must be sorted by start locus (read %llu)", (unsigned long long)i);
+    prev_start = start;
+    if (start < 0) fail(GUAC_ERR_INVALID_ARGUMENT, "read %llu: negative start", (unsigned long long)i);
+    if (b->sample && b->sample[i] != out.sample) fail(GUAC_ERR_UNSUPPORTED, "one read set must hold one sample (split by sample before packing)");
+    if (!(b->flags[i] & GUAC_READ_HAS_MD)) fail(GUAC_ERR_MISSING_MD, "read %llu has no MD tag (the callers load reads with hasMdTag = true)", (unsigned long long)i);
+    const uint64_t c0 = b->cigar_off[i], c1 = b->cigar_off[i + 1];
+    const uint64_t read_len = b->seq_off[i + 1] - b->seq_off[i];
+    if (read_len > (uint64_t)kMaxReadLen) fail(GUAC_ERR_UNSUPPORTED, "read %llu longer than %d bases", (unsigned long long)i, kMaxReadLen);
+    int64_t ref_len = 0, consumed = 0, lead = 0;
+    int phase = 0;  // 0 leading clips, 1 inside the aligned run, 2 trailing clips
+    bool simple = true;
+    for (uint64_t k = c0; k < c1; ++k) {
+      const uint32_t op = b->cigar[k] & 0xF, len = b->cigar[k] >> 4;
+      if (op > 8 || op == GUAC_CIGAR_P) fail(GUAC_ERR_INVALID_CIGAR, "read %llu: unsupported CIGAR operator %u", (unsigned long long)i, op);
+      if (len == 0) fail(GUAC_ERR_INVALID_CIGAR, "read %llu: zero-length CIGAR element", (unsigned long long)i);
+      const bool m = op == GUAC_CIGAR_M || op == GUAC_CIGAR_EQ || op == GUAC_CIGAR_X;
+      if (m || op == GUAC_CIGAR_D || op == GUAC_CIGAR_N) ref_len += len;
+      if (m || op == GUAC_CIGAR_I || op == GUAC_CIGAR_S) consumed += len;
+      if (m) {
+        if (phase == 2) simple = false;
+        phase = 1;
+      } else if (op == GUAC_CIGAR_S || op == GUAC_CIGAR_H) {
+        if (phase == 0) {
+          if (op == GUAC_CIGAR_S) lead += len;
+        } else
+          phase = 2;
+      } else {
+        simple = false;
+      }
+    }
+    if (c1 == c0) simple = false;
+    if ((uint64_t)consumed != read_len) fail(GUAC_ERR_INVALID_CIGAR, "read %llu: CIGAR consumes %lld bases, the read has %llu", (unsigned long long)i, (long long)consumed, (unsigned long long)read_len);
+    const int64_t end = start + ref_len;
+    if (end > 0x7FFFFF00ll) fail(GUAC_ERR_UNSUPPORTED, "read %llu: coordinates beyond 2^31", (unsigned long long)i);
+    if (b->contig_length && end > b->contig_length[c]) fail(GUAC_ERR_INVALID_ARGUMENT, "read %llu ends past its contig", (unsigned long long)i);
+    if (simple && lead > 0xFFFF) simple = false;
+    contig_end[c] = std::max(contig_end[c], end);
+    uint32_t info = (uint32_t)(simple ? (lead & 0xFFFF) : 0) | (simple ? kInfoSimple : 0) |
+                    ((b->flags[i] & GUAC_READ_POSITIVE_STRAND) ? kInfoPositive : 0) | (ref_len == 0 ? kInfoEmpty : 0) |
+                    ((uint32_t)b->mapq[i] << kInfoMapqShift);
+    rec[i] = ReadRec{(int32_t)start, (int32_t)end, (uint32_t)pair_total, info};
+    cig_off[i] = (uint32_t)c0;
+    md_off[i] = (uint32_t)b->md_off[i];
+    read_contig[i] = (uint32_t)c;
+    pair_total += (read_len + 31) / 32;
+    if (pair_total >= 0xFFFFFF00ull) fail(GUAC_ERR_UNSUPPORTED, "more than 2^37 bases in one read set: shard it");
+  }
+  rec[n] = ReadRec{0x7FFFFFFF, 0x7FFFFFFF, (uint32_t)pair_total, 0};
+  cig_off[n] = (uint32_t)b->cigar_off[n];
+  md_off[n] = (uint32_t)b->md_off[n];
+
+  // ---- contig geometry
+  out.contigs.resize(b->n_contigs);
+  uint64_t word_off = 0, gran_off = 0;
+  for (uint32_t c = 0; c < b->n_contigs; ++c) {
+    ContigInfo& ci = out.contigs[c];
+    int64_t len = b->contig_length ? b->contig_length[c] : contig_end[c];
+    if (ref) len = std::max<int64_t>(len, (int64_t)(ref->base_off[c + 1] - ref->base_off[c]));
+    if (len > 0x7FFFFF00ll) fail(GUAC_ERR_UNSUPPORTED, "contig longer than 2^31");
+    ci.read_begin = contig_first[c] == ~0ull ? 0 : contig_first[c];
+    ci.read_end = contig_first[c] == ~0ull ? 0 : contig_last[c];
+    ci.length = (int32_t)len;
+    ci.n_words = (int32_t)((len + 31) / 32);
+    ci.n_grans = (int32_t)((len + kGranuleLoci - 1) / kGranuleLoci);
+    ci.word_off = (uint32_t)word_off;
+    ci.gran_off = (uint32_t)gran_off;
+    ci.pad_ = 0;
+    word_off += (uint64_t)ci.n_words;
+    gran_off += (uint64_t)ci.n_grans;
+    if (word_off >= 0xFFFFFF00ull) fail(GUAC_ERR_UNSUPPORTED, "reference track too large");
+  }
+  out.total_words = word_off;
+  out.total_grans = gran_off;
+
+  // ---- H2D of the raw columns
+  cudaStream_t st = ctx->stream;
+  h2d(ctx, out.rec, rec.data(), n + 1);
+  h2d(ctx, out.cig_off, cig_off.data(), n + 1);
+  h2d(ctx, out.cigar, b->cigar, (size_t)b->cigar_off[n], 1);
+  h2d(ctx, out.seq_off, b->seq_off, n + 1);
+  h2d(ctx, out.seq, b->seq, (size_t)b->seq_off[n], 64);
+  h2d(ctx, out.qual, b->qual, (size_t)b->seq_off[n], 64);
+  h2d(ctx, out.md_off, md_off.data(), n + 1);
+  h2d(ctx, out.md, b->md, (size_t)b->md_off[n], 16);
+  h2d(ctx, out.d_contigs, out.contigs.data(), out.contigs.size());
+  DevBuf<uint32_t> d_read_contig, conflict, gran_count;
+  h2d(ctx, d_read_contig, read_contig.data(), n);
+  out.pairs.alloc(pair_total + 8);
+  out.xmask.alloc(pair_total + 8);
+  out.nm.alloc(n);
+  CUDA_OK(cudaMemsetAsync(out.pairs.p, 0, out.pairs.bytes(), st));
+  CUDA_OK(cudaMemsetAsync(out.xmask.p, 0, out.xmask.bytes(), st));
+  out.trk_lo.alloc(word_off + 1);
+  out.trk_hi.alloc(word_off + 1);
+  out.trk_std.alloc(word_off + 1);
+  conflict.alloc(word_off + 1);
+  CUDA_OK(cudaMemsetAsync(out.trk_lo.p, 0, out.trk_lo.bytes(), st));
+  CUDA_OK(cudaMemsetAsync(out.trk_hi.p, 0, out.trk_hi.bytes(), st));
+  CUDA_OK(cudaMemsetAsync(out.trk_std.p, 0, out.trk_std.bytes(), st));
+  CUDA_OK(cudaMemsetAsync(conflict.p, 0, conflict.bytes(), st));
+  out.gran_first.alloc(gran_off + 1);
+  out.gran_last.alloc(gran_off + 1);
+  gran_count.alloc(gran_off + 1);
+  CUDA_OK(cudaMemsetAsync(out.gran_first.p, 0xFF, out.gran_first.bytes(), st));
+  CUDA_OK(cudaMemsetAsync(out.gran_last.p, 0, out.gran_last.bytes(), st));
+  CUDA_OK(cudaMemsetAsync(gran_count.p, 0, gran_count.bytes(), st));
+  if (ref) {
+    h2d(ctx, out.fasta_off, ref->base_off, (size_t)ref->n_contigs + 1);
+    h2d(ctx, out.fasta, ref->bases, (size_t)ref->base_off[ref->n_contigs], 16);
+  }
+  CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
+
+  PackArgs A;
+  A.R = out.view();
+  A.rec_w = out.rec.p;
+  A.pairs_w = out.pairs.p;
+  A.xmask_w = out.xmask.p;
+  A.nm_w = out.nm.p;
+  A.md_w = out.md.p;
+  A.trk_lo_w = out.trk_lo.p;
+  A.trk_hi_w = out.trk_hi.p;
+  A.trk_std_w = out.trk_std.p;
+  A.conflict_w = conflict.p;
+  A.gran_first_w = out.gran_first.p;
+  A.gran_last_w = out.gran_last.p;
+  A.gran_count_w = gran_count.p;
+  A.read_contig = d_read_contig.p;
+  A.err = ctx->d_err;
+  A.counters = ctx->d_counters;
+
+  CUDA_OK(cudaEventRecord(ctx->ev0, st));
+  out.pack_launches = 0;
+  if (n) {
+    k_pack_bases<<<grid_for(n * 32, 256, ctx->sm_count), 256, 0, st>>>(A);
+    k_granule_index<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(A);
+    k_granule_max<<<grid_for(gran_off, 256, ctx->sm_count), 256, 0, st>>>(A, (uint32_t)gran_off);
+    k_md_track<0><<<grid_for(n, 128, ctx->sm_count), 128, 0, st>>>(A);
+    out.pack_launches += 4;
+    if (!ref) {
+      k_md_track<1><<<grid_for(n, 128, ctx->sm_count), 128, 0, st>>>(A);
+      k_resolve_conflicts<<<grid_for(word_off, 128, ctx->sm_count), 128, 0, st>>>(A, b->n_contigs);
+      out.pack_launches += 2;
+    }
+  }
+  if (ref) {
+    k_fasta_track<<<grid_for(word_off, 256, ctx->sm_count), 256, 0, st>>>(A, b->n_contigs);
+    out.pack_launches += 1;
+  }
+  CUDA_OK(cudaEventRecord(ctx->ev1, st));
+  CUDA_OK(cudaGetLastError());
+  unsigned long long counters[2];
+  CUDA_OK(cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, st));
+  check_device_error(ctx, "guac_reads_pack");
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  out.pack_kernel_ms = ms;
+  out.order_sensitive_loci = counters[0];
+  out.max_reads_per_granule = counters[1];
+}
+
+// ---- tiles over the requested loci -------------------------------------------------------------------------------------------
+uint64_t build_tiles(const guac_reads& reads, const guac_locus_range* ranges, size_t n_ranges, std::vector<TileDesc>& tiles) {
+  uint64_t requested = 0;
+  for (size_t i = 0; i < n_ranges; ++i) {
+    const guac_locus_range& r = ranges[i];
+    if (r.contig < 0 || (uint32_t)r.contig >= reads.n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "locus range %zu: contig out of range", i);
+    if (r.start < 0 || r.end < r.start) fail(GUAC_ERR_INVALID_ARGUMENT, "locus range %zu: bad bounds", i);
+    requested += (uint64_t)(r.end - r.start);
+    const ContigInfo& ci = reads.contigs[r.contig];
+    int64_t s = r.start, e = std::min<int64_t>(r.end, ci.length);  // loci past the track hold no reads
+    for (int64_t t = s / kTileLoci; t * kTileLoci < e; ++t) {
+      TileDesc td;
+      td.contig = r.contig;
+      td.word0 = (int32_t)(t * kTileWords);
+      td.locus_begin = (int32_t)std::max<int64_t>(s, t * kTileLoci);
+      td.locus_end = (int32_t)std::min<int64_t>(e, (t + 1) * kTileLoci);
+      if (td.locus_end > td.locus_begin) tiles.push_back(td);
+    }
+  }
+  return requested;
+}
+
+struct OutBuffers {
+  DevBuf<guac_threshold_record> trec;
+  DevBuf<guac_locus_counts> crec;
+  DevBuf<uint8_t> pool;
+  DevBuf<SlowLocus> slow;
+};
+
+template <int MODE>
+void launch_tile(int W, int grid, size_t smem, cudaStream_t st, const DevReads& R, const TileDesc* tiles, const CallParams& prm, const DevOut& out) {
+  switch (W) {
+    case 8: k_pileup_tile<8, MODE><<<grid, kTileWords, smem, st>>>(R, tiles, prm, out); break;
+    case 12: k_pileup_tile<12, MODE><<<grid, kTileWords, smem, st>>>(R, tiles, prm, out); break;
+    case 16: k_pileup_tile<16, MODE><<<grid, kTileWords, smem, st>>>(R, tiles, prm, out); break;
+    default: k_pileup_tile<20, MODE><<<grid, kTileWords, smem, st>>>(R, tiles, prm, out); break;
+  }
+}
+
+template <int W, int MODE>
+void set_smem_attr() {
+  static bool done = false;
+  if (!done) {
+    CUDA_OK(cudaFuncSetAttribute(k_pileup_tile<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    done = true;
+  }
+}
+void set_all_smem_attrs() {
+  set_smem_attr<8, 0>(); set_smem_attr<12, 0>(); set_smem_attr<16, 0>(); set_smem_attr<20, 0>();
+  set_smem_attr<8, 1>(); set_smem_attr<12, 1>(); set_smem_attr<16, 1>(); set_smem_attr<20, 1>();
+}
+
+int planes_for(uint64_t bound) {
+  if (bound < 256) return 8;
+  if (bound < 4096) return 12;
+  if (bound < 65536) return 16;
+  return 20;
+}
+
+// runs K_tile (+ K_exact on the loci it defers) for one read set; returns the device counters
+void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* ranges, size_t n_ranges, CallParams prm,
+                guac_result& res) {
+  std::vector<TileDesc> tiles;
+  const uint64_t requested = build_tiles(reads, ranges, n_ranges, tiles);
+  res.stats.reads_total = reads.n;
+  res.stats.loci_requested = requested;
+  res.stats.order_sensitive_loci = reads.order_sensitive_loci;
+  if (tiles.empty()) return;
+  set_all_smem_attrs();
+  cudaStream_t st = ctx->stream;
+  DevBuf<TileDesc> d_tiles;
+  h2d(ctx, d_tiles, tiles.data(), tiles.size());
+  uint64_t tile_loci = 0;
+  for (auto& t : tiles) tile_loci += (uint64_t)(t.locus_end - t.locus_begin);
+  const bool dense = prm.mode == 1 || prm.emit_ref || prm.emit_no_call;
+  uint64_t cap_rec = dense ? tile_loci + 16 : std::max<uint64_t>(4096, tile_loci / 64);
+  uint64_t cap_slow = std::max<uint64_t>(4096, tile_loci / 32);
+  uint64_t cap_pool = kPoolDynOff + std::max<uint64_t>(65536, tile_loci / 64);
+  int W = planes_for(reads.max_reads_per_granule);
+  double total_ms = 0;
+  int launches = 0;
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    if (cap_rec >= 0xFFFFFFF0ull || cap_slow >= 0xFFFFFFF0ull || cap_pool >= 0xFFFFFFF0ull)
+      fail(GUAC_ERR_UNSUPPORTED, "too many output records for one call: split the loci ranges");
+    OutBuffers ob;
+    if (prm.mode == 1) ob.crec.alloc(cap_rec); else ob.trec.alloc(cap_rec);
+    ob.pool.alloc(cap_pool);
+    ob.slow.alloc(cap_slow);
+    {
+      std::vector<uint8_t> head(kPoolDynOff, 0);
+      memcpy(head.data(), "<ALT>", 5);
+      for (int v = 0; v < 256; ++v) head[kPoolByteOff + v] = (uint8_t)v;
+      CUDA_OK(cudaMemcpyAsync(ob.pool.p, head.data(), head.size(), cudaMemcpyHostToDevice, st));
+    }
+    CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
+    DevOut out;
+    out.trec = ob.trec.p;
+    out.crec = ob.crec.p;
+    out.cap_rec = (uint32_t)cap_rec;
+    out.pool = ob.pool.p;
+    out.cap_pool = (uint32_t)cap_pool;
+    out.slow = ob.slow.p;
+    out.cap_slow = (uint32_t)cap_slow;
+    out.counters = ctx->d_counters;
+    out.err = ctx->d_err;
+    const DevReads R = reads.view();
+    CUDA_OK(cudaEventRecord(ctx->ev0, st));
+    if (prm.mode == 1) launch_tile<1>(W, (int)tiles.size(), sizeof(TileSmem), st, R, d_tiles.p, prm, out);
+    else launch_tile<0>(W, (int)tiles.size(), sizeof(TileSmem), st, R, d_tiles.p, prm, out);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    unsigned long long c[8];
+    CUDA_OK(cudaMemcpyAsync(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (c[5]) {  // a bit-sliced counter overflowed: widen and rerun
+      if (W >= 20) fail(GUAC_ERR_UNSUPPORTED, "pileup deeper than 2^20 reads");
+      W = W == 8 ? 12 : W == 12 ? 16 : 20;
+      continue;
+    }
+    if (c[2] > cap_slow) {
+      cap_slow = c[2] + 16;
+      continue;
+    }
+    if (c[2]) {
+      const uint32_t n_slow = (uint32_t)c[2];
+      k_exact_loci<<<(n_slow + 63) / 64, 64, 0, st>>>(R, ob.slow.p, n_slow, prm, out);
+      ++launches;
+      CUDA_OK(cudaGetLastError());
+    }
+    CUDA_OK(cudaEventRecord(ctx->ev1, st));
+    CUDA_OK(cudaMemcpyAsync(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, st));
+    check_device_error(ctx, "pileup");
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    total_ms += ms;
+    if (c[0] > cap_rec || kPoolDynOff + c[1] > cap_pool) {
+      cap_rec = std::max<uint64_t>(cap_rec, c[0] + 16);
+      cap_pool = std::max<uint64_t>(cap_pool, kPoolDynOff + c[1] + 16);
+      continue;
+    }
+    // ---- D2H and canonical order
+    std::vector<uint8_t> pool((size_t)(kPoolDynOff + c[1]));
+    CUDA_OK(cudaMemcpyAsync(pool.data(), ob.pool.p, pool.size(), cudaMemcpyDeviceToHost, st));
+    if (prm.mode == 1) {
+      res.counts.resize((size_t)c[0]);
+      if (c[0]) CUDA_OK(cudaMemcpyAsync(res.counts.data(), ob.crec.p, c[0] * sizeof(guac_locus_counts), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      std::sort(res.counts.begin(), res.counts.end(), [](const guac_locus_counts& a, const guac_locus_counts& b) {
+        return std::make_pair(a.contig, a.locus) < std::make_pair(b.contig, b.locus);
+      });
+    } else {
+      std::vector<guac_threshold_record> recs((size_t)c[0]);
+      if (c[0]) CUDA_OK(cudaMemcpyAsync(recs.data(), ob.trec.p, c[0] * sizeof(guac_threshold_record), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      auto key = [&](const guac_threshold_record& r) {
+        return std::make_tuple(r.contig, r.start, r.sample, std::string((const char*)pool.data() + r.ref_off, r.ref_len),
+                               std::string((const char*)pool.data() + r.alt_off, r.alt_len));
+      };
+      std::sort(recs.begin(), recs.end(), [&](const guac_threshold_record& a, const guac_threshold_record& b) { return key(a) < key(b); });
+      res.bytes.clear();
+      for (auto& r : recs) {  // compact the byte pool in record order
+        uint32_t ro = (uint32_t)res.bytes.size();
+        res.bytes.insert(res.bytes.end(), pool.begin() + r.ref_off, pool.begin() + r.ref_off + r.ref_len);
+        uint32_t ao = (uint32_t)res.bytes.size();
+        res.bytes.insert(res.bytes.end(), pool.begin() + r.alt_off, pool.begin() + r.alt_off + r.alt_len);
+        r.ref_off = ro;
+        r.alt_off = ao;
+      }
+      res.threshold = std::move(recs);
+    }
+    res.stats.loci_visited = c[3];
+    res.stats.tie_loci = c[4];
+    res.stats.records = c[0];
+    res.stats.kernel_ms = total_ms;
+    res.stats.kernel_launches = (uint64_t)launches;
+    res.stats.reads_relevant = c[2];  // loci decided by the exact per-element kernel (diagnostic)
+    return;
+  }
+  fail(GUAC_ERR_CUDA, "output buffers did not converge");
+}
+
+}  // namespace
+
+// ---- exported C ABI -------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int guac_abi_version(void) { return GUAC_ABI_VERSION; }
+
+const char* guac_status_string(guac_status s) {
+  switch (s) {
+    case GUAC_OK: return "GUAC_OK";
+    case GUAC_ERR_INVALID_ARGUMENT: return "GUAC_ERR_INVALID_ARGUMENT";
+    case GUAC_ERR_UNSORTED_READS: return "GUAC_ERR_UNSORTED_READS";
+    case GUAC_ERR_CONTIG_ORDER: return "GUAC_ERR_CONTIG_ORDER";
+    case GUAC_ERR_INVALID_CIGAR: return "GUAC_ERR_INVALID_CIGAR";
+    case GUAC_ERR_MISSING_MD: return "GUAC_ERR_MISSING_MD";
+    case GUAC_ERR_MULTIPLE_REFERENCE_BASES: return "GUAC_ERR_MULTIPLE_REFERENCE_BASES";
+    case GUAC_ERR_BAD_QUALITY: return "GUAC_ERR_BAD_QUALITY";
+    case GUAC_ERR_CUDA: return "GUAC_ERR_CUDA";
+    case GUAC_ERR_OOM: return "GUAC_ERR_OOM";
+    case GUAC_ERR_NO_DEVICE: return "GUAC_ERR_NO_DEVICE";
+    case GUAC_ERR_UNSUPPORTED: return "GUAC_ERR_UNSUPPORTED";
+  }
+  return "GUAC_ERR_?";
+}
+
+guac_status guac_ctx_create(int device, guac_ctx** out) {
+  if (!out) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return GUAC_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GUAC_ERR_NO_DEVICE;
+  if (prop.major != 10) return GUAC_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+  guac_ctx* ctx = new (std::nothrow) guac_ctx();
+  if (!ctx) return GUAC_ERR_OOM;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  guac_status s = guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaMalloc((void**)&ctx->d_err, sizeof(DevError)));
+    CUDA_OK(cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemset(ctx->d_err, 0, sizeof(DevError)));
+    CUDA_OK(cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned long long)));
+    CUDA_OK(cudaEventCreate(&ctx->ev0));
+    CUDA_OK(cudaEventCreate(&ctx->ev1));
+    somatic_init_tables(ctx);
+  });
+  if (s != GUAC_OK) {
+    guac_ctx_destroy(ctx);
+    return s;
+  }
+  *out = ctx;
+  return GUAC_OK;
+}
+
+void guac_ctx_destroy(guac_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->d_err) cudaFree(ctx->d_err);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->d_phred) cudaFree(ctx->d_phred);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* guac_last_error(const guac_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
+
+guac_status guac_reads_pack(guac_ctx* ctx, const guac_read_batch* batch, const guac_reference* ref, guac_reads** out) {
+  if (!ctx || !out) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    std::unique_ptr<guac_reads> r(new guac_reads());
+    pack_reads(ctx, batch, ref, *r);
+    *out = r.release();
+  });
+}
+
+void guac_reads_free(guac_reads* reads) {
+  if (!reads) return;
+  if (reads->ctx) cudaSetDevice(reads->ctx->device);
+  delete reads;
+}
+uint64_t guac_reads_count(const guac_reads* reads) { return reads ? reads->n : 0; }
+uint64_t guac_reads_device_bytes(const guac_reads* reads) { return reads ? reads->device_bytes() : 0; }
+uint64_t guac_reads_order_sensitive_loci(const guac_reads* reads) { return reads ? reads->order_sensitive_loci : 0; }
+double guac_reads_pack_kernel_ms(const guac_reads* reads) { return reads ? reads->pack_kernel_ms : 0.0; }
+
+guac_status guac_germline_threshold(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges, size_t n_ranges,
+                                    const guac_threshold_params* params, guac_result** out) {
+  if (!ctx || !reads || !params || !out || (n_ranges && !ranges)) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    std::unique_ptr<guac_result> res(new guac_result());
+    res->kind = 0;
+    CallParams prm{0, params->threshold_percent, params->emit_ref, params->emit_no_call, params->skip_empty, reads->sample};
+    run_pileup(ctx, *reads, ranges, n_ranges, prm, *res);
+    *out = res.release();
+  });
+}
+
+guac_status guac_pileup_counts(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges, size_t n_ranges,
+                               int skip_empty, guac_result** out) {
+  if (!ctx || !reads || !out || (n_ranges && !ranges)) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    std::unique_ptr<guac_result> res(new guac_result());
+    res->kind = 2;
+    CallParams prm{1, 0, 0, 0, skip_empty, reads->sample};
+    run_pileup(ctx, *reads, ranges, n_ranges, prm, *res);
+    *out = res.release();
+  });
+}
+
+guac_status guac_somatic_standard(guac_ctx* ctx, const guac_reads* tumor, const guac_reads* normal, const guac_locus_range* ranges,
+                                  size_t n_ranges, const guac_somatic_params* params, guac_result** out) {
+  if (!ctx || !tumor || !normal || !params || !out || (n_ranges && !ranges)) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    std::unique_ptr<guac_result> res(new guac_result());
+    res->kind = 1;
+    run_somatic(ctx, *tumor, *normal, ranges, n_ranges, *params, *res);
+    *out = res.release();
+  });
+}
+
+size_t guac_result_n(const guac_result* r) {
+  if (!r) return 0;
+  return r->kind == 0 ? r->threshold.size() : r->kind == 1 ? r->somatic.size() : r->counts.size();
+}
+const guac_threshold_record* guac_result_threshold_records(const guac_result* r) { return (r && r->kind == 0) ? r->threshold.data() : nullptr; }
+const guac_somatic_record* guac_result_somatic_records(const guac_result* r) { return (r && r->kind == 1) ? r->somatic.data() : nullptr; }
+const guac_locus_counts* guac_result_counts(const guac_result* r) { return (r && r->kind == 2) ? r->counts.data() : nullptr; }
+const uint8_t* guac_result_bytes(const guac_result* r, size_t* n_bytes) {
+  if (n_bytes) *n_bytes = r ? r->bytes.size() : 0;
+  return r ? r->bytes.data() : nullptr;
+}
+const guac_stats* guac_result_stats(const guac_result* r) { return r ? &r->stats : nullptr; }
+void guac_result_free(guac_result* r) { delete r; }
+
+// partitionLociUniformly (DistributedUtil.scala:83-108): host-side LociPartitioning
+guac_status guac_partition_loci_uniformly(int64_t tasks, const guac_locus_range* loci, size_t n_loci, guac_locus_range* out,
+                                          size_t max_out, size_t* n_out) {
+  if (tasks < 1 || (!loci && n_loci) || !n_out) return GUAC_ERR_INVALID_ARGUMENT;
+  int64_t count = 0;
+  for (size_t i = 0; i < n_loci; ++i) count += loci[i].end - loci[i].start;
+  const double per_task = std::max(1.0, (double)count / (double)tasks);
+  int64_t assigned = 0, task = 0;
+  auto remaining = [&] { return (int64_t)std::floor((double)(task + 1) * per_task - (double)assigned + 0.5); };  // math.round
+  size_t n = 0;
+  guac_locus_range last{};
+  bool have_last = false;
+  auto flush = [&] {
+    if (have_last) {
+      if (n < max_out && out) out[n] = last;
+      ++n;
+    }
+  };
+  for (size_t i = 0; i < n_loci; ++i) {
+    int64_t start = loci[i].start;
+    const int64_t end = loci[i].end;
+    while (start < end) {
+      const int64_t length = std::min(remaining(), end - start);
+      if (length <= 0) return GUAC_ERR_INVALID_ARGUMENT;
+      if (have_last && last.contig == loci[i].contig && last.task == (int32_t)task && last.end == start) {
+        last.end = start + length;
+      } else {
+        flush();
+        last = guac_locus_range{loci[i].contig, (int32_t)task, start, start + length};
+        have_last = true;
+      }
+      start += length;
+      assigned += length;
+      if (remaining() == 0) ++task;
+    }
+  }
+  flush();
+  *n_out = n;
+  return n > max_out && out ? GUAC_ERR_INVALID_ARGUMENT : GUAC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+// guac_device.cuh — device-side data layout and helpers of the B200 pileup-and-call engine (sm_100a only).
+//
+// Layout in HBM (one guac_reads object = one sample's start-sorted reads):
+//   rec[n+1]      16 B/read   {start, end, pair_off, info}   contig-relative 0-based [start, end)   (MappedRead.start/end)
+//   pairs[]       8 B/32 bases  bit-plane pairs (lo, hi) of the 2-bit read bases, read coordinates, 32 bases per pair
+//   xmask[]       4 B/32 bases  1 = base is not A/C/G/T (read only for reads flagged HAS_EXC)
+//   cig_off/cigar BAM-encoded run-length CIGAR ops (read only for reads that are not SIMPLE)
+//   seq/qual      raw bytes (qual feeds the likelihood kernels; seq only the exact per-locus path)
+//   md_off/md     upper-cased MD strings (deleted bases for the exact per-locus path)
+//   trk_lo/hi/std reference track per contig as three bit-planes, 32 loci per word (MD- or FASTA-derived)
+//   gran_first/last per 1024-loci granule: the range of read indices that can overlap it
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/guac.h"
+
+namespace guac {
+
+constexpr int kGranuleShift = 10;               // 1024 loci per granule
+constexpr int kGranuleLoci = 1 << kGranuleShift;
+constexpr int kTileWords = 128;                 // one CTA = 128 threads = 128 words = 4096 loci
+constexpr int kTileLoci = kTileWords * 32;
+constexpr int kChunkReads = 512;                // reads staged per chunk
+constexpr int kChunkPairs = 4096;               // plane pairs staged per chunk (32 KB)
+constexpr int kMaxReadLen = 65535;
+
+// ReadRec.info bits
+constexpr uint32_t kInfoLeadMask = 0xFFFFu;     // SIMPLE reads: read bases skipped before the aligned segment
+constexpr uint32_t kInfoSimple = 1u << 16;      // one M/=/X segment plus S/H clips only
+constexpr uint32_t kInfoHasExc = 1u << 17;      // read holds a non-ACGT base
+constexpr uint32_t kInfoPositive = 1u << 18;    // isPositiveStrand
+constexpr uint32_t kInfoEmpty = 1u << 19;       // consumes no reference (overlaps nothing)
+constexpr int kInfoMapqShift = 24;
+
+struct __align__(16) ReadRec {
+  int32_t start;
+  int32_t end;
+  uint32_t pair_off;
+  uint32_t info;
+};
+
+struct ContigInfo {
+  uint64_t read_begin, read_end;  // global read index range
+  uint32_t word_off;              // into trk_* (words)
+  uint32_t gran_off;              // into gran_*
+  int32_t length;                 // loci covered by the track
+  int32_t n_words;
+  int32_t n_grans;
+  int32_t pad_;
+};
+
+struct DevReads {
+  uint64_t n;
+  const ReadRec* rec;
+  const uint32_t* cig_off;
+  const uint32_t* cigar;
+  const uint2* pairs;
+  const uint32_t* xmask;
+  const uint64_t* seq_off;
+  const uint8_t* seq;
+  const uint8_t* qual;
+  const uint32_t* md_off;
+  const char* md;
+  const uint16_t* nm;
+  const ContigInfo* contigs;
+  const uint32_t* trk_lo;
+  const uint32_t* trk_hi;
+  const uint32_t* trk_std;
+  const uint8_t* fasta;       // optional raw reference bytes (FASTA mode), else nullptr
+  const uint64_t* fasta_off;
+  const uint32_t* gran_first;
+  const uint32_t* gran_last;
+};
+
+struct DevError {
+  int code;
+  int pad;
+  unsigned long long where;
+};
+
+__device__ __forceinline__ void report_error(DevError* e, int code, unsigned long long where) {
+  if (atomicCAS(&e->code, 0, code) == 0) e->where = where;
+}
+
+__device__ __forceinline__ bool op_consumes_read(uint32_t op) {
+  return op == GUAC_CIGAR_M || op == GUAC_CIGAR_I || op == GUAC_CIGAR_S || op == GUAC_CIGAR_EQ || op == GUAC_CIGAR_X;
+}
+__device__ __forceinline__ bool op_consumes_ref(uint32_t op) {
+  return op == GUAC_CIGAR_M || op == GUAC_CIGAR_D || op == GUAC_CIGAR_N || op == GUAC_CIGAR_EQ || op == GUAC_CIGAR_X;
+}
+__device__ __forceinline__ bool op_is_match_like(uint32_t op) {
+  return op == GUAC_CIGAR_M || op == GUAC_CIGAR_EQ || op == GUAC_CIGAR_X;
+}
+__device__ __forceinline__ bool is_std_base(uint8_t b) { return b == 'A' || b == 'C' || b == 'G' || b == 'T'; }
+// A=0 C=1 G=2 T=3 (lo = bit 0, hi = bit 1)
+__device__ __forceinline__ uint32_t base_code(uint8_t b) { return b == 'C' ? 1u : b == 'G' ? 2u : b == 'T' ? 3u : 0u; }
+__device__ __forceinline__ uint8_t code_base(uint32_t c) { return (uint8_t)("ACGT"[c & 3]); }
+
+// mask of bits b in [lo_b, hi_b) of a 32-bit word, 0 <= lo_b, hi_b <= 32
+__device__ __forceinline__ uint32_t bit_range(int lo_b, int hi_b) {
+  if (hi_b <= lo_b) return 0u;
+  uint32_t hi_m = hi_b >= 32 ? 0xFFFFFFFFu : ((1u << hi_b) - 1u);
+  uint32_t lo_m = lo_b <= 0 ? 0xFFFFFFFFu : (lo_b >= 32 ? 0u : (0xFFFFFFFFu << lo_b));
+  return hi_m & lo_m;
+}
+
+// 32 bits of a read's bit-plane starting at (possibly negative, > -32) base index q0.  `get(j)` returns word j (j >= 0).
+template <typename Get>
+__device__ __forceinline__ uint32_t plane_window(Get get, int q0) {
+  int j = q0 >> 5;  // arithmetic shift: floor
+  int sh = q0 & 31;
+  uint32_t a = j >= 0 ? get(j) : 0u;
+  uint32_t b = get(j + 1);
+  return __funnelshift_r(a, b, sh);
+}
+
+// ---- MD walk shared by the track builder, its verifier and the exact per-locus path ------------------------------
+// Visits the alignment of one read in reference order, driven by the CIGAR with the MD tag consumed alongside
+// (ADAM MdTag semantics, restated in oracle/guac_oracle.cpp Read::parse_md).  The visitor gets
+//   run(ref_pos, read_pos, k)        k aligned bases where MD says "match"  (reference base == read base)
+//   mismatch(ref_pos, read_pos, ch)  MD mismatch: reference base ch
+//   deleted(ref_pos, ch)             reference base ch inside a D op
+//   skipped(ref_pos, len)            N op
+// and returns false from any callback to stop early.  Returns 0 or a guac_status.
+template <typename V>
+__device__ int md_walk(const DevReads& R, uint64_t r, V& v) {
+  const ReadRec rec = R.rec[r];
+  const uint32_t c0 = R.cig_off[r], c1 = R.cig_off[r + 1];
+  const char* md = R.md + R.md_off[r];
+  const int md_len = (int)(R.md_off[r + 1] - R.md_off[r]);
+  int pos = 0;
+  int64_t pending = 0;
+  int ref_pos = rec.start, read_pos = 0;
+  bool trivial = (md_len == 1 && md[0] == '0') || md_len == 0;  // MdTag: null or "0" -> empty tag
+  if (!trivial && !(md[0] >= '0' && md[0] <= '9')) return GUAC_ERR_MISSING_MD;
+  for (uint32_t c = c0; c < c1; ++c) {
+    const uint32_t op = R.cigar[c] & 0xF;
+    int len = (int)(R.cigar[c] >> 4);
+    if (op_is_match_like(op)) {
+      int remaining = len;
+      if (trivial) {  // no mismatches known: everything matches
+        if (!v.run(ref_pos, read_pos, remaining)) return 0;
+        ref_pos += remaining;
+        read_pos += remaining;
+        continue;
+      }
+      while (remaining > 0) {
+        if (pending > 0) {
+          int k = (int)(pending < remaining ? pending : remaining);
+          if (!v.run(ref_pos, read_pos, k)) return 0;
+          ref_pos += k;
+          read_pos += k;
+          remaining -= k;
+          pending -= k;
+        } else if (pos >= md_len) {
+          return GUAC_ERR_MISSING_MD;
+        } else {
+          char ch = md[pos];
+          if (ch >= '0' && ch <= '9') {
+            int64_t n = 0;
+            while (pos < md_len && md[pos] >= '0' && md[pos] <= '9') n = n * 10 + (md[pos++] - '0');
+            pending = n;
+          } else if (ch == '^') {
+            return GUAC_ERR_MISSING_MD;
+          } else {
+            ++pos;
+            if (!v.mismatch(ref_pos, read_pos, (uint8_t)ch)) return 0;
+            ++ref_pos;
+            ++read_pos;
+            --remaining;
+          }
+        }
+      }
+    } else if (op == GUAC_CIGAR_D) {
+      int remaining = len;
+      if (trivial) return GUAC_ERR_MISSING_MD;
+      while (remaining > 0) {
+        if (pending > 0) return GUAC_ERR_MISSING_MD;  // "found matching bases in deletion"
+        if (pos >= md_len) return GUAC_ERR_MISSING_MD;
+        char ch = md[pos];
+        if (ch >= '0' && ch <= '9') {
+          int64_t n = 0;
+          while (pos < md_len && md[pos] >= '0' && md[pos] <= '9') n = n * 10 + (md[pos++] - '0');
+          pending = n;
+        } else if (ch == '^') {
+          ++pos;
+        } else {
+          ++pos;
+          if (!v.deleted(ref_pos, (uint8_t)ch)) return 0;
+          ++ref_pos;
+          --remaining;
+        }
+      }
+    } else if (op == GUAC_CIGAR_N) {
+      if (!v.skipped(ref_pos, len)) return 0;
+      ref_pos += len;
+    } else if (op == GUAC_CIGAR_I || op == GUAC_CIGAR_S) {
+      read_pos += len;
+    }
+  }
+  return 0;
+}
+
+}  // namespace guac

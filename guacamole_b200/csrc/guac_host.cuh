@@ -1,0 +1,175 @@
+// guac_host.cuh — host-side state shared by the C-ABI translation unit: context, device buffers, packed read store,
+// results.  (Internal; the public contract is include/guac.h.)
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "guac_device.cuh"
+
+using namespace guac;
+
+// ---- context / errors ---------------------------------------------------------------------------------------------------
+struct guac_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  DevError* d_err = nullptr;
+  unsigned long long* d_counters = nullptr;  // 16 counters
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 148;
+  double* d_phred = nullptr;  // [256] success probabilities, [256..512) their logs ... (somatic tables)
+};
+
+namespace {
+
+struct StatusError {
+  guac_status code;
+  std::string msg;
+};
+
+[[noreturn]] void fail(guac_status code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw StatusError{code, buf};
+}
+
+#define CUDA_OK(expr)                                                                                          \
+  do {                                                                                                         \
+    cudaError_t e_ = (expr);                                                                                   \
+    if (e_ != cudaSuccess)                                                                                     \
+      fail(e_ == cudaErrorMemoryAllocation ? GUAC_ERR_OOM : GUAC_ERR_CUDA, "%s: %s (%s:%d)", #expr,            \
+           cudaGetErrorString(e_), __FILE__, __LINE__);                                                        \
+  } while (0)
+
+template <typename F>
+guac_status guarded(guac_ctx* ctx, F&& f) {
+  try {
+    f();
+    return GUAC_OK;
+  } catch (const StatusError& e) {
+    if (ctx) ctx->last_error = e.msg;
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    if (ctx) ctx->last_error = "host allocation failed";
+    return GUAC_ERR_OOM;
+  }
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    CUDA_OK(cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+void check_device_error(guac_ctx* ctx, const char* what) {
+  DevError e;
+  CUDA_OK(cudaMemcpyAsync(&e, ctx->d_err, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (e.code) {
+    CUDA_OK(cudaMemsetAsync(ctx->d_err, 0, sizeof(DevError), ctx->stream));
+    fail((guac_status)e.code, "%s: %s at read/locus %llu", what, guac_status_string((guac_status)e.code), e.where);
+  }
+}
+
+template <typename T>
+void h2d(guac_ctx* ctx, DevBuf<T>& dst, const T* src, size_t n, size_t extra = 0) {
+  dst.alloc(n + extra);
+  if (extra) CUDA_OK(cudaMemsetAsync(dst.p + n, 0, extra * sizeof(T), ctx->stream));
+  if (n) CUDA_OK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+}
+
+int grid_for(uint64_t n, int block, int sm_count) {
+  uint64_t g = (n + block - 1) / block;
+  uint64_t cap = (uint64_t)sm_count * 32;
+  return (int)std::max<uint64_t>(1, std::min(g, cap));
+}
+
+}  // namespace
+
+// ---- packed read store ---------------------------------------------------------------------------------------------------
+struct guac_reads {
+  guac_ctx* ctx = nullptr;
+  uint64_t n = 0;
+  uint32_t n_contigs = 0;
+  int32_t sample = 0;
+  std::vector<ContigInfo> contigs;
+  DevBuf<ReadRec> rec;
+  DevBuf<uint32_t> cig_off, cigar, xmask, md_off, trk_lo, trk_hi, trk_std, gran_first, gran_last;
+  DevBuf<uint2> pairs;
+  DevBuf<uint64_t> seq_off, fasta_off;
+  DevBuf<uint8_t> seq, qual, fasta;
+  DevBuf<char> md;
+  DevBuf<uint16_t> nm;
+  DevBuf<ContigInfo> d_contigs;
+  uint64_t order_sensitive_loci = 0;
+  uint64_t max_reads_per_granule = 0;
+  uint64_t total_words = 0, total_grans = 0;
+  double pack_kernel_ms = 0;
+  int pack_launches = 0;
+
+  DevReads view() const {
+    DevReads R;
+    R.n = n;
+    R.rec = rec.p;
+    R.cig_off = cig_off.p;
+    R.cigar = cigar.p;
+    R.pairs = pairs.p;
+    R.xmask = xmask.p;
+    R.seq_off = seq_off.p;
+    R.seq = seq.p;
+    R.qual = qual.p;
+    R.md_off = md_off.p;
+    R.md = md.p;
+    R.nm = nm.p;
+    R.contigs = d_contigs.p;
+    R.trk_lo = trk_lo.p;
+    R.trk_hi = trk_hi.p;
+    R.trk_std = trk_std.p;
+    R.fasta = fasta.n ? fasta.p : nullptr;
+    R.fasta_off = fasta.n ? fasta_off.p : nullptr;
+    R.gran_first = gran_first.p;
+    R.gran_last = gran_last.p;
+    return R;
+  }
+  uint64_t device_bytes() const {
+    return rec.bytes() + cig_off.bytes() + cigar.bytes() + xmask.bytes() + md_off.bytes() + trk_lo.bytes() * 3 +
+           gran_first.bytes() * 2 + pairs.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + md.bytes() + nm.bytes() +
+           fasta.bytes();
+  }
+};
+
+struct guac_result {
+  int kind = 0;  // 0 threshold, 1 somatic, 2 counts
+  std::vector<guac_threshold_record> threshold;
+  std::vector<guac_somatic_record> somatic;
+  std::vector<guac_locus_counts> counts;
+  std::vector<uint8_t> bytes;
+  guac_stats stats{};
+};
+

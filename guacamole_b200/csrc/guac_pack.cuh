@@ -1,0 +1,271 @@
+// guac_pack.cuh — device side of guac_reads_pack: raw host columns (already copied to HBM) -> the packed read store.
+//
+// Replaces, for the hot path, the lazy per-read work the reference does on the JVM:
+//   MDTagUtils.getReference / MappedRead.mdTagReferenceBases   (reads/MDTagUtils.scala:23-78, reads/MappedRead.scala:57-76)
+//   Pileup.referenceBaseAtLocus                                 (pileup/Pileup.scala:157-165)
+//   windowTaskFlatMapMultipleRDDs' read -> task expansion       (DistributedUtil.scala:585-597) -> granule index
+#pragma once
+
+#include "guac_device.cuh"
+
+namespace guac {
+
+struct PackArgs {
+  DevReads R;            // const view
+  ReadRec* rec_w;        // writable aliases
+  uint2* pairs_w;
+  uint32_t* xmask_w;
+  uint16_t* nm_w;
+  char* md_w;
+  uint32_t* trk_lo_w;
+  uint32_t* trk_hi_w;
+  uint32_t* trk_std_w;
+  uint32_t* conflict_w;  // per track word: loci where reads' MD-derived reference bases disagree
+  uint32_t* gran_first_w;
+  uint32_t* gran_last_w;
+  uint32_t* gran_count_w;
+  const uint32_t* read_contig;  // [n] contig index per read (scratch)
+  DevError* err;
+  unsigned long long* counters;  // [0] order-sensitive loci resolved, [1] max reads per granule
+};
+
+// ---- K_pack_bases: warp per read; ASCII bases -> (lo, hi) bit-plane pairs + non-ACGT mask -------------------------
+__global__ void __launch_bounds__(256) k_pack_bases(PackArgs A) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t r = warp; r < A.R.n; r += n_warps) {
+    const uint64_t s0 = A.R.seq_off[r], s1 = A.R.seq_off[r + 1];
+    const int len = (int)(s1 - s0);
+    const uint32_t p0 = A.R.rec[r].pair_off;
+    uint32_t any_exc = 0;
+    bool bad_q = false;
+    for (int base = 0; base < len; base += 32) {
+      int i = base + lane;
+      uint8_t b = i < len ? A.R.seq[s0 + i] : (uint8_t)'A';
+      if (i < len && A.R.qual[s0 + i] > 127) bad_q = true;
+      uint32_t code = base_code(b);
+      bool exc = i < len && !is_std_base(b);
+      uint32_t lo = __ballot_sync(0xFFFFFFFFu, (code & 1u) && !exc);
+      uint32_t hi = __ballot_sync(0xFFFFFFFFu, (code & 2u) && !exc);
+      uint32_t x = __ballot_sync(0xFFFFFFFFu, exc);
+      any_exc |= x;
+      if (lane == 0) {
+        A.pairs_w[p0 + (base >> 5)] = make_uint2(lo, hi);
+        A.xmask_w[p0 + (base >> 5)] = x;
+      }
+    }
+    if (__any_sync(0xFFFFFFFFu, bad_q) && lane == 0) report_error(A.err, GUAC_ERR_BAD_QUALITY, r);
+    if (lane == 0 && any_exc) A.rec_w[r].info |= kInfoHasExc;
+    // upper-case the MD tag in place (ADAM MdTag upper-cases before parsing)
+    const uint32_t m0 = A.R.md_off[r], m1 = A.R.md_off[r + 1];
+    for (uint32_t i = m0 + lane; i < m1; i += 32) {
+      char c = A.md_w[i];
+      if (c >= 'a' && c <= 'z') A.md_w[i] = (char)(c - 32);
+    }
+  }
+}
+
+// ---- K_granule_index: thread per read; which reads can overlap each 1024-loci granule ---------------------------------
+__global__ void __launch_bounds__(256) k_granule_index(PackArgs A) {
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < A.R.n; r += (uint64_t)gridDim.x * blockDim.x) {
+    const ReadRec rec = A.R.rec[r];
+    if (rec.end <= rec.start) continue;
+    const ContigInfo ci = A.R.contigs[A.read_contig[r]];
+    int g0 = rec.start >> kGranuleShift, g1 = (rec.end - 1) >> kGranuleShift;
+    for (int g = g0; g <= g1; ++g) {
+      atomicMin(&A.gran_first_w[ci.gran_off + g], (uint32_t)r);
+      atomicMax(&A.gran_last_w[ci.gran_off + g], (uint32_t)r + 1u);
+      atomicAdd(&A.gran_count_w[ci.gran_off + g], 1u);
+    }
+  }
+}
+
+__global__ void k_granule_max(PackArgs A, uint32_t n_grans) {
+  uint32_t m = 0;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_grans; g += gridDim.x * blockDim.x) m = max(m, A.gran_count_w[g]);
+  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(&A.counters[1], (unsigned long long)m);
+}
+
+// ---- K_md_track: thread per read; MD-derived reference bases -> the per-contig reference track ---------------------------
+// MODE 0 builds (OR-merge, exact when all reads agree), MODE 1 verifies and marks the loci where they do not.
+template <int MODE>
+struct TrackVisitor {
+  const PackArgs& A;
+  const ContigInfo& ci;
+  uint64_t r;
+  uint32_t pair_off;
+  int n_mismatch = 0;
+  __device__ TrackVisitor(const PackArgs& a, const ContigInfo& c, uint64_t read, uint32_t po) : A(a), ci(c), r(read), pair_off(po) {}
+
+  __device__ __forceinline__ void put_base(int ref_pos, uint8_t ch) {
+    if (ref_pos < 0 || ref_pos >= ci.length || !is_std_base(ch)) return;
+    const uint32_t w = ci.word_off + (uint32_t)(ref_pos >> 5), bit = 1u << (ref_pos & 31);
+    const uint32_t code = base_code(ch);
+    if (MODE == 0) {
+      if ((code & 1u) && !(A.trk_lo_w[w] & bit)) atomicOr(&A.trk_lo_w[w], bit);
+      if ((code & 2u) && !(A.trk_hi_w[w] & bit)) atomicOr(&A.trk_hi_w[w], bit);
+      if (!(A.trk_std_w[w] & bit)) atomicOr(&A.trk_std_w[w], bit);
+    } else {
+      uint32_t lo = (A.trk_lo_w[w] & bit) ? 1u : 0u, hi = (A.trk_hi_w[w] & bit) ? 2u : 0u;
+      if ((lo | hi) != code) atomicOr(&A.conflict_w[w], bit);
+    }
+  }
+  __device__ bool run(int ref_pos, int read_pos, int k) {
+    // k aligned bases whose reference base equals the read base: word-parallel merge of the read's planes
+    const uint2* P = A.R.pairs + pair_off;
+    const uint32_t* X = A.R.xmask + pair_off;
+    int w0 = ref_pos >> 5, w1 = (ref_pos + k - 1) >> 5;
+    for (int w = w0; w <= w1; ++w) {
+      if (w < 0 || w >= ci.n_words) continue;
+      int wbase = w << 5;
+      int q0 = read_pos + (wbase - ref_pos);
+      uint32_t valid = bit_range(ref_pos - wbase, ref_pos + k - wbase);
+      uint32_t lo = plane_window([&](int j) { return P[j].x; }, q0);
+      uint32_t hi = plane_window([&](int j) { return P[j].y; }, q0);
+      uint32_t x = plane_window([&](int j) { return X[j]; }, q0);
+      uint32_t bits = valid & ~x;
+      if (wbase + 32 > ci.length) bits &= bit_range(0, ci.length - wbase);
+      lo &= bits;
+      hi &= bits;
+      const uint32_t gw = ci.word_off + (uint32_t)w;
+      if (MODE == 0) {
+        if ((A.trk_lo_w[gw] & lo) != lo) atomicOr(&A.trk_lo_w[gw], lo);
+        if ((A.trk_hi_w[gw] & hi) != hi) atomicOr(&A.trk_hi_w[gw], hi);
+        if ((A.trk_std_w[gw] & bits) != bits) atomicOr(&A.trk_std_w[gw], bits);
+      } else {
+        uint32_t diff = bits & ((lo ^ A.trk_lo_w[gw]) | (hi ^ A.trk_hi_w[gw]));
+        if (diff) atomicOr(&A.conflict_w[gw], diff);
+      }
+    }
+    return true;
+  }
+  __device__ bool mismatch(int ref_pos, int, uint8_t ch) {
+    ++n_mismatch;
+    put_base(ref_pos, ch);
+    return true;
+  }
+  __device__ bool deleted(int ref_pos, uint8_t ch) {
+    put_base(ref_pos, ch);
+    return true;
+  }
+  __device__ bool skipped(int, int) { return true; }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_md_track(PackArgs A) {
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < A.R.n; r += (uint64_t)gridDim.x * blockDim.x) {
+    const ContigInfo ci = A.R.contigs[A.read_contig[r]];
+    TrackVisitor<MODE> v(A, ci, r, A.R.rec[r].pair_off);
+    int rc = md_walk(A.R, r, v);
+    if (rc) report_error(A.err, rc, r);
+    if (MODE == 0) A.nm_w[r] = (uint16_t)min(v.n_mismatch, 65535);
+  }
+}
+
+// MD-derived reference base of one read at one locus (MappedRead.getReferenceBaseAtLocus); 0 if the read has none there
+struct BaseAtVisitor {
+  const DevReads& R;
+  uint64_t r;
+  int locus;
+  uint8_t out = 0;
+  __device__ BaseAtVisitor(const DevReads& rr, uint64_t read, int l) : R(rr), r(read), locus(l) {}
+  __device__ bool run(int ref_pos, int read_pos, int k) {
+    if (locus >= ref_pos && locus < ref_pos + k) {
+      out = R.seq[R.seq_off[r] + read_pos + (locus - ref_pos)];
+      return false;
+    }
+    return locus >= ref_pos + k;
+  }
+  __device__ bool mismatch(int ref_pos, int, uint8_t ch) {
+    if (ref_pos == locus) {
+      out = ch;
+      return false;
+    }
+    return locus > ref_pos;
+  }
+  __device__ bool deleted(int ref_pos, uint8_t ch) {
+    if (ref_pos == locus) {
+      out = ch;
+      return false;
+    }
+    return locus > ref_pos;
+  }
+  __device__ bool skipped(int ref_pos, int len) {
+    if (locus >= ref_pos && locus < ref_pos + len) {
+      out = 'N';
+      return false;
+    }
+    return locus >= ref_pos + len;
+  }
+};
+
+// ---- K_resolve_conflicts: thread per track word.  Canonical rule for loci where the reads' MD tags disagree (SURVEY
+// H1a): the standard base given by the overlapping read with the smallest end, earliest read on ties — what
+// Pileup.referenceBaseAtLocus sees first in the sliding window's heap order on a single-task run. ---------------------
+__global__ void __launch_bounds__(128) k_resolve_conflicts(PackArgs A, uint32_t n_contigs) {
+  for (uint32_t c = 0; c < n_contigs; ++c) {
+    const ContigInfo ci = A.R.contigs[c];
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < ci.n_words; w += gridDim.x * blockDim.x) {
+      uint32_t conf = A.conflict_w[ci.word_off + w];
+      if (!conf) continue;
+      uint32_t lo = A.trk_lo_w[ci.word_off + w], hi = A.trk_hi_w[ci.word_off + w];
+      while (conf) {
+        int b = __ffs(conf) - 1;
+        conf &= conf - 1;
+        int locus = (w << 5) + b;
+        int g = locus >> kGranuleShift;
+        uint32_t first = A.gran_first_w[ci.gran_off + g], last = A.gran_last_w[ci.gran_off + g];
+        int best_end = 0x7FFFFFFF;
+        uint8_t best = 0;
+        for (uint32_t r = first; r < last && first != 0xFFFFFFFFu; ++r) {
+          const ReadRec rec = A.R.rec[r];
+          if (rec.start > locus || rec.end <= locus || rec.end >= best_end) continue;
+          BaseAtVisitor v(A.R, r, locus);
+          md_walk(A.R, r, v);
+          if (is_std_base(v.out)) {
+            best_end = rec.end;
+            best = v.out;
+          }
+        }
+        if (best) {
+          uint32_t code = base_code(best), bit = 1u << b;
+          lo = (lo & ~bit) | ((code & 1u) ? bit : 0u);
+          hi = (hi & ~bit) | ((code & 2u) ? bit : 0u);
+        }
+        atomicAdd(&A.counters[0], 1ull);
+      }
+      A.trk_lo_w[ci.word_off + w] = lo;
+      A.trk_hi_w[ci.word_off + w] = hi;
+    }
+  }
+}
+
+// ---- K_fasta_track: FASTA mode (ReferenceGenome.getReferenceBase, DistributedUtil.scala:266): track = given bases ----------
+__global__ void __launch_bounds__(256) k_fasta_track(PackArgs A, uint32_t n_contigs) {
+  for (uint32_t c = 0; c < n_contigs; ++c) {
+    const ContigInfo ci = A.R.contigs[c];
+    const uint8_t* f = A.R.fasta + A.R.fasta_off[c];
+    const int64_t flen = (int64_t)(A.R.fasta_off[c + 1] - A.R.fasta_off[c]);
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < ci.n_words; w += gridDim.x * blockDim.x) {
+      uint32_t lo = 0, hi = 0, st = 0;
+      for (int b = 0; b < 32; ++b) {
+        int64_t x = ((int64_t)w << 5) + b;
+        if (x >= flen || x >= ci.length) break;
+        uint8_t ch = f[x];
+        if (is_std_base(ch)) {
+          uint32_t code = base_code(ch);
+          lo |= (code & 1u) << b;
+          hi |= ((code >> 1) & 1u) << b;
+          st |= 1u << b;
+        }
+      }
+      A.trk_lo_w[ci.word_off + w] = lo;
+      A.trk_hi_w[ci.word_off + w] = hi;
+      A.trk_std_w[ci.word_off + w] = st;
+    }
+  }
+}
+
+}  // namespace guac

@@ -213,6 +213,9 @@ guac_status guac_reads_pack(guac_ctx* ctx, const guac_read_batch* batch, const g
 void guac_reads_free(guac_reads* reads);
 uint64_t guac_reads_count(const guac_reads* reads);
 uint64_t guac_reads_device_bytes(const guac_reads* reads);
+/* loci where the reads' MD-derived reference bases disagreed and the canonical rule chose one */
+uint64_t guac_reads_order_sensitive_loci(const guac_reads* reads);
+double guac_reads_pack_kernel_ms(const guac_reads* reads);   /* device time of the pack kernels (CUDA events) */
 
 /* ---- the hot path ---------------------------------------------------------------------------------------- */
 /* pileupFlatMap(reads, ranges, skip_empty, callVariantsAtLocus(_, threshold, emitRef, emitNoCall)) */

@@ -1,0 +1,184 @@
+"""Parity tests proper (-m gpu): the CUDA engine, called through the C ABI of include/guac.h, against the CPU oracle on
+the same inputs.  Integer outputs (depths, allele counts, called loci, genotypes, allele strings) must be bit-exact."""
+import numpy as np
+import pytest
+
+import oracle_binding as orc
+from conftest import load_golden
+from guacamole_b200 import abi
+from guacamole_b200.reads import ReadBatch, make_read
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from guacamole_b200.callers import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def gpu_threshold(ctx, batch, ranges, **kw):
+    from guacamole_b200 import callers
+    reads = ctx.pack(batch)
+    res = callers.germline_threshold(ctx, reads, ranges, **kw)
+    reads.free()
+    return res
+
+
+def gpu_counts(ctx, batch, ranges, skip_empty=True, reference=None):
+    from guacamole_b200 import callers
+    reads = ctx.pack(batch, reference)
+    res = callers.pileup_counts(ctx, reads, ranges, skip_empty)
+    reads.free()
+    return res
+
+
+def assert_threshold_equal(ctx, batch, ranges, threshold=8, emit_ref=False, emit_no_call=False, skip_empty=True, oracle_ranges=None):
+    want = orc.germline_threshold(batch, oracle_ranges or ranges, orc.threshold_params(threshold, emit_ref, emit_no_call, skip_empty))
+    got = gpu_threshold(ctx, batch, ranges, threshold=threshold, emit_ref=emit_ref, emit_no_call=emit_no_call, skip_empty=skip_empty)
+    w, g = want.threshold(), got.genotypes()
+    assert len(g) == len(w), (len(g), len(w))
+    for a, b in zip(g, w):
+        assert a == b, (a, b)
+    assert got.stats["loci_visited"] == want.stats["loci_visited"]
+    assert got.stats["tie_loci"] == want.stats["tie_loci"]
+    return got
+
+
+def assert_counts_equal(ctx, batch, ranges, skip_empty=True, reference=None):
+    want = orc.pileup_counts(batch, ranges, skip_empty, reference=reference).counts()
+    got = gpu_counts(ctx, batch, ranges, skip_empty, reference).records
+    assert len(got) == len(want)
+    for f in ("locus", "contig", "depth", "positive_depth", "reference_depth", "base_count", "other_count", "reference_base"):
+        assert np.array_equal(got[f], want[f]), f
+    return got
+
+
+UNIT_SETS = {
+    "long_insert": [make_read("TCGATCGA", "8M", "8", 1), make_read("TCGATCGA", "8M", "8", 1), make_read("TCGACCCTCGA", "4M3I4M", "8", 1)],
+    "deletion": [make_read("AATTGAATTG", "5M1D5M", "5^C5", 0), make_read("AATTGCAATTG", "11M", "11", 0, is_positive_strand=False)],
+    "contig_start_insertion": [make_read("AAAAAACGT", "5I4M", "4", 0), make_read("ACGT", "4M", "4", 0)],
+    "mixed_indels": [make_read("TCATCTCAAAAGAGATCGA", "2M2D1M2I2M4I2M2D6M", "2^GA5^TC6", 10)] * 3 + [make_read("TCGAATCGATCGATCGA", "17M", "17", 10)] * 2,
+    "het_snv": [make_read("TCGATCGA", "8M", "8", 1), make_read("TCGATCGA", "8M", "8", 1), make_read("GCGATCGA", "8M", "0T7", 1)],
+    "clips_and_eq": [make_read("GGACGTACGTACGTACGCC", "2S5M4=1X5=2S", "9G5", 10), make_read("ACGTACGTAC", "2H10M3H", "10", 12)],
+    "n_base_in_read": [make_read("ACNTACGT", "8M", "8", 3), make_read("ACGTACGT", "8M", "8", 3), make_read("ACGTACGT", "8M", "2N5", 3)],
+    "rna_skip": [make_read("CCCCAGCCTAGG", "7M5000N5M", "12", 100), make_read("CCCCAGC", "7M", "7", 100)],
+    "x_before_i": [make_read("ACGTTTACGT", "3M1X2I4M", "3C4", 5), make_read("ACGAACGT", "8M", "8", 5)],
+    "deletion_then_mismatch": [make_read("ACGTACGT", "4M2D4M", "4^TT0C3", 20), make_read("ACGTTTCCGT", "10M", "10", 20)],
+}
+
+
+@pytest.mark.parametrize("name", sorted(UNIT_SETS))
+def test_unit_sets(ctx, name):
+    b = ReadBatch.from_records(UNIT_SETS[name]).sorted()
+    ranges = [(0, 0, 6000)]
+    assert_counts_equal(ctx, b, ranges)
+    assert_counts_equal(ctx, b, [(0, 0, 40)], skip_empty=False)
+    for thr in (0, 8, 34, 50):
+        assert_threshold_equal(ctx, b, ranges, threshold=thr)
+    assert_threshold_equal(ctx, b, ranges, threshold=8, emit_ref=True, emit_no_call=True)
+    assert_threshold_equal(ctx, b, ranges, threshold=60, emit_ref=False, emit_no_call=True)
+
+
+def test_germline_suite_vectors(ctx):  # GermlineThresholdCallerSuite.scala:72-85 through the engine
+    hom = ReadBatch.from_records([make_read("TCGATCGA", "8M", "8", 1), make_read("GCGATCGA", "8M", "0T7", 1), make_read("GCGATCGA", "8M", "0T7", 1)])
+    g = gpu_threshold(ctx, hom, [(0, 0, 100)], threshold=50).genotypes()
+    assert [(x["start"], x["ref"], x["alt"], x["gt"]) for x in g] == [(1, "T", "G", (abi.GT_ALT, abi.GT_ALT))]
+
+
+def chrm():
+    return load_golden("chrM.sorted").filtered(non_duplicate=True, has_md=True).sorted()
+
+
+def test_chrm_config1(ctx):  # BASELINE.json configs[0]: germline-threshold on chrM.sorted.bam, loci "all", threshold 8
+    b = chrm()
+    got = assert_threshold_equal(ctx, b, [(0, 0, 16570)])
+    assert len(got) == 138 and got.stats["loci_visited"] == 15904
+    assert_counts_equal(ctx, b, [(0, 0, 16570)])
+    assert_threshold_equal(ctx, b, [(0, 0, 16570)], emit_ref=True, emit_no_call=True)
+    # LociPartitioning: 8 contiguous tasks give the same records as one task (the oracle runs single-task: its own
+    # result at the order-sensitive locus 13854 depends on the task cut)
+    parts = orc.partition_loci_uniformly(8, [(0, 0, 16570)])
+    assert_threshold_equal(ctx, b, parts, oracle_ranges=[(0, 0, 16570)])
+
+
+def test_gatk_bundle_indel_heavy(ctx):
+    g = load_golden("gatk_mini_bundle_extract").filtered(has_md=True, non_duplicate=True).sorted()
+    c = g.contig_names.index("20")
+    ranges = [(c, 9999000, 10271000)]
+    assert_counts_equal(ctx, g, ranges)
+    assert_threshold_equal(ctx, g, ranges, threshold=8)
+    assert_threshold_equal(ctx, g, ranges, threshold=0)
+    assert_threshold_equal(ctx, g, [(c, 10006000, 10010000)], emit_ref=True, emit_no_call=True)
+
+
+def test_somatic_fixture_counts(ctx):
+    for name, contig in (("tumor.chr20.tough", "20"), ("synthetic.challenge.set1.tumor.v2.withMDTags.chr2.complexvar", "2")):
+        b = load_golden(name).filtered(non_duplicate=True, passed_qc=True, has_md=True).sorted()
+        c = b.contig_names.index(contig)
+        ranges = [(c, 0, int(b.end().max()) + 10)]
+        assert_counts_equal(ctx, b, ranges)
+        assert_threshold_equal(ctx, b, ranges)
+
+
+def test_synthetic_shape(ctx):
+    from guacamole_b200 import synth
+    b = synth.generate([("20", 300000)], depth=30, seed=11).to_read_batch()
+    ranges = [(0, 0, 299999)]
+    assert_counts_equal(ctx, b, ranges)
+    got = assert_threshold_equal(ctx, b, ranges)
+    assert len(got) > 100
+    assert_threshold_equal(ctx, b, [(0, 1000, 5000), (0, 70000, 70001), (0, 100000, 200000)])
+
+
+def test_synthetic_multi_contig_and_deep(ctx):
+    from guacamole_b200 import synth
+    b = synth.generate([("1", 60000), ("2", 30000), ("3", 5000)], depth=40, seed=5).to_read_batch()
+    ranges = [(0, 0, 59999), (1, 0, 29999), (2, 0, 4999)]
+    assert_counts_equal(ctx, b, ranges)
+    assert_threshold_equal(ctx, b, ranges)
+    deep = synth.generate([("amp", 3000)], depth=3000, seed=9).to_read_batch()   # > 255 reads deep: 12-plane counters
+    assert_counts_equal(ctx, deep, [(0, 0, 2999)])
+    assert_threshold_equal(ctx, deep, [(0, 0, 2999)])
+
+
+def test_fasta_reference(ctx):
+    b = ReadBatch.from_records([make_read("TCGATCGA", "8M", "8", 1), make_read("TCGATCGA", "8M", "8", 1), make_read("GCGATCGA", "8M", "0T7", 1)])
+    ref = [b"NTCGATCGANNNN"]
+    assert_counts_equal(ctx, b, [(0, 0, 12)], reference=ref)
+    assert_counts_equal(ctx, b, [(0, 0, 12)], skip_empty=False, reference=ref)
+
+
+def test_errors(ctx):
+    from guacamole_b200._lib import GuacError
+    unsorted = ReadBatch.from_records([make_read("TCGATCGA", "8M", "8", 5), make_read("TCGATCGA", "8M", "8", 2)])
+    with pytest.raises(GuacError) as e:
+        ctx.pack(unsorted)
+    assert e.value.code == abi.ERR_UNSORTED_READS
+    no_md = ReadBatch.from_records([make_read("TCGATCGA", "8M", None, 5)])
+    with pytest.raises(GuacError) as e:
+        ctx.pack(no_md)
+    assert e.value.code == abi.ERR_MISSING_MD
+    bad_md = ReadBatch.from_records([make_read("AATTGAATTG", "5M1D5M", "10", 0)])
+    with pytest.raises(GuacError) as e:
+        ctx.pack(bad_md)
+    assert e.value.code == abi.ERR_MISSING_MD
+    bad_cigar = ReadBatch.from_records([make_read("AATTG", "7M", "7", 0)])
+    with pytest.raises(GuacError) as e:
+        ctx.pack(bad_cigar)
+    assert e.value.code == abi.ERR_INVALID_CIGAR
+    contig_order = ReadBatch.from_records([make_read("ACGT", "4M", "4", 1, "a"), make_read("ACGT", "4M", "4", 1, "b"), make_read("ACGT", "4M", "4", 9, "a")])
+    with pytest.raises(GuacError) as e:
+        ctx.pack(contig_order)
+    assert e.value.code == abi.ERR_CONTIG_ORDER
+
+
+def test_empty_inputs(ctx):
+    from guacamole_b200 import callers
+    empty = ReadBatch.from_records([], contig_names=["chr1"], contig_lengths=[1000])
+    reads = ctx.pack(empty)
+    assert len(callers.germline_threshold(ctx, reads, [(0, 0, 1000)])) == 0
+    assert len(callers.pileup_counts(ctx, reads, [(0, 0, 10)], skip_empty=False)) == 10
+    assert len(callers.germline_threshold(ctx, reads, [])) == 0
