@@ -279,7 +279,24 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
   res.stats.reads_total = reads.n;
   res.stats.loci_requested = requested;
   res.stats.order_sensitive_loci = reads.order_sensitive_loci;
-  if (tiles.empty()) return;
+  auto append_rows_past_track = [&] {  // requested loci past the end of the track hold no reads: empty pileups, reference base N
+    if (prm.mode != 1 || prm.skip_empty) return;
+    for (size_t i = 0; i < n_ranges; ++i) {
+      const ContigInfo& ci = reads.contigs[ranges[i].contig];
+      for (int64_t x = std::max<int64_t>(ranges[i].start, ci.length); x < ranges[i].end; ++x) {
+        guac_locus_counts z{};
+        z.locus = x;
+        z.contig = ranges[i].contig;
+        z.reference_base = 'N';
+        res.counts.push_back(z);
+      }
+    }
+  };
+  if (tiles.empty()) {
+    append_rows_past_track();
+    res.stats.loci_visited = res.stats.records = res.counts.size();
+    return;
+  }
   set_all_smem_attrs();
   cudaStream_t st = ctx->stream;
   DevBuf<TileDesc> d_tiles;
@@ -359,6 +376,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       res.counts.resize((size_t)c[0]);
       if (c[0]) CUDA_OK(cudaMemcpyAsync(res.counts.data(), ob.crec.p, c[0] * sizeof(guac_locus_counts), cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
+      append_rows_past_track();
       std::sort(res.counts.begin(), res.counts.end(), [](const guac_locus_counts& a, const guac_locus_counts& b) {
         return std::make_pair(a.contig, a.locus) < std::make_pair(b.contig, b.locus);
       });
@@ -382,9 +400,9 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       }
       res.threshold = std::move(recs);
     }
-    res.stats.loci_visited = c[3];
+    res.stats.loci_visited = c[3] + (prm.mode == 1 ? res.counts.size() - c[0] : 0);
     res.stats.tie_loci = c[4];
-    res.stats.records = c[0];
+    res.stats.records = prm.mode == 1 ? res.counts.size() : c[0];
     res.stats.kernel_ms = total_ms;
     res.stats.kernel_launches = (uint64_t)launches;
     res.stats.reads_relevant = c[2];  // loci decided by the exact per-element kernel (diagnostic)

@@ -100,10 +100,11 @@ __device__ __forceinline__ uint8_t code_base(uint32_t c) { return (uint8_t)("ACG
 
 // mask of bits b in [lo_b, hi_b) of a 32-bit word, 0 <= lo_b, hi_b <= 32
 __device__ __forceinline__ uint32_t bit_range(int lo_b, int hi_b) {
+  lo_b = max(lo_b, 0);
+  hi_b = min(hi_b, 32);
   if (hi_b <= lo_b) return 0u;
   uint32_t hi_m = hi_b >= 32 ? 0xFFFFFFFFu : ((1u << hi_b) - 1u);
-  uint32_t lo_m = lo_b <= 0 ? 0xFFFFFFFFu : (lo_b >= 32 ? 0u : (0xFFFFFFFFu << lo_b));
-  return hi_m & lo_m;
+  return hi_m & (0xFFFFFFFFu << lo_b);
 }
 
 // 32 bits of a read's bit-plane starting at (possibly negative, > -32) base index q0.  `get(j)` returns word j (j >= 0).
