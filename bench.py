@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — pileup+call throughput of the B200 engine on the synthetic shapes of BASELINE.json.
+
+    python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torch.distributed.run, one rank per GPU)
+    python bench.py --impl reference ...                    (the reference algorithm's CPU path: the oracle, all host threads)
+
+A "step" is one pass of the hot path (K_tile + K_exact + record download) over one batch of synthetic reads.  At N = 1 the
+workload is BASELINE.json configs[1]: germline-threshold, chr20 shape (63,025,520 loci), 30x, 150 bp.  At N > 1 every rank
+holds one chr20-shaped contig of an N-contig genome (LociPartitioning assigns contiguous contig ranges to ranks; no
+data-path collective) and rank 0 gathers the variant records over NCCL — weak scaling.
+
+`value` is measured with the packed reads already resident in HBM; `e2e` goes through guac_reads_pack +
+guac_germline_threshold from (pinned) HOST buffers every step, results copied back.  `cpu_baseline` is the oracle (a C++
+restatement of the reference's Scala algorithm — there is no JVM on the box) on a bounded window of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+from guacamole_b200 import abi, synth  # noqa: E402
+
+CHR20 = synth.CHR20_LENGTH
+READ_LEN = 150
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="germline", choices=["germline", "somatic"])
+    ap.add_argument("--contig-length", type=int, default=CHR20)
+    ap.add_argument("--depth", type=float, default=30.0)
+    ap.add_argument("--cpu-window", type=int, default=4_000_000, help="loci of the bounded CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--seed", type=int, default=20261020)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(view, n_loci):
+    """per read start 4 + ref_len 4 + 4*c + ceil(L/4) + 1 flag bytes; per locus 0.25 B of reference."""
+    n = int(view.n_reads)
+    n_ops = int(np.ctypeslib.as_array(view.cigar_off, shape=(n + 1,))[n])
+    bases = int(np.ctypeslib.as_array(view.seq_off, shape=(n + 1,))[n])
+    return n * 9 + 4 * n_ops + (bases + 3) // 4 + 0.25 * n_loci
+
+
+def pinned_copy(view):
+    """Copies the generator's columns into page-locked host memory (torch pinned tensors) and returns a guac_read_batch
+    over them, so that the e2e leg's host->device copies start from pinned memory."""
+    import torch
+    n = int(view.n_reads)
+    so = np.ctypeslib.as_array(view.seq_off, shape=(n + 1,))
+    co = np.ctypeslib.as_array(view.cigar_off, shape=(n + 1,))
+    mo = np.ctypeslib.as_array(view.md_off, shape=(n + 1,))
+    keep = []
+
+    def col(ptr, count, dtype, ctype):
+        count = max(int(count), 1)
+        src = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,))
+        t = torch.empty(count, dtype=dtype, pin_memory=True)
+        t.numpy()[:] = src.view(t.numpy().dtype)
+        keep.append(t)
+        return C.cast(t.data_ptr(), C.POINTER(ctype))
+
+    b = abi.ReadBatchC()
+    b.n_reads, b.n_contigs = view.n_reads, view.n_contigs
+    b.contig_length = col(view.contig_length, view.n_contigs, torch.int64, C.c_int64)
+    b.contig = col(view.contig, n, torch.int32, C.c_int32)
+    b.start = col(view.start, n, torch.int64, C.c_int64)
+    b.cigar_off = C.cast(col(view.cigar_off, n + 1, torch.int64, C.c_int64), C.POINTER(C.c_uint64))
+    b.cigar = C.cast(col(view.cigar, co[n], torch.int32, C.c_int32), C.POINTER(C.c_uint32))
+    b.seq_off = C.cast(col(view.seq_off, n + 1, torch.int64, C.c_int64), C.POINTER(C.c_uint64))
+    b.seq = col(view.seq, so[n], torch.uint8, C.c_uint8)
+    b.qual = col(view.qual, so[n], torch.uint8, C.c_uint8)
+    b.mapq = col(view.mapq, n, torch.uint8, C.c_uint8)
+    b.flags = col(view.flags, n, torch.uint8, C.c_uint8)
+    b.sample = col(view.sample, n, torch.int32, C.c_int32)
+    b.md_off = C.cast(col(view.md_off, n + 1, torch.int64, C.c_int64), C.POINTER(C.c_uint64))
+    # c_char_p fields convert to Python bytes on access: take the raw pointer value from the struct instead
+    md_addr = C.c_void_p.from_address(C.addressof(view) + abi.ReadBatchC.md.offset).value
+    md_pinned = col(C.cast(md_addr, C.POINTER(C.c_uint8)), mo[n], torch.uint8, C.c_uint8)
+    C.c_void_p.from_address(C.addressof(b) + abi.ReadBatchC.md.offset).value = C.cast(md_pinned, C.c_void_p).value
+    return b, keep
+
+
+def cpu_leg(args, steps, warmup, n_threads):
+    """The reference algorithm on host cores: oracle over a bounded window of the same workload, Spark-style loci tasks."""
+    import oracle_binding as orc
+    window = min(args.cpu_window, args.contig_length)
+    sb = synth.generate([("20", args.contig_length)], depth=args.depth, read_length=READ_LEN, seed=args.seed,
+                        window=(0, 0, window))
+    batch_c = sb.c
+    ranges = orc.partition_loci_uniformly(n_threads, [(0, 0, window - READ_LEN - 40)])
+    arr = orc.ranges_array(ranges)
+    prm = orc.threshold_params(8)
+    L = orc.lib()
+    n_loci = sum(r[2] - r[1] for r in ranges)
+    times = []
+    n_rec = 0
+    for i in range(warmup + steps):
+        h = C.c_void_p()
+        t0 = time.perf_counter()
+        rc = L.orc_germline_threshold(C.byref(batch_c), None, arr, C.c_size_t(len(ranges)), C.byref(prm), n_threads, C.byref(h))
+        dt = time.perf_counter() - t0
+        if rc != 0:
+            raise RuntimeError("oracle failed: " + L.orc_last_error().decode())
+        n_rec = L.orc_result_n(h)
+        L.orc_result_free(h)
+        if i >= warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    return {"loci_per_s": n_loci / sec, "reads_per_s": sb.n_reads / sec, "sec_per_step": sec, "loci": n_loci,
+            "reads": sb.n_reads, "records": int(n_rec), "threads": n_threads, "window": window}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_threads = os.cpu_count() or 1
+    config = {"workload": f"{args.workload}-threshold, synthetic chr20 shape ({args.contig_length:,} loci), {args.depth:g}x, "
+                          f"{READ_LEN} bp (BASELINE.json configs[1]) per GPU",
+              "threshold_percent": 8, "loci_per_gpu": args.contig_length, "depth": args.depth, "read_length": READ_LEN,
+              "parallelism": f"loci-partitioned x{world}", "l2": "inputs larger than L2 (no flush needed)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cpu = cpu_leg(args, max(1, args.steps), max(0, min(args.warmup, 1)), n_threads)
+        line = {"impl": "reference", "metric": "loci_per_sec", "value": cpu["loci_per_s"], "unit": "loci/s",
+                "reads_per_sec": cpu["reads_per_s"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": cpu["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": cpu["loci_per_s"], "unit": "loci/s", "cores": cpu["threads"], "kind": "port",
+                                 "sample": f"first {cpu['window']:,} loci of the chr20-shape workload ({cpu['reads']:,} reads); "
+                                           "C++ oracle restating the reference's Scala algorithm (no JVM on the box)"},
+                "e2e": {"value": cpu["loci_per_s"], "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from guacamole_b200 import callers
+    from guacamole_b200._lib import lib
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    L = lib()
+
+    # ---- this rank's shard: one chr20-shaped contig of a `world`-contig genome (LociPartitioning over contigs)
+    contigs = [(f"20_{r}" if world > 1 else "20", args.contig_length) for r in range(world)]
+    from guacamole_b200.loci import partition_loci_uniformly
+    loci_all = [(c, 0, args.contig_length - 1) for c in range(world)]  # LociSet "all" drops the last base of a contig
+    parts = partition_loci_uniformly(world, loci_all)
+    my_ranges = [p for p in parts if p[3] == rank]
+    t_gen = time.perf_counter()
+    sb = synth.generate(contigs, depth=args.depth, read_length=READ_LEN, seed=args.seed,
+                        window=(rank, 0, args.contig_length), n_reads=int(args.depth * args.contig_length / READ_LEN))
+    gen_s = time.perf_counter() - t_gen
+    view = sb.c
+    n_reads = sb.n_reads
+    n_loci = sum(r[2] - r[1] for r in my_ranges)
+    algorithmic = algorithmic_bytes(view, n_loci)
+    view, pinned = pinned_copy(view)
+    sb.free()
+
+    ctx = callers.Context(local_rank)
+    ctx.set_option(abi.OPT_PACK_QUALITIES, 0 if args.workload == "germline" else 1)
+    reads = ctx.pack_c(view, [c[0] for c in contigs])
+    pack_ms = reads.pack_kernel_ms
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return callers.germline_threshold(ctx, reads, my_ranges, threshold=8)
+
+    # ---- device-resident leg
+    ctx.set_option(abi.OPT_SORT_RECORDS, 0)
+    for _ in range(args.warmup):
+        res = step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    tile_ms, exact_ms, launches = 0.0, 0.0, 0
+    for _ in range(args.steps):
+        res = step()
+        tile_ms += res.stats["tile_kernel_ms"]
+        exact_ms += res.stats["exact_kernel_ms"]
+        launches += res.stats["kernel_launches"]
+    dev_ms = ctx.timer_stop()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    n_records = len(res)
+    step_ms = max(dev_ms, 0.0) / args.steps
+
+    # ---- end-to-end leg: host buffers -> pack -> call -> records on the host, every step
+    ctx.set_option(abi.OPT_SORT_RECORDS, 1)
+    e2e_steps = args.e2e_steps or min(args.steps, 5)
+    h2d = d2h = 0
+    for i in range(1 + e2e_steps):
+        if i == 1:
+            barrier()
+            t1 = time.perf_counter()
+        r2 = ctx.pack_c(view, [c[0] for c in contigs])
+        out = callers.germline_threshold(ctx, r2, my_ranges, threshold=8)
+        h2d = int(L.guac_reads_h2d_bytes(r2._h)) + int(out.stats["h2d_bytes"])
+        d2h = int(out.stats["d2h_bytes"])
+        r2.free()
+    barrier()
+    e2e_ms = (time.perf_counter() - t1) * 1e3 / e2e_steps
+    assert len(out) == n_records, "e2e and resident legs disagree"
+
+    # ---- gather per-shard records to rank 0 (the path's only exchange), max-over-ranks timing
+    t = torch.tensor([step_ms, e2e_ms, float(n_records), tile_ms / args.steps, exact_ms / args.steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        rec_bytes = torch.from_numpy(res.records.view(np.uint8).copy()).cuda()
+        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([rec_bytes.numel()], dtype=torch.int64, device="cuda"))
+        cap = int(max(int(s.item()) for s in sizes))
+        padded = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        padded[:rec_bytes.numel()] = rec_bytes
+        gathered = [torch.zeros(cap, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+        dist.gather(padded, gathered, dst=0)
+        step_ms, e2e_ms = float(mx[0]), float(mx[1])
+        total_records = int(sm[2].item())
+        tile_step_ms, exact_step_ms = float(mx[3]), float(mx[4])
+    else:
+        total_records = n_records
+        tile_step_ms, exact_step_ms = tile_ms / args.steps, exact_ms / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    alg_bytes = algorithmic
+    total_loci = n_loci * world
+    total_reads = n_reads * world
+    value = total_loci / (step_ms * 1e-3)
+    e2e_value = total_loci / (e2e_ms * 1e-3)
+    achieved = alg_bytes / (tile_step_ms * 1e-3) / 1e9
+    line = {
+        "metric": "loci_per_sec", "value": value, "unit": "loci/s", "reads_per_sec": total_reads / (step_ms * 1e-3),
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+        "records_per_step": total_records, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "loci/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "pinned_host_buffers": len(pinned)},
+        "roofline": {"bound": "hbm", "kernel": "k_pileup_tile", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tile_step_ms, "exact_kernel_ms": exact_step_ms,
+                     "whole_step_achieved_gbs": alg_bytes / (step_ms * 1e-3) / 1e9},
+        "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps, "pack_kernel_ms": pack_ms, "generate_s": gen_s,
+    }
+    if world == 1:
+        cpu = cpu_leg(args, 1, 0, n_threads)
+        line["cpu_baseline"] = {"value": cpu["loci_per_s"], "unit": "loci/s", "cores": cpu["threads"], "kind": "port",
+                                "sample": f"first {cpu['window']:,} loci of the same workload ({cpu['reads']:,} reads, "
+                                          f"{cpu['sec_per_step']:.1f} s); C++ oracle restating the reference's Scala algorithm"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

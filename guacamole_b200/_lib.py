@@ -13,8 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libguac_b200.so")
 # every symbol include/guac.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTED = [
     "guac_abi_version", "guac_ctx_create", "guac_ctx_destroy", "guac_last_error", "guac_status_string",
+    "guac_ctx_set_option", "guac_ctx_timer_start", "guac_ctx_timer_stop", "guac_host_register", "guac_host_unregister",
     "guac_reads_pack", "guac_reads_free", "guac_reads_count", "guac_reads_device_bytes",
-    "guac_reads_order_sensitive_loci", "guac_reads_pack_kernel_ms",
+    "guac_reads_order_sensitive_loci", "guac_reads_h2d_bytes", "guac_reads_pack_kernel_ms",
     "guac_germline_threshold", "guac_somatic_standard", "guac_pileup_counts",
     "guac_result_n", "guac_result_threshold_records", "guac_result_somatic_records", "guac_result_counts",
     "guac_result_bytes", "guac_result_stats", "guac_result_free", "guac_partition_loci_uniformly",
@@ -44,12 +45,17 @@ def lib():
     L.guac_ctx_destroy.restype = None
     L.guac_last_error.argtypes = [vp]
     L.guac_last_error.restype = C.c_char_p
+    L.guac_ctx_set_option.argtypes = [vp, C.c_int, C.c_int64]
+    L.guac_ctx_timer_start.argtypes = [vp]
+    L.guac_ctx_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
+    L.guac_host_register.argtypes = [vp, C.c_size_t]
+    L.guac_host_unregister.argtypes = [vp]
     L.guac_status_string.argtypes = [C.c_int]
     L.guac_status_string.restype = C.c_char_p
     L.guac_reads_pack.argtypes = [vp, C.POINTER(abi.ReadBatchC), C.POINTER(abi.ReferenceC), C.POINTER(vp)]
     L.guac_reads_free.argtypes = [vp]
     L.guac_reads_free.restype = None
-    for f in ("guac_reads_count", "guac_reads_device_bytes", "guac_reads_order_sensitive_loci"):
+    for f in ("guac_reads_count", "guac_reads_device_bytes", "guac_reads_order_sensitive_loci", "guac_reads_h2d_bytes"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = C.c_uint64
     L.guac_reads_pack_kernel_ms.argtypes = [vp]

@@ -113,7 +113,11 @@ class StatsC(C.Structure):
     _fields_ = [("reads_total", C.c_uint64), ("reads_relevant", C.c_uint64), ("reads_expanded", C.c_uint64),
                 ("loci_requested", C.c_uint64), ("loci_visited", C.c_uint64), ("records", C.c_uint64),
                 ("tie_loci", C.c_uint64), ("order_sensitive_loci", C.c_uint64), ("kernel_ms", C.c_double),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("tile_kernel_ms", C.c_double), ("exact_kernel_ms", C.c_double),
+                ("exact_loci", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+OPT_SORT_RECORDS = 1
+OPT_PACK_QUALITIES = 2
 
 
 def struct_to_dict(s):

@@ -65,6 +65,21 @@ class Context:
         except Exception:
             pass
 
+    def set_option(self, option: int, value: int) -> None:
+        self._check(lib().guac_ctx_set_option(self._h, option, value))
+
+    def timer_start(self) -> None:
+        self._check(lib().guac_ctx_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(lib().guac_ctx_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def pack_c(self, batch_c, contig_names=None, sample_names=None) -> "PackedReads":
+        """Pack straight from a guac_read_batch (e.g. the synthetic generator's buffers) without a numpy copy."""
+        return PackedReads(self, None, None, batch_c=batch_c, contig_names=contig_names, sample_names=sample_names)
+
     def pack(self, batch: ReadBatch, reference: Optional[Sequence[bytes]] = None) -> "PackedReads":
         return PackedReads(self, batch, reference)
 
@@ -72,12 +87,13 @@ class Context:
 class PackedReads:
     """guac_reads: one sample's start-sorted reads packed into the device SoA (guac_reads_pack)."""
 
-    def __init__(self, ctx: Context, batch: ReadBatch, reference: Optional[Sequence[bytes]] = None):
+    def __init__(self, ctx: Context, batch: Optional[ReadBatch], reference: Optional[Sequence[bytes]] = None,
+                 batch_c=None, contig_names=None, sample_names=None):
         self.ctx = ctx
-        self.contig_names = list(batch.contig_names)
-        self.sample_names = list(batch.sample_names)
+        self.contig_names = list(batch.contig_names if batch is not None else (contig_names or []))
+        self.sample_names = list(batch.sample_names if batch is not None else (sample_names or ["default"]))
         self._h = C.c_void_p()
-        b = batch.to_c()
+        b = batch.to_c() if batch is not None else batch_c
         ref = None
         if reference is not None:
             offs = np.zeros(len(reference) + 1, np.uint64)

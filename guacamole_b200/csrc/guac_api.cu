@@ -133,7 +133,8 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   h2d(ctx, out.cigar, b->cigar, (size_t)b->cigar_off[n], 1);
   h2d(ctx, out.seq_off, b->seq_off, n + 1);
   h2d(ctx, out.seq, b->seq, (size_t)b->seq_off[n], 64);
-  h2d(ctx, out.qual, b->qual, (size_t)b->seq_off[n], 64);
+  out.has_qualities = ctx->pack_qualities != 0;
+  if (out.has_qualities) h2d(ctx, out.qual, b->qual, (size_t)b->seq_off[n], 64);
   h2d(ctx, out.md_off, md_off.data(), n + 1);
   h2d(ctx, out.md, b->md, (size_t)b->md_off[n], 16);
   h2d(ctx, out.d_contigs, out.contigs.data(), out.contigs.size());
@@ -163,6 +164,8 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     h2d(ctx, out.fasta, ref->bases, (size_t)ref->base_off[ref->n_contigs], 16);
   }
   CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
+  out.h2d_bytes = out.rec.bytes() + out.cig_off.bytes() * 2 + out.cigar.bytes() + out.seq_off.bytes() + out.seq.bytes() +
+                  out.qual.bytes() + out.md.bytes() + out.d_contigs.bytes() + d_read_contig.bytes() + out.fasta.bytes();
 
   PackArgs A;
   A.R = out.view();
@@ -182,7 +185,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   A.err = ctx->d_err;
   A.counters = ctx->d_counters;
 
-  CUDA_OK(cudaEventRecord(ctx->ev0, st));
+  CUDA_OK(cudaEventRecord(ctx->ev[0], st));
   out.pack_launches = 0;
   if (n) {
     k_pack_bases<<<grid_for(n * 32, 256, ctx->sm_count), 256, 0, st>>>(A);
@@ -200,13 +203,13 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     k_fasta_track<<<grid_for(word_off, 256, ctx->sm_count), 256, 0, st>>>(A, b->n_contigs);
     out.pack_launches += 1;
   }
-  CUDA_OK(cudaEventRecord(ctx->ev1, st));
+  CUDA_OK(cudaEventRecord(ctx->ev[1], st));
   CUDA_OK(cudaGetLastError());
   unsigned long long counters[2];
   CUDA_OK(cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, st));
   check_device_error(ctx, "guac_reads_pack");
   float ms = 0;
-  CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   out.pack_kernel_ms = ms;
   out.order_sensitive_loci = counters[0];
   out.max_reads_per_granule = counters[1];
@@ -234,13 +237,6 @@ uint64_t build_tiles(const guac_reads& reads, const guac_locus_range* ranges, si
   return requested;
 }
 
-struct OutBuffers {
-  DevBuf<guac_threshold_record> trec;
-  DevBuf<guac_locus_counts> crec;
-  DevBuf<uint8_t> pool;
-  DevBuf<SlowLocus> slow;
-};
-
 template <int MODE>
 void launch_tile(int W, int grid, size_t smem, cudaStream_t st, const DevReads& R, const TileDesc* tiles, const CallParams& prm, const DevOut& out) {
   switch (W) {
@@ -253,11 +249,7 @@ void launch_tile(int W, int grid, size_t smem, cudaStream_t st, const DevReads& 
 
 template <int W, int MODE>
 void set_smem_attr() {
-  static bool done = false;
-  if (!done) {
-    CUDA_OK(cudaFuncSetAttribute(k_pileup_tile<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
-    done = true;
-  }
+  CUDA_OK(cudaFuncSetAttribute(k_pileup_tile<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
 }
 void set_all_smem_attrs() {
   set_smem_attr<8, 0>(); set_smem_attr<12, 0>(); set_smem_attr<16, 0>(); set_smem_attr<20, 0>();
@@ -271,11 +263,37 @@ int planes_for(uint64_t bound) {
   return 20;
 }
 
-// runs K_tile (+ K_exact on the loci it defers) for one read set; returns the device counters
+// the tile list of (reads, ranges) is cached in the context: a repeated call does not rebuild or re-upload it
+uint64_t prepare_tiles(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* ranges, size_t n_ranges, uint64_t* tile_loci) {
+  bool same = ctx->tiles_key_reads == (const void*)&reads && ctx->tiles_key_ranges.size() == n_ranges;
+  for (size_t i = 0; same && i < n_ranges; ++i)
+    same = ctx->tiles_key_ranges[i].contig == ranges[i].contig && ctx->tiles_key_ranges[i].start == ranges[i].start &&
+           ctx->tiles_key_ranges[i].end == ranges[i].end;
+  uint64_t requested = 0;
+  for (size_t i = 0; i < n_ranges; ++i) requested += (uint64_t)std::max<int64_t>(0, ranges[i].end - ranges[i].start);
+  if (!same) {
+    std::vector<TileDesc> tiles;
+    build_tiles(reads, ranges, n_ranges, tiles);
+    uint64_t tl = 0;
+    for (auto& t : tiles) tl += (uint64_t)(t.locus_end - t.locus_begin);
+    ctx->tiles.ensure(std::max<size_t>(tiles.size(), 1) * sizeof(TileDesc));
+    if (!tiles.empty())
+      CUDA_OK(cudaMemcpyAsync(ctx->tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_tiles = tiles.size();
+    ctx->tiles_key_loci = tl;
+    ctx->tiles_key_reads = (const void*)&reads;
+    ctx->tiles_key_ranges.assign(ranges, ranges + n_ranges);
+  }
+  *tile_loci = ctx->tiles_key_loci;
+  return requested;
+}
+
+// runs K_tile (+ K_exact on the loci it defers) for one read set
 void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* ranges, size_t n_ranges, CallParams prm,
                 guac_result& res) {
-  std::vector<TileDesc> tiles;
-  const uint64_t requested = build_tiles(reads, ranges, n_ranges, tiles);
+  uint64_t tile_loci = 0;
+  const uint64_t requested = prepare_tiles(ctx, reads, ranges, n_ranges, &tile_loci);
   res.stats.reads_total = reads.n;
   res.stats.loci_requested = requested;
   res.stats.order_sensitive_loci = reads.order_sensitive_loci;
@@ -292,104 +310,114 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       }
     }
   };
-  if (tiles.empty()) {
+  if (ctx->n_tiles == 0) {
     append_rows_past_track();
     res.stats.loci_visited = res.stats.records = res.counts.size();
     return;
   }
-  set_all_smem_attrs();
+  static bool attrs_done = false;
+  if (!attrs_done) {
+    set_all_smem_attrs();
+    attrs_done = true;
+  }
   cudaStream_t st = ctx->stream;
-  DevBuf<TileDesc> d_tiles;
-  h2d(ctx, d_tiles, tiles.data(), tiles.size());
-  uint64_t tile_loci = 0;
-  for (auto& t : tiles) tile_loci += (uint64_t)(t.locus_end - t.locus_begin);
+  const size_t rec_size = prm.mode == 1 ? sizeof(guac_locus_counts) : sizeof(guac_threshold_record);
   const bool dense = prm.mode == 1 || prm.emit_ref || prm.emit_no_call;
   uint64_t cap_rec = dense ? tile_loci + 16 : std::max<uint64_t>(4096, tile_loci / 64);
   uint64_t cap_slow = std::max<uint64_t>(4096, tile_loci / 32);
   uint64_t cap_pool = kPoolDynOff + std::max<uint64_t>(65536, tile_loci / 64);
+  cap_rec = std::max<uint64_t>(cap_rec, ctx->out_rec.n / rec_size);
+  cap_slow = std::max<uint64_t>(cap_slow, ctx->out_slow.n / sizeof(SlowLocus));
+  cap_pool = std::max<uint64_t>(cap_pool, ctx->out_pool.n);
   int W = planes_for(reads.max_reads_per_granule);
-  double total_ms = 0;
+  double tile_ms = 0, exact_ms = 0;
   int launches = 0;
-  for (int attempt = 0; attempt < 6; ++attempt) {
+  for (int attempt = 0; attempt < 8; ++attempt) {
     if (cap_rec >= 0xFFFFFFF0ull || cap_slow >= 0xFFFFFFF0ull || cap_pool >= 0xFFFFFFF0ull)
       fail(GUAC_ERR_UNSUPPORTED, "too many output records for one call: split the loci ranges");
-    OutBuffers ob;
-    if (prm.mode == 1) ob.crec.alloc(cap_rec); else ob.trec.alloc(cap_rec);
-    ob.pool.alloc(cap_pool);
-    ob.slow.alloc(cap_slow);
-    {
+    ctx->out_rec.ensure(cap_rec * rec_size);
+    ctx->out_slow.ensure(cap_slow * sizeof(SlowLocus));
+    if (ctx->out_pool.ensure(cap_pool)) ctx->pool_head_ready = false;
+    if (!ctx->pool_head_ready) {
       std::vector<uint8_t> head(kPoolDynOff, 0);
       memcpy(head.data(), "<ALT>", 5);
       for (int v = 0; v < 256; ++v) head[kPoolByteOff + v] = (uint8_t)v;
-      CUDA_OK(cudaMemcpyAsync(ob.pool.p, head.data(), head.size(), cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaMemcpyAsync(ctx->out_pool.p, head.data(), head.size(), cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      ctx->pool_head_ready = true;
     }
     CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
     DevOut out;
-    out.trec = ob.trec.p;
-    out.crec = ob.crec.p;
+    out.trec = (guac_threshold_record*)ctx->out_rec.p;
+    out.crec = (guac_locus_counts*)ctx->out_rec.p;
     out.cap_rec = (uint32_t)cap_rec;
-    out.pool = ob.pool.p;
+    out.pool = ctx->out_pool.p;
     out.cap_pool = (uint32_t)cap_pool;
-    out.slow = ob.slow.p;
+    out.slow = (SlowLocus*)ctx->out_slow.p;
     out.cap_slow = (uint32_t)cap_slow;
     out.counters = ctx->d_counters;
     out.err = ctx->d_err;
     const DevReads R = reads.view();
-    CUDA_OK(cudaEventRecord(ctx->ev0, st));
-    if (prm.mode == 1) launch_tile<1>(W, (int)tiles.size(), sizeof(TileSmem), st, R, d_tiles.p, prm, out);
-    else launch_tile<0>(W, (int)tiles.size(), sizeof(TileSmem), st, R, d_tiles.p, prm, out);
-    ++launches;
+    const TileDesc* d_tiles = (const TileDesc*)ctx->tiles.p;
+    CUDA_OK(cudaEventRecord(ctx->ev[0], st));
+    if (prm.mode == 1) launch_tile<1>(W, (int)ctx->n_tiles, sizeof(TileSmem), st, R, d_tiles, prm, out);
+    else launch_tile<0>(W, (int)ctx->n_tiles, sizeof(TileSmem), st, R, d_tiles, prm, out);
+    CUDA_OK(cudaEventRecord(ctx->ev[1], st));
+    // K_exact reads the number of deferred loci from the device counter: no host round trip in between
+    k_exact_loci<<<ctx->sm_count * 8, 64, 0, st>>>(R, out.slow, prm, out);
+    CUDA_OK(cudaEventRecord(ctx->ev[2], st));
+    launches += 2;
     CUDA_OK(cudaGetLastError());
-    unsigned long long c[8];
-    CUDA_OK(cudaMemcpyAsync(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
+    unsigned long long* c = ctx->h_counters;
+    CUDA_OK(cudaMemcpyAsync(c, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    check_device_error(ctx, "pileup");
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    tile_ms += ms;
+    CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+    exact_ms += ms;
     if (c[5]) {  // a bit-sliced counter overflowed: widen and rerun
       if (W >= 20) fail(GUAC_ERR_UNSUPPORTED, "pileup deeper than 2^20 reads");
       W = W == 8 ? 12 : W == 12 ? 16 : 20;
       continue;
     }
-    if (c[2] > cap_slow) {
-      cap_slow = c[2] + 16;
+    if (c[2] > cap_slow || c[0] > cap_rec || kPoolDynOff + c[1] > cap_pool) {
+      cap_slow = std::max<uint64_t>(cap_slow, c[2] + c[2] / 8 + 16);
+      cap_rec = std::max<uint64_t>(cap_rec, c[0] + c[0] / 8 + 16);
+      cap_pool = std::max<uint64_t>(cap_pool, kPoolDynOff + c[1] + c[1] / 8 + 16);
       continue;
     }
-    if (c[2]) {
-      const uint32_t n_slow = (uint32_t)c[2];
-      k_exact_loci<<<(n_slow + 63) / 64, 64, 0, st>>>(R, ob.slow.p, n_slow, prm, out);
-      ++launches;
-      CUDA_OK(cudaGetLastError());
-    }
-    CUDA_OK(cudaEventRecord(ctx->ev1, st));
-    CUDA_OK(cudaMemcpyAsync(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, st));
-    check_device_error(ctx, "pileup");
-    float ms = 0;
-    CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    total_ms += ms;
-    if (c[0] > cap_rec || kPoolDynOff + c[1] > cap_pool) {
-      cap_rec = std::max<uint64_t>(cap_rec, c[0] + 16);
-      cap_pool = std::max<uint64_t>(cap_pool, kPoolDynOff + c[1] + 16);
-      continue;
-    }
-    // ---- D2H and canonical order
+    // ---- D2H (+ canonical order unless switched off)
+    const uint64_t n_rec = c[0];
     std::vector<uint8_t> pool((size_t)(kPoolDynOff + c[1]));
-    CUDA_OK(cudaMemcpyAsync(pool.data(), ob.pool.p, pool.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(pool.data(), ctx->out_pool.p, pool.size(), cudaMemcpyDeviceToHost, st));
+    res.stats.d2h_bytes = pool.size() + n_rec * rec_size + 8 * sizeof(unsigned long long);
     if (prm.mode == 1) {
-      res.counts.resize((size_t)c[0]);
-      if (c[0]) CUDA_OK(cudaMemcpyAsync(res.counts.data(), ob.crec.p, c[0] * sizeof(guac_locus_counts), cudaMemcpyDeviceToHost, st));
+      res.counts.resize((size_t)n_rec);
+      if (n_rec) CUDA_OK(cudaMemcpyAsync(res.counts.data(), ctx->out_rec.p, n_rec * rec_size, cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
       append_rows_past_track();
-      std::sort(res.counts.begin(), res.counts.end(), [](const guac_locus_counts& a, const guac_locus_counts& b) {
-        return std::make_pair(a.contig, a.locus) < std::make_pair(b.contig, b.locus);
-      });
+      if (ctx->sort_records)
+        std::sort(res.counts.begin(), res.counts.end(), [](const guac_locus_counts& a, const guac_locus_counts& b) {
+          return std::make_pair(a.contig, a.locus) < std::make_pair(b.contig, b.locus);
+        });
     } else {
-      std::vector<guac_threshold_record> recs((size_t)c[0]);
-      if (c[0]) CUDA_OK(cudaMemcpyAsync(recs.data(), ob.trec.p, c[0] * sizeof(guac_threshold_record), cudaMemcpyDeviceToHost, st));
+      std::vector<guac_threshold_record> recs((size_t)n_rec);
+      if (n_rec) CUDA_OK(cudaMemcpyAsync(recs.data(), ctx->out_rec.p, n_rec * rec_size, cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
-      auto key = [&](const guac_threshold_record& r) {
-        return std::make_tuple(r.contig, r.start, r.sample, std::string((const char*)pool.data() + r.ref_off, r.ref_len),
-                               std::string((const char*)pool.data() + r.alt_off, r.alt_len));
-      };
-      std::sort(recs.begin(), recs.end(), [&](const guac_threshold_record& a, const guac_threshold_record& b) { return key(a) < key(b); });
+      if (ctx->sort_records) {
+        auto str = [&](uint32_t off, uint16_t len) { return std::string((const char*)pool.data() + off, len); };
+        std::sort(recs.begin(), recs.end(), [&](const guac_threshold_record& a, const guac_threshold_record& b) {
+          if (a.contig != b.contig) return a.contig < b.contig;
+          if (a.start != b.start) return a.start < b.start;
+          if (a.sample != b.sample) return a.sample < b.sample;
+          std::string ra = str(a.ref_off, a.ref_len), rb = str(b.ref_off, b.ref_len);
+          if (ra != rb) return ra < rb;
+          return str(a.alt_off, a.alt_len) < str(b.alt_off, b.alt_len);
+        });
+      }
       res.bytes.clear();
+      res.bytes.reserve(recs.size() * 2 + 16);
       for (auto& r : recs) {  // compact the byte pool in record order
         uint32_t ro = (uint32_t)res.bytes.size();
         res.bytes.insert(res.bytes.end(), pool.begin() + r.ref_off, pool.begin() + r.ref_off + r.ref_len);
@@ -400,12 +428,14 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       }
       res.threshold = std::move(recs);
     }
-    res.stats.loci_visited = c[3] + (prm.mode == 1 ? res.counts.size() - c[0] : 0);
+    res.stats.loci_visited = c[3] + (prm.mode == 1 ? res.counts.size() - n_rec : 0);
     res.stats.tie_loci = c[4];
-    res.stats.records = prm.mode == 1 ? res.counts.size() : c[0];
-    res.stats.kernel_ms = total_ms;
+    res.stats.records = prm.mode == 1 ? res.counts.size() : n_rec;
+    res.stats.kernel_ms = tile_ms + exact_ms;
+    res.stats.tile_kernel_ms = tile_ms;
+    res.stats.exact_kernel_ms = exact_ms;
     res.stats.kernel_launches = (uint64_t)launches;
-    res.stats.reads_relevant = c[2];  // loci decided by the exact per-element kernel (diagnostic)
+    res.stats.exact_loci = c[2];
     return;
   }
   fail(GUAC_ERR_CUDA, "output buffers did not converge");
@@ -455,8 +485,8 @@ guac_status guac_ctx_create(int device, guac_ctx** out) {
     CUDA_OK(cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(unsigned long long)));
     CUDA_OK(cudaMemset(ctx->d_err, 0, sizeof(DevError)));
     CUDA_OK(cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned long long)));
-    CUDA_OK(cudaEventCreate(&ctx->ev0));
-    CUDA_OK(cudaEventCreate(&ctx->ev1));
+    CUDA_OK(cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned long long)));
+    for (auto& e : ctx->ev) CUDA_OK(cudaEventCreate(&e));
     somatic_init_tables(ctx);
   });
   if (s != GUAC_OK) {
@@ -472,11 +502,58 @@ void guac_ctx_destroy(guac_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->d_err) cudaFree(ctx->d_err);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
-  if (ctx->d_phred) cudaFree(ctx->d_phred);
-  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  for (auto& e : ctx->ev)
+    if (e) cudaEventDestroy(e);
+  ctx->out_rec.release();
+  ctx->out_pool.release();
+  ctx->out_slow.release();
+  ctx->tiles.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+guac_status guac_ctx_set_option(guac_ctx* ctx, int option, int64_t value) {
+  if (!ctx) return GUAC_ERR_INVALID_ARGUMENT;
+  switch (option) {
+    case GUAC_OPT_SORT_RECORDS: ctx->sort_records = value != 0; return GUAC_OK;
+    case GUAC_OPT_PACK_QUALITIES: ctx->pack_qualities = value != 0; return GUAC_OK;
+  }
+  ctx->last_error = "unknown option";
+  return GUAC_ERR_INVALID_ARGUMENT;
+}
+
+guac_status guac_ctx_timer_start(guac_ctx* ctx) {
+  if (!ctx) return GUAC_ERR_INVALID_ARGUMENT;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    CUDA_OK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  });
+}
+guac_status guac_ctx_timer_stop(guac_ctx* ctx, double* elapsed_ms) {
+  if (!ctx || !elapsed_ms) return GUAC_ERR_INVALID_ARGUMENT;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    CUDA_OK(cudaEventSynchronize(ctx->ev[5]));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+    *elapsed_ms = ms;
+  });
+}
+
+guac_status guac_host_register(void* ptr, size_t bytes) {
+  if (!ptr || !bytes) return GUAC_ERR_INVALID_ARGUMENT;
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return GUAC_OK; }
+  return e == cudaSuccess ? GUAC_OK : GUAC_ERR_CUDA;
+}
+guac_status guac_host_unregister(void* ptr) {
+  if (!ptr) return GUAC_ERR_INVALID_ARGUMENT;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) cudaGetLastError();
+  return e == cudaSuccess ? GUAC_OK : GUAC_ERR_CUDA;
 }
 
 const char* guac_last_error(const guac_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
@@ -494,12 +571,16 @@ guac_status guac_reads_pack(guac_ctx* ctx, const guac_read_batch* batch, const g
 
 void guac_reads_free(guac_reads* reads) {
   if (!reads) return;
-  if (reads->ctx) cudaSetDevice(reads->ctx->device);
+  if (reads->ctx) {
+    cudaSetDevice(reads->ctx->device);
+    if (reads->ctx->tiles_key_reads == (const void*)reads) reads->ctx->tiles_key_reads = nullptr;
+  }
   delete reads;
 }
 uint64_t guac_reads_count(const guac_reads* reads) { return reads ? reads->n : 0; }
 uint64_t guac_reads_device_bytes(const guac_reads* reads) { return reads ? reads->device_bytes() : 0; }
 uint64_t guac_reads_order_sensitive_loci(const guac_reads* reads) { return reads ? reads->order_sensitive_loci : 0; }
+uint64_t guac_reads_h2d_bytes(const guac_reads* reads) { return reads ? reads->h2d_bytes : 0; }
 double guac_reads_pack_kernel_ms(const guac_reads* reads) { return reads ? reads->pack_kernel_ms : 0.0; }
 
 guac_status guac_germline_threshold(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges, size_t n_ranges,

@@ -16,17 +16,8 @@
 
 using namespace guac;
 
-// ---- context / errors ---------------------------------------------------------------------------------------------------
-struct guac_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  std::string last_error;
-  DevError* d_err = nullptr;
-  unsigned long long* d_counters = nullptr;  // 16 counters
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int sm_count = 148;
-  double* d_phred = nullptr;  // [256] success probabilities, [256..512) their logs ... (somatic tables)
-};
+// ---- errors / device buffers -----------------------------------------------------------------------------------------------
+struct guac_ctx;
 
 namespace {
 
@@ -52,20 +43,6 @@ struct StatusError {
            cudaGetErrorString(e_), __FILE__, __LINE__);                                                        \
   } while (0)
 
-template <typename F>
-guac_status guarded(guac_ctx* ctx, F&& f) {
-  try {
-    f();
-    return GUAC_OK;
-  } catch (const StatusError& e) {
-    if (ctx) ctx->last_error = e.msg;
-    return e.code;
-  } catch (const std::bad_alloc&) {
-    if (ctx) ctx->last_error = "host allocation failed";
-    return GUAC_ERR_OOM;
-  }
-}
-
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -84,8 +61,54 @@ struct DevBuf {
     n = count;
     CUDA_OK(cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
   }
+  bool ensure(size_t count) {  // grow-only; true if (re)allocated
+    if (p && n >= count) return false;
+    alloc(count);
+    return true;
+  }
   size_t bytes() const { return n * sizeof(T); }
 };
+
+}  // namespace
+
+// ---- context ----------------------------------------------------------------------------------------------------------------
+struct guac_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  DevError* d_err = nullptr;
+  unsigned long long* d_counters = nullptr;  // 16 counters
+  unsigned long long* h_counters = nullptr;  // pinned mirror
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [4], [5]: user stopwatch
+  int sm_count = 148;
+  // options
+  int sort_records = 1;
+  int pack_qualities = 1;
+  // scratch kept across calls so that a repeated call neither allocates nor rebuilds its tile list
+  DevBuf<unsigned char> out_rec, out_pool, out_slow, tiles;
+  std::vector<guac_locus_range> tiles_key_ranges;
+  const void* tiles_key_reads = nullptr;
+  uint64_t tiles_key_loci = 0, n_tiles = 0;
+  bool pool_head_ready = false;
+  // somatic tables (device): see guac_somatic.cuh
+  double* d_tables = nullptr;
+};
+
+namespace {
+
+template <typename F>
+guac_status guarded(guac_ctx* ctx, F&& f) {
+  try {
+    f();
+    return GUAC_OK;
+  } catch (const StatusError& e) {
+    if (ctx) ctx->last_error = e.msg;
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    if (ctx) ctx->last_error = "host allocation failed";
+    return GUAC_ERR_OOM;
+  }
+}
 
 void check_device_error(guac_ctx* ctx, const char* what) {
   DevError e;
@@ -132,6 +155,8 @@ struct guac_reads {
   uint64_t total_words = 0, total_grans = 0;
   double pack_kernel_ms = 0;
   int pack_launches = 0;
+  uint64_t h2d_bytes = 0;
+  bool has_qualities = true;
 
   DevReads view() const {
     DevReads R;

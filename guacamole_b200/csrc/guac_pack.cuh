@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) k_pack_bases(PackArgs A) {
     for (int base = 0; base < len; base += 32) {
       int i = base + lane;
       uint8_t b = i < len ? A.R.seq[s0 + i] : (uint8_t)'A';
-      if (i < len && A.R.qual[s0 + i] > 127) bad_q = true;
+      if (A.R.qual && i < len && A.R.qual[s0 + i] > 127) bad_q = true;
       uint32_t code = base_code(b);
       bool exc = i < len && !is_std_base(b);
       uint32_t lo = __ballot_sync(0xFFFFFFFFu, (code & 1u) && !exc);

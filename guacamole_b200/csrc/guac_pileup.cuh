@@ -461,7 +461,7 @@ __device__ int classify(const DevReads& R, uint64_t r, int locus, uint8_t ref_ba
   const ReadRec rec = R.rec[r];
   const uint32_t c0 = R.cig_off[r], c1 = R.cig_off[r + 1];
   const uint8_t* seq = R.seq + R.seq_off[r];
-  const uint8_t* qual = R.qual + R.seq_off[r];
+  const uint8_t* qual = R.qual ? R.qual + R.seq_off[r] : nullptr;  // absent when packed without qualities
   const int read_len = (int)(R.seq_off[r + 1] - R.seq_off[r]);
   const int mapq = (int)(rec.info >> kInfoMapqShift);
   int ref_pos = rec.start, read_pos = 0;
@@ -490,7 +490,7 @@ __device__ int classify(const DevReads& R, uint64_t r, int locus, uint8_t ref_ba
       e.len = until - from;
       e.ptr = R.seq_off[r] + from;
       int q = 255;
-      for (int k = from; k < until; ++k) q = min(q, (int)(int8_t)qual[k]);
+      for (int k = from; k < until; ++k) q = min(q, qual ? (int)(int8_t)qual[k] : 0);
       e.qual = q;
       e.base = seq[from];
       return 0;
@@ -506,7 +506,7 @@ __device__ int classify(const DevReads& R, uint64_t r, int locus, uint8_t ref_ba
       e.kind = kDeletion;
       e.len = next_len;
       e.ptr = (uint64_t)off;
-      e.qual = (int)(int8_t)qual[rp];
+      e.qual = qual ? (int)(int8_t)qual[rp] : 0;
       e.base = ref_base;
       return 0;
     }
@@ -523,7 +523,7 @@ __device__ int classify(const DevReads& R, uint64_t r, int locus, uint8_t ref_ba
     if (op_is_match_like(op)) {
       if (rp < 0 || rp >= read_len) return GUAC_ERR_INVALID_CIGAR;
       e.base = seq[rp];
-      e.qual = (int)(int8_t)qual[rp];
+      e.qual = qual ? (int)(int8_t)qual[rp] : 0;
       e.kind = (e.base == ref_base) ? kMatch : kMismatch;
       e.len = 1;
       return 0;
@@ -609,10 +609,16 @@ __device__ uint32_t pool_alloc(DevOut& out, uint32_t n) {
 }
 
 // ---- K_exact: thread per locus ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_exact_loci(DevReads R, const SlowLocus* __restrict__ loci, uint32_t n_loci, CallParams prm, DevOut out) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_loci) return;
-  const int contig = loci[t].contig, locus = loci[t].locus;
+__device__ void exact_locus(const DevReads& R, int contig, int locus, const CallParams& prm, DevOut& out);
+
+// grid-stride over the loci K_tile deferred; their number is read from the device counter (no host round trip)
+__global__ void __launch_bounds__(64) k_exact_loci(DevReads R, const SlowLocus* __restrict__ loci, CallParams prm, DevOut out) {
+  const uint32_t n_loci = (uint32_t)min(out.counters[2], (unsigned long long)out.cap_slow);
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_loci; t += gridDim.x * blockDim.x)
+    exact_locus(R, loci[t].contig, loci[t].locus, prm, out);
+}
+
+__device__ void exact_locus(const DevReads& R, const int contig, const int locus, const CallParams& prm, DevOut& out) {
   const ContigInfo ci = R.contigs[contig];
   bool std_ref;
   const uint8_t ref_base = reference_base_of(R, ci, contig, locus, &std_ref);

@@ -69,7 +69,8 @@ class SynthBatch:
         cigar_off = self._arr(c.cigar_off, n + 1, np.uint64).copy()
         seq_off = self._arr(c.seq_off, n + 1, np.uint64).copy()
         md_off = self._arr(c.md_off, n + 1, np.uint64).copy()
-        md = np.frombuffer(C.string_at(c.md, int(md_off[-1])), dtype=np.uint8).copy() if n else np.zeros(0, np.uint8)
+        md_addr = C.c_void_p.from_address(C.addressof(c) + abi.ReadBatchC.md.offset).value  # raw pointer, not bytes
+        md = np.frombuffer(C.string_at(md_addr, int(md_off[-1])), dtype=np.uint8).copy() if n else np.zeros(0, np.uint8)
         return ReadBatch(
             self.contig_names, self._arr(c.contig_length, int(c.n_contigs), np.int64).copy(), [self.sample_name],
             self._arr(c.contig, n, np.int32).copy(), self._arr(c.start, n, np.int64).copy(), cigar_off,

@@ -193,6 +193,11 @@ typedef struct guac_stats {
   uint64_t order_sensitive_loci; /* MD-derived reference bases disagree */
   double kernel_ms;              /* device time of the pileup+call kernels of the last call (CUDA events) */
   uint64_t kernel_launches;      /* number of kernels launched by the last call */
+  double tile_kernel_ms;         /* ... of which the bit-sliced tile kernel (K_tile) */
+  double exact_kernel_ms;        /* ... of which the exact per-element kernel(s) (K_exact / likelihoods) */
+  uint64_t exact_loci;           /* loci decided by the exact per-element kernel */
+  uint64_t h2d_bytes;            /* bytes copied host -> device by the call */
+  uint64_t d2h_bytes;            /* bytes copied device -> host by the call */
 } guac_stats;
 
 typedef struct guac_ctx guac_ctx;
@@ -206,6 +211,22 @@ void guac_ctx_destroy(guac_ctx* ctx);
 const char* guac_last_error(const guac_ctx* ctx);   /* valid until the next call on ctx */
 const char* guac_status_string(guac_status s);
 
+/* per-context options (defaults in brackets) */
+#define GUAC_OPT_SORT_RECORDS 1    /* [1] return records in canonical (contig, start, sample, ref, alt) order; 0 = device
+                                      order (the reference's own order is unspecified: coalesce(1, shuffle = true),
+                                      Common.scala:293) */
+#define GUAC_OPT_PACK_QUALITIES 2  /* [1] copy base qualities to the device at pack time; germline-threshold never reads
+                                      them, somatic-standard needs them */
+guac_status guac_ctx_set_option(guac_ctx* ctx, int option, int64_t value);
+
+/* Device-side stopwatch on the context's stream (CUDA events): start, run any number of calls, stop -> elapsed ms. */
+guac_status guac_ctx_timer_start(guac_ctx* ctx);
+guac_status guac_ctx_timer_stop(guac_ctx* ctx, double* elapsed_ms);
+
+/* Page-lock caller-owned host buffers (e.g. direct ByteBuffers) so that guac_reads_pack copies at full PCIe speed. */
+guac_status guac_host_register(void* ptr, size_t bytes);
+guac_status guac_host_unregister(void* ptr);
+
 /* Pack a host batch into the device SoA (copies; caller keeps ownership of `batch`).  Validates sortedness,
  * CIGAR/MD consistency and quality range — the checks SlidingWindow / MappedRead do lazily. `ref` may be NULL
  * (reference bases then come from MD tags, Pileup.referenceBaseAtLocus pileup/Pileup.scala:157-165). */
@@ -215,6 +236,7 @@ uint64_t guac_reads_count(const guac_reads* reads);
 uint64_t guac_reads_device_bytes(const guac_reads* reads);
 /* loci where the reads' MD-derived reference bases disagreed and the canonical rule chose one */
 uint64_t guac_reads_order_sensitive_loci(const guac_reads* reads);
+uint64_t guac_reads_h2d_bytes(const guac_reads* reads);      /* bytes guac_reads_pack copied host -> device */
 double guac_reads_pack_kernel_ms(const guac_reads* reads);   /* device time of the pack kernels (CUDA events) */
 
 /* ---- the hot path ---------------------------------------------------------------------------------------- */

@@ -47,7 +47,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(abi.SomaticRecordC) == 40 + 2 * 64
     assert C.sizeof(abi.LocusCountsC) == 48
     assert C.sizeof(abi.LocusRangeC) == 24
-    assert C.sizeof(abi.StatsC) == 80
+    assert C.sizeof(abi.StatsC) == 120
 
 
 def test_partition_loci_uniformly_goldens():  # DistributedUtilSuite.scala:46-63 through the product's host entry point
