@@ -238,29 +238,17 @@ uint64_t build_tiles(const guac_reads& reads, const guac_locus_range* ranges, si
 }
 
 template <int MODE>
-void launch_tile(int W, int grid, size_t smem, cudaStream_t st, const DevReads& R, const TileDesc* tiles, const CallParams& prm, const DevOut& out) {
-  switch (W) {
-    case 8: k_pileup_tile<8, MODE><<<grid, kTileWords, smem, st>>>(R, tiles, prm, out); break;
-    case 12: k_pileup_tile<12, MODE><<<grid, kTileWords, smem, st>>>(R, tiles, prm, out); break;
-    case 16: k_pileup_tile<16, MODE><<<grid, kTileWords, smem, st>>>(R, tiles, prm, out); break;
-    default: k_pileup_tile<20, MODE><<<grid, kTileWords, smem, st>>>(R, tiles, prm, out); break;
-  }
+void launch_tile(bool wide, int grid, cudaStream_t st, const DevReads& R, const TileDesc* tiles, const CallParams& prm, const DevOut& out) {
+  if (wide) k_pileup_tile<uint64_t, MODE><<<grid, kTileThreads, sizeof(TileSmem<uint64_t, MODE>), st>>>(R, tiles, prm, out);
+  else k_pileup_tile<uint32_t, MODE><<<grid, kTileThreads, sizeof(TileSmem<uint32_t, MODE>), st>>>(R, tiles, prm, out);
 }
 
-template <int W, int MODE>
+template <typename CntT, int MODE>
 void set_smem_attr() {
-  CUDA_OK(cudaFuncSetAttribute(k_pileup_tile<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+  CUDA_OK(cudaFuncSetAttribute(k_pileup_tile<CntT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<CntT, MODE>)));
 }
 void set_all_smem_attrs() {
-  set_smem_attr<8, 0>(); set_smem_attr<12, 0>(); set_smem_attr<16, 0>(); set_smem_attr<20, 0>();
-  set_smem_attr<8, 1>(); set_smem_attr<12, 1>(); set_smem_attr<16, 1>(); set_smem_attr<20, 1>();
-}
-
-int planes_for(uint64_t bound) {
-  if (bound < 256) return 8;
-  if (bound < 4096) return 12;
-  if (bound < 65536) return 16;
-  return 20;
+  set_smem_attr<uint32_t, 0>(); set_smem_attr<uint64_t, 0>(); set_smem_attr<uint32_t, 1>(); set_smem_attr<uint64_t, 1>();
 }
 
 // the tile list of (reads, ranges) is cached in the context: a repeated call does not rebuild or re-upload it
@@ -329,7 +317,8 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
   cap_rec = std::max<uint64_t>(cap_rec, ctx->out_rec.n / rec_size);
   cap_slow = std::max<uint64_t>(cap_slow, ctx->out_slow.n / sizeof(SlowLocus));
   cap_pool = std::max<uint64_t>(cap_pool, ctx->out_pool.n);
-  int W = planes_for(reads.max_reads_per_granule);
+  // 8-bit counter fields first unless the pileup is certainly deeper; K_tile reports an overflow and we widen
+  bool wide = reads.max_reads_per_granule >= 2048;
   double tile_ms = 0, exact_ms = 0;
   int launches = 0;
   for (int attempt = 0; attempt < 8; ++attempt) {
@@ -360,11 +349,11 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     const DevReads R = reads.view();
     const TileDesc* d_tiles = (const TileDesc*)ctx->tiles.p;
     CUDA_OK(cudaEventRecord(ctx->ev[0], st));
-    if (prm.mode == 1) launch_tile<1>(W, (int)ctx->n_tiles, sizeof(TileSmem), st, R, d_tiles, prm, out);
-    else launch_tile<0>(W, (int)ctx->n_tiles, sizeof(TileSmem), st, R, d_tiles, prm, out);
+    if (prm.mode == 1) launch_tile<1>(wide, (int)ctx->n_tiles, st, R, d_tiles, prm, out);
+    else launch_tile<0>(wide, (int)ctx->n_tiles, st, R, d_tiles, prm, out);
     CUDA_OK(cudaEventRecord(ctx->ev[1], st));
     // K_exact reads the number of deferred loci from the device counter: no host round trip in between
-    k_exact_loci<<<ctx->sm_count * 8, 64, 0, st>>>(R, out.slow, prm, out);
+    k_exact_loci<<<ctx->sm_count * 4, kExactWarps * 32, 0, st>>>(R, out.slow, prm, out);
     CUDA_OK(cudaEventRecord(ctx->ev[2], st));
     launches += 2;
     CUDA_OK(cudaGetLastError());
@@ -376,9 +365,9 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     tile_ms += ms;
     CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
     exact_ms += ms;
-    if (c[5]) {  // a bit-sliced counter overflowed: widen and rerun
-      if (W >= 20) fail(GUAC_ERR_UNSUPPORTED, "pileup deeper than 2^20 reads");
-      W = W == 8 ? 12 : W == 12 ? 16 : 20;
+    if (c[5]) {  // a counter field may have wrapped: widen and rerun
+      if (wide) fail(GUAC_ERR_UNSUPPORTED, "pileup deeper than 65535 reads");
+      wide = true;
       continue;
     }
     if (c[2] > cap_slow || c[0] > cap_rec || kPoolDynOff + c[1] > cap_pool) {

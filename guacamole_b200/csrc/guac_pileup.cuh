@@ -1,15 +1,17 @@
 // guac_pileup.cuh — the pileup hot path: CIGAR expansion + per-locus allele / depth / strand counting + fused callers.
 //
-// K_tile   (k_pileup_tile): one CTA per tile of 4096 loci, one THREAD per 32-loci word.  The tile's reads (a contiguous
-//           index range of the start-sorted store, found through the granule index) are staged chunk-wise into shared
-//           memory; every thread aligns each overlapping read's 2-bit base planes onto its word with funnel shifts
-//           (CIGAR expansion, bit-parallel over 32 loci) and adds them into bit-sliced ("vertical") counters with
-//           carry-save adders — no atomics, no per-(read, locus) work.  The epilogue evaluates the caller per locus:
+// K_tile   (k_pileup_tile): one CTA per tile of 4096 loci.  Phase 1 is READ-centric: each thread takes one read of the
+//           tile's candidate range (a contiguous index range of the start-sorted store, found through the granule index),
+//           aligns its 2-bit base planes onto the reference track word by word with funnel shifts (CIGAR expansion,
+//           bit-parallel over 32 loci), XORs with the reference planes held in shared memory and touches the per-locus
+//           counter tile only where the read DIFFERS from the reference (sparse shared-memory atomics: one per mismatch /
+//           insertion / deletion / clipped element) plus two atomics per read for the depth difference array.
+//           Phase 2 scans the difference array into depth (+ strand depth).  Phase 3 is LOCUS-centric: the caller.
 //             GermlineThreshold.Caller.callVariantsAtLocus      commands/GermlineThresholdCaller.scala:90-179
 //             Pileup.depth/positiveDepth/referenceDepth           pileup/Pileup.scala:76-91
 //           Replaces SlidingWindow.setCurrentLocus (windowing/SlidingWindow.scala:83-110), Pileup.atGreaterLocus
 //           (pileup/Pileup.scala:103-132) and PileupElement.advanceToLocus/alignment (pileup/PileupElement.scala:68-248).
-// K_exact  (k_exact_loci): one thread per locus that the bit-sliced path cannot decide exactly (insertions, deletions,
+// K_exact  (k_exact_loci): one WARP per locus that the counter tile cannot decide exactly (insertions, deletions,
 //           clipped/N-skipped elements, non-ACGT bases, non-standard reference base): a literal per-element walk.
 #pragma once
 
@@ -56,46 +58,6 @@ struct CallParams {
   int32_t sample;
 };
 
-// ---- bit-sliced counters --------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a ^ b)); }
-
-template <int W>
-struct VCounter {
-  uint32_t p[W];  // p[k] holds bit k of the 32 per-locus counts
-  __device__ __forceinline__ void clear() {
-#pragma unroll
-    for (int k = 0; k < W; ++k) p[k] = 0;
-  }
-  // add four one-bit-per-locus words; returns the carry out of the top plane
-  __device__ __forceinline__ uint32_t add4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    uint32_t t0 = maj3(p[0], a, b);
-    uint32_t s0 = p[0] ^ a ^ b;
-    uint32_t t1 = maj3(s0, c, d);
-    p[0] = s0 ^ c ^ d;
-    uint32_t f = maj3(p[1], t0, t1);
-    p[1] = p[1] ^ t0 ^ t1;
-#pragma unroll
-    for (int k = 2; k < W; ++k) {
-      uint32_t cy = p[k] & f;
-      p[k] ^= f;
-      f = cy;
-    }
-    return f;
-  }
-  __device__ __forceinline__ uint32_t any() const {
-    uint32_t o = 0;
-#pragma unroll
-    for (int k = 0; k < W; ++k) o |= p[k];
-    return o;
-  }
-  __device__ __forceinline__ int at(int b) const {
-    int v = 0;
-#pragma unroll
-    for (int k = 0; k < W; ++k) v |= (int)((p[k] >> b) & 1u) << k;
-    return v;
-  }
-};
-
 // ---- one read aligned onto one word ------------------------------------------------------------------------------------
 struct Aligned {
   uint32_t plain;  // Match/Mismatch elements whose read base is A/C/G/T
@@ -103,31 +65,11 @@ struct Aligned {
   uint32_t other;  // every other element of this read in the word (insertion / deletion anchors, mid-deletion, N-skip, non-ACGT)
 };
 
-// SIMPLE reads: a single aligned segment [start, end) <-> read bases [lead, lead + end - start)
-__device__ __forceinline__ Aligned align_simple(const ReadRec& rec, const uint2* P, int wbase) {
-  Aligned a;
-  int q0 = (int)(rec.info & kInfoLeadMask) + (wbase - rec.start);
-  uint32_t valid = bit_range(rec.start - wbase, rec.end - wbase);
-  a.lo = plane_window([&](int j) { return P[j].x; }, q0) & valid;
-  a.hi = plane_window([&](int j) { return P[j].y; }, q0) & valid;
-  a.plain = valid;
-  a.other = 0;
-  return a;
-}
-
-// reads with a non-ACGT base: take the exception mask from HBM (rare)
-__device__ __noinline__ void apply_exceptions(Aligned& a, const DevReads& R, uint32_t pair_off, int q0_of_bit0, uint32_t valid) {
-  const uint32_t* X = R.xmask + pair_off;
-  uint32_t x = plane_window([&](int j) { return X[j]; }, q0_of_bit0) & valid & a.plain;
-  a.plain &= ~x;
-  a.lo &= ~x;
-  a.hi &= ~x;
-  a.other |= x;
-}
-
 // general reads: walk the run-length CIGAR; each M/=/X run is one funnel-shifted window
-__device__ __noinline__ Aligned align_cigar(const DevReads& R, uint64_t r, const ReadRec& rec, const uint2* P, int wbase) {
+__device__ __noinline__ Aligned align_cigar(const DevReads& R, uint64_t r, const ReadRec rec, int wbase) {
   Aligned a{0, 0, 0, 0};
+  const uint2* P = R.pairs + rec.pair_off;
+  const uint32_t* X = R.xmask + rec.pair_off;
   const uint32_t c0 = R.cig_off[r], c1 = R.cig_off[r + 1];
   int ref_pos = rec.start, read_pos = 0;
   uint32_t prev_op = 0xFFu;
@@ -141,7 +83,7 @@ __device__ __noinline__ Aligned align_cigar(const DevReads& R, uint64_t r, const
         a.lo |= plane_window([&](int j) { return P[j].x; }, q0) & valid;
         a.hi |= plane_window([&](int j) { return P[j].y; }, q0) & valid;
         a.plain |= valid;
-        if (rec.info & kInfoHasExc) apply_exceptions(a, R, rec.pair_off, q0, valid);
+        if (rec.info & kInfoHasExc) a.other |= plane_window([&](int j) { return X[j]; }, q0) & valid;
       }
       ref_pos += len;
       read_pos += len;
@@ -170,37 +112,79 @@ __device__ __noinline__ Aligned align_cigar(const DevReads& R, uint64_t r, const
 }
 
 // ---- K_tile ---------------------------------------------------------------------------------------------------------------
-struct __align__(16) TileSmem {
-  ReadRec rec[kChunkReads + 4];
-  uint2 pairs[kChunkPairs + 8];
-  int32_t pmax[kChunkReads];
-  int32_t warp_max[8];
-  uint32_t first, last;
-  uint32_t cut;
+// Per-locus counter word: four fields of FB bits — [0] "other" elements, [1..3] mismatches by class (lo ^ ref_lo) |
+// (hi ^ ref_hi) << 1, i.e. read base code = reference code ^ class.  CntT = uint32_t (8-bit fields, pileups < 256 deep) or
+// uint64_t (16-bit fields, < 65536 deep).  Depth (and, in counts mode, positive-strand depth) come from difference arrays.
+constexpr int kTileThreads = 128;
+__host__ __device__ constexpr int cov_index(int i) { return i + (i >> 5); }  // one pad word per 32: conflict-free scan
+
+constexpr int kListCap = 1024;  // reads of one tile that need the CIGAR walk (kept in shared memory; overflow handled inline)
+
+template <typename CntT, int MODE>
+struct TileSmem {
+  uint32_t ref_lo[kTileWords], ref_hi[kTileWords], ref_std[kTileWords];
+  uint32_t cov[cov_index(kTileLoci + 32) + 1];
+  uint32_t pos[MODE == 1 ? cov_index(kTileLoci + 32) + 1 : 1];  // positive-strand difference array (counts mode only)
+  CntT cnt[kTileLoci];
+  uint32_t list[kListCap];
+  uint32_t warp_sum[kTileThreads / 32];
+  uint32_t first, last, n_list;
 };
 
-template <int W, int MODE>
-__global__ void __launch_bounds__(kTileWords) k_pileup_tile(DevReads R, const TileDesc* __restrict__ tiles, CallParams prm, DevOut out) {
+// one shared-memory atomic per set bit; the loop is warp-uniform so that the warp stays converged
+template <typename CntT>
+__device__ __forceinline__ void count_bits(CntT* cnt, int word_in_tile, uint32_t bits, uint32_t x, uint32_t y) {
+  constexpr int FB = sizeof(CntT) * 2;
+  while (__any_sync(0xFFFFFFFFu, bits != 0)) {
+    if (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const int cls = (int)((x >> b) & 1u) | ((int)((y >> b) & 1u) << 1);
+      if constexpr (sizeof(CntT) == 8)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&cnt[(word_in_tile << 5) + b]), 1ull << (FB * cls));
+      else
+        atomicAdd(&cnt[(word_in_tile << 5) + b], (CntT)1 << (FB * cls));
+    }
+  }
+}
+
+template <typename CntT, int MODE>
+__global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const TileDesc* __restrict__ tiles, CallParams prm, DevOut out) {
+  constexpr int FB = sizeof(CntT) * 2;
+  constexpr uint32_t FMASK = (1u << FB) - 1u;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
+  TileSmem<CntT, MODE>& S = *reinterpret_cast<TileSmem<CntT, MODE>*>(smem_raw);
   const TileDesc td = tiles[blockIdx.x];
   const ContigInfo ci = R.contigs[td.contig];
   const int tid = threadIdx.x;
-  const int w = td.word0 + tid;          // this thread's word (contig-relative)
-  const int wbase = w << 5;
+  const int tile_lo = td.word0 << 5;
+  const int tile_hi = min(tile_lo + kTileLoci, ci.n_words << 5);
 
-  // candidate reads of the tile through the granule index
+  // ---- phase 0: clear the counter tile, stage the reference planes, find the candidate reads through the granule index
+  for (int i = tid; i < kTileLoci; i += kTileThreads) S.cnt[i] = 0;
+  for (int i = tid; i < cov_index(kTileLoci + 32) + 1; i += kTileThreads) {
+    S.cov[i] = 0;
+    if (MODE == 1) S.pos[i] = 0;
+  }
+  {
+    const int w = td.word0 + tid;
+    const bool in = w < ci.n_words;
+    S.ref_lo[tid] = in ? R.trk_lo[ci.word_off + w] : 0u;
+    S.ref_hi[tid] = in ? R.trk_hi[ci.word_off + w] : 0u;
+    S.ref_std[tid] = in ? R.trk_std[ci.word_off + w] : 0u;
+  }
   if (tid == 0) {
     S.first = 0xFFFFFFFFu;
     S.last = 0;
+    S.n_list = 0;
   }
   __syncthreads();
   {
-    int g0 = (td.word0 << 5) >> kGranuleShift;
-    int g1 = min(((td.word0 + kTileWords) << 5) - 1, ci.length - 1) >> kGranuleShift;
-    int g = g0 + tid;
+    const int g0 = tile_lo >> kGranuleShift;
+    const int g1 = min(tile_lo + kTileLoci - 1, ci.length - 1) >> kGranuleShift;
+    const int g = g0 + tid;
     if (g <= g1 && g < ci.n_grans) {
-      uint32_t f = R.gran_first[ci.gran_off + g], l = R.gran_last[ci.gran_off + g];
+      const uint32_t f = R.gran_first[ci.gran_off + g], l = R.gran_last[ci.gran_off + g];
       if (f != 0xFFFFFFFFu) {
         atomicMin(&S.first, f);
         atomicMax(&S.last, l);
@@ -208,203 +192,250 @@ __global__ void __launch_bounds__(kTileWords) k_pileup_tile(DevReads R, const Ti
     }
   }
   __syncthreads();
-  const uint32_t first = S.first, last = S.last;
+  const uint32_t first = S.first, last = S.first == 0xFFFFFFFFu ? 0u : S.last;
 
-  VCounter<W> cV, cL, cH, cHL;   // plain elements, lo bit, hi bit, both
-  VCounter<(MODE == 1 ? W : 3)> cO;  // other elements (narrow + sticky overflow in caller mode)
-  VCounter<(MODE == 1 ? W : 1)> cP;  // positive-strand elements (counts mode only)
-  cV.clear(); cL.clear(); cH.clear(); cHL.clear(); cO.clear(); cP.clear();
-  uint32_t ovf = 0, o_sat = 0;
-
-  for (uint32_t c0 = first; c0 < last && first != 0xFFFFFFFFu;) {
-    // ---- stage a chunk of records, cut it so that its plane pairs fit, then stage the pairs
-    const uint32_t cn_max = min((uint32_t)kChunkReads, last - c0);
-    __syncthreads();
-    for (uint32_t i = tid; i <= cn_max; i += kTileWords) S.rec[i] = R.rec[c0 + i];
-    if (tid == 0) S.cut = cn_max;
-    __syncthreads();
-    const uint32_t pbase = S.rec[0].pair_off;
-    for (uint32_t i = tid + 1; i <= cn_max; i += kTileWords)
-      if (S.rec[i].pair_off - pbase > (uint32_t)kChunkPairs) atomicMin(&S.cut, i - 1);
-    __syncthreads();
-    const uint32_t cn = S.cut;
-    const uint32_t np = S.rec[cn].pair_off - pbase;
-    for (uint32_t i = tid; i < np + 2; i += kTileWords) S.pairs[i] = R.pairs[pbase + i];
-    // prefix maximum of `end` over the chunk: reads before the first index with pmax > wbase cannot reach this word
-    {
-      int m = -0x7FFFFFFF;
-      const uint32_t per = (cn + kTileWords - 1) / kTileWords;
-      const uint32_t b0 = min(cn, tid * per), b1 = min(cn, b0 + per);
-      for (uint32_t i = b0; i < b1; ++i) m = max(m, S.rec[i].end);
-      int incl = m;
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if ((tid & 31) >= o) incl = max(incl, t);
-      }
-      if ((tid & 31) == 31) S.warp_max[tid >> 5] = incl;
-      __syncthreads();
-      int before = -0x7FFFFFFF;
-      for (int k = 0; k < (tid >> 5); ++k) before = max(before, S.warp_max[k]);
-      int excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
-      if ((tid & 31) == 0) excl = -0x7FFFFFFF;
-      int run = max(before, excl);
-      for (uint32_t i = b0; i < b1; ++i) {
-        run = max(run, S.rec[i].end);
-        S.pmax[i] = run;
-      }
-    }
-    __syncthreads();
-
-    // ---- this thread's reads in the chunk: [lb, ub)
-    uint32_t lb, ub;
-    {
-      uint32_t lo_i = 0, hi_i = cn;  // first i with rec[i].start >= wbase + 32
-      while (lo_i < hi_i) {
-        uint32_t mid = (lo_i + hi_i) >> 1;
-        if (S.rec[mid].start >= wbase + 32) hi_i = mid; else lo_i = mid + 1;
-      }
-      ub = lo_i;
-      lo_i = 0; hi_i = ub;           // first i with pmax[i] > wbase
-      while (lo_i < hi_i) {
-        uint32_t mid = (lo_i + hi_i) >> 1;
-        if (S.pmax[mid] > wbase) hi_i = mid; else lo_i = mid + 1;
-      }
-      lb = lo_i;
-    }
-    for (uint32_t i = lb; i < ub; i += 4) {
-      Aligned a[4];
-      uint32_t pos[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        a[u] = Aligned{0, 0, 0, 0};
-        pos[u] = 0;
-        const uint32_t idx = i + u;
-        if (idx < ub) {
-          const ReadRec rec = S.rec[idx];
-          if (rec.end > wbase) {
-            const uint2* P = S.pairs + (rec.pair_off - pbase);
-            if (rec.info & kInfoSimple) {
-              a[u] = align_simple(rec, P, wbase);
-              if (rec.info & kInfoHasExc)
-                apply_exceptions(a[u], R, rec.pair_off, (int)(rec.info & kInfoLeadMask) + (wbase - rec.start), a[u].plain);
-            } else {
-              a[u] = align_cigar(R, c0 + idx, rec, P, wbase);
-            }
-            if (MODE == 1 && (rec.info & kInfoPositive)) pos[u] = a[u].plain | a[u].other;
-          }
+  // general path for one read (CIGAR walk / exception mask), one word at a time
+  auto general_read = [&](uint32_t r, const ReadRec rec, bool active, int w0, int w1) {
+    const int nw = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)(active ? w1 - w0 + 1 : 0));
+    for (int k = 0; k < nw; ++k) {
+      const int w = w0 + k;
+      Aligned a{0, 0, 0, 0};
+      if (active && w <= w1) {
+        const int wbase = tile_lo + (w << 5);
+        if (rec.info & kInfoSimple) {  // simple read holding non-ACGT bases
+          const uint2* P = R.pairs + rec.pair_off;
+          const uint32_t* X = R.xmask + rec.pair_off;
+          const int q0 = (int)(rec.info & kInfoLeadMask) + (wbase - rec.start);
+          const uint32_t valid = bit_range(rec.start - wbase, rec.end - wbase);
+          a.other = plane_window([&](int j) { return X[j]; }, q0) & valid;
+          a.plain = valid & ~a.other;
+          a.lo = plane_window([&](int j) { return P[j].x; }, q0) & a.plain;
+          a.hi = plane_window([&](int j) { return P[j].y; }, q0) & a.plain;
+        } else {
+          a = align_cigar(R, r, rec, wbase);
         }
       }
-      ovf |= cV.add4(a[0].plain, a[1].plain, a[2].plain, a[3].plain);
-      cL.add4(a[0].lo, a[1].lo, a[2].lo, a[3].lo);
-      cH.add4(a[0].hi, a[1].hi, a[2].hi, a[3].hi);
-      cHL.add4(a[0].lo & a[0].hi, a[1].lo & a[1].hi, a[2].lo & a[2].hi, a[3].lo & a[3].hi);
-      uint32_t oc = cO.add4(a[0].other, a[1].other, a[2].other, a[3].other);
-      if (MODE == 1) { ovf |= oc; ovf |= cP.add4(pos[0], pos[1], pos[2], pos[3]); } else o_sat |= oc;
+      const int ws = (active && w <= w1) ? w : 0;
+      const uint32_t x = (a.lo ^ S.ref_lo[ws]) & a.plain, y = (a.hi ^ S.ref_hi[ws]) & a.plain;
+      count_bits<CntT>(S.cnt, ws, x | y, x, y);
+      count_bits<CntT>(S.cnt, ws, a.other, 0u, 0u);
     }
-    c0 += cn;
-  }
-  if (ovf) atomicAdd(&out.counters[5], 1ull);
+  };
 
-  // ---- epilogue: the caller, per locus of this word ----------------------------------------------------------------------
-  if (w >= ci.n_words) return;
-  const uint32_t in_range = bit_range(td.locus_begin - wbase, td.locus_end - wbase);
-  if (!in_range) return;
-  const uint32_t rlo = R.trk_lo[ci.word_off + w], rhi = R.trk_hi[ci.word_off + w], rstd = R.trk_std[ci.word_off + w];
-  const uint32_t anyO = cO.any() | o_sat;
-  const uint32_t covered = cV.any() | anyO;
-  uint32_t mm = 0;
-#pragma unroll
-  for (int k = 0; k < W; ++k) mm |= (cL.p[k] ^ (rlo & cV.p[k])) | (cH.p[k] ^ (rhi & cV.p[k]));
-  uint32_t visit = (prm.skip_empty ? covered : 0xFFFFFFFFu) & in_range;
-  if (MODE == 0 && !prm.skip_empty) visit &= covered;  // callVariantsAtLocus returns nothing on an empty pileup
-  atomicAdd(&out.counters[3], (unsigned long long)__popc(visit));
-  uint32_t todo = visit;
-  if (MODE == 0 && !prm.emit_ref && !prm.emit_no_call) todo &= (mm | anyO | ~rstd);
-  while (todo) {
-    const int b = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const int locus = wbase + b;
-    const int v = cV.at(b), l = cL.at(b), h = cH.at(b), hl = cHL.at(b), o = cO.at(b);
-    const bool o_over = (o_sat >> b) & 1u;
-    const bool std_ref = (rstd >> b) & 1u;
-    int cnt[4] = {v - l - h + hl, l - hl, h - hl, hl};
-    const int rcode = (int)(((rlo >> b) & 1u) | (((rhi >> b) & 1u) << 1));
+  // ---- phase 1a: one read per thread; SIMPLE reads take the fast path, the others are listed for phase 1b
+  for (uint32_t base = first; base < last; base += kTileThreads) {  // uniform trip count: the warp stays converged
+    const uint32_t r = base + tid;
+    ReadRec rec{0, 0, 0, 0};
+    if (r < last) rec = R.rec[r];
+    const bool active = r < last && rec.end > tile_lo && rec.start < tile_hi && rec.end > rec.start;
+    int w0 = 0, w1 = -1;
+    if (active) {
+      const int s = max(rec.start, tile_lo) - tile_lo, e = min(rec.end, tile_hi) - tile_lo;
+      atomicAdd(&S.cov[cov_index(s)], 1u);
+      atomicSub(&S.cov[cov_index(e)], 1u);
+      if (MODE == 1 && (rec.info & kInfoPositive)) {
+        atomicAdd(&S.pos[cov_index(s)], 1u);
+        atomicSub(&S.pos[cov_index(e)], 1u);
+      }
+      w0 = s >> 5;
+      w1 = (e - 1) >> 5;
+    }
+    const bool fast = active && (rec.info & (kInfoSimple | kInfoHasExc)) == kInfoSimple;
+    bool slow_now = false;
+    if (active && !fast) {
+      const uint32_t slot = atomicAdd(&S.n_list, 1u);
+      if (slot < (uint32_t)kListCap) S.list[slot] = r; else slow_now = true;
+    }
+    // fast path: the read's planes slide over the reference words; one 64-bit load, two funnel shifts per word
+    const uint2* __restrict__ P = R.pairs + rec.pair_off;
+    const int q0 = (int)(rec.info & kInfoLeadMask) + (tile_lo + (w0 << 5) - rec.start);  // read base under bit 0 of word w0
+    int j = q0 >> 5;
+    const int sh = q0 & 31;
+    uint2 pa = make_uint2(0u, 0u), pb = make_uint2(0u, 0u);
+    if (fast) {
+      if (j >= 0) pa = __ldg(&P[j]);
+      pb = __ldg(&P[j + 1]);
+    }
+    const int nw = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)(fast ? w1 - w0 + 1 : 0));
+    for (int k = 0; k < nw; ++k) {
+      const int w = w0 + k;
+      const bool on = fast && w <= w1;
+      uint32_t x = 0, y = 0;
+      if (on) {
+        const int wbase = tile_lo + (w << 5);
+        const uint32_t valid = bit_range(rec.start - wbase, rec.end - wbase);
+        x = (__funnelshift_r(pa.x, pb.x, sh) ^ S.ref_lo[w]) & valid;
+        y = (__funnelshift_r(pa.y, pb.y, sh) ^ S.ref_hi[w]) & valid;
+        pa = pb;
+        if (w < w1) pb = __ldg(&P[j + 2]);
+        ++j;
+      }
+      count_bits<CntT>(S.cnt, on ? w : 0, x | y, x, y);
+    }
+    if (__any_sync(0xFFFFFFFFu, slow_now)) general_read(r, rec, slow_now, w0, w1);  // list overflow (very deep tiles)
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- phase 1b: the listed reads, one per thread again (full lanes on the slow path)
+  {
+    const uint32_t n_list = min(S.n_list, (uint32_t)kListCap);
+    for (uint32_t base = 0; base < n_list; base += kTileThreads) {
+      const uint32_t i = base + tid;
+      const bool active = i < n_list;
+      const uint32_t r = active ? S.list[i] : 0u;
+      ReadRec rec{0, 0, 0, 0};
+      int w0 = 0, w1 = -1;
+      if (active) {
+        rec = R.rec[r];
+        w0 = (max(rec.start, tile_lo) - tile_lo) >> 5;
+        w1 = (min(rec.end, tile_hi) - tile_lo - 1) >> 5;
+      }
+      general_read(r, rec, active, w0, w1);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: inclusive scan of the difference array(s) -> depth (and positive-strand depth); visited loci counted here
+  uint32_t n_visited = 0;
+  bool overflow = false;
+  for (int which = 0; which < (MODE == 1 ? 2 : 1); ++which) {
+    uint32_t* A = which == 0 ? S.cov : S.pos;
+    uint32_t run = 0;
+    const int base = tid * 33;  // 32 loci + 1 pad word per thread
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) run += A[base + k];
+    uint32_t incl = run;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if ((tid & 31) >= o) incl += t;
+    }
+    __syncthreads();
+    if ((tid & 31) == 31) S.warp_sum[tid >> 5] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int k = 0; k < (tid >> 5); ++k) before += S.warp_sum[k];
+    uint32_t acc = before + incl - run;
+    uint32_t covered = 0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      acc += A[base + k];
+      A[base + k] = acc;
+      if (which == 0) {
+        covered |= (acc != 0u ? 1u : 0u) << k;
+        overflow |= acc > FMASK;  // a counter field may have wrapped: the host reruns with wider fields
+      }
+    }
+    if (which == 0) {
+      const uint32_t in_range = bit_range(td.locus_begin - (tile_lo + (tid << 5)), td.locus_end - (tile_lo + (tid << 5)));
+      n_visited = __popc((prm.skip_empty ? covered : 0xFFFFFFFFu) & in_range);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: the caller, one locus per thread per step (stride kTileThreads: conflict-free shared memory)
+  const bool all_loci = MODE == 1 ? !prm.skip_empty : false;          // rows for empty pileups (counts mode only)
+  const bool every_covered = MODE == 1 || prm.emit_ref || prm.emit_no_call;
+  for (int x = tid; x < kTileLoci; x += kTileThreads) {
+    const CntT c = S.cnt[x];
+    const int w = x >> 5, b = x & 31;
+    const bool std_ref = (S.ref_std[w] >> b) & 1u;
+    if (c == 0 && std_ref && !every_covered) continue;  // every element matches the reference: nothing to call
+    const int locus = tile_lo + x;
+    if (locus < td.locus_begin || locus >= td.locus_end) continue;
+    const int total = (int)S.cov[cov_index(x)];
+    if (total == 0 && !all_loci) continue;  // callVariantsAtLocus returns nothing on an empty pileup
+    const int o = (int)((uint32_t)c & FMASK);
+    const int m1 = (int)((uint32_t)(c >> FB) & FMASK), m2 = (int)((uint32_t)(c >> (2 * FB)) & FMASK), m3 = (int)((uint32_t)(c >> (3 * FB)) & FMASK);
+    const int rcode = (int)(((S.ref_lo[w] >> b) & 1u) | (((S.ref_hi[w] >> b) & 1u) << 1));
     const uint8_t rbase = code_base(rcode);
     if (MODE == 1) {
-      if (!std_ref && (v + o) > 0) {
+      if (!std_ref && total > 0) {
         uint32_t s = (uint32_t)atomicAdd(&out.counters[2], 1ull);
         if (s < out.cap_slow) out.slow[s] = SlowLocus{td.contig, locus};
         continue;
       }
       uint32_t s = (uint32_t)atomicAdd(&out.counters[0], 1ull);
       if (s < out.cap_rec) {
-        guac_locus_counts c;
-        c.locus = locus;
-        c.contig = td.contig;
-        c.depth = v + o;
-        c.positive_depth = cP.at(b);
-        c.reference_depth = std_ref ? cnt[rcode] : 0;
-        c.base_count[0] = cnt[0]; c.base_count[1] = cnt[1]; c.base_count[2] = cnt[2]; c.base_count[3] = cnt[3];
-        c.other_count = o;
-        c.reference_base = std_ref ? rbase : (uint8_t)'N';
-        c.pad_[0] = c.pad_[1] = c.pad_[2] = 0;
-        out.crec[s] = c;
+        guac_locus_counts g;
+        g.locus = locus;
+        g.contig = td.contig;
+        g.depth = total;
+        g.positive_depth = (int)S.pos[cov_index(x)];
+        g.reference_depth = std_ref ? total - o - m1 - m2 - m3 : 0;
+        g.base_count[rcode] = total - o - m1 - m2 - m3;
+        g.base_count[rcode ^ 1] = m1;
+        g.base_count[rcode ^ 2] = m2;
+        g.base_count[rcode ^ 3] = m3;
+        g.other_count = o;
+        g.reference_base = std_ref ? rbase : (uint8_t)'N';
+        g.pad_[0] = g.pad_[1] = g.pad_[2] = 0;
+        out.crec[s] = g;
       }
       continue;
     }
     // ---- GermlineThreshold.Caller.callVariantsAtLocus on the SNV alleles -------------------------------------------------
-    const int total = v + o;
+    const int thr = prm.threshold_percent;
     // any allele made of "other" elements has count <= o: if o cannot pass the threshold the SNV counts decide alone
-    const bool exact = std_ref && !o_over && ((long long)o * 100 / total <= prm.threshold_percent);
+    const bool exact = std_ref && ((long long)o * 100 / total <= thr);
     if (!exact) {
       uint32_t s = (uint32_t)atomicAdd(&out.counters[2], 1ull);
       if (s < out.cap_slow) out.slow[s] = SlowLocus{td.contig, locus};
       continue;
     }
-    int n = 0, sc[4], sb[4];
+    const int mref = total - o - m1 - m2 - m3;
+    if (!every_covered && (long long)max(m1, max(m2, m3)) * 100 / total <= thr) continue;  // no alternate allele passes
+    // alleles in Allele.compare order (= base code order), stable-sorted by descending count: keep the best three
+    int c0 = -1, c1 = -1, c2 = -1, b0 = 0, b1 = 0, n = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (cnt[k] > 0 && (long long)cnt[k] * 100 / total > prm.threshold_percent) {
-        int j = n++;  // stable insertion sort: count descending, allele order (= base code order) ascending on ties
-        while (j > 0 && sc[j - 1] < cnt[k]) { sc[j] = sc[j - 1]; sb[j] = sb[j - 1]; --j; }
-        sc[j] = cnt[k];
-        sb[j] = k;
+    for (int code = 0; code < 4; ++code) {
+      const int cls = code ^ rcode;
+      const int cntv = cls == 0 ? mref : cls == 1 ? m1 : cls == 2 ? m2 : m3;
+      if (cntv > 0 && (long long)cntv * 100 / total > thr) {
+        ++n;
+        if (cntv > c0) { c2 = c1; c1 = c0; b1 = b0; c0 = cntv; b0 = code; }
+        else if (cntv > c1) { c2 = c1; c1 = cntv; b1 = code; }
+        else if (cntv > c2) { c2 = cntv; }
       }
-    const uint8_t tie = (n >= 3 && sc[1] == sc[2]) ? 1 : 0;
-    uint8_t e_alt[2], e_g0[2], e_g1[2];
-    bool e_sym[2];
-    int ne = 0;
-    auto emit = [&](int code, bool sym, uint8_t g0, uint8_t g1) { e_alt[ne] = code_base(code); e_sym[ne] = sym; e_g0[ne] = g0; e_g1[ne] = g1; ++ne; };
-    if (n == 0) {
-      if (prm.emit_no_call) emit(0, true, GUAC_GT_NO_CALL, GUAC_GT_NO_CALL);
-    } else if (n == 1) {
-      if (sb[0] == rcode) { if (prm.emit_ref) emit(0, true, GUAC_GT_REF, GUAC_GT_REF); }
-      else emit(sb[0], false, GUAC_GT_ALT, GUAC_GT_ALT);
-    } else {
-      const bool v1 = sb[0] != rcode, v2 = sb[1] != rcode;
-      if (v1 != v2) emit(v1 ? sb[0] : sb[1], false, GUAC_GT_REF, GUAC_GT_ALT);
-      else { emit(sb[0], false, GUAC_GT_ALT, GUAC_GT_OTHER_ALT); emit(sb[1], false, GUAC_GT_ALT, GUAC_GT_OTHER_ALT); }
     }
+    const uint8_t tie = (n >= 3 && c1 == c2) ? 1 : 0;
     if (tie) atomicAdd(&out.counters[4], 1ull);
+    int ne = 0;
+    uint8_t e_alt0 = 0, e_alt1 = 0, g0 = 0, g1 = 0;
+    bool sym = false;
+    if (n == 0) {
+      if (prm.emit_no_call) { ne = 1; sym = true; g0 = g1 = GUAC_GT_NO_CALL; }
+    } else if (n == 1) {
+      if (b0 == rcode) { if (prm.emit_ref) { ne = 1; sym = true; g0 = g1 = GUAC_GT_REF; } }
+      else { ne = 1; e_alt0 = code_base(b0); g0 = g1 = GUAC_GT_ALT; }
+    } else {
+      const bool v1 = b0 != rcode, v2 = b1 != rcode;
+      if (v1 != v2) { ne = 1; e_alt0 = code_base(v1 ? b0 : b1); g0 = GUAC_GT_REF; g1 = GUAC_GT_ALT; }
+      else { ne = 2; e_alt0 = code_base(b0); e_alt1 = code_base(b1); g0 = GUAC_GT_ALT; g1 = GUAC_GT_OTHER_ALT; }
+    }
     for (int k = 0; k < ne; ++k) {
       uint32_t s = (uint32_t)atomicAdd(&out.counters[0], 1ull);
       if (s < out.cap_rec) {
-        guac_threshold_record r;
-        r.start = locus;
-        r.contig = td.contig;
-        r.sample = prm.sample;
-        r.ref_off = kPoolByteOff + rbase;
-        r.ref_len = 1;
-        r.alt_off = e_sym[k] ? kPoolAltOff : kPoolByteOff + e_alt[k];
-        r.alt_len = e_sym[k] ? 5 : 1;
-        r.gt[0] = e_g0[k];
-        r.gt[1] = e_g1[k];
-        r.tie = tie;
-        r.pad_ = 0;
-        out.trec[s] = r;
+        guac_threshold_record rcd;
+        rcd.start = locus;
+        rcd.contig = td.contig;
+        rcd.sample = prm.sample;
+        rcd.ref_off = kPoolByteOff + rbase;
+        rcd.ref_len = 1;
+        rcd.alt_off = sym ? kPoolAltOff : kPoolByteOff + (k == 0 ? e_alt0 : e_alt1);
+        rcd.alt_len = sym ? 5 : 1;
+        rcd.gt[0] = g0;
+        rcd.gt[1] = g1;
+        rcd.tie = tie;
+        rcd.pad_ = 0;
+        out.trec[s] = rcd;
       }
     }
   }
+  // one atomic per warp for the visited-loci counter
+  for (int o = 16; o; o >>= 1) n_visited += __shfl_xor_sync(0xFFFFFFFFu, n_visited, o);
+  if ((tid & 31) == 0 && n_visited) atomicAdd(&out.counters[3], (unsigned long long)n_visited);
+  if (overflow) atomicAdd(&out.counters[5], 1ull);
 }
 
 // ---- the exact per-element walk ------------------------------------------------------------------------------------------
@@ -608,65 +639,112 @@ __device__ uint32_t pool_alloc(DevOut& out, uint32_t n) {
   return kPoolDynOff + o;
 }
 
-// ---- K_exact: thread per locus ------------------------------------------------------------------------------------------------
-__device__ void exact_locus(const DevReads& R, int contig, int locus, const CallParams& prm, DevOut& out);
+// ---- K_exact: one warp per locus --------------------------------------------------------------------------------------------
+constexpr int kExactWarps = 4;
 
-// grid-stride over the loci K_tile deferred; their number is read from the device counter (no host round trip)
-__global__ void __launch_bounds__(64) k_exact_loci(DevReads R, const SlowLocus* __restrict__ loci, CallParams prm, DevOut out) {
-  const uint32_t n_loci = (uint32_t)min(out.counters[2], (unsigned long long)out.cap_slow);
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_loci; t += gridDim.x * blockDim.x)
-    exact_locus(R, loci[t].contig, loci[t].locus, prm, out);
-}
-
-__device__ void exact_locus(const DevReads& R, const int contig, const int locus, const CallParams& prm, DevOut& out) {
+__device__ void exact_locus(const DevReads& R, const int contig, const int locus, const CallParams& prm, DevOut& out, AlleleEntry* tab) {
+  const int lane = threadIdx.x & 31;
   const ContigInfo ci = R.contigs[contig];
   bool std_ref;
   const uint8_t ref_base = reference_base_of(R, ci, contig, locus, &std_ref);
   AlleleView av{R, ref_base};
-  AlleleEntry tab[kMaxAlleles];
-  int na = 0, total = 0, pos_depth = 0, ref_depth = 0, other = 0;
+  int na = 0, total = 0, pos_depth = 0, ref_depth = 0;
   int bc[4] = {0, 0, 0, 0};
   const int g = locus >> kGranuleShift;
   const uint32_t first = R.gran_first[ci.gran_off + g], last = R.gran_last[ci.gran_off + g];
-  for (uint32_t r = first; r < last && first != 0xFFFFFFFFu; ++r) {
-    const ReadRec rec = R.rec[r];
-    if (rec.start > locus || rec.end <= locus) continue;
+  if (first == 0xFFFFFFFFu) return;
+  for (uint32_t base = first; base < last; base += 32) {
+    const uint32_t r = base + lane;
+    bool valid = r < last;
+    ReadRec rec{0, 0, 0, 0};
+    if (valid) {
+      rec = R.rec[r];
+      valid = rec.start <= locus && rec.end > locus;
+    }
     Elem e;
-    int rc = classify(R, r, locus, ref_base, e);
-    if (rc || e.kind == kNone) {
-      report_error(out.err, rc ? rc : GUAC_ERR_INVALID_CIGAR, r);
+    e.kind = kNone;
+    e.base = 0;
+    e.len = 0;
+    e.ptr = 0;
+    int rc = 0;
+    if (valid) {
+      rc = classify(R, r, locus, ref_base, e);
+      if (rc == 0 && e.kind == kNone) rc = GUAC_ERR_INVALID_CIGAR;
+    }
+    if (__any_sync(0xFFFFFFFFu, rc != 0)) {
+      if (rc) report_error(out.err, rc, r);
       return;
     }
-    ++total;
-    if (rec.info & kInfoPositive) ++pos_depth;
-    if (e.kind == kMatch) ++ref_depth;
-    if ((e.kind == kMatch || e.kind == kMismatch) && is_std_base(e.base)) ++bc[base_code(e.base)]; else ++other;
+    const bool snv = valid && (e.kind == kMatch || e.kind == kMismatch) && is_std_base(e.base);
+    if (valid) {
+      ++total;
+      if (rec.info & kInfoPositive) ++pos_depth;
+      if (e.kind == kMatch) ++ref_depth;
+      if (snv) ++bc[base_code(e.base)];
+    }
     if (prm.mode == 1) continue;
-    int k = 0;
-    for (; k < na; ++k)
-      if (av.same(tab[k], e)) { ++tab[k].count; break; }
-    if (k == na) {
-      if (na == kMaxAlleles) { report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus); return; }
-      tab[na].kind = (e.kind == kMatch || e.kind == kMismatch) ? 0 : e.kind;
-      tab[na].len = e.len;
-      tab[na].ptr = e.ptr;
-      tab[na].base = e.base;
-      tab[na].count = 1;
-      ++na;
+    // everything that is not an A/C/G/T match or mismatch goes through the allele table, one element at a time
+    uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid && !snv);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      Elem s;
+      s.kind = __shfl_sync(0xFFFFFFFFu, e.kind, src);
+      s.len = __shfl_sync(0xFFFFFFFFu, e.len, src);
+      s.base = (uint8_t)__shfl_sync(0xFFFFFFFFu, (int)e.base, src);
+      s.ptr = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(e.ptr >> 32), src) << 32) | __shfl_sync(0xFFFFFFFFu, (uint32_t)e.ptr, src);
+      s.qual = 0;
+      int found = -1;
+      if (lane == 0) {
+        for (int k = 0; k < na; ++k)
+          if (av.same(tab[k], s)) { found = k; break; }
+        if (found >= 0) ++tab[found].count;
+        else if (na < kMaxAlleles) {
+          tab[na].kind = (s.kind == kMatch || s.kind == kMismatch) ? 0 : s.kind;
+          tab[na].len = s.len;
+          tab[na].ptr = s.ptr;
+          tab[na].base = s.base;
+          tab[na].count = 1;
+        }
+      }
+      found = __shfl_sync(0xFFFFFFFFu, found, 0);
+      if (found < 0) {
+        if (na == kMaxAlleles) {
+          if (lane == 0) report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus);
+          return;
+        }
+        ++na;
+      }
+      __syncwarp();
     }
   }
-  if (total == 0) return;
+  for (int o = 16; o; o >>= 1) {
+    total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+    pos_depth += __shfl_xor_sync(0xFFFFFFFFu, pos_depth, o);
+    ref_depth += __shfl_xor_sync(0xFFFFFFFFu, ref_depth, o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bc[k] += __shfl_xor_sync(0xFFFFFFFFu, bc[k], o);
+  }
+  if (total == 0 || lane != 0) return;
   if (prm.mode == 1) {
     uint32_t s = (uint32_t)atomicAdd(&out.counters[0], 1ull);
     if (s < out.cap_rec) {
       guac_locus_counts c;
       c.locus = locus; c.contig = contig; c.depth = total; c.positive_depth = pos_depth; c.reference_depth = ref_depth;
       c.base_count[0] = bc[0]; c.base_count[1] = bc[1]; c.base_count[2] = bc[2]; c.base_count[3] = bc[3];
-      c.other_count = other; c.reference_base = ref_base; c.pad_[0] = c.pad_[1] = c.pad_[2] = 0;
+      c.other_count = total - bc[0] - bc[1] - bc[2] - bc[3]; c.reference_base = ref_base; c.pad_[0] = c.pad_[1] = c.pad_[2] = 0;
       out.crec[s] = c;
     }
     return;
   }
+  // the A/C/G/T match / mismatch alleles join the table from their counters
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (bc[k] > 0) {
+      if (na == kMaxAlleles) { report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus); return; }
+      tab[na].kind = 0; tab[na].len = 1; tab[na].ptr = 0; tab[na].base = code_base(k); tab[na].count = bc[k];
+      ++na;
+    }
   // counts.toList.filter(count * 100 / total > threshold).sortBy(-count)  — canonical pre-order: Allele.compare
   int idx[kMaxAlleles], n = 0;
   for (int k = 0; k < na; ++k)
@@ -725,6 +803,18 @@ __device__ void exact_locus(const DevReads& R, const int contig, const int locus
         report_error(out.err, GUAC_ERR_MULTIPLE_REFERENCE_BASES, ((unsigned long long)contig << 32) | (uint32_t)locus);
       }
     }
+  }
+}
+
+
+// grid-stride over the loci K_tile deferred; their number is read from the device counter (no host round trip)
+__global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, const SlowLocus* __restrict__ loci, CallParams prm, DevOut out) {
+  __shared__ AlleleEntry tabs[kExactWarps][kMaxAlleles];
+  const uint32_t n_loci = (uint32_t)min(out.counters[2], (unsigned long long)out.cap_slow);
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t t = warp; t < n_loci; t += n_warps) {
+    exact_locus(R, loci[t].contig, loci[t].locus, prm, out, tabs[threadIdx.x >> 5]);
+    __syncwarp();
   }
 }
 
