@@ -353,7 +353,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     else launch_tile<0>(wide, (int)ctx->n_tiles, st, R, d_tiles, prm, out);
     CUDA_OK(cudaEventRecord(ctx->ev[1], st));
     // K_exact reads the number of deferred loci from the device counter: no host round trip in between
-    k_exact_loci<<<ctx->sm_count * 4, kExactWarps * 32, 0, st>>>(R, out.slow, prm, out);
+    k_exact_loci<<<ctx->sm_count * 16, kExactWarps * 32, 0, st>>>(R, out.slow, prm, out);
     CUDA_OK(cudaEventRecord(ctx->ev[2], st));
     launches += 2;
     CUDA_OK(cudaGetLastError());

@@ -115,7 +115,7 @@ __device__ __noinline__ Aligned align_cigar(const DevReads& R, uint64_t r, const
 // Per-locus counter word: four fields of FB bits — [0] "other" elements, [1..3] mismatches by class (lo ^ ref_lo) |
 // (hi ^ ref_hi) << 1, i.e. read base code = reference code ^ class.  CntT = uint32_t (8-bit fields, pileups < 256 deep) or
 // uint64_t (16-bit fields, < 65536 deep).  Depth (and, in counts mode, positive-strand depth) come from difference arrays.
-constexpr int kTileThreads = 128;
+constexpr int kTileThreads = 256;              // 16 loci per thread in the scan / caller phases
 __host__ __device__ constexpr int cov_index(int i) { return i + (i >> 5); }  // one pad word per 32: conflict-free scan
 
 constexpr int kListCap = 1024;  // reads of one tile that need the CIGAR walk (kept in shared memory; overflow handled inline)
@@ -128,24 +128,23 @@ struct TileSmem {
   CntT cnt[kTileLoci];
   uint32_t list[kListCap];
   uint32_t warp_sum[kTileThreads / 32];
-  uint32_t first, last, n_list;
+  uint32_t first, last, n_list, next;
 };
 
-// one shared-memory atomic per set bit; the loop is warp-uniform so that the warp stays converged
+// one shared-memory atomic per set bit; lanes loop independently and the warp reconverges right after
 template <typename CntT>
-__device__ __forceinline__ void count_bits(CntT* cnt, int word_in_tile, uint32_t bits, uint32_t x, uint32_t y) {
+__device__ __forceinline__ void count_bits(CntT* cnt_word, uint32_t bits, uint32_t x, uint32_t y) {
   constexpr int FB = sizeof(CntT) * 2;
-  while (__any_sync(0xFFFFFFFFu, bits != 0)) {
-    if (bits) {
-      const int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const int cls = (int)((x >> b) & 1u) | ((int)((y >> b) & 1u) << 1);
-      if constexpr (sizeof(CntT) == 8)
-        atomicAdd(reinterpret_cast<unsigned long long*>(&cnt[(word_in_tile << 5) + b]), 1ull << (FB * cls));
-      else
-        atomicAdd(&cnt[(word_in_tile << 5) + b], (CntT)1 << (FB * cls));
-    }
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    const int sh = FB * ((int)((x >> b) & 1u) | ((int)((y >> b) & 1u) << 1));
+    if constexpr (sizeof(CntT) == 8)
+      atomicAdd(reinterpret_cast<unsigned long long*>(cnt_word + b), 1ull << sh);
+    else
+      atomicAdd(cnt_word + b, (CntT)1 << sh);
   }
+  __syncwarp();
 }
 
 template <typename CntT, int MODE>
@@ -166,7 +165,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     S.cov[i] = 0;
     if (MODE == 1) S.pos[i] = 0;
   }
-  {
+  if (tid < kTileWords) {
     const int w = td.word0 + tid;
     const bool in = w < ci.n_words;
     S.ref_lo[tid] = in ? R.trk_lo[ci.word_off + w] : 0u;
@@ -193,6 +192,8 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
   }
   __syncthreads();
   const uint32_t first = S.first, last = S.first == 0xFFFFFFFFu ? 0u : S.last;
+  if (tid == 0) S.next = first;
+  __syncthreads();
 
   // general path for one read (CIGAR walk / exception mask), one word at a time
   auto general_read = [&](uint32_t r, const ReadRec rec, bool active, int w0, int w1) {
@@ -217,16 +218,29 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
       }
       const int ws = (active && w <= w1) ? w : 0;
       const uint32_t x = (a.lo ^ S.ref_lo[ws]) & a.plain, y = (a.hi ^ S.ref_hi[ws]) & a.plain;
-      count_bits<CntT>(S.cnt, ws, x | y, x, y);
-      count_bits<CntT>(S.cnt, ws, a.other, 0u, 0u);
+      count_bits<CntT>(S.cnt + (ws << 5), x | y, x, y);
+      count_bits<CntT>(S.cnt + (ws << 5), a.other, 0u, 0u);
     }
   };
 
   // ---- phase 1a: one read per thread; SIMPLE reads take the fast path, the others are listed for phase 1b
-  for (uint32_t base = first; base < last; base += kTileThreads) {  // uniform trip count: the warp stays converged
-    const uint32_t r = base + tid;
-    ReadRec rec{0, 0, 0, 0};
-    if (r < last) rec = R.rec[r];
+  // Warps grab 32 reads at a time from a shared cursor (balances the warps ahead of the barrier) and fetch the records
+  // of their next batch before working on the current one.
+  const int lane = tid & 31;
+  auto grab = [&]() {
+    uint32_t b = 0;
+    if (lane == 0) b = atomicAdd(&S.next, 32u);
+    return __shfl_sync(0xFFFFFFFFu, b, 0);
+  };
+  uint32_t base = grab();
+  ReadRec rec_next{0, 0, 0, 0};
+  if (base + lane < last) rec_next = R.rec[base + lane];
+  while (base < last) {  // warp-uniform
+    const uint32_t r = base + lane;
+    const ReadRec rec = rec_next;
+    const uint32_t nbase = grab();
+    rec_next = ReadRec{0, 0, 0, 0};
+    if (nbase + lane < last) rec_next = R.rec[nbase + lane];
     const bool active = r < last && rec.end > tile_lo && rec.start < tile_hi && rec.end > rec.start;
     int w0 = 0, w1 = -1;
     if (active) {
@@ -247,33 +261,38 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
       if (slot < (uint32_t)kListCap) S.list[slot] = r; else slow_now = true;
     }
     // fast path: the read's planes slide over the reference words; one 64-bit load, two funnel shifts per word
-    const uint2* __restrict__ P = R.pairs + rec.pair_off;
     const int q0 = (int)(rec.info & kInfoLeadMask) + (tile_lo + (w0 << 5) - rec.start);  // read base under bit 0 of word w0
-    int j = q0 >> 5;
     const int sh = q0 & 31;
+    const uint2* __restrict__ P = R.pairs + rec.pair_off + (q0 >> 5);  // P[0] may sit one pair before the read (never loaded then)
     uint2 pa = make_uint2(0u, 0u), pb = make_uint2(0u, 0u);
     if (fast) {
-      if (j >= 0) pa = __ldg(&P[j]);
-      pb = __ldg(&P[j + 1]);
+      if (q0 >= 0) pa = __ldg(P);
+      pb = __ldg(P + 1);
     }
+    P += 2;
+    // bits of the first / last word that belong to the read
+    const uint32_t first_mask = bit_range(rec.start - (tile_lo + (w0 << 5)), 32);
+    const uint32_t last_mask = bit_range(0, rec.end - (tile_lo + (w1 << 5)));
     const int nw = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)(fast ? w1 - w0 + 1 : 0));
+    const uint32_t* ref_lo = S.ref_lo + w0;
+    CntT* cnt_word = S.cnt + (w0 << 5);
     for (int k = 0; k < nw; ++k) {
       const int w = w0 + k;
-      const bool on = fast && w <= w1;
       uint32_t x = 0, y = 0;
-      if (on) {
-        const int wbase = tile_lo + (w << 5);
-        const uint32_t valid = bit_range(rec.start - wbase, rec.end - wbase);
-        x = (__funnelshift_r(pa.x, pb.x, sh) ^ S.ref_lo[w]) & valid;
-        y = (__funnelshift_r(pa.y, pb.y, sh) ^ S.ref_hi[w]) & valid;
+      if (fast && w <= w1) {
+        uint32_t valid = k == 0 ? first_mask : 0xFFFFFFFFu;
+        if (w == w1) valid &= last_mask;
+        x = (__funnelshift_r(pa.x, pb.x, sh) ^ ref_lo[k]) & valid;
+        y = (__funnelshift_r(pa.y, pb.y, sh) ^ ref_lo[k + kTileWords]) & valid;  // ref_hi follows ref_lo in shared memory
         pa = pb;
-        if (w < w1) pb = __ldg(&P[j + 2]);
-        ++j;
+        if (w < w1) pb = __ldg(P);
+        ++P;
       }
-      count_bits<CntT>(S.cnt, on ? w : 0, x | y, x, y);
+      count_bits<CntT>(cnt_word + (k << 5), x | y, x, y);
     }
     if (__any_sync(0xFFFFFFFFu, slow_now)) general_read(r, rec, slow_now, w0, w1);  // list overflow (very deep tiles)
     __syncwarp();
+    base = nbase;
   }
   __syncthreads();
   // ---- phase 1b: the listed reads, one per thread again (full lanes on the slow path)
@@ -301,10 +320,11 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
   bool overflow = false;
   for (int which = 0; which < (MODE == 1 ? 2 : 1); ++which) {
     uint32_t* A = which == 0 ? S.cov : S.pos;
+    constexpr int LPT = kTileLoci / kTileThreads;  // loci per thread (16)
     uint32_t run = 0;
-    const int base = tid * 33;  // 32 loci + 1 pad word per thread
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) run += A[base + k];
+    const int base = cov_index(tid * LPT);
+#pragma unroll
+    for (int k = 0; k < LPT; ++k) run += A[base + k];
     uint32_t incl = run;
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -317,8 +337,8 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     for (int k = 0; k < (tid >> 5); ++k) before += S.warp_sum[k];
     uint32_t acc = before + incl - run;
     uint32_t covered = 0;
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
+#pragma unroll
+    for (int k = 0; k < LPT; ++k) {
       acc += A[base + k];
       A[base + k] = acc;
       if (which == 0) {
@@ -327,7 +347,8 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
       }
     }
     if (which == 0) {
-      const uint32_t in_range = bit_range(td.locus_begin - (tile_lo + (tid << 5)), td.locus_end - (tile_lo + (tid << 5)));
+      const int l0 = tile_lo + tid * LPT;
+      const uint32_t in_range = bit_range(td.locus_begin - l0, min(td.locus_end - l0, LPT));
       n_visited = __popc((prm.skip_empty ? covered : 0xFFFFFFFFu) & in_range);
     }
   }
@@ -375,23 +396,25 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
       continue;
     }
     // ---- GermlineThreshold.Caller.callVariantsAtLocus on the SNV alleles -------------------------------------------------
-    const int thr = prm.threshold_percent;
+    // count * 100 / total > threshold  <=>  count * 100 >= (threshold + 1) * total   (integers, no division)
+    const long long bar = (long long)(prm.threshold_percent + 1) * total;
+    auto passes = [&](int count) { return (long long)count * 100 >= bar; };
     // any allele made of "other" elements has count <= o: if o cannot pass the threshold the SNV counts decide alone
-    const bool exact = std_ref && ((long long)o * 100 / total <= thr);
+    const bool exact = std_ref && !passes(o);
     if (!exact) {
       uint32_t s = (uint32_t)atomicAdd(&out.counters[2], 1ull);
       if (s < out.cap_slow) out.slow[s] = SlowLocus{td.contig, locus};
       continue;
     }
     const int mref = total - o - m1 - m2 - m3;
-    if (!every_covered && (long long)max(m1, max(m2, m3)) * 100 / total <= thr) continue;  // no alternate allele passes
+    if (!every_covered && !passes(max(m1, max(m2, m3)))) continue;  // no alternate allele passes
     // alleles in Allele.compare order (= base code order), stable-sorted by descending count: keep the best three
     int c0 = -1, c1 = -1, c2 = -1, b0 = 0, b1 = 0, n = 0;
 #pragma unroll
     for (int code = 0; code < 4; ++code) {
       const int cls = code ^ rcode;
       const int cntv = cls == 0 ? mref : cls == 1 ? m1 : cls == 2 ? m2 : m3;
-      if (cntv > 0 && (long long)cntv * 100 / total > thr) {
+      if (cntv > 0 && passes(cntv)) {
         ++n;
         if (cntv > c0) { c2 = c1; c1 = c0; b1 = b0; c0 = cntv; b0 = code; }
         else if (cntv > c1) { c2 = c1; c1 = cntv; b1 = code; }

@@ -1,7 +1,7 @@
 // guac_synth.cpp — deterministic synthetic read generator for the benchmark shapes of BASELINE.json (host code, no CUDA).
 //
 // Produces a guac_read_batch (include/guac.h) of start-sorted mapped reads with consistent CIGAR + MD tags:
-//   reference   counter-hashed i.i.d. ACGT, one 100-base N run per 100 kb (0.1 %)
+//   reference   counter-hashed i.i.d. ACGT, one 100-base N run per 100 kb (0.1 %); like an aligner, no read is placed on one
 //   germline    one SNV per 1,000 loci (2/3 het, 1/3 hom), one 1-10 bp indel per 10,000 loci (het)
 //   somatic     tumor sample only: one SNV per 100,000 loci at VAF U(0.1, 0.5)
 //   reads       fixed length; 78 % all-M, 20 % one soft clip of 5-50 bases, 0.9 % one insertion, 0.9 % one deletion,
@@ -293,10 +293,24 @@ int guac_synth_generate(const guac_synth_params* P, guac_synth_batch** out) {
     for (uint32_t c = 0; c < P->n_contigs; ++c) {
       Rng rng(h2(P->seed ^ 0xABCDEFull, c + 977ull * (uint64_t)P->sample));
       const uint64_t span = (uint64_t)(hi[c] - lo[c]);
+      Genome Gc{P->seed, P->sample};
       for (uint64_t i = first[c]; i < first[c + 1]; ++i) {
-        B->start[i] = lo[c] + (int64_t)(rng.next() % std::max<uint64_t>(span, 1));
+        // aligners place no reads inside the reference's N runs: redraw starts whose read would touch one
+        int64_t st = 0;
+        for (int tries = 0; tries < 16; ++tries) {
+          st = lo[c] + (int64_t)(rng.next() % std::max<uint64_t>(span, 1));
+          const int64_t blk0 = st / 100000, blk1 = (st + P->read_length + 40) / 100000;
+          bool hit = false;
+          for (int64_t blk = blk0; blk <= blk1 && !hit; ++blk) {
+            const int64_t n0 = blk * 100000 + (int64_t)(h3(P->seed, 0x4E00 + c, (uint64_t)blk) % 99900);
+            hit = st < n0 + 100 && st + P->read_length + 40 > n0;
+          }
+          if (!hit) break;
+        }
+        B->start[i] = st;
         B->contig[i] = (int32_t)c;
       }
+      (void)Gc;
       std::sort(B->start.begin() + first[c], B->start.begin() + first[c + 1]);
     }
     int nt = P->n_threads > 0 ? P->n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
