@@ -89,6 +89,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     if (b->contig_length && end > b->contig_length[c]) fail(GUAC_ERR_INVALID_ARGUMENT, "read %llu ends past its contig", (unsigned long long)i);
     if (simple && lead > 0xFFFF) simple = false;
     contig_end[c] = std::max(contig_end[c], end);
+    out.max_ref_span = std::max<int64_t>(out.max_ref_span, ref_len);
     uint32_t info = (uint32_t)(simple ? (lead & 0xFFFF) : 0) | (simple ? kInfoSimple : 0) |
                     ((b->flags[i] & GUAC_READ_POSITIVE_STRAND) ? kInfoPositive : 0) | (ref_len == 0 ? kInfoEmpty : 0) |
                     ((uint32_t)b->mapq[i] << kInfoMapqShift);

@@ -152,6 +152,7 @@ struct guac_reads {
   DevBuf<ContigInfo> d_contigs;
   uint64_t order_sensitive_loci = 0;
   uint64_t max_reads_per_granule = 0;
+  int64_t max_ref_span = 0;  // longest reference span of a read (look-back of the start-sorted binary searches)
   uint64_t total_words = 0, total_grans = 0;
   double pack_kernel_ms = 0;
   int pack_launches = 0;

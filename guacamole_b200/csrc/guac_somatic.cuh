@@ -1,9 +1,797 @@
-// guac_somatic.cuh — somatic-standard caller (placeholder until the kernels land)
+// guac_somatic.cuh — somatic-standard caller: tumor / normal genotype likelihoods per locus, fused with the pileup.
+//
+//   PileupFilter.apply (mapq >= min, optional multi-allelic)              filters/PileupFilter.scala:69-89
+//   Likelihood.likelihoodsOfAllPossibleGenotypesFromPileup / OfGenotypes   likelihood/Likelihood.scala:99-113, 149-201
+//   SomaticStandard.Caller.findPotentialVariantAtLocus                     commands/SomaticStandardCaller.scala:162-245
+//   AlleleEvidence.apply                                                   variants/AlleleEvidence.scala:58-101
+//
+// K_somatic       one warp per 32 loci, lane = locus (gather): both samples' overlapping reads are walked in lockstep by the
+//                 warp (record loads are broadcast, base-quality loads are coalesced: consecutive lanes = consecutive bases
+//                 of the same read).  Every element adds table values log(s + s), log((1-s) + (1-s)) into per-allele fp64
+//                 sums; loci whose elements are all A/C/G/T matches / mismatches are decided right there.
+// K_somatic_exact one warp per locus holding an insertion / deletion / clipped / non-ACGT element: literal per-element walk
+//                 with a small allele table.
+// K_evidence      one warp per emitted record: AlleleEvidence of both samples (depths, strand depths, mean / median MQ, BQ,
+//                 median mismatches).
+//
+// With P[a][e] = s_e if element e carries allele a else 1 - s_e, the reference's
+//   logL(a1, a2) = sum_e log(P[a1][e] + P[a2][e]) - log(2) * depth
+// depends only on per-allele sums:  S1[a] = sum_{e in a} log(s + s),  S0[a] = sum_{e in a} log((1-s) + (1-s)),
+// T0 = sum_all log((1-s) + (1-s)):   hom(a) = S1[a] + T0 - S0[a],  het(a, b) = T0 - S0[a] - S0[b]  (+ sum log(s + (1-s)),
+// which is 0 up to one ulp per element).  Summation order differs from colt's last-to-first walk: results agree with the
+// reference to ~1e-13 relative, inside the 1e-9 tolerance the north star states.
 #pragma once
+
 #include "guac_host.cuh"
-namespace {
-void somatic_init_tables(guac_ctx*) {}
-void run_somatic(guac_ctx*, const guac_reads&, const guac_reads&, const guac_locus_range*, size_t, const guac_somatic_params&, guac_result&) {
-  fail(GUAC_ERR_UNSUPPORTED, "somatic-standard kernels not built yet");
+#include "guac_pileup.cuh"
+
+namespace guac {
+
+constexpr int kSomMaxAlleles = 10;                                           // alleles entering the genotype enumeration
+constexpr int kSomMaxGenotypes = kSomMaxAlleles * (kSomMaxAlleles + 1) / 2;
+constexpr int kSomTab = 24;                                                  // distinct alleles kept per sample and locus
+
+// d_tables layout (doubles): succ[256] | nl1[256] nl0[256] | tl1[256][256] tl0[256][256]   (index [mapq][quality])
+constexpr int kTabSucc = 0, kTabNl1 = 256, kTabNl0 = 512, kTabTl1 = 768, kTabTl0 = 768 + 65536, kTabTotal = 768 + 2 * 65536;
+
+struct SomParams {
+  int32_t odds_threshold, min_mapq, filter_multi_allelic, max_read_depth, skip_empty, tumor_sample;
+};
+
+struct SomOut {
+  guac_somatic_record* rec;
+  uint32_t cap_rec;
+  uint8_t* pool;
+  uint32_t cap_pool;
+  SlowLocus* slow;
+  uint32_t cap_slow;
+  unsigned long long* counters;  // [0] records [1] pool bytes [2] slow loci [3] visited loci
+  DevError* err;
+};
+
+// ---- scala.math.round(Double).toInt and ADAM PhredUtils.successProbabilityToPhred (see oracle/guac_oracle.cpp) ------------
+__device__ inline int java_round_to_int(double x) {
+  long long r;
+  if (isnan(x)) r = 0;
+  else {
+    double f = floor(x + 0.5);
+    if (f >= 9.2233720368547758e18) r = 0x7FFFFFFFFFFFFFFFll;
+    else if (f <= -9.2233720368547758e18) r = (long long)0x8000000000000000ull;
+    else r = (long long)f;
+  }
+  return (int)(unsigned int)(unsigned long long)r;
 }
+__device__ inline int success_probability_to_phred(double p) { return java_round_to_int(-10.0 * log10(1.0 - p)); }
+
+// ---- per-sample allele statistics at one locus -------------------------------------------------------------------------------
+struct SomAllele {
+  int kind;      // AlleleEntry kinds: 0 SNV, 2 insertion, 3 deletion, 4 mid-deletion, 5 clipped
+  int len;
+  uint64_t ptr;
+  uint8_t base;
+  int count;
+  double s1, s0;
+};
+
+struct SampleStats {
+  int depth;      // filtered elements
+  int ref_depth;  // Match elements among them
+  int n_alleles;  // entries in tab (all distinct alleles of the filtered pileup)
+  int distinct_unfiltered;  // distinct alleles before the mapq filter (multi-allelic filter), capped
+  double t0;
+};
+
+__device__ inline AlleleEntry as_entry(const SomAllele& a) {
+  AlleleEntry e;
+  e.kind = a.kind; e.len = a.len; e.ptr = a.ptr; e.base = a.base; e.count = a.count;
+  return e;
+}
+
+// Likelihood.likelihoodsOfAllPossibleGenotypesFromPileup(pileup, probabilityCorrect, normalize = true), plain probabilities.
+// tab[0..n) must be sorted by Allele.compare.  Returns the number of genotypes; lk[] in the reference's (i <= j) order.
+__device__ int genotype_likelihoods(const AlleleView& av, const SomAllele* tab, int n_tab, const SampleStats& st, int* gi, int* gj,
+                                    double* lk) {
+  int idx[kSomMaxAlleles], n = 0;
+  for (int k = 0; k < n_tab; ++k) {  // alleles whose alternate bases are all standard (an empty alternate passes)
+    const AlleleEntry e = as_entry(tab[k]);
+    bool ok = true;
+    const int al = av.alt_len(e);
+    for (int i = 0; i < al && ok; ++i) ok = is_std_base(av.alt_at(e, i));
+    if (ok) {
+      if (n == kSomMaxAlleles) return -1;
+      idx[n++] = k;
+    }
+  }
+  int ng = 0;
+  const double nlog2 = log(2.0) * (double)st.depth;
+  for (int i = 0; i < n; ++i)
+    for (int j = i; j < n; ++j) {
+      const SomAllele& a = tab[idx[i]];
+      const SomAllele& b = tab[idx[j]];
+      const double agg = (i == j) ? (a.s1 + (st.t0 - a.s0)) : (st.t0 - a.s0 - b.s0);
+      gi[ng] = idx[i];
+      gj[ng] = idx[j];
+      lk[ng] = agg + 0.0 - nlog2;
+      ++ng;
+    }
+  double total = 0.0;
+  for (int g = 0; g < ng; ++g) total += exp(lk[g]);
+  const double log_total = log(total);  // naive normalisation on purpose: Inf / NaN flow like the reference
+  for (int g = 0; g < ng; ++g) lk[g] = exp(lk[g] - log_total);
+  return ng;
+}
+
+// findPotentialVariantAtLocus once both filtered pileups are summarised.  tabT / tabN sorted by Allele.compare.
+__device__ void decide_somatic(const DevReads& RT, const AlleleView& avT, const AlleleView& avN, const SomAllele* tabT,
+                               const SampleStats& sT, const SomAllele* tabN, const SampleStats& sN, int contig, int locus,
+                               const SomParams& prm, SomOut& out) {
+  if (sT.depth == 0 || sN.depth == 0 || sT.depth > prm.max_read_depth || sN.depth > prm.max_read_depth || sT.ref_depth == sT.depth) return;
+  int gi[kSomMaxGenotypes], gj[kSomMaxGenotypes];
+  double lk[kSomMaxGenotypes];
+  const int ng = genotype_likelihoods(avT, tabT, sT.n_alleles, sT, gi, gj, lk);
+  if (ng < 0) { report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus); return; }
+  if (ng == 0) return;
+  int best = 0;  // maxBy = reduceLeft((x, y) => if (f(x) >= f(y)) x else y)
+  for (int g = 1; g < ng; ++g)
+    if (!(lk[best] >= lk[g])) best = g;
+  const AlleleEntry a1 = as_entry(tabT[gi[best]]), a2 = as_entry(tabT[gj[best]]);
+  const bool v1 = avT.is_variant(a1), v2 = avT.is_variant(a2);
+  if (!v1 && !v2) return;
+  const double tumor_l = lk[best];
+  const int ngn = genotype_likelihoods(avN, tabN, sN.n_alleles, sN, gi, gj, lk);
+  if (ngn < 0) { report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus); return; }
+  double normal_variants_total = 0.0;
+  for (int g = 0; g < ngn; ++g)
+    if (avN.is_variant(as_entry(tabN[gi[g]])) || avN.is_variant(as_entry(tabN[gj[g]]))) normal_variants_total += lk[g];
+  const double somatic_odds = tumor_l / normal_variants_total;
+  if (!(somatic_odds * 100 >= (double)prm.odds_threshold)) return;
+  // first non-reference allele of the genotype whose alternate is not empty
+  const AlleleEntry* allele = nullptr;
+  if (v1 && !avT.alt_empty(a1)) allele = &a1;
+  else if (v2 && !avT.alt_empty(a2)) allele = &a2;
+  if (!allele) return;
+  guac_somatic_record r;
+  memset(&r, 0, sizeof r);
+  r.start = locus;
+  r.contig = contig;
+  r.sample = prm.tumor_sample;
+  const int rl = avT.ref_len(*allele), al = avT.alt_len(*allele);
+  const uint32_t o = kPoolDynOff + (uint32_t)atomicAdd(&out.counters[1], (unsigned long long)(rl + al));
+  if ((unsigned long long)o + rl + al <= out.cap_pool) {
+    for (int i = 0; i < rl; ++i) out.pool[o + i] = avT.ref_at(*allele, i);
+    for (int i = 0; i < al; ++i) out.pool[o + rl + i] = avT.alt_at(*allele, i);
+  }
+  r.ref_off = o;
+  r.ref_len = (uint16_t)rl;
+  r.alt_off = o + rl;
+  r.alt_len = (uint16_t)al;
+  r.somatic_log_odds = log(somatic_odds);
+  r.tumor.likelihood = tumor_l;
+  r.normal.likelihood = 1 - normal_variants_total;
+  r.phred_scaled_somatic_likelihood = success_probability_to_phred(r.tumor.likelihood * r.normal.likelihood - 1e-10);
+  (void)RT;
+  const uint32_t s = (uint32_t)atomicAdd(&out.counters[0], 1ull);
+  if (s < out.cap_rec) out.rec[s] = r;
+}
+
+// sort a small allele table by Allele.compare (insertion sort)
+__device__ void sort_alleles(const AlleleView& av, SomAllele* tab, int n) {
+  for (int i = 1; i < n; ++i) {
+    SomAllele x = tab[i];
+    int j = i;
+    while (j > 0 && av.compare(as_entry(tab[j - 1]), as_entry(x)) > 0) {
+      tab[j] = tab[j - 1];
+      --j;
+    }
+    tab[j] = x;
+  }
+}
+
+__device__ inline int lower_bound_start(const ReadRec* rec, uint64_t lo, uint64_t hi, int value) {  // first i with start >= value
+  while (lo < hi) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (rec[mid].start >= value) hi = mid; else lo = mid + 1;
+  }
+  return (int)lo;
+}
+
+// ---- K_somatic: warp per 32 loci, lane per locus ---------------------------------------------------------------------------------
+struct LaneAcc {
+  int depth, ref_depth, other;   // filtered depth, Match elements, elements that are not A/C/G/T matches / mismatches
+  int any;                       // overlapping reads before any filter (decides whether the locus is visited)
+  int cnt[4];                    // filtered elements by base code
+  uint32_t seen;                 // base codes seen before the mapq filter (multi-allelic filter)
+  double t0, s1[4], s0[4];
+};
+
+__device__ __forceinline__ void acc_clear(LaneAcc& a) {
+  a.depth = a.ref_depth = a.other = a.any = 0;
+  a.seen = 0;
+  a.t0 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { a.cnt[k] = 0; a.s1[k] = 0.0; a.s0[k] = 0.0; }
+}
+
+template <bool TUMOR>
+__device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x, int rcode, bool std_ref, int max_span,
+                              const SomParams& prm, const double* __restrict__ tables, LaneAcc& A) {
+  const int lane = threadIdx.x & 31;
+  const ContigInfo ci = R.contigs[contig];
+  acc_clear(A);
+  if (ci.read_end == ci.read_begin) return;
+  const int lower = lower_bound_start(R.rec, ci.read_begin, ci.read_end, span_lo - max_span + 1);
+  const int upper = lower_bound_start(R.rec, ci.read_begin, ci.read_end, span_lo + 32);
+  const double* l1_tab = tables + (TUMOR ? kTabTl1 : kTabNl1);
+  const double* l0_tab = tables + (TUMOR ? kTabTl0 : kTabNl0);
+  const uint8_t ref_base = std_ref ? code_base(rcode) : (uint8_t)'N';
+  for (int base = lower; base < upper; base += 32) {
+    const int mine = base + lane;
+    ReadRec my{0, 0, 0, 0};
+    uint64_t my_seq_off = 0;
+    if (mine < upper) {
+      my = R.rec[mine];
+      my_seq_off = R.seq_off[mine];
+    }
+    const int n_here = min(32, upper - base);
+    for (int j = 0; j < n_here; ++j) {
+      ReadRec rec;
+      rec.start = __shfl_sync(0xFFFFFFFFu, my.start, j);
+      rec.end = __shfl_sync(0xFFFFFFFFu, my.end, j);
+      if (rec.end <= span_lo) continue;  // warp-uniform
+      rec.pair_off = __shfl_sync(0xFFFFFFFFu, my.pair_off, j);
+      rec.info = __shfl_sync(0xFFFFFFFFu, my.info, j);
+      const uint64_t seq_off = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(my_seq_off >> 32), j) << 32) |
+                               __shfl_sync(0xFFFFFFFFu, (uint32_t)my_seq_off, j);
+      const int mapq = (int)(rec.info >> kInfoMapqShift);
+      const bool keep = !(prm.min_mapq > 0) || mapq >= prm.min_mapq;
+      const bool inside = rec.start <= x && x < rec.end;
+      A.any += inside ? 1 : 0;
+      if (!keep && !prm.filter_multi_allelic) continue;  // warp-uniform
+      int code = -1, q = 0;
+      bool other = false, match = false;
+      if ((rec.info & (kInfoSimple | kInfoHasExc)) == kInfoSimple) {
+        if (inside) {
+          const int idx = (int)(rec.info & kInfoLeadMask) + (x - rec.start);
+          const uint2 pw = __ldg(&R.pairs[rec.pair_off + (idx >> 5)]);
+          code = (int)((pw.x >> (idx & 31)) & 1u) | ((int)((pw.y >> (idx & 31)) & 1u) << 1);
+          q = (int)R.qual[seq_off + idx];
+          match = std_ref && code == rcode;
+        }
+      } else if (inside) {
+        Elem e;
+        const int rc = classify(R, (uint64_t)(base + j), x, ref_base, e);
+        if (rc || e.kind == kNone) other = true;  // the exact kernel reports the error
+        else if ((e.kind == kMatch || e.kind == kMismatch) && is_std_base(e.base)) {
+          code = (int)base_code(e.base);
+          q = e.qual;
+          match = e.kind == kMatch;
+        } else other = true;
+      }
+      if (!inside) continue;
+      if (other) { A.other += 1; continue; }
+      A.seen |= 1u << code;
+      if (!keep) continue;
+      const int ti = TUMOR ? (mapq << 8) + q : q;
+      const double l1 = l1_tab[ti], l0 = l0_tab[ti];
+      A.depth += 1;
+      A.ref_depth += match ? 1 : 0;
+      A.t0 += l0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool is = code == k;
+        A.cnt[k] += is ? 1 : 0;
+        A.s1[k] += is ? l1 : 0.0;
+        A.s0[k] += is ? l0 : 0.0;
+      }
+    }
+  }
+}
+
+__device__ inline int lane_table(const LaneAcc& A, int rcode, SomAllele* tab, SampleStats& st) {
+  // SNV alleles share the reference base, so Allele.compare order is base-code order
+  int n = 0;
+  (void)rcode;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (A.cnt[k] > 0) {
+      tab[n].kind = 0; tab[n].len = 1; tab[n].ptr = 0; tab[n].base = code_base(k); tab[n].count = A.cnt[k];
+      tab[n].s1 = A.s1[k]; tab[n].s0 = A.s0[k];
+      ++n;
+    }
+  st.depth = A.depth;
+  st.ref_depth = A.ref_depth;
+  st.n_alleles = n;
+  st.distinct_unfiltered = __popc(A.seen);
+  st.t0 = A.t0;
+  return n;
+}
+
+constexpr int kSomThreads = 256;
+
+__global__ void __launch_bounds__(kSomThreads) k_somatic(DevReads RT, DevReads RN, const TileDesc* __restrict__ tiles, SomParams prm,
+                                                        const double* __restrict__ tables, int max_span_t, int max_span_n, SomOut out) {
+  const TileDesc td = tiles[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const ContigInfo ciT = RT.contigs[td.contig], ciN = RN.contigs[td.contig];
+  uint32_t n_visited = 0;
+  for (int wi = warp; wi < kTileWords; wi += kSomThreads / 32) {
+    const int w = td.word0 + wi;
+    const int span_lo = w << 5, x = span_lo + lane;
+    if (span_lo >= td.locus_end || span_lo + 32 <= td.locus_begin) continue;
+    const bool in_req = x >= td.locus_begin && x < td.locus_end;
+    // each sample has its own MD-derived reference track (its pileup's referenceBase comes from its own reads)
+    uint32_t tl = 0, th = 0, ts = 0, nl = 0, nh = 0, ns = 0;
+    if (w < ciT.n_words) { tl = RT.trk_lo[ciT.word_off + w]; th = RT.trk_hi[ciT.word_off + w]; ts = RT.trk_std[ciT.word_off + w]; }
+    if (w < ciN.n_words) { nl = RN.trk_lo[ciN.word_off + w]; nh = RN.trk_hi[ciN.word_off + w]; ns = RN.trk_std[ciN.word_off + w]; }
+    const int rcT = (int)((tl >> lane) & 1u) | ((int)((th >> lane) & 1u) << 1), rcN = (int)((nl >> lane) & 1u) | ((int)((nh >> lane) & 1u) << 1);
+    const bool stdT = (ts >> lane) & 1u, stdN = (ns >> lane) & 1u;
+    LaneAcc AT, AN;
+    gather_sample<true>(RT, td.contig, span_lo, x, rcT, stdT, max_span_t, prm, tables, AT);
+    gather_sample<false>(RN, td.contig, span_lo, x, rcN, stdN, max_span_n, prm, tables, AN);
+    if (!in_req) continue;
+    const int covT = AT.depth + AT.other, covN = AN.depth + AN.other;  // (filtered when no multi-allelic filter is on)
+    if (AT.any + AN.any > 0 || !prm.skip_empty) ++n_visited;
+    if (covT == 0 || covN == 0) continue;
+    // anything but A/C/G/T matches / mismatches over a standard reference base goes to the exact kernel
+    const bool exact_needed = AT.other > 0 || AN.other > 0 || !stdT || !stdN || prm.filter_multi_allelic;
+    if (exact_needed) {
+      if (AT.ref_depth == AT.depth && AT.other == 0 && stdT && !prm.filter_multi_allelic) continue;  // tumor all-Match: early out either way
+      const uint32_t s = (uint32_t)atomicAdd(&out.counters[2], 1ull);
+      if (s < out.cap_slow) out.slow[s] = SlowLocus{td.contig, x};
+      continue;
+    }
+    if (AT.ref_depth == AT.depth) continue;
+    SomAllele tabT[4], tabN[4];
+    SampleStats sT, sN;
+    lane_table(AT, rcT, tabT, sT);
+    lane_table(AN, rcN, tabN, sN);
+    AlleleView avT{RT, code_base(rcT)}, avN{RN, code_base(rcN)};
+    decide_somatic(RT, avT, avN, tabT, sT, tabN, sN, td.contig, x, prm, out);
+  }
+  for (int o = 16; o; o >>= 1) n_visited += __shfl_xor_sync(0xFFFFFFFFu, n_visited, o);
+  if (lane == 0 && n_visited) atomicAdd(&out.counters[3], (unsigned long long)n_visited);
+}
+
+// ---- K_somatic_exact: warp per locus ----------------------------------------------------------------------------------------------
+struct ExactSmem {
+  SomAllele tab[2][kSomTab];
+};
+
+template <bool TUMOR>
+__device__ bool exact_sample(const DevReads& R, int contig, int locus, const SomParams& prm, const double* __restrict__ tables,
+                             SomAllele* tab, SampleStats& st, uint8_t* ref_base_out, DevError* err) {
+  const int lane = threadIdx.x & 31;
+  const ContigInfo ci = R.contigs[contig];
+  bool std_ref = false;
+  uint8_t ref_base = 'N';
+  if (locus < ci.length) ref_base = reference_base_of(R, ci, contig, locus, &std_ref);
+  *ref_base_out = ref_base;
+  AlleleView av{R, ref_base};
+  int na = 0, n_unf = 0;  // table entries; entries [0, na) carry filtered sums, distinct_unfiltered counts all alleles seen
+  int depth = 0, ref_depth = 0;
+  double t0 = 0.0, s1c[4] = {0, 0, 0, 0}, s0c[4] = {0, 0, 0, 0};
+  int cntc[4] = {0, 0, 0, 0};
+  uint32_t seen = 0;
+  const double* l1_tab = tables + (TUMOR ? kTabTl1 : kTabNl1);
+  const double* l0_tab = tables + (TUMOR ? kTabTl0 : kTabNl0);
+  uint32_t first = 0xFFFFFFFFu, last = 0;
+  if (locus < ci.length) {
+    const int g = locus >> kGranuleShift;
+    first = R.gran_first[ci.gran_off + g];
+    last = R.gran_last[ci.gran_off + g];
+  }
+  for (uint32_t base = first; base < last && first != 0xFFFFFFFFu; base += 32) {
+    const uint32_t r = base + lane;
+    bool valid = r < last;
+    ReadRec rec{0, 0, 0, 0};
+    if (valid) {
+      rec = R.rec[r];
+      valid = rec.start <= locus && rec.end > locus;
+    }
+    const int mapq = (int)(rec.info >> kInfoMapqShift);
+    const bool keep = valid && (!(prm.min_mapq > 0) || mapq >= prm.min_mapq);
+    Elem e;
+    e.kind = kNone; e.base = 0; e.len = 0; e.ptr = 0; e.qual = 0;
+    int rc = 0;
+    if (valid && (keep || prm.filter_multi_allelic)) {
+      rc = classify(R, r, locus, ref_base, e);
+      if (rc == 0 && e.kind == kNone) rc = GUAC_ERR_INVALID_CIGAR;
+    }
+    if (__any_sync(0xFFFFFFFFu, rc != 0)) {
+      if (rc) report_error(err, rc, r);
+      return false;
+    }
+    const bool have = e.kind != kNone;
+    const bool snv = have && (e.kind == kMatch || e.kind == kMismatch) && is_std_base(e.base);
+    double l1 = 0.0, l0 = 0.0;
+    if (have && keep) {
+      const int q = e.qual & 255;
+      const int ti = TUMOR ? (mapq << 8) + q : q;
+      l1 = l1_tab[ti];
+      l0 = l0_tab[ti];
+      depth += 1;
+      ref_depth += e.kind == kMatch ? 1 : 0;
+      t0 += l0;
+    }
+    if (snv) {
+      const int code = (int)base_code(e.base);
+      seen |= 1u << code;
+      if (keep) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool is = code == k;
+          cntc[k] += is ? 1 : 0;
+          s1c[k] += is ? l1 : 0.0;
+          s0c[k] += is ? l0 : 0.0;
+        }
+      }
+    }
+    uint32_t mask = __ballot_sync(0xFFFFFFFFu, have && !snv);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      Elem s;
+      s.kind = __shfl_sync(0xFFFFFFFFu, e.kind, src);
+      s.len = __shfl_sync(0xFFFFFFFFu, e.len, src);
+      s.base = (uint8_t)__shfl_sync(0xFFFFFFFFu, (int)e.base, src);
+      s.ptr = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(e.ptr >> 32), src) << 32) | __shfl_sync(0xFFFFFFFFu, (uint32_t)e.ptr, src);
+      s.qual = 0;
+      const bool s_keep = __shfl_sync(0xFFFFFFFFu, (int)keep, src) != 0;
+      const double sl1 = __shfl_sync(0xFFFFFFFFu, l1, src), sl0 = __shfl_sync(0xFFFFFFFFu, l0, src);
+      int status = 0;  // 0 updated, 1 inserted, 2 table full
+      if (lane == 0) {
+        int found = -1;
+        for (int k = 0; k < na; ++k)
+          if (av.same(as_entry(tab[k]), s)) { found = k; break; }
+        if (found < 0) {
+          if (na == kSomTab) status = 2;
+          else {
+            found = na;
+            tab[na].kind = (s.kind == kMatch || s.kind == kMismatch) ? 0 : s.kind;
+            tab[na].len = s.len; tab[na].ptr = s.ptr; tab[na].base = s.base; tab[na].count = 0; tab[na].s1 = 0.0; tab[na].s0 = 0.0;
+            status = 1;
+          }
+        }
+        if (status != 2 && s_keep) { tab[found].count += 1; tab[found].s1 += sl1; tab[found].s0 += sl0; }
+      }
+      status = __shfl_sync(0xFFFFFFFFu, status, 0);
+      if (status == 2) {
+        if (lane == 0) report_error(err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus);
+        return false;
+      }
+      if (status == 1) { ++na; ++n_unf; }
+      __syncwarp();
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    depth += __shfl_xor_sync(0xFFFFFFFFu, depth, o);
+    ref_depth += __shfl_xor_sync(0xFFFFFFFFu, ref_depth, o);
+    t0 += __shfl_xor_sync(0xFFFFFFFFu, t0, o);
+    seen |= __shfl_xor_sync(0xFFFFFFFFu, seen, o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      cntc[k] += __shfl_xor_sync(0xFFFFFFFFu, cntc[k], o);
+      s1c[k] += __shfl_xor_sync(0xFFFFFFFFu, s1c[k], o);
+      s0c[k] += __shfl_xor_sync(0xFFFFFFFFu, s0c[k], o);
+    }
+  }
+  bool ok = true;
+  if (lane == 0) {
+    // drop entries that only unfiltered (low-mapq) elements carried, then add the A/C/G/T alleles from their counters
+    int m = 0;
+    for (int k = 0; k < na; ++k)
+      if (tab[k].count > 0) tab[m++] = tab[k];
+    na = m;
+    for (int k = 0; k < 4; ++k)
+      if (cntc[k] > 0) {
+        if (na == kSomTab) { ok = false; break; }
+        tab[na].kind = 0; tab[na].len = 1; tab[na].ptr = 0; tab[na].base = code_base(k); tab[na].count = cntc[k];
+        tab[na].s1 = s1c[k]; tab[na].s0 = s0c[k];
+        ++na;
+      }
+    if (ok) sort_alleles(av, tab, na);
+    else report_error(err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus);
+  }
+  ok = __shfl_sync(0xFFFFFFFFu, (int)ok, 0) != 0;
+  st.depth = depth;
+  st.ref_depth = ref_depth;
+  st.n_alleles = __shfl_sync(0xFFFFFFFFu, na, 0);
+  st.distinct_unfiltered = n_unf + __popc(seen);
+  st.t0 = t0;
+  __syncwarp();
+  return ok;
+}
+
+constexpr int kSomExactWarps = 4;
+
+__global__ void __launch_bounds__(kSomExactWarps * 32) k_somatic_exact(DevReads RT, DevReads RN, const SlowLocus* __restrict__ loci, SomParams prm,
+                                                                       const double* __restrict__ tables, SomOut out) {
+  __shared__ ExactSmem sm[kSomExactWarps];
+  const int lane = threadIdx.x & 31;
+  ExactSmem& S = sm[threadIdx.x >> 5];
+  const uint32_t n_loci = (uint32_t)min(out.counters[2], (unsigned long long)out.cap_slow);
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t t = warp; t < n_loci; t += n_warps) {
+    const int contig = loci[t].contig, locus = loci[t].locus;
+    SampleStats sT, sN;
+    uint8_t refT, refN;
+    bool ok = exact_sample<true>(RT, contig, locus, prm, tables, S.tab[0], sT, &refT, out.err);
+    ok = ok && exact_sample<false>(RN, contig, locus, prm, tables, S.tab[1], sN, &refN, out.err);
+    if (ok && lane == 0) {
+      // MultiAllelicPileupFilter (before the mapq filter): more than two distinct alleles empty the pileup
+      if (prm.filter_multi_allelic) {
+        if (sT.distinct_unfiltered > 2) sT.depth = 0;
+        if (sN.distinct_unfiltered > 2) sN.depth = 0;
+      }
+      AlleleView avT{RT, refT}, avN{RN, refN};
+      decide_somatic(RT, avT, avN, S.tab[0], sT, S.tab[1], sN, contig, locus, prm, out);
+    }
+    __syncwarp();
+  }
+}
+
+// ---- K_evidence: warp per record ------------------------------------------------------------------------------------------------------
+// does element e of read set R carry the allele (ref bytes, alt bytes)?
+__device__ bool elem_is_allele(const DevReads& R, const Elem& e, uint8_t ref_base, const uint8_t* ref, int ref_len, const uint8_t* alt, int alt_len) {
+  AlleleView av{R, ref_base};
+  AlleleEntry a;
+  a.kind = (e.kind == kMatch || e.kind == kMismatch) ? 0 : e.kind;
+  a.len = e.len; a.ptr = e.ptr; a.base = e.base; a.count = 1;
+  if (av.ref_len(a) != ref_len || av.alt_len(a) != alt_len) return false;
+  for (int i = 0; i < ref_len; ++i) if (av.ref_at(a, i) != ref[i]) return false;
+  for (int i = 0; i < alt_len; ++i) if (av.alt_at(a, i) != alt[i]) return false;
+  return true;
+}
+
+constexpr int kEvidenceCap = 1024;  // supporting elements kept for the medians (deeper: medians from the first kEvidenceCap)
+
+struct EvidenceSmem {
+  float mq[kEvidenceCap], bq[kEvidenceCap];
+  int nm[kEvidenceCap];
+  int n;
+};
+
+__device__ double median_f(float* v, int n) {  // breeze median: sort a copy, mean of the middle two for even n
+  for (int i = 1; i < n; ++i) { float x = v[i]; int j = i; while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; --j; } v[j] = x; }
+  if (n % 2 == 1) return (double)v[(n - 1) / 2];
+  return ((double)v[n / 2 - 1] + (double)v[n / 2]) / 2;
+}
+__device__ double median_i(int* v, int n) {  // DenseVector[Int]: integer arithmetic
+  for (int i = 1; i < n; ++i) { int x = v[i]; int j = i; while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; --j; } v[j] = x; }
+  if (n % 2 == 1) return (double)v[(n - 1) / 2];
+  return (double)((v[n / 2 - 1] + v[n / 2]) / 2);
+}
+
+__device__ void evidence_sample(const DevReads& R, int contig, int locus, const SomParams& prm, const uint8_t* ref, int ref_len,
+                                const uint8_t* alt, int alt_len, guac_allele_evidence& ev, EvidenceSmem& S, DevError* err) {
+  const int lane = threadIdx.x & 31;
+  const ContigInfo ci = R.contigs[contig];
+  bool std_ref = false;
+  uint8_t ref_base = 'N';
+  if (locus < ci.length) ref_base = reference_base_of(R, ci, contig, locus, &std_ref);
+  if (lane == 0) S.n = 0;
+  __syncwarp();
+  int depth = 0, fwd = 0, adepth = 0, afwd = 0;
+  uint32_t first = 0xFFFFFFFFu, last = 0;
+  if (locus < ci.length) {
+    const int g = locus >> kGranuleShift;
+    first = R.gran_first[ci.gran_off + g];
+    last = R.gran_last[ci.gran_off + g];
+  }
+  for (uint32_t base = first; base < last && first != 0xFFFFFFFFu; base += 32) {
+    const uint32_t r = base + lane;
+    bool valid = r < last;
+    ReadRec rec{0, 0, 0, 0};
+    if (valid) {
+      rec = R.rec[r];
+      valid = rec.start <= locus && rec.end > locus;
+    }
+    const int mapq = (int)(rec.info >> kInfoMapqShift);
+    valid = valid && (!(prm.min_mapq > 0) || mapq >= prm.min_mapq);
+    Elem e;
+    e.kind = kNone; e.base = 0; e.len = 0; e.ptr = 0; e.qual = 0;
+    if (valid && classify(R, r, locus, ref_base, e) != 0) valid = false;
+    bool is = false;
+    if (valid && e.kind != kNone) {
+      ++depth;
+      if (rec.info & kInfoPositive) ++fwd;
+      is = elem_is_allele(R, e, ref_base, ref, ref_len, alt, alt_len);
+      if (is) { ++adepth; if (rec.info & kInfoPositive) ++afwd; }
+    }
+    // supporting elements in read order (the mean is a running mean in element order)
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, is);
+    if (is) {
+      const int slot = S.n + __popc(m & ((1u << lane) - 1u));
+      if (slot < kEvidenceCap) { S.mq[slot] = (float)mapq; S.bq[slot] = (float)e.qual; S.nm[slot] = (int)R.nm[r]; }
+    }
+    __syncwarp();
+    if (lane == 0) S.n = min(S.n + __popc(m), kEvidenceCap);
+    __syncwarp();
+  }
+  for (int o = 16; o; o >>= 1) {
+    depth += __shfl_xor_sync(0xFFFFFFFFu, depth, o);
+    fwd += __shfl_xor_sync(0xFFFFFFFFu, fwd, o);
+    adepth += __shfl_xor_sync(0xFFFFFFFFu, adepth, o);
+    afwd += __shfl_xor_sync(0xFFFFFFFFu, afwd, o);
+  }
+  if (lane == 0) {
+    ev.read_depth = depth;
+    ev.allele_read_depth = adepth;
+    ev.forward_depth = fwd;
+    ev.allele_forward_depth = afwd;
+    const int n = S.n;
+    if (n == 0) {
+      const double nan = __longlong_as_double(0x7FF8000000000000ll);
+      ev.mean_mapping_quality = ev.median_mapping_quality = ev.mean_base_quality = ev.median_base_quality = ev.median_mismatches_per_read = nan;
+    } else {
+      double mu_m = 0.0, mu_b = 0.0;
+      for (int i = 0; i < n; ++i) {  // breeze mean: mu += (x - mu) / n
+        mu_m = mu_m + ((double)S.mq[i] - mu_m) / (double)(i + 1);
+        mu_b = mu_b + ((double)S.bq[i] - mu_b) / (double)(i + 1);
+      }
+      ev.mean_mapping_quality = mu_m;
+      ev.mean_base_quality = mu_b;
+      ev.median_mapping_quality = median_f(S.mq, n);
+      ev.median_base_quality = median_f(S.bq, n);
+      ev.median_mismatches_per_read = median_i(S.nm, n);
+    }
+  }
+  (void)err;
+  __syncwarp();
+}
+
+constexpr int kEvidenceWarps = 2;
+
+__global__ void __launch_bounds__(kEvidenceWarps * 32) k_evidence(DevReads RT, DevReads RN, SomParams prm, SomOut out) {
+  __shared__ EvidenceSmem sm[kEvidenceWarps];
+  EvidenceSmem& S = sm[threadIdx.x >> 5];
+  const uint32_t n_rec = (uint32_t)min(out.counters[0], (unsigned long long)out.cap_rec);
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t t = warp; t < n_rec; t += n_warps) {
+    guac_somatic_record& r = out.rec[t];
+    if ((unsigned long long)r.alt_off + r.alt_len > out.cap_pool) continue;  // pool overflow: the host reruns
+    const uint8_t* ref = out.pool + r.ref_off;
+    const uint8_t* alt = out.pool + r.alt_off;
+    guac_allele_evidence evT = r.tumor, evN = r.normal;
+    // tumorVariantEvidence = AlleleEvidence(L, allele, filteredTumor); normalReferenceEvidence = AlleleEvidence(1 - total,
+    // Allele(allele.refBases, allele.refBases), filteredNormal)
+    evidence_sample(RT, r.contig, (int)r.start, prm, ref, r.ref_len, alt, r.alt_len, evT, S, out.err);
+    evidence_sample(RN, r.contig, (int)r.start, prm, ref, r.ref_len, ref, r.ref_len, evN, S, out.err);
+    if ((threadIdx.x & 31) == 0) {
+      r.tumor = evT;
+      r.normal = evN;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace guac
+
+// ---- host side ------------------------------------------------------------------------------------------------------------------------
+namespace {
+
+void somatic_init_tables(guac_ctx* ctx) {
+  std::vector<double> t(kTabTotal);
+  for (int p = 0; p < 256; ++p) t[kTabSucc + p] = 1.0 - std::pow(10.0, -p / 10.0);  // ADAM PhredUtils.phredToSuccessProbability
+  for (int q = 0; q < 256; ++q) {
+    const double s = t[kTabSucc + q];  // probabilityCorrectIgnoringAlignment
+    t[kTabNl1 + q] = std::log(s + s);
+    t[kTabNl0 + q] = std::log((1 - s) + (1 - s));
+    for (int m = 0; m < 256; ++m) {
+      const double sm = t[kTabSucc + q] * t[kTabSucc + m];  // probabilityCorrectIncludingAlignment
+      t[kTabTl1 + m * 256 + q] = std::log(sm + sm);
+      t[kTabTl0 + m * 256 + q] = std::log((1 - sm) + (1 - sm));
+    }
+  }
+  CUDA_OK(cudaMalloc((void**)&ctx->d_tables, kTabTotal * sizeof(double)));
+  CUDA_OK(cudaMemcpy(ctx->d_tables, t.data(), kTabTotal * sizeof(double), cudaMemcpyHostToDevice));
+}
+
+void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& normal, const guac_locus_range* ranges, size_t n_ranges,
+                 const guac_somatic_params& p, guac_result& res) {
+  if (tumor.n_contigs != normal.n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "tumor and normal samples have different sequence dictionaries");
+  if (!tumor.has_qualities || !normal.has_qualities) fail(GUAC_ERR_UNSUPPORTED, "somatic-standard needs reads packed with base qualities");
+  cudaStream_t st = ctx->stream;
+  // tiles over the union of both tracks: a locus past one sample's track simply holds no reads of that sample
+  std::vector<TileDesc> tiles;
+  uint64_t requested = 0;
+  for (size_t i = 0; i < n_ranges; ++i) {
+    const guac_locus_range& r = ranges[i];
+    if (r.contig < 0 || (uint32_t)r.contig >= tumor.n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "locus range %zu: contig out of range", i);
+    if (r.start < 0 || r.end < r.start) fail(GUAC_ERR_INVALID_ARGUMENT, "locus range %zu: bad bounds", i);
+    requested += (uint64_t)(r.end - r.start);
+    const int64_t len = std::max(tumor.contigs[r.contig].length, normal.contigs[r.contig].length);
+    const int64_t s = r.start, e = std::min<int64_t>(r.end, len);
+    for (int64_t t = s / kTileLoci; t * kTileLoci < e; ++t) {
+      TileDesc td{r.contig, (int32_t)(t * kTileWords), (int32_t)std::max<int64_t>(s, t * kTileLoci), (int32_t)std::min<int64_t>(e, (t + 1) * kTileLoci)};
+      if (td.locus_end > td.locus_begin) tiles.push_back(td);
+    }
+  }
+  res.stats.reads_total = tumor.n + normal.n;
+  res.stats.loci_requested = requested;
+  res.stats.order_sensitive_loci = tumor.order_sensitive_loci + normal.order_sensitive_loci;
+  if (tiles.empty()) return;
+  uint64_t tile_loci = 0;
+  for (auto& t : tiles) tile_loci += (uint64_t)(t.locus_end - t.locus_begin);
+  DevBuf<TileDesc> d_tiles;
+  h2d(ctx, d_tiles, tiles.data(), tiles.size());
+  res.stats.h2d_bytes = d_tiles.bytes();
+  uint64_t cap_rec = std::max<uint64_t>(4096, tile_loci / 256), cap_slow = std::max<uint64_t>(4096, tile_loci / 8);
+  uint64_t cap_pool = kPoolDynOff + std::max<uint64_t>(65536, tile_loci / 64);
+  SomParams prm{p.odds_threshold, p.min_alignment_quality, p.filter_multi_allelic, p.max_read_depth, p.skip_empty, tumor.sample};
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    if (cap_rec >= 0xFFFFFFF0ull || cap_slow >= 0xFFFFFFF0ull || cap_pool >= 0xFFFFFFF0ull)
+      fail(GUAC_ERR_UNSUPPORTED, "too many output records for one call: split the loci ranges");
+    ctx->out_rec.ensure(cap_rec * sizeof(guac_somatic_record));
+    ctx->out_slow.ensure(cap_slow * sizeof(SlowLocus));
+    if (ctx->out_pool.ensure(cap_pool)) ctx->pool_head_ready = false;
+    CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
+    SomOut out;
+    out.rec = (guac_somatic_record*)ctx->out_rec.p;
+    out.cap_rec = (uint32_t)cap_rec;
+    out.pool = ctx->out_pool.p;
+    out.cap_pool = (uint32_t)cap_pool;
+    out.slow = (SlowLocus*)ctx->out_slow.p;
+    out.cap_slow = (uint32_t)cap_slow;
+    out.counters = ctx->d_counters;
+    out.err = ctx->d_err;
+    const DevReads RT = tumor.view(), RN = normal.view();
+    CUDA_OK(cudaEventRecord(ctx->ev[0], st));
+    k_somatic<<<(int)tiles.size(), kSomThreads, 0, st>>>(RT, RN, d_tiles.p, prm, ctx->d_tables, (int)tumor.max_ref_span, (int)normal.max_ref_span, out);
+    CUDA_OK(cudaEventRecord(ctx->ev[1], st));
+    k_somatic_exact<<<ctx->sm_count * 16, kSomExactWarps * 32, 0, st>>>(RT, RN, out.slow, prm, ctx->d_tables, out);
+    k_evidence<<<ctx->sm_count * 8, kEvidenceWarps * 32, 0, st>>>(RT, RN, prm, out);
+    CUDA_OK(cudaEventRecord(ctx->ev[2], st));
+    CUDA_OK(cudaGetLastError());
+    unsigned long long* c = ctx->h_counters;
+    CUDA_OK(cudaMemcpyAsync(c, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    check_device_error(ctx, "somatic-standard");
+    float ms0 = 0, ms1 = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms0, ctx->ev[0], ctx->ev[1]));
+    CUDA_OK(cudaEventElapsedTime(&ms1, ctx->ev[1], ctx->ev[2]));
+    res.stats.tile_kernel_ms += ms0;
+    res.stats.exact_kernel_ms += ms1;
+    res.stats.kernel_launches += 3;
+    if (c[2] > cap_slow || c[0] > cap_rec || kPoolDynOff + c[1] > cap_pool) {
+      cap_slow = std::max<uint64_t>(cap_slow, c[2] + c[2] / 8 + 16);
+      cap_rec = std::max<uint64_t>(cap_rec, c[0] + c[0] / 8 + 16);
+      cap_pool = std::max<uint64_t>(cap_pool, kPoolDynOff + c[1] + c[1] / 8 + 16);
+      continue;
+    }
+    const uint64_t n_rec = c[0];
+    std::vector<uint8_t> pool((size_t)(kPoolDynOff + c[1]));
+    std::vector<guac_somatic_record> recs((size_t)n_rec);
+    CUDA_OK(cudaMemcpyAsync(pool.data(), ctx->out_pool.p, pool.size(), cudaMemcpyDeviceToHost, st));
+    if (n_rec) CUDA_OK(cudaMemcpyAsync(recs.data(), ctx->out_rec.p, n_rec * sizeof(guac_somatic_record), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    res.stats.d2h_bytes = pool.size() + n_rec * sizeof(guac_somatic_record) + 64;
+    if (ctx->sort_records) {
+      auto str = [&](uint32_t off, uint16_t len) { return std::string((const char*)pool.data() + off, len); };
+      std::sort(recs.begin(), recs.end(), [&](const guac_somatic_record& a, const guac_somatic_record& b) {
+        if (a.contig != b.contig) return a.contig < b.contig;
+        if (a.start != b.start) return a.start < b.start;
+        std::string ra = str(a.ref_off, a.ref_len), rb = str(b.ref_off, b.ref_len);
+        if (ra != rb) return ra < rb;
+        return str(a.alt_off, a.alt_len) < str(b.alt_off, b.alt_len);
+      });
+    }
+    res.bytes.clear();
+    for (auto& r : recs) {
+      uint32_t ro = (uint32_t)res.bytes.size();
+      res.bytes.insert(res.bytes.end(), pool.begin() + r.ref_off, pool.begin() + r.ref_off + r.ref_len);
+      uint32_t ao = (uint32_t)res.bytes.size();
+      res.bytes.insert(res.bytes.end(), pool.begin() + r.alt_off, pool.begin() + r.alt_off + r.alt_len);
+      r.ref_off = ro;
+      r.alt_off = ao;
+    }
+    res.somatic = std::move(recs);
+    res.stats.loci_visited = c[3];
+    res.stats.records = n_rec;
+    res.stats.exact_loci = c[2];
+    res.stats.kernel_ms = res.stats.tile_kernel_ms + res.stats.exact_kernel_ms;
+    return;
+  }
+  fail(GUAC_ERR_CUDA, "output buffers did not converge");
+}
+
 }  // namespace

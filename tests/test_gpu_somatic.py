@@ -1,0 +1,122 @@
+"""Parity of the somatic-standard kernels (K_somatic, K_somatic_exact, K_evidence) with the oracle, through the C ABI.
+Integers and allele strings bit-exact; fp64 likelihoods / odds / means within 1e-9 relative
+(summation order differs from colt's last-to-first walk); quantities obtained by cancellation next to 1
+(log of odds ~ 1, 1 - total) get an absolute floor of 1e-12, the reference's own assertAlmostEqual epsilon."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle_binding as orc
+from conftest import load_golden
+from guacamole_b200.reads import ReadBatch, make_read
+
+pytestmark = pytest.mark.gpu
+REL = 1e-9
+ABS = 1e-12   # TestUtil.assertAlmostEqual's epsilon (src/test/.../util/TestUtil.scala:204-206)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from guacamole_b200.callers import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def close(a, b):
+    if isinstance(a, float) or isinstance(b, float):
+        if math.isnan(a) or math.isnan(b):
+            return math.isnan(a) and math.isnan(b)
+        if math.isinf(a) or math.isinf(b):
+            return a == b
+        return abs(a - b) <= REL * max(abs(a), abs(b)) + ABS
+    return a == b
+
+
+def assert_somatic_equal(ctx, tumor, normal, ranges, **kw):
+    from guacamole_b200 import callers
+    want = orc.somatic_standard(tumor, normal, ranges, orc.somatic_params(**kw))
+    t, n = ctx.pack(tumor), ctx.pack(normal)
+    got = callers.somatic_standard(ctx, t, n, ranges, odds_threshold=kw.get("odds", 20), min_alignment_quality=kw.get("min_mapq", 1),
+                                   filter_multi_allelic=kw.get("filter_multi_allelic", False),
+                                   max_read_depth=kw.get("max_read_depth", 2 ** 31 - 1))
+    t.free()
+    n.free()
+    w, g = want.somatic(), got.genotypes()
+    assert [(x["contig"], x["start"], x["ref"], x["alt"]) for x in g] == [(x["contig"], x["start"], x["ref"], x["alt"]) for x in w]
+    for a, b in zip(g, w):
+        assert a["phred"] == b["phred"], (a, b)
+        assert close(a["somatic_log_odds"], b["somatic_log_odds"]), (a, b)
+        for side in ("tumor", "normal"):
+            for k, v in b[side].items():
+                assert close(a[side][k], v), (side, k, a, b)
+    assert got.stats["loci_visited"] == want.stats["loci_visited"]
+    return got
+
+
+NORMAL8 = [make_read("TCGATCGA", "8M", "8", 0)] * 3
+
+
+def pair(tumor, normal):
+    return ReadBatch.from_records(tumor).sorted(), ReadBatch.from_records(normal).sorted()
+
+
+def test_suite_indels(ctx):  # SomaticStandardCallerSuite.scala:117-262 through the engine
+    cases = [
+        ([make_read("TCGGTCGA", "8M", "3G4", 0)] * 3, NORMAL8),
+        ([make_read("TCGTCGA", "3M1D4M", "3^A4", 0)] * 3, NORMAL8),
+        ([make_read("TCGAAAAGCT", "5M6D5M", "5^GCTTCG5", 0)] * 3, [make_read("TCGAAGCTTCGAAGCT", "16M", "16", 0)] * 3),
+        ([make_read("TCGAGTCGA", "4M1I4M", "8", 0)] * 3, NORMAL8),
+        ([make_read("TCGAGGTCTCGA", "4M4I4M", "8", 0)] * 3, NORMAL8),
+        ([make_read("TCATCTCAAAAGAGATCGA", "2M2D1M2I2M4I2M2D6M", "2^GA5^TC6", 10)] * 3, [make_read("TCGAATCGATCGATCGA", "17M", "17", 10)] * 3),
+    ]
+    for tumor, normal in cases:
+        t, n = pair(tumor, normal)
+        got = assert_somatic_equal(ctx, t, n, [(0, 0, 64)], odds=2)
+        assert_somatic_equal(ctx, t, n, [(0, 0, 64)], odds=2, filter_multi_allelic=True)
+    t, n = pair(*cases[1])
+    g = assert_somatic_equal(ctx, t, n, [(0, 0, 64)], odds=2).genotypes()
+    assert [(x["start"], x["ref"], x["alt"]) for x in g] == [(2, "GA", "G")]
+
+
+def tn(tumor_name, normal_name):
+    t = load_golden(tumor_name).filtered(non_duplicate=True, passed_qc=True, has_md=True).sorted()
+    n = load_golden(normal_name).filtered(non_duplicate=True, passed_qc=True, has_md=True).sorted()
+    return t, n
+
+
+FIXTURES = [("tumor.chr20.tough", "normal.chr20.tough", "20"),
+            ("synthetic.challenge.set1.tumor.v2.withMDTags.chr2.syn1fp", "synthetic.challenge.set1.normal.v2.withMDTags.chr2.syn1fp", "2"),
+            ("synthetic.challenge.set1.tumor.v2.withMDTags.chr2.complexvar", "synthetic.challenge.set1.normal.v2.withMDTags.chr2.complexvar", "2"),
+            ("tumor.chr20.simplefp", "normal.chr20.simplefp", "20")]
+
+
+@pytest.mark.parametrize("tumor_name,normal_name,contig", FIXTURES)
+def test_real_fixtures(ctx, tumor_name, normal_name, contig):
+    t, n = tn(tumor_name, normal_name)
+    c = t.contig_names.index(contig)
+    hi = int(max(t.end().max(), n.end().max())) + 10
+    got = assert_somatic_equal(ctx, t, n, [(c, 0, hi)], odds=20)
+    assert_somatic_equal(ctx, t, n, [(c, 0, hi)], odds=120)
+    assert_somatic_equal(ctx, t, n, [(c, 0, hi)], odds=20, min_mapq=30, max_read_depth=60)
+    if "tough" in tumor_name:
+        assert len(got) > 20
+
+
+def test_synthetic_pair(ctx):  # BASELINE.json configs[2] shape, small
+    from guacamole_b200 import synth
+    contigs = [("20", 200000)]
+    tumor = synth.generate(contigs, depth=60, seed=21, sample=1).to_read_batch()
+    normal = synth.generate(contigs, depth=30, seed=21, sample=0).to_read_batch()
+    got = assert_somatic_equal(ctx, tumor, normal, [(0, 0, 199999)], odds=20)
+    assert len(got) >= 1
+    assert_somatic_equal(ctx, tumor, normal, [(0, 5000, 90000), (0, 120000, 120777)], odds=20, filter_multi_allelic=True)
+
+
+def test_deep_underflow_flow(ctx):  # the reference's naive normalisation underflows at ~1,100x; Inf / NaN must flow alike
+    from guacamole_b200 import synth
+    contigs = [("amp", 2000)]
+    tumor = synth.generate(contigs, depth=2500, seed=33, sample=1).to_read_batch()
+    normal = synth.generate(contigs, depth=2500, seed=33, sample=0).to_read_batch()
+    assert_somatic_equal(ctx, tumor, normal, [(0, 0, 1999)], odds=20)
