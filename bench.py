@@ -157,13 +157,13 @@ def pinned_copy(view):
 def cpu_leg(args, steps, warmup, n_threads):
     """The reference algorithm on host cores: oracle over a bounded window of the same workload, Spark-style loci tasks."""
     import oracle_binding as orc
-    window = min(args.cpu_window, args.contig_length)
-    sb = synth.generate([("20", args.contig_length)], depth=args.depth, read_length=READ_LEN, seed=args.seed,
-                        window=(0, 0, window))
-    batch_c = sb.c
+    somatic = args.workload == "somatic"
+    window = min(args.cpu_window // (3 if somatic else 1), args.contig_length)
+    samples = [(1, args.depth * 2), (0, args.depth)] if somatic else [(0, args.depth)]
+    sbs = [synth.generate([("20", args.contig_length)], depth=d, read_length=READ_LEN, seed=args.seed, sample=s,
+                          window=(0, 0, window)) for s, d in samples]
     ranges = orc.partition_loci_uniformly(n_threads, [(0, 0, window - READ_LEN - 40)])
     arr = orc.ranges_array(ranges)
-    prm = orc.threshold_params(8)
     L = orc.lib()
     n_loci = sum(r[2] - r[1] for r in ranges)
     times = []
@@ -171,7 +171,13 @@ def cpu_leg(args, steps, warmup, n_threads):
     for i in range(warmup + steps):
         h = C.c_void_p()
         t0 = time.perf_counter()
-        rc = L.orc_germline_threshold(C.byref(batch_c), None, arr, C.c_size_t(len(ranges)), C.byref(prm), n_threads, C.byref(h))
+        if somatic:
+            prm = orc.somatic_params(odds=20, min_mapq=1)
+            rc = L.orc_somatic_standard(C.byref(sbs[0].c), C.byref(sbs[1].c), None, arr, C.c_size_t(len(ranges)), C.byref(prm),
+                                        n_threads, C.byref(h))
+        else:
+            prm = orc.threshold_params(8)
+            rc = L.orc_germline_threshold(C.byref(sbs[0].c), None, arr, C.c_size_t(len(ranges)), C.byref(prm), n_threads, C.byref(h))
         dt = time.perf_counter() - t0
         if rc != 0:
             raise RuntimeError("oracle failed: " + L.orc_last_error().decode())
@@ -180,8 +186,9 @@ def cpu_leg(args, steps, warmup, n_threads):
         if i >= warmup:
             times.append(dt)
     sec = float(np.mean(times))
-    return {"loci_per_s": n_loci / sec, "reads_per_s": sb.n_reads / sec, "sec_per_step": sec, "loci": n_loci,
-            "reads": sb.n_reads, "records": int(n_rec), "threads": n_threads, "window": window}
+    reads = sum(sb.n_reads for sb in sbs)
+    return {"loci_per_s": n_loci / sec, "reads_per_s": reads / sec, "sec_per_step": sec, "loci": n_loci,
+            "reads": reads, "records": int(n_rec), "threads": n_threads, "window": window}
 
 
 def main():
@@ -190,9 +197,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_threads = os.cpu_count() or 1
-    config = {"workload": f"{args.workload}-threshold, synthetic chr20 shape ({args.contig_length:,} loci), {args.depth:g}x, "
-                          f"{READ_LEN} bp (BASELINE.json configs[1]) per GPU",
-              "threshold_percent": 8, "loci_per_gpu": args.contig_length, "depth": args.depth, "read_length": READ_LEN,
+    if args.workload == "somatic":
+        wl = (f"somatic-standard, synthetic tumor/normal pair {2 * args.depth:g}x/{args.depth:g}x, chr20 shape "
+              f"({args.contig_length:,} loci), {READ_LEN} bp (BASELINE.json configs[2]) per GPU")
+    else:
+        wl = (f"germline-threshold, synthetic chr20 shape ({args.contig_length:,} loci), {args.depth:g}x, {READ_LEN} bp "
+              f"(BASELINE.json configs[1]) per GPU")
+    config = {"workload": wl, "threshold_percent": 8, "loci_per_gpu": args.contig_length, "depth": args.depth, "read_length": READ_LEN,
               "parallelism": f"loci-partitioned x{world}", "l2": "inputs larger than L2 (no flush needed)"}
 
     if args.impl == "reference":
@@ -202,7 +213,7 @@ def main():
         line = {"impl": "reference", "metric": "loci_per_sec", "value": cpu["loci_per_s"], "unit": "loci/s",
                 "reads_per_sec": cpu["reads_per_s"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": cpu["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": "synthetic", "config": config,
+                "dtype": "f64" if args.workload == "somatic" else "u8", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": cpu["loci_per_s"], "unit": "loci/s", "cores": cpu["threads"], "kind": "port",
                                  "sample": f"first {cpu['window']:,} loci of the chr20-shape workload ({cpu['reads']:,} reads); "
                                            "C++ oracle restating the reference's Scala algorithm (no JVM on the box)"},
@@ -214,47 +225,55 @@ def main():
     import torch.distributed as dist
     from guacamole_b200 import callers
     from guacamole_b200._lib import lib
+    from guacamole_b200.distributed import gather_records, ranges_of_rank
+    from guacamole_b200.loci import partition_loci_uniformly
 
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     L = lib()
+    somatic = args.workload == "somatic"
 
     # ---- this rank's shard: one chr20-shaped contig of a `world`-contig genome (LociPartitioning over contigs)
     contigs = [(f"20_{r}" if world > 1 else "20", args.contig_length) for r in range(world)]
-    from guacamole_b200.loci import partition_loci_uniformly
+    names = [c[0] for c in contigs]
     loci_all = [(c, 0, args.contig_length - 1) for c in range(world)]  # LociSet "all" drops the last base of a contig
-    parts = partition_loci_uniformly(world, loci_all)
-    my_ranges = [p for p in parts if p[3] == rank]
-    t_gen = time.perf_counter()
-    sb = synth.generate(contigs, depth=args.depth, read_length=READ_LEN, seed=args.seed,
-                        window=(rank, 0, args.contig_length), n_reads=int(args.depth * args.contig_length / READ_LEN))
-    gen_s = time.perf_counter() - t_gen
-    view = sb.c
-    n_reads = sb.n_reads
+    my_ranges = ranges_of_rank(partition_loci_uniformly(world, loci_all), rank)
     n_loci = sum(r[2] - r[1] for r in my_ranges)
-    algorithmic = algorithmic_bytes(view, n_loci)
-    view, pinned = pinned_copy(view)
-    sb.free()
+    t_gen = time.perf_counter()
+    samples = [(1, args.depth * 2), (0, args.depth)] if somatic else [(0, args.depth)]   # tumor 60x + normal 30x
+    views, keeps, n_reads, algorithmic = [], [], 0, 0.25 * n_loci
+    for sample, depth in samples:
+        sb = synth.generate(contigs, depth=depth, read_length=READ_LEN, seed=args.seed, sample=sample,
+                            window=(rank, 0, args.contig_length), n_reads=int(depth * args.contig_length / READ_LEN))
+        n_reads += sb.n_reads
+        algorithmic += algorithmic_bytes(sb.c, 0) + ((READ_LEN + 3) * sb.n_reads if somatic else 0)
+        v, k = pinned_copy(sb.c)
+        sb.free()
+        views.append(v)
+        keeps.append(k)
+    gen_s = time.perf_counter() - t_gen
 
     ctx = callers.Context(local_rank)
-    ctx.set_option(abi.OPT_PACK_QUALITIES, 0 if args.workload == "germline" else 1)
-    reads = ctx.pack_c(view, [c[0] for c in contigs])
-    pack_ms = reads.pack_kernel_ms
+    ctx.set_option(abi.OPT_PACK_QUALITIES, 1 if somatic else 0)
+    packed = [ctx.pack_c(v, names) for v in views]
+    pack_ms = sum(p.pack_kernel_ms for p in packed)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        return callers.germline_threshold(ctx, reads, my_ranges, threshold=8)
+    def call(reads_list):
+        if somatic:
+            return callers.somatic_standard(ctx, reads_list[0], reads_list[1], my_ranges, odds_threshold=20, min_alignment_quality=1)
+        return callers.germline_threshold(ctx, reads_list[0], my_ranges, threshold=8)
 
     # ---- device-resident leg
     ctx.set_option(abi.OPT_SORT_RECORDS, 0)
     for _ in range(args.warmup):
-        res = step()
+        res = call(packed)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -262,7 +281,7 @@ def main():
     t0 = time.perf_counter()
     tile_ms, exact_ms, launches = 0.0, 0.0, 0
     for _ in range(args.steps):
-        res = step()
+        res = call(packed)
         tile_ms += res.stats["tile_kernel_ms"]
         exact_ms += res.stats["exact_kernel_ms"]
         launches += res.stats["kernel_launches"]
@@ -281,11 +300,12 @@ def main():
         if i == 1:
             barrier()
             t1 = time.perf_counter()
-        r2 = ctx.pack_c(view, [c[0] for c in contigs])
-        out = callers.germline_threshold(ctx, r2, my_ranges, threshold=8)
-        h2d = int(L.guac_reads_h2d_bytes(r2._h)) + int(out.stats["h2d_bytes"])
+        fresh = [ctx.pack_c(v, names) for v in views]
+        out = call(fresh)
+        h2d = sum(int(L.guac_reads_h2d_bytes(f._h)) for f in fresh) + int(out.stats["h2d_bytes"])
         d2h = int(out.stats["d2h_bytes"])
-        r2.free()
+        for f in fresh:
+            f.free()
     barrier()
     e2e_ms = (time.perf_counter() - t1) * 1e3 / e2e_steps
     assert len(out) == n_records, "e2e and resident legs disagree"
@@ -295,21 +315,16 @@ def main():
     if world > 1:
         mx = t.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = t.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        rec_bytes = torch.from_numpy(res.records.view(np.uint8).copy()).cuda()
-        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([rec_bytes.numel()], dtype=torch.int64, device="cuda"))
-        cap = int(max(int(s.item()) for s in sizes))
-        padded = torch.zeros(cap, dtype=torch.uint8, device="cuda")
-        padded[:rec_bytes.numel()] = rec_bytes
-        gathered = [torch.zeros(cap, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
-        dist.gather(padded, gathered, dst=0)
+        t_g = time.perf_counter()
+        allrec, _ = gather_records(out.records, out.bytes, dst=0, device=torch.device("cuda", local_rank))
+        torch.cuda.synchronize()
+        gather_ms = (time.perf_counter() - t_g) * 1e3
         step_ms, e2e_ms = float(mx[0]), float(mx[1])
-        total_records = int(sm[2].item())
+        total_records = len(allrec) if rank == 0 else 0
         tile_step_ms, exact_step_ms = float(mx[3]), float(mx[4])
     else:
         total_records = n_records
+        gather_ms = 0.0
         tile_step_ms, exact_step_ms = tile_ms / args.steps, exact_ms / args.steps
 
     if rank != 0:
@@ -327,15 +342,16 @@ def main():
     line = {
         "metric": "loci_per_sec", "value": value, "unit": "loci/s", "reads_per_sec": total_reads / (step_ms * 1e-3),
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if somatic else "u8", "data": "synthetic", "config": config,
         "records_per_step": total_records, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "loci/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "pinned_host_buffers": len(pinned)},
-        "roofline": {"bound": "hbm", "kernel": "k_pileup_tile", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "steps": e2e_steps, "pinned_host_buffers": sum(len(k) for k in keeps)},
+        "roofline": {"bound": "hbm", "kernel": "k_somatic" if somatic else "k_pileup_tile", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tile_step_ms, "exact_kernel_ms": exact_step_ms,
                      "whole_step_achieved_gbs": alg_bytes / (step_ms * 1e-3) / 1e9},
         "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps, "pack_kernel_ms": pack_ms, "generate_s": gen_s,
+        "gather_ms": gather_ms,
     }
     if world == 1:
         cpu = cpu_leg(args, 1, 0, n_threads)

@@ -182,3 +182,20 @@ def test_empty_inputs(ctx):
     assert len(callers.germline_threshold(ctx, reads, [(0, 0, 1000)])) == 0
     assert len(callers.pileup_counts(ctx, reads, [(0, 0, 10)], skip_empty=False)) == 10
     assert len(callers.germline_threshold(ctx, reads, [])) == 0
+
+
+def test_sharded_ranks_equal_single_run(ctx):
+    """LociPartitioning across ranks (emulated one after the other on one GPU): shard reads by each rank's ranges,
+    run the engine per shard, concatenate — identical to the unsharded run (T/DistributedUtilSuite.scala:208-220)."""
+    from guacamole_b200 import callers, synth
+    from guacamole_b200.distributed import ranges_of_rank, shard_reads
+    from guacamole_b200.loci import partition_loci_uniformly
+    b = synth.generate([("1", 50000), ("2", 30000)], depth=30, seed=23).to_read_batch()
+    loci = [(0, 0, 49999), (1, 0, 29999)]
+    full = gpu_threshold(ctx, b, loci).genotypes()
+    parts = partition_loci_uniformly(4, loci)
+    merged = []
+    for rank in range(4):
+        mine = ranges_of_rank(parts, rank)
+        merged += gpu_threshold(ctx, shard_reads(b, mine), mine).genotypes()
+    assert sorted(merged, key=lambda r: (r["contig"], r["start"], r["ref"], r["alt"])) == full and len(full) > 100
