@@ -149,7 +149,11 @@ class Result:
             p, dt = L.guac_result_somatic_records(handle), SOMATIC_DTYPE
         else:
             p, dt = L.guac_result_counts(handle), COUNTS_DTYPE
-        self.records = np.frombuffer(C.string_at(p, n * dt.itemsize), dtype=dt).copy() if n else np.zeros(0, dt)
+        if n:  # one copy out of the library-owned buffer
+            raw = (C.c_uint8 * (n * dt.itemsize)).from_address(C.cast(p, C.c_void_p).value)
+            self.records = np.frombuffer(raw, dtype=np.uint8).copy().view(dt)
+        else:
+            self.records = np.zeros(0, dt)
         L.guac_result_free(handle)
 
     def __len__(self):

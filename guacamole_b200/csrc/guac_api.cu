@@ -11,6 +11,9 @@
 #include <tuple>
 #include <vector>
 
+#include <functional>
+#include <thread>
+
 #include "guac_host.cuh"
 #include "guac_pack.cuh"
 #include "guac_pileup.cuh"
@@ -29,81 +32,137 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   out.n_contigs = b->n_contigs;
   if (ref && ref->n_contigs != b->n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "reference and batch disagree on the number of contigs");
 
+  Trace tr("pack");
   // ---- host pass over the read headers: O(reads + cigar ops); everything per-base happens on the device
-  std::vector<ReadRec> rec(n + 1);
-  std::vector<uint32_t> cig_off(n + 1), md_off(n + 1), read_contig(n);
+  // header columns are built in a pinned arena owned by the context (no page faults after the first call, fast H2D)
+  const size_t col = ((n + 1) * sizeof(uint32_t) + 63) & ~(size_t)63;
+  unsigned char* arena = pack_arena(ctx, (n + 1) * sizeof(ReadRec) + 64 + 3 * col);
+  ReadRec* rec = reinterpret_cast<ReadRec*>(arena);
+  uint32_t* cig_off = reinterpret_cast<uint32_t*>(arena + (((n + 1) * sizeof(ReadRec) + 63) & ~(size_t)63));
+  uint32_t* md_off = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(cig_off) + col);
+  uint32_t* read_contig = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(md_off) + col);
   std::vector<int64_t> contig_end(b->n_contigs, 0);
   std::vector<uint64_t> contig_first(b->n_contigs, ~0ull), contig_last(b->n_contigs, 0);
-  uint64_t pair_total = 0;
-  int32_t prev_contig = -1;
-  int64_t prev_start = 0;
-  std::vector<char> contig_seen(b->n_contigs, 0);
   if (b->cigar_off[n] >= 0xFFFFFFFFull || b->md_off[n] >= 0xFFFFFFFFull) fail(GUAC_ERR_UNSUPPORTED, "cigar / MD columns too large: shard the read set");
   out.sample = n ? (b->sample ? b->sample[0] : 0) : 0;
-  for (uint64_t i = 0; i < n; ++i) {
-    const int32_t c = b->contig[i];
-    if (c < 0 || (uint32_t)c >= b->n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "read %llu: contig index %d out of range", (unsigned long long)i, c);
-    if (c != prev_contig) {
-      if (contig_seen[c]) fail(GUAC_ERR_CONTIG_ORDER, "Regions are not sorted by contig (read %llu)", (unsigned long long)i);
-      contig_seen[c] = 1;
-      prev_contig = c;
-      prev_start = 0;
-      contig_first[c] = i;
-    }
-    contig_last[c] = i + 1;
-    const int64_t start = b->start[i];
-    if (start < prev_start) fail(GUAC_ERR_UNSORTED_READS, "Regions must be sorted by start locus (read %llu)", (unsigned long long)i);
-    prev_start = start;
-    if (start < 0) fail(GUAC_ERR_INVALID_ARGUMENT, "read %llu: negative start", (unsigned long long)i);
-    if (b->sample && b->sample[i] != out.sample) fail(GUAC_ERR_UNSUPPORTED, "one read set must hold one sample (split by sample before packing)");
-    if (!(b->flags[i] & GUAC_READ_HAS_MD)) fail(GUAC_ERR_MISSING_MD, "read %llu has no MD tag (the callers load reads with hasMdTag = true)", (unsigned long long)i);
-    const uint64_t c0 = b->cigar_off[i], c1 = b->cigar_off[i + 1];
-    const uint64_t read_len = b->seq_off[i + 1] - b->seq_off[i];
-    if (read_len > (uint64_t)kMaxReadLen) fail(GUAC_ERR_UNSUPPORTED, "read %llu longer than %d bases", (unsigned long long)i, kMaxReadLen);
-    int64_t ref_len = 0, consumed = 0, lead = 0;
-    int phase = 0;  // 0 leading clips, 1 inside the aligned run, 2 trailing clips
-    bool simple = true;
-    for (uint64_t k = c0; k < c1; ++k) {
-      const uint32_t op = b->cigar[k] & 0xF, len = b->cigar[k] >> 4;
-      if (op > 8 || op == GUAC_CIGAR_P) fail(GUAC_ERR_INVALID_CIGAR, "read %llu: unsupported CIGAR operator %u", (unsigned long long)i, op);
-      if (len == 0) fail(GUAC_ERR_INVALID_CIGAR, "read %llu: zero-length CIGAR element", (unsigned long long)i);
-      const bool m = op == GUAC_CIGAR_M || op == GUAC_CIGAR_EQ || op == GUAC_CIGAR_X;
-      if (m || op == GUAC_CIGAR_D || op == GUAC_CIGAR_N) ref_len += len;
-      if (m || op == GUAC_CIGAR_I || op == GUAC_CIGAR_S) consumed += len;
-      if (m) {
-        if (phase == 2) simple = false;
-        phase = 1;
-      } else if (op == GUAC_CIGAR_S || op == GUAC_CIGAR_H) {
-        if (phase == 0) {
-          if (op == GUAC_CIGAR_S) lead += len;
-        } else
-          phase = 2;
-      } else {
-        simple = false;
+  const int32_t sample0 = out.sample;
+  // Reads are independent except for the order checks (which look at read i - 1 in the input) and the running pair offset
+  // (chunk-local first, rebased after an exclusive scan over the chunks): the pass runs on all host threads.
+  struct Chunk {
+    uint64_t begin = 0, end = 0, pairs = 0;
+    int64_t max_span = 0;
+    std::vector<std::pair<uint64_t, int32_t>> runs;  // (first read, contig) of every contig run that starts in the chunk
+    std::vector<int64_t> contig_end;
+    StatusError err{GUAC_OK, ""};
+  };
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t n_chunks = n < 200000 ? 1 : std::min<size_t>(hw, 64);
+  std::vector<Chunk> chunks(n_chunks);
+  auto header_pass = [&](Chunk& ch) {
+    ch.contig_end.assign(b->n_contigs, 0);
+    uint64_t pair_total = 0;
+    try {
+      for (uint64_t i = ch.begin; i < ch.end; ++i) {
+        const int32_t c = b->contig[i];
+        if (c < 0 || (uint32_t)c >= b->n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "read %llu: contig index %d out of range", (unsigned long long)i, c);
+        const int64_t start = b->start[i];
+        if (i == 0 || b->contig[i - 1] != c) ch.runs.push_back({i, c});
+        else if (start < b->start[i - 1]) fail(GUAC_ERR_UNSORTED_READS, "Regions must be sorted by start locus (read %llu)", (unsigned long long)i);
+        if (start < 0) fail(GUAC_ERR_INVALID_ARGUMENT, "read %llu: negative start", (unsigned long long)i);
+        if (b->sample && b->sample[i] != sample0) fail(GUAC_ERR_UNSUPPORTED, "one read set must hold one sample (split by sample before packing)");
+        if (!(b->flags[i] & GUAC_READ_HAS_MD)) fail(GUAC_ERR_MISSING_MD, "read %llu has no MD tag (the callers load reads with hasMdTag = true)", (unsigned long long)i);
+        const uint64_t c0 = b->cigar_off[i], c1 = b->cigar_off[i + 1];
+        const uint64_t read_len = b->seq_off[i + 1] - b->seq_off[i];
+        if (read_len > (uint64_t)kMaxReadLen) fail(GUAC_ERR_UNSUPPORTED, "read %llu longer than %d bases", (unsigned long long)i, kMaxReadLen);
+        int64_t ref_len = 0, consumed = 0, lead = 0;
+        int phase = 0;  // 0 leading clips, 1 inside the aligned run, 2 trailing clips
+        bool simple = true;
+        for (uint64_t k = c0; k < c1; ++k) {
+          const uint32_t op = b->cigar[k] & 0xF, len = b->cigar[k] >> 4;
+          if (op > 8 || op == GUAC_CIGAR_P) fail(GUAC_ERR_INVALID_CIGAR, "read %llu: unsupported CIGAR operator %u", (unsigned long long)i, op);
+          if (len == 0) fail(GUAC_ERR_INVALID_CIGAR, "read %llu: zero-length CIGAR element", (unsigned long long)i);
+          const bool m = op == GUAC_CIGAR_M || op == GUAC_CIGAR_EQ || op == GUAC_CIGAR_X;
+          if (m || op == GUAC_CIGAR_D || op == GUAC_CIGAR_N) ref_len += len;
+          if (m || op == GUAC_CIGAR_I || op == GUAC_CIGAR_S) consumed += len;
+          if (m) {
+            if (phase == 2) simple = false;
+            phase = 1;
+          } else if (op == GUAC_CIGAR_S || op == GUAC_CIGAR_H) {
+            if (phase == 0) {
+              if (op == GUAC_CIGAR_S) lead += len;
+            } else
+              phase = 2;
+          } else {
+            simple = false;
+          }
+        }
+        if (c1 == c0) simple = false;
+        if ((uint64_t)consumed != read_len) fail(GUAC_ERR_INVALID_CIGAR, "read %llu: CIGAR consumes %lld bases, the read has %llu", (unsigned long long)i, (long long)consumed, (unsigned long long)read_len);
+        const int64_t end = start + ref_len;
+        if (end > 0x7FFFFF00ll) fail(GUAC_ERR_UNSUPPORTED, "read %llu: coordinates beyond 2^31", (unsigned long long)i);
+        if (b->contig_length && end > b->contig_length[c]) fail(GUAC_ERR_INVALID_ARGUMENT, "read %llu ends past its contig", (unsigned long long)i);
+        if (simple && lead > 0xFFFF) simple = false;
+        ch.contig_end[c] = std::max(ch.contig_end[c], end);
+        ch.max_span = std::max<int64_t>(ch.max_span, ref_len);
+        uint32_t info = (uint32_t)(simple ? (lead & 0xFFFF) : 0) | (simple ? kInfoSimple : 0) |
+                        ((b->flags[i] & GUAC_READ_POSITIVE_STRAND) ? kInfoPositive : 0) | (ref_len == 0 ? kInfoEmpty : 0) |
+                        ((uint32_t)b->mapq[i] << kInfoMapqShift);
+        rec[i] = ReadRec{(int32_t)start, (int32_t)end, (uint32_t)pair_total, info};  // pair_off is chunk-local here
+        cig_off[i] = (uint32_t)c0;
+        md_off[i] = (uint32_t)b->md_off[i];
+        read_contig[i] = (uint32_t)c;
+        pair_total += (read_len + 31) / 32;
       }
+    } catch (const StatusError& e) {
+      ch.err = e;
     }
-    if (c1 == c0) simple = false;
-    if ((uint64_t)consumed != read_len) fail(GUAC_ERR_INVALID_CIGAR, "read %llu: CIGAR consumes %lld bases, the read has %llu", (unsigned long long)i, (long long)consumed, (unsigned long long)read_len);
-    const int64_t end = start + ref_len;
-    if (end > 0x7FFFFF00ll) fail(GUAC_ERR_UNSUPPORTED, "read %llu: coordinates beyond 2^31", (unsigned long long)i);
-    if (b->contig_length && end > b->contig_length[c]) fail(GUAC_ERR_INVALID_ARGUMENT, "read %llu ends past its contig", (unsigned long long)i);
-    if (simple && lead > 0xFFFF) simple = false;
-    contig_end[c] = std::max(contig_end[c], end);
-    out.max_ref_span = std::max<int64_t>(out.max_ref_span, ref_len);
-    uint32_t info = (uint32_t)(simple ? (lead & 0xFFFF) : 0) | (simple ? kInfoSimple : 0) |
-                    ((b->flags[i] & GUAC_READ_POSITIVE_STRAND) ? kInfoPositive : 0) | (ref_len == 0 ? kInfoEmpty : 0) |
-                    ((uint32_t)b->mapq[i] << kInfoMapqShift);
-    rec[i] = ReadRec{(int32_t)start, (int32_t)end, (uint32_t)pair_total, info};
-    cig_off[i] = (uint32_t)c0;
-    md_off[i] = (uint32_t)b->md_off[i];
-    read_contig[i] = (uint32_t)c;
-    pair_total += (read_len + 31) / 32;
-    if (pair_total >= 0xFFFFFF00ull) fail(GUAC_ERR_UNSUPPORTED, "more than 2^37 bases in one read set: shard it");
+    ch.pairs = pair_total;
+  };
+  for (size_t k = 0; k < n_chunks; ++k) {
+    chunks[k].begin = n * k / n_chunks;
+    chunks[k].end = n * (k + 1) / n_chunks;
+  }
+  {
+    std::vector<std::thread> th;
+    for (size_t k = 1; k < n_chunks; ++k) th.emplace_back(header_pass, std::ref(chunks[k]));
+    header_pass(chunks[0]);
+    for (auto& t : th) t.join();
+  }
+  uint64_t pair_total = 0;
+  {
+    std::vector<char> contig_seen(b->n_contigs, 0);
+    int32_t open_contig = -1;
+    for (auto& ch : chunks) {
+      if (ch.err.code != GUAC_OK) throw ch.err;  // chunks are in read order: the first failing read wins
+      for (auto& run : ch.runs) {
+        if (contig_seen[run.second]) fail(GUAC_ERR_CONTIG_ORDER, "Regions are not sorted by contig (read %llu)", (unsigned long long)run.first);
+        contig_seen[run.second] = 1;
+        if (open_contig >= 0) contig_last[open_contig] = run.first;
+        open_contig = run.second;
+        contig_first[run.second] = run.first;
+      }
+      for (uint32_t c = 0; c < b->n_contigs; ++c) contig_end[c] = std::max(contig_end[c], ch.contig_end[c]);
+      out.max_ref_span = std::max(out.max_ref_span, ch.max_span);
+      const uint64_t base = pair_total;
+      pair_total += ch.pairs;
+      if (pair_total >= 0xFFFFFF00ull) fail(GUAC_ERR_UNSUPPORTED, "more than 2^37 bases in one read set: shard it");
+      ch.pairs = base;  // now the chunk's base offset
+    }
+    if (open_contig >= 0) contig_last[open_contig] = n;
+    std::vector<std::thread> th;
+    auto rebase = [&](const Chunk& ch) {
+      if (ch.pairs == 0) return;
+      for (uint64_t i = ch.begin; i < ch.end; ++i) rec[i].pair_off += (uint32_t)ch.pairs;
+    };
+    for (size_t k = 1; k < n_chunks; ++k) th.emplace_back(rebase, std::cref(chunks[k]));
+    rebase(chunks[0]);
+    for (auto& t : th) t.join();
   }
   rec[n] = ReadRec{0x7FFFFFFF, 0x7FFFFFFF, (uint32_t)pair_total, 0};
   cig_off[n] = (uint32_t)b->cigar_off[n];
   md_off[n] = (uint32_t)b->md_off[n];
 
+  tr.lap("header pass");
   // ---- contig geometry
   out.contigs.resize(b->n_contigs);
   uint64_t word_off = 0, gran_off = 0;
@@ -129,18 +188,18 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
 
   // ---- H2D of the raw columns
   cudaStream_t st = ctx->stream;
-  h2d(ctx, out.rec, rec.data(), n + 1);
-  h2d(ctx, out.cig_off, cig_off.data(), n + 1);
+  h2d(ctx, out.rec, rec, n + 1);
+  h2d(ctx, out.cig_off, cig_off, n + 1);
   h2d(ctx, out.cigar, b->cigar, (size_t)b->cigar_off[n], 1);
   h2d(ctx, out.seq_off, b->seq_off, n + 1);
   h2d(ctx, out.seq, b->seq, (size_t)b->seq_off[n], 64);
   out.has_qualities = ctx->pack_qualities != 0;
   if (out.has_qualities) h2d(ctx, out.qual, b->qual, (size_t)b->seq_off[n], 64);
-  h2d(ctx, out.md_off, md_off.data(), n + 1);
+  h2d(ctx, out.md_off, md_off, n + 1);
   h2d(ctx, out.md, b->md, (size_t)b->md_off[n], 16);
   h2d(ctx, out.d_contigs, out.contigs.data(), out.contigs.size());
   DevBuf<uint32_t> d_read_contig, conflict, gran_count;
-  h2d(ctx, d_read_contig, read_contig.data(), n);
+  h2d(ctx, d_read_contig, read_contig, n);
   out.pairs.alloc(pair_total + 8);
   out.xmask.alloc(pair_total + 8);
   out.nm.alloc(n);
@@ -168,6 +227,8 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   out.h2d_bytes = out.rec.bytes() + out.cig_off.bytes() * 2 + out.cigar.bytes() + out.seq_off.bytes() + out.seq.bytes() +
                   out.qual.bytes() + out.md.bytes() + out.d_contigs.bytes() + d_read_contig.bytes() + out.fasta.bytes();
 
+  if (tr.on) cudaStreamSynchronize(st);
+  tr.lap("alloc + h2d");
   PackArgs A;
   A.R = out.view();
   A.rec_w = out.rec.p;
@@ -214,6 +275,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   out.pack_kernel_ms = ms;
   out.order_sensitive_loci = counters[0];
   out.max_reads_per_granule = counters[1];
+  tr.lap("kernels");
 }
 
 // ---- tiles over the requested loci -------------------------------------------------------------------------------------------
@@ -377,46 +439,42 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       cap_pool = std::max<uint64_t>(cap_pool, kPoolDynOff + c[1] + c[1] / 8 + 16);
       continue;
     }
-    // ---- D2H (+ canonical order unless switched off)
+    // ---- D2H through pinned staging (+ canonical order unless switched off).  Records keep their offsets into the pool,
+    // which is returned whole: no per-record work on the host.
     const uint64_t n_rec = c[0];
-    std::vector<uint8_t> pool((size_t)(kPoolDynOff + c[1]));
-    CUDA_OK(cudaMemcpyAsync(pool.data(), ctx->out_pool.p, pool.size(), cudaMemcpyDeviceToHost, st));
-    res.stats.d2h_bytes = pool.size() + n_rec * rec_size + 8 * sizeof(unsigned long long);
+    const size_t pool_bytes = (size_t)(kPoolDynOff + c[1]), rec_bytes = (size_t)(n_rec * rec_size);
+    unsigned char* hs = stage(ctx, pool_bytes + rec_bytes + 64);
+    CUDA_OK(cudaMemcpyAsync(hs, ctx->out_pool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
+    unsigned char* hrec = hs + ((pool_bytes + 63) & ~(size_t)63);
+    if (n_rec) CUDA_OK(cudaMemcpyAsync(hrec, ctx->out_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    res.stats.d2h_bytes = pool_bytes + rec_bytes + 8 * sizeof(unsigned long long);
     if (prm.mode == 1) {
       res.counts.resize((size_t)n_rec);
-      if (n_rec) CUDA_OK(cudaMemcpyAsync(res.counts.data(), ctx->out_rec.p, n_rec * rec_size, cudaMemcpyDeviceToHost, st));
-      CUDA_OK(cudaStreamSynchronize(st));
+      if (n_rec) memcpy(res.counts.data(), hrec, rec_bytes);
       append_rows_past_track();
       if (ctx->sort_records)
         std::sort(res.counts.begin(), res.counts.end(), [](const guac_locus_counts& a, const guac_locus_counts& b) {
           return std::make_pair(a.contig, a.locus) < std::make_pair(b.contig, b.locus);
         });
     } else {
-      std::vector<guac_threshold_record> recs((size_t)n_rec);
-      if (n_rec) CUDA_OK(cudaMemcpyAsync(recs.data(), ctx->out_rec.p, n_rec * rec_size, cudaMemcpyDeviceToHost, st));
-      CUDA_OK(cudaStreamSynchronize(st));
+      res.threshold.resize((size_t)n_rec);
+      if (n_rec) memcpy(res.threshold.data(), hrec, rec_bytes);
+      res.bytes.assign(hs, hs + pool_bytes);
       if (ctx->sort_records) {
-        auto str = [&](uint32_t off, uint16_t len) { return std::string((const char*)pool.data() + off, len); };
-        std::sort(recs.begin(), recs.end(), [&](const guac_threshold_record& a, const guac_threshold_record& b) {
+        const uint8_t* pool = res.bytes.data();
+        std::sort(res.threshold.begin(), res.threshold.end(), [pool](const guac_threshold_record& a, const guac_threshold_record& b) {
           if (a.contig != b.contig) return a.contig < b.contig;
           if (a.start != b.start) return a.start < b.start;
           if (a.sample != b.sample) return a.sample < b.sample;
-          std::string ra = str(a.ref_off, a.ref_len), rb = str(b.ref_off, b.ref_len);
-          if (ra != rb) return ra < rb;
-          return str(a.alt_off, a.alt_len) < str(b.alt_off, b.alt_len);
+          int c = memcmp(pool + a.ref_off, pool + b.ref_off, std::min(a.ref_len, b.ref_len));
+          if (c != 0) return c < 0;
+          if (a.ref_len != b.ref_len) return a.ref_len < b.ref_len;
+          c = memcmp(pool + a.alt_off, pool + b.alt_off, std::min(a.alt_len, b.alt_len));
+          if (c != 0) return c < 0;
+          return a.alt_len < b.alt_len;
         });
       }
-      res.bytes.clear();
-      res.bytes.reserve(recs.size() * 2 + 16);
-      for (auto& r : recs) {  // compact the byte pool in record order
-        uint32_t ro = (uint32_t)res.bytes.size();
-        res.bytes.insert(res.bytes.end(), pool.begin() + r.ref_off, pool.begin() + r.ref_off + r.ref_len);
-        uint32_t ao = (uint32_t)res.bytes.size();
-        res.bytes.insert(res.bytes.end(), pool.begin() + r.alt_off, pool.begin() + r.alt_off + r.alt_len);
-        r.ref_off = ro;
-        r.alt_off = ao;
-      }
-      res.threshold = std::move(recs);
     }
     res.stats.loci_visited = c[3] + (prm.mode == 1 ? res.counts.size() - n_rec : 0);
     res.stats.tie_loci = c[4];
@@ -471,6 +529,7 @@ guac_status guac_ctx_create(int device, guac_ctx** out) {
   guac_status s = guarded(ctx, [&] {
     CUDA_OK(cudaSetDevice(device));
     CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+
     CUDA_OK(cudaMalloc((void**)&ctx->d_err, sizeof(DevError)));
     CUDA_OK(cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(unsigned long long)));
     CUDA_OK(cudaMemset(ctx->d_err, 0, sizeof(DevError)));
@@ -494,12 +553,15 @@ void guac_ctx_destroy(guac_ctx* ctx) {
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
   ctx->out_rec.release();
   ctx->out_pool.release();
   ctx->out_slow.release();
   ctx->tiles.release();
+  tl_dev_cache.trim();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

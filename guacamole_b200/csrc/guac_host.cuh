@@ -2,10 +2,13 @@
 // results.  (Internal; the public contract is include/guac.h.)
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <new>
 #include <string>
@@ -43,23 +46,75 @@ struct StatusError {
            cudaGetErrorString(e_), __FILE__, __LINE__);                                                        \
   } while (0)
 
+// Device buffers come from a small exact-size cache kept per host thread (i.e. per context user): repeated pack / call
+// cycles over batches of the same shape reuse their allocations instead of paying cudaMalloc / cudaFree every time.
+struct DevCache {
+  std::multimap<std::pair<int, size_t>, void*> free_blocks;  // (device, bytes) -> block
+  size_t cached_bytes = 0;
+  static constexpr size_t kMaxCachedBytes = 64ull << 30;
+  static int device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+  }
+  void* take(size_t bytes) {
+    auto it = free_blocks.find({device(), bytes});
+    if (it == free_blocks.end()) return nullptr;
+    void* p = it->second;
+    free_blocks.erase(it);
+    cached_bytes -= bytes;
+    return p;
+  }
+  void give(void* p, size_t bytes) {
+    if (cached_bytes + bytes > kMaxCachedBytes || free_blocks.size() >= 512) {
+      cudaFree(p);
+      return;
+    }
+    free_blocks.emplace(std::make_pair(device(), bytes), p);
+    cached_bytes += bytes;
+  }
+  void trim() {
+    for (auto& kv : free_blocks) cudaFree(kv.second);
+    free_blocks.clear();
+    cached_bytes = 0;
+  }
+  ~DevCache() { trim(); }
+};
+static thread_local DevCache tl_dev_cache;
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  size_t alloc_bytes = 0;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) tl_dev_cache.give(p, alloc_bytes);
     p = nullptr;
     n = 0;
+    alloc_bytes = 0;
   }
   void alloc(size_t count) {
     release();
     n = count;
-    CUDA_OK(cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
+    alloc_bytes = ((std::max<size_t>(count, 1) * sizeof(T)) + 255) & ~(size_t)255;
+    p = (T*)tl_dev_cache.take(alloc_bytes);
+    if (!p) {
+      cudaError_t e = cudaMalloc((void**)&p, alloc_bytes);
+      if (e == cudaErrorMemoryAllocation) {  // give the cache back and retry once
+        cudaGetLastError();
+        tl_dev_cache.trim();
+        e = cudaMalloc((void**)&p, alloc_bytes);
+      }
+      if (e != cudaSuccess) {
+        p = nullptr;
+        n = 0;
+        fail(e == cudaErrorMemoryAllocation ? GUAC_ERR_OOM : GUAC_ERR_CUDA, "cudaMalloc(%zu bytes): %s", alloc_bytes, cudaGetErrorString(e));
+      }
+    }
   }
   bool ensure(size_t count) {  // grow-only; true if (re)allocated
     if (p && n >= count) return false;
@@ -90,6 +145,12 @@ struct guac_ctx {
   const void* tiles_key_reads = nullptr;
   uint64_t tiles_key_loci = 0, n_tiles = 0;
   bool pool_head_ready = false;
+  // pinned host staging for result downloads (grow-only)
+  unsigned char* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+  // pinned host arena for the per-read header columns built by guac_reads_pack (grow-only)
+  unsigned char* h_pack = nullptr;
+  size_t h_pack_bytes = 0;
   // somatic tables (device): see guac_somatic.cuh
   double* d_tables = nullptr;
 };
@@ -126,6 +187,43 @@ void h2d(guac_ctx* ctx, DevBuf<T>& dst, const T* src, size_t n, size_t extra = 0
   if (extra) CUDA_OK(cudaMemsetAsync(dst.p + n, 0, extra * sizeof(T), ctx->stream));
   if (n) CUDA_OK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
 }
+
+unsigned char* stage(guac_ctx* ctx, size_t bytes) {
+  if (ctx->h_stage_bytes < bytes) {
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr;
+    ctx->h_stage_bytes = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    CUDA_OK(cudaMallocHost((void**)&ctx->h_stage, want));
+    ctx->h_stage_bytes = want;
+  }
+  return ctx->h_stage;
+}
+
+unsigned char* pack_arena(guac_ctx* ctx, size_t bytes) {
+  if (ctx->h_pack_bytes < bytes) {
+    if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
+    ctx->h_pack = nullptr;
+    ctx->h_pack_bytes = 0;
+    size_t want = bytes + bytes / 8 + 4096;
+    CUDA_OK(cudaMallocHost((void**)&ctx->h_pack, want));
+    ctx->h_pack_bytes = want;
+  }
+  return ctx->h_pack;
+}
+
+struct Trace {  // GUAC_TRACE=1 prints host-side phase times (diagnostics only)
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  const char* what;
+  Trace(const char* w) : on(getenv("GUAC_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), what(w) {}
+  void lap(const char* phase) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[guac %s] %-18s %8.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 int grid_for(uint64_t n, int block, int sm_count) {
   uint64_t g = (n + block - 1) / block;

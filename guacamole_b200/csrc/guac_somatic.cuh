@@ -759,32 +759,29 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
       continue;
     }
     const uint64_t n_rec = c[0];
-    std::vector<uint8_t> pool((size_t)(kPoolDynOff + c[1]));
-    std::vector<guac_somatic_record> recs((size_t)n_rec);
-    CUDA_OK(cudaMemcpyAsync(pool.data(), ctx->out_pool.p, pool.size(), cudaMemcpyDeviceToHost, st));
-    if (n_rec) CUDA_OK(cudaMemcpyAsync(recs.data(), ctx->out_rec.p, n_rec * sizeof(guac_somatic_record), cudaMemcpyDeviceToHost, st));
+    const size_t pool_bytes = (size_t)(kPoolDynOff + c[1]), rec_bytes = (size_t)(n_rec * sizeof(guac_somatic_record));
+    unsigned char* hs = stage(ctx, pool_bytes + rec_bytes + 64);
+    CUDA_OK(cudaMemcpyAsync(hs, ctx->out_pool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
+    unsigned char* hrec = hs + ((pool_bytes + 63) & ~(size_t)63);
+    if (n_rec) CUDA_OK(cudaMemcpyAsync(hrec, ctx->out_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    res.stats.d2h_bytes = pool.size() + n_rec * sizeof(guac_somatic_record) + 64;
+    res.stats.d2h_bytes = pool_bytes + rec_bytes + 64;
+    res.somatic.resize((size_t)n_rec);
+    if (n_rec) memcpy(res.somatic.data(), hrec, rec_bytes);
+    res.bytes.assign(hs, hs + pool_bytes);
     if (ctx->sort_records) {
-      auto str = [&](uint32_t off, uint16_t len) { return std::string((const char*)pool.data() + off, len); };
-      std::sort(recs.begin(), recs.end(), [&](const guac_somatic_record& a, const guac_somatic_record& b) {
+      const uint8_t* pool = res.bytes.data();
+      std::sort(res.somatic.begin(), res.somatic.end(), [pool](const guac_somatic_record& a, const guac_somatic_record& b) {
         if (a.contig != b.contig) return a.contig < b.contig;
         if (a.start != b.start) return a.start < b.start;
-        std::string ra = str(a.ref_off, a.ref_len), rb = str(b.ref_off, b.ref_len);
-        if (ra != rb) return ra < rb;
-        return str(a.alt_off, a.alt_len) < str(b.alt_off, b.alt_len);
+        int c = memcmp(pool + a.ref_off, pool + b.ref_off, std::min(a.ref_len, b.ref_len));
+        if (c != 0) return c < 0;
+        if (a.ref_len != b.ref_len) return a.ref_len < b.ref_len;
+        c = memcmp(pool + a.alt_off, pool + b.alt_off, std::min(a.alt_len, b.alt_len));
+        if (c != 0) return c < 0;
+        return a.alt_len < b.alt_len;
       });
     }
-    res.bytes.clear();
-    for (auto& r : recs) {
-      uint32_t ro = (uint32_t)res.bytes.size();
-      res.bytes.insert(res.bytes.end(), pool.begin() + r.ref_off, pool.begin() + r.ref_off + r.ref_len);
-      uint32_t ao = (uint32_t)res.bytes.size();
-      res.bytes.insert(res.bytes.end(), pool.begin() + r.alt_off, pool.begin() + r.alt_off + r.alt_len);
-      r.ref_off = ro;
-      r.alt_off = ao;
-    }
-    res.somatic = std::move(recs);
     res.stats.loci_visited = c[3];
     res.stats.records = n_rec;
     res.stats.exact_loci = c[2];
