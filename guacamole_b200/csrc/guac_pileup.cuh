@@ -148,7 +148,7 @@ __device__ __forceinline__ void count_bits(CntT* cnt_word, uint32_t bits, uint32
 }
 
 template <typename CntT, int MODE>
-__global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const TileDesc* __restrict__ tiles, CallParams prm, DevOut out) {
+__global__ void __launch_bounds__(kTileThreads, 5) k_pileup_tile(DevReads R, const TileDesc* __restrict__ tiles, CallParams prm, DevOut out) {
   constexpr int FB = sizeof(CntT) * 2;
   constexpr uint32_t FMASK = (1u << FB) - 1u;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -298,8 +298,11 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
   // ---- phase 1b: the listed reads, one per thread again (full lanes on the slow path)
   {
     const uint32_t n_list = min(S.n_list, (uint32_t)kListCap);
+    constexpr uint32_t kWarps = kTileThreads / 32;
     for (uint32_t base = 0; base < n_list; base += kTileThreads) {
-      const uint32_t i = base + tid;
+      // interleave the listed reads over the warps (lane * kWarps + warp): a handful of slow reads should not leave seven
+      // warps waiting at the barrier for one
+      const uint32_t i = base + (uint32_t)(tid & 31) * kWarps + (uint32_t)(tid >> 5);
       const bool active = i < n_list;
       const uint32_t r = active ? S.list[i] : 0u;
       ReadRec rec{0, 0, 0, 0};
@@ -365,6 +368,9 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     const int locus = tile_lo + x;
     if (locus < td.locus_begin || locus >= td.locus_end) continue;
     const int total = (int)S.cov[cov_index(x)];
+    // cheap reject of the commonest dirty locus: every class seen at most once and one read cannot pass the threshold
+    constexpr CntT kOnes = sizeof(CntT) == 8 ? (CntT)0x0001000100010001ull : (CntT)0x01010101u;
+    if (std_ref && !every_covered && (c & ~kOnes) == 0 && 100 < (prm.threshold_percent + 1) * total) continue;
     if (total == 0 && !all_loci) continue;  // callVariantsAtLocus returns nothing on an empty pileup
     const int o = (int)((uint32_t)c & FMASK);
     const int m1 = (int)((uint32_t)(c >> FB) & FMASK), m2 = (int)((uint32_t)(c >> (2 * FB)) & FMASK), m3 = (int)((uint32_t)(c >> (3 * FB)) & FMASK);
