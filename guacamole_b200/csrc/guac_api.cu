@@ -288,12 +288,12 @@ uint64_t build_tiles(const guac_reads& reads, const guac_locus_range* ranges, si
     requested += (uint64_t)(r.end - r.start);
     const ContigInfo& ci = reads.contigs[r.contig];
     int64_t s = r.start, e = std::min<int64_t>(r.end, ci.length);  // loci past the track hold no reads
-    for (int64_t t = s / kTileLoci; t * kTileLoci < e; ++t) {
+    for (int64_t t = s / kWarpLoci; t * kWarpLoci < e; ++t) {  // one descriptor per granule = per warp
       TileDesc td;
       td.contig = r.contig;
-      td.word0 = (int32_t)(t * kTileWords);
-      td.locus_begin = (int32_t)std::max<int64_t>(s, t * kTileLoci);
-      td.locus_end = (int32_t)std::min<int64_t>(e, (t + 1) * kTileLoci);
+      td.word0 = (int32_t)(t * kWarpWords);
+      td.locus_begin = (int32_t)std::max<int64_t>(s, t * kWarpLoci);
+      td.locus_end = (int32_t)std::min<int64_t>(e, (t + 1) * kWarpLoci);
       if (td.locus_end > td.locus_begin) tiles.push_back(td);
     }
   }
@@ -302,13 +302,15 @@ uint64_t build_tiles(const guac_reads& reads, const guac_locus_range* ranges, si
 
 template <int MODE>
 void launch_tile(bool wide, int grid, cudaStream_t st, const DevReads& R, const TileDesc* tiles, const CallParams& prm, const DevOut& out) {
-  if (wide) k_pileup_tile<uint64_t, MODE><<<grid, kTileThreads, sizeof(TileSmem<uint64_t, MODE>), st>>>(R, tiles, prm, out);
-  else k_pileup_tile<uint32_t, MODE><<<grid, kTileThreads, sizeof(TileSmem<uint32_t, MODE>), st>>>(R, tiles, prm, out);
+  const uint32_t n = (uint32_t)grid;  // descriptors (one per warp)
+  const int ctas = (int)((n + kWarpsPerCta - 1) / kWarpsPerCta);
+  if (wide) k_pileup_tile<uint64_t, MODE><<<ctas, kTileThreads, kWarpsPerCta * sizeof(WarpSmem<uint64_t, MODE>), st>>>(R, tiles, n, prm, out);
+  else k_pileup_tile<uint32_t, MODE><<<ctas, kTileThreads, kWarpsPerCta * sizeof(WarpSmem<uint32_t, MODE>), st>>>(R, tiles, n, prm, out);
 }
 
 template <typename CntT, int MODE>
 void set_smem_attr() {
-  CUDA_OK(cudaFuncSetAttribute(k_pileup_tile<CntT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<CntT, MODE>)));
+  CUDA_OK(cudaFuncSetAttribute(k_pileup_tile<CntT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kWarpsPerCta * sizeof(WarpSmem<CntT, MODE>))));
 }
 void set_all_smem_attrs() {
   set_smem_attr<uint32_t, 0>(); set_smem_attr<uint64_t, 0>(); set_smem_attr<uint32_t, 1>(); set_smem_attr<uint64_t, 1>();

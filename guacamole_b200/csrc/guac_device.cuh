@@ -20,7 +20,7 @@ namespace guac {
 
 constexpr int kGranuleShift = 10;               // 1024 loci per granule
 constexpr int kGranuleLoci = 1 << kGranuleShift;
-constexpr int kTileWords = 128;                 // one CTA = 128 threads = 128 words = 4096 loci
+constexpr int kTileWords = 128;                 // somatic kernel: one CTA per 128 words = 4096 loci
 constexpr int kTileLoci = kTileWords * 32;
 constexpr int kChunkReads = 512;                // reads staged per chunk
 constexpr int kChunkPairs = 4096;               // plane pairs staged per chunk (32 KB)

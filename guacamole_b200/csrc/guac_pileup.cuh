@@ -112,23 +112,31 @@ __device__ __noinline__ Aligned align_cigar(const DevReads& R, uint64_t r, const
 }
 
 // ---- K_tile ---------------------------------------------------------------------------------------------------------------
+// One WARP owns one granule of 1024 loci and everything about it — its slice of shared memory, its reads, its scan, its
+// calls — so the kernel has no block-wide barrier at all: warps of a CTA (and of the other resident CTAs) progress
+// independently and hide one another's memory latency.  Reads crossing a granule boundary are handled by both owners
+// (for 150 bp reads: 15 % more read work than one 4096-loci tile per CTA, bought back by the missing barrier stalls).
+//
 // Per-locus counter word: four fields of FB bits — [0] "other" elements, [1..3] mismatches by class (lo ^ ref_lo) |
 // (hi ^ ref_hi) << 1, i.e. read base code = reference code ^ class.  CntT = uint32_t (8-bit fields, pileups < 256 deep) or
 // uint64_t (16-bit fields, < 65536 deep).  Depth (and, in counts mode, positive-strand depth) come from difference arrays.
-constexpr int kTileThreads = 256;              // 16 loci per thread in the scan / caller phases
+constexpr int kWarpWords = kGranuleLoci / 32;   // 32 words = 1024 loci per warp
+constexpr int kWarpLoci = kGranuleLoci;
+constexpr int kWarpsPerCta = 4;
+constexpr int kTileThreads = kWarpsPerCta * 32;
+constexpr int kListCap = 64;                    // reads of one granule that need the CIGAR walk (overflow handled inline)
 __host__ __device__ constexpr int cov_index(int i) { return i + (i >> 5); }  // one pad word per 32: conflict-free scan
-
-constexpr int kListCap = 1024;  // reads of one tile that need the CIGAR walk (kept in shared memory; overflow handled inline)
+constexpr int kCovWords = cov_index(kWarpLoci + 32) + 1;
 
 template <typename CntT, int MODE>
-struct TileSmem {
-  uint32_t ref_lo[kTileWords], ref_hi[kTileWords], ref_std[kTileWords];
-  uint32_t cov[cov_index(kTileLoci + 32) + 1];
-  uint32_t pos[MODE == 1 ? cov_index(kTileLoci + 32) + 1 : 1];  // positive-strand difference array (counts mode only)
-  CntT cnt[kTileLoci];
+struct WarpSmem {
+  uint32_t ref_lo[kWarpWords], ref_hi[kWarpWords], ref_std[kWarpWords];   // ref_hi must follow ref_lo
+  uint32_t cov[kCovWords];
+  uint32_t pos[MODE == 1 ? kCovWords : 1];  // positive-strand difference array (counts mode only)
+  CntT cnt[kWarpLoci];
   uint32_t list[kListCap];
-  uint32_t warp_sum[kTileThreads / 32];
-  uint32_t first, last, n_list, next;
+  uint32_t n_list;
+  uint32_t pad_[3];
 };
 
 // one shared-memory atomic per set bit; lanes loop independently and the warp reconverges right after
@@ -148,52 +156,43 @@ __device__ __forceinline__ void count_bits(CntT* cnt_word, uint32_t bits, uint32
 }
 
 template <typename CntT, int MODE>
-__global__ void __launch_bounds__(kTileThreads, 5) k_pileup_tile(DevReads R, const TileDesc* __restrict__ tiles, CallParams prm, DevOut out) {
+__global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const TileDesc* __restrict__ tiles, uint32_t n_tiles, CallParams prm, DevOut out) {
   constexpr int FB = sizeof(CntT) * 2;
   constexpr uint32_t FMASK = (1u << FB) - 1u;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<CntT, MODE>& S = *reinterpret_cast<TileSmem<CntT, MODE>*>(smem_raw);
-  const TileDesc td = tiles[blockIdx.x];
+  const int lane = threadIdx.x & 31;
+  const uint32_t tile = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (tile >= n_tiles) return;  // whole warp
+  WarpSmem<CntT, MODE>& S = reinterpret_cast<WarpSmem<CntT, MODE>*>(smem_raw)[threadIdx.x >> 5];
+  const TileDesc td = tiles[tile];
   const ContigInfo ci = R.contigs[td.contig];
-  const int tid = threadIdx.x;
   const int tile_lo = td.word0 << 5;
-  const int tile_hi = min(tile_lo + kTileLoci, ci.n_words << 5);
+  const int tile_hi = min(tile_lo + kWarpLoci, ci.n_words << 5);
 
-  // ---- phase 0: clear the counter tile, stage the reference planes, find the candidate reads through the granule index
-  for (int i = tid; i < kTileLoci; i += kTileThreads) S.cnt[i] = 0;
-  for (int i = tid; i < cov_index(kTileLoci + 32) + 1; i += kTileThreads) {
+  // ---- phase 0: clear the counter slice, stage the reference planes, candidate reads of the granule
+  for (int i = lane; i < kWarpLoci; i += 32) S.cnt[i] = 0;
+  for (int i = lane; i < kCovWords; i += 32) {
     S.cov[i] = 0;
     if (MODE == 1) S.pos[i] = 0;
   }
-  if (tid < kTileWords) {
-    const int w = td.word0 + tid;
-    const bool in = w < ci.n_words;
-    S.ref_lo[tid] = in ? R.trk_lo[ci.word_off + w] : 0u;
-    S.ref_hi[tid] = in ? R.trk_hi[ci.word_off + w] : 0u;
-    S.ref_std[tid] = in ? R.trk_std[ci.word_off + w] : 0u;
-  }
-  if (tid == 0) {
-    S.first = 0xFFFFFFFFu;
-    S.last = 0;
-    S.n_list = 0;
-  }
-  __syncthreads();
   {
-    const int g0 = tile_lo >> kGranuleShift;
-    const int g1 = min(tile_lo + kTileLoci - 1, ci.length - 1) >> kGranuleShift;
-    const int g = g0 + tid;
-    if (g <= g1 && g < ci.n_grans) {
-      const uint32_t f = R.gran_first[ci.gran_off + g], l = R.gran_last[ci.gran_off + g];
-      if (f != 0xFFFFFFFFu) {
-        atomicMin(&S.first, f);
-        atomicMax(&S.last, l);
-      }
-    }
+    const int w = td.word0 + lane;
+    const bool in = w < ci.n_words;
+    S.ref_lo[lane] = in ? R.trk_lo[ci.word_off + w] : 0u;
+    S.ref_hi[lane] = in ? R.trk_hi[ci.word_off + w] : 0u;
+    S.ref_std[lane] = in ? R.trk_std[ci.word_off + w] : 0u;
   }
-  __syncthreads();
-  const uint32_t first = S.first, last = S.first == 0xFFFFFFFFu ? 0u : S.last;
-  if (tid == 0) S.next = first;
-  __syncthreads();
+  if (lane == 0) S.n_list = 0;
+  uint32_t first = 0xFFFFFFFFu, last = 0;
+  {
+    const int g = tile_lo >> kGranuleShift;
+    if (g < ci.n_grans) {
+      first = R.gran_first[ci.gran_off + g];
+      last = R.gran_last[ci.gran_off + g];
+    }
+    if (first == 0xFFFFFFFFu) last = 0;
+  }
+  __syncwarp();
 
   // general path for one read (CIGAR walk / exception mask), one word at a time
   auto general_read = [&](uint32_t r, const ReadRec rec, bool active, int w0, int w1) {
@@ -223,24 +222,15 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_pileup_tile(DevReads R, con
     }
   };
 
-  // ---- phase 1a: one read per thread; SIMPLE reads take the fast path, the others are listed for phase 1b
-  // Warps grab 32 reads at a time from a shared cursor (balances the warps ahead of the barrier) and fetch the records
-  // of their next batch before working on the current one.
-  const int lane = tid & 31;
-  auto grab = [&]() {
-    uint32_t b = 0;
-    if (lane == 0) b = atomicAdd(&S.next, 32u);
-    return __shfl_sync(0xFFFFFFFFu, b, 0);
-  };
-  uint32_t base = grab();
+  // ---- phase 1a: one read per lane; SIMPLE reads take the fast path, the others are listed for phase 1b.  The records
+  // of the next batch are fetched before the current one is worked on.
   ReadRec rec_next{0, 0, 0, 0};
-  if (base + lane < last) rec_next = R.rec[base + lane];
-  while (base < last) {  // warp-uniform
+  if (first + lane < last) rec_next = R.rec[first + lane];
+  for (uint32_t base = first; base < last; base += 32) {  // warp-uniform
     const uint32_t r = base + lane;
     const ReadRec rec = rec_next;
-    const uint32_t nbase = grab();
     rec_next = ReadRec{0, 0, 0, 0};
-    if (nbase + lane < last) rec_next = R.rec[nbase + lane];
+    if (r + 32 < last) rec_next = R.rec[r + 32];
     const bool active = r < last && rec.end > tile_lo && rec.start < tile_hi && rec.end > rec.start;
     int w0 = 0, w1 = -1;
     if (active) {
@@ -283,26 +273,22 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_pileup_tile(DevReads R, con
         uint32_t valid = k == 0 ? first_mask : 0xFFFFFFFFu;
         if (w == w1) valid &= last_mask;
         x = (__funnelshift_r(pa.x, pb.x, sh) ^ ref_lo[k]) & valid;
-        y = (__funnelshift_r(pa.y, pb.y, sh) ^ ref_lo[k + kTileWords]) & valid;  // ref_hi follows ref_lo in shared memory
+        y = (__funnelshift_r(pa.y, pb.y, sh) ^ ref_lo[k + kWarpWords]) & valid;  // ref_hi follows ref_lo in shared memory
         pa = pb;
         if (w < w1) pb = __ldg(P);
         ++P;
       }
       count_bits<CntT>(cnt_word + (k << 5), x | y, x, y);
     }
-    if (__any_sync(0xFFFFFFFFu, slow_now)) general_read(r, rec, slow_now, w0, w1);  // list overflow (very deep tiles)
+    if (__any_sync(0xFFFFFFFFu, slow_now)) general_read(r, rec, slow_now, w0, w1);  // list overflow (very deep granules)
     __syncwarp();
-    base = nbase;
   }
-  __syncthreads();
-  // ---- phase 1b: the listed reads, one per thread again (full lanes on the slow path)
+  __syncwarp();
+  // ---- phase 1b: the listed reads, one per lane again
   {
     const uint32_t n_list = min(S.n_list, (uint32_t)kListCap);
-    constexpr uint32_t kWarps = kTileThreads / 32;
-    for (uint32_t base = 0; base < n_list; base += kTileThreads) {
-      // interleave the listed reads over the warps (lane * kWarps + warp): a handful of slow reads should not leave seven
-      // warps waiting at the barrier for one
-      const uint32_t i = base + (uint32_t)(tid & 31) * kWarps + (uint32_t)(tid >> 5);
+    for (uint32_t base = 0; base < n_list; base += 32) {
+      const uint32_t i = base + lane;
       const bool active = i < n_list;
       const uint32_t r = active ? S.list[i] : 0u;
       ReadRec rec{0, 0, 0, 0};
@@ -316,32 +302,26 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_pileup_tile(DevReads R, con
       __syncwarp();
     }
   }
-  __syncthreads();
+  __syncwarp();
 
   // ---- phase 2: inclusive scan of the difference array(s) -> depth (and positive-strand depth); visited loci counted here
   uint32_t n_visited = 0;
   bool overflow = false;
   for (int which = 0; which < (MODE == 1 ? 2 : 1); ++which) {
     uint32_t* A = which == 0 ? S.cov : S.pos;
-    constexpr int LPT = kTileLoci / kTileThreads;  // loci per thread (16)
     uint32_t run = 0;
-    const int base = cov_index(tid * LPT);
-#pragma unroll
-    for (int k = 0; k < LPT; ++k) run += A[base + k];
+    const int base = lane * 33;  // 32 loci + 1 pad word per lane
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) run += A[base + k];
     uint32_t incl = run;
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if ((tid & 31) >= o) incl += t;
+      if (lane >= o) incl += t;
     }
-    __syncthreads();
-    if ((tid & 31) == 31) S.warp_sum[tid >> 5] = incl;
-    __syncthreads();
-    uint32_t before = 0;
-    for (int k = 0; k < (tid >> 5); ++k) before += S.warp_sum[k];
-    uint32_t acc = before + incl - run;
+    uint32_t acc = incl - run;
     uint32_t covered = 0;
-#pragma unroll
-    for (int k = 0; k < LPT; ++k) {
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
       acc += A[base + k];
       A[base + k] = acc;
       if (which == 0) {
@@ -350,19 +330,19 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_pileup_tile(DevReads R, con
       }
     }
     if (which == 0) {
-      const int l0 = tile_lo + tid * LPT;
-      const uint32_t in_range = bit_range(td.locus_begin - l0, min(td.locus_end - l0, LPT));
+      const int l0 = tile_lo + (lane << 5);
+      const uint32_t in_range = bit_range(td.locus_begin - l0, td.locus_end - l0);
       n_visited = __popc((prm.skip_empty ? covered : 0xFFFFFFFFu) & in_range);
     }
   }
-  __syncthreads();
+  __syncwarp();
 
-  // ---- phase 3: the caller, one locus per thread per step (stride kTileThreads: conflict-free shared memory)
+  // ---- phase 3: the caller, one locus per lane per step (stride 32: conflict-free shared memory)
   const bool all_loci = MODE == 1 ? !prm.skip_empty : false;          // rows for empty pileups (counts mode only)
   const bool every_covered = MODE == 1 || prm.emit_ref || prm.emit_no_call;
-  for (int x = tid; x < kTileLoci; x += kTileThreads) {
+  for (int x = lane; x < kWarpLoci; x += 32) {
     const CntT c = S.cnt[x];
-    const int w = x >> 5, b = x & 31;
+    const int w = x >> 5, b = x & 31;   // w is warp-uniform
     const bool std_ref = (S.ref_std[w] >> b) & 1u;
     if (c == 0 && std_ref && !every_covered) continue;  // every element matches the reference: nothing to call
     const int locus = tile_lo + x;
@@ -463,7 +443,7 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_pileup_tile(DevReads R, con
   }
   // one atomic per warp for the visited-loci counter
   for (int o = 16; o; o >>= 1) n_visited += __shfl_xor_sync(0xFFFFFFFFu, n_visited, o);
-  if ((tid & 31) == 0 && n_visited) atomicAdd(&out.counters[3], (unsigned long long)n_visited);
+  if (lane == 0 && n_visited) atomicAdd(&out.counters[3], (unsigned long long)n_visited);
   if (overflow) atomicAdd(&out.counters[5], 1ull);
 }
 
