@@ -121,23 +121,32 @@ __device__ int genotype_likelihoods(const AlleleView& av, const SomAllele* tab, 
   return ng;
 }
 
-// findPotentialVariantAtLocus once both filtered pileups are summarised.  tabT / tabN sorted by Allele.compare.
-__device__ void decide_somatic(const DevReads& RT, const AlleleView& avT, const AlleleView& avN, const SomAllele* tabT,
-                               const SampleStats& sT, const SomAllele* tabN, const SampleStats& sN, int contig, int locus,
-                               const SomParams& prm, SomOut& out) {
-  if (sT.depth == 0 || sN.depth == 0 || sT.depth > prm.max_read_depth || sN.depth > prm.max_read_depth || sT.ref_depth == sT.depth) return;
+// findPotentialVariantAtLocus, tumor half: early outs + the most likely tumor genotype.  Returns true when that genotype
+// holds a variant allele (only then does the reference look at the normal sample); a1 / a2 / tumor_l describe it.
+__device__ bool tumor_most_likely(const AlleleView& avT, const SomAllele* tabT, const SampleStats& sT, int contig, int locus,
+                                  const SomParams& prm, SomOut& out, AlleleEntry* a1, AlleleEntry* a2, double* tumor_l) {
+  if (sT.depth == 0 || sT.depth > prm.max_read_depth || sT.ref_depth == sT.depth) return false;
   int gi[kSomMaxGenotypes], gj[kSomMaxGenotypes];
   double lk[kSomMaxGenotypes];
   const int ng = genotype_likelihoods(avT, tabT, sT.n_alleles, sT, gi, gj, lk);
-  if (ng < 0) { report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus); return; }
-  if (ng == 0) return;
+  if (ng < 0) { report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus); return false; }
+  if (ng == 0) return false;
   int best = 0;  // maxBy = reduceLeft((x, y) => if (f(x) >= f(y)) x else y)
   for (int g = 1; g < ng; ++g)
     if (!(lk[best] >= lk[g])) best = g;
-  const AlleleEntry a1 = as_entry(tabT[gi[best]]), a2 = as_entry(tabT[gj[best]]);
-  const bool v1 = avT.is_variant(a1), v2 = avT.is_variant(a2);
-  if (!v1 && !v2) return;
-  const double tumor_l = lk[best];
+  *a1 = as_entry(tabT[gi[best]]);
+  *a2 = as_entry(tabT[gj[best]]);
+  *tumor_l = lk[best];
+  return avT.is_variant(*a1) || avT.is_variant(*a2);
+}
+
+// ... normal half: somatic odds against the normal sample's variant genotypes, then the record
+__device__ void somatic_against_normal(const AlleleView& avT, const AlleleView& avN, const AlleleEntry& a1, const AlleleEntry& a2,
+                                       double tumor_l, const SomAllele* tabN, const SampleStats& sN, int contig, int locus,
+                                       const SomParams& prm, SomOut& out) {
+  if (sN.depth == 0 || sN.depth > prm.max_read_depth) return;
+  int gi[kSomMaxGenotypes], gj[kSomMaxGenotypes];
+  double lk[kSomMaxGenotypes];
   const int ngn = genotype_likelihoods(avN, tabN, sN.n_alleles, sN, gi, gj, lk);
   if (ngn < 0) { report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus); return; }
   double normal_variants_total = 0.0;
@@ -146,6 +155,7 @@ __device__ void decide_somatic(const DevReads& RT, const AlleleView& avT, const 
   const double somatic_odds = tumor_l / normal_variants_total;
   if (!(somatic_odds * 100 >= (double)prm.odds_threshold)) return;
   // first non-reference allele of the genotype whose alternate is not empty
+  const bool v1 = avT.is_variant(a1), v2 = avT.is_variant(a2);
   const AlleleEntry* allele = nullptr;
   if (v1 && !avT.alt_empty(a1)) allele = &a1;
   else if (v2 && !avT.alt_empty(a2)) allele = &a2;
@@ -169,9 +179,20 @@ __device__ void decide_somatic(const DevReads& RT, const AlleleView& avT, const 
   r.tumor.likelihood = tumor_l;
   r.normal.likelihood = 1 - normal_variants_total;
   r.phred_scaled_somatic_likelihood = success_probability_to_phred(r.tumor.likelihood * r.normal.likelihood - 1e-10);
-  (void)RT;
   const uint32_t s = (uint32_t)atomicAdd(&out.counters[0], 1ull);
   if (s < out.cap_rec) out.rec[s] = r;
+}
+
+// findPotentialVariantAtLocus once both filtered pileups are summarised.  tabT / tabN sorted by Allele.compare.
+__device__ void decide_somatic(const DevReads& RT, const AlleleView& avT, const AlleleView& avN, const SomAllele* tabT,
+                               const SampleStats& sT, const SomAllele* tabN, const SampleStats& sN, int contig, int locus,
+                               const SomParams& prm, SomOut& out) {
+  (void)RT;
+  if (sT.depth == 0 || sN.depth == 0 || sT.depth > prm.max_read_depth || sN.depth > prm.max_read_depth) return;
+  AlleleEntry a1, a2;
+  double tumor_l;
+  if (!tumor_most_likely(avT, tabT, sT, contig, locus, prm, out, &a1, &a2, &tumor_l)) return;
+  somatic_against_normal(avT, avN, a1, a2, tumor_l, tabN, sN, contig, locus, prm, out);
 }
 
 // sort a small allele table by Allele.compare (insertion sort)
@@ -213,31 +234,48 @@ __device__ __forceinline__ void acc_clear(LaneAcc& a) {
 }
 
 template <bool TUMOR>
-__device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x, int rcode, bool std_ref, int max_span,
+__device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x, int rcode, bool std_ref,
                               const SomParams& prm, const double* __restrict__ tables, LaneAcc& A) {
   const int lane = threadIdx.x & 31;
   const ContigInfo ci = R.contigs[contig];
   acc_clear(A);
-  if (ci.read_end == ci.read_begin) return;
-  const int lower = lower_bound_start(R.rec, ci.read_begin, ci.read_end, span_lo - max_span + 1);
-  const int upper = lower_bound_start(R.rec, ci.read_begin, ci.read_end, span_lo + 32);
+  if (span_lo >= ci.length) return;
+  // candidate reads of the word: the granule's read range (no dependent binary-search chain); every lane tests one record
+  // and the warp then walks only the reads that really overlap the 32 loci
+  const int g = span_lo >> kGranuleShift;
+  const uint32_t first = R.gran_first[ci.gran_off + g], last = R.gran_last[ci.gran_off + g];
+  if (first == 0xFFFFFFFFu) return;
   const double* l1_tab = tables + (TUMOR ? kTabTl1 : kTabNl1);
   const double* l0_tab = tables + (TUMOR ? kTabTl0 : kTabNl0);
   const uint8_t ref_base = std_ref ? code_base(rcode) : (uint8_t)'N';
-  for (int base = lower; base < upper; base += 32) {
-    const int mine = base + lane;
+  // per-class sums, class = base code ^ reference code (class 0 = the reference base): the common class stays branch-free
+  double sr1 = 0.0, sr0 = 0.0;
+  for (uint32_t base = first; base < last; base += 32) {
+    const uint32_t mine = base + lane;
     ReadRec my{0, 0, 0, 0};
-    uint64_t my_seq_off = 0;
-    if (mine < upper) {
-      my = R.rec[mine];
-      my_seq_off = R.seq_off[mine];
+    if (mine < last) my = R.rec[mine];
+    const bool keep_mine = !(prm.min_mapq > 0) || (int)(my.info >> kInfoMapqShift) >= prm.min_mapq;
+    uint32_t ov = __ballot_sync(0xFFFFFFFFu, mine < last && my.start < span_lo + 32 && my.end > span_lo && my.end > my.start &&
+                                                 (keep_mine || prm.filter_multi_allelic));
+    // reads that overlap but are dropped by the mapq filter still decide whether the locus is visited
+    const uint32_t any_m = __ballot_sync(0xFFFFFFFFu, mine < last && my.start < span_lo + 32 && my.end > span_lo && my.end > my.start && !keep_mine);
+    if (any_m && !prm.filter_multi_allelic) {
+      uint32_t m = any_m;
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const int st = __shfl_sync(0xFFFFFFFFu, my.start, j), en = __shfl_sync(0xFFFFFFFFu, my.end, j);
+        A.any += (st <= x && x < en) ? 1 : 0;
+      }
     }
-    const int n_here = min(32, upper - base);
-    for (int j = 0; j < n_here; ++j) {
+    uint64_t my_seq_off = 0;
+    if (ov & (1u << lane)) my_seq_off = R.seq_off[mine];
+    while (ov) {  // warp-uniform
+      const int j = __ffs(ov) - 1;
+      ov &= ov - 1;
       ReadRec rec;
       rec.start = __shfl_sync(0xFFFFFFFFu, my.start, j);
       rec.end = __shfl_sync(0xFFFFFFFFu, my.end, j);
-      if (rec.end <= span_lo) continue;  // warp-uniform
       rec.pair_off = __shfl_sync(0xFFFFFFFFu, my.pair_off, j);
       rec.info = __shfl_sync(0xFFFFFFFFu, my.info, j);
       const uint64_t seq_off = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(my_seq_off >> 32), j) << 32) |
@@ -246,7 +284,6 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
       const bool keep = !(prm.min_mapq > 0) || mapq >= prm.min_mapq;
       const bool inside = rec.start <= x && x < rec.end;
       A.any += inside ? 1 : 0;
-      if (!keep && !prm.filter_multi_allelic) continue;  // warp-uniform
       int code = -1, q = 0;
       bool other = false, match = false;
       if ((rec.info & (kInfoSimple | kInfoHasExc)) == kInfoSimple) {
@@ -254,7 +291,7 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
           const int idx = (int)(rec.info & kInfoLeadMask) + (x - rec.start);
           const uint2 pw = __ldg(&R.pairs[rec.pair_off + (idx >> 5)]);
           code = (int)((pw.x >> (idx & 31)) & 1u) | ((int)((pw.y >> (idx & 31)) & 1u) << 1);
-          q = (int)R.qual[seq_off + idx];
+          q = (int)__ldg(&R.qual[seq_off + idx]);
           match = std_ref && code == rcode;
         }
       } else if (inside) {
@@ -272,18 +309,31 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
       A.seen |= 1u << code;
       if (!keep) continue;
       const int ti = TUMOR ? (mapq << 8) + q : q;
-      const double l1 = l1_tab[ti], l0 = l0_tab[ti];
+      const double l1 = __ldg(&l1_tab[ti]), l0 = __ldg(&l0_tab[ti]);
       A.depth += 1;
-      A.ref_depth += match ? 1 : 0;
       A.t0 += l0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool is = code == k;
-        A.cnt[k] += is ? 1 : 0;
-        A.s1[k] += is ? l1 : 0.0;
-        A.s0[k] += is ? l0 : 0.0;
+      for (int k = 0; k < 4; ++k) A.cnt[k] += (code == k) ? 1 : 0;
+      if (match) {
+        A.ref_depth += 1;
+        sr1 += l1;
+        sr0 += l0;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool is = code == k;
+          A.s1[k] += is ? l1 : 0.0;
+          A.s0[k] += is ? l0 : 0.0;
+        }
       }
     }
+  }
+  // fold the reference-class sums into their base code
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool is = std_ref && k == rcode;
+    A.s1[k] += is ? sr1 : 0.0;
+    A.s0[k] += is ? sr0 : 0.0;
   }
 }
 
@@ -326,27 +376,50 @@ __global__ void __launch_bounds__(kSomThreads) k_somatic(DevReads RT, DevReads R
     const int rcT = (int)((tl >> lane) & 1u) | ((int)((th >> lane) & 1u) << 1), rcN = (int)((nl >> lane) & 1u) | ((int)((nh >> lane) & 1u) << 1);
     const bool stdT = (ts >> lane) & 1u, stdN = (ns >> lane) & 1u;
     LaneAcc AT, AN;
-    gather_sample<true>(RT, td.contig, span_lo, x, rcT, stdT, max_span_t, prm, tables, AT);
-    gather_sample<false>(RN, td.contig, span_lo, x, rcN, stdN, max_span_n, prm, tables, AN);
-    if (!in_req) continue;
-    const int covT = AT.depth + AT.other, covN = AN.depth + AN.other;  // (filtered when no multi-allelic filter is on)
-    if (AT.any + AN.any > 0 || !prm.skip_empty) ++n_visited;
-    if (covT == 0 || covN == 0) continue;
+    gather_sample<true>(RT, td.contig, span_lo, x, rcT, stdT, prm, tables, AT);
+    // The reference looks at the normal sample only where the tumor's most likely genotype holds a variant allele: decide
+    // the tumor half per lane first and walk the normal reads of this word only if some lane still needs them.
+    const int covT = AT.depth + AT.other;  // (filtered when no multi-allelic filter is on)
+    const bool tumor_exact = AT.other > 0 || !stdT || prm.filter_multi_allelic;
+    const bool tumor_all_match = AT.ref_depth == AT.depth && AT.other == 0 && stdT && !prm.filter_multi_allelic;
+    bool need_normal = false, variant = false;
+    AlleleEntry a1, a2;
+    double tumor_l = 0.0;
+    AlleleView avT{RT, code_base(rcT)};
+    if (in_req) {
+      if (AT.any == 0) need_normal = true;  // visited iff the normal sample has reads here
+      else if (covT > 0 && !tumor_all_match) {
+        if (tumor_exact) need_normal = true;
+        else {
+          SomAllele tabT[4];
+          SampleStats sT;
+          lane_table(AT, rcT, tabT, sT);
+          variant = tumor_most_likely(avT, tabT, sT, td.contig, x, prm, out, &a1, &a2, &tumor_l);
+          need_normal = variant;
+        }
+      }
+    }
+    if (in_req && AT.any > 0) ++n_visited;
+    if (!__any_sync(0xFFFFFFFFu, need_normal)) continue;
+    gather_sample<false>(RN, td.contig, span_lo, x, rcN, stdN, prm, tables, AN);
+    if (!need_normal) continue;
+    if (AT.any == 0) {
+      if (AN.any > 0 || !prm.skip_empty) ++n_visited;
+      continue;
+    }
+    const int covN = AN.depth + AN.other;
+    if (covN == 0) continue;
     // anything but A/C/G/T matches / mismatches over a standard reference base goes to the exact kernel
-    const bool exact_needed = AT.other > 0 || AN.other > 0 || !stdT || !stdN || prm.filter_multi_allelic;
-    if (exact_needed) {
-      if (AT.ref_depth == AT.depth && AT.other == 0 && stdT && !prm.filter_multi_allelic) continue;  // tumor all-Match: early out either way
+    if (tumor_exact || AN.other > 0 || !stdN) {
       const uint32_t s = (uint32_t)atomicAdd(&out.counters[2], 1ull);
       if (s < out.cap_slow) out.slow[s] = SlowLocus{td.contig, x};
       continue;
     }
-    if (AT.ref_depth == AT.depth) continue;
-    SomAllele tabT[4], tabN[4];
-    SampleStats sT, sN;
-    lane_table(AT, rcT, tabT, sT);
+    SomAllele tabN[4];
+    SampleStats sN;
     lane_table(AN, rcN, tabN, sN);
-    AlleleView avT{RT, code_base(rcT)}, avN{RN, code_base(rcN)};
-    decide_somatic(RT, avT, avN, tabT, sT, tabN, sN, td.contig, x, prm, out);
+    AlleleView avN{RN, code_base(rcN)};
+    somatic_against_normal(avT, avN, a1, a2, tumor_l, tabN, sN, td.contig, x, prm, out);
   }
   for (int o = 16; o; o >>= 1) n_visited += __shfl_xor_sync(0xFFFFFFFFu, n_visited, o);
   if (lane == 0 && n_visited) atomicAdd(&out.counters[3], (unsigned long long)n_visited);
