@@ -648,10 +648,50 @@ __device__ uint32_t pool_alloc(DevOut& out, uint32_t n) {
   return kPoolDynOff + o;
 }
 
+// Walks the reads that overlap one locus, 32 at a time with all lanes busy: the granule's candidate range (mostly reads
+// that do NOT reach the locus) is scanned with one record test per lane and the hits are compacted, in read order, into
+// a 64-entry ring in shared memory.
+struct OverlapWalker {
+  uint32_t* ring;   // 64 entries, per warp
+  uint32_t src, last;
+  uint32_t head, tail;
+  int locus;
+  __device__ OverlapWalker(uint32_t* r, uint32_t first, uint32_t last_, int l)
+      : ring(r), src(first == 0xFFFFFFFFu ? last_ : first), last(first == 0xFFFFFFFFu ? 0u : last_), head(0), tail(0), locus(l) {
+    if (first == 0xFFFFFFFFu) src = last = 0;
+  }
+  // warp-uniform; false when no read is left.  Lanes with valid == true hold one overlapping read each.
+  __device__ bool next(const DevReads& R, uint32_t& r, ReadRec& rec, bool& valid) {
+    const int lane = threadIdx.x & 31;
+    while (tail - head < 32u && src < last) {
+      const uint32_t rr = src + lane;
+      bool hit = false;
+      if (rr < last) {
+        const ReadRec c = R.rec[rr];
+        hit = c.start <= locus && c.end > locus;
+      }
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+      if (hit) ring[(tail + __popc(m & ((1u << lane) - 1u))) & 63u] = rr;
+      tail += __popc(m);
+      src += 32;
+      __syncwarp();
+    }
+    if (tail == head) return false;
+    const uint32_t idx = head + lane;
+    valid = idx < tail;
+    r = valid ? ring[idx & 63u] : 0u;
+    rec = ReadRec{0, 0, 0, 0};
+    if (valid) rec = R.rec[r];
+    head = min(head + 32u, tail);
+    __syncwarp();
+    return true;
+  }
+};
+
 // ---- K_exact: one warp per locus --------------------------------------------------------------------------------------------
 constexpr int kExactWarps = 4;
 
-__device__ void exact_locus(const DevReads& R, const int contig, const int locus, const CallParams& prm, DevOut& out, AlleleEntry* tab) {
+__device__ void exact_locus(const DevReads& R, const int contig, const int locus, const CallParams& prm, DevOut& out, AlleleEntry* tab, uint32_t* ring) {
   const int lane = threadIdx.x & 31;
   const ContigInfo ci = R.contigs[contig];
   bool std_ref;
@@ -662,14 +702,11 @@ __device__ void exact_locus(const DevReads& R, const int contig, const int locus
   const int g = locus >> kGranuleShift;
   const uint32_t first = R.gran_first[ci.gran_off + g], last = R.gran_last[ci.gran_off + g];
   if (first == 0xFFFFFFFFu) return;
-  for (uint32_t base = first; base < last; base += 32) {
-    const uint32_t r = base + lane;
-    bool valid = r < last;
-    ReadRec rec{0, 0, 0, 0};
-    if (valid) {
-      rec = R.rec[r];
-      valid = rec.start <= locus && rec.end > locus;
-    }
+  OverlapWalker walk(ring, first, last, locus);
+  uint32_t r;
+  ReadRec rec;
+  bool valid;
+  while (walk.next(R, r, rec, valid)) {
     Elem e;
     e.kind = kNone;
     e.base = 0;
@@ -819,10 +856,11 @@ __device__ void exact_locus(const DevReads& R, const int contig, const int locus
 // grid-stride over the loci K_tile deferred; their number is read from the device counter (no host round trip)
 __global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, const SlowLocus* __restrict__ loci, CallParams prm, DevOut out) {
   __shared__ AlleleEntry tabs[kExactWarps][kMaxAlleles];
+  __shared__ uint32_t rings[kExactWarps][64];
   const uint32_t n_loci = (uint32_t)min(out.counters[2], (unsigned long long)out.cap_slow);
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t t = warp; t < n_loci; t += n_warps) {
-    exact_locus(R, loci[t].contig, loci[t].locus, prm, out, tabs[threadIdx.x >> 5]);
+    exact_locus(R, loci[t].contig, loci[t].locus, prm, out, tabs[threadIdx.x >> 5], rings[threadIdx.x >> 5]);
     __syncwarp();
   }
 }

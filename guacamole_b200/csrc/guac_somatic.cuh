@@ -428,11 +428,12 @@ __global__ void __launch_bounds__(kSomThreads) k_somatic(DevReads RT, DevReads R
 // ---- K_somatic_exact: warp per locus ----------------------------------------------------------------------------------------------
 struct ExactSmem {
   SomAllele tab[2][kSomTab];
+  uint32_t ring[64];
 };
 
 template <bool TUMOR>
 __device__ bool exact_sample(const DevReads& R, int contig, int locus, const SomParams& prm, const double* __restrict__ tables,
-                             SomAllele* tab, SampleStats& st, uint8_t* ref_base_out, DevError* err) {
+                             SomAllele* tab, uint32_t* ring, SampleStats& st, uint8_t* ref_base_out, DevError* err) {
   const int lane = threadIdx.x & 31;
   const ContigInfo ci = R.contigs[contig];
   bool std_ref = false;
@@ -453,14 +454,11 @@ __device__ bool exact_sample(const DevReads& R, int contig, int locus, const Som
     first = R.gran_first[ci.gran_off + g];
     last = R.gran_last[ci.gran_off + g];
   }
-  for (uint32_t base = first; base < last && first != 0xFFFFFFFFu; base += 32) {
-    const uint32_t r = base + lane;
-    bool valid = r < last;
-    ReadRec rec{0, 0, 0, 0};
-    if (valid) {
-      rec = R.rec[r];
-      valid = rec.start <= locus && rec.end > locus;
-    }
+  OverlapWalker walk(ring, first, last, locus);
+  uint32_t r;
+  ReadRec rec;
+  bool valid;
+  while (walk.next(R, r, rec, valid)) {
     const int mapq = (int)(rec.info >> kInfoMapqShift);
     const bool keep = valid && (!(prm.min_mapq > 0) || mapq >= prm.min_mapq);
     Elem e;
@@ -588,8 +586,8 @@ __global__ void __launch_bounds__(kSomExactWarps * 32) k_somatic_exact(DevReads 
     const int contig = loci[t].contig, locus = loci[t].locus;
     SampleStats sT, sN;
     uint8_t refT, refN;
-    bool ok = exact_sample<true>(RT, contig, locus, prm, tables, S.tab[0], sT, &refT, out.err);
-    ok = ok && exact_sample<false>(RN, contig, locus, prm, tables, S.tab[1], sN, &refN, out.err);
+    bool ok = exact_sample<true>(RT, contig, locus, prm, tables, S.tab[0], S.ring, sT, &refT, out.err);
+    ok = ok && exact_sample<false>(RN, contig, locus, prm, tables, S.tab[1], S.ring, sN, &refN, out.err);
     if (ok && lane == 0) {
       // MultiAllelicPileupFilter (before the mapq filter): more than two distinct alleles empty the pileup
       if (prm.filter_multi_allelic) {
@@ -621,6 +619,7 @@ constexpr int kEvidenceCap = 1024;  // supporting elements kept for the medians 
 struct EvidenceSmem {
   float mq[kEvidenceCap], bq[kEvidenceCap];
   int nm[kEvidenceCap];
+  uint32_t ring[64];
   int n;
 };
 
@@ -651,14 +650,11 @@ __device__ void evidence_sample(const DevReads& R, int contig, int locus, const 
     first = R.gran_first[ci.gran_off + g];
     last = R.gran_last[ci.gran_off + g];
   }
-  for (uint32_t base = first; base < last && first != 0xFFFFFFFFu; base += 32) {
-    const uint32_t r = base + lane;
-    bool valid = r < last;
-    ReadRec rec{0, 0, 0, 0};
-    if (valid) {
-      rec = R.rec[r];
-      valid = rec.start <= locus && rec.end > locus;
-    }
+  OverlapWalker walk(S.ring, first, last, locus);
+  uint32_t r;
+  ReadRec rec;
+  bool valid;
+  while (walk.next(R, r, rec, valid)) {
     const int mapq = (int)(rec.info >> kInfoMapqShift);
     valid = valid && (!(prm.min_mapq > 0) || mapq >= prm.min_mapq);
     Elem e;
