@@ -254,31 +254,54 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     const int q0 = (int)(rec.info & kInfoLeadMask) + (tile_lo + (w0 << 5) - rec.start);  // read base under bit 0 of word w0
     const int sh = q0 & 31;
     const uint2* __restrict__ P = R.pairs + rec.pair_off + (q0 >> 5);  // P[0] may sit one pair before the read (never loaded then)
-    uint2 pa = make_uint2(0u, 0u), pb = make_uint2(0u, 0u);
+    // all pair loads of a short read are issued up front (memory-level parallelism); longer reads roll on from there
+    constexpr int kPre = 7;
+    uint2 pre[kPre];
+#pragma unroll
+    for (int k = 0; k < kPre; ++k) pre[k] = make_uint2(0u, 0u);
+    const int n_pairs_needed = fast ? (w1 - w0 + 2) : 0;  // pairs P[0 .. w1 - w0 + 1]
     if (fast) {
-      if (q0 >= 0) pa = __ldg(P);
-      pb = __ldg(P + 1);
+#pragma unroll
+      for (int k = 0; k < kPre; ++k)
+        if (k < n_pairs_needed && (k > 0 || q0 >= 0)) pre[k] = __ldg(P + k);
     }
-    P += 2;
     // bits of the first / last word that belong to the read
     const uint32_t first_mask = bit_range(rec.start - (tile_lo + (w0 << 5)), 32);
     const uint32_t last_mask = bit_range(0, rec.end - (tile_lo + (w1 << 5)));
     const int nw = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)(fast ? w1 - w0 + 1 : 0));
     const uint32_t* ref_lo = S.ref_lo + w0;
     CntT* cnt_word = S.cnt + (w0 << 5);
-    for (int k = 0; k < nw; ++k) {
-      const int w = w0 + k;
-      uint32_t x = 0, y = 0;
-      if (fast && w <= w1) {
-        uint32_t valid = k == 0 ? first_mask : 0xFFFFFFFFu;
-        if (w == w1) valid &= last_mask;
-        x = (__funnelshift_r(pa.x, pb.x, sh) ^ ref_lo[k]) & valid;
-        y = (__funnelshift_r(pa.y, pb.y, sh) ^ ref_lo[k + kWarpWords]) & valid;  // ref_hi follows ref_lo in shared memory
-        pa = pb;
-        if (w < w1) pb = __ldg(P);
-        ++P;
+    if (nw <= kPre - 1) {
+#pragma unroll
+      for (int k = 0; k < kPre - 1; ++k) {
+        if (k < nw) {  // warp-uniform
+          uint32_t x = 0, y = 0;
+          if (fast && w0 + k <= w1) {
+            uint32_t valid = k == 0 ? first_mask : 0xFFFFFFFFu;
+            if (w0 + k == w1) valid &= last_mask;
+            x = (__funnelshift_r(pre[k].x, pre[k + 1].x, sh) ^ ref_lo[k]) & valid;
+            y = (__funnelshift_r(pre[k].y, pre[k + 1].y, sh) ^ ref_lo[k + kWarpWords]) & valid;  // ref_hi follows ref_lo
+          }
+          count_bits<CntT>(cnt_word + (k << 5), x | y, x, y);
+        }
       }
-      count_bits<CntT>(cnt_word + (k << 5), x | y, x, y);
+    } else {  // long reads: rolling window of two pairs
+      uint2 pa = pre[0], pb = pre[1];
+      const uint2* __restrict__ Q = P + 2;
+      for (int k = 0; k < nw; ++k) {
+        const int w = w0 + k;
+        uint32_t x = 0, y = 0;
+        if (fast && w <= w1) {
+          uint32_t valid = k == 0 ? first_mask : 0xFFFFFFFFu;
+          if (w == w1) valid &= last_mask;
+          x = (__funnelshift_r(pa.x, pb.x, sh) ^ ref_lo[k]) & valid;
+          y = (__funnelshift_r(pa.y, pb.y, sh) ^ ref_lo[k + kWarpWords]) & valid;
+          pa = pb;
+          if (w < w1) pb = __ldg(Q);
+          ++Q;
+        }
+        count_bits<CntT>(cnt_word + (k << 5), x | y, x, y);
+      }
     }
     if (__any_sync(0xFFFFFFFFu, slow_now)) general_read(r, rec, slow_now, w0, w1);  // list overflow (very deep granules)
     __syncwarp();
