@@ -107,6 +107,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(kernel, n_loci, depth):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_traffic.json), scaled
+    linearly in loci when the capture was taken on a slice; None if there is no capture for this shape."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p)).get(kernel)
+    if not t or abs(t["depth"] - depth) > 1e-9:
+        return None
+    return t["traffic_bytes"] * (n_loci / t["workload_loci"])
+
+
 def algorithmic_bytes(view, n_loci):
     """per read start 4 + ref_len 4 + 4*c + ceil(L/4) + 1 flag bytes; per locus 0.25 B of reference."""
     n = int(view.n_reads)
@@ -347,7 +359,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "loci/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "pinned_host_buffers": sum(len(k) for k in keeps)},
         "roofline": {"bound": "hbm", "kernel": "k_somatic" if somatic else "k_pileup_tile", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": measured_traffic("k_somatic" if somatic else "k_pileup_tile", n_loci, args.depth), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tile_step_ms, "exact_kernel_ms": exact_step_ms,
                      "whole_step_achieved_gbs": alg_bytes / (step_ms * 1e-3) / 1e9},
         "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps, "pack_kernel_ms": pack_ms, "generate_s": gen_s,
