@@ -15,6 +15,8 @@
 //           clipped/N-skipped elements, non-ACGT bases, non-standard reference base): a literal per-element walk.
 #pragma once
 
+#include <type_traits>
+
 #include "guac_device.cuh"
 
 namespace guac {
@@ -125,14 +127,78 @@ constexpr int kWarpLoci = kGranuleLoci;
 constexpr int kWarpsPerCta = 4;
 constexpr int kTileThreads = kWarpsPerCta * 32;
 constexpr int kListCap = 64;                    // reads of one granule that need the CIGAR walk (overflow handled inline)
-__host__ __device__ constexpr int cov_index(int i) { return i + (i >> 5); }  // one pad word per 32: conflict-free scan
-constexpr int kCovWords = cov_index(kWarpLoci + 32) + 1;
+// Depth difference array of one granule.  PACKED (8-bit counter fields, < 2048 reads per granule): two loci per 32-bit word,
+// each half biased by 0x4000 so that +1 / -1 never carry into the neighbour — half the shared memory, hence more resident
+// warps.  Otherwise one 32-bit word per locus.  One pad word per lane's 32 loci keeps the scan conflict-free.
+template <bool PACKED>
+struct CovArray {
+  static constexpr int kWords = PACKED ? (kWarpLoci / 2 + kWarpLoci / 32 + 4) : (kWarpLoci + kWarpLoci / 32 + 36);
+  uint32_t w[kWords];
+  static __device__ __forceinline__ int index(int i) { return PACKED ? (i >> 1) + (i >> 5) : i + (i >> 5); }
+  __device__ __forceinline__ void clear(int lane) {
+    for (int i = lane; i < kWords; i += 32) w[i] = PACKED ? 0x40004000u : 0u;
+  }
+  __device__ __forceinline__ void start(int i) { atomicAdd(&w[index(i)], PACKED ? (1u << (16 * (i & 1))) : 1u); }
+  __device__ __forceinline__ void end(int i) { atomicSub(&w[index(i)], PACKED ? (1u << (16 * (i & 1))) : 1u); }
+  __device__ __forceinline__ int get(int i) const { return PACKED ? (int)((w[index(i)] >> (16 * (i & 1))) & 0xFFFFu) : (int)w[index(i)]; }
+  // inclusive scan over the granule (lane owns loci [32 lane, 32 lane + 32)); returns the bit mask of the lane's loci with
+  // depth > 0 and ORs `over` when a depth exceeds `limit`
+  __device__ __forceinline__ uint32_t scan(int lane, uint32_t limit, bool& over) {
+    const int base = PACKED ? lane * 17 : lane * 33;
+    int run = 0;
+    if (PACKED) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) run += (int)(w[base + k] & 0xFFFFu) + (int)(w[base + k] >> 16) - 0x8000;
+    } else {
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) run += (int)w[base + k];
+    }
+    int incl = run;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int acc = incl - run;
+    uint32_t covered = 0;
+    if (PACKED) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const uint32_t v = w[base + k];
+        acc += (int)(v & 0xFFFFu) - 0x4000;
+        const uint32_t d0 = (uint32_t)acc;
+        acc += (int)(v >> 16) - 0x4000;
+        const uint32_t d1 = (uint32_t)acc;
+        w[base + k] = d0 | (d1 << 16);
+        covered |= (d0 != 0u ? 1u : 0u) << (2 * k);
+        covered |= (d1 != 0u ? 1u : 0u) << (2 * k + 1);
+        over |= d0 > limit || d1 > limit;
+      }
+    } else {
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) {
+        acc += (int)w[base + k];
+        w[base + k] = (uint32_t)acc;
+        covered |= (acc != 0 ? 1u : 0u) << k;
+        over |= (uint32_t)acc > limit;
+      }
+    }
+    return covered;
+  }
+};
+
+struct NoCovArray {
+  __device__ __forceinline__ void clear(int) {}
+  __device__ __forceinline__ void start(int) {}
+  __device__ __forceinline__ void end(int) {}
+  __device__ __forceinline__ int get(int) const { return 0; }
+  __device__ __forceinline__ uint32_t scan(int, uint32_t, bool&) { return 0u; }
+};
 
 template <typename CntT, int MODE>
 struct WarpSmem {
   uint32_t ref_lo[kWarpWords], ref_hi[kWarpWords], ref_std[kWarpWords];   // ref_hi must follow ref_lo
-  uint32_t cov[kCovWords];
-  uint32_t pos[MODE == 1 ? kCovWords : 1];  // positive-strand difference array (counts mode only)
+  CovArray<sizeof(CntT) == 4> cov;
+  typename std::conditional<MODE == 1, CovArray<sizeof(CntT) == 4>, NoCovArray>::type pos;  // positive-strand depth (counts mode)
   CntT cnt[kWarpLoci];
   uint32_t list[kListCap];
   uint32_t n_list;
@@ -171,10 +237,8 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
 
   // ---- phase 0: clear the counter slice, stage the reference planes, candidate reads of the granule
   for (int i = lane; i < kWarpLoci; i += 32) S.cnt[i] = 0;
-  for (int i = lane; i < kCovWords; i += 32) {
-    S.cov[i] = 0;
-    if (MODE == 1) S.pos[i] = 0;
-  }
+  S.cov.clear(lane);
+  if (MODE == 1) S.pos.clear(lane);
   {
     const int w = td.word0 + lane;
     const bool in = w < ci.n_words;
@@ -235,11 +299,11 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     int w0 = 0, w1 = -1;
     if (active) {
       const int s = max(rec.start, tile_lo) - tile_lo, e = min(rec.end, tile_hi) - tile_lo;
-      atomicAdd(&S.cov[cov_index(s)], 1u);
-      atomicSub(&S.cov[cov_index(e)], 1u);
+      S.cov.start(s);
+      S.cov.end(e);
       if (MODE == 1 && (rec.info & kInfoPositive)) {
-        atomicAdd(&S.pos[cov_index(s)], 1u);
-        atomicSub(&S.pos[cov_index(e)], 1u);
+        S.pos.start(s);
+        S.pos.end(e);
       }
       w0 = s >> 5;
       w1 = (e - 1) >> 5;
@@ -330,33 +394,15 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
   // ---- phase 2: inclusive scan of the difference array(s) -> depth (and positive-strand depth); visited loci counted here
   uint32_t n_visited = 0;
   bool overflow = false;
-  for (int which = 0; which < (MODE == 1 ? 2 : 1); ++which) {
-    uint32_t* A = which == 0 ? S.cov : S.pos;
-    uint32_t run = 0;
-    const int base = lane * 33;  // 32 loci + 1 pad word per lane
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) run += A[base + k];
-    uint32_t incl = run;
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += t;
+  {
+    const uint32_t covered = S.cov.scan(lane, FMASK, overflow);  // a counter field may have wrapped: the host widens and reruns
+    if (MODE == 1) {
+      bool ignore = false;
+      S.pos.scan(lane, 0xFFFFFFFFu, ignore);
     }
-    uint32_t acc = incl - run;
-    uint32_t covered = 0;
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-      acc += A[base + k];
-      A[base + k] = acc;
-      if (which == 0) {
-        covered |= (acc != 0u ? 1u : 0u) << k;
-        overflow |= acc > FMASK;  // a counter field may have wrapped: the host reruns with wider fields
-      }
-    }
-    if (which == 0) {
-      const int l0 = tile_lo + (lane << 5);
-      const uint32_t in_range = bit_range(td.locus_begin - l0, td.locus_end - l0);
-      n_visited = __popc((prm.skip_empty ? covered : 0xFFFFFFFFu) & in_range);
-    }
+    const int l0 = tile_lo + (lane << 5);
+    const uint32_t in_range = bit_range(td.locus_begin - l0, td.locus_end - l0);
+    n_visited = __popc((prm.skip_empty ? covered : 0xFFFFFFFFu) & in_range);
   }
   __syncwarp();
 
@@ -370,7 +416,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     if (c == 0 && std_ref && !every_covered) continue;  // every element matches the reference: nothing to call
     const int locus = tile_lo + x;
     if (locus < td.locus_begin || locus >= td.locus_end) continue;
-    const int total = (int)S.cov[cov_index(x)];
+    const int total = S.cov.get(x);
     // cheap reject of the commonest dirty locus: every class seen at most once and one read cannot pass the threshold
     constexpr CntT kOnes = sizeof(CntT) == 8 ? (CntT)0x0001000100010001ull : (CntT)0x01010101u;
     if (std_ref && !every_covered && (c & ~kOnes) == 0 && 100 < (prm.threshold_percent + 1) * total) continue;
@@ -391,7 +437,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
         g.locus = locus;
         g.contig = td.contig;
         g.depth = total;
-        g.positive_depth = (int)S.pos[cov_index(x)];
+        g.positive_depth = S.pos.get(x);
         g.reference_depth = std_ref ? total - o - m1 - m2 - m3 : 0;
         g.base_count[rcode] = total - o - m1 - m2 - m3;
         g.base_count[rcode ^ 1] = m1;
