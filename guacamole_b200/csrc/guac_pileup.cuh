@@ -60,59 +60,6 @@ struct CallParams {
   int32_t sample;
 };
 
-// ---- one read aligned onto one word ------------------------------------------------------------------------------------
-struct Aligned {
-  uint32_t plain;  // Match/Mismatch elements whose read base is A/C/G/T
-  uint32_t lo, hi; // their 2-bit codes
-  uint32_t other;  // every other element of this read in the word (insertion / deletion anchors, mid-deletion, N-skip, non-ACGT)
-};
-
-// general reads: walk the run-length CIGAR; each M/=/X run is one funnel-shifted window
-__device__ __noinline__ Aligned align_cigar(const DevReads& R, uint64_t r, const ReadRec rec, int wbase) {
-  Aligned a{0, 0, 0, 0};
-  const uint2* P = R.pairs + rec.pair_off;
-  const uint32_t* X = R.xmask + rec.pair_off;
-  const uint32_t c0 = R.cig_off[r], c1 = R.cig_off[r + 1];
-  int ref_pos = rec.start, read_pos = 0;
-  uint32_t prev_op = 0xFFu;
-  for (uint32_t c = c0; c < c1 && ref_pos <= wbase + 32; ++c) {
-    const uint32_t op = R.cigar[c] & 0xF;
-    const int len = (int)(R.cigar[c] >> 4);
-    if (op_is_match_like(op)) {
-      if (ref_pos + len > wbase) {
-        uint32_t valid = bit_range(ref_pos - wbase, ref_pos + len - wbase);
-        int q0 = read_pos + (wbase - ref_pos);
-        a.lo |= plane_window([&](int j) { return P[j].x; }, q0) & valid;
-        a.hi |= plane_window([&](int j) { return P[j].y; }, q0) & valid;
-        a.plain |= valid;
-        if (rec.info & kInfoHasExc) a.other |= plane_window([&](int j) { return X[j]; }, q0) & valid;
-      }
-      ref_pos += len;
-      read_pos += len;
-    } else if (op == GUAC_CIGAR_I) {
-      // (M|=, I): the last base of the preceding run carries the insertion; an I at reference position 0 of the
-      // contig is the contig-start insertion.  Either way that locus is not a plain element.
-      int anchor = (ref_pos == 0) ? 0 : ref_pos - 1;
-      if ((prev_op == GUAC_CIGAR_M || prev_op == GUAC_CIGAR_EQ || ref_pos == 0) && anchor >= wbase && anchor < wbase + 32)
-        a.other |= 1u << (anchor - wbase);
-      read_pos += len;
-    } else if (op == GUAC_CIGAR_D || op == GUAC_CIGAR_N) {
-      if (op == GUAC_CIGAR_D && ref_pos - 1 >= wbase && ref_pos - 1 < wbase + 32 && ref_pos > rec.start)
-        a.other |= 1u << (ref_pos - 1 - wbase);  // deletion anchor (or an invalid predecessor: decided exactly later)
-      if (ref_pos + len > wbase) a.other |= bit_range(ref_pos - wbase, ref_pos + len - wbase);
-      ref_pos += len;
-    } else if (op == GUAC_CIGAR_S) {
-      read_pos += len;
-    }
-    prev_op = op;
-  }
-  // (the loop runs while ref_pos <= wbase + 32 so that an I / D starting right after the word still marks its anchor)
-  a.plain &= ~a.other;
-  a.lo &= a.plain;
-  a.hi &= a.plain;
-  return a;
-}
-
 // ---- K_tile ---------------------------------------------------------------------------------------------------------------
 // One WARP owns one granule of 1024 loci and everything about it — its slice of shared memory, its reads, its scan, its
 // calls — so the kernel has no block-wide barrier at all: warps of a CTA (and of the other resident CTAs) progress
@@ -205,6 +152,20 @@ struct WarpSmem {
   uint32_t pad_[3];
 };
 
+// same, callable from divergent code (no reconvergence point inside)
+template <typename CntT>
+__device__ __forceinline__ void count_bits_nosync(CntT* cnt_word, uint32_t bits, int cls) {
+  constexpr int FB = sizeof(CntT) * 2;
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    if constexpr (sizeof(CntT) == 8)
+      atomicAdd(reinterpret_cast<unsigned long long*>(cnt_word + b), 1ull << (FB * cls));
+    else
+      atomicAdd(cnt_word + b, (CntT)1 << (FB * cls));
+  }
+}
+
 // one shared-memory atomic per set bit; lanes loop independently and the warp reconverges right after
 template <typename CntT>
 __device__ __forceinline__ void count_bits(CntT* cnt_word, uint32_t bits, uint32_t x, uint32_t y) {
@@ -258,31 +219,95 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
   }
   __syncwarp();
 
-  // general path for one read (CIGAR walk / exception mask), one word at a time
-  auto general_read = [&](uint32_t r, const ReadRec rec, bool active, int w0, int w1) {
-    const int nw = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)(active ? w1 - w0 + 1 : 0));
-    for (int k = 0; k < nw; ++k) {
-      const int w = w0 + k;
-      Aligned a{0, 0, 0, 0};
-      if (active && w <= w1) {
-        const int wbase = tile_lo + (w << 5);
-        if (rec.info & kInfoSimple) {  // simple read holding non-ACGT bases
-          const uint2* P = R.pairs + rec.pair_off;
-          const uint32_t* X = R.xmask + rec.pair_off;
-          const int q0 = (int)(rec.info & kInfoLeadMask) + (wbase - rec.start);
-          const uint32_t valid = bit_range(rec.start - wbase, rec.end - wbase);
-          a.other = plane_window([&](int j) { return X[j]; }, q0) & valid;
-          a.plain = valid & ~a.other;
-          a.lo = plane_window([&](int j) { return P[j].x; }, q0) & a.plain;
-          a.hi = plane_window([&](int j) { return P[j].y; }, q0) & a.plain;
-        } else {
-          a = align_cigar(R, r, rec, wbase);
+  // General path (reads with insertions / deletions / skips, or with non-ACGT bases): the run-length CIGAR is walked ONCE,
+  // op by op, in lockstep across the warp.  Every M/=/X run is a segment that slides over the reference words exactly like
+  // the fast path; insertion / deletion anchors, deleted and skipped loci and non-ACGT bases are "other" elements.
+  auto mark_other = [&](int lo, int hi) {  // loci [lo, hi) of this lane's read that are not plain elements (divergent-safe)
+    lo = max(lo, tile_lo);
+    hi = min(hi, tile_hi);
+    for (int w = (lo - tile_lo) >> 5; lo < hi && w <= (hi - 1 - tile_lo) >> 5; ++w) {
+      const int wbase = tile_lo + (w << 5);
+      count_bits_nosync<CntT>(S.cnt + (w << 5), bit_range(lo - wbase, hi - wbase), 0);
+    }
+  };
+  auto general_read = [&](uint32_t r, const ReadRec rec, bool active) {
+    uint32_t c = active ? R.cig_off[r] : 0u;
+    const uint32_t c_end = active ? R.cig_off[r + 1] : 0u;
+    const bool has_exc = (rec.info & kInfoHasExc) != 0;
+    int ref_pos = rec.start, read_pos = 0;
+    bool skip_first = false;  // contig-start insertion: the element at locus 0 is the insertion, not a plain base
+    const int n_ops = (int)__reduce_max_sync(0xFFFFFFFFu, c_end - c);
+    for (int oi = 0; oi < n_ops; ++oi) {
+      int seg_ref = 0, seg_read = 0, seg_len = 0;
+      if (c < c_end) {
+        const uint32_t v = R.cigar[c];
+        const uint32_t op = v & 0xF, next_op = (c + 1 < c_end) ? (R.cigar[c + 1] & 0xF) : 0xFFu;
+        const int len = (int)(v >> 4);
+        ++c;
+        if (op_is_match_like(op)) {
+          seg_ref = ref_pos;
+          seg_read = read_pos;
+          seg_len = len;
+          if (skip_first) {
+            mark_other(ref_pos, ref_pos + 1);
+            ++seg_ref; ++seg_read; --seg_len;
+            skip_first = false;
+          }
+          // (M|=, I) and (M|=|X, D): the run's last base is the insertion / deletion anchor (PileupElement.scala:93, 109)
+          const bool anchor = (next_op == GUAC_CIGAR_I && (op == GUAC_CIGAR_M || op == GUAC_CIGAR_EQ)) || next_op == GUAC_CIGAR_D;
+          if (anchor && seg_len > 0) {
+            mark_other(ref_pos + len - 1, ref_pos + len);
+            --seg_len;
+          }
+          ref_pos += len;
+          read_pos += len;
+        } else if (op == GUAC_CIGAR_D || op == GUAC_CIGAR_N) {
+          mark_other(ref_pos, ref_pos + len);  // mid-deletion / skipped loci
+          ref_pos += len;
+        } else if (op == GUAC_CIGAR_I) {
+          if (ref_pos == 0 && rec.start == 0) skip_first = true;
+          read_pos += len;
+        } else if (op == GUAC_CIGAR_S) {
+          read_pos += len;
         }
       }
-      const int ws = (active && w <= w1) ? w : 0;
-      const uint32_t x = (a.lo ^ S.ref_lo[ws]) & a.plain, y = (a.hi ^ S.ref_hi[ws]) & a.plain;
-      count_bits<CntT>(S.cnt + (ws << 5), x | y, x, y);
-      count_bits<CntT>(S.cnt + (ws << 5), a.other, 0u, 0u);
+      __syncwarp();
+      // the plain segment, clipped to the granule
+      const int s = max(seg_ref, tile_lo), e = min(seg_ref + seg_len, tile_hi);
+      const bool on_seg = seg_len > 0 && s < e;
+      const int w0 = on_seg ? (s - tile_lo) >> 5 : 0, w1 = on_seg ? (e - 1 - tile_lo) >> 5 : -1;
+      const int q0 = seg_read + (tile_lo + (w0 << 5) - seg_ref);
+      const int sh = q0 & 31;
+      const uint2* __restrict__ P = R.pairs + rec.pair_off + (q0 >> 5);
+      const uint32_t* __restrict__ X = R.xmask + rec.pair_off + (q0 >> 5);
+      uint2 pa = make_uint2(0u, 0u), pb = make_uint2(0u, 0u);
+      uint32_t xa = 0, xb = 0;
+      if (on_seg) {
+        if (q0 >= 0) { pa = __ldg(P); if (has_exc) xa = __ldg(X); }
+        pb = __ldg(P + 1);
+        if (has_exc) xb = __ldg(X + 1);
+      }
+      const uint32_t first_mask = bit_range(seg_ref - (tile_lo + (w0 << 5)), 32);
+      const uint32_t last_mask = bit_range(0, seg_ref + seg_len - (tile_lo + (w1 << 5)));
+      const int nw = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)(w1 - w0 + 1));
+      for (int k = 0; k < nw; ++k) {
+        const int w = w0 + k;
+        uint32_t x = 0, y = 0, oth = 0;
+        if (on_seg && w <= w1) {
+          uint32_t valid = k == 0 ? first_mask : 0xFFFFFFFFu;
+          if (w == w1) valid &= last_mask;
+          oth = __funnelshift_r(xa, xb, sh) & valid;  // non-ACGT bases
+          valid &= ~oth;
+          x = (__funnelshift_r(pa.x, pb.x, sh) ^ S.ref_lo[w]) & valid;
+          y = (__funnelshift_r(pa.y, pb.y, sh) ^ S.ref_hi[w]) & valid;
+          pa = pb;
+          xa = xb;
+          if (w < w1) { pb = __ldg(P + k + 2); if (has_exc) xb = __ldg(X + k + 2); }
+        }
+        const int ws = (on_seg && w <= w1) ? w : 0;
+        count_bits<CntT>(S.cnt + (ws << 5), x | y, x, y);
+        if (__any_sync(0xFFFFFFFFu, oth != 0)) count_bits<CntT>(S.cnt + (ws << 5), oth, 0u, 0u);
+      }
     }
   };
 
@@ -367,7 +392,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
         count_bits<CntT>(cnt_word + (k << 5), x | y, x, y);
       }
     }
-    if (__any_sync(0xFFFFFFFFu, slow_now)) general_read(r, rec, slow_now, w0, w1);  // list overflow (very deep granules)
+    if (__any_sync(0xFFFFFFFFu, slow_now)) general_read(r, rec, slow_now);  // list overflow (very deep granules)
     __syncwarp();
   }
   __syncwarp();
@@ -379,13 +404,8 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
       const bool active = i < n_list;
       const uint32_t r = active ? S.list[i] : 0u;
       ReadRec rec{0, 0, 0, 0};
-      int w0 = 0, w1 = -1;
-      if (active) {
-        rec = R.rec[r];
-        w0 = (max(rec.start, tile_lo) - tile_lo) >> 5;
-        w1 = (min(rec.end, tile_hi) - tile_lo - 1) >> 5;
-      }
-      general_read(r, rec, active, w0, w1);
+      if (active) rec = R.rec[r];
+      general_read(r, rec, active);
       __syncwarp();
     }
   }
