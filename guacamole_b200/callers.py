@@ -132,16 +132,35 @@ class PackedReads:
             pass
 
 
+class _ResultHandle:
+    """Owns one guac_result; freed when the last view onto its buffers goes away."""
+
+    def __init__(self, h):
+        self.h = h
+
+    def release(self):
+        if self.h:
+            h, self.h = self.h, None
+            lib().guac_result_free(h)
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 class Result:
-    """guac_result copied into numpy structured arrays + the allele byte pool."""
+    """guac_result: numpy views straight onto the library-owned (page-locked) record buffer and allele byte pool — no
+    copy.  The buffers live as long as this object (or any array derived from `records`) does."""
 
     def __init__(self, handle, kind: str):
         L = lib()
         self.kind = kind
+        self._h = _ResultHandle(handle)
         n = L.guac_result_n(handle)
         nb = C.c_size_t()
         bp = L.guac_result_bytes(handle, C.byref(nb))
-        self.bytes = C.string_at(bp, nb.value) if nb.value else b""
         self.stats = abi.struct_to_dict(L.guac_result_stats(handle).contents)
         if kind == "threshold":
             p, dt = L.guac_result_threshold_records(handle), THRESHOLD_DTYPE
@@ -149,18 +168,34 @@ class Result:
             p, dt = L.guac_result_somatic_records(handle), SOMATIC_DTYPE
         else:
             p, dt = L.guac_result_counts(handle), COUNTS_DTYPE
-        if n:  # one copy out of the library-owned buffer
+        if n:
             raw = (C.c_uint8 * (n * dt.itemsize)).from_address(C.cast(p, C.c_void_p).value)
-            self.records = np.frombuffer(raw, dtype=np.uint8).copy().view(dt)
+            raw._owner = self._h  # the view keeps the library buffer alive (no reference cycle through self)
+            self.records = np.frombuffer(raw, dtype=np.uint8).view(dt)
         else:
             self.records = np.zeros(0, dt)
-        L.guac_result_free(handle)
+        if nb.value:
+            rawb = (C.c_uint8 * nb.value).from_address(C.cast(bp, C.c_void_p).value)
+            rawb._owner = self._h
+            self._bytes = memoryview(rawb).cast("B")
+        else:
+            self._bytes = memoryview(b"")
+
+    @property
+    def bytes(self) -> bytes:
+        return bytes(self._bytes)
+
+    def free(self):
+        """Detach from the library buffers (copying what is still referenced) and release them now."""
+        self.records = self.records.copy()
+        self._bytes = memoryview(bytes(self._bytes))
+        self._h.release()
 
     def __len__(self):
         return len(self.records)
 
     def _s(self, off, ln):
-        return self.bytes[int(off):int(off) + int(ln)].decode("latin1")
+        return bytes(self._bytes[int(off):int(off) + int(ln)]).decode("latin1")
 
     def genotypes(self) -> List[dict]:
         """Records as the fields of the bdg-formats Genotype the reference builds

@@ -441,13 +441,17 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       cap_pool = std::max<uint64_t>(cap_pool, kPoolDynOff + c[1] + c[1] / 8 + 16);
       continue;
     }
-    // ---- D2H through pinned staging (+ canonical order unless switched off).  Records keep their offsets into the pool,
-    // which is returned whole: no per-record work on the host.
+    // ---- D2H straight into the pinned block the result will own (+ canonical order unless switched off).  Records keep
+    // their offsets into the pool, which is returned whole: no per-record work on the host.
     const uint64_t n_rec = c[0];
     const size_t pool_bytes = (size_t)(kPoolDynOff + c[1]), rec_bytes = (size_t)(n_rec * rec_size);
-    unsigned char* hs = stage(ctx, pool_bytes + rec_bytes + 64);
+    const size_t rec_at = (pool_bytes + 63) & ~(size_t)63;
+    res.pool = ctx->pinned;
+    res.block = ctx->pinned->take(rec_at + rec_bytes + 64, &res.block_bytes);
+    if (!res.block) fail(GUAC_ERR_OOM, "pinned host allocation of %zu bytes failed", rec_at + rec_bytes + 64);
+    unsigned char* hs = (unsigned char*)res.block;
+    unsigned char* hrec = hs + rec_at;
     CUDA_OK(cudaMemcpyAsync(hs, ctx->out_pool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
-    unsigned char* hrec = hs + ((pool_bytes + 63) & ~(size_t)63);
     if (n_rec) CUDA_OK(cudaMemcpyAsync(hrec, ctx->out_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
     res.stats.d2h_bytes = pool_bytes + rec_bytes + 8 * sizeof(unsigned long long);
@@ -460,12 +464,14 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
           return std::make_pair(a.contig, a.locus) < std::make_pair(b.contig, b.locus);
         });
     } else {
-      res.threshold.resize((size_t)n_rec);
-      if (n_rec) memcpy(res.threshold.data(), hrec, rec_bytes);
-      res.bytes.assign(hs, hs + pool_bytes);
+      res.records = hrec;
+      res.n_records = (size_t)n_rec;
+      res.bytes = hs;
+      res.n_bytes = pool_bytes;
       if (ctx->sort_records) {
-        const uint8_t* pool = res.bytes.data();
-        std::sort(res.threshold.begin(), res.threshold.end(), [pool](const guac_threshold_record& a, const guac_threshold_record& b) {
+        const uint8_t* pool = hs;
+        guac_threshold_record* first = (guac_threshold_record*)hrec;
+        std::sort(first, first + n_rec, [pool](const guac_threshold_record& a, const guac_threshold_record& b) {
           if (a.contig != b.contig) return a.contig < b.contig;
           if (a.start != b.start) return a.start < b.start;
           if (a.sample != b.sample) return a.sample < b.sample;
@@ -680,14 +686,14 @@ guac_status guac_somatic_standard(guac_ctx* ctx, const guac_reads* tumor, const 
 
 size_t guac_result_n(const guac_result* r) {
   if (!r) return 0;
-  return r->kind == 0 ? r->threshold.size() : r->kind == 1 ? r->somatic.size() : r->counts.size();
+  return r->kind == 2 ? r->counts.size() : r->n_records;
 }
-const guac_threshold_record* guac_result_threshold_records(const guac_result* r) { return (r && r->kind == 0) ? r->threshold.data() : nullptr; }
-const guac_somatic_record* guac_result_somatic_records(const guac_result* r) { return (r && r->kind == 1) ? r->somatic.data() : nullptr; }
+const guac_threshold_record* guac_result_threshold_records(const guac_result* r) { return (r && r->kind == 0) ? (const guac_threshold_record*)r->records : nullptr; }
+const guac_somatic_record* guac_result_somatic_records(const guac_result* r) { return (r && r->kind == 1) ? (const guac_somatic_record*)r->records : nullptr; }
 const guac_locus_counts* guac_result_counts(const guac_result* r) { return (r && r->kind == 2) ? r->counts.data() : nullptr; }
 const uint8_t* guac_result_bytes(const guac_result* r, size_t* n_bytes) {
-  if (n_bytes) *n_bytes = r ? r->bytes.size() : 0;
-  return r ? r->bytes.data() : nullptr;
+  if (n_bytes) *n_bytes = r ? r->n_bytes : 0;
+  return r ? r->bytes : nullptr;
 }
 const guac_stats* guac_result_stats(const guac_result* r) { return r ? &r->stats : nullptr; }
 void guac_result_free(guac_result* r) { delete r; }

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <tuple>
@@ -126,6 +127,45 @@ struct DevBuf {
 
 }  // namespace
 
+// Page-locked host blocks for results: a call downloads its records straight into the block its guac_result will own
+// (no staging copy); guac_result_free hands the block back for the next call.  Shared between the context and its
+// results so that either may be destroyed first.
+struct PinnedPool {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;
+  void* take(size_t bytes, size_t* got) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = free_blocks.lower_bound(bytes);
+      if (it != free_blocks.end() && it->first <= bytes * 2 + (1 << 20)) {
+        void* p = it->second;
+        *got = it->first;
+        free_blocks.erase(it);
+        return p;
+      }
+    }
+    void* p = nullptr;
+    const size_t want = bytes + bytes / 4 + 4096;
+    if (cudaMallocHost(&p, want) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    *got = want;
+    return p;
+  }
+  void give(void* p, size_t bytes) {
+    std::lock_guard<std::mutex> g(mu);
+    if (free_blocks.size() >= 8) {
+      cudaFreeHost(p);
+      return;
+    }
+    free_blocks.emplace(bytes, p);
+  }
+  ~PinnedPool() {
+    for (auto& kv : free_blocks) cudaFreeHost(kv.second);
+  }
+};
+
 // ---- context ----------------------------------------------------------------------------------------------------------------
 struct guac_ctx {
   int device = 0;
@@ -151,6 +191,7 @@ struct guac_ctx {
   // pinned host arena for the per-read header columns built by guac_reads_pack (grow-only)
   unsigned char* h_pack = nullptr;
   size_t h_pack_bytes = 0;
+  std::shared_ptr<PinnedPool> pinned = std::make_shared<PinnedPool>();
   // somatic tables (device): see guac_somatic.cuh
   double* d_tables = nullptr;
 };
@@ -290,10 +331,18 @@ struct guac_reads {
 
 struct guac_result {
   int kind = 0;  // 0 threshold, 1 somatic, 2 counts
-  std::vector<guac_threshold_record> threshold;
-  std::vector<guac_somatic_record> somatic;
-  std::vector<guac_locus_counts> counts;
-  std::vector<uint8_t> bytes;
+  // threshold / somatic records and the allele byte pool live in one pinned block (downloaded in place)
+  std::shared_ptr<PinnedPool> pool;
+  void* block = nullptr;
+  size_t block_bytes = 0;
+  size_t n_records = 0;
+  const void* records = nullptr;
+  const uint8_t* bytes = nullptr;
+  size_t n_bytes = 0;
+  std::vector<guac_locus_counts> counts;  // counts mode (rows for empty loci are appended on the host)
   guac_stats stats{};
+  ~guac_result() {
+    if (block && pool) pool->give(block, block_bytes);
+  }
 };
 

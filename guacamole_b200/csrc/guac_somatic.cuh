@@ -829,18 +829,24 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
     }
     const uint64_t n_rec = c[0];
     const size_t pool_bytes = (size_t)(kPoolDynOff + c[1]), rec_bytes = (size_t)(n_rec * sizeof(guac_somatic_record));
-    unsigned char* hs = stage(ctx, pool_bytes + rec_bytes + 64);
+    const size_t rec_at = (pool_bytes + 63) & ~(size_t)63;
+    res.pool = ctx->pinned;
+    res.block = ctx->pinned->take(rec_at + rec_bytes + 64, &res.block_bytes);
+    if (!res.block) fail(GUAC_ERR_OOM, "pinned host allocation of %zu bytes failed", rec_at + rec_bytes + 64);
+    unsigned char* hs = (unsigned char*)res.block;
+    unsigned char* hrec = hs + rec_at;
     CUDA_OK(cudaMemcpyAsync(hs, ctx->out_pool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
-    unsigned char* hrec = hs + ((pool_bytes + 63) & ~(size_t)63);
     if (n_rec) CUDA_OK(cudaMemcpyAsync(hrec, ctx->out_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
     res.stats.d2h_bytes = pool_bytes + rec_bytes + 64;
-    res.somatic.resize((size_t)n_rec);
-    if (n_rec) memcpy(res.somatic.data(), hrec, rec_bytes);
-    res.bytes.assign(hs, hs + pool_bytes);
+    res.records = hrec;
+    res.n_records = (size_t)n_rec;
+    res.bytes = hs;
+    res.n_bytes = pool_bytes;
     if (ctx->sort_records) {
-      const uint8_t* pool = res.bytes.data();
-      std::sort(res.somatic.begin(), res.somatic.end(), [pool](const guac_somatic_record& a, const guac_somatic_record& b) {
+      const uint8_t* pool = hs;
+      guac_somatic_record* first = (guac_somatic_record*)hrec;
+      std::sort(first, first + n_rec, [pool](const guac_somatic_record& a, const guac_somatic_record& b) {
         if (a.contig != b.contig) return a.contig < b.contig;
         if (a.start != b.start) return a.start < b.start;
         int c = memcmp(pool + a.ref_off, pool + b.ref_off, std::min(a.ref_len, b.ref_len));
