@@ -33,6 +33,21 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   if (ref && ref->n_contigs != b->n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "reference and batch disagree on the number of contigs");
 
   Trace tr("pack");
+  // The raw columns go first: from page-locked caller buffers these copies are asynchronous and overlap the host pass below.
+  if (n && (b->cigar_off[n] >= 0xFFFFFFFFull || b->md_off[n] >= 0xFFFFFFFFull)) fail(GUAC_ERR_UNSUPPORTED, "cigar / MD columns too large: shard the read set");
+  if (n) {
+    h2d(ctx, out.seq, b->seq, (size_t)b->seq_off[n], 64);
+    out.has_qualities = ctx->pack_qualities != 0;
+    if (out.has_qualities) h2d(ctx, out.qual, b->qual, (size_t)b->seq_off[n], 64);
+    h2d(ctx, out.cigar, b->cigar, (size_t)b->cigar_off[n], 1);
+    h2d(ctx, out.seq_off, b->seq_off, n + 1);
+    h2d(ctx, out.md, b->md, (size_t)b->md_off[n], 16);
+  } else {
+    out.has_qualities = ctx->pack_qualities != 0;
+    out.seq.alloc(64); out.qual.alloc(64); out.cigar.alloc(1); out.md.alloc(16);
+    static const uint64_t zero = 0;
+    h2d(ctx, out.seq_off, &zero, 1);
+  }
   // ---- host pass over the read headers: O(reads + cigar ops); everything per-base happens on the device
   // header columns are built in a pinned arena owned by the context (no page faults after the first call, fast H2D)
   const size_t col = ((n + 1) * sizeof(uint32_t) + 63) & ~(size_t)63;
@@ -43,7 +58,6 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   uint32_t* read_contig = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(md_off) + col);
   std::vector<int64_t> contig_end(b->n_contigs, 0);
   std::vector<uint64_t> contig_first(b->n_contigs, ~0ull), contig_last(b->n_contigs, 0);
-  if (b->cigar_off[n] >= 0xFFFFFFFFull || b->md_off[n] >= 0xFFFFFFFFull) fail(GUAC_ERR_UNSUPPORTED, "cigar / MD columns too large: shard the read set");
   out.sample = n ? (b->sample ? b->sample[0] : 0) : 0;
   const int32_t sample0 = out.sample;
   // Reads are independent except for the order checks (which look at read i - 1 in the input) and the running pair offset
@@ -190,13 +204,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   cudaStream_t st = ctx->stream;
   h2d(ctx, out.rec, rec, n + 1);
   h2d(ctx, out.cig_off, cig_off, n + 1);
-  h2d(ctx, out.cigar, b->cigar, (size_t)b->cigar_off[n], 1);
-  h2d(ctx, out.seq_off, b->seq_off, n + 1);
-  h2d(ctx, out.seq, b->seq, (size_t)b->seq_off[n], 64);
-  out.has_qualities = ctx->pack_qualities != 0;
-  if (out.has_qualities) h2d(ctx, out.qual, b->qual, (size_t)b->seq_off[n], 64);
   h2d(ctx, out.md_off, md_off, n + 1);
-  h2d(ctx, out.md, b->md, (size_t)b->md_off[n], 16);
   h2d(ctx, out.d_contigs, out.contigs.data(), out.contigs.size());
   DevBuf<uint32_t> d_read_contig, conflict, gran_count;
   h2d(ctx, d_read_contig, read_contig, n);
@@ -471,9 +479,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       if (ctx->sort_records) {
         const uint8_t* pool = hs;
         guac_threshold_record* first = (guac_threshold_record*)hrec;
-        std::sort(first, first + n_rec, [pool](const guac_threshold_record& a, const guac_threshold_record& b) {
-          if (a.contig != b.contig) return a.contig < b.contig;
-          if (a.start != b.start) return a.start < b.start;
+        sort_records_canonical(first, (size_t)n_rec, [pool](const guac_threshold_record& a, const guac_threshold_record& b) {
           if (a.sample != b.sample) return a.sample < b.sample;
           int c = memcmp(pool + a.ref_off, pool + b.ref_off, std::min(a.ref_len, b.ref_len));
           if (c != 0) return c < 0;
@@ -624,7 +630,12 @@ guac_status guac_reads_pack(guac_ctx* ctx, const guac_read_batch* batch, const g
   return guarded(ctx, [&] {
     CUDA_OK(cudaSetDevice(ctx->device));
     std::unique_ptr<guac_reads> r(new guac_reads());
-    pack_reads(ctx, batch, ref, *r);
+    try {
+      pack_reads(ctx, batch, ref, *r);
+    } catch (...) {
+      cudaStreamSynchronize(ctx->stream);  // copies from the caller's buffers may still be in flight
+      throw;
+    }
     *out = r.release();
   });
 }

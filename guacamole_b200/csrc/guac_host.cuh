@@ -266,6 +266,51 @@ struct Trace {  // GUAC_TRACE=1 prints host-side phase times (diagnostics only)
   }
 };
 
+// Canonical record order (contig, start, then `tie_less` among equal loci): LSD radix sort on the 48-bit (contig, start)
+// key, groups of equal keys finished with the full comparator.  ~10x faster than std::sort with the byte-string comparator.
+template <typename Rec, typename TieLess>
+void sort_records_canonical(Rec* recs, size_t n, TieLess tie_less) {
+  if (n < 2) return;
+  bool fits = true;
+  for (size_t i = 0; i < n && fits; ++i) fits = recs[i].contig >= 0 && recs[i].contig < 65536 && recs[i].start >= 0 && recs[i].start < (1ll << 32);
+  if (!fits) {
+    std::sort(recs, recs + n, [&](const Rec& a, const Rec& b) {
+      if (a.contig != b.contig) return a.contig < b.contig;
+      if (a.start != b.start) return a.start < b.start;
+      return tie_less(a, b);
+    });
+    return;
+  }
+  std::vector<uint64_t> key(n), key2(n);
+  std::vector<uint32_t> idx(n), idx2(n);
+  for (size_t i = 0; i < n; ++i) {
+    key[i] = ((uint64_t)recs[i].contig << 32) | (uint64_t)recs[i].start;
+    idx[i] = (uint32_t)i;
+  }
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = 16 * pass;
+    std::vector<uint32_t> count(65537, 0);
+    for (size_t i = 0; i < n; ++i) ++count[((key[i] >> shift) & 0xFFFF) + 1];
+    for (int d = 0; d < 65536; ++d) count[d + 1] += count[d];
+    for (size_t i = 0; i < n; ++i) {
+      const uint32_t pos = count[(key[i] >> shift) & 0xFFFF]++;
+      key2[pos] = key[i];
+      idx2[pos] = idx[i];
+    }
+    key.swap(key2);
+    idx.swap(idx2);
+  }
+  std::vector<Rec> tmp(n);
+  for (size_t i = 0; i < n; ++i) tmp[i] = recs[idx[i]];
+  for (size_t i = 0; i < n;) {
+    size_t j = i + 1;
+    while (j < n && key[j] == key[i]) ++j;
+    if (j - i > 1) std::sort(tmp.begin() + i, tmp.begin() + j, tie_less);
+    i = j;
+  }
+  memcpy(recs, tmp.data(), n * sizeof(Rec));
+}
+
 int grid_for(uint64_t n, int block, int sm_count) {
   uint64_t g = (n + block - 1) / block;
   uint64_t cap = (uint64_t)sm_count * 32;

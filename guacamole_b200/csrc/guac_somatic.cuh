@@ -846,9 +846,7 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
     if (ctx->sort_records) {
       const uint8_t* pool = hs;
       guac_somatic_record* first = (guac_somatic_record*)hrec;
-      std::sort(first, first + n_rec, [pool](const guac_somatic_record& a, const guac_somatic_record& b) {
-        if (a.contig != b.contig) return a.contig < b.contig;
-        if (a.start != b.start) return a.start < b.start;
+      sort_records_canonical(first, (size_t)n_rec, [pool](const guac_somatic_record& a, const guac_somatic_record& b) {
         int c = memcmp(pool + a.ref_off, pool + b.ref_off, std::min(a.ref_len, b.ref_len));
         if (c != 0) return c < 0;
         if (a.ref_len != b.ref_len) return a.ref_len < b.ref_len;
