@@ -19,6 +19,7 @@ EXPORTED = [
     "guac_germline_threshold", "guac_somatic_standard", "guac_pileup_counts",
     "guac_result_n", "guac_result_threshold_records", "guac_result_somatic_records", "guac_result_counts",
     "guac_result_bytes", "guac_result_stats", "guac_result_free", "guac_partition_loci_uniformly",
+    "guac_somatic_genotype_filter",
 ]
 
 _lib = None
@@ -81,5 +82,7 @@ def lib():
     L.guac_result_free.restype = None
     L.guac_partition_loci_uniformly.argtypes = [C.c_int64, C.POINTER(abi.LocusRangeC), C.c_size_t,
                                                 C.POINTER(abi.LocusRangeC), C.c_size_t, C.POINTER(C.c_size_t)]
+    L.guac_somatic_genotype_filter.argtypes = [vp, C.c_size_t, C.POINTER(abi.SomaticFilterParamsC), vp]
+    L.guac_somatic_genotype_filter.restype = C.c_size_t
     _lib = L
     return L

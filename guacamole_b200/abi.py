@@ -103,6 +103,14 @@ class SomaticRecordC(C.Structure):
                 ("tumor", AlleleEvidenceC), ("normal", AlleleEvidenceC)]
 
 
+class SomaticFilterParamsC(C.Structure):
+    _fields_ = [("min_tumor_read_depth", C.c_int32), ("max_tumor_read_depth", C.c_int32),
+                ("min_normal_read_depth", C.c_int32), ("min_tumor_alternate_read_depth", C.c_int32),
+                ("min_lod", C.c_int32), ("min_likelihood", C.c_int32), ("min_vaf", C.c_int32),
+                ("min_average_mapping_quality", C.c_int32), ("min_average_base_quality", C.c_int32),
+                ("max_median_mismatches", C.c_int32), ("seq_overload", C.c_int32), ("pad_", C.c_int32)]
+
+
 class LocusCountsC(C.Structure):
     _fields_ = [("locus", C.c_int64), ("contig", C.c_int32), ("depth", C.c_int32), ("positive_depth", C.c_int32),
                 ("reference_depth", C.c_int32), ("base_count", C.c_int32 * 4), ("other_count", C.c_int32),

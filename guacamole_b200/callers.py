@@ -250,3 +250,21 @@ def pileup_counts(ctx: Context, reads: PackedReads, loci_partitions, skip_empty:
     h = C.c_void_p()
     ctx._check(lib().guac_pileup_counts(ctx._h, reads._h, arr, n, int(skip_empty), C.byref(h)))
     return Result(h, "counts")
+
+
+def somatic_genotype_filter(records: np.ndarray, min_tumor_read_depth=0, max_tumor_read_depth=2 ** 31 - 1, min_normal_read_depth=0,
+                            min_tumor_alternate_read_depth=0, min_lod=0, min_likelihood=0, min_vaf=0,
+                            min_average_mapping_quality=0, min_average_base_quality=0, max_median_mismatches=2 ** 31 - 1,
+                            seq_overload=False) -> np.ndarray:
+    """SomaticGenotypeFilter over an array of guac_somatic_record (SOMATIC_DTYPE): boolean keep mask
+    (filters/SomaticGenotypeFilter.scala:282-335; called after findPotentialVariantAtLocus, SomaticStandardCaller.scala:125-151)."""
+    recs = np.ascontiguousarray(records)
+    assert recs.dtype == SOMATIC_DTYPE
+    prm = abi.SomaticFilterParamsC(min_tumor_read_depth, max_tumor_read_depth, min_normal_read_depth,
+                                   min_tumor_alternate_read_depth, min_lod, min_likelihood, min_vaf,
+                                   min_average_mapping_quality, min_average_base_quality, max_median_mismatches,
+                                   int(seq_overload), 0)
+    keep = np.zeros(len(recs), np.uint8)
+    if len(recs):
+        lib().guac_somatic_genotype_filter(recs.ctypes.data_as(C.c_void_p), len(recs), C.byref(prm), keep.ctypes.data_as(C.c_void_p))
+    return keep.astype(bool)

@@ -709,6 +709,35 @@ const uint8_t* guac_result_bytes(const guac_result* r, size_t* n_bytes) {
 const guac_stats* guac_result_stats(const guac_result* r) { return r ? &r->stats : nullptr; }
 void guac_result_free(guac_result* r) { delete r; }
 
+// SomaticGenotypeFilter (filters/SomaticGenotypeFilter.scala): cheap predicates on the emitted records
+size_t guac_somatic_genotype_filter(const guac_somatic_record* g, size_t n, const guac_somatic_filter_params* p, uint8_t* keep) {
+  if (!g || !p || !keep) return 0;
+  size_t kept = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const guac_allele_evidence& t = g[i].tumor;
+    const guac_allele_evidence& nrm = g[i].normal;
+    // SomaticReadDepthFilter.withinReadDepthRange: min inclusive, max exclusive; the normal side has no upper bound
+    bool ok = t.read_depth >= p->min_tumor_read_depth && t.read_depth < p->max_tumor_read_depth &&
+              nrm.read_depth >= p->min_normal_read_depth && nrm.read_depth < 0x7FFFFFFF;
+    if (p->min_tumor_alternate_read_depth > 0) ok = ok && t.allele_read_depth >= p->min_tumor_alternate_read_depth;
+    const float vaf = (float)t.allele_read_depth / (float)t.read_depth;  // AlleleEvidence.variantAlleleFrequency (Float)
+    ok = ok && ((double)vaf * 100.0 > (double)p->min_vaf);
+    ok = ok && g[i].phred_scaled_somatic_likelihood >= p->min_likelihood;
+    if (!p->seq_overload) {
+      ok = ok && g[i].somatic_log_odds > (double)p->min_lod;
+      ok = ok && t.mean_mapping_quality >= (double)p->min_average_mapping_quality &&
+           nrm.mean_mapping_quality >= (double)p->min_average_mapping_quality;
+      // SomaticAverageBaseQualityFilter compares meanMappingQuality (sic) against the base-quality bound
+      ok = ok && t.mean_mapping_quality >= (double)p->min_average_base_quality &&
+           nrm.mean_mapping_quality >= (double)p->min_average_base_quality;
+      ok = ok && t.median_mismatches_per_read <= (double)p->max_median_mismatches;
+    }
+    keep[i] = ok ? 1 : 0;
+    kept += ok ? 1 : 0;
+  }
+  return kept;
+}
+
 // partitionLociUniformly (DistributedUtil.scala:83-108): host-side LociPartitioning
 guac_status guac_partition_loci_uniformly(int64_t tasks, const guac_locus_range* loci, size_t n_loci, guac_locus_range* out,
                                           size_t max_out, size_t* n_out) {

@@ -260,6 +260,29 @@ const uint8_t* guac_result_bytes(const guac_result* r, size_t* n_bytes);        
 const guac_stats* guac_result_stats(const guac_result* r);
 void guac_result_free(guac_result* r);
 
+/* ---- post-call genotype filters (host-side predicates on emitted records) -------------------------------
+ * filters/SomaticGenotypeFilter.scala: SomaticReadDepthFilter (:69-75, upper bound exclusive, filters/GenotypeFilter.scala:63),
+ * SomaticAlternateReadDepthFilter (:107-110), SomaticLogOddsFilter (:176-179), SomaticMinimumLikelihoodFilter (:38-41),
+ * SomaticVAFFilter (:142-145, Float VAF), SomaticAverageMappingQualityFilter (:210-214), SomaticAverageBaseQualityFilter
+ * (:194-198 — tests MAPPING quality, kept as is), SomaticMedianMismatchFilter (:228-231). */
+typedef struct guac_somatic_filter_params {   /* SomaticGenotypeFilterArguments :245-280; defaults in brackets */
+  int32_t min_tumor_read_depth;            /* --min-tumor-read-depth [0] */
+  int32_t max_tumor_read_depth;            /* --max-tumor-read-depth [INT32_MAX] */
+  int32_t min_normal_read_depth;           /* --min-normal-read-depth [0] */
+  int32_t min_tumor_alternate_read_depth;  /* --min-tumor-alternate-read-depth [0 = off] */
+  int32_t min_lod;                         /* --min-lod [0] */
+  int32_t min_likelihood;                  /* --min-likelihood [0] */
+  int32_t min_vaf;                         /* --min-vaf [0] */
+  int32_t min_average_mapping_quality;     /* --min-average-mapping-quality [0] */
+  int32_t min_average_base_quality;        /* --min-average-base-quality [0] */
+  int32_t max_median_mismatches;           /* --max-median-mismatches [INT32_MAX] */
+  int32_t seq_overload;                    /* 1: the Seq[...] overload (:310-335: depth, VAF, likelihood, alternate depth only) */
+  int32_t pad_;
+} guac_somatic_filter_params;
+/* keep[i] = 1 if records[i] passes every filter; returns the number kept. */
+size_t guac_somatic_genotype_filter(const guac_somatic_record* records, size_t n, const guac_somatic_filter_params* params,
+                                    uint8_t* keep);
+
 /* ---- LociPartitioning (host-side; DistributedUtil.scala:83-108). Writes at most max_out ranges (task set),
  * returns the number produced through *n_out. ------------------------------------------------------------- */
 guac_status guac_partition_loci_uniformly(int64_t tasks, const guac_locus_range* loci, size_t n_loci,

@@ -98,3 +98,33 @@ def test_synth_is_deterministic_and_consistent():
     # overlapping reads agree on it (no order-sensitive loci by construction)
     c = orc.pileup_counts(a, [(0, 0, 49999)]).counts()
     assert len(c) > 40000 and c["depth"].max() < 80
+
+
+def test_somatic_genotype_filter_matches_oracle():
+    """guac_somatic_genotype_filter (host code of the engine, no GPU needed) against the oracle's restatement of
+    SomaticGenotypeFilter.apply(Seq, ...) on the records the oracle calls on the reference's tumor/normal fixture."""
+    import numpy as np
+    import oracle_binding as orc
+    from conftest import load_golden
+    from guacamole_b200.callers import SOMATIC_DTYPE, somatic_genotype_filter
+    t = load_golden("tumor.chr20.tough").filtered(non_duplicate=True, passed_qc=True, has_md=True).sorted()
+    n = load_golden("normal.chr20.tough").filtered(non_duplicate=True, passed_qc=True, has_md=True).sorted()
+    c = t.contig_names.index("20")
+    recs = orc.somatic_standard(t, n, [(c, 0, 63025520)], orc.somatic_params(odds=20)).somatic()
+    assert len(recs) > 30
+    arr = np.zeros(len(recs), SOMATIC_DTYPE)
+    for i, r in enumerate(recs):
+        arr[i] = np.frombuffer(bytes(r["_raw"]), dtype=SOMATIC_DTYPE)[0]
+    kw = dict(min_tumor_read_depth=8, max_tumor_read_depth=200, min_normal_read_depth=4, min_tumor_alternate_read_depth=3,
+              min_vaf=5, min_likelihood=70)
+    got = somatic_genotype_filter(arr, seq_overload=True, **kw)
+    want = [orc.somatic_genotype_filter(r["_raw"], 8, 200, 4, 3, 120, 5, 70) for r in recs]
+    assert list(got) == want and 0 < sum(want) < len(want)
+    # the RDD overload adds LOD / mean-MQ / median-mismatch predicates: each can only remove records
+    strict = somatic_genotype_filter(arr, min_lod=1, min_average_mapping_quality=40, max_median_mismatches=3, **kw)
+    assert np.all(~strict | got) and strict.sum() <= got.sum()
+    # all defaults: what is left are the predicates that bite at 0 (log odds > 0, VAF > 0, phred >= 0, NaN means fail)
+    default = (arr["somatic_log_odds"] > 0) & (arr["tumor"]["allele_read_depth"] > 0) & (arr["phred_scaled_somatic_likelihood"] >= 0) & \
+              (arr["tumor"]["mean_mapping_quality"] >= 0) & (arr["normal"]["mean_mapping_quality"] >= 0) & \
+              (arr["tumor"]["median_mismatches_per_read"] <= 2 ** 31 - 1)
+    assert np.array_equal(somatic_genotype_filter(arr), default)
