@@ -373,7 +373,8 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
   };
   if (ctx->n_tiles == 0) {
     append_rows_past_track();
-    res.stats.loci_visited = res.stats.records = res.counts.size();
+    res.stats.records = res.counts.size();
+    res.stats.loci_visited = prm.skip_empty ? 0 : requested;
     return;
   }
   static bool attrs_done = false;
@@ -490,7 +491,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
         });
       }
     }
-    res.stats.loci_visited = c[3] + (prm.mode == 1 ? res.counts.size() - n_rec : 0);
+    res.stats.loci_visited = c[3] + (prm.skip_empty ? 0 : requested - tile_loci);  // loci past the track: empty pileups
     res.stats.tie_loci = c[4];
     res.stats.records = prm.mode == 1 ? res.counts.size() : n_rec;
     res.stats.kernel_ms = tile_ms + exact_ms;

@@ -199,3 +199,59 @@ def test_sharded_ranks_equal_single_run(ctx):
         mine = ranges_of_rank(parts, rank)
         merged += gpu_threshold(ctx, shard_reads(b, mine), mine).genotypes()
     assert sorted(merged, key=lambda r: (r["contig"], r["start"], r["ref"], r["alt"])) == full and len(full) > 100
+
+
+def test_more_input_errors(ctx):
+    from guacamole_b200._lib import GuacError
+    import numpy as np
+
+    def code_of(batch, **kw):
+        with pytest.raises(GuacError) as e:
+            ctx.pack(batch, **kw)
+        return e.value.code
+
+    assert code_of(ReadBatch.from_records([make_read("ACGTACGT", "4M2P4M", "8", 3)])) == abi.ERR_INVALID_CIGAR            # P operator
+    past = ReadBatch.from_records([make_read("ACGTACGT", "8M", "8", 95, "c")], contig_names=["c"], contig_lengths=[100])
+    assert code_of(past) == abi.ERR_INVALID_ARGUMENT                                                                        # read ends past its contig
+    badq = ReadBatch.from_records([make_read("ACGT", "4M", "4", 3, quality_scores=[30, 200, 30, 30])])
+    assert code_of(badq) == abi.ERR_BAD_QUALITY                                                                             # quality byte > 127
+    two = ReadBatch.from_records([make_read("ACGT", "4M", "4", 3, sample="a"), make_read("ACGT", "4M", "4", 4, sample="b")])
+    assert code_of(two) == abi.ERR_UNSUPPORTED                                                                              # one sample per read set
+    ok = ctx.pack(ReadBatch.from_records([make_read("ACGT", "4M", "4", 3)]))
+    from guacamole_b200 import callers
+    with pytest.raises(GuacError) as e:
+        callers.germline_threshold(ctx, ok, [(5, 0, 10)])
+    assert e.value.code == abi.ERR_INVALID_ARGUMENT                                                                         # contig out of range
+    ok.free()
+
+
+def test_depth_overflow_retry_and_long_reads(ctx):
+    from guacamole_b200 import synth
+    # ~300x: deeper than the 8-bit counter fields but under 2048 reads per granule -> the engine detects the overflow and
+    # reruns with 16-bit fields
+    b = synth.generate([("c", 6000)], depth=300, seed=41).to_read_batch()
+    assert_counts_equal(ctx, b, [(0, 0, 5999)])
+    assert_threshold_equal(ctx, b, [(0, 0, 5999)])
+    # 700 bp reads span more than the seven plane pairs the fast path preloads (rolling-window path)
+    long_reads = synth.generate([("c", 60000)], depth=20, read_length=700, seed=43).to_read_batch()
+    assert_counts_equal(ctx, long_reads, [(0, 0, 59999)])
+    assert_threshold_equal(ctx, long_reads, [(0, 0, 59999)])
+    # reads much shorter than a word
+    short_reads = synth.generate([("c", 20000)], depth=15, read_length=25, seed=45, frac_clip=0.0).to_read_batch()
+    assert_counts_equal(ctx, short_reads, [(0, 0, 19999)])
+    assert_threshold_equal(ctx, short_reads, [(0, 3, 19990)], threshold=0)
+
+
+def test_no_skip_empty_and_fasta_threshold(ctx):
+    b = ReadBatch.from_records([make_read("TCGATCGA", "8M", "8", 1), make_read("TCGATCGA", "8M", "8", 1), make_read("GCGATCGA", "8M", "0T7", 1),
+                                make_read("ACGTACGT", "8M", "8", 2000)])
+    assert_threshold_equal(ctx, b, [(0, 0, 3000)], threshold=0, skip_empty=False)
+    assert_threshold_equal(ctx, b, [(0, 0, 3000)], threshold=0, skip_empty=False, emit_ref=True, emit_no_call=True)
+    # with a FASTA reference the pileup's reference base is the FASTA base, whatever the MD tags say
+    ref = [b"N" + b"ACGATCGA" + b"N" * 3000]
+    from guacamole_b200 import callers
+    want = orc.germline_threshold(b, [(0, 0, 20)], orc.threshold_params(0), reference=ref).threshold()
+    reads = ctx.pack(b, ref)
+    got = callers.germline_threshold(ctx, reads, [(0, 0, 20)], threshold=0).genotypes()
+    reads.free()
+    assert got == want and any(g["start"] == 1 and g["ref"] == "A" for g in got)
