@@ -58,53 +58,69 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons sampled DURING the timed region: NVML in a background thread every 5 ms (the timed
+    region of the resident leg lasts milliseconds), nvidia-smi as the fallback."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples, self.reason_bits, self.max_mhz = [], 0, None
+        self._stop = threading.Event()
+        self.thread = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        n = self.nvml
+        try:
+            self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self._stop.is_set():
+            self._sample()
+            self._stop.wait(0.005)
 
     def start(self):
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+        if self.nvml:
+            self._sample()
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if not self.nvml:
+            return self._smi_once()
+        self._stop.set()
+        if self.thread:
+            self.thread.join(timeout=1)
+        self._sample()
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.reason_bits & bit)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml"}
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc.wait(timeout=2)
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            f = [x.strip() for x in out]
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]),
+                    "reasons": [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")], "samples": 1,
+                    "source": "nvidia-smi (after the timed region)"}
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
 
 
 def measured_traffic(kernel, n_loci, depth):
@@ -269,6 +285,7 @@ def main():
 
     ctx = callers.Context(local_rank)
     ctx.set_option(abi.OPT_PACK_QUALITIES, 1 if somatic else 0)
+    ctx.set_option(abi.OPT_HOST_THREADS, max(1, n_threads // world))  # ranks share the box's host cores
     packed = [ctx.pack_c(v, names) for v in views]
     pack_ms = sum(p.pack_kernel_ms for p in packed)
 

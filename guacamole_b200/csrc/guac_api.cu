@@ -69,7 +69,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     std::vector<int64_t> contig_end;
     StatusError err{GUAC_OK, ""};
   };
-  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const unsigned hw = ctx->host_threads > 0 ? (unsigned)ctx->host_threads : std::max(1u, std::thread::hardware_concurrency());
   const size_t n_chunks = n < 200000 ? 1 : std::min<size_t>(hw, 64);
   std::vector<Chunk> chunks(n_chunks);
   auto header_pass = [&](Chunk& ch) {
@@ -586,6 +586,7 @@ guac_status guac_ctx_set_option(guac_ctx* ctx, int option, int64_t value) {
   switch (option) {
     case GUAC_OPT_SORT_RECORDS: ctx->sort_records = value != 0; return GUAC_OK;
     case GUAC_OPT_PACK_QUALITIES: ctx->pack_qualities = value != 0; return GUAC_OK;
+    case GUAC_OPT_HOST_THREADS: ctx->host_threads = value > 0 ? (int)value : 0; return GUAC_OK;
   }
   ctx->last_error = "unknown option";
   return GUAC_ERR_INVALID_ARGUMENT;

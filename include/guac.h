@@ -217,6 +217,8 @@ const char* guac_status_string(guac_status s);
                                       Common.scala:293) */
 #define GUAC_OPT_PACK_QUALITIES 2  /* [1] copy base qualities to the device at pack time; germline-threshold never reads
                                       them, somatic-standard needs them */
+#define GUAC_OPT_HOST_THREADS 3     /* [0 = all] host threads guac_reads_pack may use for its header pass (set it to
+                                      cores / ranks when several ranks share one box) */
 guac_status guac_ctx_set_option(guac_ctx* ctx, int option, int64_t value);
 
 /* Device-side stopwatch on the context's stream (CUDA events): start, run any number of calls, stop -> elapsed ms. */
