@@ -31,8 +31,8 @@ constexpr int kSomMaxAlleles = 10;                                           // 
 constexpr int kSomMaxGenotypes = kSomMaxAlleles * (kSomMaxAlleles + 1) / 2;
 constexpr int kSomTab = 24;                                                  // distinct alleles kept per sample and locus
 
-// d_tables layout (doubles): succ[256] | nl1[256] nl0[256] | tl1[256][256] tl0[256][256]   (index [mapq][quality])
-constexpr int kTabSucc = 0, kTabNl1 = 256, kTabNl0 = 512, kTabTl1 = 768, kTabTl0 = 768 + 65536, kTabTotal = 768 + 2 * 65536;
+// d_tables layout (doubles): succ[256] | normal (l1, l0)[256] | tumor (l1, l0)[256 mapq][256 quality] — pairs are read as double2
+constexpr int kTabSucc = 0, kTabN = 256, kTabT = 768, kTabTotal = 768 + 2 * 65536;
 
 struct SomParams {
   int32_t odds_threshold, min_mapq, filter_multi_allelic, max_read_depth, skip_empty, tumor_sample;
@@ -245,11 +245,12 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
   const int g = span_lo >> kGranuleShift;
   const uint32_t first = R.gran_first[ci.gran_off + g], last = R.gran_last[ci.gran_off + g];
   if (first == 0xFFFFFFFFu) return;
-  const double* l1_tab = tables + (TUMOR ? kTabTl1 : kTabNl1);
-  const double* l0_tab = tables + (TUMOR ? kTabTl0 : kTabNl0);
+  const double2* __restrict__ tab = reinterpret_cast<const double2*>(tables + (TUMOR ? kTabT : kTabN));
   const uint8_t ref_base = std_ref ? code_base(rcode) : (uint8_t)'N';
-  // per-class sums, class = base code ^ reference code (class 0 = the reference base): the common class stays branch-free
-  double sr1 = 0.0, sr0 = 0.0;
+  // the reference class is the common one: it keeps one running sum (its S0 is T0 minus the other classes' S0 at the
+  // end) and a packed element counter; the mismatch classes are touched only when some lane mismatches
+  double sr1 = 0.0;
+  unsigned long long cnt_packed = 0;  // four 16-bit fields, one per base code
   for (uint32_t base = first; base < last; base += 32) {
     const uint32_t mine = base + lane;
     ReadRec my{0, 0, 0, 0};
@@ -268,18 +269,11 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
         A.any += (st <= x && x < en) ? 1 : 0;
       }
     }
-    uint64_t my_seq_off = 0;
-    if (ov & (1u << lane)) my_seq_off = R.seq_off[mine];
     while (ov) {  // warp-uniform
       const int j = __ffs(ov) - 1;
       ov &= ov - 1;
-      ReadRec rec;
-      rec.start = __shfl_sync(0xFFFFFFFFu, my.start, j);
-      rec.end = __shfl_sync(0xFFFFFFFFu, my.end, j);
-      rec.pair_off = __shfl_sync(0xFFFFFFFFu, my.pair_off, j);
-      rec.info = __shfl_sync(0xFFFFFFFFu, my.info, j);
-      const uint64_t seq_off = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(my_seq_off >> 32), j) << 32) |
-                               __shfl_sync(0xFFFFFFFFu, (uint32_t)my_seq_off, j);
+      const ReadRec rec = R.rec[base + j];              // same address in every lane: one broadcast load
+      const uint64_t seq_off = R.seq_off[base + j];
       const int mapq = (int)(rec.info >> kInfoMapqShift);
       const bool keep = !(prm.min_mapq > 0) || mapq >= prm.min_mapq;
       const bool inside = rec.start <= x && x < rec.end;
@@ -308,26 +302,32 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
       if (other) { A.other += 1; continue; }
       A.seen |= 1u << code;
       if (!keep) continue;
-      const int ti = TUMOR ? (mapq << 8) + q : q;
-      const double l1 = __ldg(&l1_tab[ti]), l0 = __ldg(&l0_tab[ti]);
-      A.depth += 1;
-      A.t0 += l0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) A.cnt[k] += (code == k) ? 1 : 0;
+      const double2 l = __ldg(&tab[TUMOR ? (mapq << 8) + q : q]);  // (log(s + s), log((1-s) + (1-s)))
+      A.t0 += l.y;
+      cnt_packed += 1ull << (16 * code);
       if (match) {
-        A.ref_depth += 1;
-        sr1 += l1;
-        sr0 += l0;
+        sr1 += l.x;
       } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const bool is = code == k;
-          A.s1[k] += is ? l1 : 0.0;
-          A.s0[k] += is ? l0 : 0.0;
+          A.s1[k] += is ? l.x : 0.0;
+          A.s0[k] += is ? l.y : 0.0;
         }
       }
     }
   }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    A.cnt[k] = (int)((cnt_packed >> (16 * k)) & 0xFFFFu);
+    A.depth += A.cnt[k];
+  }
+  A.ref_depth = std_ref ? A.cnt[rcode] : 0;
+  if (A.depth > 0xFFFF || cnt_packed == ~0ull) A.other += 1;  // (cannot happen below 65,536 reads; the exact kernel decides then)
+  // S0 of the reference class = T0 - the other classes' S0 (every kept plain element is in exactly one class)
+  double sr0 = A.t0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sr0 -= A.s0[k];
   // fold the reference-class sums into their base code
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -446,8 +446,7 @@ __device__ bool exact_sample(const DevReads& R, int contig, int locus, const Som
   double t0 = 0.0, s1c[4] = {0, 0, 0, 0}, s0c[4] = {0, 0, 0, 0};
   int cntc[4] = {0, 0, 0, 0};
   uint32_t seen = 0;
-  const double* l1_tab = tables + (TUMOR ? kTabTl1 : kTabNl1);
-  const double* l0_tab = tables + (TUMOR ? kTabTl0 : kTabNl0);
+  const double2* __restrict__ lut = reinterpret_cast<const double2*>(tables + (TUMOR ? kTabT : kTabN));
   uint32_t first = 0xFFFFFFFFu, last = 0;
   if (locus < ci.length) {
     const int g = locus >> kGranuleShift;
@@ -477,9 +476,9 @@ __device__ bool exact_sample(const DevReads& R, int contig, int locus, const Som
     double l1 = 0.0, l0 = 0.0;
     if (have && keep) {
       const int q = e.qual & 255;
-      const int ti = TUMOR ? (mapq << 8) + q : q;
-      l1 = l1_tab[ti];
-      l0 = l0_tab[ti];
+      const double2 l = __ldg(&lut[TUMOR ? (mapq << 8) + q : q]);
+      l1 = l.x;
+      l0 = l.y;
       depth += 1;
       ref_depth += e.kind == kMatch ? 1 : 0;
       t0 += l0;
@@ -744,12 +743,12 @@ void somatic_init_tables(guac_ctx* ctx) {
   for (int p = 0; p < 256; ++p) t[kTabSucc + p] = 1.0 - std::pow(10.0, -p / 10.0);  // ADAM PhredUtils.phredToSuccessProbability
   for (int q = 0; q < 256; ++q) {
     const double s = t[kTabSucc + q];  // probabilityCorrectIgnoringAlignment
-    t[kTabNl1 + q] = std::log(s + s);
-    t[kTabNl0 + q] = std::log((1 - s) + (1 - s));
+    t[kTabN + 2 * q] = std::log(s + s);
+    t[kTabN + 2 * q + 1] = std::log((1 - s) + (1 - s));
     for (int m = 0; m < 256; ++m) {
       const double sm = t[kTabSucc + q] * t[kTabSucc + m];  // probabilityCorrectIncludingAlignment
-      t[kTabTl1 + m * 256 + q] = std::log(sm + sm);
-      t[kTabTl0 + m * 256 + q] = std::log((1 - sm) + (1 - sm));
+      t[kTabT + 2 * (m * 256 + q)] = std::log(sm + sm);
+      t[kTabT + 2 * (m * 256 + q) + 1] = std::log((1 - sm) + (1 - sm));
     }
   }
   CUDA_OK(cudaMalloc((void**)&ctx->d_tables, kTabTotal * sizeof(double)));
