@@ -258,7 +258,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   CUDA_OK(cudaEventRecord(ctx->ev[0], st));
   out.pack_launches = 0;
   if (n) {
-    k_pack_bases<<<grid_for(n * 32, 256, ctx->sm_count), 256, 0, st>>>(A);
+    k_pack_bases<<<(int)std::min<uint64_t>((n + kPackReads - 1) / kPackReads, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(A);
     k_granule_index<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(A);
     k_granule_max<<<grid_for(gran_off, 256, ctx->sm_count), 256, 0, st>>>(A, (uint32_t)gran_off);
     k_md_track<0><<<grid_for(n, 128, ctx->sm_count), 128, 0, st>>>(A);

@@ -29,40 +29,97 @@ struct PackArgs {
   unsigned long long* counters;  // [0] order-sensitive loci resolved, [1] max reads per granule
 };
 
-// ---- K_pack_bases: warp per read; ASCII bases -> (lo, hi) bit-plane pairs + non-ACGT mask -------------------------
+// ---- K_pack_bases: ASCII bases -> (lo, hi) bit-plane pairs + non-ACGT mask ---------------------------------------------------
+// A CTA takes 64 consecutive reads at a time.  Their bases (and qualities) are one contiguous byte range of the raw columns:
+// it is staged into shared memory with one TMA bulk copy per column (cp.async.bulk, completion on an mbarrier), then every
+// warp packs whole reads out of shared memory: 32 bases per step, three ballots build the lo / hi / exception words.
+constexpr int kPackReads = 64;
+constexpr int kPackStageBytes = 20 * 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {  // 16 B aligned, 16 B multiple
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(phase)
+                 : "memory");
+  } while (!done);
+}
+
 __global__ void __launch_bounds__(256) k_pack_bases(PackArgs A) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  for (uint64_t r = warp; r < A.R.n; r += n_warps) {
-    const uint64_t s0 = A.R.seq_off[r], s1 = A.R.seq_off[r + 1];
-    const int len = (int)(s1 - s0);
-    const uint32_t p0 = A.R.rec[r].pair_off;
-    uint32_t any_exc = 0;
-    bool bad_q = false;
-    for (int base = 0; base < len; base += 32) {
-      int i = base + lane;
-      uint8_t b = i < len ? A.R.seq[s0 + i] : (uint8_t)'A';
-      if (A.R.qual && i < len && A.R.qual[s0 + i] > 127) bad_q = true;
-      uint32_t code = base_code(b);
-      bool exc = i < len && !is_std_base(b);
-      uint32_t lo = __ballot_sync(0xFFFFFFFFu, (code & 1u) && !exc);
-      uint32_t hi = __ballot_sync(0xFFFFFFFFu, (code & 2u) && !exc);
-      uint32_t x = __ballot_sync(0xFFFFFFFFu, exc);
-      any_exc |= x;
-      if (lane == 0) {
-        A.pairs_w[p0 + (base >> 5)] = make_uint2(lo, hi);
-        A.xmask_w[p0 + (base >> 5)] = x;
+  __shared__ __align__(128) uint8_t s_seq[kPackStageBytes];
+  __shared__ __align__(128) uint8_t s_qual[kPackStageBytes];
+  __shared__ __align__(8) uint64_t bar;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  uint32_t phase = 0;
+  const bool have_qual = A.R.qual != nullptr;
+  for (uint64_t r0 = (uint64_t)blockIdx.x * kPackReads; r0 < A.R.n; r0 += (uint64_t)gridDim.x * kPackReads) {
+    const uint64_t r1 = min(r0 + (uint64_t)kPackReads, A.R.n);
+    const uint64_t b0 = A.R.seq_off[r0], b1 = A.R.seq_off[r1];
+    const uint64_t a0 = b0 & ~(uint64_t)15;                      // align the source down to 16 bytes
+    const uint32_t bytes = (uint32_t)(((b1 - a0) + 15) & ~(uint64_t)15);
+    const bool staged = b1 > b0 && (b1 - a0) + 16 <= (uint64_t)kPackStageBytes;  // (the raw columns carry 64 bytes of padding)
+    if (staged) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, have_qual ? 2 * bytes : bytes);
+        bulk_copy_g2s(s_seq, A.R.seq + a0, bytes, &bar);
+        if (have_qual) bulk_copy_g2s(s_qual, A.R.qual + a0, bytes, &bar);
+      }
+      mbar_wait(&bar, phase);
+      phase ^= 1u;
+    }
+    for (uint64_t r = r0 + warp; r < r1; r += 8) {
+      const uint64_t s0 = A.R.seq_off[r], s1 = A.R.seq_off[r + 1];
+      const int len = (int)(s1 - s0);
+      const uint32_t p0 = A.R.rec[r].pair_off;
+      const uint8_t* sq = staged ? s_seq + (s0 - a0) : nullptr;
+      const uint8_t* qq = staged ? s_qual + (s0 - a0) : nullptr;
+      uint32_t any_exc = 0;
+      bool bad_q = false;
+      for (int base = 0; base < len; base += 32) {
+        const int i = base + lane;
+        uint8_t b = 'A';
+        if (i < len) {
+          b = staged ? sq[i] : A.R.seq[s0 + i];
+          if (have_qual && (staged ? qq[i] : A.R.qual[s0 + i]) > 127) bad_q = true;
+        }
+        const uint32_t code = base_code(b);
+        const bool exc = i < len && !is_std_base(b);
+        const uint32_t lo = __ballot_sync(0xFFFFFFFFu, (code & 1u) && !exc);
+        const uint32_t hi = __ballot_sync(0xFFFFFFFFu, (code & 2u) && !exc);
+        const uint32_t x = __ballot_sync(0xFFFFFFFFu, exc);
+        any_exc |= x;
+        if (lane == 0) {
+          A.pairs_w[p0 + (base >> 5)] = make_uint2(lo, hi);
+          A.xmask_w[p0 + (base >> 5)] = x;
+        }
+      }
+      if (__any_sync(0xFFFFFFFFu, bad_q) && lane == 0) report_error(A.err, GUAC_ERR_BAD_QUALITY, r);
+      if (lane == 0 && any_exc) A.rec_w[r].info |= kInfoHasExc;
+      // upper-case the MD tag in place (ADAM MdTag upper-cases before parsing)
+      const uint32_t m0 = A.R.md_off[r], m1 = A.R.md_off[r + 1];
+      for (uint32_t i = m0 + lane; i < m1; i += 32) {
+        const char c = A.md_w[i];
+        if (c >= 'a' && c <= 'z') A.md_w[i] = (char)(c - 32);
       }
     }
-    if (__any_sync(0xFFFFFFFFu, bad_q) && lane == 0) report_error(A.err, GUAC_ERR_BAD_QUALITY, r);
-    if (lane == 0 && any_exc) A.rec_w[r].info |= kInfoHasExc;
-    // upper-case the MD tag in place (ADAM MdTag upper-cases before parsing)
-    const uint32_t m0 = A.R.md_off[r], m1 = A.R.md_off[r + 1];
-    for (uint32_t i = m0 + lane; i < m1; i += 32) {
-      char c = A.md_w[i];
-      if (c >= 'a' && c <= 'z') A.md_w[i] = (char)(c - 32);
-    }
+    __syncthreads();  // the stage buffers are reused by the next block of reads
   }
 }
 
