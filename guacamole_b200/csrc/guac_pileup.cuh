@@ -429,17 +429,29 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
   // ---- phase 3: the caller, one locus per lane per step (stride 32: conflict-free shared memory)
   const bool all_loci = MODE == 1 ? !prm.skip_empty : false;          // rows for empty pileups (counts mode only)
   const bool every_covered = MODE == 1 || prm.emit_ref || prm.emit_no_call;
+  const int thr_plus_1 = prm.threshold_percent + 1;
+  const int td_contig = td.contig, td_begin = td.locus_begin, td_end = td.locus_end;
   for (int x = lane; x < kWarpLoci; x += 32) {
     const CntT c = S.cnt[x];
     const int w = x >> 5, b = x & 31;   // w is warp-uniform
     const bool std_ref = (S.ref_std[w] >> b) & 1u;
     if (c == 0 && std_ref && !every_covered) continue;  // every element matches the reference: nothing to call
     const int locus = tile_lo + x;
-    if (locus < td.locus_begin || locus >= td.locus_end) continue;
+    if (locus < td_begin || locus >= td_end) continue;
     const int total = S.cov.get(x);
-    // cheap reject of the commonest dirty locus: every class seen at most once and one read cannot pass the threshold
-    constexpr CntT kOnes = sizeof(CntT) == 8 ? (CntT)0x0001000100010001ull : (CntT)0x01010101u;
-    if (std_ref && !every_covered && (c & ~kOnes) == 0 && 100 < (prm.threshold_percent + 1) * total) continue;
+    // cheap exact reject of most dirty loci: no class (mismatch or "other") is large enough to pass the threshold, so the
+    // only allele that can pass is the reference one and nothing is emitted
+    if (std_ref && !every_covered) {
+      uint32_t maxf;
+      if constexpr (sizeof(CntT) == 4) {
+        const uint32_t m = __vmaxu4((uint32_t)c, (uint32_t)c >> 16);
+        maxf = max(m & 0xFFu, (m >> 8) & 0xFFu);
+      } else {
+        const uint32_t lo2 = __vmaxu2((uint32_t)c, (uint32_t)(c >> 32));
+        maxf = max(lo2 & 0xFFFFu, lo2 >> 16);
+      }
+      if ((long long)maxf * 100 < (long long)(thr_plus_1) * total) continue;
+    }
     if (total == 0 && !all_loci) continue;  // callVariantsAtLocus returns nothing on an empty pileup
     const int o = (int)((uint32_t)c & FMASK);
     const int m1 = (int)((uint32_t)(c >> FB) & FMASK), m2 = (int)((uint32_t)(c >> (2 * FB)) & FMASK), m3 = (int)((uint32_t)(c >> (3 * FB)) & FMASK);
@@ -448,14 +460,14 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     if (MODE == 1) {
       if (!std_ref && total > 0) {
         uint32_t s = (uint32_t)atomicAdd(&out.counters[2], 1ull);
-        if (s < out.cap_slow) out.slow[s] = SlowLocus{td.contig, locus};
+        if (s < out.cap_slow) out.slow[s] = SlowLocus{td_contig, locus};
         continue;
       }
       uint32_t s = (uint32_t)atomicAdd(&out.counters[0], 1ull);
       if (s < out.cap_rec) {
         guac_locus_counts g;
         g.locus = locus;
-        g.contig = td.contig;
+        g.contig = td_contig;
         g.depth = total;
         g.positive_depth = S.pos.get(x);
         g.reference_depth = std_ref ? total - o - m1 - m2 - m3 : 0;
@@ -478,7 +490,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     const bool exact = std_ref && !passes(o);
     if (!exact) {
       uint32_t s = (uint32_t)atomicAdd(&out.counters[2], 1ull);
-      if (s < out.cap_slow) out.slow[s] = SlowLocus{td.contig, locus};
+      if (s < out.cap_slow) out.slow[s] = SlowLocus{td_contig, locus};
       continue;
     }
     const int mref = total - o - m1 - m2 - m3;
@@ -516,7 +528,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
       if (s < out.cap_rec) {
         guac_threshold_record rcd;
         rcd.start = locus;
-        rcd.contig = td.contig;
+        rcd.contig = td_contig;
         rcd.sample = prm.sample;
         rcd.ref_off = kPoolByteOff + rbase;
         rcd.ref_len = 1;
