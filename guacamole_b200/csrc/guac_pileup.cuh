@@ -598,7 +598,7 @@ __device__ long md_deleted_offset(const DevReads& R, uint64_t r, int pos) {
 }
 
 // PileupElement(read, locus, referenceBase) + alignment + qualityScore  (pileup/PileupElement.scala:68-171, 220-274)
-__device__ int classify(const DevReads& R, uint64_t r, int locus, uint8_t ref_base, Elem& e) {
+__device__ __noinline__ int classify(const DevReads& R, uint64_t r, int locus, uint8_t ref_base, Elem& e) {
   const ReadRec rec = R.rec[r];
   const uint32_t c0 = R.cig_off[r], c1 = R.cig_off[r + 1];
   const uint8_t* seq = R.seq + R.seq_off[r];

@@ -25,6 +25,10 @@
 #include "guac_host.cuh"
 #include "guac_pileup.cuh"
 
+#ifndef GUAC_SOM_EXP
+#define GUAC_SOM_EXP 0  // timing experiments only (1: no table load, 2: no quality load, 3: no fp64 adds)
+#endif
+
 namespace guac {
 
 constexpr int kSomMaxAlleles = 10;                                           // alleles entering the genotype enumeration
@@ -251,61 +255,95 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
   // end) and a packed element counter; the mismatch classes are touched only when some lane mismatches
   double sr1 = 0.0;
   unsigned long long cnt_packed = 0;  // four 16-bit fields, one per base code
+  const bool fma = prm.filter_multi_allelic != 0;
+  const int min_mapq = prm.min_mapq;
   for (uint32_t base = first; base < last; base += 32) {
     const uint32_t mine = base + lane;
     ReadRec my{0, 0, 0, 0};
     if (mine < last) my = R.rec[mine];
-    const bool keep_mine = !(prm.min_mapq > 0) || (int)(my.info >> kInfoMapqShift) >= prm.min_mapq;
-    uint32_t ov = __ballot_sync(0xFFFFFFFFu, mine < last && my.start < span_lo + 32 && my.end > span_lo && my.end > my.start &&
-                                                 (keep_mine || prm.filter_multi_allelic));
-    // reads that overlap but are dropped by the mapq filter still decide whether the locus is visited
-    const uint32_t any_m = __ballot_sync(0xFFFFFFFFu, mine < last && my.start < span_lo + 32 && my.end > span_lo && my.end > my.start && !keep_mine);
-    if (any_m && !prm.filter_multi_allelic) {
-      uint32_t m = any_m;
-      while (m) {
-        const int j = __ffs(m) - 1;
-        m &= m - 1;
-        const int st = __shfl_sync(0xFFFFFFFFu, my.start, j), en = __shfl_sync(0xFFFFFFFFu, my.end, j);
-        A.any += (st <= x && x < en) ? 1 : 0;
-      }
+    const bool overlaps = mine < last && my.start < span_lo + 32 && my.end > span_lo && my.end > my.start;
+    const bool keep_mine = !(min_mapq > 0) || (int)(my.info >> kInfoMapqShift) >= min_mapq;
+    const bool simple_mine = (my.info & (kInfoSimple | kInfoHasExc)) == kInfoSimple;
+    // kept SIMPLE reads take the lean loop; everything else (CIGAR walk, mapq-dropped reads that only count towards the
+    // visited loci / the multi-allelic filter) takes the general loop below
+    uint32_t ov = __ballot_sync(0xFFFFFFFFu, overlaps && keep_mine && simple_mine);
+    uint32_t ov_general = __ballot_sync(0xFFFFFFFFu, overlaps && !(keep_mine && simple_mine));
+    // Every lane owns one read of the batch here: fetch its quality offset (one coalesced load for the batch) and pull the
+    // plane word and the 32 quality bytes this word's loci will need into the cache now, so that the per-read loop
+    // below does not serialise one memory round trip after another.
+    uint64_t my_seq_off = 0;
+    if (overlaps && keep_mine && simple_mine) {
+      my_seq_off = R.seq_off[mine];
+      const int idx0 = max((int)(my.info & kInfoLeadMask) + (span_lo - my.start), 0);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(R.qual + my_seq_off + idx0));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(R.qual + my_seq_off + idx0 + 31));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(R.pairs + my.pair_off + (idx0 >> 5)));
     }
-    while (ov) {  // warp-uniform
+    while (ov) {  // warp-uniform, lean: SIMPLE read kept by the mapq filter
       const int j = __ffs(ov) - 1;
       ov &= ov - 1;
-      const ReadRec rec = R.rec[base + j];              // same address in every lane: one broadcast load
-      const uint64_t seq_off = R.seq_off[base + j];
-      const int mapq = (int)(rec.info >> kInfoMapqShift);
-      const bool keep = !(prm.min_mapq > 0) || mapq >= prm.min_mapq;
-      const bool inside = rec.start <= x && x < rec.end;
-      A.any += inside ? 1 : 0;
-      int code = -1, q = 0;
-      bool other = false, match = false;
-      if ((rec.info & (kInfoSimple | kInfoHasExc)) == kInfoSimple) {
-        if (inside) {
-          const int idx = (int)(rec.info & kInfoLeadMask) + (x - rec.start);
-          const uint2 pw = __ldg(&R.pairs[rec.pair_off + (idx >> 5)]);
-          code = (int)((pw.x >> (idx & 31)) & 1u) | ((int)((pw.y >> (idx & 31)) & 1u) << 1);
-          q = (int)__ldg(&R.qual[seq_off + idx]);
-          match = std_ref && code == rcode;
-        }
-      } else if (inside) {
-        Elem e;
-        const int rc = classify(R, (uint64_t)(base + j), x, ref_base, e);
-        if (rc || e.kind == kNone) other = true;  // the exact kernel reports the error
-        else if ((e.kind == kMatch || e.kind == kMismatch) && is_std_base(e.base)) {
-          code = (int)base_code(e.base);
-          q = e.qual;
-          match = e.kind == kMatch;
-        } else other = true;
-      }
-      if (!inside) continue;
-      if (other) { A.other += 1; continue; }
-      A.seen |= 1u << code;
-      if (!keep) continue;
-      const double2 l = __ldg(&tab[TUMOR ? (mapq << 8) + q : q]);  // (log(s + s), log((1-s) + (1-s)))
+      ReadRec rec;
+      rec.start = __shfl_sync(0xFFFFFFFFu, my.start, j);
+      rec.end = __shfl_sync(0xFFFFFFFFu, my.end, j);
+      rec.pair_off = __shfl_sync(0xFFFFFFFFu, my.pair_off, j);
+      rec.info = __shfl_sync(0xFFFFFFFFu, my.info, j);
+      const uint64_t seq_off = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(my_seq_off >> 32), j) << 32) |
+                               __shfl_sync(0xFFFFFFFFu, (uint32_t)my_seq_off, j);
+      const int idx = (int)(rec.info & kInfoLeadMask) + (x - rec.start);
+      if ((unsigned)(x - rec.start) >= (unsigned)(rec.end - rec.start)) continue;  // this lane's locus is outside the read
+      const uint2 pw = __ldg(&R.pairs[rec.pair_off + (idx >> 5)]);
+#if GUAC_SOM_EXP == 2
+      const int q = idx & 63;
+#else
+      const int q = (int)__ldg(&R.qual[seq_off + idx]);
+#endif
+      const int code = (int)((pw.x >> (idx & 31)) & 1u) | ((int)((pw.y >> (idx & 31)) & 1u) << 1);
+#if GUAC_SOM_EXP == 1
+      const double2 l = make_double2(1e-3 * q, 2e-3);
+#else
+      const double2 l = __ldg(&tab[TUMOR ? (int)((rec.info >> kInfoMapqShift) << 8) + q : q]);  // (log(s + s), log((1-s) + (1-s)))
+#endif
+      A.any += 1;
+#if GUAC_SOM_EXP == 3
+      A.any += __double2hiint(l.y) + __double2hiint(l.x);
+      cnt_packed += 1ull << (16 * code);
+      continue;
+#endif
       A.t0 += l.y;
       cnt_packed += 1ull << (16 * code);
-      if (match) {
+      if (std_ref && code == rcode) {
+        sr1 += l.x;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool is = code == k;
+          A.s1[k] += is ? l.x : 0.0;
+          A.s0[k] += is ? l.y : 0.0;
+        }
+      }
+    }
+    while (ov_general) {  // warp-uniform, rare
+      const int j = __ffs(ov_general) - 1;
+      ov_general &= ov_general - 1;
+      const ReadRec rec = R.rec[base + j];
+      if (!(rec.start <= x && x < rec.end)) continue;
+      A.any += 1;
+      const int mapq = (int)(rec.info >> kInfoMapqShift);
+      const bool keep = !(min_mapq > 0) || mapq >= min_mapq;
+      if (!keep && !fma) continue;
+      Elem e;
+      const int rc = classify(R, (uint64_t)(base + j), x, ref_base, e);
+      if (rc || !((e.kind == kMatch || e.kind == kMismatch) && is_std_base(e.base))) {
+        A.other += 1;  // insertion / deletion / clipped / non-ACGT element (or an error the exact kernel reports)
+        continue;
+      }
+      const int code = (int)base_code(e.base);
+      A.seen |= 1u << code;
+      if (!keep) continue;
+      const double2 l = __ldg(&tab[TUMOR ? (mapq << 8) + (e.qual & 255) : (e.qual & 255)]);
+      A.t0 += l.y;
+      cnt_packed += 1ull << (16 * code);
+      if (e.kind == kMatch) {
         sr1 += l.x;
       } else {
 #pragma unroll
@@ -323,6 +361,8 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
     A.depth += A.cnt[k];
   }
   A.ref_depth = std_ref ? A.cnt[rcode] : 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) A.seen |= A.cnt[k] > 0 ? (1u << k) : 0u;
   if (A.depth > 0xFFFF || cnt_packed == ~0ull) A.other += 1;  // (cannot happen below 65,536 reads; the exact kernel decides then)
   // S0 of the reference class = T0 - the other classes' S0 (every kept plain element is in exactly one class)
   double sr0 = A.t0;
