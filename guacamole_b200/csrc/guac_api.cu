@@ -211,6 +211,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   out.pairs.alloc(pair_total + 8);
   out.xmask.alloc(pair_total + 8);
   out.nm.alloc(n);
+  if (out.has_qualities) out.qc.alloc((n ? (size_t)b->seq_off[n] : 0) + 64);
   CUDA_OK(cudaMemsetAsync(out.pairs.p, 0, out.pairs.bytes(), st));
   CUDA_OK(cudaMemsetAsync(out.xmask.p, 0, out.xmask.bytes(), st));
   out.trk_lo.alloc(word_off + 1);
@@ -242,6 +243,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   A.rec_w = out.rec.p;
   A.pairs_w = out.pairs.p;
   A.xmask_w = out.xmask.p;
+  A.qc_w = out.has_qualities ? out.qc.p : nullptr;
   A.nm_w = out.nm.p;
   A.md_w = out.md.p;
   A.trk_lo_w = out.trk_lo.p;

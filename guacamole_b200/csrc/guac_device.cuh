@@ -5,7 +5,8 @@
 //   pairs[]       8 B/32 bases  bit-plane pairs (lo, hi) of the 2-bit read bases, read coordinates, 32 bases per pair
 //   xmask[]       4 B/32 bases  1 = base is not A/C/G/T (read only for reads flagged HAS_EXC)
 //   cig_off/cigar BAM-encoded run-length CIGAR ops (read only for reads that are not SIMPLE)
-//   seq/qual      raw bytes (qual feeds the likelihood kernels; seq only the exact per-locus path)
+//   seq/qual      raw bytes (the exact per-locus paths read them)
+//   qc[]          1 B/base   quality (6 bits) | base code << 6: the one byte per pileup element the likelihood kernel loads
 //   md_off/md     upper-cased MD strings (deleted bases for the exact per-locus path)
 //   trk_lo/hi/std reference track per contig as three bit-planes, 32 loci per word (MD- or FASTA-derived)
 //   gran_first/last per 1024-loci granule: the range of read indices that can overlap it
@@ -32,6 +33,7 @@ constexpr uint32_t kInfoSimple = 1u << 16;      // one M/=/X segment plus S/H cl
 constexpr uint32_t kInfoHasExc = 1u << 17;      // read holds a non-ACGT base
 constexpr uint32_t kInfoPositive = 1u << 18;    // isPositiveStrand
 constexpr uint32_t kInfoEmpty = 1u << 19;       // consumes no reference (overlaps nothing)
+constexpr uint32_t kInfoWideQ = 1u << 20;       // read holds a base quality > 63 (its qc bytes are not usable)
 constexpr int kInfoMapqShift = 24;
 
 struct __align__(16) ReadRec {
@@ -61,6 +63,7 @@ struct DevReads {
   const uint64_t* seq_off;
   const uint8_t* seq;
   const uint8_t* qual;
+  const uint8_t* qc;          // per base: quality (6 bits) | base code << 6; valid for reads without HAS_EXC / WIDE_Q
   const uint32_t* md_off;
   const char* md;
   const uint16_t* nm;

@@ -331,7 +331,7 @@ struct guac_reads {
   DevBuf<uint32_t> cig_off, cigar, xmask, md_off, trk_lo, trk_hi, trk_std, gran_first, gran_last;
   DevBuf<uint2> pairs;
   DevBuf<uint64_t> seq_off, fasta_off;
-  DevBuf<uint8_t> seq, qual, fasta;
+  DevBuf<uint8_t> seq, qual, qc, fasta;
   DevBuf<char> md;
   DevBuf<uint16_t> nm;
   DevBuf<ContigInfo> d_contigs;
@@ -355,6 +355,7 @@ struct guac_reads {
     R.seq_off = seq_off.p;
     R.seq = seq.p;
     R.qual = qual.p;
+    R.qc = qc.p;
     R.md_off = md_off.p;
     R.md = md.p;
     R.nm = nm.p;
@@ -370,7 +371,7 @@ struct guac_reads {
   }
   uint64_t device_bytes() const {
     return rec.bytes() + cig_off.bytes() + cigar.bytes() + xmask.bytes() + md_off.bytes() + trk_lo.bytes() * 3 +
-           gran_first.bytes() * 2 + pairs.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + md.bytes() + nm.bytes() +
+           gran_first.bytes() * 2 + pairs.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + qc.bytes() + md.bytes() + nm.bytes() +
            fasta.bytes();
   }
 };

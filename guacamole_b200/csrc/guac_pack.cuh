@@ -15,6 +15,7 @@ struct PackArgs {
   ReadRec* rec_w;        // writable aliases
   uint2* pairs_w;
   uint32_t* xmask_w;
+  uint8_t* qc_w;         // (quality | base code << 6) per base, nullptr when qualities are not packed
   uint16_t* nm_w;
   char* md_w;
   uint32_t* trk_lo_w;
@@ -91,15 +92,19 @@ __global__ void __launch_bounds__(256) k_pack_bases(PackArgs A) {
       const uint8_t* sq = staged ? s_seq + (s0 - a0) : nullptr;
       const uint8_t* qq = staged ? s_qual + (s0 - a0) : nullptr;
       uint32_t any_exc = 0;
-      bool bad_q = false;
+      bool bad_q = false, wide_q = false;
       for (int base = 0; base < len; base += 32) {
         const int i = base + lane;
         uint8_t b = 'A';
+        uint32_t q = 0;
         if (i < len) {
           b = staged ? sq[i] : A.R.seq[s0 + i];
-          if (have_qual && (staged ? qq[i] : A.R.qual[s0 + i]) > 127) bad_q = true;
+          if (have_qual) q = staged ? qq[i] : A.R.qual[s0 + i];
         }
+        bad_q = bad_q || q > 127;
+        wide_q = wide_q || q > 63;
         const uint32_t code = base_code(b);
+        if (have_qual && i < len) A.qc_w[s0 + i] = (uint8_t)((q & 63u) | (code << 6));
         const bool exc = i < len && !is_std_base(b);
         const uint32_t lo = __ballot_sync(0xFFFFFFFFu, (code & 1u) && !exc);
         const uint32_t hi = __ballot_sync(0xFFFFFFFFu, (code & 2u) && !exc);
@@ -111,7 +116,8 @@ __global__ void __launch_bounds__(256) k_pack_bases(PackArgs A) {
         }
       }
       if (__any_sync(0xFFFFFFFFu, bad_q) && lane == 0) report_error(A.err, GUAC_ERR_BAD_QUALITY, r);
-      if (lane == 0 && any_exc) A.rec_w[r].info |= kInfoHasExc;
+      const bool any_wide = __any_sync(0xFFFFFFFFu, wide_q);
+      if (lane == 0 && (any_exc || any_wide)) A.rec_w[r].info |= (any_exc ? kInfoHasExc : 0u) | (any_wide ? kInfoWideQ : 0u);
       // upper-case the MD tag in place (ADAM MdTag upper-cases before parsing)
       const uint32_t m0 = A.R.md_off[r], m1 = A.R.md_off[r + 1];
       for (uint32_t i = m0 + lane; i < m1; i += 32) {

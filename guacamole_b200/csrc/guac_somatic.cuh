@@ -25,10 +25,6 @@
 #include "guac_host.cuh"
 #include "guac_pileup.cuh"
 
-#ifndef GUAC_SOM_EXP
-#define GUAC_SOM_EXP 0  // timing experiments only (1: no table load, 2: no quality load, 3: no fp64 adds)
-#endif
-
 namespace guac {
 
 constexpr int kSomMaxAlleles = 10;                                           // alleles entering the genotype enumeration
@@ -144,18 +140,9 @@ __device__ bool tumor_most_likely(const AlleleView& avT, const SomAllele* tabT, 
   return avT.is_variant(*a1) || avT.is_variant(*a2);
 }
 
-// ... normal half: somatic odds against the normal sample's variant genotypes, then the record
-__device__ void somatic_against_normal(const AlleleView& avT, const AlleleView& avN, const AlleleEntry& a1, const AlleleEntry& a2,
-                                       double tumor_l, const SomAllele* tabN, const SampleStats& sN, int contig, int locus,
-                                       const SomParams& prm, SomOut& out) {
-  if (sN.depth == 0 || sN.depth > prm.max_read_depth) return;
-  int gi[kSomMaxGenotypes], gj[kSomMaxGenotypes];
-  double lk[kSomMaxGenotypes];
-  const int ngn = genotype_likelihoods(avN, tabN, sN.n_alleles, sN, gi, gj, lk);
-  if (ngn < 0) { report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus); return; }
-  double normal_variants_total = 0.0;
-  for (int g = 0; g < ngn; ++g)
-    if (avN.is_variant(as_entry(tabN[gi[g]])) || avN.is_variant(as_entry(tabN[gj[g]]))) normal_variants_total += lk[g];
+// ... normal half, last step: somatic odds from the normal sample's variant-genotype mass, then the record
+__device__ void emit_somatic(const AlleleView& avT, const AlleleEntry& a1, const AlleleEntry& a2, double tumor_l,
+                             double normal_variants_total, int contig, int locus, const SomParams& prm, SomOut& out) {
   const double somatic_odds = tumor_l / normal_variants_total;
   if (!(somatic_odds * 100 >= (double)prm.odds_threshold)) return;
   // first non-reference allele of the genotype whose alternate is not empty
@@ -185,6 +172,21 @@ __device__ void somatic_against_normal(const AlleleView& avT, const AlleleView& 
   r.phred_scaled_somatic_likelihood = success_probability_to_phred(r.tumor.likelihood * r.normal.likelihood - 1e-10);
   const uint32_t s = (uint32_t)atomicAdd(&out.counters[0], 1ull);
   if (s < out.cap_rec) out.rec[s] = r;
+}
+
+// ... normal half: the normal sample's genotype likelihoods, summed over the genotypes holding a variant allele
+__device__ void somatic_against_normal(const AlleleView& avT, const AlleleView& avN, const AlleleEntry& a1, const AlleleEntry& a2,
+                                       double tumor_l, const SomAllele* tabN, const SampleStats& sN, int contig, int locus,
+                                       const SomParams& prm, SomOut& out) {
+  if (sN.depth == 0 || sN.depth > prm.max_read_depth) return;
+  int gi[kSomMaxGenotypes], gj[kSomMaxGenotypes];
+  double lk[kSomMaxGenotypes];
+  const int ngn = genotype_likelihoods(avN, tabN, sN.n_alleles, sN, gi, gj, lk);
+  if (ngn < 0) { report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus); return; }
+  double normal_variants_total = 0.0;
+  for (int g = 0; g < ngn; ++g)
+    if (avN.is_variant(as_entry(tabN[gi[g]])) || avN.is_variant(as_entry(tabN[gj[g]]))) normal_variants_total += lk[g];
+  emit_somatic(avT, a1, a2, tumor_l, normal_variants_total, contig, locus, prm, out);
 }
 
 // findPotentialVariantAtLocus once both filtered pileups are summarised.  tabT / tabN sorted by Allele.compare.
@@ -223,18 +225,192 @@ __device__ inline int lower_bound_start(const ReadRec* rec, uint64_t lo, uint64_
 // ---- K_somatic: warp per 32 loci, lane per locus ---------------------------------------------------------------------------------
 struct LaneAcc {
   int depth, ref_depth, other;   // filtered depth, Match elements, elements that are not A/C/G/T matches / mismatches
+  int hard;                      // elements only the exact kernel can handle (it reports their error)
   int any;                       // overlapping reads before any filter (decides whether the locus is visited)
   int cnt[4];                    // filtered elements by base code
   uint32_t seen;                 // base codes seen before the mapq filter (multi-allelic filter)
   double t0, s1[4], s0[4];
+  // over the kept "other" elements (l1, l0 = their table values): sum l0, sum max(0, l0), sum max(l1, l0)
+  double o0, ohet, ohom;
 };
 
 __device__ __forceinline__ void acc_clear(LaneAcc& a) {
-  a.depth = a.ref_depth = a.other = a.any = 0;
+  a.depth = a.ref_depth = a.other = a.hard = a.any = 0;
   a.seen = 0;
-  a.t0 = 0.0;
+  a.t0 = a.o0 = a.ohet = a.ohom = 0.0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) { a.cnt[k] = 0; a.s1[k] = 0.0; a.s0[k] = 0.0; }
+}
+
+// ---- loci whose elements are all A/C/G/T matches / mismatches: at most 4 alleles and 10 genotypes, kept in registers -------
+// (the general routines above index small local arrays, which the compiler places in local memory: at 768 threads per SM
+// that traffic alone thrashes L1.)  Alleles in base-code order = Allele.compare order, since they share the reference base.
+struct SnvAlleles {
+  int n, depth;
+  int code[4];
+  double s1[4], s0[4], t0;
+};
+
+__device__ __forceinline__ void snv_compact(const LaneAcc& A, SnvAlleles& S) {
+  S.n = 0;
+  S.depth = A.depth;
+  S.t0 = A.t0;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) { S.code[p] = 0; S.s1[p] = 0.0; S.s0[p] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool have = A.cnt[k] > 0;
+#pragma unroll
+    for (int p = 0; p <= k; ++p) {
+      const bool here = have && p == S.n;
+      S.code[p] = here ? k : S.code[p];
+      S.s1[p] = here ? A.s1[k] : S.s1[p];
+      S.s0[p] = here ? A.s0[k] : S.s0[p];
+    }
+    S.n += have ? 1 : 0;
+  }
+}
+
+// un-normalised log likelihoods of the genotypes (i <= j < n) in the static slot order (0,0) (0,1) (0,2) (0,3) (1,1) ... (3,3),
+// which restricted to the valid slots is the reference's enumeration order.  Same expression as genotype_likelihoods().
+__device__ __forceinline__ void snv_log_likelihoods(const SnvAlleles& S, double (&lk)[10]) {
+  const double nlog2 = log(2.0) * (double)S.depth;
+  int g = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j) {
+      const double agg = (i == j) ? (S.s1[i] + (S.t0 - S.s0[i])) : (S.t0 - S.s0[i] - S.s0[j]);
+      lk[g++] = agg + 0.0 - nlog2;
+    }
+}
+
+// Likelihood.likelihoodsOfAllPossibleGenotypesFromPileup(..., normalize = true) on the valid slots, in place
+__device__ __forceinline__ void snv_normalize(const SnvAlleles& S, double (&lk)[10]) {
+  double total = 0.0;
+  int g = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j, ++g)
+      if (j < S.n) total += exp(lk[g]);
+  const double log_total = log(total);  // naive normalisation on purpose
+  g = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j, ++g)
+      if (j < S.n) lk[g] = exp(lk[g] - log_total);
+}
+
+// tumor half of findPotentialVariantAtLocus (tumor_most_likely() above) for such a locus over the standard reference base
+// code `rc`.  *c1 / *c2 = base codes of the most likely genotype.
+__device__ __forceinline__ bool snv_tumor_most_likely(const SnvAlleles& S, int ref_depth, int rc, const SomParams& prm, int* c1, int* c2,
+                                                      double* tumor_l) {
+  if (S.depth == 0 || S.depth > prm.max_read_depth || ref_depth == S.depth) return false;
+  double lk[10];
+  snv_log_likelihoods(S, lk);
+  // Exact early out.  If the homozygous-reference genotype leads every other genotype by a clear margin in log space (and
+  // is far from underflow, and nothing is NaN), then it is also the maximum after exp / normalisation, which are monotone
+  // and accurate to an ulp: the most likely genotype holds no variant allele and nothing else about it is needed.
+  {
+    double ref_lk = -1.0 / 0.0;
+    int g = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = i; j < 4; ++j, ++g)
+        if (i == j && i < S.n && S.code[i] == rc) ref_lk = lk[g];
+    bool lead = ref_lk > -700.0;
+    g = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = i; j < 4; ++j, ++g)
+        if (j < S.n && !(i == j && S.code[i] == rc)) lead = lead && (lk[g] < ref_lk - 1e-6);
+    if (lead) return false;
+  }
+  snv_normalize(S, lk);
+  // maxBy = reduceLeft((x, y) => if (f(x) >= f(y)) x else y)
+  double best = 0.0;
+  int bi = 0, bj = 0, g = 0;
+  bool first = true;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j, ++g)
+      if (j < S.n) {
+        if (first || !(best >= lk[g])) { best = lk[g]; bi = i; bj = j; }
+        first = false;
+      }
+  int ci = 0, cj = 0;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    ci = bi == p ? S.code[p] : ci;
+    cj = bj == p ? S.code[p] : cj;
+  }
+  *c1 = ci;
+  *c2 = cj;
+  *tumor_l = best;
+  return ci != rc || cj != rc;
+}
+
+// normal half: likelihood mass of the normal genotypes holding a variant allele (reference base code `rc`)
+__device__ __forceinline__ double snv_normal_variants_total(const SnvAlleles& S, int rc) {
+  double lk[10];
+  snv_log_likelihoods(S, lk);
+  snv_normalize(S, lk);
+  double total = 0.0;
+  int g = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j, ++g)
+      if (j < S.n && (S.code[i] != rc || S.code[j] != rc)) total += lk[g];
+  return total;
+}
+
+// A locus that also holds insertion / deletion / clipped / non-ACGT elements (set O, kept by the mapq filter).  Which
+// alleles they form is unknown here, but every genotype has an upper bound: an element of O contributes at most
+// max(l1, l0) to a homozygous genotype and at most max(0, l0) to a heterozygous one, an A/C/G/T element contributes what it
+// always does.  If the homozygous-reference genotype (whose value is exact) leads all of these bounds by a clear margin,
+// it is the most likely genotype, tumor_most_likely() would return "no variant allele" and the locus yields nothing:
+// no exact pass needed.  (Alleles the reference drops from the enumeration only shrink the candidate set.)
+__device__ __forceinline__ bool ref_leads_despite_others(const LaneAcc& A, int rc) {
+  double s1r = 0.0, s0r = 0.0;
+  int cr = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    s1r = k == rc ? A.s1[k] : s1r;
+    s0r = k == rc ? A.s0[k] : s0r;
+    cr = k == rc ? A.cnt[k] : cr;
+  }
+  if (cr == 0) return false;
+  const double ref_lk = s1r + (A.t0 - s0r) + A.o0;
+  bool lead = ref_lk - log(2.0) * (double)(A.depth + A.other) > -700.0;  // (false for NaN)
+  const double bar = ref_lk - 1e-6;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool have = k != rc && A.cnt[k] > 0;
+    lead = lead && (!have || (A.s1[k] + (A.t0 - A.s0[k]) + A.o0 < bar));  // hom(k)
+    lead = lead && (!have || (A.t0 - s0r - A.s0[k] + A.o0 < bar));        // het(ref, k)
+    lead = lead && (!have || ((A.t0 - A.s0[k]) + A.ohet < bar));          // het(k, O*)
+#pragma unroll
+    for (int m = k + 1; m < 4; ++m) {
+      const bool both = have && m != rc && A.cnt[m] > 0;
+      lead = lead && (!both || (A.t0 - A.s0[k] - A.s0[m] + A.o0 < bar));  // het(k, m)
+    }
+  }
+  lead = lead && ((A.t0 - s0r) + A.ohet < bar);  // het(ref, O*)
+  lead = lead && (A.t0 + A.ohet < bar);          // het(O*, O*)
+  lead = lead && (A.t0 + A.ohom < bar);          // hom(O*)
+  return lead;
+}
+
+__device__ __forceinline__ AlleleEntry snv_entry(int code, int count) {
+  AlleleEntry e;
+  e.kind = 0; e.len = 1; e.ptr = 0; e.base = code_base(code); e.count = count;
+  return e;
 }
 
 template <bool TUMOR>
@@ -252,68 +428,55 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
   const double2* __restrict__ tab = reinterpret_cast<const double2*>(tables + (TUMOR ? kTabT : kTabN));
   const uint8_t ref_base = std_ref ? code_base(rcode) : (uint8_t)'N';
   // the reference class is the common one: it keeps one running sum (its S0 is T0 minus the other classes' S0 at the
-  // end) and a packed element counter; the mismatch classes are touched only when some lane mismatches
+  // end) and a plain counter; the mismatch classes are touched only when some lane mismatches
   double sr1 = 0.0;
-  unsigned long long cnt_packed = 0;  // four 16-bit fields, one per base code
+  int n_ref = 0;
+  unsigned long long cnt_packed = 0;  // mismatching elements: four 16-bit fields, one per base code
+  const uint32_t rc_eff = std_ref ? (uint32_t)rcode : 4u;
   const bool fma = prm.filter_multi_allelic != 0;
   const int min_mapq = prm.min_mapq;
+  constexpr uint32_t kLeanMask = kInfoSimple | kInfoHasExc | kInfoWideQ;
   for (uint32_t base = first; base < last; base += 32) {
     const uint32_t mine = base + lane;
     ReadRec my{0, 0, 0, 0};
     if (mine < last) my = R.rec[mine];
     const bool overlaps = mine < last && my.start < span_lo + 32 && my.end > span_lo && my.end > my.start;
     const bool keep_mine = !(min_mapq > 0) || (int)(my.info >> kInfoMapqShift) >= min_mapq;
-    const bool simple_mine = (my.info & (kInfoSimple | kInfoHasExc)) == kInfoSimple;
-    // kept SIMPLE reads take the lean loop; everything else (CIGAR walk, mapq-dropped reads that only count towards the
-    // visited loci / the multi-allelic filter) takes the general loop below
-    uint32_t ov = __ballot_sync(0xFFFFFFFFu, overlaps && keep_mine && simple_mine);
-    uint32_t ov_general = __ballot_sync(0xFFFFFFFFu, overlaps && !(keep_mine && simple_mine));
-    // Every lane owns one read of the batch here: fetch its quality offset (one coalesced load for the batch) and pull the
-    // plane word and the 32 quality bytes this word's loci will need into the cache now, so that the per-read loop
-    // below does not serialise one memory round trip after another.
-    uint64_t my_seq_off = 0;
-    if (overlaps && keep_mine && simple_mine) {
-      my_seq_off = R.seq_off[mine];
-      const int idx0 = max((int)(my.info & kInfoLeadMask) + (span_lo - my.start), 0);
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(R.qual + my_seq_off + idx0));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(R.qual + my_seq_off + idx0 + 31));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(R.pairs + my.pair_off + (idx0 >> 5)));
+    // kept SIMPLE reads of plain A/C/G/T bases with 6-bit qualities take the lean loop: one byte (quality | base code << 6)
+    // per pileup element.  Everything else (CIGAR walk, mapq-dropped reads that only count towards the visited loci / the
+    // multi-allelic filter) takes the general loop below.
+    const bool lean_mine = overlaps && keep_mine && (my.info & kLeanMask) == kInfoSimple;
+    uint32_t ov = __ballot_sync(0xFFFFFFFFu, lean_mine);
+    uint32_t ov_general = __ballot_sync(0xFFFFFFFFu, overlaps && !lean_mine);
+    // Every lane owns one read of the batch here: it forms the address its read's byte for locus 0 would have (so the
+    // per-read loop adds just the lane's locus), packs (span, mapq << 8) into one word and pulls the bytes this word's loci
+    // need into the cache now, so that the loop below does not serialise one memory round trip after another.
+    uint64_t my_qa = 0;
+    uint32_t my_lm = 0;
+    if (lean_mine) {
+      my_qa = (uint64_t)(uintptr_t)R.qc + R.seq_off[mine] + (uint64_t)(my.info & kInfoLeadMask) - (uint64_t)(int64_t)my.start;
+      my_lm = (uint32_t)(my.end - my.start) | ((my.info >> kInfoMapqShift) << 24);
+      const int x0 = max(span_lo, my.start);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(my_qa + (uint64_t)(int64_t)x0));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(my_qa + (uint64_t)(int64_t)min(span_lo + 31, my.end - 1)));
     }
-    while (ov) {  // warp-uniform, lean: SIMPLE read kept by the mapq filter
+    while (ov) {  // warp-uniform, lean
       const int j = __ffs(ov) - 1;
       ov &= ov - 1;
-      ReadRec rec;
-      rec.start = __shfl_sync(0xFFFFFFFFu, my.start, j);
-      rec.end = __shfl_sync(0xFFFFFFFFu, my.end, j);
-      rec.pair_off = __shfl_sync(0xFFFFFFFFu, my.pair_off, j);
-      rec.info = __shfl_sync(0xFFFFFFFFu, my.info, j);
-      const uint64_t seq_off = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(my_seq_off >> 32), j) << 32) |
-                               __shfl_sync(0xFFFFFFFFu, (uint32_t)my_seq_off, j);
-      const int idx = (int)(rec.info & kInfoLeadMask) + (x - rec.start);
-      if ((unsigned)(x - rec.start) >= (unsigned)(rec.end - rec.start)) continue;  // this lane's locus is outside the read
-      const uint2 pw = __ldg(&R.pairs[rec.pair_off + (idx >> 5)]);
-#if GUAC_SOM_EXP == 2
-      const int q = idx & 63;
-#else
-      const int q = (int)__ldg(&R.qual[seq_off + idx]);
-#endif
-      const int code = (int)((pw.x >> (idx & 31)) & 1u) | ((int)((pw.y >> (idx & 31)) & 1u) << 1);
-#if GUAC_SOM_EXP == 1
-      const double2 l = make_double2(1e-3 * q, 2e-3);
-#else
-      const double2 l = __ldg(&tab[TUMOR ? (int)((rec.info >> kInfoMapqShift) << 8) + q : q]);  // (log(s + s), log((1-s) + (1-s)))
-#endif
-      A.any += 1;
-#if GUAC_SOM_EXP == 3
-      A.any += __double2hiint(l.y) + __double2hiint(l.x);
-      cnt_packed += 1ull << (16 * code);
-      continue;
-#endif
+      const int start = __shfl_sync(0xFFFFFFFFu, my.start, j);
+      const uint32_t lm = __shfl_sync(0xFFFFFFFFu, my_lm, j);
+      const uint64_t qa = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(my_qa >> 32), j) << 32) |
+                          __shfl_sync(0xFFFFFFFFu, (uint32_t)my_qa, j);
+      if ((unsigned)(x - start) >= (lm & 0xFFFFu)) continue;  // this lane's locus is outside the read
+      const uint32_t b = __ldg(reinterpret_cast<const uint8_t*>((uintptr_t)(qa + (uint64_t)(int64_t)x)));
+      const double2 l = __ldg(&tab[TUMOR ? ((lm >> 16) & 0xFF00u) + (b & 63u) : (b & 63u)]);  // (log(s + s), log((1-s) + (1-s)))
       A.t0 += l.y;
-      cnt_packed += 1ull << (16 * code);
-      if (std_ref && code == rcode) {
+      if ((b >> 6) == rc_eff) {
         sr1 += l.x;
+        n_ref += 1;
       } else {
+        const int code = (int)(b >> 6);
+        cnt_packed += 1ull << (16 * code);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const bool is = code == k;
@@ -333,8 +496,19 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
       if (!keep && !fma) continue;
       Elem e;
       const int rc = classify(R, (uint64_t)(base + j), x, ref_base, e);
-      if (rc || !((e.kind == kMatch || e.kind == kMismatch) && is_std_base(e.base))) {
-        A.other += 1;  // insertion / deletion / clipped / non-ACGT element (or an error the exact kernel reports)
+      if (rc || e.kind == kNone) {  // an error the exact kernel reports
+        A.other += 1;
+        A.hard += 1;
+        continue;
+      }
+      if (!((e.kind == kMatch || e.kind == kMismatch) && is_std_base(e.base))) {
+        A.other += 1;  // insertion / deletion / clipped / non-ACGT element: which allele it carries is the exact kernel's job,
+        if (keep) {    // but its likelihood terms bound every genotype it can be part of (ref_leads_despite_others)
+          const double2 l = __ldg(&tab[TUMOR ? (mapq << 8) + (e.qual & 255) : (e.qual & 255)]);
+          A.o0 += l.y;
+          A.ohet += fmax(0.0, l.y);
+          A.ohom += fmax(l.x, l.y);
+        }
         continue;
       }
       const int code = (int)base_code(e.base);
@@ -342,10 +516,11 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
       if (!keep) continue;
       const double2 l = __ldg(&tab[TUMOR ? (mapq << 8) + (e.qual & 255) : (e.qual & 255)]);
       A.t0 += l.y;
-      cnt_packed += 1ull << (16 * code);
-      if (e.kind == kMatch) {
+      if ((uint32_t)code == rc_eff) {
         sr1 += l.x;
+        n_ref += 1;
       } else {
+        cnt_packed += 1ull << (16 * code);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const bool is = code == k;
@@ -357,13 +532,14 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    A.cnt[k] = (int)((cnt_packed >> (16 * k)) & 0xFFFFu);
+    A.cnt[k] = (int)((cnt_packed >> (16 * k)) & 0xFFFFu) + ((uint32_t)k == rc_eff ? n_ref : 0);
     A.depth += A.cnt[k];
   }
+  A.any += A.depth;  // (only any > 0 matters: the lean loop's elements all count towards the depth)
   A.ref_depth = std_ref ? A.cnt[rcode] : 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) A.seen |= A.cnt[k] > 0 ? (1u << k) : 0u;
-  if (A.depth > 0xFFFF || cnt_packed == ~0ull) A.other += 1;  // (cannot happen below 65,536 reads; the exact kernel decides then)
+  if (last - first > 0xFFFFu) A.other += 1;  // the packed counters hold 16 bits: deeper granules go to the exact kernel
   // S0 of the reference class = T0 - the other classes' S0 (every kept plain element is in exactly one class)
   double sr0 = A.t0;
 #pragma unroll
@@ -375,25 +551,6 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
     A.s1[k] += is ? sr1 : 0.0;
     A.s0[k] += is ? sr0 : 0.0;
   }
-}
-
-__device__ inline int lane_table(const LaneAcc& A, int rcode, SomAllele* tab, SampleStats& st) {
-  // SNV alleles share the reference base, so Allele.compare order is base-code order
-  int n = 0;
-  (void)rcode;
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (A.cnt[k] > 0) {
-      tab[n].kind = 0; tab[n].len = 1; tab[n].ptr = 0; tab[n].base = code_base(k); tab[n].count = A.cnt[k];
-      tab[n].s1 = A.s1[k]; tab[n].s0 = A.s0[k];
-      ++n;
-    }
-  st.depth = A.depth;
-  st.ref_depth = A.ref_depth;
-  st.n_alleles = n;
-  st.distinct_unfiltered = __popc(A.seen);
-  st.t0 = A.t0;
-  return n;
 }
 
 constexpr int kSomThreads = 256;
@@ -420,21 +577,21 @@ __global__ void __launch_bounds__(kSomThreads) k_somatic(DevReads RT, DevReads R
     // The reference looks at the normal sample only where the tumor's most likely genotype holds a variant allele: decide
     // the tumor half per lane first and walk the normal reads of this word only if some lane still needs them.
     const int covT = AT.depth + AT.other;  // (filtered when no multi-allelic filter is on)
-    const bool tumor_exact = AT.other > 0 || !stdT || prm.filter_multi_allelic;
+    bool tumor_exact = AT.hard > 0 || !stdT || prm.filter_multi_allelic;
     const bool tumor_all_match = AT.ref_depth == AT.depth && AT.other == 0 && stdT && !prm.filter_multi_allelic;
     bool need_normal = false, variant = false;
-    AlleleEntry a1, a2;
+    int c1 = 0, c2 = 0;
     double tumor_l = 0.0;
     AlleleView avT{RT, code_base(rcT)};
     if (in_req) {
       if (AT.any == 0) need_normal = true;  // visited iff the normal sample has reads here
       else if (covT > 0 && !tumor_all_match) {
+        if (!tumor_exact && AT.other > 0) tumor_exact = !ref_leads_despite_others(AT, rcT);
         if (tumor_exact) need_normal = true;
-        else {
-          SomAllele tabT[4];
-          SampleStats sT;
-          lane_table(AT, rcT, tabT, sT);
-          variant = tumor_most_likely(avT, tabT, sT, td.contig, x, prm, out, &a1, &a2, &tumor_l);
+        else if (AT.other == 0) {
+          SnvAlleles sT;
+          snv_compact(AT, sT);
+          variant = snv_tumor_most_likely(sT, AT.ref_depth, rcT, prm, &c1, &c2, &tumor_l);
           need_normal = variant;
         }
       }
@@ -455,11 +612,11 @@ __global__ void __launch_bounds__(kSomThreads) k_somatic(DevReads RT, DevReads R
       if (s < out.cap_slow) out.slow[s] = SlowLocus{td.contig, x};
       continue;
     }
-    SomAllele tabN[4];
-    SampleStats sN;
-    lane_table(AN, rcN, tabN, sN);
-    AlleleView avN{RN, code_base(rcN)};
-    somatic_against_normal(avT, avN, a1, a2, tumor_l, tabN, sN, td.contig, x, prm, out);
+    if (AN.depth == 0 || AN.depth > prm.max_read_depth) continue;
+    SnvAlleles sN;
+    snv_compact(AN, sN);
+    const double normal_variants_total = snv_normal_variants_total(sN, rcN);
+    emit_somatic(avT, snv_entry(c1, 0), snv_entry(c2, 0), tumor_l, normal_variants_total, td.contig, x, prm, out);
   }
   for (int o = 16; o; o >>= 1) n_visited += __shfl_xor_sync(0xFFFFFFFFu, n_visited, o);
   if (lane == 0 && n_visited) atomicAdd(&out.counters[3], (unsigned long long)n_visited);
