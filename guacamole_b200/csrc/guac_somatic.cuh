@@ -70,6 +70,7 @@ struct SomAllele {
   uint64_t ptr;
   uint8_t base;
   int count;
+  int n0inf;     // elements whose l0 = log((1-s) + (1-s)) is -inf (s == 1: a deletion element of a mapq-255 read), kept out of s0
   double s1, s0;
 };
 
@@ -78,6 +79,7 @@ struct SampleStats {
   int ref_depth;  // Match elements among them
   int n_alleles;  // entries in tab (all distinct alleles of the filtered pileup)
   int distinct_unfiltered;  // distinct alleles before the mapq filter (multi-allelic filter), capped
+  int t0inf;                // elements with l0 = -inf, kept out of t0 (T0 - S0[a] must not become inf - inf)
   double t0;
 };
 
@@ -108,7 +110,10 @@ __device__ int genotype_likelihoods(const AlleleView& av, const SomAllele* tab, 
     for (int j = i; j < n; ++j) {
       const SomAllele& a = tab[idx[i]];
       const SomAllele& b = tab[idx[j]];
-      const double agg = (i == j) ? (a.s1 + (st.t0 - a.s0)) : (st.t0 - a.s0 - b.s0);
+      // sum over the elements outside the genotype's alleles of l0: -inf as soon as one of them has l0 = -inf
+      const int outside_inf = st.t0inf - a.n0inf - (i == j ? 0 : b.n0inf);
+      const double outside = outside_inf > 0 ? -1.0 / 0.0 : ((i == j) ? (st.t0 - a.s0) : (st.t0 - a.s0 - b.s0));
+      const double agg = (i == j) ? (a.s1 + outside) : outside;
       gi[ng] = idx[i];
       gj[ng] = idx[j];
       lk[ng] = agg + 0.0 - nlog2;
@@ -639,7 +644,7 @@ __device__ bool exact_sample(const DevReads& R, int contig, int locus, const Som
   *ref_base_out = ref_base;
   AlleleView av{R, ref_base};
   int na = 0, n_unf = 0;  // table entries; entries [0, na) carry filtered sums, distinct_unfiltered counts all alleles seen
-  int depth = 0, ref_depth = 0;
+  int depth = 0, ref_depth = 0, t0inf = 0;
   double t0 = 0.0, s1c[4] = {0, 0, 0, 0}, s0c[4] = {0, 0, 0, 0};
   int cntc[4] = {0, 0, 0, 0};
   uint32_t seen = 0;
@@ -678,7 +683,8 @@ __device__ bool exact_sample(const DevReads& R, int contig, int locus, const Som
       l0 = l.y;
       depth += 1;
       ref_depth += e.kind == kMatch ? 1 : 0;
-      t0 += l0;
+      if (l0 == -1.0 / 0.0) t0inf += 1;
+      else t0 += l0;
     }
     if (snv) {
       const int code = (int)base_code(e.base);
@@ -715,11 +721,17 @@ __device__ bool exact_sample(const DevReads& R, int contig, int locus, const Som
           else {
             found = na;
             tab[na].kind = (s.kind == kMatch || s.kind == kMismatch) ? 0 : s.kind;
-            tab[na].len = s.len; tab[na].ptr = s.ptr; tab[na].base = s.base; tab[na].count = 0; tab[na].s1 = 0.0; tab[na].s0 = 0.0;
+            tab[na].len = s.len; tab[na].ptr = s.ptr; tab[na].base = s.base; tab[na].count = 0; tab[na].n0inf = 0;
+            tab[na].s1 = 0.0; tab[na].s0 = 0.0;
             status = 1;
           }
         }
-        if (status != 2 && s_keep) { tab[found].count += 1; tab[found].s1 += sl1; tab[found].s0 += sl0; }
+        if (status != 2 && s_keep) {
+          tab[found].count += 1;
+          tab[found].s1 += sl1;
+          if (sl0 == -1.0 / 0.0) tab[found].n0inf += 1;
+          else tab[found].s0 += sl0;
+        }
       }
       status = __shfl_sync(0xFFFFFFFFu, status, 0);
       if (status == 2) {
@@ -733,6 +745,7 @@ __device__ bool exact_sample(const DevReads& R, int contig, int locus, const Som
   for (int o = 16; o; o >>= 1) {
     depth += __shfl_xor_sync(0xFFFFFFFFu, depth, o);
     ref_depth += __shfl_xor_sync(0xFFFFFFFFu, ref_depth, o);
+    t0inf += __shfl_xor_sync(0xFFFFFFFFu, t0inf, o);
     t0 += __shfl_xor_sync(0xFFFFFFFFu, t0, o);
     seen |= __shfl_xor_sync(0xFFFFFFFFu, seen, o);
 #pragma unroll
@@ -753,6 +766,7 @@ __device__ bool exact_sample(const DevReads& R, int contig, int locus, const Som
       if (cntc[k] > 0) {
         if (na == kSomTab) { ok = false; break; }
         tab[na].kind = 0; tab[na].len = 1; tab[na].ptr = 0; tab[na].base = code_base(k); tab[na].count = cntc[k];
+        tab[na].n0inf = 0;  // (an A/C/G/T element's quality is a base quality <= 127: s < 1)
         tab[na].s1 = s1c[k]; tab[na].s0 = s0c[k];
         ++na;
       }
@@ -764,6 +778,7 @@ __device__ bool exact_sample(const DevReads& R, int contig, int locus, const Som
   st.ref_depth = ref_depth;
   st.n_alleles = __shfl_sync(0xFFFFFFFFu, na, 0);
   st.distinct_unfiltered = n_unf + __popc(seen);
+  st.t0inf = t0inf;
   st.t0 = t0;
   __syncwarp();
   return ok;
