@@ -29,6 +29,13 @@ namespace guac {
 
 constexpr int kSomMaxAlleles = 10;                                           // alleles entering the genotype enumeration
 constexpr int kSomMaxGenotypes = kSomMaxAlleles * (kSomMaxAlleles + 1) / 2;
+#ifndef GUAC_LEAN_UNROLL
+#define GUAC_LEAN_UNROLL 3
+#endif
+#ifndef GUAC_SOM_MINB
+#define GUAC_SOM_MINB 3
+#endif
+constexpr int kLeanUnroll = GUAC_LEAN_UNROLL;                                               // reads whose element loads fly together
 constexpr int kSomTab = 24;                                                  // distinct alleles kept per sample and locus
 
 // d_tables layout (doubles): succ[256] | normal (l1, l0)[256] | tumor (l1, l0)[256 mapq][256 quality] — pairs are read as double2
@@ -465,28 +472,47 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
       asm volatile("prefetch.global.L1 [%0];" ::"l"(my_qa + (uint64_t)(int64_t)x0));
       asm volatile("prefetch.global.L1 [%0];" ::"l"(my_qa + (uint64_t)(int64_t)min(span_lo + 31, my.end - 1)));
     }
-    while (ov) {  // warp-uniform, lean
-      const int j = __ffs(ov) - 1;
-      ov &= ov - 1;
-      const int start = __shfl_sync(0xFFFFFFFFu, my.start, j);
-      const uint32_t lm = __shfl_sync(0xFFFFFFFFu, my_lm, j);
-      const uint64_t qa = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(my_qa >> 32), j) << 32) |
-                          __shfl_sync(0xFFFFFFFFu, (uint32_t)my_qa, j);
-      if ((unsigned)(x - start) >= (lm & 0xFFFFu)) continue;  // this lane's locus is outside the read
-      const uint32_t b = __ldg(reinterpret_cast<const uint8_t*>((uintptr_t)(qa + (uint64_t)(int64_t)x)));
-      const double2 l = __ldg(&tab[TUMOR ? ((lm >> 16) & 0xFF00u) + (b & 63u) : (b & 63u)]);  // (log(s + s), log((1-s) + (1-s)))
-      A.t0 += l.y;
-      if ((b >> 6) == rc_eff) {
-        sr1 += l.x;
-        n_ref += 1;
-      } else {
-        const int code = (int)(b >> 6);
-        cnt_packed += 1ull << (16 * code);
+    while (ov) {  // warp-uniform, lean: kLeanUnroll reads per round, so that their element loads are in flight together
+      bool inr[kLeanUnroll];
+      uint64_t ea[kLeanUnroll];
+      uint32_t lmu[kLeanUnroll];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const bool is = code == k;
-          A.s1[k] += is ? l.x : 0.0;
-          A.s0[k] += is ? l.y : 0.0;
+      for (int u = 0; u < kLeanUnroll; ++u) {
+        const bool act = ov != 0;
+        const int j = __ffs(ov) - 1;  // (-1 once the batch is exhausted: the shuffles then read lane 31, unused)
+        ov &= ov - 1;
+        const int start = __shfl_sync(0xFFFFFFFFu, my.start, j);
+        lmu[u] = __shfl_sync(0xFFFFFFFFu, my_lm, j);
+        const uint64_t qa = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(my_qa >> 32), j) << 32) |
+                            __shfl_sync(0xFFFFFFFFu, (uint32_t)my_qa, j);
+        inr[u] = act && (unsigned)(x - start) < (lmu[u] & 0xFFFFu);  // is this lane's locus inside the read?
+        ea[u] = qa + (uint64_t)(int64_t)x;
+      }
+      uint32_t bq[kLeanUnroll];
+#pragma unroll
+      for (int u = 0; u < kLeanUnroll; ++u) bq[u] = inr[u] ? (uint32_t)__ldg(reinterpret_cast<const uint8_t*>((uintptr_t)ea[u])) : 0u;
+      double2 lq[kLeanUnroll];
+#pragma unroll
+      for (int u = 0; u < kLeanUnroll; ++u)  // (log(s + s), log((1-s) + (1-s)))
+        lq[u] = inr[u] ? __ldg(&tab[TUMOR ? ((lmu[u] >> 16) & 0xFF00u) + (bq[u] & 63u) : (bq[u] & 63u)]) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < kLeanUnroll; ++u) {  // accumulate in read order
+        if (!inr[u]) continue;
+        const double2 l = lq[u];
+        const uint32_t b = bq[u];
+        A.t0 += l.y;
+        if ((b >> 6) == rc_eff) {
+          sr1 += l.x;
+          n_ref += 1;
+        } else {
+          const int code = (int)(b >> 6);
+          cnt_packed += 1ull << (16 * code);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool is = code == k;
+            A.s1[k] += is ? l.x : 0.0;
+            A.s0[k] += is ? l.y : 0.0;
+          }
         }
       }
     }
@@ -560,7 +586,7 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
 
 constexpr int kSomThreads = 256;
 
-__global__ void __launch_bounds__(kSomThreads) k_somatic(DevReads RT, DevReads RN, const TileDesc* __restrict__ tiles, SomParams prm,
+__global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads RT, DevReads RN, const TileDesc* __restrict__ tiles, SomParams prm,
                                                         const double* __restrict__ tables, int max_span_t, int max_span_n, SomOut out) {
   const TileDesc td = tiles[blockIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
