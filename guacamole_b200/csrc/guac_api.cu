@@ -211,6 +211,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   out.pairs.alloc(pair_total + 8);
   out.xmask.alloc(pair_total + 8);
   out.nm.alloc(n);
+  out.mm.alloc(n + 1);
   if (out.has_qualities) out.qc.alloc((n ? (size_t)b->seq_off[n] : 0) + 64);
   CUDA_OK(cudaMemsetAsync(out.pairs.p, 0, out.pairs.bytes(), st));
   CUDA_OK(cudaMemsetAsync(out.xmask.p, 0, out.xmask.bytes(), st));
@@ -243,6 +244,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   A.rec_w = out.rec.p;
   A.pairs_w = out.pairs.p;
   A.xmask_w = out.xmask.p;
+  A.mm_w = out.mm.p;
   A.qc_w = out.has_qualities ? out.qc.p : nullptr;
   A.nm_w = out.nm.p;
   A.md_w = out.md.p;
@@ -273,6 +275,10 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   }
   if (ref) {
     k_fasta_track<<<grid_for(word_off, 256, ctx->sm_count), 256, 0, st>>>(A, b->n_contigs);
+    out.pack_launches += 1;
+  }
+  if (n) {  // the track is final: SIMPLE reads as differences against it
+    k_mismatch_lists<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(A);
     out.pack_launches += 1;
   }
   CUDA_OK(cudaEventRecord(ctx->ev[1], st));

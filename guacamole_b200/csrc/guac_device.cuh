@@ -4,6 +4,8 @@
 //   rec[n+1]      16 B/read   {start, end, pair_off, info}   contig-relative 0-based [start, end)   (MappedRead.start/end)
 //   pairs[]       8 B/32 bases  bit-plane pairs (lo, hi) of the 2-bit read bases, read coordinates, 32 bases per pair
 //   xmask[]       4 B/32 bases  1 = base is not A/C/G/T (read only for reads flagged HAS_EXC)
+//   mm[n]         16 B/read   SIMPLE reads as differences against the reference track (reference-based encoding, like CRAM):
+//                             up to 8 (offset, base) pairs; the germline tile kernel reads rec + mm and never the planes
 //   cig_off/cigar BAM-encoded run-length CIGAR ops (read only for reads that are not SIMPLE)
 //   seq/qual      raw bytes (the exact per-locus paths read them)
 //   qc[]          1 B/base   quality (6 bits) | base code << 6: the one byte per pileup element the likelihood kernel loads
@@ -34,7 +36,10 @@ constexpr uint32_t kInfoHasExc = 1u << 17;      // read holds a non-ACGT base
 constexpr uint32_t kInfoPositive = 1u << 18;    // isPositiveStrand
 constexpr uint32_t kInfoEmpty = 1u << 19;       // consumes no reference (overlaps nothing)
 constexpr uint32_t kInfoWideQ = 1u << 20;       // read holds a base quality > 63 (its qc bytes are not usable)
+constexpr uint32_t kInfoMmList = 1u << 21;      // mm[] holds the read's differences against the reference track
 constexpr int kInfoMapqShift = 24;
+constexpr int kMmSlots = 8;                     // differences kept per read (more: the read takes the general path)
+constexpr int kMmMaxSpan = 16383;               // offsets are 14 bits
 
 struct __align__(16) ReadRec {
   int32_t start;
@@ -60,6 +65,7 @@ struct DevReads {
   const uint32_t* cigar;
   const uint2* pairs;
   const uint32_t* xmask;
+  const uint4* mm;            // per read: up to 8 x u16 (reference offset << 2 | read base code), 0xFFFF = unused
   const uint64_t* seq_off;
   const uint8_t* seq;
   const uint8_t* qual;

@@ -330,6 +330,7 @@ struct guac_reads {
   DevBuf<ReadRec> rec;
   DevBuf<uint32_t> cig_off, cigar, xmask, md_off, trk_lo, trk_hi, trk_std, gran_first, gran_last;
   DevBuf<uint2> pairs;
+  DevBuf<uint4> mm;
   DevBuf<uint64_t> seq_off, fasta_off;
   DevBuf<uint8_t> seq, qual, qc, fasta;
   DevBuf<char> md;
@@ -352,6 +353,7 @@ struct guac_reads {
     R.cigar = cigar.p;
     R.pairs = pairs.p;
     R.xmask = xmask.p;
+    R.mm = mm.p;
     R.seq_off = seq_off.p;
     R.seq = seq.p;
     R.qual = qual.p;
@@ -371,7 +373,7 @@ struct guac_reads {
   }
   uint64_t device_bytes() const {
     return rec.bytes() + cig_off.bytes() + cigar.bytes() + xmask.bytes() + md_off.bytes() + trk_lo.bytes() * 3 +
-           gran_first.bytes() * 2 + pairs.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + qc.bytes() + md.bytes() + nm.bytes() +
+           gran_first.bytes() * 2 + pairs.bytes() + mm.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + qc.bytes() + md.bytes() + nm.bytes() +
            fasta.bytes();
   }
 };

@@ -15,6 +15,7 @@ struct PackArgs {
   ReadRec* rec_w;        // writable aliases
   uint2* pairs_w;
   uint32_t* xmask_w;
+  uint4* mm_w;
   uint8_t* qc_w;         // (quality | base code << 6) per base, nullptr when qualities are not packed
   uint16_t* nm_w;
   char* md_w;
@@ -126,6 +127,46 @@ __global__ void __launch_bounds__(256) k_pack_bases(PackArgs A) {
       }
     }
     __syncthreads();  // the stage buffers are reused by the next block of reads
+  }
+}
+
+// ---- K_mismatch_lists: thread per read; a SIMPLE read of plain A/C/G/T bases as its differences against the final track ------
+// Runs after the reference track is complete (MD-derived and conflict-resolved, or FASTA-derived), so the lists agree
+// with the track by construction, order-sensitive loci included.  Loci whose track base is not A/C/G/T are left out: the
+// callers hand those to the exact per-locus path whatever the counters say.
+__global__ void __launch_bounds__(256) k_mismatch_lists(PackArgs A) {
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < A.R.n; r += (uint64_t)gridDim.x * blockDim.x) {
+    const ReadRec rec = A.R.rec[r];
+    unsigned long long e_lo = ~0ull, e_hi = ~0ull;
+    bool ok = (rec.info & (kInfoSimple | kInfoHasExc | kInfoEmpty)) == kInfoSimple && rec.end > rec.start &&
+              rec.end - rec.start <= kMmMaxSpan;
+    if (ok) {
+      const ContigInfo ci = A.R.contigs[A.read_contig[r]];
+      const uint2* __restrict__ P = A.R.pairs + rec.pair_off;
+      const int w0 = rec.start >> 5, w1 = (rec.end - 1) >> 5;
+      int q0 = (int)(rec.info & kInfoLeadMask) + ((w0 << 5) - rec.start);  // read base under bit 0 of word w0 (> -32)
+      int n = 0;
+      for (int w = w0; w <= w1 && ok; ++w, q0 += 32) {
+        const int j = q0 >> 5, sh = q0 & 31;  // arithmetic shift: floor
+        const uint2 pa = j >= 0 ? P[j] : make_uint2(0u, 0u), pb = P[j + 1];
+        const uint32_t lo = __funnelshift_r(pa.x, pb.x, sh), hi = __funnelshift_r(pa.y, pb.y, sh);
+        const uint32_t valid = bit_range(rec.start - (w << 5), rec.end - (w << 5)) & A.R.trk_std[ci.word_off + w];
+        uint32_t d = ((lo ^ A.R.trk_lo[ci.word_off + w]) | (hi ^ A.R.trk_hi[ci.word_off + w])) & valid;
+        while (d) {
+          const int b = __ffs(d) - 1;
+          d &= d - 1;
+          if (n == kMmSlots) { ok = false; break; }
+          const unsigned long long e = ((unsigned long long)((w << 5) + b - rec.start) << 2) | ((lo >> b) & 1u) | (((hi >> b) & 1u) << 1);
+          const int sft = 16 * (n & 3);
+          if (n < 4) e_lo = (e_lo & ~(0xFFFFull << sft)) | (e << sft);
+          else e_hi = (e_hi & ~(0xFFFFull << sft)) | (e << sft);
+          ++n;
+        }
+      }
+    }
+    if (!ok) e_lo = e_hi = ~0ull;
+    A.mm_w[r] = make_uint4((uint32_t)e_lo, (uint32_t)(e_lo >> 32), (uint32_t)e_hi, (uint32_t)(e_hi >> 32));
+    if (ok) A.rec_w[r].info = rec.info | kInfoMmList;
   }
 }
 

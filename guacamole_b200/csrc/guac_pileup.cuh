@@ -311,17 +311,19 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     }
   };
 
-  // ---- phase 1a: one read per lane; SIMPLE reads take the fast path, the others are listed for phase 1b.  The records
-  // of the next batch are fetched before the current one is worked on.
+  // ---- phase 1a: one read per lane.  A SIMPLE read of plain A/C/G/T bases is stored as its differences against the reference
+  // track (mm[], built at pack time): it costs two depth updates plus one shared-memory atomic per differing base.  The
+  // others are listed for phase 1b.  The records of the next batch are fetched before the current one is worked on.
   ReadRec rec_next{0, 0, 0, 0};
-  if (first + lane < last) rec_next = R.rec[first + lane];
+  uint4 mm_next = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  if (first + lane < last) { rec_next = R.rec[first + lane]; mm_next = __ldg(&R.mm[first + lane]); }
   for (uint32_t base = first; base < last; base += 32) {  // warp-uniform
     const uint32_t r = base + lane;
     const ReadRec rec = rec_next;
+    const uint4 mm = mm_next;
     rec_next = ReadRec{0, 0, 0, 0};
-    if (r + 32 < last) rec_next = R.rec[r + 32];
+    if (r + 32 < last) { rec_next = R.rec[r + 32]; mm_next = __ldg(&R.mm[r + 32]); }
     const bool active = r < last && rec.end > tile_lo && rec.start < tile_hi && rec.end > rec.start;
-    int w0 = 0, w1 = -1;
     if (active) {
       const int s = max(rec.start, tile_lo) - tile_lo, e = min(rec.end, tile_hi) - tile_lo;
       S.cov.start(s);
@@ -330,68 +332,39 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
         S.pos.start(s);
         S.pos.end(e);
       }
-      w0 = s >> 5;
-      w1 = (e - 1) >> 5;
     }
-    const bool fast = active && (rec.info & (kInfoSimple | kInfoHasExc)) == kInfoSimple;
+    const bool fast = active && (rec.info & kInfoMmList) != 0;
     bool slow_now = false;
     if (active && !fast) {
       const uint32_t slot = atomicAdd(&S.n_list, 1u);
       if (slot < (uint32_t)kListCap) S.list[slot] = r; else slow_now = true;
     }
-    // fast path: the read's planes slide over the reference words; one 64-bit load, two funnel shifts per word
-    const int q0 = (int)(rec.info & kInfoLeadMask) + (tile_lo + (w0 << 5) - rec.start);  // read base under bit 0 of word w0
-    const int sh = q0 & 31;
-    const uint2* __restrict__ P = R.pairs + rec.pair_off + (q0 >> 5);  // P[0] may sit one pair before the read (never loaded then)
-    // all pair loads of a short read are issued up front (memory-level parallelism); longer reads roll on from there
-    constexpr int kPre = 7;
-    uint2 pre[kPre];
-#pragma unroll
-    for (int k = 0; k < kPre; ++k) pre[k] = make_uint2(0u, 0u);
-    const int n_pairs_needed = fast ? (w1 - w0 + 2) : 0;  // pairs P[0 .. w1 - w0 + 1]
+    // entries are (reference offset << 2 | read base code), ascending, unused slots 0xFFFF
+    const uint32_t mmw[4] = {mm.x, mm.y, mm.z, mm.w};
+    int n_mine = 0;
     if (fast) {
 #pragma unroll
-      for (int k = 0; k < kPre; ++k)
-        if (k < n_pairs_needed && (k > 0 || q0 >= 0)) pre[k] = __ldg(P + k);
+      for (int k = 0; k < 4; ++k) n_mine += ((mmw[k] & 0xFFFFu) != 0xFFFFu ? 1 : 0) + ((mmw[k] >> 16) != 0xFFFFu ? 1 : 0);
     }
-    // bits of the first / last word that belong to the read
-    const uint32_t first_mask = bit_range(rec.start - (tile_lo + (w0 << 5)), 32);
-    const uint32_t last_mask = bit_range(0, rec.end - (tile_lo + (w1 << 5)));
-    const int nw = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)(fast ? w1 - w0 + 1 : 0));
-    const uint32_t* ref_lo = S.ref_lo + w0;
-    CntT* cnt_word = S.cnt + (w0 << 5);
-    if (nw <= kPre - 1) {
+    const int n_max = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)n_mine);
+    const int rel = rec.start - tile_lo;
 #pragma unroll
-      for (int k = 0; k < kPre - 1; ++k) {
-        if (k < nw) {  // warp-uniform
-          uint32_t x = 0, y = 0;
-          if (fast && w0 + k <= w1) {
-            uint32_t valid = k == 0 ? first_mask : 0xFFFFFFFFu;
-            if (w0 + k == w1) valid &= last_mask;
-            x = (__funnelshift_r(pre[k].x, pre[k + 1].x, sh) ^ ref_lo[k]) & valid;
-            y = (__funnelshift_r(pre[k].y, pre[k + 1].y, sh) ^ ref_lo[k + kWarpWords]) & valid;  // ref_hi follows ref_lo
+    for (int k = 0; k < kMmSlots; ++k) {
+      if (k < n_max) {  // warp-uniform
+        const uint32_t e = (mmw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+        const int x = rel + (int)(e >> 2);
+        if (k < n_mine && (unsigned)x < (unsigned)kWarpLoci) {
+          const int w = x >> 5, bb = x & 31;
+          const uint32_t rcode = ((S.ref_lo[w] >> bb) & 1u) | (((S.ref_hi[w] >> bb) & 1u) << 1);
+          const int cls = (int)((e & 3u) ^ rcode);
+          if (cls) {
+            if constexpr (sizeof(CntT) == 8) atomicAdd(reinterpret_cast<unsigned long long*>(S.cnt + x), 1ull << (FB * cls));
+            else atomicAdd(S.cnt + x, (CntT)1 << (FB * cls));
           }
-          count_bits<CntT>(cnt_word + (k << 5), x | y, x, y);
         }
-      }
-    } else {  // long reads: rolling window of two pairs
-      uint2 pa = pre[0], pb = pre[1];
-      const uint2* __restrict__ Q = P + 2;
-      for (int k = 0; k < nw; ++k) {
-        const int w = w0 + k;
-        uint32_t x = 0, y = 0;
-        if (fast && w <= w1) {
-          uint32_t valid = k == 0 ? first_mask : 0xFFFFFFFFu;
-          if (w == w1) valid &= last_mask;
-          x = (__funnelshift_r(pa.x, pb.x, sh) ^ ref_lo[k]) & valid;
-          y = (__funnelshift_r(pa.y, pb.y, sh) ^ ref_lo[k + kWarpWords]) & valid;
-          pa = pb;
-          if (w < w1) pb = __ldg(Q);
-          ++Q;
-        }
-        count_bits<CntT>(cnt_word + (k << 5), x | y, x, y);
       }
     }
+    __syncwarp();
     if (__any_sync(0xFFFFFFFFu, slow_now)) general_read(r, rec, slow_now);  // list overflow (very deep granules)
     __syncwarp();
   }
