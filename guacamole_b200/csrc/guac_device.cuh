@@ -65,7 +65,7 @@ struct DevReads {
   const uint32_t* cigar;
   const uint2* pairs;
   const uint32_t* xmask;
-  const uint4* mm;            // per read: up to 8 x u16 (reference offset << 2 | read base code), 0xFFFF = unused
+  const uint4* mm;            // per read: up to 8 x u16 (reference offset << 2 | class), 0 = unused; class = base ^ reference base
   const uint64_t* seq_off;
   const uint8_t* seq;
   const uint8_t* qual;

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) k_pack_bases(PackArgs A) {
 __global__ void __launch_bounds__(256) k_mismatch_lists(PackArgs A) {
   for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < A.R.n; r += (uint64_t)gridDim.x * blockDim.x) {
     const ReadRec rec = A.R.rec[r];
-    unsigned long long e_lo = ~0ull, e_hi = ~0ull;
+    unsigned long long e_lo = 0ull, e_hi = 0ull;
     bool ok = (rec.info & (kInfoSimple | kInfoHasExc | kInfoEmpty)) == kInfoSimple && rec.end > rec.start &&
               rec.end - rec.start <= kMmMaxSpan;
     if (ok) {
@@ -151,20 +151,22 @@ __global__ void __launch_bounds__(256) k_mismatch_lists(PackArgs A) {
         const uint2 pa = j >= 0 ? P[j] : make_uint2(0u, 0u), pb = P[j + 1];
         const uint32_t lo = __funnelshift_r(pa.x, pb.x, sh), hi = __funnelshift_r(pa.y, pb.y, sh);
         const uint32_t valid = bit_range(rec.start - (w << 5), rec.end - (w << 5)) & A.R.trk_std[ci.word_off + w];
-        uint32_t d = ((lo ^ A.R.trk_lo[ci.word_off + w]) | (hi ^ A.R.trk_hi[ci.word_off + w])) & valid;
+        const uint32_t x = (lo ^ A.R.trk_lo[ci.word_off + w]) & valid, y = (hi ^ A.R.trk_hi[ci.word_off + w]) & valid;
+        uint32_t d = x | y;
         while (d) {
           const int b = __ffs(d) - 1;
           d &= d - 1;
           if (n == kMmSlots) { ok = false; break; }
-          const unsigned long long e = ((unsigned long long)((w << 5) + b - rec.start) << 2) | ((lo >> b) & 1u) | (((hi >> b) & 1u) << 1);
+          // (offset << 2 | class), class = read base code ^ reference base code, never 0 here: an entry is never 0
+          const unsigned long long e = ((unsigned long long)((w << 5) + b - rec.start) << 2) | ((x >> b) & 1u) | (((y >> b) & 1u) << 1);
           const int sft = 16 * (n & 3);
-          if (n < 4) e_lo = (e_lo & ~(0xFFFFull << sft)) | (e << sft);
-          else e_hi = (e_hi & ~(0xFFFFull << sft)) | (e << sft);
+          if (n < 4) e_lo |= e << sft;
+          else e_hi |= e << sft;
           ++n;
         }
       }
     }
-    if (!ok) e_lo = e_hi = ~0ull;
+    if (!ok) e_lo = e_hi = 0ull;
     A.mm_w[r] = make_uint4((uint32_t)e_lo, (uint32_t)(e_lo >> 32), (uint32_t)e_hi, (uint32_t)(e_hi >> 32));
     if (ok) A.rec_w[r].info = rec.info | kInfoMmList;
   }

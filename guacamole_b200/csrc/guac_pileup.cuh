@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
   // track (mm[], built at pack time): it costs two depth updates plus one shared-memory atomic per differing base.  The
   // others are listed for phase 1b.  The records of the next batch are fetched before the current one is worked on.
   ReadRec rec_next{0, 0, 0, 0};
-  uint4 mm_next = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  uint4 mm_next = make_uint4(0u, 0u, 0u, 0u);
   if (first + lane < last) { rec_next = R.rec[first + lane]; mm_next = __ldg(&R.mm[first + lane]); }
   for (uint32_t base = first; base < last; base += 32) {  // warp-uniform
     const uint32_t r = base + lane;
@@ -339,29 +339,18 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
       const uint32_t slot = atomicAdd(&S.n_list, 1u);
       if (slot < (uint32_t)kListCap) S.list[slot] = r; else slow_now = true;
     }
-    // entries are (reference offset << 2 | read base code), ascending, unused slots 0xFFFF
-    const uint32_t mmw[4] = {mm.x, mm.y, mm.z, mm.w};
-    int n_mine = 0;
-    if (fast) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) n_mine += ((mmw[k] & 0xFFFFu) != 0xFFFFu ? 1 : 0) + ((mmw[k] >> 16) != 0xFFFFu ? 1 : 0);
-    }
-    const int n_max = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)n_mine);
+    // entries are (reference offset << 2 | class), ascending, class = read base code ^ reference base code (1..3) = the
+    // counter field; unused slots 0.  A slot no lane uses ends the walk (the lists are filled from slot 0).
+    const uint32_t mmw[4] = {fast ? mm.x : 0u, fast ? mm.y : 0u, fast ? mm.z : 0u, fast ? mm.w : 0u};
     const int rel = rec.start - tile_lo;
 #pragma unroll
     for (int k = 0; k < kMmSlots; ++k) {
-      if (k < n_max) {  // warp-uniform
-        const uint32_t e = (mmw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-        const int x = rel + (int)(e >> 2);
-        if (k < n_mine && (unsigned)x < (unsigned)kWarpLoci) {
-          const int w = x >> 5, bb = x & 31;
-          const uint32_t rcode = ((S.ref_lo[w] >> bb) & 1u) | (((S.ref_hi[w] >> bb) & 1u) << 1);
-          const int cls = (int)((e & 3u) ^ rcode);
-          if (cls) {
-            if constexpr (sizeof(CntT) == 8) atomicAdd(reinterpret_cast<unsigned long long*>(S.cnt + x), 1ull << (FB * cls));
-            else atomicAdd(S.cnt + x, (CntT)1 << (FB * cls));
-          }
-        }
+      const uint32_t e = (k & 1) ? (mmw[k >> 1] >> 16) : (mmw[k >> 1] & 0xFFFFu);
+      if (!__any_sync(0xFFFFFFFFu, e != 0u)) break;  // warp-uniform
+      const int x = rel + (int)(e >> 2);
+      if (e != 0u && (unsigned)x < (unsigned)kWarpLoci) {
+        if constexpr (sizeof(CntT) == 8) atomicAdd(reinterpret_cast<unsigned long long*>(S.cnt + x), 1ull << (FB * (e & 3u)));
+        else atomicAdd(S.cnt + x, (CntT)1 << (FB * (e & 3u)));
       }
     }
     __syncwarp();
