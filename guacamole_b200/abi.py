@@ -127,6 +127,7 @@ class StatsC(C.Structure):
 OPT_SORT_RECORDS = 1
 OPT_PACK_QUALITIES = 2
 OPT_HOST_THREADS = 3
+OPT_DIFFERENCE_LISTS = 4
 
 
 def struct_to_dict(s):

@@ -212,6 +212,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   out.xmask.alloc(pair_total + 8);
   out.nm.alloc(n);
   out.mm.alloc(n + 1);
+  if (!ctx->difference_lists) CUDA_OK(cudaMemsetAsync(out.mm.p, 0xFF, out.mm.bytes(), ctx->stream));
   if (out.has_qualities) out.qc.alloc((n ? (size_t)b->seq_off[n] : 0) + 64);
   CUDA_OK(cudaMemsetAsync(out.pairs.p, 0, out.pairs.bytes(), st));
   CUDA_OK(cudaMemsetAsync(out.xmask.p, 0, out.xmask.bytes(), st));
@@ -277,7 +278,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     k_fasta_track<<<grid_for(word_off, 256, ctx->sm_count), 256, 0, st>>>(A, b->n_contigs);
     out.pack_launches += 1;
   }
-  if (n) {  // the track is final: SIMPLE reads as differences against it
+  if (n && ctx->difference_lists) {  // the track is final: every read as its differences against it
     k_mismatch_lists<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(A);
     out.pack_launches += 1;
   }
@@ -595,6 +596,7 @@ guac_status guac_ctx_set_option(guac_ctx* ctx, int option, int64_t value) {
     case GUAC_OPT_SORT_RECORDS: ctx->sort_records = value != 0; return GUAC_OK;
     case GUAC_OPT_PACK_QUALITIES: ctx->pack_qualities = value != 0; return GUAC_OK;
     case GUAC_OPT_HOST_THREADS: ctx->host_threads = value > 0 ? (int)value : 0; return GUAC_OK;
+    case GUAC_OPT_DIFFERENCE_LISTS: ctx->difference_lists = value != 0; return GUAC_OK;
   }
   ctx->last_error = "unknown option";
   return GUAC_ERR_INVALID_ARGUMENT;

@@ -4,8 +4,9 @@
 //   rec[n+1]      16 B/read   {start, end, pair_off, info}   contig-relative 0-based [start, end)   (MappedRead.start/end)
 //   pairs[]       8 B/32 bases  bit-plane pairs (lo, hi) of the 2-bit read bases, read coordinates, 32 bases per pair
 //   xmask[]       4 B/32 bases  1 = base is not A/C/G/T (read only for reads flagged HAS_EXC)
-//   mm[n]         16 B/read   SIMPLE reads as differences against the reference track (reference-based encoding, like CRAM):
-//                             up to 8 (offset, base) pairs; the germline tile kernel reads rec + mm and never the planes
+//   mm[n]         16 B/read   a read as its differences against the reference track (reference-based encoding, like CRAM):
+//                             up to 8 (offset, class) pairs; the germline tile kernel reads rec + mm and, for reads that
+//                             fit, never the planes or the CIGAR
 //   cig_off/cigar BAM-encoded run-length CIGAR ops (read only for reads that are not SIMPLE)
 //   seq/qual      raw bytes (the exact per-locus paths read them)
 //   qc[]          1 B/base   quality (6 bits) | base code << 6: the one byte per pileup element the likelihood kernel loads
@@ -65,7 +66,7 @@ struct DevReads {
   const uint32_t* cigar;
   const uint2* pairs;
   const uint32_t* xmask;
-  const uint4* mm;            // per read: up to 8 x u16 (reference offset << 2 | class), 0 = unused; class = base ^ reference base
+  const uint4* mm;            // per read: up to 8 x u16 (reference offset << 2 | class), 0xFFFF = unused (guac_pack.cuh)
   const uint64_t* seq_off;
   const uint8_t* seq;
   const uint8_t* qual;

@@ -311,11 +311,11 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     }
   };
 
-  // ---- phase 1a: one read per lane.  A SIMPLE read of plain A/C/G/T bases is stored as its differences against the reference
-  // track (mm[], built at pack time): it costs two depth updates plus one shared-memory atomic per differing base.  The
-  // others are listed for phase 1b.  The records of the next batch are fetched before the current one is worked on.
+  // ---- phase 1a: one read per lane.  A read is stored as its differences against the reference track (mm[], built at pack
+  // time: mismatching bases and elements that are not plain bases): it costs two depth updates plus one shared-memory
+  // atomic per entry.  Reads with more entries than mm[] holds are listed for phase 1b (CIGAR walk).  The records of the next batch are fetched before the current one is worked on.
   ReadRec rec_next{0, 0, 0, 0};
-  uint4 mm_next = make_uint4(0u, 0u, 0u, 0u);
+  uint4 mm_next = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
   if (first + lane < last) { rec_next = R.rec[first + lane]; mm_next = __ldg(&R.mm[first + lane]); }
   for (uint32_t base = first; base < last; base += 32) {  // warp-uniform
     const uint32_t r = base + lane;
@@ -339,16 +339,17 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
       const uint32_t slot = atomicAdd(&S.n_list, 1u);
       if (slot < (uint32_t)kListCap) S.list[slot] = r; else slow_now = true;
     }
-    // entries are (reference offset << 2 | class), ascending, class = read base code ^ reference base code (1..3) = the
-    // counter field; unused slots 0.  A slot no lane uses ends the walk (the lists are filled from slot 0).
-    const uint32_t mmw[4] = {fast ? mm.x : 0u, fast ? mm.y : 0u, fast ? mm.z : 0u, fast ? mm.w : 0u};
+    // entries are (reference offset << 2 | class); class = the counter field: 0 "other" element, 1..3 read base code ^
+    // reference base code; unused slots 0xFFFF.  A slot no lane uses ends the walk (the lists are filled from slot 0).
+    const uint32_t none = 0xFFFFFFFFu;
+    const uint32_t mmw[4] = {fast ? mm.x : none, fast ? mm.y : none, fast ? mm.z : none, fast ? mm.w : none};
     const int rel = rec.start - tile_lo;
 #pragma unroll
     for (int k = 0; k < kMmSlots; ++k) {
       const uint32_t e = (k & 1) ? (mmw[k >> 1] >> 16) : (mmw[k >> 1] & 0xFFFFu);
-      if (!__any_sync(0xFFFFFFFFu, e != 0u)) break;  // warp-uniform
+      if (!__any_sync(0xFFFFFFFFu, e != 0xFFFFu)) break;  // warp-uniform
       const int x = rel + (int)(e >> 2);
-      if (e != 0u && (unsigned)x < (unsigned)kWarpLoci) {
+      if (e != 0xFFFFu && (unsigned)x < (unsigned)kWarpLoci) {
         if constexpr (sizeof(CntT) == 8) atomicAdd(reinterpret_cast<unsigned long long*>(S.cnt + x), 1ull << (FB * (e & 3u)));
         else atomicAdd(S.cnt + x, (CntT)1 << (FB * (e & 3u)));
       }

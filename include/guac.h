@@ -219,6 +219,9 @@ const char* guac_status_string(guac_status s);
                                       them, somatic-standard needs them */
 #define GUAC_OPT_HOST_THREADS 3     /* [0 = all] host threads guac_reads_pack may use for its header pass (set it to
                                       cores / ranks when several ranks share one box) */
+#define GUAC_OPT_DIFFERENCE_LISTS 4  /* [1] guac_reads_pack also stores every read as its differences against the reference
+                                      track (16 B/read); the pileup kernels then skip the base planes and the CIGAR for
+                                      reads that fit.  0 = always walk planes / CIGAR (same results; a test knob) */
 guac_status guac_ctx_set_option(guac_ctx* ctx, int option, int64_t value);
 
 /* Device-side stopwatch on the context's stream (CUDA events): start, run any number of calls, stop -> elapsed ms. */

@@ -19,6 +19,16 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(scope="module", params=[1, 0], ids=["difference-lists", "cigar-walk"], autouse=True)
+def difference_lists(request, ctx):
+    """Every parity test runs twice: with reads packed as differences against the reference track (the default) and with
+    the pileup kernels walking bit planes / CIGARs for every read (the path reads with many differences take)."""
+    from guacamole_b200 import abi
+    ctx.set_option(abi.OPT_DIFFERENCE_LISTS, request.param)
+    yield request.param
+    ctx.set_option(abi.OPT_DIFFERENCE_LISTS, 1)
+
+
 def gpu_threshold(ctx, batch, ranges, **kw):
     from guacamole_b200 import callers
     reads = ctx.pack(batch)
