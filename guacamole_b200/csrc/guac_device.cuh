@@ -61,6 +61,8 @@ struct ContigInfo {
 
 struct DevReads {
   uint64_t n;
+  int32_t max_ref_span;       // longest reference span of a read (how far back of a locus a start-sorted search must look)
+  int32_t pad_;
   const ReadRec* rec;
   const uint32_t* cig_off;
   const uint32_t* cigar;
@@ -125,6 +127,23 @@ __device__ __forceinline__ uint32_t plane_window(Get get, int q0) {
   uint32_t a = j >= 0 ? get(j) : 0u;
   uint32_t b = get(j + 1);
   return __funnelshift_r(a, b, sh);
+}
+
+// Reads are sorted by start, and a granule's candidate range [first, last) can hold several hundred of them.  One
+// warp-cooperative probe round (32 evenly spaced records) narrows it to the reads that can overlap loci [lo, hi): those with
+// start < hi and start > lo - max_ref_span.  Conservative: it only drops whole probe intervals.  Warp-uniform result.
+__device__ __forceinline__ void narrow_candidates(const DevReads& R, uint32_t& first, uint32_t& last, int lo, int hi) {
+  const uint32_t n = last - first;
+  if (first == 0xFFFFFFFFu || last <= first || n <= 96u) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t step = (n + 31u) >> 5;
+  const uint32_t idx = first + (uint32_t)lane * step;
+  const int s = idx < last ? R.rec[idx].start : 0x7FFFFFFF;
+  const uint32_t before = __ballot_sync(0xFFFFFFFFu, (long long)s + R.max_ref_span <= (long long)lo);  // a prefix of the lanes
+  const uint32_t after = __ballot_sync(0xFFFFFFFFu, s >= hi);                                         // a suffix of the lanes
+  const int k = __popc(before);
+  if (after) last = min(last, first + (uint32_t)(__ffs(after) - 1) * step);
+  if (k > 0) first = first + (uint32_t)(k - 1) * step;
 }
 
 // ---- MD walk shared by the track builder, its verifier and the exact per-locus path ------------------------------

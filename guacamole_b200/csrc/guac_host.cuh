@@ -349,6 +349,8 @@ struct guac_reads {
   DevReads view() const {
     DevReads R;
     R.n = n;
+    R.max_ref_span = (int32_t)std::min<int64_t>(max_ref_span, 0x7FFFFFFF);
+    R.pad_ = 0;
     R.rec = rec.p;
     R.cig_off = cig_off.p;
     R.cigar = cigar.p;

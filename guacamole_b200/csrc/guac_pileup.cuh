@@ -720,9 +720,10 @@ struct OverlapWalker {
   uint32_t src, last;
   uint32_t head, tail;
   int locus;
-  __device__ OverlapWalker(uint32_t* r, uint32_t first, uint32_t last_, int l)
-      : ring(r), src(first == 0xFFFFFFFFu ? last_ : first), last(first == 0xFFFFFFFFu ? 0u : last_), head(0), tail(0), locus(l) {
+  __device__ OverlapWalker(const DevReads& R, uint32_t* r, uint32_t first, uint32_t last_, int l)
+      : ring(r), src(first), last(last_), head(0), tail(0), locus(l) {
     if (first == 0xFFFFFFFFu) src = last = 0;
+    else narrow_candidates(R, src, last, l, l + 1);
   }
   // warp-uniform; false when no read is left.  Lanes with valid == true hold one overlapping read each.
   __device__ bool next(const DevReads& R, uint32_t& r, ReadRec& rec, bool& valid) {
@@ -766,7 +767,7 @@ __device__ void exact_locus(const DevReads& R, const int contig, const int locus
   const int g = locus >> kGranuleShift;
   const uint32_t first = R.gran_first[ci.gran_off + g], last = R.gran_last[ci.gran_off + g];
   if (first == 0xFFFFFFFFu) return;
-  OverlapWalker walk(ring, first, last, locus);
+  OverlapWalker walk(R, ring, first, last, locus);
   uint32_t r;
   ReadRec rec;
   bool valid;

@@ -435,8 +435,9 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
   // candidate reads of the word: the granule's read range (no dependent binary-search chain); every lane tests one record
   // and the warp then walks only the reads that really overlap the 32 loci
   const int g = span_lo >> kGranuleShift;
-  const uint32_t first = R.gran_first[ci.gran_off + g], last = R.gran_last[ci.gran_off + g];
+  uint32_t first = R.gran_first[ci.gran_off + g], last = R.gran_last[ci.gran_off + g];
   if (first == 0xFFFFFFFFu) return;
+  narrow_candidates(R, first, last, span_lo, span_lo + 32);
   const double2* __restrict__ tab = reinterpret_cast<const double2*>(tables + (TUMOR ? kTabT : kTabN));
   const uint8_t ref_base = std_ref ? code_base(rcode) : (uint8_t)'N';
   // the reference class is the common one: it keeps one running sum (its S0 is T0 minus the other classes' S0 at the
@@ -681,7 +682,7 @@ __device__ bool exact_sample(const DevReads& R, int contig, int locus, const Som
     first = R.gran_first[ci.gran_off + g];
     last = R.gran_last[ci.gran_off + g];
   }
-  OverlapWalker walk(ring, first, last, locus);
+  OverlapWalker walk(R, ring, first, last, locus);
   uint32_t r;
   ReadRec rec;
   bool valid;
@@ -887,7 +888,7 @@ __device__ void evidence_sample(const DevReads& R, int contig, int locus, const 
     first = R.gran_first[ci.gran_off + g];
     last = R.gran_last[ci.gran_off + g];
   }
-  OverlapWalker walk(S.ring, first, last, locus);
+  OverlapWalker walk(R, S.ring, first, last, locus);
   uint32_t r;
   ReadRec rec;
   bool valid;
