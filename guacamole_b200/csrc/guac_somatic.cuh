@@ -506,14 +506,12 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
           sr1 += l.x;
           n_ref += 1;
         } else {
-          const int code = (int)(b >> 6);
+          const uint32_t code = b >> 6;
           cnt_packed += 1ull << (16 * code);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const bool is = code == k;
-            A.s1[k] += is ? l.x : 0.0;
-            A.s0[k] += is ? l.y : 0.0;
-          }
+          if (code == 0u) { A.s1[0] += l.x; A.s0[0] += l.y; }
+          else if (code == 1u) { A.s1[1] += l.x; A.s0[1] += l.y; }
+          else if (code == 2u) { A.s1[2] += l.x; A.s0[2] += l.y; }
+          else { A.s1[3] += l.x; A.s0[3] += l.y; }
         }
       }
     }
