@@ -397,7 +397,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
   uint64_t cap_rec = dense ? tile_loci + 16 : std::max<uint64_t>(4096, tile_loci / 64);
   uint64_t cap_slow = std::max<uint64_t>(4096, tile_loci / 32);
   uint64_t cap_pool = kPoolDynOff + std::max<uint64_t>(65536, tile_loci / 64);
-  cap_rec = std::max<uint64_t>(cap_rec, ctx->out_rec.n / rec_size);
+  if (dense) cap_rec = std::max<uint64_t>(cap_rec, ctx->out_rec.n / rec_size);  // (sparse records go to a pinned block sized per call)
   cap_slow = std::max<uint64_t>(cap_slow, ctx->out_slow.n / sizeof(SlowLocus));
   cap_pool = std::max<uint64_t>(cap_pool, ctx->out_pool.n);
   // 8-bit counter fields first unless the pileup is certainly deeper; K_tile reports an overflow and we widen
@@ -407,7 +407,25 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
   for (int attempt = 0; attempt < 8; ++attempt) {
     if (cap_rec >= 0xFFFFFFF0ull || cap_slow >= 0xFFFFFFF0ull || cap_pool >= 0xFFFFFFF0ull)
       fail(GUAC_ERR_UNSUPPORTED, "too many output records for one call: split the loci ranges");
-    ctx->out_rec.ensure(cap_rec * rec_size);
+    // Sparse records are written by the kernels straight into the pinned host block the result will own (the device sees
+    // pinned memory through unified addressing): the PCIe writes overlap the kernels and no record copy follows them.
+    // Dense outputs (counts, emit_ref) stay in HBM and are copied afterwards.
+    const bool zero_copy = !dense;
+    const size_t rec_at_zc = ((size_t)cap_pool + 63) & ~(size_t)63;
+    if (zero_copy) {
+      const size_t want = rec_at_zc + (size_t)cap_rec * rec_size + 64;
+      if (res.block && res.block_bytes < want) {
+        ctx->pinned->give(res.block, res.block_bytes);
+        res.block = nullptr;
+      }
+      if (!res.block) {
+        res.pool = ctx->pinned;
+        res.block = ctx->pinned->take(want, &res.block_bytes);
+        if (!res.block) fail(GUAC_ERR_OOM, "pinned host allocation of %zu bytes failed", want);
+      }
+    } else {
+      ctx->out_rec.ensure(cap_rec * rec_size);
+    }
     ctx->out_slow.ensure(cap_slow * sizeof(SlowLocus));
     if (ctx->out_pool.ensure(cap_pool)) ctx->pool_head_ready = false;
     if (!ctx->pool_head_ready) {
@@ -420,7 +438,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     }
     CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
     DevOut out;
-    out.trec = (guac_threshold_record*)ctx->out_rec.p;
+    out.trec = zero_copy ? (guac_threshold_record*)((unsigned char*)res.block + rec_at_zc) : (guac_threshold_record*)ctx->out_rec.p;
     out.crec = (guac_locus_counts*)ctx->out_rec.p;
     out.cap_rec = (uint32_t)cap_rec;
     out.pool = ctx->out_pool.p;
@@ -463,16 +481,18 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     // their offsets into the pool, which is returned whole: no per-record work on the host.
     const uint64_t n_rec = c[0];
     const size_t pool_bytes = (size_t)(kPoolDynOff + c[1]), rec_bytes = (size_t)(n_rec * rec_size);
-    const size_t rec_at = (pool_bytes + 63) & ~(size_t)63;
-    res.pool = ctx->pinned;
-    res.block = ctx->pinned->take(rec_at + rec_bytes + 64, &res.block_bytes);
-    if (!res.block) fail(GUAC_ERR_OOM, "pinned host allocation of %zu bytes failed", rec_at + rec_bytes + 64);
+    const size_t rec_at = zero_copy ? rec_at_zc : ((pool_bytes + 63) & ~(size_t)63);
+    if (!zero_copy) {
+      res.pool = ctx->pinned;
+      res.block = ctx->pinned->take(rec_at + rec_bytes + 64, &res.block_bytes);
+      if (!res.block) fail(GUAC_ERR_OOM, "pinned host allocation of %zu bytes failed", rec_at + rec_bytes + 64);
+    }
     unsigned char* hs = (unsigned char*)res.block;
     unsigned char* hrec = hs + rec_at;
     CUDA_OK(cudaMemcpyAsync(hs, ctx->out_pool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
-    if (n_rec) CUDA_OK(cudaMemcpyAsync(hrec, ctx->out_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
+    if (n_rec && !zero_copy) CUDA_OK(cudaMemcpyAsync(hrec, ctx->out_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    res.stats.d2h_bytes = pool_bytes + rec_bytes + 8 * sizeof(unsigned long long);
+    res.stats.d2h_bytes = pool_bytes + rec_bytes + 8 * sizeof(unsigned long long);  // (records cross PCIe either way)
     if (prm.mode == 1) {
       res.counts.resize((size_t)n_rec);
       if (n_rec) memcpy(res.counts.data(), hrec, rec_bytes);
