@@ -1,11 +1,13 @@
 // guac_pileup.cuh — the pileup hot path: CIGAR expansion + per-locus allele / depth / strand counting + fused callers.
 //
-// K_tile   (k_pileup_tile): one CTA per tile of 4096 loci.  Phase 1 is READ-centric: each thread takes one read of the
-//           tile's candidate range (a contiguous index range of the start-sorted store, found through the granule index),
-//           aligns its 2-bit base planes onto the reference track word by word with funnel shifts (CIGAR expansion,
-//           bit-parallel over 32 loci), XORs with the reference planes held in shared memory and touches the per-locus
-//           counter tile only where the read DIFFERS from the reference (sparse shared-memory atomics: one per mismatch /
-//           insertion / deletion / clipped element) plus two atomics per read for the depth difference array.
+// K_tile   (k_pileup_tile): one WARP per granule of 1024 loci (4 warps per CTA, no block barrier).  Phase 1 is
+//           READ-centric: each lane takes one read of the granule's candidate range (a contiguous index range of the
+//           start-sorted store, found through the granule index) and replays the read's differences against the reference
+//           track (mm[], built once at pack time by k_mismatch_lists: the CIGAR expansion, bit-parallel over 32 loci):
+//           the per-locus counter tile is touched only where the read DIFFERS from the reference (sparse shared-memory
+//           atomics: one per mismatch / insertion / deletion / clipped element) plus two atomics per read for the depth
+//           difference array.  Reads with more differences than mm[] holds align their 2-bit base planes onto the
+//           reference planes word by word with funnel shifts + XOR, walking their CIGAR in the kernel.
 //           Phase 2 scans the difference array into depth (+ strand depth).  Phase 3 is LOCUS-centric: the caller.
 //             GermlineThreshold.Caller.callVariantsAtLocus      commands/GermlineThresholdCaller.scala:90-179
 //             Pileup.depth/positiveDepth/referenceDepth           pileup/Pileup.scala:76-91
