@@ -82,6 +82,10 @@ class SomaticParamsC(C.Structure):
                 ("filter_multi_allelic", C.c_int32), ("max_read_depth", C.c_int32), ("skip_empty", C.c_int32)]
 
 
+class StandardParamsC(C.Structure):
+    _fields_ = [("min_alignment_quality", C.c_int32), ("skip_empty", C.c_int32)]
+
+
 class ThresholdRecordC(C.Structure):
     _fields_ = [("start", C.c_int64), ("contig", C.c_int32), ("sample", C.c_int32), ("ref_off", C.c_uint32),
                 ("alt_off", C.c_uint32), ("ref_len", C.c_uint16), ("alt_len", C.c_uint16), ("gt", C.c_uint8 * 2),
@@ -101,6 +105,12 @@ class SomaticRecordC(C.Structure):
                 ("alt_off", C.c_uint32), ("ref_len", C.c_uint16), ("alt_len", C.c_uint16),
                 ("phred_scaled_somatic_likelihood", C.c_int32), ("somatic_log_odds", C.c_double),
                 ("tumor", AlleleEvidenceC), ("normal", AlleleEvidenceC)]
+
+
+class CalledAlleleC(C.Structure):
+    _fields_ = [("start", C.c_int64), ("contig", C.c_int32), ("sample", C.c_int32), ("ref_off", C.c_uint32),
+                ("alt_off", C.c_uint32), ("ref_len", C.c_uint16), ("alt_len", C.c_uint16),
+                ("phred_scaled_likelihood", C.c_int32), ("evidence", AlleleEvidenceC)]
 
 
 class SomaticFilterParamsC(C.Structure):

@@ -36,6 +36,10 @@ SOMATIC_DTYPE = np.dtype([("start", "<i8"), ("contig", "<i4"), ("sample", "<i4")
                           ("alt_off", "<u4"), ("ref_len", "<u2"), ("alt_len", "<u2"),
                           ("phred_scaled_somatic_likelihood", "<i4"), ("somatic_log_odds", "<f8"),
                           ("tumor", _EVIDENCE), ("normal", _EVIDENCE)])
+CALLED_DTYPE = np.dtype([("start", "<i8"), ("contig", "<i4"), ("sample", "<i4"), ("ref_off", "<u4"),
+                         ("alt_off", "<u4"), ("ref_len", "<u2"), ("alt_len", "<u2"),
+                         ("phred_scaled_likelihood", "<i4"), ("evidence", _EVIDENCE)])
+assert CALLED_DTYPE.itemsize == C.sizeof(abi.CalledAlleleC)
 assert COUNTS_DTYPE.itemsize == C.sizeof(abi.LocusCountsC)
 assert THRESHOLD_DTYPE.itemsize == C.sizeof(abi.ThresholdRecordC)
 assert SOMATIC_DTYPE.itemsize == C.sizeof(abi.SomaticRecordC)
@@ -166,6 +170,8 @@ class Result:
             p, dt = L.guac_result_threshold_records(handle), THRESHOLD_DTYPE
         elif kind == "somatic":
             p, dt = L.guac_result_somatic_records(handle), SOMATIC_DTYPE
+        elif kind == "called":
+            p, dt = L.guac_result_called_alleles(handle), CALLED_DTYPE
         else:
             p, dt = L.guac_result_counts(handle), COUNTS_DTYPE
         if n:
@@ -207,6 +213,11 @@ class Result:
             if self.kind == "threshold":
                 d["gt"] = (int(r["gt"][0]), int(r["gt"][1]))
                 d["tie"] = int(r["tie"])
+            elif self.kind == "called":  # AlleleConversions.calledAlleleToADAMGenotype (AlleleConversions.scala:30-45)
+                d["gt"] = (abi.GT_REF, abi.GT_ALT)
+                d["phred"] = int(r["phred_scaled_likelihood"])
+                d["evidence"] = {k: (float(r["evidence"][k]) if k[0] == "m" or k == "likelihood" else int(r["evidence"][k]))
+                                 for k, _ in _EVIDENCE}
             else:
                 d["gt"] = (abi.GT_REF, abi.GT_ALT)
                 d["phred"] = int(r["phred_scaled_somatic_likelihood"])
@@ -242,6 +253,17 @@ def somatic_standard(ctx: Context, tumor: PackedReads, normal: PackedReads, loci
     h = C.c_void_p()
     ctx._check(lib().guac_somatic_standard(ctx._h, tumor._h, normal._h, arr, n, C.byref(prm), C.byref(h)))
     return Result(h, "somatic")
+
+
+def germline_standard(ctx: Context, reads: PackedReads, loci_partitions, min_alignment_quality: int = 1,
+                      skip_empty: bool = True) -> Result:
+    """pileupFlatMap(reads, lociPartitions, skipEmpty, GermlineStandard.callVariantsAtLocus(_, minAlignmentQuality))
+    (commands/GermlineStandardCaller.scala:66-70): one CalledAllele per non-reference allele of the most likely genotype."""
+    arr, n = _ranges(loci_partitions)
+    prm = abi.StandardParamsC(min_alignment_quality, int(skip_empty))
+    h = C.c_void_p()
+    ctx._check(lib().guac_germline_standard(ctx._h, reads._h, arr, n, C.byref(prm), C.byref(h)))
+    return Result(h, "called")
 
 
 def pileup_counts(ctx: Context, reads: PackedReads, loci_partitions, skip_empty: bool = True) -> Result:

@@ -18,6 +18,7 @@
 #include "guac_pack.cuh"
 #include "guac_pileup.cuh"
 #include "guac_somatic.cuh"
+#include "guac_standard.cuh"
 
 namespace {
 
@@ -727,6 +728,19 @@ guac_status guac_somatic_standard(guac_ctx* ctx, const guac_reads* tumor, const 
   });
 }
 
+guac_status guac_germline_standard(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges, size_t n_ranges,
+                                   const guac_standard_params* params, guac_result** out) {
+  if (!ctx || !reads || !params || !out || (n_ranges && !ranges)) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    std::unique_ptr<guac_result> res(new guac_result());
+    res->kind = 3;
+    run_standard(ctx, *reads, ranges, n_ranges, *params, *res);
+    *out = res.release();
+  });
+}
+
 size_t guac_result_n(const guac_result* r) {
   if (!r) return 0;
   return r->kind == 2 ? r->counts.size() : r->n_records;
@@ -734,6 +748,7 @@ size_t guac_result_n(const guac_result* r) {
 const guac_threshold_record* guac_result_threshold_records(const guac_result* r) { return (r && r->kind == 0) ? (const guac_threshold_record*)r->records : nullptr; }
 const guac_somatic_record* guac_result_somatic_records(const guac_result* r) { return (r && r->kind == 1) ? (const guac_somatic_record*)r->records : nullptr; }
 const guac_locus_counts* guac_result_counts(const guac_result* r) { return (r && r->kind == 2) ? r->counts.data() : nullptr; }
+const guac_called_allele* guac_result_called_alleles(const guac_result* r) { return (r && r->kind == 3) ? (const guac_called_allele*)r->records : nullptr; }
 const uint8_t* guac_result_bytes(const guac_result* r, size_t* n_bytes) {
   if (n_bytes) *n_bytes = r ? r->n_bytes : 0;
   return r ? r->bytes : nullptr;

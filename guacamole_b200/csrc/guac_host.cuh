@@ -382,7 +382,7 @@ struct guac_reads {
 };
 
 struct guac_result {
-  int kind = 0;  // 0 threshold, 1 somatic, 2 counts
+  int kind = 0;  // 0 threshold, 1 somatic, 2 counts, 3 called alleles (germline-standard)
   // threshold / somatic records and the allele byte pool live in one pinned block (downloaded in place)
   std::shared_ptr<PinnedPool> pool;
   void* block = nullptr;

@@ -99,7 +99,7 @@ __device__ inline AlleleEntry as_entry(const SomAllele& a) {
 // Likelihood.likelihoodsOfAllPossibleGenotypesFromPileup(pileup, probabilityCorrect, normalize = true), plain probabilities.
 // tab[0..n) must be sorted by Allele.compare.  Returns the number of genotypes; lk[] in the reference's (i <= j) order.
 __device__ int genotype_likelihoods(const AlleleView& av, const SomAllele* tab, int n_tab, const SampleStats& st, int* gi, int* gj,
-                                    double* lk) {
+                                    double* lk, bool log_space = false) {
   int idx[kSomMaxAlleles], n = 0;
   for (int k = 0; k < n_tab; ++k) {  // alleles whose alternate bases are all standard (an empty alternate passes)
     const AlleleEntry e = as_entry(tab[k]);
@@ -129,7 +129,7 @@ __device__ int genotype_likelihoods(const AlleleView& av, const SomAllele* tab, 
   double total = 0.0;
   for (int g = 0; g < ng; ++g) total += exp(lk[g]);
   const double log_total = log(total);  // naive normalisation on purpose: Inf / NaN flow like the reference
-  for (int g = 0; g < ng; ++g) lk[g] = exp(lk[g] - log_total);
+  for (int g = 0; g < ng; ++g) lk[g] = log_space ? lk[g] - log_total : exp(lk[g] - log_total);
   return ng;
 }
 
@@ -298,6 +298,7 @@ __device__ __forceinline__ void snv_log_likelihoods(const SnvAlleles& S, double 
 }
 
 // Likelihood.likelihoodsOfAllPossibleGenotypesFromPileup(..., normalize = true) on the valid slots, in place
+template <bool LOG_SPACE = false>
 __device__ __forceinline__ void snv_normalize(const SnvAlleles& S, double (&lk)[10]) {
   double total = 0.0;
   int g = 0;
@@ -312,7 +313,7 @@ __device__ __forceinline__ void snv_normalize(const SnvAlleles& S, double (&lk)[
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = i; j < 4; ++j, ++g)
-      if (j < S.n) lk[g] = exp(lk[g] - log_total);
+      if (j < S.n) lk[g] = LOG_SPACE ? lk[g] - log_total : exp(lk[g] - log_total);
 }
 
 // tumor half of findPotentialVariantAtLocus (tumor_most_likely() above) for such a locus over the standard reference base

@@ -117,6 +117,13 @@ typedef struct guac_somatic_params {     /* commands/SomaticStandardCaller.scala
   int32_t skip_empty;
 } guac_somatic_params;
 
+typedef struct guac_standard_params {    /* commands/GermlineStandardCaller.scala:64-70, 90-92 */
+  int32_t min_alignment_quality; /* --min-mapq (PileupFilterArguments, default 1): elements of reads below it do not enter
+                                    the likelihoods (QualityAlignedReadsFilter, filters/PileupElementsFilter.scala:48-50);
+                                    the AlleleEvidence of a call is still taken over the unfiltered pileup (:120) */
+  int32_t skip_empty;            /* the caller passes skipEmpty = true (:68) */
+} guac_standard_params;
+
 /* ---- output records ------------------------------------------------------------------------------------ */
 /* bdg-formats GenotypeAllele */
 #define GUAC_GT_REF 0u
@@ -167,6 +174,22 @@ typedef struct guac_somatic_record {
   guac_allele_evidence tumor;    /* tumorVariantEvidence */
   guac_allele_evidence normal;   /* normalReferenceEvidence */
 } guac_somatic_record;
+
+/* variants/CalledAllele.scala:34-43 as built by GermlineStandard.Caller.callVariantsAtLocus
+ * (commands/GermlineStandardCaller.scala:113-121) + genotypeQuality of AlleleConversions.scala:30-45.  One record per
+ * non-reference allele of the most likely genotype: a homozygous alternate call yields two equal records, as the reference
+ * does (Genotype.getNonReferenceAlleles keeps both copies, variants/Genotype.scala:46-48). */
+typedef struct guac_called_allele {
+  int64_t start;
+  int32_t contig;
+  int32_t sample;
+  uint32_t ref_off;
+  uint32_t alt_off;
+  uint16_t ref_len;
+  uint16_t alt_len;
+  int32_t phred_scaled_likelihood;  /* AlleleEvidence.phredScaledLikelihood (variants/AlleleEvidence.scala:52) */
+  guac_allele_evidence evidence;    /* likelihood = exp(normalised log likelihood of the most likely genotype) */
+} guac_called_allele;
 
 /* per-locus histogram (guac_pileup_counts): one row per visited locus */
 typedef struct guac_locus_counts {
@@ -252,6 +275,10 @@ guac_status guac_germline_threshold(guac_ctx* ctx, const guac_reads* reads, cons
 guac_status guac_somatic_standard(guac_ctx* ctx, const guac_reads* tumor, const guac_reads* normal,
                                   const guac_locus_range* ranges, size_t n_ranges,
                                   const guac_somatic_params* params, guac_result** out);
+/* pileupFlatMap(reads, ranges, skip_empty, callVariantsAtLocus(_, minAlignmentQuality)) of GermlineStandard
+ * (commands/GermlineStandardCaller.scala:66-70, 90-124).  Needs reads packed with base qualities. */
+guac_status guac_germline_standard(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges,
+                                   size_t n_ranges, const guac_standard_params* params, guac_result** out);
 /* pileupFlatMap(reads, ranges, skip_empty, p => (depth, positiveDepth, referenceDepth, base histogram)) */
 guac_status guac_pileup_counts(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges,
                                size_t n_ranges, int skip_empty, guac_result** out);
@@ -261,6 +288,7 @@ size_t guac_result_n(const guac_result* r);
 const guac_threshold_record* guac_result_threshold_records(const guac_result* r); /* NULL if other kind */
 const guac_somatic_record* guac_result_somatic_records(const guac_result* r);
 const guac_locus_counts* guac_result_counts(const guac_result* r);
+const guac_called_allele* guac_result_called_alleles(const guac_result* r);
 const uint8_t* guac_result_bytes(const guac_result* r, size_t* n_bytes);            /* allele byte pool */
 const guac_stats* guac_result_stats(const guac_result* r);
 void guac_result_free(guac_result* r);

@@ -670,6 +670,7 @@ bool advance_multiple_windows(std::vector<SlidingWindow>& windows, LociIterator&
 struct Output {
   std::vector<guac_threshold_record> threshold;
   std::vector<guac_somatic_record> somatic;
+  std::vector<guac_called_allele> called;
   std::vector<guac_locus_counts> counts;
   std::vector<orc_element> elements;
   std::vector<orc_genotype_likelihood> likelihoods;
@@ -955,6 +956,48 @@ void find_potential_variant_at_locus(Pileup& tumor, Pileup& normal, const guac_s
   out.somatic.push_back(r);
 }
 
+// GermlineStandard.Caller.callVariantsAtLocus (commands/GermlineStandardCaller.scala:90-124)
+void call_standard_at_locus(Pileup& pileup, const guac_standard_params& p, Output& out) {
+  if (pileup.elements.empty()) return;
+  // pileup.bySample: groups in Scala Map order (unpinned); canonical here: ascending sample index
+  std::map<int32_t, std::vector<const Element*>> by_sample;
+  for (auto& e : pileup.elements) by_sample[e.read->sample].push_back(&e);
+  for (auto& kv : by_sample) {
+    Pileup sample_pileup;  // Pileup(referenceName, locus, referenceBase, the sample's elements)
+    sample_pileup.contig = pileup.contig;
+    sample_pileup.locus = pileup.locus;
+    sample_pileup.reference_base = pileup.reference_base;
+    for (const Element* e : kv.second) sample_pileup.elements.push_back(*e);
+    Pileup filtered = sample_pileup;  // QualityAlignedReadsFilter (filters/PileupElementsFilter.scala:48-50)
+    filtered.elements.clear();
+    for (auto& e : sample_pileup.elements)
+      if (e.read->mapq >= p.min_alignment_quality) filtered.elements.push_back(e);
+    if (filtered.elements.empty()) continue;
+    std::vector<GenotypeL> gl = likelihoods_of_all_possible_genotypes(filtered, /*include_alignment=*/false, /*log_space=*/true,
+                                                                      /*normalize=*/true);
+    if (gl.empty()) continue;  // (Scala's maxBy would throw on an empty list: every allele holds a non-ACGT base)
+    size_t best = 0;  // maxBy = reduceLeft((x, y) => if (f(x) >= f(y)) x else y)
+    for (size_t i = 1; i < gl.size(); ++i)
+      if (!(gl[best].value >= gl[i].value)) best = i;
+    const double probability = std::exp(gl[best].value);
+    const Allele* pair[2] = {&gl[best].a1, &gl[best].a2};
+    for (const Allele* a : pair) {  // genotype.getNonReferenceAlleles: both copies of a homozygous alternate
+      if (!a->is_variant()) continue;
+      guac_called_allele r{};
+      r.start = pileup.locus;
+      r.contig = pileup.contig;
+      r.sample = kv.first;
+      r.ref_off = out.put(a->ref);
+      r.ref_len = (uint16_t)a->ref.size();
+      r.alt_off = out.put(a->alt);
+      r.alt_len = (uint16_t)a->alt.size();
+      r.evidence = allele_evidence(probability, *a, sample_pileup);  // over the unfiltered sample pileup (:120)
+      r.phred_scaled_likelihood = success_probability_to_phred(r.evidence.likelihood - 1e-10);  // AlleleEvidence.scala:52
+      out.called.push_back(r);
+    }
+  }
+}
+
 void counts_at_locus(Pileup& p, Output& out) {
   guac_locus_counts c{};
   c.locus = p.locus;
@@ -1088,6 +1131,11 @@ struct Engine {
         r.alt_off += base;
         out.somatic.push_back(r);
       }
+      for (auto r : o.called) {
+        r.ref_off += base;
+        r.alt_off += base;
+        out.called.push_back(r);
+      }
       out.counts.insert(out.counts.end(), o.counts.begin(), o.counts.end());
       out.stats.reads_expanded += o.stats.reads_expanded;
       out.stats.loci_requested += o.stats.loci_requested;
@@ -1183,6 +1231,25 @@ int orc_somatic_standard(const guac_read_batch* tumor, const guac_read_batch* no
   });
 }
 
+int orc_germline_standard(const guac_read_batch* batch, const guac_reference* ref, const guac_locus_range* ranges,
+                          size_t n_ranges, const guac_standard_params* params, int n_threads, orc_result** out) {
+  return guarded([&] {
+    ReadSet rs;
+    load_batch(batch, rs);
+    auto res = std::make_unique<orc_result>();
+    Engine eng;
+    eng.sets = {&rs};
+    eng.ref = ref;
+    eng.skip_empty = params->skip_empty != 0;
+    guac_standard_params p = *params;
+    eng.run(ranges, n_ranges, n_threads, res->o,
+            [p](std::vector<std::unique_ptr<Pileup>>& st, Output& o) { call_standard_at_locus(*st[0], p, o); });
+    sort_records(res->o.called, res->o.bytes);
+    res->o.stats.records = res->o.called.size();
+    *out = res.release();
+  });
+}
+
 int orc_pileup_counts(const guac_read_batch* batch, const guac_reference* ref, const guac_locus_range* ranges,
                       size_t n_ranges, int skip_empty, int n_threads, orc_result** out) {
   return guarded([&] {
@@ -1205,10 +1272,11 @@ int orc_pileup_counts(const guac_read_batch* batch, const guac_reference* ref, c
 
 size_t orc_result_n(const orc_result* r) {
   const Output& o = r->o;
-  return std::max({o.threshold.size(), o.somatic.size(), o.counts.size(), o.elements.size(), o.likelihoods.size()});
+  return std::max({o.threshold.size(), o.somatic.size(), o.called.size(), o.counts.size(), o.elements.size(), o.likelihoods.size()});
 }
 const guac_threshold_record* orc_result_threshold_records(const orc_result* r) { return r->o.threshold.data(); }
 const guac_somatic_record* orc_result_somatic_records(const orc_result* r) { return r->o.somatic.data(); }
+const guac_called_allele* orc_result_called_alleles(const orc_result* r) { return r->o.called.data(); }
 const guac_locus_counts* orc_result_counts(const orc_result* r) { return r->o.counts.data(); }
 const orc_element* orc_result_elements(const orc_result* r) { return r->o.elements.data(); }
 const orc_genotype_likelihood* orc_result_likelihoods(const orc_result* r) { return r->o.likelihoods.data(); }

@@ -65,6 +65,12 @@ int orc_pileup_counts(const guac_read_batch* batch, const guac_reference* ref, c
 size_t orc_result_n(const orc_result* r);
 const guac_threshold_record* orc_result_threshold_records(const orc_result* r);
 const guac_somatic_record* orc_result_somatic_records(const orc_result* r);
+/* pileupFlatMap(reads, ...) + GermlineStandard.Caller.callVariantsAtLocus — GermlineStandardCaller.scala:66-70, 90-124.
+ * PARITY UNPINNED end to end: the reference has no test of this caller; its parts (likelihoods, AlleleEvidence, pileup)
+ * are pinned by LikelihoodSuite / AlleleEvidenceSuite / PileupSuite. */
+int orc_germline_standard(const guac_read_batch* batch, const guac_reference* ref, const guac_locus_range* ranges,
+                          size_t n_ranges, const guac_standard_params* params, int n_threads, orc_result** out);
+const guac_called_allele* orc_result_called_alleles(const orc_result* r);
 const guac_locus_counts* orc_result_counts(const orc_result* r);
 const orc_element* orc_result_elements(const orc_result* r);
 const orc_genotype_likelihood* orc_result_likelihoods(const orc_result* r);

@@ -51,6 +51,7 @@ def lib():
         _lib.orc_result_n.restype = C.c_size_t
         _lib.orc_result_threshold_records.restype = C.POINTER(abi.ThresholdRecordC)
         _lib.orc_result_somatic_records.restype = C.POINTER(abi.SomaticRecordC)
+        _lib.orc_result_called_alleles.restype = C.POINTER(abi.CalledAlleleC)
         _lib.orc_result_counts.restype = C.POINTER(abi.LocusCountsC)
         _lib.orc_result_elements.restype = C.POINTER(ElementC)
         _lib.orc_result_likelihoods.restype = C.POINTER(GenotypeLikelihoodC)
@@ -58,7 +59,8 @@ def lib():
         _lib.orc_result_stats.restype = C.POINTER(abi.StatsC)
         _lib.orc_result_reference_base.restype = C.c_uint8
         _lib.orc_phred_to_success_probability.restype = C.c_double
-        for f in ("orc_result_n", "orc_result_threshold_records", "orc_result_somatic_records", "orc_result_counts",
+        for f in ("orc_result_n", "orc_result_threshold_records", "orc_result_somatic_records", "orc_result_called_alleles",
+                  "orc_result_counts",
                   "orc_result_elements", "orc_result_likelihoods", "orc_result_stats", "orc_result_free",
                   "orc_result_reference_base"):
             getattr(_lib, f).argtypes = [C.c_void_p]
@@ -123,6 +125,18 @@ class Result:
                      normal=abi.struct_to_dict(r.normal))
             d["_raw"] = abi.SomaticRecordC.from_buffer_copy(r)
             out.append(d)
+        return out
+
+    def called(self) -> List[dict]:
+        L = lib()
+        n = L.orc_result_n(self.h)
+        p = L.orc_result_called_alleles(self.h)
+        out = []
+        for i in range(n):
+            r = p[i]
+            out.append(dict(contig=r.contig, start=r.start, sample=r.sample, ref=self._s(r.ref_off, r.ref_len),
+                            alt=self._s(r.alt_off, r.alt_len), phred=r.phred_scaled_likelihood,
+                            evidence=abi.struct_to_dict(r.evidence)))
         return out
 
     def counts(self) -> np.ndarray:
@@ -208,6 +222,17 @@ def somatic_standard(tumor: ReadBatch, normal: ReadBatch, ranges, params=None, n
     arr = ranges_array(ranges)
     _check(lib().orc_somatic_standard(C.byref(bt), C.byref(bn), C.byref(ref) if ref else None, arr,
                                       C.c_size_t(len(ranges)), C.byref(params), n_threads, C.byref(h)))
+    return Result(h)
+
+
+def germline_standard(batch: ReadBatch, ranges, min_mapq=1, skip_empty=True, n_threads=1, reference=None) -> Result:
+    params = abi.StandardParamsC(min_mapq, int(skip_empty))
+    h = C.c_void_p()
+    b = batch.to_c()
+    ref, keep = reference_c(reference)
+    arr = ranges_array(ranges)
+    _check(lib().orc_germline_standard(C.byref(b), C.byref(ref) if ref else None, arr, C.c_size_t(len(ranges)),
+                                       C.byref(params), n_threads, C.byref(h)))
     return Result(h)
 
 
