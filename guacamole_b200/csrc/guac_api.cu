@@ -408,8 +408,9 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
   for (int attempt = 0; attempt < 8; ++attempt) {
     if (cap_rec >= 0xFFFFFFF0ull || cap_slow >= 0xFFFFFFF0ull || cap_pool >= 0xFFFFFFF0ull)
       fail(GUAC_ERR_UNSUPPORTED, "too many output records for one call: split the loci ranges");
-    // Sparse records are written by the kernels straight into the pinned host block the result will own (the device sees
-    // pinned memory through unified addressing): the PCIe writes overlap the kernels and no record copy follows them.
+    // Sparse records end up in the pinned host block the result will own without a copy after the kernels (the device sees
+    // pinned memory through unified addressing): K_tile writes its records to HBM, K_exact streams them to the host block
+    // with coalesced stores while it walks its loci and appends its own records there directly.
     // Dense outputs (counts, emit_ref) stay in HBM and are copied afterwards.
     const bool zero_copy = !dense;
     const size_t rec_at_zc = ((size_t)cap_pool + 63) & ~(size_t)63;
@@ -424,9 +425,8 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
         res.block = ctx->pinned->take(want, &res.block_bytes);
         if (!res.block) fail(GUAC_ERR_OOM, "pinned host allocation of %zu bytes failed", want);
       }
-    } else {
-      ctx->out_rec.ensure(cap_rec * rec_size);
     }
+    ctx->out_rec.ensure(cap_rec * rec_size);
     ctx->out_slow.ensure(cap_slow * sizeof(SlowLocus));
     if (ctx->out_pool.ensure(cap_pool)) ctx->pool_head_ready = false;
     if (!ctx->pool_head_ready) {
@@ -439,7 +439,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     }
     CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
     DevOut out;
-    out.trec = zero_copy ? (guac_threshold_record*)((unsigned char*)res.block + rec_at_zc) : (guac_threshold_record*)ctx->out_rec.p;
+    out.trec = (guac_threshold_record*)ctx->out_rec.p;
     out.crec = (guac_locus_counts*)ctx->out_rec.p;
     out.cap_rec = (uint32_t)cap_rec;
     out.pool = ctx->out_pool.p;
@@ -455,7 +455,13 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     else launch_tile<0>(wide, (int)ctx->n_tiles, st, R, d_tiles, prm, out);
     CUDA_OK(cudaEventRecord(ctx->ev[1], st));
     // K_exact reads the number of deferred loci from the device counter: no host round trip in between
-    k_exact_loci<<<ctx->sm_count * 16, kExactWarps * 32, 0, st>>>(R, out.slow, prm, out);
+    const guac_threshold_record* tile_rec = nullptr;
+    if (zero_copy) {
+      CUDA_OK(cudaMemcpyAsync(ctx->d_counters + 8, ctx->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+      tile_rec = out.trec;
+      out.trec = (guac_threshold_record*)((unsigned char*)res.block + rec_at_zc);
+    }
+    k_exact_loci<<<ctx->sm_count * 16, kExactWarps * 32, 0, st>>>(R, out.slow, prm, out, tile_rec);
     CUDA_OK(cudaEventRecord(ctx->ev[2], st));
     launches += 2;
     CUDA_OK(cudaGetLastError());

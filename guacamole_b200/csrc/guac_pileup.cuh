@@ -920,10 +920,23 @@ __device__ void exact_locus(const DevReads& R, const int contig, const int locus
 }
 
 
-// grid-stride over the loci K_tile deferred; their number is read from the device counter (no host round trip)
-__global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, const SlowLocus* __restrict__ loci, CallParams prm, DevOut out) {
+// grid-stride over the loci K_tile deferred; their number is read from the device counter (no host round trip).
+// When `tile_rec` is set, K_tile wrote its sparse records to HBM and out.trec points into the pinned host block of the
+// result: the kernel first streams the K_tile records (counters[8] = their number, snapshot taken between the two kernels)
+// to the host block with coalesced 16-byte stores — posted PCIe writes that drain while the warps walk their loci —
+// and appends its own records behind them directly.
+__global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, const SlowLocus* __restrict__ loci, CallParams prm, DevOut out,
+                                                                 const guac_threshold_record* __restrict__ tile_rec) {
   __shared__ AlleleEntry tabs[kExactWarps][kMaxAlleles];
   __shared__ uint32_t rings[kExactWarps][64];
+  if (tile_rec) {
+    const unsigned long long n_tile = min(out.counters[8], (unsigned long long)out.cap_rec);
+    const unsigned long long n16 = n_tile * (sizeof(guac_threshold_record) / 16);
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(tile_rec);
+    uint4* dst = reinterpret_cast<uint4*>(out.trec);
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * blockDim.x)
+      dst[i] = src[i];
+  }
   const uint32_t n_loci = (uint32_t)min(out.counters[2], (unsigned long long)out.cap_slow);
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t t = warp; t < n_loci; t += n_warps) {
