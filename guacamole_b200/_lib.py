@@ -17,6 +17,7 @@ EXPORTED = [
     "guac_reads_pack", "guac_reads_free", "guac_reads_count", "guac_reads_device_bytes",
     "guac_reads_order_sensitive_loci", "guac_reads_h2d_bytes", "guac_reads_pack_kernel_ms",
     "guac_germline_threshold", "guac_somatic_standard", "guac_germline_standard", "guac_pileup_counts",
+    "guac_allele_counts", "guac_result_allele_counts",
     "guac_result_n", "guac_result_threshold_records", "guac_result_somatic_records", "guac_result_counts",
     "guac_result_called_alleles",
     "guac_result_bytes", "guac_result_stats", "guac_result_free", "guac_partition_loci_uniformly",
@@ -68,6 +69,9 @@ def lib():
                                         C.POINTER(abi.SomaticParamsC), C.POINTER(vp)]
     L.guac_germline_standard.argtypes = [vp, vp, C.POINTER(abi.LocusRangeC), C.c_size_t,
                                          C.POINTER(abi.StandardParamsC), C.POINTER(vp)]
+    L.guac_allele_counts.argtypes = [vp, vp, C.POINTER(abi.LocusRangeC), C.c_size_t, C.POINTER(vp)]
+    L.guac_result_allele_counts.argtypes = [vp]
+    L.guac_result_allele_counts.restype = C.POINTER(abi.AlleleCountC)
     L.guac_result_called_alleles.argtypes = [vp]
     L.guac_result_called_alleles.restype = C.POINTER(abi.CalledAlleleC)
     L.guac_pileup_counts.argtypes = [vp, vp, C.POINTER(abi.LocusRangeC), C.c_size_t, C.c_int, C.POINTER(vp)]

@@ -107,6 +107,11 @@ class SomaticRecordC(C.Structure):
                 ("tumor", AlleleEvidenceC), ("normal", AlleleEvidenceC)]
 
 
+class AlleleCountC(C.Structure):
+    _fields_ = [("start", C.c_int64), ("contig", C.c_int32), ("sample", C.c_int32), ("ref_off", C.c_uint32),
+                ("alt_off", C.c_uint32), ("ref_len", C.c_uint16), ("alt_len", C.c_uint16), ("count", C.c_int32)]
+
+
 class CalledAlleleC(C.Structure):
     _fields_ = [("start", C.c_int64), ("contig", C.c_int32), ("sample", C.c_int32), ("ref_off", C.c_uint32),
                 ("alt_off", C.c_uint32), ("ref_len", C.c_uint16), ("alt_len", C.c_uint16),

@@ -40,6 +40,9 @@ CALLED_DTYPE = np.dtype([("start", "<i8"), ("contig", "<i4"), ("sample", "<i4"),
                          ("alt_off", "<u4"), ("ref_len", "<u2"), ("alt_len", "<u2"),
                          ("phred_scaled_likelihood", "<i4"), ("evidence", _EVIDENCE)])
 assert CALLED_DTYPE.itemsize == C.sizeof(abi.CalledAlleleC)
+ALLELE_COUNT_DTYPE = np.dtype([("start", "<i8"), ("contig", "<i4"), ("sample", "<i4"), ("ref_off", "<u4"),
+                               ("alt_off", "<u4"), ("ref_len", "<u2"), ("alt_len", "<u2"), ("count", "<i4")])
+assert ALLELE_COUNT_DTYPE.itemsize == C.sizeof(abi.AlleleCountC)
 assert COUNTS_DTYPE.itemsize == C.sizeof(abi.LocusCountsC)
 assert THRESHOLD_DTYPE.itemsize == C.sizeof(abi.ThresholdRecordC)
 assert SOMATIC_DTYPE.itemsize == C.sizeof(abi.SomaticRecordC)
@@ -172,6 +175,8 @@ class Result:
             p, dt = L.guac_result_somatic_records(handle), SOMATIC_DTYPE
         elif kind == "called":
             p, dt = L.guac_result_called_alleles(handle), CALLED_DTYPE
+        elif kind == "allele_counts":
+            p, dt = L.guac_result_allele_counts(handle), ALLELE_COUNT_DTYPE
         else:
             p, dt = L.guac_result_counts(handle), COUNTS_DTYPE
         if n:
@@ -213,6 +218,8 @@ class Result:
             if self.kind == "threshold":
                 d["gt"] = (int(r["gt"][0]), int(r["gt"][1]))
                 d["tie"] = int(r["tie"])
+            elif self.kind == "allele_counts":  # VariantSupport.AlleleCount (commands/VariantSupport.scala:36-41)
+                d["count"] = int(r["count"])
             elif self.kind == "called":  # AlleleConversions.calledAlleleToADAMGenotype (AlleleConversions.scala:30-45)
                 d["gt"] = (abi.GT_REF, abi.GT_ALT)
                 d["phred"] = int(r["phred_scaled_likelihood"])
@@ -264,6 +271,42 @@ def germline_standard(ctx: Context, reads: PackedReads, loci_partitions, min_ali
     h = C.c_void_p()
     ctx._check(lib().guac_germline_standard(ctx._h, reads._h, arr, n, C.byref(prm), C.byref(h)))
     return Result(h, "called")
+
+
+def allele_counts(ctx: Context, reads: PackedReads, loci_partitions) -> Result:
+    """pileupFlatMap(reads, lociPartitions, true, VariantSupport.Caller.pileupToAlleleCounts)
+    (commands/VariantSupport.scala:93-98, 110-118): every distinct allele of every non-empty pileup with its read count."""
+    arr, n = _ranges(loci_partitions)
+    h = C.c_void_p()
+    ctx._check(lib().guac_allele_counts(ctx._h, reads._h, arr, n, C.byref(h)))
+    return Result(h, "allele_counts")
+
+
+def variant_loci(counts: np.ndarray, min_read_depth: int = 0, min_variant_allele_frequency: int = 0) -> np.ndarray:
+    """VAFHistogram.variantLociFromReads' closure (commands/VAFHistogram.scala:31-38, 215-223) over the rows of
+    pileup_counts(): loci with referenceDepth != depth, depth >= minReadDepth and variantAlleleFrequency (a Float:
+    (depth - referenceDepth).toFloat / depth) >= minVariantAlleleFrequency / 100.0.  Returns (contig, locus, vaf) rows."""
+    depth = counts["depth"].astype(np.int64)
+    refd = counts["reference_depth"].astype(np.int64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        vaf = (depth - refd).astype(np.float32) / depth.astype(np.float32)   # Float / Int -> Float
+    keep = (refd != depth) & (depth >= min_read_depth) & (vaf.astype(np.float64) >= min_variant_allele_frequency / 100.0)
+    out = np.zeros(int(keep.sum()), dtype=[("contig", "<i4"), ("locus", "<i8"), ("variant_allele_frequency", "<f4")])
+    out["contig"], out["locus"], out["variant_allele_frequency"] = counts["contig"][keep], counts["locus"][keep], vaf[keep]
+    return out
+
+
+def generate_vaf_histogram(variant_allele_frequencies: Sequence[float], bins: int) -> dict:
+    """VAFHistogram.generateVAFHistogram (commands/VAFHistogram.scala:185-194): bin = percent - percent % (100 / bins)
+    with percent = (vaf * 100).toInt in Float arithmetic; returns {bin: number of loci}."""
+    if not (1 <= bins <= 100):
+        raise ValueError("Bins should be between 1 and 100")
+    v = np.asarray(variant_allele_frequencies, dtype=np.float32)
+    percent = (v * np.float32(100)).astype(np.int64)   # Float * Int -> Float, .toInt truncates
+    width = 100 // bins
+    keys = percent - percent % width
+    uniq, cnt = np.unique(keys, return_counts=True)
+    return {int(k): int(c) for k, c in zip(uniq, cnt)}
 
 
 def pileup_counts(ctx: Context, reads: PackedReads, loci_partitions, skip_empty: bool = True) -> Result:

@@ -734,6 +734,108 @@ guac_status guac_somatic_standard(guac_ctx* ctx, const guac_reads* tumor, const 
   });
 }
 
+// pileupFlatMap(reads, ranges, true, pileupToAlleleCounts): the exact per-element walk over every requested locus
+static void run_allele_counts(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* ranges, size_t n_ranges, guac_result& res) {
+  cudaStream_t st = ctx->stream;
+  std::vector<unsigned long long> prefix(n_ranges + 1, 0);
+  for (size_t i = 0; i < n_ranges; ++i) {
+    const guac_locus_range& r = ranges[i];
+    if (r.contig < 0 || (uint32_t)r.contig >= reads.n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "locus range %zu: contig out of range", i);
+    if (r.start < 0 || r.end < r.start) fail(GUAC_ERR_INVALID_ARGUMENT, "locus range %zu: bad bounds", i);
+    prefix[i + 1] = prefix[i] + (unsigned long long)(r.end - r.start);
+  }
+  const uint64_t requested = prefix[n_ranges];
+  res.stats.reads_total = reads.n;
+  res.stats.loci_requested = requested;
+  res.stats.order_sensitive_loci = reads.order_sensitive_loci;
+  if (requested == 0 || reads.n == 0) return;
+  DevBuf<guac_locus_range> d_ranges;
+  DevBuf<unsigned long long> d_prefix;
+  h2d(ctx, d_ranges, ranges, n_ranges);
+  h2d(ctx, d_prefix, prefix.data(), prefix.size());
+  res.stats.h2d_bytes = d_ranges.bytes() + d_prefix.bytes();
+  uint64_t cap_rec = std::max<uint64_t>(4096, 2 * requested), cap_pool = kPoolDynOff + std::max<uint64_t>(65536, 8 * requested);
+  const CallParams prm{2, 0, 0, 0, 1, reads.sample};
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    if (cap_rec >= 0xFFFFFFF0ull || cap_pool >= 0xFFFFFFF0ull) fail(GUAC_ERR_UNSUPPORTED, "too many output records for one call: split the loci ranges");
+    ctx->out_rec.ensure(cap_rec * sizeof(guac_allele_count));
+    if (ctx->out_pool.ensure(cap_pool)) ctx->pool_head_ready = false;
+    CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
+    DevOut out;
+    out.trec = (guac_threshold_record*)ctx->out_rec.p;
+    out.crec = (guac_locus_counts*)ctx->out_rec.p;
+    out.cap_rec = (uint32_t)cap_rec;
+    out.pool = ctx->out_pool.p;
+    out.cap_pool = (uint32_t)cap_pool;
+    out.slow = nullptr;
+    out.cap_slow = 0;
+    out.counters = ctx->d_counters;
+    out.err = ctx->d_err;
+    CUDA_OK(cudaEventRecord(ctx->ev[0], st));
+    const uint64_t warps_needed = requested;
+    const int grid = (int)std::min<uint64_t>((warps_needed + kExactWarps - 1) / kExactWarps, (uint64_t)ctx->sm_count * 16);
+    k_allele_counts<<<grid, kExactWarps * 32, 0, st>>>(reads.view(), d_ranges.p, d_prefix.p, (uint32_t)n_ranges, prm, out);
+    CUDA_OK(cudaEventRecord(ctx->ev[1], st));
+    CUDA_OK(cudaGetLastError());
+    unsigned long long* c = ctx->h_counters;
+    CUDA_OK(cudaMemcpyAsync(c, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    check_device_error(ctx, "allele counts");
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    res.stats.exact_kernel_ms += ms;
+    res.stats.kernel_launches += 1;
+    if (c[0] > cap_rec || kPoolDynOff + c[1] > cap_pool) {
+      cap_rec = std::max<uint64_t>(cap_rec, c[0] + c[0] / 8 + 16);
+      cap_pool = std::max<uint64_t>(cap_pool, kPoolDynOff + c[1] + c[1] / 8 + 16);
+      continue;
+    }
+    const uint64_t n_rec = c[0];
+    const size_t pool_bytes = (size_t)(kPoolDynOff + c[1]), rec_bytes = (size_t)(n_rec * sizeof(guac_allele_count));
+    const size_t rec_at = (pool_bytes + 63) & ~(size_t)63;
+    res.pool = ctx->pinned;
+    res.block = ctx->pinned->take(rec_at + rec_bytes + 64, &res.block_bytes);
+    if (!res.block) fail(GUAC_ERR_OOM, "pinned host allocation of %zu bytes failed", rec_at + rec_bytes + 64);
+    unsigned char* hs = (unsigned char*)res.block;
+    unsigned char* hrec = hs + rec_at;
+    CUDA_OK(cudaMemcpyAsync(hs, ctx->out_pool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
+    if (n_rec) CUDA_OK(cudaMemcpyAsync(hrec, ctx->out_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    res.stats.d2h_bytes = pool_bytes + rec_bytes + 64;
+    res.records = hrec;
+    res.n_records = (size_t)n_rec;
+    res.bytes = hs;
+    res.n_bytes = pool_bytes;
+    if (ctx->sort_records) {
+      const uint8_t* pool = hs;
+      sort_records_canonical((guac_allele_count*)hrec, (size_t)n_rec, [pool](const guac_allele_count& a, const guac_allele_count& b) {
+        int c = memcmp(pool + a.ref_off, pool + b.ref_off, std::min(a.ref_len, b.ref_len));
+        if (c != 0) return c < 0;
+        if (a.ref_len != b.ref_len) return a.ref_len < b.ref_len;
+        c = memcmp(pool + a.alt_off, pool + b.alt_off, std::min(a.alt_len, b.alt_len));
+        if (c != 0) return c < 0;
+        return a.alt_len < b.alt_len;
+      });
+    }
+    res.stats.records = n_rec;
+    res.stats.exact_loci = requested;
+    res.stats.kernel_ms = res.stats.exact_kernel_ms;
+    return;
+  }
+  fail(GUAC_ERR_CUDA, "output buffers did not converge");
+}
+
+guac_status guac_allele_counts(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges, size_t n_ranges, guac_result** out) {
+  if (!ctx || !reads || !out || (n_ranges && !ranges)) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    std::unique_ptr<guac_result> res(new guac_result());
+    res->kind = 4;
+    run_allele_counts(ctx, *reads, ranges, n_ranges, *res);
+    *out = res.release();
+  });
+}
+
 guac_status guac_germline_standard(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges, size_t n_ranges,
                                    const guac_standard_params* params, guac_result** out) {
   if (!ctx || !reads || !params || !out || (n_ranges && !ranges)) return GUAC_ERR_INVALID_ARGUMENT;
@@ -754,6 +856,7 @@ size_t guac_result_n(const guac_result* r) {
 const guac_threshold_record* guac_result_threshold_records(const guac_result* r) { return (r && r->kind == 0) ? (const guac_threshold_record*)r->records : nullptr; }
 const guac_somatic_record* guac_result_somatic_records(const guac_result* r) { return (r && r->kind == 1) ? (const guac_somatic_record*)r->records : nullptr; }
 const guac_locus_counts* guac_result_counts(const guac_result* r) { return (r && r->kind == 2) ? r->counts.data() : nullptr; }
+const guac_allele_count* guac_result_allele_counts(const guac_result* r) { return (r && r->kind == 4) ? (const guac_allele_count*)r->records : nullptr; }
 const guac_called_allele* guac_result_called_alleles(const guac_result* r) { return (r && r->kind == 3) ? (const guac_called_allele*)r->records : nullptr; }
 const uint8_t* guac_result_bytes(const guac_result* r, size_t* n_bytes) {
   if (n_bytes) *n_bytes = r ? r->n_bytes : 0;

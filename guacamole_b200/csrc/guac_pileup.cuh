@@ -54,7 +54,7 @@ struct TileDesc {
 };
 
 struct CallParams {
-  int32_t mode;             // 0 germline threshold, 1 per-locus counts
+  int32_t mode;             // 0 germline threshold, 1 per-locus counts, 2 per-allele counts (exact kernel only)
   int32_t threshold_percent;
   int32_t emit_ref;
   int32_t emit_no_call;
@@ -858,6 +858,22 @@ __device__ void exact_locus(const DevReads& R, const int contig, const int locus
       tab[na].kind = 0; tab[na].len = 1; tab[na].ptr = 0; tab[na].base = code_base(k); tab[na].count = bc[k];
       ++na;
     }
+  if (prm.mode == 2) {  // VariantSupport.Caller.pileupToAlleleCounts (commands/VariantSupport.scala:110-118)
+    for (int k = 0; k < na; ++k) {
+      const uint32_t s = (uint32_t)atomicAdd(&out.counters[0], 1ull);
+      guac_allele_count rcd;
+      rcd.start = locus; rcd.contig = contig; rcd.sample = prm.sample; rcd.count = tab[k].count;
+      const int rl = av.ref_len(tab[k]), al = av.alt_len(tab[k]);
+      const uint32_t o = pool_alloc(out, (uint32_t)(rl + al));
+      if ((unsigned long long)o + rl + al <= out.cap_pool) {
+        for (int i = 0; i < rl; ++i) out.pool[o + i] = av.ref_at(tab[k], i);
+        for (int i = 0; i < al; ++i) out.pool[o + rl + i] = av.alt_at(tab[k], i);
+      }
+      rcd.ref_off = o; rcd.ref_len = (uint16_t)rl; rcd.alt_off = o + rl; rcd.alt_len = (uint16_t)al;
+      if (s < out.cap_rec) reinterpret_cast<guac_allele_count*>(out.trec)[s] = rcd;
+    }
+    return;
+  }
   // counts.toList.filter(count * 100 / total > threshold).sortBy(-count)  — canonical pre-order: Allele.compare
   int idx[kMaxAlleles], n = 0;
   for (int k = 0; k < na; ++k)
@@ -941,6 +957,27 @@ __global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, con
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t t = warp; t < n_loci; t += n_warps) {
     exact_locus(R, loci[t].contig, loci[t].locus, prm, out, tabs[threadIdx.x >> 5], rings[threadIdx.x >> 5]);
+    __syncwarp();
+  }
+}
+
+// per-allele counts: one warp per requested locus of the ranges (prefix[i] = loci before range i)
+__global__ void __launch_bounds__(kExactWarps * 32) k_allele_counts(DevReads R, const guac_locus_range* __restrict__ ranges,
+                                                                    const unsigned long long* __restrict__ prefix, uint32_t n_ranges,
+                                                                    CallParams prm, DevOut out) {
+  __shared__ AlleleEntry tabs[kExactWarps][kMaxAlleles];
+  __shared__ uint32_t rings[kExactWarps][64];
+  const unsigned long long n_loci = prefix[n_ranges];
+  const unsigned long long warp = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * (unsigned long long)blockDim.x) >> 5;
+  for (unsigned long long t = warp; t < n_loci; t += n_warps) {
+    uint32_t lo = 0, hi = n_ranges - 1;  // the range holding locus number t
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi + 1) >> 1;
+      if (prefix[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int contig = ranges[lo].contig;
+    const long long locus = ranges[lo].start + (long long)(t - prefix[lo]);
+    if (locus < R.contigs[contig].length) exact_locus(R, contig, (int)locus, prm, out, tabs[threadIdx.x >> 5], rings[threadIdx.x >> 5]);
     __syncwarp();
   }
 }

@@ -191,6 +191,19 @@ typedef struct guac_called_allele {
   guac_allele_evidence evidence;    /* likelihood = exp(normalised log likelihood of the most likely genotype) */
 } guac_called_allele;
 
+/* commands/VariantSupport.scala:36-41 AlleleCount as built by pileupToAlleleCounts (:110-118): one row per distinct allele
+ * of a non-empty pileup, count = elements carrying it.  Same layout as guac_threshold_record up to the last 4 bytes. */
+typedef struct guac_allele_count {
+  int64_t start;
+  int32_t contig;
+  int32_t sample;
+  uint32_t ref_off;
+  uint32_t alt_off;
+  uint16_t ref_len;
+  uint16_t alt_len;
+  int32_t count;
+} guac_allele_count;
+
 /* per-locus histogram (guac_pileup_counts): one row per visited locus */
 typedef struct guac_locus_counts {
   int64_t locus;
@@ -283,12 +296,19 @@ guac_status guac_germline_standard(guac_ctx* ctx, const guac_reads* reads, const
 guac_status guac_pileup_counts(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges,
                                size_t n_ranges, int skip_empty, guac_result** out);
 
+/* pileupFlatMap(reads, ranges, true, VariantSupport.Caller.pileupToAlleleCounts) (commands/VariantSupport.scala:93-98,
+ * 110-118): every distinct allele of every non-empty pileup with its read count, variable-length alleles
+ * included.  One warp per requested locus (the exact per-element walk): meant for the loci of a variant list. */
+guac_status guac_allele_counts(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges,
+                               size_t n_ranges, guac_result** out);
+
 /* ---- results (library-owned; pointers valid until guac_result_free) -------------------------------------- */
 size_t guac_result_n(const guac_result* r);
 const guac_threshold_record* guac_result_threshold_records(const guac_result* r); /* NULL if other kind */
 const guac_somatic_record* guac_result_somatic_records(const guac_result* r);
 const guac_locus_counts* guac_result_counts(const guac_result* r);
 const guac_called_allele* guac_result_called_alleles(const guac_result* r);
+const guac_allele_count* guac_result_allele_counts(const guac_result* r);
 const uint8_t* guac_result_bytes(const guac_result* r, size_t* n_bytes);            /* allele byte pool */
 const guac_stats* guac_result_stats(const guac_result* r);
 void guac_result_free(guac_result* r);

@@ -671,6 +671,7 @@ struct Output {
   std::vector<guac_threshold_record> threshold;
   std::vector<guac_somatic_record> somatic;
   std::vector<guac_called_allele> called;
+  std::vector<guac_allele_count> allele_counts;
   std::vector<guac_locus_counts> counts;
   std::vector<orc_element> elements;
   std::vector<orc_genotype_likelihood> likelihoods;
@@ -998,6 +999,35 @@ void call_standard_at_locus(Pileup& pileup, const guac_standard_params& p, Outpu
   }
 }
 
+// VariantSupport.Caller.pileupToAlleleCounts (commands/VariantSupport.scala:110-118): elements.groupBy(_.allele)
+void allele_counts_at_locus(Pileup& pileup, Output& out) {
+  if (pileup.elements.empty()) return;
+  std::vector<std::pair<Allele, int>> counts;  // Scala Map order is unspecified; the records are sorted afterwards
+  for (auto& e : pileup.elements) {
+    Allele a = e.allele();
+    bool found = false;
+    for (auto& c : counts)
+      if (c.first == a) {
+        ++c.second;
+        found = true;
+        break;
+      }
+    if (!found) counts.push_back({a, 1});
+  }
+  for (auto& c : counts) {
+    guac_allele_count r{};
+    r.start = pileup.locus;
+    r.contig = pileup.contig;
+    r.sample = pileup.elements.front().read->sample;  // pileup.sampleName = elements.head.read.sampleName
+    r.ref_off = out.put(c.first.ref);
+    r.ref_len = (uint16_t)c.first.ref.size();
+    r.alt_off = out.put(c.first.alt);
+    r.alt_len = (uint16_t)c.first.alt.size();
+    r.count = c.second;
+    out.allele_counts.push_back(r);
+  }
+}
+
 void counts_at_locus(Pileup& p, Output& out) {
   guac_locus_counts c{};
   c.locus = p.locus;
@@ -1131,6 +1161,11 @@ struct Engine {
         r.alt_off += base;
         out.somatic.push_back(r);
       }
+      for (auto r : o.allele_counts) {
+        r.ref_off += base;
+        r.alt_off += base;
+        out.allele_counts.push_back(r);
+      }
       for (auto r : o.called) {
         r.ref_off += base;
         r.alt_off += base;
@@ -1250,6 +1285,24 @@ int orc_germline_standard(const guac_read_batch* batch, const guac_reference* re
   });
 }
 
+int orc_allele_counts(const guac_read_batch* batch, const guac_reference* ref, const guac_locus_range* ranges,
+                      size_t n_ranges, int n_threads, orc_result** out) {
+  return guarded([&] {
+    ReadSet rs;
+    load_batch(batch, rs);
+    auto res = std::make_unique<orc_result>();
+    Engine eng;
+    eng.sets = {&rs};
+    eng.ref = ref;
+    eng.skip_empty = true;
+    eng.run(ranges, n_ranges, n_threads, res->o,
+            [](std::vector<std::unique_ptr<Pileup>>& st, Output& o) { allele_counts_at_locus(*st[0], o); });
+    sort_records(res->o.allele_counts, res->o.bytes);
+    res->o.stats.records = res->o.allele_counts.size();
+    *out = res.release();
+  });
+}
+
 int orc_pileup_counts(const guac_read_batch* batch, const guac_reference* ref, const guac_locus_range* ranges,
                       size_t n_ranges, int skip_empty, int n_threads, orc_result** out) {
   return guarded([&] {
@@ -1272,11 +1325,12 @@ int orc_pileup_counts(const guac_read_batch* batch, const guac_reference* ref, c
 
 size_t orc_result_n(const orc_result* r) {
   const Output& o = r->o;
-  return std::max({o.threshold.size(), o.somatic.size(), o.called.size(), o.counts.size(), o.elements.size(), o.likelihoods.size()});
+  return std::max({o.threshold.size(), o.somatic.size(), o.called.size(), o.allele_counts.size(), o.counts.size(), o.elements.size(), o.likelihoods.size()});
 }
 const guac_threshold_record* orc_result_threshold_records(const orc_result* r) { return r->o.threshold.data(); }
 const guac_somatic_record* orc_result_somatic_records(const orc_result* r) { return r->o.somatic.data(); }
 const guac_called_allele* orc_result_called_alleles(const orc_result* r) { return r->o.called.data(); }
+const guac_allele_count* orc_result_allele_counts(const orc_result* r) { return r->o.allele_counts.data(); }
 const guac_locus_counts* orc_result_counts(const orc_result* r) { return r->o.counts.data(); }
 const orc_element* orc_result_elements(const orc_result* r) { return r->o.elements.data(); }
 const orc_genotype_likelihood* orc_result_likelihoods(const orc_result* r) { return r->o.likelihoods.data(); }

@@ -71,6 +71,10 @@ const guac_somatic_record* orc_result_somatic_records(const orc_result* r);
 int orc_germline_standard(const guac_read_batch* batch, const guac_reference* ref, const guac_locus_range* ranges,
                           size_t n_ranges, const guac_standard_params* params, int n_threads, orc_result** out);
 const guac_called_allele* orc_result_called_alleles(const orc_result* r);
+/* pileupFlatMap(reads, ..., true, VariantSupport.Caller.pileupToAlleleCounts) — VariantSupport.scala:93-98, 110-118 */
+int orc_allele_counts(const guac_read_batch* batch, const guac_reference* ref, const guac_locus_range* ranges,
+                      size_t n_ranges, int n_threads, orc_result** out);
+const guac_allele_count* orc_result_allele_counts(const orc_result* r);
 const guac_locus_counts* orc_result_counts(const orc_result* r);
 const orc_element* orc_result_elements(const orc_result* r);
 const orc_genotype_likelihood* orc_result_likelihoods(const orc_result* r);

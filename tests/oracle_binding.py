@@ -52,6 +52,7 @@ def lib():
         _lib.orc_result_threshold_records.restype = C.POINTER(abi.ThresholdRecordC)
         _lib.orc_result_somatic_records.restype = C.POINTER(abi.SomaticRecordC)
         _lib.orc_result_called_alleles.restype = C.POINTER(abi.CalledAlleleC)
+        _lib.orc_result_allele_counts.restype = C.POINTER(abi.AlleleCountC)
         _lib.orc_result_counts.restype = C.POINTER(abi.LocusCountsC)
         _lib.orc_result_elements.restype = C.POINTER(ElementC)
         _lib.orc_result_likelihoods.restype = C.POINTER(GenotypeLikelihoodC)
@@ -60,7 +61,7 @@ def lib():
         _lib.orc_result_reference_base.restype = C.c_uint8
         _lib.orc_phred_to_success_probability.restype = C.c_double
         for f in ("orc_result_n", "orc_result_threshold_records", "orc_result_somatic_records", "orc_result_called_alleles",
-                  "orc_result_counts",
+                  "orc_result_allele_counts", "orc_result_counts",
                   "orc_result_elements", "orc_result_likelihoods", "orc_result_stats", "orc_result_free",
                   "orc_result_reference_base"):
             getattr(_lib, f).argtypes = [C.c_void_p]
@@ -126,6 +127,13 @@ class Result:
             d["_raw"] = abi.SomaticRecordC.from_buffer_copy(r)
             out.append(d)
         return out
+
+    def allele_counts(self) -> List[dict]:
+        L = lib()
+        n = L.orc_result_n(self.h)
+        p = L.orc_result_allele_counts(self.h)
+        return [dict(contig=p[i].contig, start=p[i].start, sample=p[i].sample, ref=self._s(p[i].ref_off, p[i].ref_len),
+                     alt=self._s(p[i].alt_off, p[i].alt_len), count=p[i].count) for i in range(n)]
 
     def called(self) -> List[dict]:
         L = lib()
@@ -222,6 +230,16 @@ def somatic_standard(tumor: ReadBatch, normal: ReadBatch, ranges, params=None, n
     arr = ranges_array(ranges)
     _check(lib().orc_somatic_standard(C.byref(bt), C.byref(bn), C.byref(ref) if ref else None, arr,
                                       C.c_size_t(len(ranges)), C.byref(params), n_threads, C.byref(h)))
+    return Result(h)
+
+
+def allele_counts(batch: ReadBatch, ranges, n_threads=1, reference=None) -> Result:
+    h = C.c_void_p()
+    b = batch.to_c()
+    ref, keep = reference_c(reference)
+    arr = ranges_array(ranges)
+    _check(lib().orc_allele_counts(C.byref(b), C.byref(ref) if ref else None, arr, C.c_size_t(len(ranges)), n_threads,
+                                   C.byref(h)))
     return Result(h)
 
 

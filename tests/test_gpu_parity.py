@@ -265,3 +265,26 @@ def test_no_skip_empty_and_fasta_threshold(ctx):
     got = callers.germline_threshold(ctx, reads, [(0, 0, 20)], threshold=0).genotypes()
     reads.free()
     assert got == want and any(g["start"] == 1 and g["ref"] == "A" for g in got)
+
+
+def test_allele_counts_and_variant_loci(ctx):  # VariantSupport / VAFHistogram closures
+    from guacamole_b200 import callers, synth
+    g = load_golden("gatk_mini_bundle_extract").filtered(has_md=True, non_duplicate=True).sorted()
+    c = g.contig_names.index("20")
+    syn = synth.generate([("s", 30000)], depth=25, seed=31, sample=0).to_read_batch()
+    for batch, ranges in ((g, [(c, 10006800, 10006850), (c, 10008900, 10008960), (c, 9999990, 10000010), (c, 5, 7)]),
+                          (syn, [(0, 0, 3000), (0, 12000, 12500)])):
+        want = orc.allele_counts(batch, ranges).allele_counts()
+        reads = ctx.pack(batch)
+        got = callers.allele_counts(ctx, reads, ranges).genotypes()
+        key = lambda x: (x["contig"], x["start"], x["ref"], x["alt"], x["count"])
+        assert sorted(key(x) for x in got) == sorted(key(x) for x in want)
+        assert len(got) > 50
+        # VAFHistogram.variantLociFromReads over the per-locus counts
+        wc = orc.pileup_counts(batch, ranges).counts()
+        gc = callers.pileup_counts(ctx, reads, ranges).records
+        reads.free()
+        wl, gl = callers.variant_loci(wc, 2, 5), callers.variant_loci(gc, 2, 5)
+        assert gl.tolist() == wl.tolist() and len(gl) > 0
+        assert callers.generate_vaf_histogram(gl["variant_allele_frequency"], 20) == \
+            callers.generate_vaf_histogram(wl["variant_allele_frequency"], 20)

@@ -343,3 +343,49 @@ def test_germline_standard_indels_and_filter():
     assert len(got) == 1 and got[0]["evidence"]["allele_read_depth"] == 6          # still het (2 good reference reads)
     _, got = _std([alt_lo] * 3, min_mapq=10)
     assert got == []                                                                # every element filtered: Seq.empty
+
+
+# ---- VariantSupport.pileupToAlleleCounts / VAFHistogram (commands/VariantSupport.scala:110-118, VAFHistogram.scala:31-38, 185-194)
+def test_variant_support_allele_counts():
+    """VariantSupportSuite.scala:55-108.  The suite's `computedAlleleCounts.size` exhausts the iterator, so only the NUMBER
+    of alleles per locus is really asserted there (test_variant_support_distinct_alleles); the per-allele counts it lists
+    are checked here where they agree with that (10008920, 10007174)."""
+    g = load_golden("gatk_mini_bundle_extract")
+    c = g.contig_names.index("20")
+    allr = g.filtered(has_md=True).sorted()
+    nodup = g.filtered(has_md=True, non_duplicate=True).sorted()
+    by_alt = lambda b, p: {x["alt"]: x["count"] for x in orc.allele_counts(b, [(c, p, p + 1)]).allele_counts()}
+    assert by_alt(nodup, 10008920) == {"C": 2, "CA": 1, "CAA": 1}
+    assert by_alt(allr, 10007174) == {"T": 5, "C": 3}
+    assert by_alt(allr, 1) == {}
+    r = orc.allele_counts(nodup, [(c, 10006822, 10006823)]).allele_counts()
+    assert [(x["ref"], x["alt"], x["count"]) for x in r] == [("C", "", 3), ("C", "C", 1)]   # mid-deletion + match
+    # a range: rows sorted by (locus, ref, alt), counts add up to the depth
+    r = orc.allele_counts(nodup, [(c, 10008900, 10008960)])
+    rows = r.allele_counts()
+    depth = {int(x["locus"]): int(x["depth"]) for x in orc.pileup_counts(nodup, [(c, 10008900, 10008960)]).counts()}
+    total = {}
+    for x in rows:
+        total[x["start"]] = total.get(x["start"], 0) + x["count"]
+    assert total == depth
+    assert rows == sorted(rows, key=lambda x: (x["start"], x["ref"], x["alt"]))
+
+
+def test_vaf_histogram_suite():  # VAFHistogramSuite.scala:8-42
+    from guacamole_b200.callers import generate_vaf_histogram, variant_loci, COUNTS_DTYPE
+    vafs = [0.25, 0.35, 0.4, 0.5, 0.55]
+    assert generate_vaf_histogram(vafs, 10) == {20: 1, 30: 1, 40: 1, 50: 2}
+    assert generate_vaf_histogram(vafs, 20) == {25: 1, 35: 1, 40: 1, 50: 1, 55: 1}
+    assert generate_vaf_histogram(vafs, 100) == {25: 1, 35: 1, 40: 1, 50: 1, 55: 1}
+    with pytest.raises(ValueError):
+        generate_vaf_histogram(vafs, 0)
+    # VariantLocus.apply + the two filters of variantLociFromReads on hand-made count rows
+    rows = np.zeros(4, COUNTS_DTYPE)
+    rows["locus"] = [10, 11, 12, 13]
+    rows["depth"] = [10, 10, 4, 20]
+    rows["reference_depth"] = [10, 7, 1, 19]
+    got = variant_loci(rows)
+    assert got["locus"].tolist() == [11, 12, 13]
+    assert np.allclose(got["variant_allele_frequency"], [0.3, 0.75, 0.05])
+    assert variant_loci(rows, min_read_depth=5)["locus"].tolist() == [11, 13]
+    assert variant_loci(rows, min_variant_allele_frequency=30)["locus"].tolist() == [11, 12]   # 0.3f >= 0.30 as doubles
