@@ -31,12 +31,17 @@ struct PackArgs {
   unsigned long long* counters;  // [0] order-sensitive loci resolved, [1] max reads per granule
 };
 
-// ---- K_pack_bases: ASCII bases -> (lo, hi) bit-plane pairs + non-ACGT mask ---------------------------------------------------
+// ---- K_pack_bases: ASCII bases -> (lo, hi) bit-plane pairs + non-ACGT mask (+ the qc bytes) -------------------------------
 // A CTA takes 64 consecutive reads at a time.  Their bases (and qualities) are one contiguous byte range of the raw columns:
-// it is staged into shared memory with one TMA bulk copy per column (cp.async.bulk, completion on an mbarrier), then every
-// warp packs whole reads out of shared memory: 32 bases per step, three ballots build the lo / hi / exception words.
+// it is staged into shared memory with one TMA bulk copy per column (cp.async.bulk, completion on an mbarrier).  Then
+//   pass A (qualities packed): the qc bytes are a function of (base, quality) alone, so the staged range is converted 16
+//     bytes per thread, SIMD within 32-bit words, and stored with aligned 16-byte stores;
+//   pass B: eight lanes per read, one 32-base word per lane and step: nine aligned shared-memory words realigned with byte
+//     permutes, then per 4 bases the bit of interest of every byte is gathered into a nibble with one multiply
+//     (hi = bit 2 of the ASCII code, lo = bit 1 ^ bit 2: A=0 C=1 G=2 T=3), non-ACGT bytes found with byte-wise compares.
 constexpr int kPackReads = 64;
 constexpr int kPackStageBytes = 20 * 1024;
+constexpr int kPackLanesPerRead = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -62,9 +67,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
   } while (!done);
 }
 
+// bit i of the result = bit 0 of byte i of t (t holds 0 / 1 bytes)
+__device__ __forceinline__ uint32_t gather_nibble(uint32_t t) { return (t * 0x01020408u) >> 24; }
+
+__device__ __forceinline__ uint32_t std_bytes_mask(uint32_t w) {  // 0xFF in every byte that is 'A', 'C', 'G' or 'T'
+  return __vcmpeq4(w, 0x41414141u) | __vcmpeq4(w, 0x43434343u) | __vcmpeq4(w, 0x47474747u) | __vcmpeq4(w, 0x54545454u);
+}
+
+// the read (index in [r0, r1)) that owns byte b of the raw columns
+__device__ __forceinline__ uint64_t read_of_byte(const uint64_t* __restrict__ seq_off, uint64_t r0, uint64_t r1, uint64_t b) {
+  uint64_t lo = r0, hi = r1 - 1;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi + 1) >> 1;
+    if (seq_off[mid] <= b) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(256) k_pack_bases(PackArgs A) {
-  __shared__ __align__(128) uint8_t s_seq[kPackStageBytes];
-  __shared__ __align__(128) uint8_t s_qual[kPackStageBytes];
+  __shared__ __align__(128) uint8_t s_seq[kPackStageBytes + 16];
+  __shared__ __align__(128) uint8_t s_qual[kPackStageBytes + 16];
   __shared__ __align__(8) uint64_t bar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
@@ -85,45 +107,111 @@ __global__ void __launch_bounds__(256) k_pack_bases(PackArgs A) {
       }
       mbar_wait(&bar, phase);
       phase ^= 1u;
-    }
-    for (uint64_t r = r0 + warp; r < r1; r += 8) {
-      const uint64_t s0 = A.R.seq_off[r], s1 = A.R.seq_off[r + 1];
-      const int len = (int)(s1 - s0);
-      const uint32_t p0 = A.R.rec[r].pair_off;
-      const uint8_t* sq = staged ? s_seq + (s0 - a0) : nullptr;
-      const uint8_t* qq = staged ? s_qual + (s0 - a0) : nullptr;
-      uint32_t any_exc = 0;
-      bool bad_q = false, wide_q = false;
-      for (int base = 0; base < len; base += 32) {
-        const int i = base + lane;
-        uint8_t b = 'A';
-        uint32_t q = 0;
-        if (i < len) {
-          b = staged ? sq[i] : A.R.seq[s0 + i];
-          if (have_qual) q = staged ? qq[i] : A.R.qual[s0 + i];
-        }
-        bad_q = bad_q || q > 127;
-        wide_q = wide_q || q > 63;
-        const uint32_t code = base_code(b);
-        if (have_qual && i < len) A.qc_w[s0 + i] = (uint8_t)((q & 63u) | (code << 6));
-        const bool exc = i < len && !is_std_base(b);
-        const uint32_t lo = __ballot_sync(0xFFFFFFFFu, (code & 1u) && !exc);
-        const uint32_t hi = __ballot_sync(0xFFFFFFFFu, (code & 2u) && !exc);
-        const uint32_t x = __ballot_sync(0xFFFFFFFFu, exc);
-        any_exc |= x;
-        if (lane == 0) {
-          A.pairs_w[p0 + (base >> 5)] = make_uint2(lo, hi);
-          A.xmask_w[p0 + (base >> 5)] = x;
+      // ---- pass A: qc = (quality & 63) | base code << 6, 16 bytes per thread.  The 16-byte chunks at both ends also hold
+      // bytes of the neighbouring blocks of reads: those CTAs store the very same values there.
+      if (have_qual) {
+        for (uint32_t c = threadIdx.x * 16u; c < bytes; c += 256u * 16u) {
+          const uint4 sv = *reinterpret_cast<const uint4*>(s_seq + c), qv = *reinterpret_cast<const uint4*>(s_qual + c);
+          const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w}, qw[4] = {qv.x, qv.y, qv.z, qv.w};
+          uint32_t o[4], wide = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t hi = (sw[k] >> 2) & 0x01010101u, lo = ((sw[k] >> 1) ^ (sw[k] >> 2)) & 0x01010101u;
+            o[k] = (qw[k] & 0x3F3F3F3Fu) | (lo << 6) | (hi << 7);
+            wide |= qw[k] & 0xC0C0C0C0u;
+          }
+          *reinterpret_cast<uint4*>(A.qc_w + a0 + c) = make_uint4(o[0], o[1], o[2], o[3]);
+          if (wide) {  // rare: a quality > 63 (the read leaves the one-byte path) or > 127 (rejected)
+            for (uint32_t i = 0; i < 16; ++i) {
+              const uint64_t bpos = a0 + c + i;
+              const uint32_t q = s_qual[c + i];
+              if (q > 63u && bpos >= b0 && bpos < b1) {
+                const uint64_t r = read_of_byte(A.R.seq_off, r0, r1, bpos);
+                atomicOr(&A.rec_w[r].info, kInfoWideQ);
+                if (q > 127u) report_error(A.err, GUAC_ERR_BAD_QUALITY, r);
+              }
+            }
+          }
         }
       }
-      if (__any_sync(0xFFFFFFFFu, bad_q) && lane == 0) report_error(A.err, GUAC_ERR_BAD_QUALITY, r);
-      const bool any_wide = __any_sync(0xFFFFFFFFu, wide_q);
-      if (lane == 0 && (any_exc || any_wide)) A.rec_w[r].info |= (any_exc ? kInfoHasExc : 0u) | (any_wide ? kInfoWideQ : 0u);
-      // upper-case the MD tag in place (ADAM MdTag upper-cases before parsing)
-      const uint32_t m0 = A.R.md_off[r], m1 = A.R.md_off[r + 1];
-      for (uint32_t i = m0 + lane; i < m1; i += 32) {
-        const char c = A.md_w[i];
-        if (c >= 'a' && c <= 'z') A.md_w[i] = (char)(c - 32);
+      // ---- pass B: planes, eight lanes per read
+      const int grp = lane / kPackLanesPerRead, gl = lane % kPackLanesPerRead;
+      for (uint64_t r = r0 + (uint64_t)warp * (32 / kPackLanesPerRead) + grp; r < r1; r += 8 * (32 / kPackLanesPerRead)) {
+        const uint64_t s0 = A.R.seq_off[r];
+        const int len = (int)(A.R.seq_off[r + 1] - s0);
+        const uint32_t p0 = A.R.rec[r].pair_off;
+        const uint32_t off = (uint32_t)(s0 - a0);
+        bool any_exc = false;
+        for (int wd = gl; wd * 32 < len; wd += kPackLanesPerRead) {
+          const uint32_t byte0 = off + (uint32_t)wd * 32u;          // first byte of this word in the stage
+          const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(s_seq + (byte0 & ~3u));
+          const uint32_t sel = 0x3210u + 0x1111u * (byte0 & 3u);    // byte permute: 4 bytes starting at (byte0 & 3)
+          const int nb = min(32, len - wd * 32);                    // bases of the read in this word
+          uint32_t lo = 0, hi = 0, x = 0;
+          uint32_t prev = src[0];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t next = src[k + 1];
+            const uint32_t w4 = __byte_perm(prev, next, sel);
+            prev = next;
+            const uint32_t h = (w4 >> 2) & 0x01010101u, l = ((w4 >> 1) ^ (w4 >> 2)) & 0x01010101u;
+            const uint32_t ok = std_bytes_mask(w4) & 0x01010101u;
+            hi |= gather_nibble(h & ok) << (4 * k);
+            lo |= gather_nibble(l & ok) << (4 * k);
+            x |= gather_nibble(ok ^ 0x01010101u) << (4 * k);
+          }
+          const uint32_t valid = nb >= 32 ? 0xFFFFFFFFu : ((1u << nb) - 1u);
+          lo &= valid; hi &= valid; x &= valid;
+          A.pairs_w[p0 + wd] = make_uint2(lo, hi);
+          A.xmask_w[p0 + wd] = x;
+          any_exc = any_exc || x != 0u;
+        }
+        if (any_exc) atomicOr(&A.rec_w[r].info, kInfoHasExc);
+        // upper-case the MD tag in place (ADAM MdTag upper-cases before parsing)
+        const uint32_t m0 = A.R.md_off[r], m1 = A.R.md_off[r + 1];
+        for (uint32_t i = m0 + gl; i < m1; i += kPackLanesPerRead) {
+          const char ch = A.md_w[i];
+          if (ch >= 'a' && ch <= 'z') A.md_w[i] = (char)(ch - 32);
+        }
+      }
+    } else {
+      // ---- a block of reads larger than the stage (long reads): warp per read straight from global memory
+      for (uint64_t r = r0 + warp; r < r1; r += 8) {
+        const uint64_t s0 = A.R.seq_off[r], s1 = A.R.seq_off[r + 1];
+        const int len = (int)(s1 - s0);
+        const uint32_t p0 = A.R.rec[r].pair_off;
+        uint32_t any_exc = 0;
+        bool bad_q = false, wide_q = false;
+        for (int base = 0; base < len; base += 32) {
+          const int i = base + lane;
+          uint8_t b = 'A';
+          uint32_t q = 0;
+          if (i < len) {
+            b = A.R.seq[s0 + i];
+            if (have_qual) q = A.R.qual[s0 + i];
+          }
+          bad_q = bad_q || q > 127;
+          wide_q = wide_q || q > 63;
+          const uint32_t code = base_code(b);
+          if (have_qual && i < len) A.qc_w[s0 + i] = (uint8_t)((q & 63u) | (code << 6));
+          const bool exc = i < len && !is_std_base(b);
+          const uint32_t lo = __ballot_sync(0xFFFFFFFFu, (code & 1u) && !exc);
+          const uint32_t hi = __ballot_sync(0xFFFFFFFFu, (code & 2u) && !exc);
+          const uint32_t x = __ballot_sync(0xFFFFFFFFu, exc);
+          any_exc |= x;
+          if (lane == 0) {
+            A.pairs_w[p0 + (base >> 5)] = make_uint2(lo, hi);
+            A.xmask_w[p0 + (base >> 5)] = x;
+          }
+        }
+        if (__any_sync(0xFFFFFFFFu, bad_q) && lane == 0) report_error(A.err, GUAC_ERR_BAD_QUALITY, r);
+        const bool any_wide = __any_sync(0xFFFFFFFFu, wide_q);
+        if (lane == 0 && (any_exc || any_wide)) atomicOr(&A.rec_w[r].info, (any_exc ? kInfoHasExc : 0u) | (any_wide ? kInfoWideQ : 0u));
+        const uint32_t m0 = A.R.md_off[r], m1 = A.R.md_off[r + 1];
+        for (uint32_t i = m0 + lane; i < m1; i += 32) {
+          const char c = A.md_w[i];
+          if (c >= 'a' && c <= 'z') A.md_w[i] = (char)(c - 32);
+        }
       }
     }
     __syncthreads();  // the stage buffers are reused by the next block of reads
