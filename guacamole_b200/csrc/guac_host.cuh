@@ -268,14 +268,25 @@ struct Trace {  // GUAC_TRACE=1 prints host-side phase times (diagnostics only)
   }
 };
 
-// Canonical record order (contig, start, then `tie_less` among equal loci): LSD radix sort on the 48-bit (contig, start)
-// key, groups of equal keys finished with the full comparator.  ~10x faster than std::sort with the byte-string comparator.
+// Canonical record order (contig, start, then `tie_less` among equal loci): LSD radix sort of (key, index) words on the
+// bits of the (contig, start) key that actually vary, 13 bits per pass (one contig of up to 67 M loci: two passes over
+// 8-byte words), one gather of the records, groups of equal keys finished with the full comparator.
 template <typename Rec, typename TieLess>
 void sort_records_canonical(Rec* recs, size_t n, TieLess tie_less) {
   if (n < 2) return;
   bool fits = true;
-  for (size_t i = 0; i < n && fits; ++i) fits = recs[i].contig >= 0 && recs[i].contig < 65536 && recs[i].start >= 0 && recs[i].start < (1ll << 32);
-  if (!fits) {
+  int ib = 1;  // bits of a record index
+  while (((n - 1) >> ib) != 0) ++ib;
+  uint64_t kmin = ~0ull, kmax = 0;
+  for (size_t i = 0; i < n && fits; ++i) {
+    fits = recs[i].contig >= 0 && recs[i].contig < 65536 && recs[i].start >= 0 && recs[i].start < (1ll << 32);
+    const uint64_t k = ((uint64_t)recs[i].contig << 32) | (uint64_t)recs[i].start;
+    kmin = std::min(kmin, k);
+    kmax = std::max(kmax, k);
+  }
+  int bits = 0;
+  while (fits && bits < 64 && ((kmax - kmin) >> bits) != 0) ++bits;
+  if (!fits || bits + ib > 64) {  // (key - kmin) and the record index must share one 64-bit word
     std::sort(recs, recs + n, [&](const Rec& a, const Rec& b) {
       if (a.contig != b.contig) return a.contig < b.contig;
       if (a.start != b.start) return a.start < b.start;
@@ -283,34 +294,42 @@ void sort_records_canonical(Rec* recs, size_t n, TieLess tie_less) {
     });
     return;
   }
-  std::vector<uint64_t> key(n), key2(n);
-  std::vector<uint32_t> idx(n), idx2(n);
+  bool sorted = true;  // device order is often already canonical for small outputs
+  static thread_local std::vector<uint64_t> v, v2;  // scratch kept between calls: no page faults on the hot path
+  static thread_local std::vector<unsigned char> tmp_bytes;
+  if (v.size() < n) { v.resize(n); v2.resize(n); }
   for (size_t i = 0; i < n; ++i) {
-    key[i] = ((uint64_t)recs[i].contig << 32) | (uint64_t)recs[i].start;
-    idx[i] = (uint32_t)i;
+    const uint64_t k = (((uint64_t)recs[i].contig << 32) | (uint64_t)recs[i].start) - kmin;
+    v[i] = (k << ib) | (uint64_t)i;
+    if (i && (v[i] >> ib) < (v[i - 1] >> ib)) sorted = false;
   }
-  for (int pass = 0; pass < 3; ++pass) {
-    const int shift = 16 * pass;
-    std::vector<uint32_t> count(65537, 0);
-    for (size_t i = 0; i < n; ++i) ++count[((key[i] >> shift) & 0xFFFF) + 1];
-    for (int d = 0; d < 65536; ++d) count[d + 1] += count[d];
-    for (size_t i = 0; i < n; ++i) {
-      const uint32_t pos = count[(key[i] >> shift) & 0xFFFF]++;
-      key2[pos] = key[i];
-      idx2[pos] = idx[i];
+  if (!sorted) {
+    constexpr int kDigit = 13;
+    std::vector<uint32_t> count((1u << kDigit) + 1);
+    for (int shift = ib; shift < ib + bits; shift += kDigit) {
+      std::fill(count.begin(), count.end(), 0u);
+      for (size_t i = 0; i < n; ++i) ++count[((v[i] >> shift) & ((1u << kDigit) - 1)) + 1];
+      for (uint32_t d = 0; d < (1u << kDigit); ++d) count[d + 1] += count[d];
+      for (size_t i = 0; i < n; ++i) v2[count[(v[i] >> shift) & ((1u << kDigit) - 1)]++] = v[i];
+      v.swap(v2);
     }
-    key.swap(key2);
-    idx.swap(idx2);
   }
-  std::vector<Rec> tmp(n);
-  for (size_t i = 0; i < n; ++i) tmp[i] = recs[idx[i]];
+  if (tmp_bytes.size() < n * sizeof(Rec)) tmp_bytes.resize(n * sizeof(Rec));
+  Rec* tmp = reinterpret_cast<Rec*>(tmp_bytes.data());
+  const uint64_t imask = (1ull << ib) - 1;
+  for (size_t i = 0; i < n; ++i) tmp[i] = recs[v[i] & imask];
   for (size_t i = 0; i < n;) {
     size_t j = i + 1;
-    while (j < n && key[j] == key[i]) ++j;
-    if (j - i > 1) std::sort(tmp.begin() + i, tmp.begin() + j, tie_less);
+    while (j < n && (v[j] >> ib) == (v[i] >> ib)) ++j;
+    if (j - i > 1) std::sort(tmp + i, tmp + j, tie_less);
     i = j;
   }
-  memcpy(recs, tmp.data(), n * sizeof(Rec));
+  memcpy(recs, tmp, n * sizeof(Rec));
+  if (n > (1u << 22)) {  // dense outputs: do not keep gigabytes of scratch around
+    std::vector<uint64_t>().swap(v);
+    std::vector<uint64_t>().swap(v2);
+    std::vector<unsigned char>().swap(tmp_bytes);
+  }
 }
 
 int grid_for(uint64_t n, int block, int sm_count) {
