@@ -27,7 +27,7 @@
 
 namespace guac {
 
-constexpr int kSomMaxAlleles = 10;                                           // alleles entering the genotype enumeration
+constexpr int kSomMaxAlleles = 32;                                           // alleles entering the genotype enumeration
 constexpr int kSomMaxGenotypes = kSomMaxAlleles * (kSomMaxAlleles + 1) / 2;
 #ifndef GUAC_LEAN_UNROLL
 #define GUAC_LEAN_UNROLL 3
@@ -36,7 +36,7 @@ constexpr int kSomMaxGenotypes = kSomMaxAlleles * (kSomMaxAlleles + 1) / 2;
 #define GUAC_SOM_MINB 3
 #endif
 constexpr int kLeanUnroll = GUAC_LEAN_UNROLL;                                               // reads whose element loads fly together
-constexpr int kSomTab = 24;                                                  // distinct alleles kept per sample and locus
+constexpr int kSomTab = 64;                                                  // distinct alleles kept per sample and locus
 
 // d_tables layout (doubles): succ[256] | normal (l1, l0)[256] | tumor (l1, l0)[256 mapq][256 quality] — pairs are read as double2
 constexpr int kTabSucc = 0, kTabN = 256, kTabT = 768, kTabTotal = 768 + 2 * 65536;
@@ -96,9 +96,15 @@ __device__ inline AlleleEntry as_entry(const SomAllele& a) {
   return e;
 }
 
+// per-warp scratch of the general genotype enumeration (shared memory: 528 genotypes would not fit a thread's stack)
+struct GenotypeScratch {
+  double lk[kSomMaxGenotypes];
+  uint8_t gi[kSomMaxGenotypes], gj[kSomMaxGenotypes];
+};
+
 // Likelihood.likelihoodsOfAllPossibleGenotypesFromPileup(pileup, probabilityCorrect, normalize = true), plain probabilities.
 // tab[0..n) must be sorted by Allele.compare.  Returns the number of genotypes; lk[] in the reference's (i <= j) order.
-__device__ int genotype_likelihoods(const AlleleView& av, const SomAllele* tab, int n_tab, const SampleStats& st, int* gi, int* gj,
+__device__ int genotype_likelihoods(const AlleleView& av, const SomAllele* tab, int n_tab, const SampleStats& st, uint8_t* gi, uint8_t* gj,
                                     double* lk, bool log_space = false) {
   int idx[kSomMaxAlleles], n = 0;
   for (int k = 0; k < n_tab; ++k) {  // alleles whose alternate bases are all standard (an empty alternate passes)
@@ -121,8 +127,8 @@ __device__ int genotype_likelihoods(const AlleleView& av, const SomAllele* tab, 
       const int outside_inf = st.t0inf - a.n0inf - (i == j ? 0 : b.n0inf);
       const double outside = outside_inf > 0 ? -1.0 / 0.0 : ((i == j) ? (st.t0 - a.s0) : (st.t0 - a.s0 - b.s0));
       const double agg = (i == j) ? (a.s1 + outside) : outside;
-      gi[ng] = idx[i];
-      gj[ng] = idx[j];
+      gi[ng] = (uint8_t)idx[i];
+      gj[ng] = (uint8_t)idx[j];
       lk[ng] = agg + 0.0 - nlog2;
       ++ng;
     }
@@ -136,10 +142,11 @@ __device__ int genotype_likelihoods(const AlleleView& av, const SomAllele* tab, 
 // findPotentialVariantAtLocus, tumor half: early outs + the most likely tumor genotype.  Returns true when that genotype
 // holds a variant allele (only then does the reference look at the normal sample); a1 / a2 / tumor_l describe it.
 __device__ bool tumor_most_likely(const AlleleView& avT, const SomAllele* tabT, const SampleStats& sT, int contig, int locus,
-                                  const SomParams& prm, SomOut& out, AlleleEntry* a1, AlleleEntry* a2, double* tumor_l) {
+                                  const SomParams& prm, SomOut& out, GenotypeScratch& G, AlleleEntry* a1, AlleleEntry* a2, double* tumor_l) {
   if (sT.depth == 0 || sT.depth > prm.max_read_depth || sT.ref_depth == sT.depth) return false;
-  int gi[kSomMaxGenotypes], gj[kSomMaxGenotypes];
-  double lk[kSomMaxGenotypes];
+  uint8_t* gi = G.gi;
+  uint8_t* gj = G.gj;
+  double* lk = G.lk;
   const int ng = genotype_likelihoods(avT, tabT, sT.n_alleles, sT, gi, gj, lk);
   if (ng < 0) { report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus); return false; }
   if (ng == 0) return false;
@@ -189,10 +196,11 @@ __device__ void emit_somatic(const AlleleView& avT, const AlleleEntry& a1, const
 // ... normal half: the normal sample's genotype likelihoods, summed over the genotypes holding a variant allele
 __device__ void somatic_against_normal(const AlleleView& avT, const AlleleView& avN, const AlleleEntry& a1, const AlleleEntry& a2,
                                        double tumor_l, const SomAllele* tabN, const SampleStats& sN, int contig, int locus,
-                                       const SomParams& prm, SomOut& out) {
+                                       const SomParams& prm, SomOut& out, GenotypeScratch& G) {
   if (sN.depth == 0 || sN.depth > prm.max_read_depth) return;
-  int gi[kSomMaxGenotypes], gj[kSomMaxGenotypes];
-  double lk[kSomMaxGenotypes];
+  uint8_t* gi = G.gi;
+  uint8_t* gj = G.gj;
+  double* lk = G.lk;
   const int ngn = genotype_likelihoods(avN, tabN, sN.n_alleles, sN, gi, gj, lk);
   if (ngn < 0) { report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus); return; }
   double normal_variants_total = 0.0;
@@ -204,13 +212,13 @@ __device__ void somatic_against_normal(const AlleleView& avT, const AlleleView& 
 // findPotentialVariantAtLocus once both filtered pileups are summarised.  tabT / tabN sorted by Allele.compare.
 __device__ void decide_somatic(const DevReads& RT, const AlleleView& avT, const AlleleView& avN, const SomAllele* tabT,
                                const SampleStats& sT, const SomAllele* tabN, const SampleStats& sN, int contig, int locus,
-                               const SomParams& prm, SomOut& out) {
+                               const SomParams& prm, SomOut& out, GenotypeScratch& G) {
   (void)RT;
   if (sT.depth == 0 || sN.depth == 0 || sT.depth > prm.max_read_depth || sN.depth > prm.max_read_depth) return;
   AlleleEntry a1, a2;
   double tumor_l;
-  if (!tumor_most_likely(avT, tabT, sT, contig, locus, prm, out, &a1, &a2, &tumor_l)) return;
-  somatic_against_normal(avT, avN, a1, a2, tumor_l, tabN, sN, contig, locus, prm, out);
+  if (!tumor_most_likely(avT, tabT, sT, contig, locus, prm, out, G, &a1, &a2, &tumor_l)) return;
+  somatic_against_normal(avT, avN, a1, a2, tumor_l, tabN, sN, contig, locus, prm, out, G);
 }
 
 // sort a small allele table by Allele.compare (insertion sort)
@@ -446,6 +454,7 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
   double sr1 = 0.0;
   int n_ref = 0;
   unsigned long long cnt_packed = 0;  // mismatching elements: four 16-bit fields, one per base code
+  uint32_t n_word_reads = 0;          // reads overlapping the word (bounds every counter field)
   const uint32_t rc_eff = std_ref ? (uint32_t)rcode : 4u;
   const bool fma = prm.filter_multi_allelic != 0;
   const int min_mapq = prm.min_mapq;
@@ -462,6 +471,7 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
     const bool lean_mine = overlaps && keep_mine && (my.info & kLeanMask) == kInfoSimple;
     uint32_t ov = __ballot_sync(0xFFFFFFFFu, lean_mine);
     uint32_t ov_general = __ballot_sync(0xFFFFFFFFu, overlaps && !lean_mine);
+    n_word_reads += (uint32_t)(__popc(ov) + __popc(ov_general));
     // Every lane owns one read of the batch here: it forms the address its read's byte for locus 0 would have (so the
     // per-read loop adds just the lane's locus), packs (span, mapq << 8) into one word and pulls the bytes this word's loci
     // need into the cache now, so that the loop below does not serialise one memory round trip after another.
@@ -570,7 +580,7 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
   A.ref_depth = std_ref ? A.cnt[rcode] : 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) A.seen |= A.cnt[k] > 0 ? (1u << k) : 0u;
-  if (last - first > 0xFFFFu) A.other += 1;  // the packed counters hold 16 bits: deeper granules go to the exact kernel
+  if (n_word_reads > 0xFFFFu) A.other += 1;  // the packed counters hold 16 bits: deeper pileups go to the exact kernel
   // S0 of the reference class = T0 - the other classes' S0 (every kept plain element is in exactly one class)
   double sr0 = A.t0;
 #pragma unroll
@@ -656,6 +666,7 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
 // ---- K_somatic_exact: warp per locus ----------------------------------------------------------------------------------------------
 struct ExactSmem {
   SomAllele tab[2][kSomTab];
+  GenotypeScratch G;
   uint32_t ring[64];
 };
 
@@ -810,7 +821,7 @@ __device__ bool exact_sample(const DevReads& R, int contig, int locus, const Som
   return ok;
 }
 
-constexpr int kSomExactWarps = 4;
+constexpr int kSomExactWarps = 2;
 
 __global__ void __launch_bounds__(kSomExactWarps * 32) k_somatic_exact(DevReads RT, DevReads RN, const SlowLocus* __restrict__ loci, SomParams prm,
                                                                        const double* __restrict__ tables, SomOut out) {
@@ -832,7 +843,7 @@ __global__ void __launch_bounds__(kSomExactWarps * 32) k_somatic_exact(DevReads 
         if (sN.distinct_unfiltered > 2) sN.depth = 0;
       }
       AlleleView avT{RT, refT}, avN{RN, refN};
-      decide_somatic(RT, avT, avN, S.tab[0], sT, S.tab[1], sN, contig, locus, prm, out);
+      decide_somatic(RT, avT, avN, S.tab[0], sT, S.tab[1], sN, contig, locus, prm, out, S.G);
     }
     __syncwarp();
   }
@@ -851,24 +862,38 @@ __device__ bool elem_is_allele(const DevReads& R, const Elem& e, uint8_t ref_bas
   return true;
 }
 
-constexpr int kEvidenceCap = 1024;  // supporting elements kept for the medians (deeper: medians from the first kEvidenceCap)
+// The statistics AlleleEvidence needs are over small integers (mapping quality 0..255, element quality 0..255, mismatches per
+// read): one histogram each in shared memory gives exact medians at any depth (breeze median = sort + middle element(s))
+// and the means as integer sums (breeze's running mean agrees with sum / n to an ulp).
+constexpr int kNmBins = 2048;  // reads with more MD mismatches than this are not supported by K_evidence
 
 struct EvidenceSmem {
-  float mq[kEvidenceCap], bq[kEvidenceCap];
-  int nm[kEvidenceCap];
+  int hmq[256], hbq[256], hnm[kNmBins];
   uint32_t ring[64];
-  int n;
 };
 
-__device__ double median_f(float* v, int n) {  // breeze median: sort a copy, mean of the middle two for even n
-  for (int i = 1; i < n; ++i) { float x = v[i]; int j = i; while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; --j; } v[j] = x; }
-  if (n % 2 == 1) return (double)v[(n - 1) / 2];
-  return ((double)v[n / 2 - 1] + (double)v[n / 2]) / 2;
-}
-__device__ double median_i(int* v, int n) {  // DenseVector[Int]: integer arithmetic
-  for (int i = 1; i < n; ++i) { int x = v[i]; int j = i; while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; --j; } v[j] = x; }
-  if (n % 2 == 1) return (double)v[(n - 1) / 2];
-  return (double)((v[n / 2 - 1] + v[n / 2]) / 2);
+// value of the rank-th smallest element (0-based) of a histogram; warp-cooperative, nbins a multiple of 32
+__device__ int hist_select(const int* h, int nbins, int rank) {
+  const int lane = threadIdx.x & 31, chunk = nbins >> 5;
+  int s = 0;
+  for (int k = 0; k < chunk; ++k) s += h[lane * chunk + k];
+  int incl = s;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int excl = incl - s;
+  int v = 0;
+  const bool mine = excl <= rank && rank < incl;
+  if (mine) {
+    int acc = excl;
+    for (int k = 0; k < chunk; ++k) {
+      acc += h[lane * chunk + k];
+      if (acc > rank) { v = lane * chunk + k; break; }
+    }
+  }
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+  return __shfl_sync(0xFFFFFFFFu, v, m ? __ffs(m) - 1 : 0);
 }
 
 __device__ void evidence_sample(const DevReads& R, int contig, int locus, const SomParams& prm, const uint8_t* ref, int ref_len,
@@ -878,7 +903,8 @@ __device__ void evidence_sample(const DevReads& R, int contig, int locus, const 
   bool std_ref = false;
   uint8_t ref_base = 'N';
   if (locus < ci.length) ref_base = reference_base_of(R, ci, contig, locus, &std_ref);
-  if (lane == 0) S.n = 0;
+  for (int i = lane; i < 256; i += 32) { S.hmq[i] = 0; S.hbq[i] = 0; }
+  for (int i = lane; i < kNmBins; i += 32) S.hnm[i] = 0;
   __syncwarp();
   int depth = 0, fwd = 0, adepth = 0, afwd = 0;
   uint32_t first = 0xFFFFFFFFu, last = 0;
@@ -897,22 +923,19 @@ __device__ void evidence_sample(const DevReads& R, int contig, int locus, const 
     Elem e;
     e.kind = kNone; e.base = 0; e.len = 0; e.ptr = 0; e.qual = 0;
     if (valid && classify(R, r, locus, ref_base, e) != 0) valid = false;
-    bool is = false;
     if (valid && e.kind != kNone) {
       ++depth;
       if (rec.info & kInfoPositive) ++fwd;
-      is = elem_is_allele(R, e, ref_base, ref, ref_len, alt, alt_len);
-      if (is) { ++adepth; if (rec.info & kInfoPositive) ++afwd; }
+      if (elem_is_allele(R, e, ref_base, ref, ref_len, alt, alt_len)) {
+        ++adepth;
+        if (rec.info & kInfoPositive) ++afwd;
+        const int nm = (int)R.nm[r];
+        if (nm >= kNmBins) report_error(err, GUAC_ERR_UNSUPPORTED, r);
+        atomicAdd(&S.hmq[mapq & 255], 1);
+        atomicAdd(&S.hbq[e.qual & 255], 1);
+        atomicAdd(&S.hnm[min(nm, kNmBins - 1)], 1);
+      }
     }
-    // supporting elements in read order (the mean is a running mean in element order)
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, is);
-    if (is) {
-      const int slot = S.n + __popc(m & ((1u << lane) - 1u));
-      if (slot < kEvidenceCap) { S.mq[slot] = (float)mapq; S.bq[slot] = (float)e.qual; S.nm[slot] = (int)R.nm[r]; }
-    }
-    __syncwarp();
-    if (lane == 0) S.n = min(S.n + __popc(m), kEvidenceCap);
-    __syncwarp();
   }
   for (int o = 16; o; o >>= 1) {
     depth += __shfl_xor_sync(0xFFFFFFFFu, depth, o);
@@ -920,29 +943,41 @@ __device__ void evidence_sample(const DevReads& R, int contig, int locus, const 
     adepth += __shfl_xor_sync(0xFFFFFFFFu, adepth, o);
     afwd += __shfl_xor_sync(0xFFFFFFFFu, afwd, o);
   }
+  __syncwarp();
+  const int n = adepth;
+  double mean_mq = 0, mean_bq = 0, med_mq = 0, med_bq = 0, med_nm = 0;
+  if (n > 0) {
+    long long sm = 0, sb = 0;
+    for (int i = lane; i < 256; i += 32) { sm += (long long)i * S.hmq[i]; sb += (long long)i * S.hbq[i]; }
+    for (int o = 16; o; o >>= 1) { sm += __shfl_xor_sync(0xFFFFFFFFu, sm, o); sb += __shfl_xor_sync(0xFFFFFFFFu, sb, o); }
+    mean_mq = (double)sm / (double)n;
+    mean_bq = (double)sb / (double)n;
+    if (n % 2 == 1) {
+      med_mq = (double)hist_select(S.hmq, 256, (n - 1) / 2);
+      med_bq = (double)hist_select(S.hbq, 256, (n - 1) / 2);
+      med_nm = (double)hist_select(S.hnm, kNmBins, (n - 1) / 2);
+    } else {  // mean of the middle two; DenseVector[Int] (mismatches) in integer arithmetic
+      med_mq = ((double)hist_select(S.hmq, 256, n / 2 - 1) + (double)hist_select(S.hmq, 256, n / 2)) / 2;
+      med_bq = ((double)hist_select(S.hbq, 256, n / 2 - 1) + (double)hist_select(S.hbq, 256, n / 2)) / 2;
+      med_nm = (double)((hist_select(S.hnm, kNmBins, n / 2 - 1) + hist_select(S.hnm, kNmBins, n / 2)) / 2);
+    }
+  }
   if (lane == 0) {
     ev.read_depth = depth;
     ev.allele_read_depth = adepth;
     ev.forward_depth = fwd;
     ev.allele_forward_depth = afwd;
-    const int n = S.n;
     if (n == 0) {
       const double nan = __longlong_as_double(0x7FF8000000000000ll);
       ev.mean_mapping_quality = ev.median_mapping_quality = ev.mean_base_quality = ev.median_base_quality = ev.median_mismatches_per_read = nan;
     } else {
-      double mu_m = 0.0, mu_b = 0.0;
-      for (int i = 0; i < n; ++i) {  // breeze mean: mu += (x - mu) / n
-        mu_m = mu_m + ((double)S.mq[i] - mu_m) / (double)(i + 1);
-        mu_b = mu_b + ((double)S.bq[i] - mu_b) / (double)(i + 1);
-      }
-      ev.mean_mapping_quality = mu_m;
-      ev.mean_base_quality = mu_b;
-      ev.median_mapping_quality = median_f(S.mq, n);
-      ev.median_base_quality = median_f(S.bq, n);
-      ev.median_mismatches_per_read = median_i(S.nm, n);
+      ev.mean_mapping_quality = mean_mq;
+      ev.mean_base_quality = mean_bq;
+      ev.median_mapping_quality = med_mq;
+      ev.median_base_quality = med_bq;
+      ev.median_mismatches_per_read = med_nm;
     }
   }
-  (void)err;
   __syncwarp();
 }
 
@@ -1045,7 +1080,7 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
     CUDA_OK(cudaEventRecord(ctx->ev[0], st));
     k_somatic<<<(int)tiles.size(), kSomThreads, 0, st>>>(RT, RN, d_tiles.p, prm, ctx->d_tables, (int)tumor.max_ref_span, (int)normal.max_ref_span, out);
     CUDA_OK(cudaEventRecord(ctx->ev[1], st));
-    k_somatic_exact<<<ctx->sm_count * 16, kSomExactWarps * 32, 0, st>>>(RT, RN, out.slow, prm, ctx->d_tables, out);
+    k_somatic_exact<<<ctx->sm_count * 32, kSomExactWarps * 32, 0, st>>>(RT, RN, out.slow, prm, ctx->d_tables, out);
     k_evidence<<<ctx->sm_count * 8, kEvidenceWarps * 32, 0, st>>>(RT, RN, prm, out);
     CUDA_OK(cudaEventRecord(ctx->ev[2], st));
     CUDA_OK(cudaGetLastError());

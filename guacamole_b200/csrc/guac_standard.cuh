@@ -160,8 +160,9 @@ __global__ void __launch_bounds__(kSomExactWarps * 32) k_standard_exact(DevReads
     const bool ok = exact_sample<false>(R, contig, locus, prm, tables, S.tab[0], S.ring, st, &ref_base, out.err);
     if (ok && lane == 0 && st.depth > 0) {
       AlleleView av{R, ref_base};
-      int gi[kSomMaxGenotypes], gj[kSomMaxGenotypes];
-      double lk[kSomMaxGenotypes];
+      uint8_t* gi = S.G.gi;
+      uint8_t* gj = S.G.gj;
+      double* lk = S.G.lk;
       const int ng = genotype_likelihoods(av, S.tab[0], st.n_alleles, st, gi, gj, lk, /*log_space=*/true);
       if (ng < 0) report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus);
       if (ng > 0) {
@@ -255,7 +256,7 @@ void run_standard(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range
     CUDA_OK(cudaEventRecord(ctx->ev[0], st));
     k_standard<<<(int)tiles.size(), kSomThreads, 0, st>>>(R, d_tiles.p, prm, ctx->d_tables, out);
     CUDA_OK(cudaEventRecord(ctx->ev[1], st));
-    k_standard_exact<<<ctx->sm_count * 16, kSomExactWarps * 32, 0, st>>>(R, out.slow, prm, ctx->d_tables, out);
+    k_standard_exact<<<ctx->sm_count * 32, kSomExactWarps * 32, 0, st>>>(R, out.slow, prm, ctx->d_tables, out);
     k_standard_evidence<<<ctx->sm_count * 8, kEvidenceWarps * 32, 0, st>>>(R, prm_unfiltered, out);
     CUDA_OK(cudaEventRecord(ctx->ev[2], st));
     CUDA_OK(cudaGetLastError());

@@ -167,3 +167,35 @@ def test_quality_extremes(ctx, seed):
     assert len(got) > 5000
     assert_somatic_equal(ctx, tumor, normal, [(0, 0, 29999)], max_tied=30, odds=20, min_mapq=1)
     assert_somatic_equal(ctx, tumor, normal, [(0, 0, 29999)], max_tied=30, odds=20, min_mapq=30, max_read_depth=45)
+
+
+def test_amplicon_shape_config5(ctx):
+    """BASELINE.json configs[4] at test size: 10,000x tumor and normal over an amplicon.  Every likelihood underflows (SURVEY
+    H4), the per-locus element counts pass 8 bits by far, and a call's supporting elements run into the thousands (the
+    AlleleEvidence medians are taken over all of them)."""
+    from guacamole_b200 import synth
+    contigs = [("amp", 300)]
+    tumor = synth.generate(contigs, depth=10000, seed=55, sample=1).to_read_batch()
+    normal = synth.generate(contigs, depth=10000, seed=56, sample=0).to_read_batch()
+    assert_somatic_equal(ctx, tumor, normal, [(0, 0, 299)], odds=20)
+    # a call whose supporting elements run into the thousands: medians / means over all 1,500 of them
+    alt = [make_read("TCGGTCGA", "8M", "3A4", 0, quality_scores=[10 + (i * 7) % 50] * 8, alignment_quality=20 + (i * 11) % 41)
+           for i in range(1500)]
+    ref = [make_read("TCGATCGA", "8M", "8", 0, quality_scores=[12 + (i * 5) % 45] * 8, alignment_quality=25 + (i * 3) % 36)
+           for i in range(1500)]
+    t, n = pair(alt, ref)
+    got = assert_somatic_equal(ctx, t, n, [(0, 0, 16)], odds=2).genotypes()
+    assert [(x["start"], x["ref"], x["alt"], x["tumor"]["allele_read_depth"]) for x in got] == [(3, "A", "G", 1500)]
+    # the same reads through germline-threshold (16-bit counter fields) and per-locus counts
+    from guacamole_b200 import callers
+    for b in (tumor,):
+        want = orc.germline_threshold(b, [(0, 0, 299)]).threshold()
+        reads = ctx.pack(b)
+        g = callers.germline_threshold(ctx, reads, [(0, 0, 299)]).genotypes()
+        wc = orc.pileup_counts(b, [(0, 0, 299)]).counts()
+        gc = callers.pileup_counts(ctx, reads, [(0, 0, 299)]).records
+        reads.free()
+        key = lambda x: (x["contig"], x["start"], x["ref"], x["alt"], x["gt"])
+        assert [key(x) for x in g] == [key(x) for x in want]
+        assert gc["depth"].tolist() == wc["depth"].tolist() and gc["reference_depth"].tolist() == wc["reference_depth"].tolist()
+        assert int(gc["depth"].max()) > 9000
