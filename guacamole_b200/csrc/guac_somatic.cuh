@@ -1011,6 +1011,22 @@ __global__ void __launch_bounds__(kEvidenceWarps * 32) k_evidence(DevReads RT, D
 // ---- host side ------------------------------------------------------------------------------------------------------------------------
 namespace {
 
+// Few tiles (a short contig, an amplicon) leave most SMs idle: split every 4096-loci tile into CTAs that own 256 loci each
+// (the kernels skip the words of the tile outside [locus_begin, locus_end), so a narrower range is all it takes).
+inline void split_tiles_for_occupancy(std::vector<TileDesc>& tiles, int sm_count) {
+  if (tiles.empty() || tiles.size() >= (size_t)sm_count * 4) return;
+  constexpr int kSub = 256;
+  std::vector<TileDesc> fine;
+  for (const TileDesc& t : tiles)
+    for (int lo = (t.locus_begin / kSub) * kSub; lo < t.locus_end; lo += kSub) {
+      TileDesc s = t;
+      s.locus_begin = std::max(t.locus_begin, lo);
+      s.locus_end = std::min(t.locus_end, lo + kSub);
+      if (s.locus_end > s.locus_begin) fine.push_back(s);
+    }
+  tiles.swap(fine);
+}
+
 void somatic_init_tables(guac_ctx* ctx) {
   std::vector<double> t(kTabTotal);
   for (int p = 0; p < 256; ++p) t[kTabSucc + p] = 1.0 - std::pow(10.0, -p / 10.0);  // ADAM PhredUtils.phredToSuccessProbability
@@ -1052,6 +1068,7 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
   res.stats.loci_requested = requested;
   res.stats.order_sensitive_loci = tumor.order_sensitive_loci + normal.order_sensitive_loci;
   if (tiles.empty()) return;
+  split_tiles_for_occupancy(tiles, ctx->sm_count);
   uint64_t tile_loci = 0;
   for (auto& t : tiles) tile_loci += (uint64_t)(t.locus_end - t.locus_begin);
   DevBuf<TileDesc> d_tiles;

@@ -226,6 +226,7 @@ void run_standard(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range
     res.stats.loci_visited = p.skip_empty ? 0 : requested;
     return;
   }
+  split_tiles_for_occupancy(tiles, ctx->sm_count);
   uint64_t tile_loci = 0;
   for (auto& t : tiles) tile_loci += (uint64_t)(t.locus_end - t.locus_begin);
   DevBuf<TileDesc> d_tiles;
