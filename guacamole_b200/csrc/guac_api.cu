@@ -387,10 +387,9 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     res.stats.loci_visited = prm.skip_empty ? 0 : requested;
     return;
   }
-  static bool attrs_done = false;
-  if (!attrs_done) {
+  if (!ctx->smem_attrs_done) {  // per context: function attributes belong to the context's device
     set_all_smem_attrs();
-    attrs_done = true;
+    ctx->smem_attrs_done = true;
   }
   cudaStream_t st = ctx->stream;
   const size_t rec_size = prm.mode == 1 ? sizeof(guac_locus_counts) : sizeof(guac_threshold_record);

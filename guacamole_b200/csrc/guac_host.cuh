@@ -181,6 +181,7 @@ struct guac_ctx {
   int pack_qualities = 1;
   int host_threads = 0;
   int difference_lists = 1;
+  bool smem_attrs_done = false;
   // scratch kept across calls so that a repeated call neither allocates nor rebuilds its tile list
   DevBuf<unsigned char> out_rec, out_pool, out_slow, tiles;
   std::vector<guac_locus_range> tiles_key_ranges;
