@@ -348,8 +348,10 @@ struct TrackVisitor {
   const ContigInfo& ci;
   uint64_t r;
   uint32_t pair_off;
+  bool has_exc;
   int n_mismatch = 0;
-  __device__ TrackVisitor(const PackArgs& a, const ContigInfo& c, uint64_t read, uint32_t po) : A(a), ci(c), r(read), pair_off(po) {}
+  __device__ TrackVisitor(const PackArgs& a, const ContigInfo& c, uint64_t read, uint32_t po, bool exc)
+      : A(a), ci(c), r(read), pair_off(po), has_exc(exc) {}
 
   __device__ __forceinline__ void put_base(int ref_pos, uint8_t ch) {
     if (ref_pos < 0 || ref_pos >= ci.length || !is_std_base(ch)) return;
@@ -366,28 +368,33 @@ struct TrackVisitor {
   }
   __device__ bool run(int ref_pos, int read_pos, int k) {
     // k aligned bases whose reference base equals the read base: word-parallel merge of the read's planes
-    const uint2* P = A.R.pairs + pair_off;
-    const uint32_t* X = A.R.xmask + pair_off;
-    int w0 = ref_pos >> 5, w1 = (ref_pos + k - 1) >> 5;
-    for (int w = w0; w <= w1; ++w) {
-      if (w < 0 || w >= ci.n_words) continue;
-      int wbase = w << 5;
-      int q0 = read_pos + (wbase - ref_pos);
-      uint32_t valid = bit_range(ref_pos - wbase, ref_pos + k - wbase);
-      uint32_t lo = plane_window([&](int j) { return P[j].x; }, q0);
-      uint32_t hi = plane_window([&](int j) { return P[j].y; }, q0);
-      uint32_t x = plane_window([&](int j) { return X[j]; }, q0);
-      uint32_t bits = valid & ~x;
+    const uint2* __restrict__ P = A.R.pairs + pair_off;
+    const uint32_t* __restrict__ X = A.R.xmask + pair_off;
+    const int w0 = max(ref_pos >> 5, 0), w1 = min((ref_pos + k - 1) >> 5, ci.n_words - 1);
+    int q0 = read_pos + ((w0 << 5) - ref_pos);  // read base under bit 0 of word w0
+    uint2 pa = make_uint2(0u, 0u);
+    uint32_t xa = 0;
+    if (w0 <= w1 && (q0 >> 5) >= 0) {  // the rolling window: one 8-byte plane-pair load per word
+      pa = P[q0 >> 5];
+      if (has_exc) xa = X[q0 >> 5];
+    }
+    for (int w = w0; w <= w1; ++w, q0 += 32) {
+      const int j = q0 >> 5, sh = q0 & 31;  // arithmetic shift: floor
+      const uint2 pb = P[j + 1];
+      const uint32_t xb = has_exc ? X[j + 1] : 0u;
+      const int wbase = w << 5;
+      uint32_t bits = bit_range(ref_pos - wbase, ref_pos + k - wbase) & ~__funnelshift_r(xa, xb, sh);
       if (wbase + 32 > ci.length) bits &= bit_range(0, ci.length - wbase);
-      lo &= bits;
-      hi &= bits;
+      const uint32_t lo = __funnelshift_r(pa.x, pb.x, sh) & bits, hi = __funnelshift_r(pa.y, pb.y, sh) & bits;
+      pa = pb;
+      xa = xb;
       const uint32_t gw = ci.word_off + (uint32_t)w;
       if (MODE == 0) {
         if ((A.trk_lo_w[gw] & lo) != lo) atomicOr(&A.trk_lo_w[gw], lo);
         if ((A.trk_hi_w[gw] & hi) != hi) atomicOr(&A.trk_hi_w[gw], hi);
         if ((A.trk_std_w[gw] & bits) != bits) atomicOr(&A.trk_std_w[gw], bits);
       } else {
-        uint32_t diff = bits & ((lo ^ A.trk_lo_w[gw]) | (hi ^ A.trk_hi_w[gw]));
+        const uint32_t diff = bits & ((lo ^ A.trk_lo_w[gw]) | (hi ^ A.trk_hi_w[gw]));
         if (diff) atomicOr(&A.conflict_w[gw], diff);
       }
     }
@@ -409,7 +416,8 @@ template <int MODE>
 __global__ void __launch_bounds__(128) k_md_track(PackArgs A) {
   for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < A.R.n; r += (uint64_t)gridDim.x * blockDim.x) {
     const ContigInfo ci = A.R.contigs[A.read_contig[r]];
-    TrackVisitor<MODE> v(A, ci, r, A.R.rec[r].pair_off);
+    const ReadRec rec = A.R.rec[r];
+    TrackVisitor<MODE> v(A, ci, r, rec.pair_off, (rec.info & kInfoHasExc) != 0);
     int rc = md_walk(A.R, r, v);
     if (rc) report_error(A.err, rc, r);
     if (MODE == 0) A.nm_w[r] = (uint16_t)min(v.n_mismatch, 65535);
