@@ -455,7 +455,8 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     CUDA_OK(cudaEventRecord(ctx->ev[1], st));
     // K_exact reads the number of deferred loci from the device counter: no host round trip in between
     const guac_threshold_record* tile_rec = nullptr;
-    if (zero_copy) {
+    const bool device_sort = zero_copy && ctx->sort_records;  // canonical order restored on the device (k_rec_*)
+    if (zero_copy && !device_sort) {
       CUDA_OK(cudaMemcpyAsync(ctx->d_counters + 8, ctx->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
       tile_rec = out.trec;
       out.trec = (guac_threshold_record*)((unsigned char*)res.block + rec_at_zc);
@@ -463,6 +464,22 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     k_exact_loci<<<ctx->sm_count * 16, kExactWarps * 32, 0, st>>>(R, out.slow, prm, out, tile_rec);
     CUDA_OK(cudaEventRecord(ctx->ev[2], st));
     launches += 2;
+    if (device_sort) {
+      const uint32_t n_bins = (uint32_t)reads.total_grans;
+      ctx->sort_bins.ensure(2 * ((size_t)n_bins + 1));
+      ctx->sort_rec.ensure(cap_rec * rec_size);
+      uint32_t* hist = ctx->sort_bins.p;
+      uint32_t* cursor = hist + n_bins + 1;
+      guac_threshold_record* grouped = (guac_threshold_record*)ctx->sort_rec.p;
+      CUDA_OK(cudaMemsetAsync(hist, 0, ((size_t)n_bins + 1) * sizeof(uint32_t), st));
+      k_rec_hist<<<ctx->sm_count * 4, 256, 0, st>>>(R, out.trec, ctx->d_counters, out.cap_rec, hist);
+      k_rec_scan<<<1, 1024, 0, st>>>(hist, cursor, n_bins);
+      k_rec_scatter<<<ctx->sm_count * 4, 256, 0, st>>>(R, out.trec, ctx->d_counters, out.cap_rec, cursor, grouped);
+      k_rec_finish<<<grid_for(n_bins, 256, ctx->sm_count), 256, 0, st>>>(hist, n_bins, out.pool, out.cap_pool, grouped);
+      k_rec_flush<<<ctx->sm_count * 2, 256, 0, st>>>(grouped, ctx->d_counters, out.cap_rec,
+                                                      (guac_threshold_record*)((unsigned char*)res.block + rec_at_zc));
+      launches += 5;
+    }
     CUDA_OK(cudaGetLastError());
     unsigned long long* c = ctx->h_counters;
     CUDA_OK(cudaMemcpyAsync(c, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -512,7 +529,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       res.n_records = (size_t)n_rec;
       res.bytes = hs;
       res.n_bytes = pool_bytes;
-      if (ctx->sort_records) {
+      if (ctx->sort_records && !device_sort) {
         const uint8_t* pool = hs;
         guac_threshold_record* first = (guac_threshold_record*)hrec;
         sort_records_canonical(first, (size_t)n_rec, [pool](const guac_threshold_record& a, const guac_threshold_record& b) {

@@ -183,7 +183,8 @@ struct guac_ctx {
   int difference_lists = 1;
   bool smem_attrs_done = false;
   // scratch kept across calls so that a repeated call neither allocates nor rebuilds its tile list
-  DevBuf<unsigned char> out_rec, out_pool, out_slow, tiles;
+  DevBuf<unsigned char> out_rec, out_pool, out_slow, tiles, sort_rec;
+  DevBuf<uint32_t> sort_bins;
   std::vector<guac_locus_range> tiles_key_ranges;
   const void* tiles_key_reads = nullptr;
   uint64_t tiles_key_loci = 0, n_tiles = 0;

@@ -961,6 +961,105 @@ __global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, con
   }
 }
 
+// ---- canonical record order on the device (sparse germline records) ----------------------------------------------------------
+// Records leave the kernels in atomic-counter order.  The canonical order (contig, start, sample, ref, alt) is restored with
+// a counting sort over granules — a record's granule is a monotone function of (contig, start) — followed by a small
+// insertion sort inside every granule (a granule holds a handful of sparse records), and the sorted records are streamed
+// to the pinned host block with coalesced stores.  Replaces a 4 ms host-side sort of 194 k records.
+__device__ __forceinline__ uint32_t record_bin(const DevReads& R, const guac_threshold_record& r) {
+  return R.contigs[r.contig].gran_off + (uint32_t)(r.start >> kGranuleShift);
+}
+
+__global__ void __launch_bounds__(256) k_rec_hist(DevReads R, const guac_threshold_record* __restrict__ rec, const unsigned long long* counters,
+                                                  uint32_t cap_rec, uint32_t* __restrict__ hist) {
+  const uint32_t n = (uint32_t)min(counters[0], (unsigned long long)cap_rec);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&hist[record_bin(R, rec[i])], 1u);
+}
+
+// exclusive scan of hist[0 .. n_bins] in place (one CTA; n_bins is tens of thousands), cursor = copy of the result
+__global__ void __launch_bounds__(1024) k_rec_scan(uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, uint32_t n_bins) {
+  __shared__ uint32_t warp_sum[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t base = 0; base <= n_bins; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i <= n_bins ? hist[i] : 0u;
+    uint32_t incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t w = warp_sum[lane];
+      uint32_t wi = w;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_sum[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    const uint32_t excl = carry + warp_sum[warp] + incl - v;
+    if (i <= n_bins) { hist[i] = excl; cursor[i] = excl; }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_rec_scatter(DevReads R, const guac_threshold_record* __restrict__ rec, const unsigned long long* counters,
+                                                     uint32_t cap_rec, uint32_t* __restrict__ cursor, guac_threshold_record* __restrict__ grouped) {
+  const uint32_t n = (uint32_t)min(counters[0], (unsigned long long)cap_rec);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const guac_threshold_record r = rec[i];
+    grouped[atomicAdd(&cursor[record_bin(R, r)], 1u)] = r;
+  }
+}
+
+__device__ inline bool record_less(const uint8_t* __restrict__ pool, const guac_threshold_record& a, const guac_threshold_record& b) {
+  if (a.start != b.start) return a.start < b.start;
+  if (a.sample != b.sample) return a.sample < b.sample;
+  const int nr = min((int)a.ref_len, (int)b.ref_len);
+  for (int i = 0; i < nr; ++i)
+    if (pool[a.ref_off + i] != pool[b.ref_off + i]) return pool[a.ref_off + i] < pool[b.ref_off + i];
+  if (a.ref_len != b.ref_len) return a.ref_len < b.ref_len;
+  const int na = min((int)a.alt_len, (int)b.alt_len);
+  for (int i = 0; i < na; ++i)
+    if (pool[a.alt_off + i] != pool[b.alt_off + i]) return pool[a.alt_off + i] < pool[b.alt_off + i];
+  return a.alt_len < b.alt_len;
+}
+
+// thread per granule: insertion sort of its records (starts[] = the scanned histogram)
+__global__ void __launch_bounds__(256) k_rec_finish(const uint32_t* __restrict__ starts, uint32_t n_bins, const uint8_t* __restrict__ pool, uint32_t cap_pool,
+                                                    guac_threshold_record* __restrict__ grouped) {
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_bins; g += gridDim.x * blockDim.x) {
+    const uint32_t lo = starts[g], hi = starts[g + 1];
+    for (uint32_t i = lo + 1; i < hi; ++i) {
+      const guac_threshold_record x = grouped[i];
+      if ((unsigned long long)x.alt_off + x.alt_len > cap_pool) break;  // pool overflow: the host reruns the call
+      uint32_t j = i;
+      while (j > lo && record_less(pool, x, grouped[j - 1])) {
+        grouped[j] = grouped[j - 1];
+        --j;
+      }
+      grouped[j] = x;
+    }
+  }
+}
+
+// coalesced copy of the sorted records to the pinned host block
+__global__ void __launch_bounds__(256) k_rec_flush(const guac_threshold_record* __restrict__ grouped, const unsigned long long* counters, uint32_t cap_rec,
+                                                   guac_threshold_record* __restrict__ host_rec) {
+  const unsigned long long n16 = min(counters[0], (unsigned long long)cap_rec) * (sizeof(guac_threshold_record) / 16);
+  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(grouped);
+  uint4* dst = reinterpret_cast<uint4*>(host_rec);
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 // per-allele counts: one warp per requested locus of the ranges (prefix[i] = loci before range i)
 __global__ void __launch_bounds__(kExactWarps * 32) k_allele_counts(DevReads R, const guac_locus_range* __restrict__ ranges,
                                                                     const unsigned long long* __restrict__ prefix, uint32_t n_ranges,
