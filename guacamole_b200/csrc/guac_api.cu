@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <memory>
 #include <new>
 #include <string>
@@ -34,20 +35,53 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   if (ref && ref->n_contigs != b->n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "reference and batch disagree on the number of contigs");
 
   Trace tr("pack");
-  // The raw columns go first: from page-locked caller buffers these copies are asynchronous and overlap the host pass below.
+  // The raw columns go first, on their own stream: from page-locked caller buffers these copies are asynchronous, overlap
+  // the host pass below and — the bases / qualities travel in chunks of reads — the pack kernels of the earlier chunks.
   if (n && (b->cigar_off[n] >= 0xFFFFFFFFull || b->md_off[n] >= 0xFFFFFFFFull)) fail(GUAC_ERR_UNSUPPORTED, "cigar / MD columns too large: shard the read set");
+  cudaStream_t cs = ctx->copy_stream;
+  CUDA_OK(cudaEventRecord(ctx->copy_ev[5], ctx->stream));  // buffers handed back by earlier calls may still be in use there
+  CUDA_OK(cudaStreamWaitEvent(cs, ctx->copy_ev[5], 0));
+  struct DrainOnError {  // a failed pack must not leave copies from the caller's buffers in flight
+    guac_ctx* c;
+    int pending = std::uncaught_exceptions();
+    ~DrainOnError() {
+      if (std::uncaught_exceptions() > pending) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->stream);
+      }
+    }
+  } drain{ctx};
+  out.has_qualities = ctx->pack_qualities != 0;
+  constexpr int kMaxCopyChunks = 4;
+  const int n_copy_chunks = n >= 1000000 ? kMaxCopyChunks : 1;
+  uint64_t chunk_read[kMaxCopyChunks + 1];
+  for (int k = 0; k <= n_copy_chunks; ++k) chunk_read[k] = n * (uint64_t)k / (uint64_t)n_copy_chunks;
+  auto copy_bases_chunk = [&](int k) {  // bases (+ qualities) of reads [chunk_read[k], chunk_read[k + 1]), then its event
+    const uint64_t o0 = b->seq_off[chunk_read[k]], o1 = b->seq_off[chunk_read[k + 1]];
+    if (o1 > o0) {
+      CUDA_OK(cudaMemcpyAsync(out.seq.p + o0, b->seq + o0, o1 - o0, cudaMemcpyHostToDevice, cs));
+      if (out.has_qualities) CUDA_OK(cudaMemcpyAsync(out.qual.p + o0, b->qual + o0, o1 - o0, cudaMemcpyHostToDevice, cs));
+    }
+    CUDA_OK(cudaEventRecord(ctx->copy_ev[k], cs));
+  };
+  int chunks_before_host_pass = 0;
   if (n) {
-    h2d(ctx, out.seq, b->seq, (size_t)b->seq_off[n], 64);
-    out.has_qualities = ctx->pack_qualities != 0;
-    if (out.has_qualities) h2d(ctx, out.qual, b->qual, (size_t)b->seq_off[n], 64);
-    h2d(ctx, out.cigar, b->cigar, (size_t)b->cigar_off[n], 1);
-    h2d(ctx, out.seq_off, b->seq_off, n + 1);
-    h2d(ctx, out.md, b->md, (size_t)b->md_off[n], 16);
+    h2d_on(cs, out.cigar, b->cigar, (size_t)b->cigar_off[n], 1);
+    h2d_on(cs, out.seq_off, b->seq_off, n + 1);
+    h2d_on(cs, out.md, b->md, (size_t)b->md_off[n], 16);
+    const size_t n_bases = (size_t)b->seq_off[n];
+    out.seq.alloc(n_bases + 64);
+    CUDA_OK(cudaMemsetAsync(out.seq.p + n_bases, 0, 64, cs));
+    if (out.has_qualities) {
+      out.qual.alloc(n_bases + 64);
+      CUDA_OK(cudaMemsetAsync(out.qual.p + n_bases, 0, 64, cs));
+    }
+    chunks_before_host_pass = n_copy_chunks == 1 ? 1 : 2;  // what the copy engine gets through while the host pass runs
+    for (int k = 0; k < chunks_before_host_pass; ++k) copy_bases_chunk(k);
   } else {
-    out.has_qualities = ctx->pack_qualities != 0;
     out.seq.alloc(64); out.qual.alloc(64); out.cigar.alloc(1); out.md.alloc(16);
     static const uint64_t zero = 0;
-    h2d(ctx, out.seq_off, &zero, 1);
+    h2d_on(cs, out.seq_off, &zero, 1);
   }
   // ---- host pass over the read headers: O(reads + cigar ops); everything per-base happens on the device
   // header columns are built in a pinned arena owned by the context (no page faults after the first call, fast H2D)
@@ -203,12 +237,15 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
 
   // ---- H2D of the raw columns
   cudaStream_t st = ctx->stream;
-  h2d(ctx, out.rec, rec, n + 1);
-  h2d(ctx, out.cig_off, cig_off, n + 1);
-  h2d(ctx, out.md_off, md_off, n + 1);
-  h2d(ctx, out.d_contigs, out.contigs.data(), out.contigs.size());
+  h2d_on(cs, out.rec, rec, n + 1);
+  h2d_on(cs, out.cig_off, cig_off, n + 1);
+  h2d_on(cs, out.md_off, md_off, n + 1);
+  h2d_on(cs, out.d_contigs, out.contigs.data(), out.contigs.size());
   DevBuf<uint32_t> d_read_contig, conflict, gran_count;
-  h2d(ctx, d_read_contig, read_contig, n);
+  h2d_on(cs, d_read_contig, read_contig, n);
+  CUDA_OK(cudaEventRecord(ctx->copy_ev[4], cs));  // the derived columns are on the device
+  if (n)
+    for (int k = chunks_before_host_pass; k < n_copy_chunks; ++k) copy_bases_chunk(k);
   out.pairs.alloc(pair_total + 8);
   out.xmask.alloc(pair_total + 8);
   out.nm.alloc(n);
@@ -236,10 +273,11 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     h2d(ctx, out.fasta, ref->bases, (size_t)ref->base_off[ref->n_contigs], 16);
   }
   CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
+  CUDA_OK(cudaStreamWaitEvent(st, ctx->copy_ev[4], 0));  // kernels below read the small raw columns and the derived ones
   out.h2d_bytes = out.rec.bytes() + out.cig_off.bytes() * 2 + out.cigar.bytes() + out.seq_off.bytes() + out.seq.bytes() +
                   out.qual.bytes() + out.md.bytes() + out.d_contigs.bytes() + d_read_contig.bytes() + out.fasta.bytes();
 
-  if (tr.on) cudaStreamSynchronize(st);
+  if (tr.on) { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); }
   tr.lap("alloc + h2d");
   PackArgs A;
   A.R = out.view();
@@ -264,11 +302,23 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   CUDA_OK(cudaEventRecord(ctx->ev[0], st));
   out.pack_launches = 0;
   if (n) {
-    k_pack_bases<<<(int)std::min<uint64_t>((n + kPackReads - 1) / kPackReads, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(A);
+    A.r_begin = 0;
+    A.r_end = n;
     k_granule_index<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(A);
     k_granule_max<<<grid_for(gran_off, 256, ctx->sm_count), 256, 0, st>>>(A, (uint32_t)gran_off);
-    k_md_track<0><<<grid_for(n, 128, ctx->sm_count), 128, 0, st>>>(A);
-    out.pack_launches += 4;
+    out.pack_launches += 2;
+    for (int k = 0; k < n_copy_chunks; ++k) {  // bases -> planes and the MD walk, chunk by chunk as the copies land
+      A.r_begin = chunk_read[k];
+      A.r_end = chunk_read[k + 1];
+      if (A.r_end == A.r_begin) continue;
+      const uint64_t nr = A.r_end - A.r_begin;
+      CUDA_OK(cudaStreamWaitEvent(st, ctx->copy_ev[k], 0));
+      k_pack_bases<<<(int)std::min<uint64_t>((nr + kPackReads - 1) / kPackReads, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(A);
+      k_md_track<0><<<grid_for(nr, 128, ctx->sm_count), 128, 0, st>>>(A);
+      out.pack_launches += 2;
+    }
+    A.r_begin = 0;
+    A.r_end = n;
     if (!ref) {
       k_md_track<1><<<grid_for(n, 128, ctx->sm_count), 128, 0, st>>>(A);
       k_resolve_conflicts<<<grid_for(word_off, 128, ctx->sm_count), 128, 0, st>>>(A, b->n_contigs);
@@ -596,6 +646,8 @@ guac_status guac_ctx_create(int device, guac_ctx** out) {
   guac_status s = guarded(ctx, [&] {
     CUDA_OK(cudaSetDevice(device));
     CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->copy_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
     CUDA_OK(cudaMalloc((void**)&ctx->d_err, sizeof(DevError)));
     CUDA_OK(cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(unsigned long long)));
@@ -629,6 +681,9 @@ void guac_ctx_destroy(guac_ctx* ctx) {
   ctx->out_slow.release();
   ctx->tiles.release();
   tl_dev_cache.trim();
+  for (auto& e : ctx->copy_ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -170,6 +170,8 @@ struct PinnedPool {
 struct guac_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // guac_reads_pack: host -> device copies, overlapped with the pack kernels
+  cudaEvent_t copy_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::string last_error;
   DevError* d_err = nullptr;
   unsigned long long* d_counters = nullptr;  // 16 counters
@@ -227,10 +229,14 @@ void check_device_error(guac_ctx* ctx, const char* what) {
 }
 
 template <typename T>
-void h2d(guac_ctx* ctx, DevBuf<T>& dst, const T* src, size_t n, size_t extra = 0) {
+void h2d_on(cudaStream_t s, DevBuf<T>& dst, const T* src, size_t n, size_t extra = 0) {
   dst.alloc(n + extra);
-  if (extra) CUDA_OK(cudaMemsetAsync(dst.p + n, 0, extra * sizeof(T), ctx->stream));
-  if (n) CUDA_OK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  if (extra) CUDA_OK(cudaMemsetAsync(dst.p + n, 0, extra * sizeof(T), s));
+  if (n) CUDA_OK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+}
+template <typename T>
+void h2d(guac_ctx* ctx, DevBuf<T>& dst, const T* src, size_t n, size_t extra = 0) {
+  h2d_on(ctx->stream, dst, src, n, extra);
 }
 
 unsigned char* stage(guac_ctx* ctx, size_t bytes) {

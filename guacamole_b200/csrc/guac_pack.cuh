@@ -12,6 +12,7 @@ namespace guac {
 
 struct PackArgs {
   DevReads R;            // const view
+  uint64_t r_begin, r_end;  // reads this launch handles (k_pack_bases, k_md_track<0>: launched per chunk of the host -> device copy)
   ReadRec* rec_w;        // writable aliases
   uint2* pairs_w;
   uint32_t* xmask_w;
@@ -93,8 +94,8 @@ __global__ void __launch_bounds__(256) k_pack_bases(PackArgs A) {
   __syncthreads();
   uint32_t phase = 0;
   const bool have_qual = A.R.qual != nullptr;
-  for (uint64_t r0 = (uint64_t)blockIdx.x * kPackReads; r0 < A.R.n; r0 += (uint64_t)gridDim.x * kPackReads) {
-    const uint64_t r1 = min(r0 + (uint64_t)kPackReads, A.R.n);
+  for (uint64_t r0 = A.r_begin + (uint64_t)blockIdx.x * kPackReads; r0 < A.r_end; r0 += (uint64_t)gridDim.x * kPackReads) {
+    const uint64_t r1 = min(r0 + (uint64_t)kPackReads, A.r_end);
     const uint64_t b0 = A.R.seq_off[r0], b1 = A.R.seq_off[r1];
     const uint64_t a0 = b0 & ~(uint64_t)15;                      // align the source down to 16 bytes
     const uint32_t bytes = (uint32_t)(((b1 - a0) + 15) & ~(uint64_t)15);
@@ -414,7 +415,7 @@ struct TrackVisitor {
 
 template <int MODE>
 __global__ void __launch_bounds__(128) k_md_track(PackArgs A) {
-  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < A.R.n; r += (uint64_t)gridDim.x * blockDim.x) {
+  for (uint64_t r = A.r_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < A.r_end; r += (uint64_t)gridDim.x * blockDim.x) {
     const ContigInfo ci = A.R.contigs[A.read_contig[r]];
     const ReadRec rec = A.R.rec[r];
     TrackVisitor<MODE> v(A, ci, r, rec.pair_off, (rec.info & kInfoHasExc) != 0);
