@@ -288,3 +288,19 @@ def test_allele_counts_and_variant_loci(ctx):  # VariantSupport / V
         assert gl.tolist() == wl.tolist() and len(gl) > 0
         assert callers.generate_vaf_histogram(gl["variant_allele_frequency"], 20) == \
             callers.generate_vaf_histogram(wl["variant_allele_frequency"], 20)
+
+
+def test_chunked_pack_above_a_million_reads(ctx):
+    """guac_reads_pack copies the bases of >= 1,000,000 reads in four chunks and runs k_pack_bases / k_md_track<0> per chunk
+    as they land: parity in windows around the chunk boundaries (reads n/4, n/2, 3n/4) and at both ends."""
+    from guacamole_b200 import synth
+    L = 5_300_000
+    b = synth.generate([("20", L)], depth=30, seed=4242, sample=0).to_read_batch()
+    assert len(b) >= 1_000_000
+    ranges = [(0, 0, 30_000)]
+    for k in (1, 2, 3):
+        s = int(b.start[len(b) * k // 4])
+        ranges.append((0, max(0, s - 20_000), s + 20_000))
+    ranges.append((0, L - 30_000, L - 1))
+    assert_threshold_equal(ctx, b, ranges)
+    assert_counts_equal(ctx, b, ranges)
