@@ -128,3 +128,25 @@ def test_somatic_genotype_filter_matches_oracle():
               (arr["tumor"]["mean_mapping_quality"] >= 0) & (arr["normal"]["mean_mapping_quality"] >= 0) & \
               (arr["tumor"]["median_mismatches_per_read"] <= 2 ** 31 - 1)
     assert np.array_equal(somatic_genotype_filter(arr), default)
+
+
+def test_plain_c_consumer_builds_and_runs(tmp_path):
+    """include/guac.h is the boundary a JNI / cgo / Panama shim compiles against: a plain-C program (tests/c/abi_driver.c)
+    must build with gcc -std=c99 -Wall -Werror against it, link the product library and pass its own checks."""
+    import shutil
+    import subprocess
+    import sys
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    from guacamole_b200._lib import LIB_PATH as so
+    lib()  # (raises with build instructions if the library is missing)
+    exe = str(tmp_path / "abi_driver")
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_driver.c"),
+           "-o", exe, so, "-Wl,-rpath," + os.path.dirname(so)]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    env = dict(os.environ)
+    env["CUDA_VISIBLE_DEVICES"] = ""   # the driver's last check wants a process without a device
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "abi_driver ok" in r.stdout
