@@ -86,8 +86,8 @@ __device__ __forceinline__ uint64_t read_of_byte(const uint64_t* __restrict__ se
 }
 
 __global__ void __launch_bounds__(256) k_pack_bases(PackArgs A) {
-  __shared__ __align__(128) uint8_t s_seq[kPackStageBytes + 16];
-  __shared__ __align__(128) uint8_t s_qual[kPackStageBytes + 16];
+  __shared__ __align__(128) uint8_t s_seq[kPackStageBytes + 64];   // (pass B reads whole words a little past the last read)
+  __shared__ __align__(128) uint8_t s_qual[kPackStageBytes + 64];
   __shared__ __align__(8) uint64_t bar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
