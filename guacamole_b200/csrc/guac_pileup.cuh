@@ -565,9 +565,19 @@ __device__ long md_deleted_offset(const DevReads& R, uint64_t r, int pos) {
 // PileupElement(read, locus, referenceBase) + alignment + qualityScore  (pileup/PileupElement.scala:68-171, 220-274)
 __device__ __noinline__ int classify(const DevReads& R, uint64_t r, int locus, uint8_t ref_base, Elem& e) {
   const ReadRec rec = R.rec[r];
-  const uint32_t c0 = R.cig_off[r], c1 = R.cig_off[r + 1];
   const uint8_t* seq = R.seq + R.seq_off[r];
   const uint8_t* qual = R.qual ? R.qual + R.seq_off[r] : nullptr;  // absent when packed without qualities
+  e.kind = kNone;
+  if ((rec.info & kInfoSimple) && locus >= rec.start && locus < rec.end) {
+    // one M/=/X run between clips: the element is a plain base, no CIGAR walk needed
+    const int rp = (int)(rec.info & kInfoLeadMask) + (locus - rec.start);
+    e.base = seq[rp];
+    e.qual = qual ? (int)(int8_t)qual[rp] : 0;
+    e.kind = (e.base == ref_base) ? kMatch : kMismatch;
+    e.len = 1;
+    return 0;
+  }
+  const uint32_t c0 = R.cig_off[r], c1 = R.cig_off[r + 1];
   const int read_len = (int)(R.seq_off[r + 1] - R.seq_off[r]);
   const int mapq = (int)(rec.info >> kInfoMapqShift);
   int ref_pos = rec.start, read_pos = 0;
