@@ -262,6 +262,24 @@ def somatic_standard(ctx: Context, tumor: PackedReads, normal: PackedReads, loci
     return Result(h, "somatic")
 
 
+def germline_threshold_by_sample(ctx: Context, batch: ReadBatch, loci_partitions, reference: Optional[Sequence[bytes]] = None,
+                                 **params) -> List[dict]:
+    """The reference's callers group a pileup `bySample` (pileup/Pileup.scala:49-53; GermlineThresholdCaller.scala:97) and
+    call every sample on its own elements; a packed read set holds ONE sample (its reference track is derived from its
+    own reads), so a batch of several samples is split here, packed and called sample by sample, and the records merged
+    in canonical (contig, start, sample, ref, alt) order.  Returns Result.genotypes()-style dicts."""
+    out = []
+    for s in np.unique(batch.sample):
+        sub = batch.select(np.nonzero(batch.sample == s)[0])
+        reads = ctx.pack(sub, reference)
+        try:
+            out.extend(germline_threshold(ctx, reads, loci_partitions, **params).genotypes())
+        finally:
+            reads.free()
+    out.sort(key=lambda g: (g["contig"], g["start"], g["sample"], g["ref"], g["alt"]))
+    return out
+
+
 def germline_standard(ctx: Context, reads: PackedReads, loci_partitions, min_alignment_quality: int = 1,
                       skip_empty: bool = True) -> Result:
     """pileupFlatMap(reads, lociPartitions, skipEmpty, GermlineStandard.callVariantsAtLocus(_, minAlignmentQuality))

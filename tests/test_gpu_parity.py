@@ -304,3 +304,22 @@ def test_chunked_pack_above_a_million_reads(ctx):
     ranges.append((0, L - 30_000, L - 1))
     assert_threshold_equal(ctx, b, ranges)
     assert_counts_equal(ctx, b, ranges)
+
+
+def test_by_sample_split(ctx):
+    """A batch holding two samples: the reference calls each sample on its own elements (pileup.bySample); the host side
+    splits, packs and calls per sample and merges in canonical order — the oracle does the grouping natively."""
+    from guacamole_b200 import callers, synth
+    from guacamole_b200.reads import concat
+    a = synth.generate([("s", 20000)], depth=20, seed=71, sample=0).to_read_batch()   # same seed = same reference,
+    b = synth.generate([("s", 20000)], depth=12, seed=71, sample=1).to_read_batch()   # other reads (+ tumor-only variants)
+    b.sample[:] = 1
+    both = concat([a, b])
+    both.sample_names = ["first", "second"]
+    both = both.sorted()
+    assert set(np.unique(both.sample).tolist()) == {0, 1}
+    want = orc.germline_threshold(both, [(0, 0, 19999)]).threshold()
+    got = callers.germline_threshold_by_sample(ctx, both, [(0, 0, 19999)], threshold=8)
+    key = lambda x: (x["contig"], x["start"], x["sample"], x["ref"], x["alt"], tuple(x["gt"]))
+    assert [key(x) for x in got] == [key(x) for x in want]
+    assert len({x["sample"] for x in got}) == 2
