@@ -102,6 +102,22 @@ def chrm():
     return load_golden("chrM.sorted").filtered(non_duplicate=True, has_md=True).sorted()
 
 
+def test_chrm_identical_vcf(ctx, tmp_path):
+    """BASELINE.json configs[0] end to end: the VCF written from the engine's records equals, line for line, the one written
+    from the oracle's (identical field sets after canonical sort)."""
+    from guacamole_b200 import callers, loci, vcf
+    b = chrm()
+    ranges = loci.parse_loci("all", b.contig_names, b.contig_lengths)
+    want = orc.germline_threshold(b, ranges).threshold()
+    reads = ctx.pack(b)
+    got = callers.germline_threshold(ctx, reads, ranges).genotypes()
+    reads.free()
+    vcf.write_vcf(str(tmp_path / "gpu.vcf"), got, b.contig_names, b.sample_names, b.contig_lengths)
+    vcf.write_vcf(str(tmp_path / "oracle.vcf"), want, b.contig_names, b.sample_names, b.contig_lengths)
+    g, w = open(tmp_path / "gpu.vcf").read(), open(tmp_path / "oracle.vcf").read()
+    assert g == w and g.count("\n") > 138
+
+
 def test_chrm_config1(ctx):  # BASELINE.json configs[0]: germline-threshold on chrM.sorted.bam, loci "all", threshold 8
     b = chrm()
     got = assert_threshold_equal(ctx, b, [(0, 0, 16570)])

@@ -389,3 +389,26 @@ def test_vaf_histogram_suite():  # VAFHistogramSuite.scala:8-42
     assert np.allclose(got["variant_allele_frequency"], [0.3, 0.75, 0.05])
     assert variant_loci(rows, min_read_depth=5)["locus"].tolist() == [11, 13]
     assert variant_loci(rows, min_variant_allele_frequency=30)["locus"].tolist() == [11, 12]   # 0.3f >= 0.30 as doubles
+
+
+def test_vcf_writer_on_chrm(tmp_path):
+    """"identical VCF" = identical field sets after canonical sort.  The writer turns records into sorted lines
+    (POS = start + 1, GT from the GenotypeAllele pair); here on the oracle's 138 chrM records (config 1)."""
+    from guacamole_b200 import vcf
+    b = load_golden("chrM.sorted").filtered(non_duplicate=True, has_md=True).sorted()
+    recs = orc.germline_threshold(b, [(0, 0, 16570)]).threshold()
+    lines = vcf.vcf_lines(recs, b.contig_names, b.sample_names)
+    assert len(recs) == 138 and len(lines) == 138
+    gts = [ln.split("\t")[-1] for ln in lines]
+    assert gts.count("0/1") == 120 and gts.count("1/1") == 18
+    first = lines[0].split("\t")
+    assert first[0] == b.contig_names[0] and int(first[1]) == recs[0]["start"] + 1 and first[3] == recs[0]["ref"]
+    assert [int(ln.split("\t")[1]) for ln in lines] == sorted(int(ln.split("\t")[1]) for ln in lines)
+    n = vcf.write_vcf(str(tmp_path / "chrM.vcf"), recs, b.contig_names, b.sample_names, b.contig_lengths)
+    text = open(tmp_path / "chrM.vcf").read().splitlines()
+    assert n == 138 and text[0] == "##fileformat=VCFv4.2" and text[-1] == lines[-1]
+    # called alleles carry GQ / DP / AD; an empty alternate is spelled <DEL>
+    dele = ReadBatch.from_records([make_read("TCGTCGA", "3M1D4M", "3^A4", 0)] * 3).sorted()
+    cl = vcf.vcf_lines([dict(g, gt=(0, 1)) for g in orc.germline_standard(dele, [(0, 0, 64)]).called()], dele.contig_names, dele.sample_names)
+    assert [ln.split("\t")[1:5] for ln in cl] == [["3", ".", "GA", "G"], ["4", ".", "A", "<DEL>"]]
+    assert cl[0].split("\t")[8] == "GT:GQ:DP:AD" and cl[0].split("\t")[9] == "0/1:100:3:0,3"
