@@ -806,38 +806,44 @@ __device__ void exact_locus(const DevReads& R, const int contig, const int locus
       if (snv) ++bc[base_code(e.base)];
     }
     if (prm.mode == 1) continue;
-    // everything that is not an A/C/G/T match or mismatch goes through the allele table, one element at a time
+    // everything that is not an A/C/G/T match or mismatch goes through the allele table, one DISTINCT allele per round:
+    // the first waiting lane's element is looked up (or entered) by lane 0, then every waiting lane compares its own
+    // element with that entry in parallel and the whole group is counted at once
     uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid && !snv);
     while (mask) {
       const int src = __ffs(mask) - 1;
-      mask &= mask - 1;
       Elem s;
       s.kind = __shfl_sync(0xFFFFFFFFu, e.kind, src);
       s.len = __shfl_sync(0xFFFFFFFFu, e.len, src);
       s.base = (uint8_t)__shfl_sync(0xFFFFFFFFu, (int)e.base, src);
       s.ptr = ((uint64_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)(e.ptr >> 32), src) << 32) | __shfl_sync(0xFFFFFFFFu, (uint32_t)e.ptr, src);
       s.qual = 0;
-      int found = -1;
+      int k = -1, created = 0;
       if (lane == 0) {
-        for (int k = 0; k < na; ++k)
-          if (av.same(tab[k], s)) { found = k; break; }
-        if (found >= 0) ++tab[found].count;
-        else if (na < kMaxAlleles) {
-          tab[na].kind = (s.kind == kMatch || s.kind == kMismatch) ? 0 : s.kind;
-          tab[na].len = s.len;
-          tab[na].ptr = s.ptr;
-          tab[na].base = s.base;
-          tab[na].count = 1;
+        for (int i = 0; i < na; ++i)
+          if (av.same(tab[i], s)) { k = i; break; }
+        if (k < 0 && na < kMaxAlleles) {
+          k = na;
+          created = 1;
+          tab[k].kind = (s.kind == kMatch || s.kind == kMismatch) ? 0 : s.kind;
+          tab[k].len = s.len;
+          tab[k].ptr = s.ptr;
+          tab[k].base = s.base;
+          tab[k].count = 0;
         }
       }
-      found = __shfl_sync(0xFFFFFFFFu, found, 0);
-      if (found < 0) {
-        if (na == kMaxAlleles) {
-          if (lane == 0) report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus);
-          return;
-        }
-        ++na;
+      k = __shfl_sync(0xFFFFFFFFu, k, 0);
+      created = __shfl_sync(0xFFFFFFFFu, created, 0);
+      if (k < 0) {
+        if (lane == 0) report_error(out.err, GUAC_ERR_UNSUPPORTED, ((unsigned long long)contig << 32) | (uint32_t)locus);
+        return;
       }
+      na += created;
+      __syncwarp();
+      const bool same = ((mask >> lane) & 1u) && (lane == src || av.same(tab[k], e));
+      const uint32_t grp = __ballot_sync(0xFFFFFFFFu, same);
+      if (lane == 0) tab[k].count += __popc(grp);
+      mask &= ~grp;
       __syncwarp();
     }
   }
