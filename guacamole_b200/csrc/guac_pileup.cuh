@@ -617,8 +617,13 @@ __device__ __noinline__ int classify(const DevReads& R, uint64_t r, int locus, u
     if (op_is_match_like(op) && next_op == GUAC_CIGAR_D) {
       long off = md_deleted_offset(R, r, locus + 1);
       if (off < 0 || rp < 0 || rp >= read_len) return GUAC_ERR_MISSING_MD;
-      // all next_len deleted bases must be present in the tag
-      if (md_deleted_offset(R, r, locus + next_len) != off + next_len - 1) return GUAC_ERR_MISSING_MD;
+      // all next_len deleted bases must be present in the tag: they follow contiguously (the tag was upper-cased at pack
+      // time; '^' or a digit in between is what a second walk to the last deleted base would also trip over)
+      if ((uint64_t)off + (uint64_t)next_len > (uint64_t)R.md_off[r + 1]) return GUAC_ERR_MISSING_MD;
+      for (int i = 1; i < next_len; ++i) {
+        const char ch = R.md[off + i];
+        if (ch < 'A' || ch > 'Z') return GUAC_ERR_MISSING_MD;
+      }
       e.kind = kDeletion;
       e.len = next_len;
       e.ptr = (uint64_t)off;
