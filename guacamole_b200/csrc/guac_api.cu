@@ -249,6 +249,9 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   out.pairs.alloc(pair_total + 8);
   out.xmask.alloc(pair_total + 8);
   out.nm.alloc(n);
+  out.del_start.alloc(n);
+  out.del_md.alloc(n);
+  out.del_len.alloc(n);
   out.mm.alloc(n + 1);
   if (!ctx->difference_lists) CUDA_OK(cudaMemsetAsync(out.mm.p, 0xFF, out.mm.bytes(), ctx->stream));
   if (out.has_qualities) out.qc.alloc((n ? (size_t)b->seq_off[n] : 0) + 64);
@@ -287,6 +290,9 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   A.mm_w = out.mm.p;
   A.qc_w = out.has_qualities ? out.qc.p : nullptr;
   A.nm_w = out.nm.p;
+  A.del_start_w = out.del_start.p;
+  A.del_md_w = out.del_md.p;
+  A.del_len_w = out.del_len.p;
   A.md_w = out.md.p;
   A.trk_lo_w = out.trk_lo.p;
   A.trk_hi_w = out.trk_hi.p;

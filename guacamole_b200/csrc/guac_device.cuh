@@ -76,6 +76,9 @@ struct DevReads {
   const uint32_t* md_off;
   const char* md;
   const uint16_t* nm;
+  const int32_t* del_start;   // per read: reference position of its first deleted base (-1: no deletion), its offset in the
+  const uint32_t* del_md;     //   read's MD string, and the number of contiguous deleted bases: the exact per-locus path finds
+  const uint16_t* del_len;    //   a deleted base without walking the tag (reads with several deletions walk for the others)
   const ContigInfo* contigs;
   const uint32_t* trk_lo;
   const uint32_t* trk_hi;
@@ -151,7 +154,7 @@ __device__ __forceinline__ void narrow_candidates(const DevReads& R, uint32_t& f
 // (ADAM MdTag semantics, restated in oracle/guac_oracle.cpp Read::parse_md).  The visitor gets
 //   run(ref_pos, read_pos, k)        k aligned bases where MD says "match"  (reference base == read base)
 //   mismatch(ref_pos, read_pos, ch)  MD mismatch: reference base ch
-//   deleted(ref_pos, ch)             reference base ch inside a D op
+//   deleted(ref_pos, ch, md_pos)     reference base ch inside a D op (md_pos = its offset in the read's MD string)
 //   skipped(ref_pos, len)            N op
 // and returns false from any callback to stop early.  Returns 0 or a guac_status.
 template <typename V>
@@ -218,7 +221,7 @@ __device__ int md_walk(const DevReads& R, uint64_t r, V& v) {
           ++pos;
         } else {
           ++pos;
-          if (!v.deleted(ref_pos, (uint8_t)ch)) return 0;
+          if (!v.deleted(ref_pos, (uint8_t)ch, pos - 1)) return 0;
           ++ref_pos;
           --remaining;
         }

@@ -362,7 +362,9 @@ struct guac_reads {
   DevBuf<uint64_t> seq_off, fasta_off;
   DevBuf<uint8_t> seq, qual, qc, fasta;
   DevBuf<char> md;
-  DevBuf<uint16_t> nm;
+  DevBuf<uint16_t> nm, del_len;
+  DevBuf<int32_t> del_start;
+  DevBuf<uint32_t> del_md;
   DevBuf<ContigInfo> d_contigs;
   uint64_t order_sensitive_loci = 0;
   uint64_t max_reads_per_granule = 0;
@@ -391,6 +393,9 @@ struct guac_reads {
     R.md_off = md_off.p;
     R.md = md.p;
     R.nm = nm.p;
+    R.del_start = del_start.p;
+    R.del_md = del_md.p;
+    R.del_len = del_len.p;
     R.contigs = d_contigs.p;
     R.trk_lo = trk_lo.p;
     R.trk_hi = trk_hi.p;
@@ -403,7 +408,7 @@ struct guac_reads {
   }
   uint64_t device_bytes() const {
     return rec.bytes() + cig_off.bytes() + cigar.bytes() + xmask.bytes() + md_off.bytes() + trk_lo.bytes() * 3 +
-           gran_first.bytes() * 2 + pairs.bytes() + mm.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + qc.bytes() + md.bytes() + nm.bytes() +
+           gran_first.bytes() * 2 + pairs.bytes() + mm.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + qc.bytes() + md.bytes() + nm.bytes() + del_start.bytes() + del_md.bytes() + del_len.bytes() +
            fasta.bytes();
   }
 };

@@ -19,6 +19,9 @@ struct PackArgs {
   uint4* mm_w;
   uint8_t* qc_w;         // (quality | base code << 6) per base, nullptr when qualities are not packed
   uint16_t* nm_w;
+  int32_t* del_start_w;
+  uint32_t* del_md_w;
+  uint16_t* del_len_w;
   char* md_w;
   uint32_t* trk_lo_w;
   uint32_t* trk_hi_w;
@@ -351,6 +354,7 @@ struct TrackVisitor {
   uint32_t pair_off;
   bool has_exc;
   int n_mismatch = 0;
+  int del_first = -1, del_md_pos = 0, del_n = 0;
   __device__ TrackVisitor(const PackArgs& a, const ContigInfo& c, uint64_t read, uint32_t po, bool exc)
       : A(a), ci(c), r(read), pair_off(po), has_exc(exc) {}
 
@@ -406,8 +410,12 @@ struct TrackVisitor {
     put_base(ref_pos, ch);
     return true;
   }
-  __device__ bool deleted(int ref_pos, uint8_t ch) {
+  __device__ bool deleted(int ref_pos, uint8_t ch, int md_pos) {
     put_base(ref_pos, ch);
+    if (MODE == 0) {  // remember the read's first deletion for the exact per-locus path
+      if (del_first < 0) { del_first = ref_pos; del_md_pos = md_pos; del_n = 1; }
+      else if (ref_pos == del_first + del_n && md_pos == del_md_pos + del_n) ++del_n;
+    }
     return true;
   }
   __device__ bool skipped(int, int) { return true; }
@@ -421,7 +429,12 @@ __global__ void __launch_bounds__(128) k_md_track(PackArgs A) {
     TrackVisitor<MODE> v(A, ci, r, rec.pair_off, (rec.info & kInfoHasExc) != 0);
     int rc = md_walk(A.R, r, v);
     if (rc) report_error(A.err, rc, r);
-    if (MODE == 0) A.nm_w[r] = (uint16_t)min(v.n_mismatch, 65535);
+    if (MODE == 0) {
+      A.nm_w[r] = (uint16_t)min(v.n_mismatch, 65535);
+      A.del_start_w[r] = v.del_first;
+      A.del_md_w[r] = (uint32_t)v.del_md_pos;
+      A.del_len_w[r] = (uint16_t)min(v.del_n, 65535);
+    }
   }
 }
 
@@ -446,7 +459,7 @@ struct BaseAtVisitor {
     }
     return locus > ref_pos;
   }
-  __device__ bool deleted(int ref_pos, uint8_t ch) {
+  __device__ bool deleted(int ref_pos, uint8_t ch, int) {
     if (ref_pos == locus) {
       out = ch;
       return false;

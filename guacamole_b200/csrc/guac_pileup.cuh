@@ -526,7 +526,12 @@ struct Elem {
 
 // offset into R.md of the deleted base at reference position `pos` of read r (inside a D op), or -1
 __device__ long md_deleted_offset(const DevReads& R, uint64_t r, int pos) {
-  // walk CIGAR and MD together; deleted bases of one D op are contiguous in the tag
+  {  // the read's first deletion was located at pack time (k_md_track)
+    const int d0 = R.del_start[r];
+    if (d0 < 0) return -1;
+    if (pos >= d0 && pos < d0 + (int)R.del_len[r]) return (long)(R.md_off[r] + R.del_md[r] + (uint32_t)(pos - d0));
+  }
+  // any further deletion: walk CIGAR and MD together; deleted bases of one D op are contiguous in the tag
   const ReadRec rec = R.rec[r];
   const uint32_t c0 = R.cig_off[r], c1 = R.cig_off[r + 1];
   const char* md = R.md + R.md_off[r];
