@@ -404,18 +404,15 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     const int locus = tile_lo + x;
     if (locus < td_begin || locus >= td_end) continue;
     const int total = S.cov.get(x);
-    // cheap exact reject of most dirty loci: no class (mismatch or "other") is large enough to pass the threshold, so the
-    // only allele that can pass is the reference one and nothing is emitted
+    // cheap reject of most dirty loci: the four counter fields together (every element that differs from the reference;
+    // one multiply sums them: a read adds at most one, so the sum cannot carry) are too few for any of them to pass the
+    // threshold, so the only allele that can pass is the reference one and nothing is emitted.  (The exact per-class
+    // tests follow for the loci that survive.)
     if (std_ref && !every_covered) {
-      uint32_t maxf;
-      if constexpr (sizeof(CntT) == 4) {
-        const uint32_t m = __vmaxu4((uint32_t)c, (uint32_t)c >> 16);
-        maxf = max(m & 0xFFu, (m >> 8) & 0xFFu);
-      } else {
-        const uint32_t lo2 = __vmaxu2((uint32_t)c, (uint32_t)(c >> 32));
-        maxf = max(lo2 & 0xFFFFu, lo2 >> 16);
-      }
-      if ((long long)maxf * 100 < (long long)(thr_plus_1) * total) continue;
+      uint32_t differing;
+      if constexpr (sizeof(CntT) == 4) differing = ((uint32_t)c * 0x01010101u) >> 24;
+      else differing = (uint32_t)(((unsigned long long)c * 0x0001000100010001ull) >> 48);
+      if (differing * 100u < (uint32_t)thr_plus_1 * (uint32_t)total) continue;
     }
     if (total == 0 && !all_loci) continue;  // callVariantsAtLocus returns nothing on an empty pileup
     const int o = (int)((uint32_t)c & FMASK);
