@@ -396,25 +396,14 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
   const bool every_covered = MODE == 1 || prm.emit_ref || prm.emit_no_call;
   const int thr_plus_1 = prm.threshold_percent + 1;
   const int td_contig = td.contig, td_begin = td.locus_begin, td_end = td.locus_end;
-  for (int x = lane; x < kWarpLoci; x += 32) {
+  // the per-locus work past the cheap reject: the counts row (counts mode) or callVariantsAtLocus on the SNV alleles
+  auto call_locus = [&](const int x) {
     const CntT c = S.cnt[x];
-    const int w = x >> 5, b = x & 31;   // w is warp-uniform
+    const int w = x >> 5, b = x & 31;
     const bool std_ref = (S.ref_std[w] >> b) & 1u;
-    if (c == 0 && std_ref && !every_covered) continue;  // every element matches the reference: nothing to call
     const int locus = tile_lo + x;
-    if (locus < td_begin || locus >= td_end) continue;
     const int total = S.cov.get(x);
-    // cheap reject of most dirty loci: the four counter fields together (every element that differs from the reference;
-    // one multiply sums them: a read adds at most one, so the sum cannot carry) are too few for any of them to pass the
-    // threshold, so the only allele that can pass is the reference one and nothing is emitted.  (The exact per-class
-    // tests follow for the loci that survive.)
-    if (std_ref && !every_covered) {
-      uint32_t differing;
-      if constexpr (sizeof(CntT) == 4) differing = ((uint32_t)c * 0x01010101u) >> 24;
-      else differing = (uint32_t)(((unsigned long long)c * 0x0001000100010001ull) >> 48);
-      if (differing * 100u < (uint32_t)thr_plus_1 * (uint32_t)total) continue;
-    }
-    if (total == 0 && !all_loci) continue;  // callVariantsAtLocus returns nothing on an empty pileup
+    if (total == 0 && !all_loci) return;  // callVariantsAtLocus returns nothing on an empty pileup
     const int o = (int)((uint32_t)c & FMASK);
     const int m1 = (int)((uint32_t)(c >> FB) & FMASK), m2 = (int)((uint32_t)(c >> (2 * FB)) & FMASK), m3 = (int)((uint32_t)(c >> (3 * FB)) & FMASK);
     const int rcode = (int)(((S.ref_lo[w] >> b) & 1u) | (((S.ref_hi[w] >> b) & 1u) << 1));
@@ -423,7 +412,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
       if (!std_ref && total > 0) {
         uint32_t s = (uint32_t)atomicAdd(&out.counters[2], 1ull);
         if (s < out.cap_slow) out.slow[s] = SlowLocus{td_contig, locus};
-        continue;
+        return;
       }
       uint32_t s = (uint32_t)atomicAdd(&out.counters[0], 1ull);
       if (s < out.cap_rec) {
@@ -442,7 +431,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
         g.pad_[0] = g.pad_[1] = g.pad_[2] = 0;
         out.crec[s] = g;
       }
-      continue;
+      return;
     }
     // ---- GermlineThreshold.Caller.callVariantsAtLocus on the SNV alleles -------------------------------------------------
     // count * 100 / total > threshold  <=>  count * 100 >= (threshold + 1) * total   (integers, no division)
@@ -453,10 +442,10 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     if (!exact) {
       uint32_t s = (uint32_t)atomicAdd(&out.counters[2], 1ull);
       if (s < out.cap_slow) out.slow[s] = SlowLocus{td_contig, locus};
-      continue;
+      return;
     }
     const int mref = total - o - m1 - m2 - m3;
-    if (!every_covered && !passes(max(m1, max(m2, m3)))) continue;  // no alternate allele passes
+    if (!every_covered && !passes(max(m1, max(m2, m3)))) return;  // no alternate allele passes
     // alleles in Allele.compare order (= base code order), stable-sorted by descending count: keep the best three
     int c0 = -1, c1 = -1, c2 = -1, b0 = 0, b1 = 0, n = 0;
 #pragma unroll
@@ -503,6 +492,42 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
         out.trec[s] = rcd;
       }
     }
+  };
+  // Sparse calls: the few loci of a granule that survive the reject (about three at a 1 % error rate) are parked in the
+  // (now idle) read list and called afterwards side by side, instead of one lane at a time while 31 lanes wait.
+  const bool park = MODE == 0 && !every_covered;
+  if (park) {
+    if (lane == 0) S.n_list = 0;
+    __syncwarp();
+  }
+  for (int x = lane; x < kWarpLoci; x += 32) {
+    const CntT c = S.cnt[x];
+    const int w = x >> 5, b = x & 31;   // w is warp-uniform
+    const bool std_ref = (S.ref_std[w] >> b) & 1u;
+    if (c == 0 && std_ref && !every_covered) continue;  // every element matches the reference: nothing to call
+    const int locus = tile_lo + x;
+    if (locus < td_begin || locus >= td_end) continue;
+    const int total = S.cov.get(x);
+    // cheap reject of most dirty loci: the four counter fields together (every element that differs from the reference;
+    // one multiply sums them: a read adds at most one, so the sum cannot carry) are too few for any of them to pass the
+    // threshold, so the only allele that can pass is the reference one and nothing is emitted.  (The exact per-class
+    // tests follow for the loci that survive.)
+    if (std_ref && !every_covered) {
+      uint32_t differing;
+      if constexpr (sizeof(CntT) == 4) differing = ((uint32_t)c * 0x01010101u) >> 24;
+      else differing = (uint32_t)(((unsigned long long)c * 0x0001000100010001ull) >> 48);
+      if (differing * 100u < (uint32_t)thr_plus_1 * (uint32_t)total) continue;
+    }
+    if (park) {
+      const uint32_t slot = atomicAdd(&S.n_list, 1u);
+      if (slot < (uint32_t)kListCap) { S.list[slot] = (uint32_t)x; continue; }
+    }
+    call_locus(x);
+  }
+  if (park) {
+    __syncwarp();
+    const uint32_t n_parked = min(S.n_list, (uint32_t)kListCap);
+    for (uint32_t i = lane; i < n_parked; i += 32) call_locus((int)S.list[i]);
   }
   // one atomic per warp for the visited-loci counter
   for (int o = 16; o; o >>= 1) n_visited += __shfl_xor_sync(0xFFFFFFFFu, n_visited, o);
