@@ -92,8 +92,10 @@ struct CovArray {
   __device__ __forceinline__ int get(int i) const { return PACKED ? (int)((w[index(i)] >> (16 * (i & 1))) & 0xFFFFu) : (int)w[index(i)]; }
   // inclusive scan over the granule (lane owns loci [32 lane, 32 lane + 32)); returns the bit mask of the lane's loci with
   // depth > 0 and ORs `over` when a depth exceeds `limit`
-  __device__ __forceinline__ uint32_t scan(int lane, uint32_t limit, bool& over) {
+  // `min_covered`: smallest non-zero depth among the lane's 32 loci (0xFFFFFFFF if none is covered)
+  __device__ __forceinline__ uint32_t scan(int lane, uint32_t limit, bool& over, uint32_t* min_covered = nullptr) {
     const int base = PACKED ? lane * 17 : lane * 33;
+    uint32_t mn = 0xFFFFFFFFu;
     int run = 0;
     if (PACKED) {
 #pragma unroll
@@ -121,6 +123,7 @@ struct CovArray {
         covered |= (d0 != 0u ? 1u : 0u) << (2 * k);
         covered |= (d1 != 0u ? 1u : 0u) << (2 * k + 1);
         over |= d0 > limit || d1 > limit;
+        mn = min(mn, min(d0 - 1u, d1 - 1u));  // (0 - 1 wraps to the maximum: uncovered loci do not count)
       }
     } else {
 #pragma unroll 8
@@ -129,8 +132,10 @@ struct CovArray {
         w[base + k] = (uint32_t)acc;
         covered |= (acc != 0 ? 1u : 0u) << k;
         over |= (uint32_t)acc > limit;
+        mn = min(mn, (uint32_t)acc - 1u);
       }
     }
+    if (min_covered) *min_covered = mn == 0xFFFFFFFFu ? mn : mn + 1u;
     return covered;
   }
 };
@@ -140,7 +145,7 @@ struct NoCovArray {
   __device__ __forceinline__ void start(int) {}
   __device__ __forceinline__ void end(int) {}
   __device__ __forceinline__ int get(int) const { return 0; }
-  __device__ __forceinline__ uint32_t scan(int, uint32_t, bool&) { return 0u; }
+  __device__ __forceinline__ uint32_t scan(int, uint32_t, bool&, uint32_t* = nullptr) { return 0u; }
 };
 
 template <typename CntT, int MODE>
@@ -377,10 +382,10 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
   __syncwarp();
 
   // ---- phase 2: inclusive scan of the difference array(s) -> depth (and positive-strand depth); visited loci counted here
-  uint32_t n_visited = 0;
+  uint32_t n_visited = 0, word_min_depth = 0;  // (smallest non-zero depth of the lane's word: phase 3's first reject)
   bool overflow = false;
   {
-    const uint32_t covered = S.cov.scan(lane, FMASK, overflow);  // a counter field may have wrapped: the host widens and reruns
+    const uint32_t covered = S.cov.scan(lane, FMASK, overflow, &word_min_depth);  // a counter field may have wrapped: the host widens and reruns
     if (MODE == 1) {
       bool ignore = false;
       S.pos.scan(lane, 0xFFFFFFFFu, ignore);
@@ -504,7 +509,15 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     const CntT c = S.cnt[x];
     const int w = x >> 5, b = x & 31;   // w is warp-uniform
     const bool std_ref = (S.ref_std[w] >> b) & 1u;
+    const uint32_t wmin = __shfl_sync(0xFFFFFFFFu, word_min_depth, w);
+    const uint32_t thr_word = wmin > 0x00FFFFFFu ? 0u : (uint32_t)thr_plus_1 * wmin;  // (no covered locus: no shortcut)
     if (c == 0 && std_ref && !every_covered) continue;  // every element matches the reference: nothing to call
+    // first reject without touching the depth array: a dirty locus is covered, so its depth is at least the smallest
+    // non-zero depth of its word (kept by the lane that scanned the word)
+    uint32_t differing;
+    if constexpr (sizeof(CntT) == 4) differing = ((uint32_t)c * 0x01010101u) >> 24;
+    else differing = (uint32_t)(((unsigned long long)c * 0x0001000100010001ull) >> 48);
+    if (std_ref && !every_covered && differing * 100u < thr_word) continue;
     const int locus = tile_lo + x;
     if (locus < td_begin || locus >= td_end) continue;
     const int total = S.cov.get(x);
@@ -512,12 +525,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     // one multiply sums them: a read adds at most one, so the sum cannot carry) are too few for any of them to pass the
     // threshold, so the only allele that can pass is the reference one and nothing is emitted.  (The exact per-class
     // tests follow for the loci that survive.)
-    if (std_ref && !every_covered) {
-      uint32_t differing;
-      if constexpr (sizeof(CntT) == 4) differing = ((uint32_t)c * 0x01010101u) >> 24;
-      else differing = (uint32_t)(((unsigned long long)c * 0x0001000100010001ull) >> 48);
-      if (differing * 100u < (uint32_t)thr_plus_1 * (uint32_t)total) continue;
-    }
+    if (std_ref && !every_covered && differing * 100u < (uint32_t)thr_plus_1 * (uint32_t)total) continue;
     if (park) {
       const uint32_t slot = atomicAdd(&S.n_list, 1u);
       if (slot < (uint32_t)kListCap) { S.list[slot] = (uint32_t)x; continue; }
