@@ -153,7 +153,7 @@ struct WarpSmem {
   uint32_t ref_lo[kWarpWords], ref_hi[kWarpWords], ref_std[kWarpWords];   // ref_hi must follow ref_lo
   CovArray<sizeof(CntT) == 4> cov;
   typename std::conditional<MODE == 1, CovArray<sizeof(CntT) == 4>, NoCovArray>::type pos;  // positive-strand depth (counts mode)
-  CntT cnt[kWarpLoci];
+  alignas(16) CntT cnt[kWarpLoci];  // (phase 3 reads four counter words per lane)
   uint32_t list[kListCap];
   uint32_t n_list;
   uint32_t pad_[3];
@@ -505,7 +505,40 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     if (lane == 0) S.n_list = 0;
     __syncwarp();
   }
-  for (int x = lane; x < kWarpLoci; x += 32) {
+  bool sparse_done = false;
+  if constexpr (sizeof(CntT) == 4) {
+    if (park) {
+      // sparse calls over 8-bit counter fields: four consecutive loci per lane and step (one 16-byte load), clean
+      // quadruples skipped at once
+      sparse_done = true;
+      for (int it = 0; it < kWarpLoci / 128; ++it) {
+        const int x0 = (it << 7) + (lane << 2);
+        const uint4 c4 = *reinterpret_cast<const uint4*>(&S.cnt[x0]);
+        const int w = x0 >> 5;
+        const uint32_t std4 = (S.ref_std[w] >> (x0 & 31)) & 0xFu;
+        const uint32_t wmin = __shfl_sync(0xFFFFFFFFu, word_min_depth, w);
+        const uint32_t thr_word = wmin > 0x00FFFFFFu ? 0u : (uint32_t)thr_plus_1 * wmin;  // (no covered locus: no shortcut)
+        if ((c4.x | c4.y | c4.z | c4.w) == 0u && std4 == 0xFu) continue;
+        const uint32_t cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t c = cc[k];
+          const bool std_ref = (std4 >> k) & 1u;
+          if (c == 0u && std_ref) continue;
+          const uint32_t differing = (c * 0x01010101u) >> 24;
+          if (std_ref && differing * 100u < thr_word) continue;
+          const int x = x0 + k, locus = tile_lo + x;
+          if (locus < td_begin || locus >= td_end) continue;
+          const int total = S.cov.get(x);
+          if (std_ref && differing * 100u < (uint32_t)thr_plus_1 * (uint32_t)total) continue;
+          const uint32_t slot = atomicAdd(&S.n_list, 1u);
+          if (slot < (uint32_t)kListCap) S.list[slot] = (uint32_t)x;
+          else call_locus(x);
+        }
+      }
+    }
+  }
+  for (int x = lane; x < kWarpLoci && !sparse_done; x += 32) {
     const CntT c = S.cnt[x];
     const int w = x >> 5, b = x & 31;   // w is warp-uniform
     const bool std_ref = (S.ref_std[w] >> b) & 1u;
