@@ -40,7 +40,7 @@ constexpr uint32_t kInfoWideQ = 1u << 20;       // read holds a base quality > 6
 constexpr uint32_t kInfoMmList = 1u << 21;      // mm[] holds the read's differences against the reference track
 constexpr int kInfoMapqShift = 24;
 constexpr int kMmSlots = 8;                     // differences kept per read (more: the read takes the general path)
-constexpr int kMmMaxSpan = 16383;               // offsets are 14 bits
+constexpr int kMmMaxSpan = 16379;               // offsets are 14 bits; 0xFFF0 | n in the last slot = "n entries" (n < 8)
 
 struct __align__(16) ReadRec {
   int32_t start;

@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(256) k_mismatch_lists(PackArgs A) {
       }
     }
     if (!L.ok) L.lo = L.hi = ~0ull;
+    else if (L.n < kMmSlots) L.hi = (L.hi & 0x0000FFFFFFFFFFFFull) | ((0xFFF0ull | (unsigned long long)L.n) << 48);  // the count rides in the last slot
     A.mm_w[r] = make_uint4((uint32_t)L.lo, (uint32_t)(L.lo >> 32), (uint32_t)L.hi, (uint32_t)(L.hi >> 32));
     if (L.ok) A.rec_w[r].info = rec.info | kInfoMmList;
   }

@@ -347,16 +347,18 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
       if (slot < (uint32_t)kListCap) S.list[slot] = r; else slow_now = true;
     }
     // entries are (reference offset << 2 | class); class = the counter field: 0 "other" element, 1..3 read base code ^
-    // reference base code; unused slots 0xFFFF.  A slot no lane uses ends the walk (the lists are filled from slot 0).
-    const uint32_t none = 0xFFFFFFFFu;
-    const uint32_t mmw[4] = {fast ? mm.x : none, fast ? mm.y : none, fast ? mm.z : none, fast ? mm.w : none};
+    // reference base code.  A list of fewer than 8 entries carries its length in the last slot (0xFFF0 | n).
+    const uint32_t mmw[4] = {mm.x, mm.y, mm.z, mm.w};
+    const uint32_t last_slot = mm.w >> 16;
+    const int n_mine = fast ? (last_slot >= 0xFFF0u ? (int)(last_slot & 0xFu) : kMmSlots) : 0;
+    const int n_max = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)n_mine);
     const int rel = rec.start - tile_lo;
 #pragma unroll
     for (int k = 0; k < kMmSlots; ++k) {
+      if (k >= n_max) break;  // warp-uniform
       const uint32_t e = (k & 1) ? (mmw[k >> 1] >> 16) : (mmw[k >> 1] & 0xFFFFu);
-      if (!__any_sync(0xFFFFFFFFu, e != 0xFFFFu)) break;  // warp-uniform
       const int x = rel + (int)(e >> 2);
-      if (e != 0xFFFFu && (unsigned)x < (unsigned)kWarpLoci) {
+      if (k < n_mine && (unsigned)x < (unsigned)kWarpLoci) {
         if constexpr (sizeof(CntT) == 8) atomicAdd(reinterpret_cast<unsigned long long*>(S.cnt + x), 1ull << (FB * (e & 3u)));
         else atomicAdd(S.cnt + x, (CntT)1 << (FB * (e & 3u)));
       }
