@@ -82,10 +82,13 @@ constexpr int kListCap = 64;                    // reads of one granule that nee
 template <bool PACKED>
 struct CovArray {
   static constexpr int kWords = PACKED ? (kWarpLoci / 2 + kWarpLoci / 32 + 4) : (kWarpLoci + kWarpLoci / 32 + 36);
-  uint32_t w[kWords];
+  alignas(16) uint32_t w[kWords];
   static __device__ __forceinline__ int index(int i) { return PACKED ? (i >> 1) + (i >> 5) : i + (i >> 5); }
   __device__ __forceinline__ void clear(int lane) {
-    for (int i = lane; i < kWords; i += 32) w[i] = PACKED ? 0x40004000u : 0u;
+    static_assert(kWords % 4 == 0, "cleared with 16-byte stores");
+    const uint32_t v = PACKED ? 0x40004000u : 0u;
+    uint4* w4 = reinterpret_cast<uint4*>(w);
+    for (int i = lane; i < kWords / 4; i += 32) w4[i] = make_uint4(v, v, v, v);
   }
   __device__ __forceinline__ void start(int i) { atomicAdd(&w[index(i)], PACKED ? (1u << (16 * (i & 1))) : 1u); }
   __device__ __forceinline__ void end(int i) { atomicSub(&w[index(i)], PACKED ? (1u << (16 * (i & 1))) : 1u); }
@@ -204,7 +207,10 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
   const int tile_hi = min(tile_lo + kWarpLoci, ci.n_words << 5);
 
   // ---- phase 0: clear the counter slice, stage the reference planes, candidate reads of the granule
-  for (int i = lane; i < kWarpLoci; i += 32) S.cnt[i] = 0;
+  {  // 16-byte stores (cnt is 16-byte aligned)
+    uint4* c4 = reinterpret_cast<uint4*>(S.cnt);
+    for (int i = lane; i < (int)(kWarpLoci * sizeof(CntT) / 16); i += 32) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   S.cov.clear(lane);
   if (MODE == 1) S.pos.clear(lane);
   {
