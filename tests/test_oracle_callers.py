@@ -412,3 +412,18 @@ def test_vcf_writer_on_chrm(tmp_path):
     cl = vcf.vcf_lines([dict(g, gt=(0, 1)) for g in orc.germline_standard(dele, [(0, 0, 64)]).called()], dele.contig_names, dele.sample_names)
     assert [ln.split("\t")[1:5] for ln in cl] == [["3", ".", "GA", "G"], ["4", ".", "A", "<DEL>"]]
     assert cl[0].split("\t")[8] == "GT:GQ:DP:AD" and cl[0].split("\t")[9] == "0/1:100:3:0,3"
+
+
+def test_vcf_lines_for_somatic_records():
+    """calledSomaticAlleleToADAMGenotype (AlleleConversions.scala:47-62): GT Ref/Alt, GQ = phredScaledSomaticLikelihood,
+    DP / AD from the tumor evidence."""
+    from guacamole_b200 import vcf
+    tumor = ReadBatch.from_records([make_read("TCGGTCGA", "8M", "3A4", 0)] * 3).sorted()
+    normal = ReadBatch.from_records([make_read("TCGATCGA", "8M", "8", 0)] * 3).sorted()
+    recs = orc.somatic_standard(tumor, normal, [(0, 0, 64)], orc.somatic_params(odds=2)).somatic()
+    assert [(r["start"], r["ref"], r["alt"]) for r in recs] == [(3, "A", "G")]
+    lines = vcf.vcf_lines([dict(r, gt=(abi.GT_REF, abi.GT_ALT)) for r in recs], tumor.contig_names, tumor.sample_names)
+    f = lines[0].split("\t")
+    assert f[1:5] == ["4", ".", "A", "G"] and f[8] == "GT:GQ:DP:AD"
+    gt, gq, dp, ad = f[9].split(":")
+    assert gt == "0/1" and int(gq) == recs[0]["phred"] and dp == "3" and ad == "0,3"
