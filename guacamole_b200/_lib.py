@@ -18,7 +18,7 @@ EXPORTED = [
     "guac_reads_order_sensitive_loci", "guac_reads_h2d_bytes", "guac_reads_pack_kernel_ms",
     "guac_germline_threshold", "guac_somatic_standard", "guac_germline_standard", "guac_pileup_counts",
     "guac_allele_counts", "guac_result_allele_counts",
-    "guac_result_n", "guac_result_threshold_records", "guac_result_somatic_records", "guac_result_counts",
+    "guac_result_n", "guac_result_threshold_records", "guac_result_compact_records", "guac_result_somatic_records", "guac_result_counts",
     "guac_result_called_alleles",
     "guac_result_bytes", "guac_result_stats", "guac_result_free", "guac_partition_loci_uniformly",
     "guac_somatic_genotype_filter",
@@ -79,6 +79,8 @@ def lib():
     L.guac_result_n.restype = C.c_size_t
     L.guac_result_threshold_records.argtypes = [vp]
     L.guac_result_threshold_records.restype = C.POINTER(abi.ThresholdRecordC)
+    L.guac_result_compact_records.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]
+    L.guac_result_compact_records.restype = C.c_size_t
     L.guac_result_somatic_records.argtypes = [vp]
     L.guac_result_somatic_records.restype = C.POINTER(abi.SomaticRecordC)
     L.guac_result_counts.argtypes = [vp]

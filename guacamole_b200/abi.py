@@ -5,7 +5,7 @@ compiled library (guac_abi_sizeof).  No torch types cross this boundary.
 """
 import ctypes as C
 
-GUAC_ABI_VERSION = 1
+GUAC_ABI_VERSION = 2
 
 # guac_status
 OK = 0

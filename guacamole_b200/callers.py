@@ -165,26 +165,11 @@ class Result:
         L = lib()
         self.kind = kind
         self._h = _ResultHandle(handle)
-        n = L.guac_result_n(handle)
+        self._n = int(L.guac_result_n(handle))
+        self._records = None
         nb = C.c_size_t()
         bp = L.guac_result_bytes(handle, C.byref(nb))
         self.stats = abi.struct_to_dict(L.guac_result_stats(handle).contents)
-        if kind == "threshold":
-            p, dt = L.guac_result_threshold_records(handle), THRESHOLD_DTYPE
-        elif kind == "somatic":
-            p, dt = L.guac_result_somatic_records(handle), SOMATIC_DTYPE
-        elif kind == "called":
-            p, dt = L.guac_result_called_alleles(handle), CALLED_DTYPE
-        elif kind == "allele_counts":
-            p, dt = L.guac_result_allele_counts(handle), ALLELE_COUNT_DTYPE
-        else:
-            p, dt = L.guac_result_counts(handle), COUNTS_DTYPE
-        if n:
-            raw = (C.c_uint8 * (n * dt.itemsize)).from_address(C.cast(p, C.c_void_p).value)
-            raw._owner = self._h  # the view keeps the library buffer alive (no reference cycle through self)
-            self.records = np.frombuffer(raw, dtype=np.uint8).view(dt)
-        else:
-            self.records = np.zeros(0, dt)
         if nb.value:
             rawb = (C.c_uint8 * nb.value).from_address(C.cast(bp, C.c_void_p).value)
             rawb._owner = self._h
@@ -192,18 +177,51 @@ class Result:
         else:
             self._bytes = memoryview(b"")
 
+    def _view(self, p, n, dt):
+        if not n:
+            return np.zeros(0, dt)
+        raw = (C.c_uint8 * (n * dt.itemsize)).from_address(C.cast(p, C.c_void_p).value)
+        raw._owner = self._h  # the view keeps the library buffer alive (no reference cycle through self)
+        return np.frombuffer(raw, dtype=np.uint8).view(dt)
+
+    @property
+    def records(self) -> np.ndarray:
+        """The records as a structured array over the library's buffer.  For germline-threshold results the library builds
+        the guac_threshold_record view on this first access (the records crossed the bus in compact form, see compact())."""
+        if self._records is None:
+            L, h = lib(), self._h.h
+            if self.kind == "threshold":
+                p, dt = L.guac_result_threshold_records(h), THRESHOLD_DTYPE
+            elif self.kind == "somatic":
+                p, dt = L.guac_result_somatic_records(h), SOMATIC_DTYPE
+            elif self.kind == "called":
+                p, dt = L.guac_result_called_alleles(h), CALLED_DTYPE
+            elif self.kind == "allele_counts":
+                p, dt = L.guac_result_allele_counts(h), ALLELE_COUNT_DTYPE
+            else:
+                p, dt = L.guac_result_counts(h), COUNTS_DTYPE
+            self._records = self._view(p, self._n, dt)
+        return self._records
+
+    def compact(self):
+        """guac_result_compact_records: (compact u64 records, general guac_threshold_record array, sample)."""
+        L = lib()
+        pc, pg, ng, sm = C.c_void_p(), C.c_void_p(), C.c_size_t(), C.c_int32()
+        n = L.guac_result_compact_records(self._h.h, C.byref(pc), C.byref(pg), C.byref(ng), C.byref(sm))
+        return (self._view(pc, int(n), np.dtype("<u8")), self._view(pg, int(ng.value), THRESHOLD_DTYPE), int(sm.value))
+
     @property
     def bytes(self) -> bytes:
         return bytes(self._bytes)
 
     def free(self):
         """Detach from the library buffers (copying what is still referenced) and release them now."""
-        self.records = self.records.copy()
+        self._records = self.records.copy()
         self._bytes = memoryview(bytes(self._bytes))
         self._h.release()
 
     def __len__(self):
-        return len(self.records)
+        return self._n
 
     def _s(self, off, ln):
         return bytes(self._bytes[int(off):int(off) + int(ln)]).decode("latin1")

@@ -18,10 +18,78 @@
 #include "guac_host.cuh"
 #include "guac_pack.cuh"
 #include "guac_pileup.cuh"
+#include "guac_tile.cuh"
 #include "guac_somatic.cuh"
 #include "guac_standard.cuh"
 
 namespace {
+
+
+// ---- per-granule difference streams (k_expand, guac_tile.cuh) -------------------------------------------------------------------
+// One launch builds every granule's stream.  The stream buffer is sized from an estimate and the start / end counters are
+// stored as nibbles first: a launch that ran out of either (counters[2] / [3]) is repeated with what it asked for.
+void launch_expand(guac_ctx* ctx, guac_reads& rd, bool huge, uint64_t cap_entries) {
+  cudaStream_t st = ctx->stream;
+  const uint64_t grans = rd.total_grans;
+  cap_entries = (cap_entries + 7) & ~7ull;
+  rd.gs_hdr.alloc(grans + 1);
+  rd.gs_diffs.alloc(cap_entries + 8);
+  rd.gs_dd.alloc(grans * kGranuleLoci * (rd.gs_wide ? 4 : 1) + 16);
+  rd.gs_dp.alloc(grans * kGranuleLoci * (rd.gs_wide ? 4 : 1) + 16);
+  CUDA_OK(cudaMemsetAsync(ctx->d_counters + 2, 0, 2 * sizeof(unsigned long long), st));
+  if (!grans) return;
+  ExpandArgs E;
+  E.R = rd.view();
+  E.hdr_w = rd.gs_hdr.p;
+  E.diffs_w = rd.gs_diffs.p;
+  E.dd_w = rd.gs_dd.p;
+  E.dp_w = rd.gs_dp.p;
+  E.cap_diffs = cap_entries;
+  E.g_begin = 0;
+  E.g_end = (uint32_t)grans;
+  E.n_contigs = rd.n_contigs;
+  E.wide = rd.gs_wide ? 1 : 0;
+  E.counters = ctx->d_counters;
+  E.err = ctx->d_err;
+  const int ctas = (int)((grans + kExpandWarps - 1) / kExpandWarps);
+  if (!ctx->expand_attrs_done) {
+    CUDA_OK(cudaFuncSetAttribute(k_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kExpandWarps * sizeof(ExpandSmem<false>))));
+    CUDA_OK(cudaFuncSetAttribute(k_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kExpandWarps * sizeof(ExpandSmem<true>))));
+    ctx->expand_attrs_done = true;
+  }
+  CUDA_OK(cudaEventRecord(ctx->ev[2], st));
+  if (huge) k_expand<true><<<ctas, kExpandWarps * 32, kExpandWarps * sizeof(ExpandSmem<true>), st>>>(E);
+  else k_expand<false><<<ctas, kExpandWarps * 32, kExpandWarps * sizeof(ExpandSmem<false>), st>>>(E);
+  CUDA_OK(cudaEventRecord(ctx->ev[3], st));
+  CUDA_OK(cudaGetLastError());
+  rd.gs_entries = cap_entries;
+}
+
+// After a launch: `entries` reserved, `field_overflow` = a start / end count did not fit.  Repeats the launch until it fits.
+void settle_streams(guac_ctx* ctx, guac_reads& rd, uint64_t entries, bool field_overflow, bool was_huge) {
+  cudaStream_t st = ctx->stream;
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    const bool need_huge = rd.max_reads_per_granule > 65535 && !was_huge;
+    const bool need_wide = !rd.gs_wide && (field_overflow || rd.max_reads_per_granule >= 2048);
+    if (field_overflow && rd.gs_wide && !need_huge) fail(GUAC_ERR_UNSUPPORTED, "more than 65535 reads start or end at one locus");
+    if (!need_huge && !need_wide && entries <= rd.gs_entries) {
+      float ms = 0;
+      CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+      rd.expand_ms = ms;
+      return;
+    }
+    if (need_wide) rd.gs_wide = true;
+    was_huge = was_huge || need_huge;
+    launch_expand(ctx, rd, was_huge, std::max<uint64_t>(entries + entries / 16 + 64, rd.gs_entries));
+    rd.pack_launches += 1;
+    unsigned long long c[2];
+    CUDA_OK(cudaMemcpyAsync(c, ctx->d_counters + 2, sizeof c, cudaMemcpyDeviceToHost, st));
+    check_device_error(ctx, "guac_reads_pack (difference streams)");
+    entries = c[0];
+    field_overflow = c[1] != 0;
+  }
+  fail(GUAC_ERR_CUDA, "difference streams did not converge");
+}
 
 void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* ref, guac_reads& out) {
   if (!b) fail(GUAC_ERR_INVALID_ARGUMENT, "null batch");
@@ -252,8 +320,6 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   out.del_start.alloc(n);
   out.del_md.alloc(n);
   out.del_len.alloc(n);
-  out.mm.alloc(n + 1);
-  if (!ctx->difference_lists) CUDA_OK(cudaMemsetAsync(out.mm.p, 0xFF, out.mm.bytes(), ctx->stream));
   if (out.has_qualities) out.qc.alloc((n ? (size_t)b->seq_off[n] : 0) + 64);
   CUDA_OK(cudaMemsetAsync(out.pairs.p, 0, out.pairs.bytes(), st));
   CUDA_OK(cudaMemsetAsync(out.xmask.p, 0, out.xmask.bytes(), st));
@@ -287,7 +353,6 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   A.rec_w = out.rec.p;
   A.pairs_w = out.pairs.p;
   A.xmask_w = out.xmask.p;
-  A.mm_w = out.mm.p;
   A.qc_w = out.has_qualities ? out.qc.p : nullptr;
   A.nm_w = out.nm.p;
   A.del_start_w = out.del_start.p;
@@ -335,13 +400,14 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     k_fasta_track<<<grid_for(word_off, 256, ctx->sm_count), 256, 0, st>>>(A, b->n_contigs);
     out.pack_launches += 1;
   }
-  if (n && ctx->difference_lists) {  // the track is final: every read as its differences against it
-    k_mismatch_lists<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(A);
+  if (n && ctx->difference_lists) {  // the track is final: every granule's reads as their differences against it
+    out.gs_wide = false;
+    launch_expand(ctx, out, /*huge=*/false, (uint64_t)n * 3 + gran_off * 8 + 4096);
     out.pack_launches += 1;
   }
   CUDA_OK(cudaEventRecord(ctx->ev[1], st));
   CUDA_OK(cudaGetLastError());
-  unsigned long long counters[2];
+  unsigned long long counters[4];
   CUDA_OK(cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, st));
   check_device_error(ctx, "guac_reads_pack");
   float ms = 0;
@@ -349,6 +415,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   out.pack_kernel_ms = ms;
   out.order_sensitive_loci = counters[0];
   out.max_reads_per_granule = counters[1];
+  if (n && ctx->difference_lists) settle_streams(ctx, out, counters[2], counters[3] != 0, /*was_huge=*/false);
   tr.lap("kernels");
 }
 
@@ -375,11 +442,16 @@ uint64_t build_tiles(const guac_reads& reads, const guac_locus_range* ranges, si
 }
 
 template <int MODE>
-void launch_tile(bool wide, int grid, cudaStream_t st, const DevReads& R, const TileDesc* tiles, const CallParams& prm, const DevOut& out) {
+void launch_tile(bool streams, bool wide, int grid, cudaStream_t st, const DevReads& R, const TileDesc* tiles, const CallParams& prm, const DevOut& out) {
   const uint32_t n = (uint32_t)grid;  // descriptors (one per warp)
   const int ctas = (int)((n + kWarpsPerCta - 1) / kWarpsPerCta);
-  if (wide) k_pileup_tile<uint64_t, MODE><<<ctas, kTileThreads, kWarpsPerCta * sizeof(WarpSmem<uint64_t, MODE>), st>>>(R, tiles, n, prm, out);
-  else k_pileup_tile<uint32_t, MODE><<<ctas, kTileThreads, kWarpsPerCta * sizeof(WarpSmem<uint32_t, MODE>), st>>>(R, tiles, n, prm, out);
+  if (streams) {
+    if (wide) k_call_tile<true, MODE><<<ctas, kTileThreads, kWarpsPerCta * sizeof(CallSmem<true>), st>>>(R, tiles, n, prm, out);
+    else k_call_tile<false, MODE><<<ctas, kTileThreads, kWarpsPerCta * sizeof(CallSmem<false>), st>>>(R, tiles, n, prm, out);
+  } else {  // GUAC_OPT_DIFFERENCE_LISTS = 0: planes / CIGAR walk inside the call
+    if (wide) k_pileup_tile<uint64_t, MODE><<<ctas, kTileThreads, kWarpsPerCta * sizeof(WarpSmem<uint64_t, MODE>), st>>>(R, tiles, n, prm, out);
+    else k_pileup_tile<uint32_t, MODE><<<ctas, kTileThreads, kWarpsPerCta * sizeof(WarpSmem<uint32_t, MODE>), st>>>(R, tiles, n, prm, out);
+  }
 }
 
 template <typename CntT, int MODE>
@@ -388,6 +460,8 @@ void set_smem_attr() {
 }
 void set_all_smem_attrs() {
   set_smem_attr<uint32_t, 0>(); set_smem_attr<uint64_t, 0>(); set_smem_attr<uint32_t, 1>(); set_smem_attr<uint64_t, 1>();
+  CUDA_OK(cudaFuncSetAttribute(k_call_tile<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kWarpsPerCta * sizeof(CallSmem<true>))));
+  CUDA_OK(cudaFuncSetAttribute(k_call_tile<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kWarpsPerCta * sizeof(CallSmem<true>))));
 }
 
 // the tile list of (reads, ranges) is cached in the context: a repeated call does not rebuild or re-upload it
@@ -416,7 +490,7 @@ uint64_t prepare_tiles(guac_ctx* ctx, const guac_reads& reads, const guac_locus_
   return requested;
 }
 
-// runs K_tile (+ K_exact on the loci it defers) for one read set
+// runs the tile kernel (+ the exact kernel on the loci it defers) for one read set
 void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* ranges, size_t n_ranges, CallParams prm,
                 guac_result& res) {
   uint64_t tile_loci = 0;
@@ -424,6 +498,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
   res.stats.reads_total = reads.n;
   res.stats.loci_requested = requested;
   res.stats.order_sensitive_loci = reads.order_sensitive_loci;
+  res.sample = reads.sample;
   auto append_rows_past_track = [&] {  // requested loci past the end of the track hold no reads: empty pileups, reference base N
     if (prm.mode != 1 || prm.skip_empty) return;
     for (size_t i = 0; i < n_ranges; ++i) {
@@ -443,34 +518,37 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     res.stats.loci_visited = prm.skip_empty ? 0 : requested;
     return;
   }
+  if (reads.n_contigs > 65535) fail(GUAC_ERR_UNSUPPORTED, "more than 65535 contigs");
   if (!ctx->smem_attrs_done) {  // per context: function attributes belong to the context's device
     set_all_smem_attrs();
     ctx->smem_attrs_done = true;
   }
-  cudaStream_t st = ctx->stream;
-  const size_t rec_size = prm.mode == 1 ? sizeof(guac_locus_counts) : sizeof(guac_threshold_record);
-  const bool dense = prm.mode == 1 || prm.emit_ref || prm.emit_no_call;
-  uint64_t cap_rec = dense ? tile_loci + 16 : std::max<uint64_t>(4096, tile_loci / 64);
+  cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+  const bool counts_mode = prm.mode == 1;
+  const bool dense = counts_mode || prm.emit_ref || prm.emit_no_call;
+  // counts mode: rows (guac_locus_counts) in HBM, copied afterwards.  Germline mode: the tile kernel's single-base records
+  // are compact (8 bytes) in HBM, ordered on the device and streamed to the pinned host block of the result; the exact
+  // kernel's few general records and their allele bytes are written to that block directly (unified addressing).
+  uint64_t cap_rec = counts_mode ? tile_loci + 16 : std::max<uint64_t>(4096, tile_loci / 256);
+  uint64_t cap_compact = counts_mode ? 8 : (dense ? tile_loci + tile_loci / 8 + 16 : std::max<uint64_t>(4096, tile_loci / 64));
   uint64_t cap_slow = std::max<uint64_t>(4096, tile_loci / 32);
   uint64_t cap_pool = kPoolDynOff + std::max<uint64_t>(65536, tile_loci / 64);
-  if (dense) cap_rec = std::max<uint64_t>(cap_rec, ctx->out_rec.n / rec_size);  // (sparse records go to a pinned block sized per call)
+  if (counts_mode) cap_rec = std::max<uint64_t>(cap_rec, ctx->out_rec.n / sizeof(guac_locus_counts));
+  cap_compact = std::max<uint64_t>(cap_compact, ctx->out_compact.n / 8);
   cap_slow = std::max<uint64_t>(cap_slow, ctx->out_slow.n / sizeof(SlowLocus));
-  cap_pool = std::max<uint64_t>(cap_pool, ctx->out_pool.n);
-  // 8-bit counter fields first unless the pileup is certainly deeper; K_tile reports an overflow and we widen
-  bool wide = reads.max_reads_per_granule >= 2048;
+  if (counts_mode) cap_pool = std::max<uint64_t>(cap_pool, ctx->out_pool.n);
+  const bool streams = reads.gs_hdr.n != 0;
+  // narrow counter fields (8 bits) unless the store is wide; the tile kernel reports a possible overflow and we widen
+  bool wide = streams ? reads.gs_wide : reads.max_reads_per_granule >= 2048;
   double tile_ms = 0, exact_ms = 0;
   int launches = 0;
   for (int attempt = 0; attempt < 8; ++attempt) {
-    if (cap_rec >= 0xFFFFFFF0ull || cap_slow >= 0xFFFFFFF0ull || cap_pool >= 0xFFFFFFF0ull)
+    if (cap_rec >= 0xFFFFFFF0ull || cap_compact >= 0xFFFFFFF0ull || cap_slow >= 0xFFFFFFF0ull || cap_pool >= 0xFFFFFFF0ull)
       fail(GUAC_ERR_UNSUPPORTED, "too many output records for one call: split the loci ranges");
-    // Sparse records end up in the pinned host block the result will own without a copy after the kernels (the device sees
-    // pinned memory through unified addressing): K_tile writes its records to HBM, K_exact streams them to the host block
-    // with coalesced stores while it walks its loci and appends its own records there directly.
-    // Dense outputs (counts, emit_ref) stay in HBM and are copied afterwards.
-    const bool zero_copy = !dense;
-    const size_t rec_at_zc = ((size_t)cap_pool + 63) & ~(size_t)63;
-    if (zero_copy) {
-      const size_t want = rec_at_zc + (size_t)cap_rec * rec_size + 64;
+    const size_t full_at = ((size_t)cap_pool + 63) & ~(size_t)63;
+    const size_t compact_at = (full_at + (size_t)cap_rec * sizeof(guac_threshold_record) + 63) & ~(size_t)63;
+    if (!counts_mode) {
+      const size_t want = compact_at + (size_t)cap_compact * 8 + 64;
       if (res.block && res.block_bytes < want) {
         ctx->pinned->give(res.block, res.block_bytes);
         res.block = nullptr;
@@ -480,66 +558,87 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
         res.block = ctx->pinned->take(want, &res.block_bytes);
         if (!res.block) fail(GUAC_ERR_OOM, "pinned host allocation of %zu bytes failed", want);
       }
+      unsigned char* hs = (unsigned char*)res.block;  // the static head of the allele pool: "<ALT>" and the 256 single bytes
+      memset(hs, 0, kPoolDynOff);
+      memcpy(hs, "<ALT>", 5);
+      for (int v = 0; v < 256; ++v) hs[kPoolByteOff + v] = (uint8_t)v;
+      ctx->out_compact.ensure(cap_compact * 8 + 16);
+    } else {
+      ctx->out_rec.ensure(cap_rec * sizeof(guac_locus_counts));
+      if (ctx->out_pool.ensure(cap_pool)) ctx->pool_head_ready = false;
     }
-    ctx->out_rec.ensure(cap_rec * rec_size);
-    ctx->out_slow.ensure(cap_slow * sizeof(SlowLocus));
-    if (ctx->out_pool.ensure(cap_pool)) ctx->pool_head_ready = false;
-    if (!ctx->pool_head_ready) {
-      std::vector<uint8_t> head(kPoolDynOff, 0);
-      memcpy(head.data(), "<ALT>", 5);
-      for (int v = 0; v < 256; ++v) head[kPoolByteOff + v] = (uint8_t)v;
-      CUDA_OK(cudaMemcpyAsync(ctx->out_pool.p, head.data(), head.size(), cudaMemcpyHostToDevice, st));
-      CUDA_OK(cudaStreamSynchronize(st));
-      ctx->pool_head_ready = true;
-    }
+    // Germline calls over many tiles run the tile kernel in two halves: the exact kernel of the first half (second stream)
+    // walks its loci while the second half's tile kernel runs.
+    const int n_seg = (!counts_mode && ctx->n_tiles >= 8192) ? 2 : 1;
+    ctx->out_slow.ensure((size_t)n_seg * cap_slow * sizeof(SlowLocus));
     CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
     DevOut out;
-    out.trec = (guac_threshold_record*)ctx->out_rec.p;
+    out.trec = counts_mode ? (guac_threshold_record*)ctx->out_rec.p : (guac_threshold_record*)((unsigned char*)res.block + full_at);
     out.crec = (guac_locus_counts*)ctx->out_rec.p;
     out.cap_rec = (uint32_t)cap_rec;
-    out.pool = ctx->out_pool.p;
+    out.compact = (unsigned long long*)ctx->out_compact.p;
+    out.cap_compact = counts_mode ? 0u : (uint32_t)cap_compact;
+    out.pool = counts_mode ? ctx->out_pool.p : (uint8_t*)res.block;
     out.cap_pool = (uint32_t)cap_pool;
     out.slow = (SlowLocus*)ctx->out_slow.p;
     out.cap_slow = (uint32_t)cap_slow;
+    out.slow_ctr = 2;
     out.counters = ctx->d_counters;
     out.err = ctx->d_err;
     const DevReads R = reads.view();
     const TileDesc* d_tiles = (const TileDesc*)ctx->tiles.p;
+    nvtx_push("guac tile + exact kernels");
     CUDA_OK(cudaEventRecord(ctx->ev[0], st));
-    if (prm.mode == 1) launch_tile<1>(wide, (int)ctx->n_tiles, st, R, d_tiles, prm, out);
-    else launch_tile<0>(wide, (int)ctx->n_tiles, st, R, d_tiles, prm, out);
-    CUDA_OK(cudaEventRecord(ctx->ev[1], st));
-    // K_exact reads the number of deferred loci from the device counter: no host round trip in between
-    const guac_threshold_record* tile_rec = nullptr;
-    const bool device_sort = zero_copy && ctx->sort_records;  // canonical order restored on the device (k_rec_*)
-    if (zero_copy && !device_sort) {
-      CUDA_OK(cudaMemcpyAsync(ctx->d_counters + 8, ctx->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-      tile_rec = out.trec;
-      out.trec = (guac_threshold_record*)((unsigned char*)res.block + rec_at_zc);
+    const uint64_t seg_tiles[3] = {0, n_seg == 2 ? (ctx->n_tiles / 2 + 3) & ~3ull : ctx->n_tiles, ctx->n_tiles};
+    for (int seg = 0; seg < n_seg; ++seg) {
+      DevOut so = out;
+      so.slow = out.slow + (size_t)seg * cap_slow;
+      so.slow_ctr = seg == 0 ? 2u : 8u;
+      const int nt = (int)(seg_tiles[seg + 1] - seg_tiles[seg]);
+      if (counts_mode) launch_tile<1>(streams, wide, nt, st, R, d_tiles + seg_tiles[seg], prm, so);
+      else launch_tile<0>(streams, wide, nt, st, R, d_tiles + seg_tiles[seg], prm, so);
+      // the exact kernel reads the number of deferred loci from the device counter: no host round trip in between
+      cudaEvent_t done = seg + 1 == n_seg ? ctx->ev[1] : ctx->seg_ev;
+      CUDA_OK(cudaEventRecord(done, st));
+      CUDA_OK(cudaStreamWaitEvent(st2, done, 0));
+      k_exact_loci<<<ctx->sm_count * 16, kExactWarps * 32, 0, st2>>>(R, so.slow, prm, so);
+      launches += 2;
     }
-    k_exact_loci<<<ctx->sm_count * 16, kExactWarps * 32, 0, st>>>(R, out.slow, prm, out, tile_rec);
+    CUDA_OK(cudaEventRecord(ctx->join_ev, st2));
+    nvtx_pop();
+    nvtx_push("guac record egress");
+    bool device_sorted = false;
+    unsigned long long* h_compact = counts_mode ? nullptr : (unsigned long long*)((unsigned char*)res.block + compact_at);
+    if (!counts_mode) {
+      const unsigned long long* src = out.compact;
+      if (ctx->sort_records && !dense) {  // canonical order restored on the device (k_rec_*)
+        const uint32_t n_bins = (uint32_t)reads.total_grans;
+        ctx->sort_bins.ensure(2 * ((size_t)n_bins + 1));
+        ctx->sort_rec.ensure(cap_compact * 8 + 16);
+        uint32_t* hist = ctx->sort_bins.p;
+        uint32_t* cursor = hist + n_bins + 1;
+        unsigned long long* grouped = (unsigned long long*)ctx->sort_rec.p;
+        CUDA_OK(cudaMemsetAsync(hist, 0, ((size_t)n_bins + 1) * sizeof(uint32_t), st));
+        k_rec_hist<<<ctx->sm_count * 2, 256, 0, st>>>(R, out.compact, ctx->d_counters, out.cap_compact, hist);
+        k_rec_scan<<<1, 1024, 0, st>>>(hist, cursor, n_bins);
+        k_rec_scatter<<<ctx->sm_count * 2, 256, 0, st>>>(R, out.compact, ctx->d_counters, out.cap_compact, cursor, grouped);
+        k_rec_finish<<<grid_for(n_bins, 256, ctx->sm_count), 256, 0, st>>>(hist, n_bins, grouped, ctx->d_counters);
+        src = grouped;
+        device_sorted = true;
+        launches += 4;
+      }
+      k_rec_flush<<<ctx->sm_count * 2, 256, 0, st>>>(src, ctx->d_counters, out.cap_compact, h_compact);
+      launches += 1;
+    }
+    CUDA_OK(cudaStreamWaitEvent(st, ctx->join_ev, 0));
     CUDA_OK(cudaEventRecord(ctx->ev[2], st));
-    launches += 2;
-    if (device_sort) {
-      const uint32_t n_bins = (uint32_t)reads.total_grans;
-      ctx->sort_bins.ensure(2 * ((size_t)n_bins + 1));
-      ctx->sort_rec.ensure(cap_rec * rec_size);
-      uint32_t* hist = ctx->sort_bins.p;
-      uint32_t* cursor = hist + n_bins + 1;
-      guac_threshold_record* grouped = (guac_threshold_record*)ctx->sort_rec.p;
-      CUDA_OK(cudaMemsetAsync(hist, 0, ((size_t)n_bins + 1) * sizeof(uint32_t), st));
-      k_rec_hist<<<ctx->sm_count * 4, 256, 0, st>>>(R, out.trec, ctx->d_counters, out.cap_rec, hist);
-      k_rec_scan<<<1, 1024, 0, st>>>(hist, cursor, n_bins);
-      k_rec_scatter<<<ctx->sm_count * 4, 256, 0, st>>>(R, out.trec, ctx->d_counters, out.cap_rec, cursor, grouped);
-      k_rec_finish<<<grid_for(n_bins, 256, ctx->sm_count), 256, 0, st>>>(hist, n_bins, out.pool, out.cap_pool, grouped);
-      k_rec_flush<<<ctx->sm_count * 2, 256, 0, st>>>(grouped, ctx->d_counters, out.cap_rec,
-                                                      (guac_threshold_record*)((unsigned char*)res.block + rec_at_zc));
-      launches += 5;
-    }
     CUDA_OK(cudaGetLastError());
+    // counters and the device error word come back in one copy, one synchronisation per call
     unsigned long long* c = ctx->h_counters;
-    CUDA_OK(cudaMemcpyAsync(c, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    check_device_error(ctx, "pileup");
+    CUDA_OK(cudaMemcpyAsync(c, ctx->d_counters, kStatusBytes, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    nvtx_pop();
+    raise_device_error(ctx, "pileup");
     float ms = 0;
     CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     tile_ms += ms;
@@ -548,68 +647,116 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     if (c[5]) {  // a counter field may have wrapped: widen and rerun
       if (wide) fail(GUAC_ERR_UNSUPPORTED, "pileup deeper than 65535 reads");
       wide = true;
+      if (streams) {  // the store's start / end fields widen with the counters: its streams are built again
+        guac_reads& rw = const_cast<guac_reads&>(reads);
+        rw.gs_wide = true;
+        launch_expand(ctx, rw, rw.max_reads_per_granule > 65535, rw.gs_entries);
+        unsigned long long e[2];
+        CUDA_OK(cudaMemcpyAsync(e, ctx->d_counters + 2, sizeof e, cudaMemcpyDeviceToHost, st));
+        check_device_error(ctx, "difference streams");
+        settle_streams(ctx, rw, e[0], e[1] != 0, rw.max_reads_per_granule > 65535);
+      }
       continue;
     }
-    if (c[2] > cap_slow || c[0] > cap_rec || kPoolDynOff + c[1] > cap_pool) {
-      cap_slow = std::max<uint64_t>(cap_slow, c[2] + c[2] / 8 + 16);
+    if (c[2] > cap_slow || c[8] > cap_slow || c[0] > cap_rec || c[6] > cap_compact || kPoolDynOff + c[1] > cap_pool) {
+      cap_slow = std::max<uint64_t>(cap_slow, std::max(c[2], c[8]) + std::max(c[2], c[8]) / 8 + 16);
       cap_rec = std::max<uint64_t>(cap_rec, c[0] + c[0] / 8 + 16);
+      cap_compact = std::max<uint64_t>(cap_compact, c[6] + c[6] / 8 + 16);
       cap_pool = std::max<uint64_t>(cap_pool, kPoolDynOff + c[1] + c[1] / 8 + 16);
       continue;
     }
-    // ---- D2H straight into the pinned block the result will own (+ canonical order unless switched off).  Records keep
-    // their offsets into the pool, which is returned whole: no per-record work on the host.
     const uint64_t n_rec = c[0];
-    const size_t pool_bytes = (size_t)(kPoolDynOff + c[1]), rec_bytes = (size_t)(n_rec * rec_size);
-    const size_t rec_at = zero_copy ? rec_at_zc : ((pool_bytes + 63) & ~(size_t)63);
-    if (!zero_copy) {
-      res.pool = ctx->pinned;
-      res.block = ctx->pinned->take(rec_at + rec_bytes + 64, &res.block_bytes);
-      if (!res.block) fail(GUAC_ERR_OOM, "pinned host allocation of %zu bytes failed", rec_at + rec_bytes + 64);
-    }
-    unsigned char* hs = (unsigned char*)res.block;
-    unsigned char* hrec = hs + rec_at;
-    CUDA_OK(cudaMemcpyAsync(hs, ctx->out_pool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
-    if (n_rec && !zero_copy) CUDA_OK(cudaMemcpyAsync(hrec, ctx->out_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
-    res.stats.d2h_bytes = pool_bytes + rec_bytes + 8 * sizeof(unsigned long long);  // (records cross PCIe either way)
-    if (prm.mode == 1) {
+    const size_t pool_bytes = (size_t)(kPoolDynOff + c[1]);
+    if (counts_mode) {
+      const size_t rec_bytes = (size_t)(n_rec * sizeof(guac_locus_counts));
       res.counts.resize((size_t)n_rec);
-      if (n_rec) memcpy(res.counts.data(), hrec, rec_bytes);
+      if (n_rec) CUDA_OK(cudaMemcpyAsync(res.counts.data(), ctx->out_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      res.stats.d2h_bytes = rec_bytes + kStatusBytes;
       append_rows_past_track();
       if (ctx->sort_records)
         std::sort(res.counts.begin(), res.counts.end(), [](const guac_locus_counts& a, const guac_locus_counts& b) {
           return std::make_pair(a.contig, a.locus) < std::make_pair(b.contig, b.locus);
         });
     } else {
-      res.records = hrec;
-      res.n_records = (size_t)n_rec;
-      res.bytes = hs;
+      res.general = (guac_threshold_record*)((unsigned char*)res.block + full_at);
+      res.n_general = (size_t)n_rec;
+      res.compact = h_compact;
+      res.n_compact = (size_t)c[6];
+      res.n_records = res.n_general + res.n_compact;
+      res.bytes = (const uint8_t*)res.block;
       res.n_bytes = pool_bytes;
-      if (ctx->sort_records && !device_sort) {
-        const uint8_t* pool = hs;
-        guac_threshold_record* first = (guac_threshold_record*)hrec;
-        sort_records_canonical(first, (size_t)n_rec, [pool](const guac_threshold_record& a, const guac_threshold_record& b) {
-          if (a.sample != b.sample) return a.sample < b.sample;
-          int c = memcmp(pool + a.ref_off, pool + b.ref_off, std::min(a.ref_len, b.ref_len));
-          if (c != 0) return c < 0;
-          if (a.ref_len != b.ref_len) return a.ref_len < b.ref_len;
-          c = memcmp(pool + a.alt_off, pool + b.alt_off, std::min(a.alt_len, b.alt_len));
-          if (c != 0) return c < 0;
-          return a.alt_len < b.alt_len;
-        });
-      }
+      res.want_sorted = ctx->sort_records != 0;
+      res.compact_sorted = device_sorted && c[7] == 0;
+      res.stats.d2h_bytes = (pool_bytes - kPoolDynOff) + n_rec * sizeof(guac_threshold_record) + res.n_compact * 8 + kStatusBytes;
     }
     res.stats.loci_visited = c[3] + (prm.skip_empty ? 0 : requested - tile_loci);  // loci past the track: empty pileups
     res.stats.tie_loci = c[4];
-    res.stats.records = prm.mode == 1 ? res.counts.size() : n_rec;
+    res.stats.records = counts_mode ? res.counts.size() : res.n_records;
     res.stats.kernel_ms = tile_ms + exact_ms;
     res.stats.tile_kernel_ms = tile_ms;
     res.stats.exact_kernel_ms = exact_ms;
     res.stats.kernel_launches = (uint64_t)launches;
-    res.stats.exact_loci = c[2];
+    res.stats.exact_loci = c[2] + c[8];
     return;
   }
   fail(GUAC_ERR_CUDA, "output buffers did not converge");
+}
+
+// guac_threshold_record view of a germline result: the compact records expanded and merged with the exact kernel's general
+// records, in canonical order when the context asked for it.  Built on first use.
+void expand_threshold_records(guac_result& r) {
+  if (r.expanded_ready) return;
+  r.expanded_ready = true;
+  if (r.kind != 0 || r.n_records == 0) return;
+  const uint8_t* pool = r.bytes;
+  std::vector<unsigned long long> sorted_compact;
+  const unsigned long long* cr = r.compact;
+  if (r.want_sorted && !r.compact_sorted && r.n_compact > 1) {
+    sorted_compact.assign(r.compact, r.compact + r.n_compact);
+    std::sort(sorted_compact.begin(), sorted_compact.end());
+    cr = sorted_compact.data();
+  }
+  std::vector<guac_threshold_record> gen(r.general, r.general + r.n_general);
+  auto less_general = [pool](const guac_threshold_record& a, const guac_threshold_record& b) {
+    if (a.contig != b.contig) return a.contig < b.contig;
+    if (a.start != b.start) return a.start < b.start;
+    if (a.sample != b.sample) return a.sample < b.sample;
+    int c = memcmp(pool + a.ref_off, pool + b.ref_off, std::min(a.ref_len, b.ref_len));
+    if (c != 0) return c < 0;
+    if (a.ref_len != b.ref_len) return a.ref_len < b.ref_len;
+    c = memcmp(pool + a.alt_off, pool + b.alt_off, std::min(a.alt_len, b.alt_len));
+    if (c != 0) return c < 0;
+    return a.alt_len < b.alt_len;
+  };
+  if (r.want_sorted) std::sort(gen.begin(), gen.end(), less_general);
+  r.expanded.resize(r.n_records);
+  auto widen = [&](unsigned long long v) {
+    guac_threshold_record t;
+    t.start = (int64_t)(uint32_t)(v >> 16);
+    t.contig = (int32_t)(v >> 48);
+    t.sample = r.sample;
+    const uint32_t alt = (uint32_t)(v >> 13) & 7u, rcode = (uint32_t)(v >> 11) & 3u;
+    t.ref_off = kPoolByteOff + (uint32_t)"ACGT"[rcode];
+    t.ref_len = 1;
+    t.alt_off = alt == 0 ? kPoolAltOff : kPoolByteOff + (uint32_t)"ACGT"[alt - 1];
+    t.alt_len = alt == 0 ? 5 : 1;
+    t.gt[0] = (uint8_t)((v >> 9) & 3u);
+    t.gt[1] = (uint8_t)((v >> 7) & 3u);
+    t.tie = (uint8_t)((v >> 6) & 1u);
+    t.pad_ = 0;
+    return t;
+  };
+  size_t i = 0, j = 0, k = 0;
+  if (r.want_sorted) {  // merge by (contig, start): a locus is decided by one kernel or the other, never both
+    while (i < r.n_compact && j < gen.size()) {
+      const unsigned long long key = (((unsigned long long)(uint32_t)gen[j].contig) << 32) | (unsigned long long)(uint32_t)gen[j].start;
+      if ((cr[i] >> 16) <= key) r.expanded[k++] = widen(cr[i++]);
+      else r.expanded[k++] = gen[j++];
+    }
+  }
+  while (i < r.n_compact) r.expanded[k++] = widen(cr[i++]);
+  while (j < gen.size()) r.expanded[k++] = gen[j++];
 }
 
 }  // namespace
@@ -652,14 +799,16 @@ guac_status guac_ctx_create(int device, guac_ctx** out) {
   guac_status s = guarded(ctx, [&] {
     CUDA_OK(cudaSetDevice(device));
     CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ctx->seg_ev, cudaEventDisableTiming));
     CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (auto& e : ctx->copy_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
-    CUDA_OK(cudaMalloc((void**)&ctx->d_err, sizeof(DevError)));
-    CUDA_OK(cudaMalloc((void**)&ctx->d_counters, 16 * sizeof(unsigned long long)));
-    CUDA_OK(cudaMemset(ctx->d_err, 0, sizeof(DevError)));
-    CUDA_OK(cudaMemset(ctx->d_counters, 0, 16 * sizeof(unsigned long long)));
-    CUDA_OK(cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMalloc((void**)&ctx->d_counters, kStatusBytes));
+    ctx->d_err = reinterpret_cast<DevError*>(ctx->d_counters + 16);
+    CUDA_OK(cudaMemset(ctx->d_counters, 0, kStatusBytes));
+    CUDA_OK(cudaMallocHost((void**)&ctx->h_counters, kStatusBytes));
     for (auto& e : ctx->ev) CUDA_OK(cudaEventCreate(&e));
     somatic_init_tables(ctx);
   });
@@ -674,7 +823,6 @@ guac_status guac_ctx_create(int device, guac_ctx** out) {
 void guac_ctx_destroy(guac_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  if (ctx->d_err) cudaFree(ctx->d_err);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -685,11 +833,17 @@ void guac_ctx_destroy(guac_ctx* ctx) {
   ctx->out_rec.release();
   ctx->out_pool.release();
   ctx->out_slow.release();
+  ctx->out_compact.release();
+  ctx->sort_rec.release();
+  ctx->sort_bins.release();
   ctx->tiles.release();
   tl_dev_cache.trim();
   for (auto& e : ctx->copy_ev)
     if (e) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
+  if (ctx->seg_ev) cudaEventDestroy(ctx->seg_ev);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -846,6 +1000,9 @@ static void run_allele_counts(guac_ctx* ctx, const guac_reads& reads, const guac
     out.cap_pool = (uint32_t)cap_pool;
     out.slow = nullptr;
     out.cap_slow = 0;
+    out.slow_ctr = 2;
+    out.compact = nullptr;
+    out.cap_compact = 0;
     out.counters = ctx->d_counters;
     out.err = ctx->d_err;
     CUDA_OK(cudaEventRecord(ctx->ev[0], st));
@@ -930,7 +1087,25 @@ size_t guac_result_n(const guac_result* r) {
   if (!r) return 0;
   return r->kind == 2 ? r->counts.size() : r->n_records;
 }
-const guac_threshold_record* guac_result_threshold_records(const guac_result* r) { return (r && r->kind == 0) ? (const guac_threshold_record*)r->records : nullptr; }
+const guac_threshold_record* guac_result_threshold_records(const guac_result* r) {
+  if (!r || r->kind != 0) return nullptr;
+  guac_result* w = const_cast<guac_result*>(r);  // (the expanded view is a cache; a result belongs to one thread)
+  try {
+    expand_threshold_records(*w);
+  } catch (const std::bad_alloc&) {
+    return nullptr;
+  }
+  return w->expanded.data();
+}
+size_t guac_result_compact_records(const guac_result* r, const guac_compact_record** compact, const guac_threshold_record** general,
+                                   size_t* n_general, int32_t* sample) {
+  if (!r || r->kind != 0) return 0;
+  if (compact) *compact = (const guac_compact_record*)r->compact;
+  if (general) *general = r->general;
+  if (n_general) *n_general = r->n_general;
+  if (sample) *sample = r->sample;
+  return r->n_compact;
+}
 const guac_somatic_record* guac_result_somatic_records(const guac_result* r) { return (r && r->kind == 1) ? (const guac_somatic_record*)r->records : nullptr; }
 const guac_locus_counts* guac_result_counts(const guac_result* r) { return (r && r->kind == 2) ? r->counts.data() : nullptr; }
 const guac_allele_count* guac_result_allele_counts(const guac_result* r) { return (r && r->kind == 4) ? (const guac_allele_count*)r->records : nullptr; }

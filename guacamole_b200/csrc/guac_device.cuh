@@ -4,9 +4,13 @@
 //   rec[n+1]      16 B/read   {start, end, pair_off, info}   contig-relative 0-based [start, end)   (MappedRead.start/end)
 //   pairs[]       8 B/32 bases  bit-plane pairs (lo, hi) of the 2-bit read bases, read coordinates, 32 bases per pair
 //   xmask[]       4 B/32 bases  1 = base is not A/C/G/T (read only for reads flagged HAS_EXC)
-//   mm[n]         16 B/read   a read as its differences against the reference track (reference-based encoding, like CRAM):
-//                             up to 8 (offset, class) pairs; the germline tile kernel reads rec + mm and, for reads that
-//                             fit, never the planes or the CIGAR
+//   gs_hdr[G]     16 B/granule  {offset of the granule's difference stream, its length, depth entering the granule (all reads,
+//                             positive strand)}: the reads of a granule as their DIFFERENCES against the reference track
+//   gs_diffs[]    2 B/difference  (locus offset in the granule, class) as the counter slot it lands in, contiguous per granule
+//                             (reference-based encoding, like CRAM): class 1..3 = read base code ^ reference base code,
+//                             0 = element that is not a plain base
+//   gs_dd/gs_dp[] 1 B/locus   reads starting (low nibble) / ending (high nibble) at the locus, all reads / positive strand
+//                             (wide stores: 4 B/locus, two 16-bit fields): the depth is their running sum
 //   cig_off/cigar BAM-encoded run-length CIGAR ops (read only for reads that are not SIMPLE)
 //   seq/qual      raw bytes (the exact per-locus paths read them)
 //   qc[]          1 B/base   quality (6 bits) | base code << 6: the one byte per pileup element the likelihood kernel loads
@@ -37,10 +41,15 @@ constexpr uint32_t kInfoHasExc = 1u << 17;      // read holds a non-ACGT base
 constexpr uint32_t kInfoPositive = 1u << 18;    // isPositiveStrand
 constexpr uint32_t kInfoEmpty = 1u << 19;       // consumes no reference (overlaps nothing)
 constexpr uint32_t kInfoWideQ = 1u << 20;       // read holds a base quality > 63 (its qc bytes are not usable)
-constexpr uint32_t kInfoMmList = 1u << 21;      // mm[] holds the read's differences against the reference track
 constexpr int kInfoMapqShift = 24;
-constexpr int kMmSlots = 8;                     // differences kept per read (more: the read takes the general path)
-constexpr int kMmMaxSpan = 16379;               // offsets are 14 bits; 0xFFF0 | n in the last slot = "n entries" (n < 8)
+
+// header of one granule's difference stream (built at pack time by k_expand, guac_tile.cuh)
+struct __align__(16) GranHdr {
+  uint32_t df_off;     // first entry of the granule in gs_diffs, in units of 8 entries (16 bytes)
+  uint32_t n_df;       // entries
+  uint32_t depth_in;   // reads that cover the granule's first locus and started before it
+  uint32_t pos_in;     // ... of which on the positive strand
+};
 
 struct __align__(16) ReadRec {
   int32_t start;
@@ -68,7 +77,12 @@ struct DevReads {
   const uint32_t* cigar;
   const uint2* pairs;
   const uint32_t* xmask;
-  const uint4* mm;            // per read: up to 8 x u16 (reference offset << 2 | class), 0xFFFF = unused (guac_pack.cuh)
+  const GranHdr* gs_hdr;      // per granule (all contigs, ContigInfo.gran_off): nullptr when the store was packed without streams
+  const uint16_t* gs_diffs;   // CntLayout::slot_code(locus offset, class) entries, 16-byte aligned per granule
+  const uint8_t* gs_dd;       // per locus of every granule: starts | ends << 4 (narrow) or u32 starts | ends << 16 (wide)
+  const uint8_t* gs_dp;       // same, positive-strand reads only
+  int32_t gs_wide;            // 1: 4 bytes per locus in gs_dd / gs_dp
+  int32_t pad2_;
   const uint64_t* seq_off;
   const uint8_t* seq;
   const uint8_t* qual;

@@ -16,6 +16,8 @@
 #include <tuple>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "guac_device.cuh"
 
 using namespace guac;
@@ -167,15 +169,24 @@ struct PinnedPool {
 };
 
 // ---- context ----------------------------------------------------------------------------------------------------------------
+// device status block: 16 counters followed by the device error word, fetched in one copy
+constexpr size_t kStatusBytes = 16 * sizeof(unsigned long long) + sizeof(DevError);
+
+// NVTX ranges around pack / copies / kernel families (visible in Nsight Systems; no cost without a profiler attached)
+inline void nvtx_push(const char* name) { nvtxRangePushA(name); }
+inline void nvtx_pop() { nvtxRangePop(); }
+
 struct guac_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;       // the exact per-locus kernel of a germline call, next to the record egress on `stream`
+  cudaEvent_t join_ev = nullptr, seg_ev = nullptr;
   cudaStream_t copy_stream = nullptr;   // guac_reads_pack: host -> device copies, overlapped with the pack kernels
   cudaEvent_t copy_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::string last_error;
-  DevError* d_err = nullptr;
-  unsigned long long* d_counters = nullptr;  // 16 counters
-  unsigned long long* h_counters = nullptr;  // pinned mirror
+  unsigned long long* d_counters = nullptr;  // 16 counters, then the DevError (kStatusBytes)
+  DevError* d_err = nullptr;                 // = d_counters + 16
+  unsigned long long* h_counters = nullptr;  // pinned mirror of the whole status block
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [4], [5]: user stopwatch
   int sm_count = 148;
   // options
@@ -183,9 +194,9 @@ struct guac_ctx {
   int pack_qualities = 1;
   int host_threads = 0;
   int difference_lists = 1;
-  bool smem_attrs_done = false;
+  bool smem_attrs_done = false, expand_attrs_done = false;
   // scratch kept across calls so that a repeated call neither allocates nor rebuilds its tile list
-  DevBuf<unsigned char> out_rec, out_pool, out_slow, tiles, sort_rec;
+  DevBuf<unsigned char> out_rec, out_pool, out_slow, out_compact, tiles, sort_rec;
   DevBuf<uint32_t> sort_bins;
   std::vector<guac_locus_range> tiles_key_ranges;
   const void* tiles_key_reads = nullptr;
@@ -222,6 +233,16 @@ void check_device_error(guac_ctx* ctx, const char* what) {
   DevError e;
   CUDA_OK(cudaMemcpyAsync(&e, ctx->d_err, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (e.code) {
+    CUDA_OK(cudaMemsetAsync(ctx->d_err, 0, sizeof(DevError), ctx->stream));
+    fail((guac_status)e.code, "%s: %s at read/locus %llu", what, guac_status_string((guac_status)e.code), e.where);
+  }
+}
+
+// after a copy of the status block into ctx->h_counters has completed: throws the device-side error, if any
+void raise_device_error(guac_ctx* ctx, const char* what) {
+  DevError e;
+  memcpy(&e, ctx->h_counters + 16, sizeof e);
   if (e.code) {
     CUDA_OK(cudaMemsetAsync(ctx->d_err, 0, sizeof(DevError), ctx->stream));
     fail((guac_status)e.code, "%s: %s at read/locus %llu", what, guac_status_string((guac_status)e.code), e.where);
@@ -358,7 +379,12 @@ struct guac_reads {
   DevBuf<ReadRec> rec;
   DevBuf<uint32_t> cig_off, cigar, xmask, md_off, trk_lo, trk_hi, trk_std, gran_first, gran_last;
   DevBuf<uint2> pairs;
-  DevBuf<uint4> mm;
+  DevBuf<GranHdr> gs_hdr;             // per-granule difference streams (k_expand); empty when packed without them
+  DevBuf<uint16_t> gs_diffs;
+  DevBuf<uint8_t> gs_dd, gs_dp;
+  bool gs_wide = false;
+  uint64_t gs_entries = 0;
+  double expand_ms = 0;
   DevBuf<uint64_t> seq_off, fasta_off;
   DevBuf<uint8_t> seq, qual, qc, fasta;
   DevBuf<char> md;
@@ -385,7 +411,12 @@ struct guac_reads {
     R.cigar = cigar.p;
     R.pairs = pairs.p;
     R.xmask = xmask.p;
-    R.mm = mm.p;
+    R.gs_hdr = gs_hdr.n ? gs_hdr.p : nullptr;
+    R.gs_diffs = gs_diffs.p;
+    R.gs_dd = gs_dd.p;
+    R.gs_dp = gs_dp.p;
+    R.gs_wide = gs_wide ? 1 : 0;
+    R.pad2_ = 0;
     R.seq_off = seq_off.p;
     R.seq = seq.p;
     R.qual = qual.p;
@@ -408,14 +439,23 @@ struct guac_reads {
   }
   uint64_t device_bytes() const {
     return rec.bytes() + cig_off.bytes() + cigar.bytes() + xmask.bytes() + md_off.bytes() + trk_lo.bytes() * 3 +
-           gran_first.bytes() * 2 + pairs.bytes() + mm.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + qc.bytes() + md.bytes() + nm.bytes() + del_start.bytes() + del_md.bytes() + del_len.bytes() +
+           gran_first.bytes() * 2 + pairs.bytes() + gs_hdr.bytes() + gs_diffs.bytes() + gs_dd.bytes() + gs_dp.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + qc.bytes() + md.bytes() + nm.bytes() + del_start.bytes() + del_md.bytes() + del_len.bytes() +
            fasta.bytes();
   }
 };
 
 struct guac_result {
-  int kind = 0;  // 0 threshold, 1 somatic, 2 counts, 3 called alleles (germline-standard)
-  // threshold / somatic records and the allele byte pool live in one pinned block (downloaded in place)
+  int kind = 0;  // 0 threshold, 1 somatic, 2 counts, 3 called alleles (germline-standard), 4 allele counts
+  // germline-threshold: compact single-base records + the exact kernel's general records + the allele byte pool in one pinned
+  // block; the guac_threshold_record view is built on first use (expand_threshold_records)
+  int32_t sample = 0;
+  const guac_threshold_record* general = nullptr;
+  size_t n_general = 0;
+  const unsigned long long* compact = nullptr;
+  size_t n_compact = 0;
+  bool want_sorted = true, compact_sorted = false, expanded_ready = false;
+  std::vector<guac_threshold_record> expanded;
+  // somatic / called-allele / allele-count records and the allele byte pool live in one pinned block (downloaded in place)
   std::shared_ptr<PinnedPool> pool;
   void* block = nullptr;
   size_t block_bytes = 0;

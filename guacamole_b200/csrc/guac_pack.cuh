@@ -16,7 +16,6 @@ struct PackArgs {
   ReadRec* rec_w;        // writable aliases
   uint2* pairs_w;
   uint32_t* xmask_w;
-  uint4* mm_w;
   uint8_t* qc_w;         // (quality | base code << 6) per base, nullptr when qualities are not packed
   uint16_t* nm_w;
   int32_t* del_start_w;
@@ -219,107 +218,6 @@ __global__ void __launch_bounds__(256) k_pack_bases(PackArgs A) {
       }
     }
     __syncthreads();  // the stage buffers are reused by the next block of reads
-  }
-}
-
-// ---- K_mismatch_lists: thread per read; a read as its differences against the final reference track ------------------------
-// Runs after the track is complete (MD-derived and conflict-resolved, or FASTA-derived), so the lists agree with the track
-// by construction, order-sensitive loci included.  An entry is (reference offset << 2 | class): class 1..3 = read base code ^
-// reference base code (a mismatch; the tile kernel's counter field), class 0 = an element that is not a plain base
-// (insertion / deletion anchor, deleted or skipped locus, non-ACGT base: PileupElement.scala:68-135).  Mismatches over a
-// track base that is not A/C/G/T are left out: the callers hand those loci to the exact per-locus path whatever the
-// counters say.  Reads that need more than kMmSlots entries (or span more than 14 bits) keep the CIGAR walk.
-struct MmList {
-  unsigned long long lo = ~0ull, hi = ~0ull;  // 8 x u16, unused = 0xFFFF
-  int n = 0;
-  bool ok = true;
-  __device__ __forceinline__ void add(int offset, uint32_t cls) {
-    if (n == kMmSlots) { ok = false; return; }
-    const unsigned long long e = ((unsigned long long)offset << 2) | cls;
-    const int sft = 16 * (n & 3);
-    if (n < 4) lo = (lo & ~(0xFFFFull << sft)) | (e << sft);
-    else hi = (hi & ~(0xFFFFull << sft)) | (e << sft);
-    ++n;
-  }
-};
-
-// one plain M/=/X run [seg_ref, seg_ref + seg_len) whose first base is read base seg_read
-__device__ __forceinline__ void mm_segment(const PackArgs& A, const ContigInfo& ci, const ReadRec& rec, int seg_ref, int seg_read, int seg_len,
-                                           bool has_exc, MmList& L) {
-  if (seg_len <= 0) return;
-  const uint2* __restrict__ P = A.R.pairs + rec.pair_off;
-  const uint32_t* __restrict__ X = A.R.xmask + rec.pair_off;
-  const int w0 = seg_ref >> 5, w1 = (seg_ref + seg_len - 1) >> 5;
-  int q0 = seg_read + ((w0 << 5) - seg_ref);  // read base under bit 0 of word w0 (> -32)
-  for (int w = w0; w <= w1 && L.ok; ++w, q0 += 32) {
-    const int j = q0 >> 5, sh = q0 & 31;  // arithmetic shift: floor
-    const uint2 pa = j >= 0 ? P[j] : make_uint2(0u, 0u), pb = P[j + 1];
-    uint32_t valid = bit_range(seg_ref - (w << 5), seg_ref + seg_len - (w << 5));
-    uint32_t oth = 0;
-    if (has_exc) oth = __funnelshift_r(j >= 0 ? X[j] : 0u, X[j + 1], sh) & valid;  // non-ACGT bases
-    valid &= ~oth;
-    const uint32_t std_m = A.R.trk_std[ci.word_off + w];
-    const uint32_t x = (__funnelshift_r(pa.x, pb.x, sh) ^ A.R.trk_lo[ci.word_off + w]) & valid & std_m;
-    const uint32_t y = (__funnelshift_r(pa.y, pb.y, sh) ^ A.R.trk_hi[ci.word_off + w]) & valid & std_m;
-    uint32_t d = x | y | oth;
-    while (d && L.ok) {
-      const int b = __ffs(d) - 1;
-      d &= d - 1;
-      const uint32_t cls = ((oth >> b) & 1u) ? 0u : (((x >> b) & 1u) | (((y >> b) & 1u) << 1));
-      L.add((w << 5) + b - rec.start, cls);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) k_mismatch_lists(PackArgs A) {
-  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < A.R.n; r += (uint64_t)gridDim.x * blockDim.x) {
-    const ReadRec rec = A.R.rec[r];
-    MmList L;
-    L.ok = !(rec.info & kInfoEmpty) && rec.end > rec.start && rec.end - rec.start <= kMmMaxSpan;
-    if (L.ok) {
-      const ContigInfo ci = A.R.contigs[A.read_contig[r]];
-      const bool has_exc = (rec.info & kInfoHasExc) != 0;
-      if (rec.info & kInfoSimple) {
-        mm_segment(A, ci, rec, rec.start, (int)(rec.info & kInfoLeadMask), rec.end - rec.start, has_exc, L);
-      } else {  // the CIGAR walk of the tile kernel's general path (guac_pileup.cuh general_read), once, at pack time
-        int ref_pos = rec.start, read_pos = 0;
-        bool skip_first = false;  // contig-start insertion: the element at locus 0 is the insertion, not a plain base
-        const uint32_t c0 = A.R.cig_off[r], c1 = A.R.cig_off[r + 1];
-        for (uint32_t c = c0; c < c1 && L.ok; ++c) {
-          const uint32_t v = A.R.cigar[c];
-          const uint32_t op = v & 0xF, next_op = (c + 1 < c1) ? (A.R.cigar[c + 1] & 0xF) : 0xFFu;
-          const int len = (int)(v >> 4);
-          if (op_is_match_like(op)) {
-            int seg_ref = ref_pos, seg_read = read_pos, seg_len = len;
-            if (skip_first) {
-              L.add(ref_pos - rec.start, 0u);
-              ++seg_ref; ++seg_read; --seg_len;
-              skip_first = false;
-            }
-            // (M|=, I) and (M|=|X, D): the run's last base is the insertion / deletion anchor (PileupElement.scala:93, 109)
-            const bool anchor = (next_op == GUAC_CIGAR_I && (op == GUAC_CIGAR_M || op == GUAC_CIGAR_EQ)) || next_op == GUAC_CIGAR_D;
-            const bool do_anchor = anchor && seg_len > 0;
-            if (do_anchor) --seg_len;
-            mm_segment(A, ci, rec, seg_ref, seg_read, seg_len, has_exc, L);
-            if (do_anchor) L.add(ref_pos + len - 1 - rec.start, 0u);
-            ref_pos += len;
-            read_pos += len;
-          } else if (op == GUAC_CIGAR_D || op == GUAC_CIGAR_N) {
-            for (int l = 0; l < len && L.ok; ++l) L.add(ref_pos + l - rec.start, 0u);  // mid-deletion / skipped loci
-            ref_pos += len;
-          } else if (op == GUAC_CIGAR_I) {
-            if (ref_pos == 0 && rec.start == 0) skip_first = true;
-            read_pos += len;
-          } else if (op == GUAC_CIGAR_S) {
-            read_pos += len;
-          }
-        }
-      }
-    }
-    if (!L.ok) L.lo = L.hi = ~0ull;
-    else if (L.n < kMmSlots) L.hi = (L.hi & 0x0000FFFFFFFFFFFFull) | ((0xFFF0ull | (unsigned long long)L.n) << 48);  // the count rides in the last slot
-    A.mm_w[r] = make_uint4((uint32_t)L.lo, (uint32_t)(L.lo >> 32), (uint32_t)L.hi, (uint32_t)(L.hi >> 32));
-    if (L.ok) A.rec_w[r].info = rec.info | kInfoMmList;
   }
 }
 

@@ -34,14 +34,18 @@ struct SlowLocus {
 };
 
 struct DevOut {
-  guac_threshold_record* trec;
+  guac_threshold_record* trec;   // general records (exact kernel); per-locus rows in counts mode
   guac_locus_counts* crec;
   uint32_t cap_rec;
+  unsigned long long* compact;   // single-base germline records of the tile kernels (guac_compact_record, include/guac.h)
+  uint32_t cap_compact;
   uint8_t* pool;
   uint32_t cap_pool;
   SlowLocus* slow;
   uint32_t cap_slow;
-  // counters: [0] records, [1] pool bytes, [2] slow loci, [3] visited loci, [4] tie loci, [5] counter overflow
+  uint32_t slow_ctr;             // which counter numbers the deferred loci of this launch: 2, or 8 for the second half of a call
+  // counters: [0] general records, [1] pool bytes, [2] slow loci, [3] visited loci, [4] tie loci, [5] counter overflow,
+  // [6] compact records, [7] a granule held too many records for the device-side ordering (the host finishes the sort)
   unsigned long long* counters;
   DevError* err;
 };
@@ -61,6 +65,67 @@ struct CallParams {
   int32_t skip_empty;
   int32_t sample;
 };
+
+// ---- compact records + the SNV part of callVariantsAtLocus, shared by both tile kernels --------------------------------------
+// guac_compact_record (include/guac.h): contig 63..48 | start 47..16 | alt 15..13 (0 "<ALT>", 1..4 A C G T) | ref code 12..11 |
+// gt0 10..9 | gt1 8..7 | tie 6.  Numeric order = canonical (contig, start, ref, alt) order.
+__device__ __forceinline__ unsigned long long compact_record(int contig, int locus, int rcode, int alt, uint32_t g0, uint32_t g1, uint32_t tie) {
+  return ((unsigned long long)(uint32_t)contig << 48) | ((unsigned long long)(uint32_t)locus << 16) | ((unsigned long long)alt << 13) |
+         ((unsigned long long)rcode << 11) | ((unsigned long long)g0 << 9) | ((unsigned long long)g1 << 7) | ((unsigned long long)tie << 6);
+}
+
+__device__ __forceinline__ void defer_locus(DevOut& out, int contig, int locus) {
+  const uint32_t s = (uint32_t)atomicAdd(&out.counters[out.slow_ctr], 1ull);
+  if (s < out.cap_slow) out.slow[s] = SlowLocus{contig, locus};
+}
+
+// GermlineThreshold.Caller.callVariantsAtLocus (commands/GermlineThresholdCaller.scala:90-179) on the A/C/G/T counts of one
+// locus: `total` elements, of which `o` are not plain bases and m1..m3 mismatch the reference base (code rcode) by class
+// (read code ^ reference code).  Loci the counts cannot decide exactly go to the exact kernel.
+__device__ __forceinline__ void call_snv_locus(const CallParams& prm, DevOut& out, int contig, int locus, int total, int o, int m1, int m2,
+                                               int m3, int rcode, bool std_ref, bool every_covered) {
+  // count * 100 / total > threshold  <=>  count * 100 >= (threshold + 1) * total   (integers, no division)
+  const long long bar = (long long)(prm.threshold_percent + 1) * total;
+  auto passes = [&](int count) { return (long long)count * 100 >= bar; };
+  // any allele made of "other" elements has count <= o: if o cannot pass the threshold the SNV counts decide alone
+  if (!(std_ref && !passes(o))) {
+    defer_locus(out, contig, locus);
+    return;
+  }
+  const int mref = total - o - m1 - m2 - m3;
+  if (!every_covered && !passes(max(m1, max(m2, m3)))) return;  // no alternate allele passes
+  // alleles in Allele.compare order (= base code order), stable-sorted by descending count: keep the best three
+  int c0 = -1, c1 = -1, c2 = -1, b0 = 0, b1 = 0, n = 0;
+#pragma unroll
+  for (int code = 0; code < 4; ++code) {
+    const int cls = code ^ rcode;
+    const int cntv = cls == 0 ? mref : cls == 1 ? m1 : cls == 2 ? m2 : m3;
+    if (cntv > 0 && passes(cntv)) {
+      ++n;
+      if (cntv > c0) { c2 = c1; c1 = c0; b1 = b0; c0 = cntv; b0 = code; }
+      else if (cntv > c1) { c2 = c1; c1 = cntv; b1 = code; }
+      else if (cntv > c2) { c2 = cntv; }
+    }
+  }
+  const uint32_t tie = (n >= 3 && c1 == c2) ? 1u : 0u;
+  if (tie) atomicAdd(&out.counters[4], 1ull);
+  int ne = 0, alt0 = 0, alt1 = 0;  // alt: 0 = "<ALT>", 1 + base code otherwise
+  uint32_t g0 = 0, g1 = 0;
+  if (n == 0) {
+    if (prm.emit_no_call) { ne = 1; g0 = g1 = GUAC_GT_NO_CALL; }
+  } else if (n == 1) {
+    if (b0 == rcode) { if (prm.emit_ref) { ne = 1; g0 = g1 = GUAC_GT_REF; } }
+    else { ne = 1; alt0 = 1 + b0; g0 = g1 = GUAC_GT_ALT; }
+  } else {
+    const bool v1 = b0 != rcode, v2 = b1 != rcode;
+    if (v1 != v2) { ne = 1; alt0 = 1 + (v1 ? b0 : b1); g0 = GUAC_GT_REF; g1 = GUAC_GT_ALT; }
+    else { ne = 2; alt0 = 1 + b0; alt1 = 1 + b1; g0 = GUAC_GT_ALT; g1 = GUAC_GT_OTHER_ALT; }
+  }
+  for (int k = 0; k < ne; ++k) {
+    const uint32_t s = (uint32_t)atomicAdd(&out.counters[6], 1ull);
+    if (s < out.cap_compact) out.compact[s] = compact_record(contig, locus, rcode, k == 0 ? alt0 : alt1, g0, g1, tie);
+  }
+}
 
 // ---- K_tile ---------------------------------------------------------------------------------------------------------------
 // One WARP owns one granule of 1024 loci and everything about it — its slice of shared memory, its reads, its scan, its
@@ -169,8 +234,8 @@ __device__ __forceinline__ void count_bits_nosync(CntT* cnt_word, uint32_t bits,
   while (bits) {
     const int b = __ffs(bits) - 1;
     bits &= bits - 1;
-    if constexpr (sizeof(CntT) == 8)
-      atomicAdd(reinterpret_cast<unsigned long long*>(cnt_word + b), 1ull << (FB * cls));
+    if constexpr (sizeof(CntT) == 8)  // (two native 32-bit halves: a 64-bit shared-memory atomic is a CAS loop)
+      atomicAdd(reinterpret_cast<uint32_t*>(cnt_word + b) + (cls >> 1), 1u << (FB * (cls & 1)));
     else
       atomicAdd(cnt_word + b, (CntT)1 << (FB * cls));
   }
@@ -183,11 +248,11 @@ __device__ __forceinline__ void count_bits(CntT* cnt_word, uint32_t bits, uint32
   while (bits) {
     const int b = __ffs(bits) - 1;
     bits &= bits - 1;
-    const int sh = FB * ((int)((x >> b) & 1u) | ((int)((y >> b) & 1u) << 1));
+    const int cls = (int)((x >> b) & 1u) | ((int)((y >> b) & 1u) << 1);
     if constexpr (sizeof(CntT) == 8)
-      atomicAdd(reinterpret_cast<unsigned long long*>(cnt_word + b), 1ull << sh);
+      atomicAdd(reinterpret_cast<uint32_t*>(cnt_word + b) + (cls >> 1), 1u << (FB * (cls & 1)));
     else
-      atomicAdd(cnt_word + b, (CntT)1 << sh);
+      atomicAdd(cnt_word + b, (CntT)1 << (FB * cls));
   }
   __syncwarp();
 }
@@ -324,18 +389,15 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     }
   };
 
-  // ---- phase 1a: one read per lane.  A read is stored as its differences against the reference track (mm[], built at pack
-  // time: mismatching bases and elements that are not plain bases): it costs two depth updates plus one shared-memory
-  // atomic per entry.  Reads with more entries than mm[] holds are listed for phase 1b (CIGAR walk).  The records of the next batch are fetched before the current one is worked on.
+  // ---- phase 1: one read per lane: two depth updates, then the read's planes / CIGAR walk.  The records of the next batch
+  // are fetched before the current one is worked on.
   ReadRec rec_next{0, 0, 0, 0};
-  uint4 mm_next = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-  if (first + lane < last) { rec_next = R.rec[first + lane]; mm_next = __ldg(&R.mm[first + lane]); }
+  if (first + lane < last) rec_next = R.rec[first + lane];
   for (uint32_t base = first; base < last; base += 32) {  // warp-uniform
     const uint32_t r = base + lane;
     const ReadRec rec = rec_next;
-    const uint4 mm = mm_next;
     rec_next = ReadRec{0, 0, 0, 0};
-    if (r + 32 < last) { rec_next = R.rec[r + 32]; mm_next = __ldg(&R.mm[r + 32]); }
+    if (r + 32 < last) rec_next = R.rec[r + 32];
     const bool active = r < last && rec.end > tile_lo && rec.start < tile_hi && rec.end > rec.start;
     if (active) {
       const int s = max(rec.start, tile_lo) - tile_lo, e = min(rec.end, tile_hi) - tile_lo;
@@ -346,46 +408,8 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
         S.pos.end(e);
       }
     }
-    const bool fast = active && (rec.info & kInfoMmList) != 0;
-    bool slow_now = false;
-    if (active && !fast) {
-      const uint32_t slot = atomicAdd(&S.n_list, 1u);
-      if (slot < (uint32_t)kListCap) S.list[slot] = r; else slow_now = true;
-    }
-    // entries are (reference offset << 2 | class); class = the counter field: 0 "other" element, 1..3 read base code ^
-    // reference base code.  A list of fewer than 8 entries carries its length in the last slot (0xFFF0 | n).
-    const uint32_t mmw[4] = {mm.x, mm.y, mm.z, mm.w};
-    const uint32_t last_slot = mm.w >> 16;
-    const int n_mine = fast ? (last_slot >= 0xFFF0u ? (int)(last_slot & 0xFu) : kMmSlots) : 0;
-    const int n_max = (int)__reduce_max_sync(0xFFFFFFFFu, (unsigned)n_mine);
-    const int rel = rec.start - tile_lo;
-#pragma unroll
-    for (int k = 0; k < kMmSlots; ++k) {
-      if (k >= n_max) break;  // warp-uniform
-      const uint32_t e = (k & 1) ? (mmw[k >> 1] >> 16) : (mmw[k >> 1] & 0xFFFFu);
-      const int x = rel + (int)(e >> 2);
-      if (k < n_mine && (unsigned)x < (unsigned)kWarpLoci) {
-        if constexpr (sizeof(CntT) == 8) atomicAdd(reinterpret_cast<unsigned long long*>(S.cnt + x), 1ull << (FB * (e & 3u)));
-        else atomicAdd(S.cnt + x, (CntT)1 << (FB * (e & 3u)));
-      }
-    }
+    general_read(r, rec, active);  // planes / CIGAR walk, in lockstep across the warp
     __syncwarp();
-    if (__any_sync(0xFFFFFFFFu, slow_now)) general_read(r, rec, slow_now);  // list overflow (very deep granules)
-    __syncwarp();
-  }
-  __syncwarp();
-  // ---- phase 1b: the listed reads, one per lane again
-  {
-    const uint32_t n_list = min(S.n_list, (uint32_t)kListCap);
-    for (uint32_t base = 0; base < n_list; base += 32) {
-      const uint32_t i = base + lane;
-      const bool active = i < n_list;
-      const uint32_t r = active ? S.list[i] : 0u;
-      ReadRec rec{0, 0, 0, 0};
-      if (active) rec = R.rec[r];
-      general_read(r, rec, active);
-      __syncwarp();
-    }
   }
   __syncwarp();
 
@@ -423,8 +447,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
     const uint8_t rbase = code_base(rcode);
     if (MODE == 1) {
       if (!std_ref && total > 0) {
-        uint32_t s = (uint32_t)atomicAdd(&out.counters[2], 1ull);
-        if (s < out.cap_slow) out.slow[s] = SlowLocus{td_contig, locus};
+        defer_locus(out, td_contig, locus);
         return;
       }
       uint32_t s = (uint32_t)atomicAdd(&out.counters[0], 1ull);
@@ -446,65 +469,7 @@ __global__ void __launch_bounds__(kTileThreads) k_pileup_tile(DevReads R, const 
       }
       return;
     }
-    // ---- GermlineThreshold.Caller.callVariantsAtLocus on the SNV alleles -------------------------------------------------
-    // count * 100 / total > threshold  <=>  count * 100 >= (threshold + 1) * total   (integers, no division)
-    const long long bar = (long long)(prm.threshold_percent + 1) * total;
-    auto passes = [&](int count) { return (long long)count * 100 >= bar; };
-    // any allele made of "other" elements has count <= o: if o cannot pass the threshold the SNV counts decide alone
-    const bool exact = std_ref && !passes(o);
-    if (!exact) {
-      uint32_t s = (uint32_t)atomicAdd(&out.counters[2], 1ull);
-      if (s < out.cap_slow) out.slow[s] = SlowLocus{td_contig, locus};
-      return;
-    }
-    const int mref = total - o - m1 - m2 - m3;
-    if (!every_covered && !passes(max(m1, max(m2, m3)))) return;  // no alternate allele passes
-    // alleles in Allele.compare order (= base code order), stable-sorted by descending count: keep the best three
-    int c0 = -1, c1 = -1, c2 = -1, b0 = 0, b1 = 0, n = 0;
-#pragma unroll
-    for (int code = 0; code < 4; ++code) {
-      const int cls = code ^ rcode;
-      const int cntv = cls == 0 ? mref : cls == 1 ? m1 : cls == 2 ? m2 : m3;
-      if (cntv > 0 && passes(cntv)) {
-        ++n;
-        if (cntv > c0) { c2 = c1; c1 = c0; b1 = b0; c0 = cntv; b0 = code; }
-        else if (cntv > c1) { c2 = c1; c1 = cntv; b1 = code; }
-        else if (cntv > c2) { c2 = cntv; }
-      }
-    }
-    const uint8_t tie = (n >= 3 && c1 == c2) ? 1 : 0;
-    if (tie) atomicAdd(&out.counters[4], 1ull);
-    int ne = 0;
-    uint8_t e_alt0 = 0, e_alt1 = 0, g0 = 0, g1 = 0;
-    bool sym = false;
-    if (n == 0) {
-      if (prm.emit_no_call) { ne = 1; sym = true; g0 = g1 = GUAC_GT_NO_CALL; }
-    } else if (n == 1) {
-      if (b0 == rcode) { if (prm.emit_ref) { ne = 1; sym = true; g0 = g1 = GUAC_GT_REF; } }
-      else { ne = 1; e_alt0 = code_base(b0); g0 = g1 = GUAC_GT_ALT; }
-    } else {
-      const bool v1 = b0 != rcode, v2 = b1 != rcode;
-      if (v1 != v2) { ne = 1; e_alt0 = code_base(v1 ? b0 : b1); g0 = GUAC_GT_REF; g1 = GUAC_GT_ALT; }
-      else { ne = 2; e_alt0 = code_base(b0); e_alt1 = code_base(b1); g0 = GUAC_GT_ALT; g1 = GUAC_GT_OTHER_ALT; }
-    }
-    for (int k = 0; k < ne; ++k) {
-      uint32_t s = (uint32_t)atomicAdd(&out.counters[0], 1ull);
-      if (s < out.cap_rec) {
-        guac_threshold_record rcd;
-        rcd.start = locus;
-        rcd.contig = td_contig;
-        rcd.sample = prm.sample;
-        rcd.ref_off = kPoolByteOff + rbase;
-        rcd.ref_len = 1;
-        rcd.alt_off = sym ? kPoolAltOff : kPoolByteOff + (k == 0 ? e_alt0 : e_alt1);
-        rcd.alt_len = sym ? 5 : 1;
-        rcd.gt[0] = g0;
-        rcd.gt[1] = g1;
-        rcd.tie = tie;
-        rcd.pad_ = 0;
-        out.trec[s] = rcd;
-      }
-    }
+    call_snv_locus(prm, out, td_contig, locus, total, o, m1, m2, m3, rcode, std_ref, every_covered);
   };
   // Sparse calls: the few loci of a granule that survive the reject (about three at a 1 % error rate) are parked in the
   // (now idle) read list and called afterwards side by side, instead of one lane at a time while 31 lanes wait.
@@ -1033,24 +998,13 @@ __device__ void exact_locus(const DevReads& R, const int contig, const int locus
 }
 
 
-// grid-stride over the loci K_tile deferred; their number is read from the device counter (no host round trip).
-// When `tile_rec` is set, K_tile wrote its sparse records to HBM and out.trec points into the pinned host block of the
-// result: the kernel first streams the K_tile records (counters[8] = their number, snapshot taken between the two kernels)
-// to the host block with coalesced 16-byte stores — posted PCIe writes that drain while the warps walk their loci —
-// and appends its own records behind them directly.
-__global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, const SlowLocus* __restrict__ loci, CallParams prm, DevOut out,
-                                                                 const guac_threshold_record* __restrict__ tile_rec) {
+// grid-stride over the loci the tile kernel deferred; their number is read from the device counter (no host round trip).
+// In germline mode out.trec / out.pool point into the pinned host block of the result (unified addressing): the few general
+// records and their allele bytes are written there directly.
+__global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, const SlowLocus* __restrict__ loci, CallParams prm, DevOut out) {
   __shared__ AlleleEntry tabs[kExactWarps][kMaxAlleles];
   __shared__ uint32_t rings[kExactWarps][64];
-  if (tile_rec) {
-    const unsigned long long n_tile = min(out.counters[8], (unsigned long long)out.cap_rec);
-    const unsigned long long n16 = n_tile * (sizeof(guac_threshold_record) / 16);
-    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(tile_rec);
-    uint4* dst = reinterpret_cast<uint4*>(out.trec);
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * blockDim.x)
-      dst[i] = src[i];
-  }
-  const uint32_t n_loci = (uint32_t)min(out.counters[2], (unsigned long long)out.cap_slow);
+  const uint32_t n_loci = (uint32_t)min(out.counters[out.slow_ctr], (unsigned long long)out.cap_slow);
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t t = warp; t < n_loci; t += n_warps) {
     exact_locus(R, loci[t].contig, loci[t].locus, prm, out, tabs[threadIdx.x >> 5], rings[threadIdx.x >> 5]);
@@ -1058,22 +1012,22 @@ __global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, con
   }
 }
 
-// ---- canonical record order on the device (sparse germline records) ----------------------------------------------------------
-// Records leave the kernels in atomic-counter order.  The canonical order (contig, start, sample, ref, alt) is restored with
-// a counting sort over granules — a record's granule is a monotone function of (contig, start) — followed by a small
-// insertion sort inside every granule (a granule holds a handful of sparse records), and the sorted records are streamed
-// to the pinned host block with coalesced stores.  Replaces a 4 ms host-side sort of 194 k records.
-__device__ __forceinline__ uint32_t record_bin(const DevReads& R, const guac_threshold_record& r) {
-  return R.contigs[r.contig].gran_off + (uint32_t)(r.start >> kGranuleShift);
+// ---- canonical record order on the device (compact germline records) ---------------------------------------------------------
+// Records leave the tile kernel in atomic-counter order.  A compact record's numeric value orders like (contig, start, ref,
+// alt), so the canonical order is restored with a counting sort over granules — a record's granule is a monotone function of
+// (contig, start) — followed by a small insertion sort inside every granule (a granule holds a handful of sparse records),
+// and the sorted records are streamed to the pinned host block with coalesced stores.
+__device__ __forceinline__ uint32_t record_bin(const DevReads& R, unsigned long long r) {
+  return R.contigs[(uint32_t)(r >> 48)].gran_off + (uint32_t)(((uint32_t)(r >> 16)) >> kGranuleShift);
 }
 
-__global__ void __launch_bounds__(256) k_rec_hist(DevReads R, const guac_threshold_record* __restrict__ rec, const unsigned long long* counters,
+__global__ void __launch_bounds__(256) k_rec_hist(DevReads R, const unsigned long long* __restrict__ rec, const unsigned long long* counters,
                                                   uint32_t cap_rec, uint32_t* __restrict__ hist) {
-  const uint32_t n = (uint32_t)min(counters[0], (unsigned long long)cap_rec);
+  const uint32_t n = (uint32_t)min(counters[6], (unsigned long long)cap_rec);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&hist[record_bin(R, rec[i])], 1u);
 }
 
-// exclusive scan of hist[0 .. n_bins] in place (one CTA; n_bins is tens of thousands), cursor = copy of the result
+// exclusive scan of hist[0 .. n_bins] in place (one CTA), cursor = copy of the result
 __global__ void __launch_bounds__(1024) k_rec_scan(uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, uint32_t n_bins) {
   __shared__ uint32_t warp_sum[32];
   __shared__ uint32_t carry;
@@ -1108,38 +1062,30 @@ __global__ void __launch_bounds__(1024) k_rec_scan(uint32_t* __restrict__ hist, 
   }
 }
 
-__global__ void __launch_bounds__(256) k_rec_scatter(DevReads R, const guac_threshold_record* __restrict__ rec, const unsigned long long* counters,
-                                                     uint32_t cap_rec, uint32_t* __restrict__ cursor, guac_threshold_record* __restrict__ grouped) {
-  const uint32_t n = (uint32_t)min(counters[0], (unsigned long long)cap_rec);
+__global__ void __launch_bounds__(256) k_rec_scatter(DevReads R, const unsigned long long* __restrict__ rec, const unsigned long long* counters,
+                                                     uint32_t cap_rec, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ grouped) {
+  const uint32_t n = (uint32_t)min(counters[6], (unsigned long long)cap_rec);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const guac_threshold_record r = rec[i];
+    const unsigned long long r = rec[i];
     grouped[atomicAdd(&cursor[record_bin(R, r)], 1u)] = r;
   }
 }
 
-__device__ inline bool record_less(const uint8_t* __restrict__ pool, const guac_threshold_record& a, const guac_threshold_record& b) {
-  if (a.start != b.start) return a.start < b.start;
-  if (a.sample != b.sample) return a.sample < b.sample;
-  const int nr = min((int)a.ref_len, (int)b.ref_len);
-  for (int i = 0; i < nr; ++i)
-    if (pool[a.ref_off + i] != pool[b.ref_off + i]) return pool[a.ref_off + i] < pool[b.ref_off + i];
-  if (a.ref_len != b.ref_len) return a.ref_len < b.ref_len;
-  const int na = min((int)a.alt_len, (int)b.alt_len);
-  for (int i = 0; i < na; ++i)
-    if (pool[a.alt_off + i] != pool[b.alt_off + i]) return pool[a.alt_off + i] < pool[b.alt_off + i];
-  return a.alt_len < b.alt_len;
-}
-
-// thread per granule: insertion sort of its records (starts[] = the scanned histogram)
-__global__ void __launch_bounds__(256) k_rec_finish(const uint32_t* __restrict__ starts, uint32_t n_bins, const uint8_t* __restrict__ pool, uint32_t cap_pool,
-                                                    guac_threshold_record* __restrict__ grouped) {
+// thread per granule: insertion sort of its records (starts[] = the scanned histogram).  Granules holding more records than
+// an insertion sort should see (dense outputs: emit-ref) are left to the host, which is told through counters[7].
+constexpr uint32_t kRecFinishMax = 96;
+__global__ void __launch_bounds__(256) k_rec_finish(const uint32_t* __restrict__ starts, uint32_t n_bins, unsigned long long* __restrict__ grouped,
+                                                    unsigned long long* counters) {
   for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_bins; g += gridDim.x * blockDim.x) {
     const uint32_t lo = starts[g], hi = starts[g + 1];
+    if (hi - lo > kRecFinishMax) {
+      counters[7] = 1ull;
+      continue;
+    }
     for (uint32_t i = lo + 1; i < hi; ++i) {
-      const guac_threshold_record x = grouped[i];
-      if ((unsigned long long)x.alt_off + x.alt_len > cap_pool) break;  // pool overflow: the host reruns the call
+      const unsigned long long x = grouped[i];
       uint32_t j = i;
-      while (j > lo && record_less(pool, x, grouped[j - 1])) {
+      while (j > lo && x < grouped[j - 1]) {
         grouped[j] = grouped[j - 1];
         --j;
       }
@@ -1148,11 +1094,11 @@ __global__ void __launch_bounds__(256) k_rec_finish(const uint32_t* __restrict__
   }
 }
 
-// coalesced copy of the sorted records to the pinned host block
-__global__ void __launch_bounds__(256) k_rec_flush(const guac_threshold_record* __restrict__ grouped, const unsigned long long* counters, uint32_t cap_rec,
-                                                   guac_threshold_record* __restrict__ host_rec) {
-  const unsigned long long n16 = min(counters[0], (unsigned long long)cap_rec) * (sizeof(guac_threshold_record) / 16);
-  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(grouped);
+// coalesced copy of the compact records to the pinned host block (16 bytes = two records per store)
+__global__ void __launch_bounds__(256) k_rec_flush(const unsigned long long* __restrict__ rec, const unsigned long long* counters, uint32_t cap_rec,
+                                                   unsigned long long* __restrict__ host_rec) {
+  const unsigned long long n16 = (min(counters[6], (unsigned long long)cap_rec) + 1) / 2;
+  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(rec);
   uint4* dst = reinterpret_cast<uint4*>(host_rec);
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * blockDim.x) dst[i] = src[i];
 }

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GUAC_ABI_VERSION 1
+#define GUAC_ABI_VERSION 2
 
 /* ---- status codes.  Each maps to the Scala exception the reference throws on this path. -------------- */
 typedef enum guac_status {
@@ -146,6 +146,12 @@ typedef struct guac_threshold_record {
   uint8_t pad_;
 } guac_threshold_record;
 
+/* Compact form of a guac_threshold_record whose reference and alternate are single bases (or the symbolic "<ALT>"): what the
+ * tile kernel emits, 8 bytes instead of 32 across PCIe / NVLink.  Bits: contig 63..48 | start 47..16 | alt 15..13 (0 = "<ALT>",
+ * 1..4 = A C G T) | ref 12..11 (0..3 = A C G T) | gt[0] 10..9 | gt[1] 8..7 | tie 6.  The numeric order of the values is the
+ * canonical (contig, start, ref, alt) order; the sample is the read set's. */
+typedef uint64_t guac_compact_record;
+
 /* variants/AlleleEvidence.scala:41-50 */
 typedef struct guac_allele_evidence {
   double likelihood;
@@ -255,9 +261,10 @@ const char* guac_status_string(guac_status s);
                                       them, somatic-standard needs them */
 #define GUAC_OPT_HOST_THREADS 3     /* [0 = all] host threads guac_reads_pack may use for its header pass (set it to
                                       cores / ranks when several ranks share one box) */
-#define GUAC_OPT_DIFFERENCE_LISTS 4  /* [1] guac_reads_pack also stores every read as its differences against the reference
-                                      track (16 B/read); the pileup kernels then skip the base planes and the CIGAR for
-                                      reads that fit.  0 = always walk planes / CIGAR (same results; a test knob) */
+#define GUAC_OPT_DIFFERENCE_LISTS 4  /* [1] guac_reads_pack also expands the reads into per-granule difference streams
+                                      (every element that differs from the reference track, plus per-locus start / end
+                                      counts): the germline kernels then do no per-read work.  0 = the call walks base planes
+                                      and CIGARs itself (same results; the cross-check the parity tests run) */
 guac_status guac_ctx_set_option(guac_ctx* ctx, int option, int64_t value);
 
 /* Device-side stopwatch on the context's stream (CUDA events): start, run any number of calls, stop -> elapsed ms. */
@@ -305,7 +312,13 @@ guac_status guac_allele_counts(guac_ctx* ctx, const guac_reads* reads, const gua
 
 /* ---- results (library-owned; pointers valid until guac_result_free) -------------------------------------- */
 size_t guac_result_n(const guac_result* r);
-const guac_threshold_record* guac_result_threshold_records(const guac_result* r); /* NULL if other kind */
+const guac_threshold_record* guac_result_threshold_records(const guac_result* r); /* NULL if other kind.  Built on first use
+                                                                                    from the compact + general records below */
+/* The records of a germline-threshold result as they crossed the bus: `*compact` (return value = their number, in canonical
+ * order when GUAC_OPT_SORT_RECORDS is on) + `*general` (`*n_general` records with variable-length alleles, from the exact
+ * per-locus kernel; unordered).  guac_result_n = the sum.  Any out pointer may be NULL. */
+size_t guac_result_compact_records(const guac_result* r, const guac_compact_record** compact,
+                                   const guac_threshold_record** general, size_t* n_general, int32_t* sample);
 const guac_somatic_record* guac_result_somatic_records(const guac_result* r);
 const guac_locus_counts* guac_result_counts(const guac_result* r);
 const guac_called_allele* guac_result_called_alleles(const guac_result* r);
