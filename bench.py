@@ -274,7 +274,7 @@ def main():
     views, keeps, n_reads, algorithmic = [], [], 0, 0.25 * n_loci
     for sample, depth in samples:
         sb = synth.generate(contigs, depth=depth, read_length=READ_LEN, seed=args.seed, sample=sample,
-                            window=(rank, 0, args.contig_length), n_reads=int(depth * args.contig_length / READ_LEN))
+                            window=(rank, 0, args.contig_length))
         n_reads += sb.n_reads
         algorithmic += algorithmic_bytes(sb.c, 0) + ((READ_LEN + 3) * sb.n_reads if somatic else 0)
         v, k = pinned_copy(sb.c)

@@ -87,6 +87,10 @@ class Context:
         """Pack straight from a guac_read_batch (e.g. the synthetic generator's buffers) without a numpy copy."""
         return PackedReads(self, None, None, batch_c=batch_c, contig_names=contig_names, sample_names=sample_names)
 
+    def pack_device(self, batch_c, contig_names=None, sample_names=None) -> "PackedReads":
+        """guac_reads_pack_device: the batch's columns already live in this context's device memory."""
+        return PackedReads(self, None, None, batch_c=batch_c, contig_names=contig_names, sample_names=sample_names, on_device=True)
+
     def pack(self, batch: ReadBatch, reference: Optional[Sequence[bytes]] = None) -> "PackedReads":
         return PackedReads(self, batch, reference)
 
@@ -95,7 +99,7 @@ class PackedReads:
     """guac_reads: one sample's start-sorted reads packed into the device SoA (guac_reads_pack)."""
 
     def __init__(self, ctx: Context, batch: Optional[ReadBatch], reference: Optional[Sequence[bytes]] = None,
-                 batch_c=None, contig_names=None, sample_names=None):
+                 batch_c=None, contig_names=None, sample_names=None, on_device=False):
         self.ctx = ctx
         self.contig_names = list(batch.contig_names if batch is not None else (contig_names or []))
         self.sample_names = list(batch.sample_names if batch is not None else (sample_names or ["default"]))
@@ -108,8 +112,8 @@ class PackedReads:
             data = np.frombuffer(b"".join(reference) or b"\0", dtype=np.uint8).copy()
             ref = abi.ReferenceC(len(reference), offs.ctypes.data_as(C.POINTER(C.c_uint64)),
                                  data.ctypes.data_as(C.POINTER(C.c_uint8)))
-        ctx._check(lib().guac_reads_pack(ctx._h, C.byref(b), C.byref(ref) if ref is not None else None,
-                                         C.byref(self._h)))
+        pack = lib().guac_reads_pack_device if on_device else lib().guac_reads_pack
+        ctx._check(pack(ctx._h, C.byref(b), C.byref(ref) if ref is not None else None, C.byref(self._h)))
 
     @property
     def n_reads(self) -> int:
@@ -167,15 +171,27 @@ class Result:
         self._h = _ResultHandle(handle)
         self._n = int(L.guac_result_n(handle))
         self._records = None
-        nb = C.c_size_t()
-        bp = L.guac_result_bytes(handle, C.byref(nb))
-        self.stats = abi.struct_to_dict(L.guac_result_stats(handle).contents)
-        if nb.value:
-            rawb = (C.c_uint8 * nb.value).from_address(C.cast(bp, C.c_void_p).value)
-            rawb._owner = self._h
-            self._bytes = memoryview(rawb).cast("B")
-        else:
-            self._bytes = memoryview(b"")
+        self._stats = None
+        self._pool = None
+
+    @property
+    def stats(self) -> dict:
+        if self._stats is None:
+            self._stats = abi.struct_to_dict(lib().guac_result_stats(self._h.h).contents)
+        return self._stats
+
+    @property
+    def _bytes(self):
+        if self._pool is None:
+            nb = C.c_size_t()
+            bp = lib().guac_result_bytes(self._h.h, C.byref(nb))
+            if nb.value:
+                rawb = (C.c_uint8 * nb.value).from_address(C.cast(bp, C.c_void_p).value)
+                rawb._owner = self._h
+                self._pool = memoryview(rawb).cast("B")
+            else:
+                self._pool = memoryview(b"")
+        return self._pool
 
     def _view(self, p, n, dt):
         if not n:
@@ -217,7 +233,8 @@ class Result:
     def free(self):
         """Detach from the library buffers (copying what is still referenced) and release them now."""
         self._records = self.records.copy()
-        self._bytes = memoryview(bytes(self._bytes))
+        self._pool = memoryview(bytes(self._bytes))
+        _ = self.stats
         self._h.release()
 
     def __len__(self):
@@ -369,3 +386,57 @@ def somatic_genotype_filter(records: np.ndarray, min_tumor_read_depth=0, max_tum
     if len(recs):
         lib().guac_somatic_genotype_filter(recs.ctypes.data_as(C.c_void_p), len(recs), C.byref(prm), keep.ctypes.data_as(C.c_void_p))
     return keep.astype(bool)
+
+
+DEPTH_BINS = 256
+
+
+def depth_histogram(ctx: Context, reads: PackedReads, loci_partitions, fetch: bool = True) -> Optional[np.ndarray]:
+    """guac_depth_histogram: hist[d] = requested loci covered by exactly d reads (last bin: deeper).  fetch = False leaves it
+    on the device for Comm.reduce_depth_histogram."""
+    arr, n = _ranges(loci_partitions)
+    hist = np.zeros(DEPTH_BINS, np.uint64) if fetch else None
+    ctx._check(lib().guac_depth_histogram(ctx._h, reads._h, arr, n,
+                                          hist.ctypes.data_as(C.POINTER(C.c_uint64)) if fetch else None))
+    return hist
+
+
+class Comm:
+    """guac_comm: NCCL communicator of the record gather, one per rank over that rank's Context.  `comm_id()` on one rank, the
+    bytes handed to every rank by the host side (here: torch.distributed / any broadcast), then Comm(ctx, id, rank, world)."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = lib().guac_comm_unique_id(buf)
+        if rc != 0:
+            raise GuacError(rc, "ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def __init__(self, ctx: Context, comm_id: bytes, rank: int, world: int):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(comm_id)
+        ctx._check(lib().guac_comm_create(ctx._h, buf, rank, world, C.byref(self._h)))
+
+    def gather(self, result: Result, root: int = 0) -> Result:
+        """guac_result_gather (collective): all ranks' germline-threshold records on `root`, in rank order."""
+        h = C.c_void_p()
+        self.ctx._check(lib().guac_result_gather(self._h, result._h.h, root, C.byref(h)))
+        return Result(h, "threshold")
+
+    def reduce_depth_histogram(self, root: int = 0) -> Optional[np.ndarray]:
+        hist = np.zeros(DEPTH_BINS, np.uint64)
+        self.ctx._check(lib().guac_comm_reduce_depth_histogram(self._h, root, hist.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return hist if self.rank == root else None
+
+    def close(self):
+        if self._h:
+            lib().guac_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

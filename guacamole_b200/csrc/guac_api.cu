@@ -21,6 +21,9 @@
 #include "guac_tile.cuh"
 #include "guac_somatic.cuh"
 #include "guac_standard.cuh"
+#include "guac_synth_device.cuh"
+#include "guac_comm.cuh"
+#include "../../include/guac_synth.h"
 
 namespace {
 
@@ -91,23 +94,24 @@ void settle_streams(guac_ctx* ctx, guac_reads& rd, uint64_t entries, bool field_
   fail(GUAC_ERR_CUDA, "difference streams did not converge");
 }
 
-void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* ref, guac_reads& out) {
+// `on_device`: the batch's column pointers are device memory of ctx's device (guac_reads_pack_device): no host -> device copies.
+void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* ref, guac_reads& out, bool on_device) {
   if (!b) fail(GUAC_ERR_INVALID_ARGUMENT, "null batch");
   const uint64_t n = b->n_reads;
   if (n >= 0xFFFFFFF0ull) fail(GUAC_ERR_UNSUPPORTED, "more than 2^32 reads in one read set: shard it");
-  if (n && (!b->contig || !b->start || !b->cigar_off || !b->seq_off || !b->seq || !b->qual || !b->mapq || !b->flags || !b->md_off))
+  const bool need_qual = ctx->pack_qualities != 0;
+  if (n && (!b->contig || !b->start || !b->cigar_off || !b->seq_off || !b->seq || (need_qual && !b->qual) || !b->mapq || !b->flags || !b->md_off))
     fail(GUAC_ERR_INVALID_ARGUMENT, "null column in read batch");
   out.ctx = ctx;
   out.n = n;
   out.n_contigs = b->n_contigs;
+  if (b->n_contigs == 0 && n) fail(GUAC_ERR_INVALID_ARGUMENT, "reads without contigs");
   if (ref && ref->n_contigs != b->n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "reference and batch disagree on the number of contigs");
 
   Trace tr("pack");
-  // The raw columns go first, on their own stream: from page-locked caller buffers these copies are asynchronous, overlap
-  // the host pass below and — the bases / qualities travel in chunks of reads — the pack kernels of the earlier chunks.
-  if (n && (b->cigar_off[n] >= 0xFFFFFFFFull || b->md_off[n] >= 0xFFFFFFFFull)) fail(GUAC_ERR_UNSUPPORTED, "cigar / MD columns too large: shard the read set");
-  cudaStream_t cs = ctx->copy_stream;
-  CUDA_OK(cudaEventRecord(ctx->copy_ev[5], ctx->stream));  // buffers handed back by earlier calls may still be in use there
+  nvtx_push("guac pack: copies + header kernel");
+  cudaStream_t cs = ctx->copy_stream, st = ctx->stream;
+  CUDA_OK(cudaEventRecord(ctx->copy_ev[5], st));  // buffers handed back by earlier calls may still be in use there
   CUDA_OK(cudaStreamWaitEvent(cs, ctx->copy_ev[5], 0));
   struct DrainOnError {  // a failed pack must not leave copies from the caller's buffers in flight
     guac_ctx* c;
@@ -116,168 +120,156 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
       if (std::uncaught_exceptions() > pending) {
         cudaStreamSynchronize(c->copy_stream);
         cudaStreamSynchronize(c->stream);
+        nvtx_pop();
       }
     }
   } drain{ctx};
-  out.has_qualities = ctx->pack_qualities != 0;
+  out.has_qualities = need_qual;
+  // totals of the variable-length columns (the last offsets)
+  uint64_t n_ops = 0, n_md = 0, n_bases = 0;
+  if (n) {
+    if (on_device) {
+      CUDA_OK(cudaMemcpyAsync(&n_ops, b->cigar_off + n, 8, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaMemcpyAsync(&n_md, b->md_off + n, 8, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaMemcpyAsync(&n_bases, b->seq_off + n, 8, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+    } else {
+      n_ops = b->cigar_off[n]; n_md = b->md_off[n]; n_bases = b->seq_off[n];
+    }
+  }
+  if (n_ops >= 0xFFFFFFFFull || n_md >= 0xFFFFFFFFull) fail(GUAC_ERR_UNSUPPORTED, "cigar / MD columns too large: shard the read set");
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  auto bring = [&](auto& dst, const auto* src, size_t count, size_t extra) {  // a column the store keeps: copied either way
+    dst.alloc(count + extra);
+    if (extra) CUDA_OK(cudaMemsetAsync(dst.p + count, 0, extra * sizeof(*dst.p), cs));
+    if (count) CUDA_OK(cudaMemcpyAsync(dst.p, src, count * sizeof(*dst.p), kind, cs));
+  };
+  // ---- the small columns first (copy stream), then the bases / qualities in chunks of reads: their copies run underneath
+  // the header kernel and the pack kernels of the earlier chunks
+  DevBuf<int32_t> t_contig, t_sample;
+  DevBuf<int64_t> t_start, d_contig_length;
+  DevBuf<uint64_t> t_cigar_off, t_md_off;
+  DevBuf<uint8_t> t_mapq, t_flags;
+  HeaderArgs H{};
+  H.n = n;
+  H.n_contigs = b->n_contigs;
+  bring(out.cigar, b->cigar, (size_t)n_ops, 1);
+  bring(out.seq_off, b->seq_off, n ? n + 1 : 0, n ? 0 : 1);
+  bring(out.md, b->md, (size_t)n_md, 16);
+  if (on_device) {
+    H.contig = b->contig; H.start = b->start; H.cigar_off = b->cigar_off; H.mapq = b->mapq; H.flags = b->flags;
+    H.sample = b->sample; H.md_off = b->md_off;
+  } else if (n) {
+    bring(t_contig, b->contig, n, 0);
+    bring(t_start, b->start, n, 0);
+    bring(t_cigar_off, b->cigar_off, n + 1, 0);
+    bring(t_md_off, b->md_off, n + 1, 0);
+    bring(t_mapq, b->mapq, n, 0);
+    bring(t_flags, b->flags, n, 0);
+    if (b->sample) bring(t_sample, b->sample, n, 0);
+    H.contig = t_contig.p; H.start = t_start.p; H.cigar_off = t_cigar_off.p; H.mapq = t_mapq.p; H.flags = t_flags.p;
+    H.sample = b->sample ? t_sample.p : nullptr; H.md_off = t_md_off.p;
+  }
+  H.cigar = out.cigar.p;
+  H.seq_off = out.seq_off.p;
+  if (b->contig_length) {
+    d_contig_length.alloc(b->n_contigs + 1);
+    CUDA_OK(cudaMemcpyAsync(d_contig_length.p, b->contig_length, b->n_contigs * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+    H.contig_length = d_contig_length.p;
+  }
+  CUDA_OK(cudaEventRecord(ctx->copy_ev[4], cs));  // the small columns are on the device
+  out.seq.alloc((size_t)n_bases + 64);
+  CUDA_OK(cudaMemsetAsync(out.seq.p + n_bases, 0, 64, cs));
+  if (need_qual) {
+    out.qual.alloc((size_t)n_bases + 64);
+    CUDA_OK(cudaMemsetAsync(out.qual.p + n_bases, 0, 64, cs));
+  }
   constexpr int kMaxCopyChunks = 4;
   const int n_copy_chunks = n >= 1000000 ? kMaxCopyChunks : 1;
-  uint64_t chunk_read[kMaxCopyChunks + 1];
+  uint64_t chunk_read[kMaxCopyChunks + 1], chunk_byte[kMaxCopyChunks + 1];
   for (int k = 0; k <= n_copy_chunks; ++k) chunk_read[k] = n * (uint64_t)k / (uint64_t)n_copy_chunks;
-  auto copy_bases_chunk = [&](int k) {  // bases (+ qualities) of reads [chunk_read[k], chunk_read[k + 1]), then its event
-    const uint64_t o0 = b->seq_off[chunk_read[k]], o1 = b->seq_off[chunk_read[k + 1]];
-    if (o1 > o0) {
-      CUDA_OK(cudaMemcpyAsync(out.seq.p + o0, b->seq + o0, o1 - o0, cudaMemcpyHostToDevice, cs));
-      if (out.has_qualities) CUDA_OK(cudaMemcpyAsync(out.qual.p + o0, b->qual + o0, o1 - o0, cudaMemcpyHostToDevice, cs));
-    }
-    CUDA_OK(cudaEventRecord(ctx->copy_ev[k], cs));
-  };
-  int chunks_before_host_pass = 0;
   if (n) {
-    h2d_on(cs, out.cigar, b->cigar, (size_t)b->cigar_off[n], 1);
-    h2d_on(cs, out.seq_off, b->seq_off, n + 1);
-    h2d_on(cs, out.md, b->md, (size_t)b->md_off[n], 16);
-    const size_t n_bases = (size_t)b->seq_off[n];
-    out.seq.alloc(n_bases + 64);
-    CUDA_OK(cudaMemsetAsync(out.seq.p + n_bases, 0, 64, cs));
-    if (out.has_qualities) {
-      out.qual.alloc(n_bases + 64);
-      CUDA_OK(cudaMemsetAsync(out.qual.p + n_bases, 0, 64, cs));
+    if (on_device) {  // (fixed offsets cannot be assumed: fetch the few chunk boundaries)
+      for (int k = 0; k <= n_copy_chunks; ++k) CUDA_OK(cudaMemcpyAsync(&chunk_byte[k], b->seq_off + chunk_read[k], 8, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+    } else {
+      for (int k = 0; k <= n_copy_chunks; ++k) chunk_byte[k] = b->seq_off[chunk_read[k]];
     }
-    chunks_before_host_pass = n_copy_chunks == 1 ? 1 : 2;  // what the copy engine gets through while the host pass runs
-    for (int k = 0; k < chunks_before_host_pass; ++k) copy_bases_chunk(k);
-  } else {
-    out.seq.alloc(64); out.qual.alloc(64); out.cigar.alloc(1); out.md.alloc(16);
-    static const uint64_t zero = 0;
-    h2d_on(cs, out.seq_off, &zero, 1);
-  }
-  // ---- host pass over the read headers: O(reads + cigar ops); everything per-base happens on the device
-  // header columns are built in a pinned arena owned by the context (no page faults after the first call, fast H2D)
-  const size_t col = ((n + 1) * sizeof(uint32_t) + 63) & ~(size_t)63;
-  unsigned char* arena = pack_arena(ctx, (n + 1) * sizeof(ReadRec) + 64 + 3 * col);
-  ReadRec* rec = reinterpret_cast<ReadRec*>(arena);
-  uint32_t* cig_off = reinterpret_cast<uint32_t*>(arena + (((n + 1) * sizeof(ReadRec) + 63) & ~(size_t)63));
-  uint32_t* md_off = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(cig_off) + col);
-  uint32_t* read_contig = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(md_off) + col);
-  std::vector<int64_t> contig_end(b->n_contigs, 0);
-  std::vector<uint64_t> contig_first(b->n_contigs, ~0ull), contig_last(b->n_contigs, 0);
-  out.sample = n ? (b->sample ? b->sample[0] : 0) : 0;
-  const int32_t sample0 = out.sample;
-  // Reads are independent except for the order checks (which look at read i - 1 in the input) and the running pair offset
-  // (chunk-local first, rebased after an exclusive scan over the chunks): the pass runs on all host threads.
-  struct Chunk {
-    uint64_t begin = 0, end = 0, pairs = 0;
-    int64_t max_span = 0;
-    std::vector<std::pair<uint64_t, int32_t>> runs;  // (first read, contig) of every contig run that starts in the chunk
-    std::vector<int64_t> contig_end;
-    StatusError err{GUAC_OK, ""};
-  };
-  const unsigned hw = ctx->host_threads > 0 ? (unsigned)ctx->host_threads : std::max(1u, std::thread::hardware_concurrency());
-  const size_t n_chunks = n < 200000 ? 1 : std::min<size_t>(hw, 64);
-  std::vector<Chunk> chunks(n_chunks);
-  auto header_pass = [&](Chunk& ch) {
-    ch.contig_end.assign(b->n_contigs, 0);
-    uint64_t pair_total = 0;
-    try {
-      for (uint64_t i = ch.begin; i < ch.end; ++i) {
-        const int32_t c = b->contig[i];
-        if (c < 0 || (uint32_t)c >= b->n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "read %llu: contig index %d out of range", (unsigned long long)i, c);
-        const int64_t start = b->start[i];
-        if (i == 0 || b->contig[i - 1] != c) ch.runs.push_back({i, c});
-        else if (start < b->start[i - 1]) fail(GUAC_ERR_UNSORTED_READS, "Regions must be sorted by start locus (read %llu)", (unsigned long long)i);
-        if (start < 0) fail(GUAC_ERR_INVALID_ARGUMENT, "read %llu: negative start", (unsigned long long)i);
-        if (b->sample && b->sample[i] != sample0) fail(GUAC_ERR_UNSUPPORTED, "one read set must hold one sample (split by sample before packing)");
-        if (!(b->flags[i] & GUAC_READ_HAS_MD)) fail(GUAC_ERR_MISSING_MD, "read %llu has no MD tag (the callers load reads with hasMdTag = true)", (unsigned long long)i);
-        const uint64_t c0 = b->cigar_off[i], c1 = b->cigar_off[i + 1];
-        const uint64_t read_len = b->seq_off[i + 1] - b->seq_off[i];
-        if (read_len > (uint64_t)kMaxReadLen) fail(GUAC_ERR_UNSUPPORTED, "read %llu longer than %d bases", (unsigned long long)i, kMaxReadLen);
-        int64_t ref_len = 0, consumed = 0, lead = 0;
-        int phase = 0;  // 0 leading clips, 1 inside the aligned run, 2 trailing clips
-        bool simple = true;
-        for (uint64_t k = c0; k < c1; ++k) {
-          const uint32_t op = b->cigar[k] & 0xF, len = b->cigar[k] >> 4;
-          if (op > 8 || op == GUAC_CIGAR_P) fail(GUAC_ERR_INVALID_CIGAR, "read %llu: unsupported CIGAR operator %u", (unsigned long long)i, op);
-          if (len == 0) fail(GUAC_ERR_INVALID_CIGAR, "read %llu: zero-length CIGAR element", (unsigned long long)i);
-          const bool m = op == GUAC_CIGAR_M || op == GUAC_CIGAR_EQ || op == GUAC_CIGAR_X;
-          if (m || op == GUAC_CIGAR_D || op == GUAC_CIGAR_N) ref_len += len;
-          if (m || op == GUAC_CIGAR_I || op == GUAC_CIGAR_S) consumed += len;
-          if (m) {
-            if (phase == 2) simple = false;
-            phase = 1;
-          } else if (op == GUAC_CIGAR_S || op == GUAC_CIGAR_H) {
-            if (phase == 0) {
-              if (op == GUAC_CIGAR_S) lead += len;
-            } else
-              phase = 2;
-          } else {
-            simple = false;
-          }
-        }
-        if (c1 == c0) simple = false;
-        if ((uint64_t)consumed != read_len) fail(GUAC_ERR_INVALID_CIGAR, "read %llu: CIGAR consumes %lld bases, the read has %llu", (unsigned long long)i, (long long)consumed, (unsigned long long)read_len);
-        const int64_t end = start + ref_len;
-        if (end > 0x7FFFFF00ll) fail(GUAC_ERR_UNSUPPORTED, "read %llu: coordinates beyond 2^31", (unsigned long long)i);
-        if (b->contig_length && end > b->contig_length[c]) fail(GUAC_ERR_INVALID_ARGUMENT, "read %llu ends past its contig", (unsigned long long)i);
-        if (simple && lead > 0xFFFF) simple = false;
-        ch.contig_end[c] = std::max(ch.contig_end[c], end);
-        ch.max_span = std::max<int64_t>(ch.max_span, ref_len);
-        uint32_t info = (uint32_t)(simple ? (lead & 0xFFFF) : 0) | (simple ? kInfoSimple : 0) |
-                        ((b->flags[i] & GUAC_READ_POSITIVE_STRAND) ? kInfoPositive : 0) | (ref_len == 0 ? kInfoEmpty : 0) |
-                        ((uint32_t)b->mapq[i] << kInfoMapqShift);
-        rec[i] = ReadRec{(int32_t)start, (int32_t)end, (uint32_t)pair_total, info};  // pair_off is chunk-local here
-        cig_off[i] = (uint32_t)c0;
-        md_off[i] = (uint32_t)b->md_off[i];
-        read_contig[i] = (uint32_t)c;
-        pair_total += (read_len + 31) / 32;
+    for (int k = 0; k < n_copy_chunks; ++k) {
+      const uint64_t o0 = chunk_byte[k], o1 = chunk_byte[k + 1];
+      if (o1 > o0) {
+        CUDA_OK(cudaMemcpyAsync(out.seq.p + o0, b->seq + o0, o1 - o0, kind, cs));
+        if (need_qual) CUDA_OK(cudaMemcpyAsync(out.qual.p + o0, b->qual + o0, o1 - o0, kind, cs));
       }
-    } catch (const StatusError& e) {
-      ch.err = e;
+      CUDA_OK(cudaEventRecord(ctx->copy_ev[k], cs));
     }
-    ch.pairs = pair_total;
-  };
-  for (size_t k = 0; k < n_chunks; ++k) {
-    chunks[k].begin = n * k / n_chunks;
-    chunks[k].end = n * (k + 1) / n_chunks;
   }
+  // ---- header kernel: per-read checks + derived columns, the plane offsets by a scan
+  DevBuf<uint32_t> d_read_contig, d_n_pairs, d_pair_off, conflict, gran_count;
+  DevBuf<unsigned long long> d_summary;  // [0..2] summary, then contig_first / contig_last / contig_end
+  const size_t nc = b->n_contigs;
+  d_summary.alloc(4 + 3 * nc);
   {
-    std::vector<std::thread> th;
-    for (size_t k = 1; k < n_chunks; ++k) th.emplace_back(header_pass, std::ref(chunks[k]));
-    header_pass(chunks[0]);
-    for (auto& t : th) t.join();
+    std::vector<unsigned long long> init(4 + 3 * nc, 0ull);
+    init[0] = ~0ull;
+    for (size_t c = 0; c < nc; ++c) init[4 + c] = ~0ull;
+    CUDA_OK(cudaMemcpyAsync(d_summary.p, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));  // (init goes out of scope)
   }
+  out.rec.alloc(n + 1);
+  out.cig_off.alloc(n + 1);
+  out.md_off.alloc(n + 1);
+  d_read_contig.alloc(n + 1);
+  d_n_pairs.alloc(n + 1);
+  d_pair_off.alloc(n + 2);
+  H.rec = out.rec.p;
+  H.cig_off32 = out.cig_off.p;
+  H.md_off32 = out.md_off.p;
+  H.read_contig = d_read_contig.p;
+  H.n_pairs = d_n_pairs.p;
+  H.summary = d_summary.p;
+  H.contig_first = d_summary.p + 4;
+  H.contig_last = d_summary.p + 4 + nc;
+  H.contig_end = reinterpret_cast<long long*>(d_summary.p + 4 + 2 * nc);
+  CUDA_OK(cudaStreamWaitEvent(st, ctx->copy_ev[4], 0));
+  CUDA_OK(cudaEventRecord(ctx->ev[0], st));
   uint64_t pair_total = 0;
-  {
-    std::vector<char> contig_seen(b->n_contigs, 0);
-    int32_t open_contig = -1;
-    for (auto& ch : chunks) {
-      if (ch.err.code != GUAC_OK) throw ch.err;  // chunks are in read order: the first failing read wins
-      for (auto& run : ch.runs) {
-        if (contig_seen[run.second]) fail(GUAC_ERR_CONTIG_ORDER, "Regions are not sorted by contig (read %llu)", (unsigned long long)run.first);
-        contig_seen[run.second] = 1;
-        if (open_contig >= 0) contig_last[open_contig] = run.first;
-        open_contig = run.second;
-        contig_first[run.second] = run.first;
-      }
-      for (uint32_t c = 0; c < b->n_contigs; ++c) contig_end[c] = std::max(contig_end[c], ch.contig_end[c]);
-      out.max_ref_span = std::max(out.max_ref_span, ch.max_span);
-      const uint64_t base = pair_total;
-      pair_total += ch.pairs;
-      if (pair_total >= 0xFFFFFF00ull) fail(GUAC_ERR_UNSUPPORTED, "more than 2^37 bases in one read set: shard it");
-      ch.pairs = base;  // now the chunk's base offset
-    }
-    if (open_contig >= 0) contig_last[open_contig] = n;
-    std::vector<std::thread> th;
-    auto rebase = [&](const Chunk& ch) {
-      if (ch.pairs == 0) return;
-      for (uint64_t i = ch.begin; i < ch.end; ++i) rec[i].pair_off += (uint32_t)ch.pairs;
-    };
-    for (size_t k = 1; k < n_chunks; ++k) th.emplace_back(rebase, std::cref(chunks[k]));
-    rebase(chunks[0]);
-    for (auto& t : th) t.join();
+  if (n) {
+    k_header<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(H);
+    pair_total = device_exclusive_scan<uint32_t>(ctx, d_n_pairs.p, n, d_pair_off.p);
+    if (pair_total >= 0xFFFFFF00ull) fail(GUAC_ERR_UNSUPPORTED, "more than 2^37 bases in one read set: shard it");
+    k_header_finish<<<grid_for(n + 1, 256, ctx->sm_count), 256, 0, st>>>(out.rec.p, d_pair_off.p, out.cig_off.p, out.md_off.p, H.cigar_off, H.md_off, n);
+  } else {
+    const ReadRec sentinel{0x7FFFFFFF, 0x7FFFFFFF, 0u, 0u};
+    CUDA_OK(cudaMemcpyAsync(out.rec.p, &sentinel, sizeof sentinel, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemsetAsync(out.cig_off.p, 0, 4, st));
+    CUDA_OK(cudaMemsetAsync(out.md_off.p, 0, 4, st));
   }
-  rec[n] = ReadRec{0x7FFFFFFF, 0x7FFFFFFF, (uint32_t)pair_total, 0};
-  cig_off[n] = (uint32_t)b->cigar_off[n];
-  md_off[n] = (uint32_t)b->md_off[n];
+  std::vector<unsigned long long> summary(4 + 3 * nc);
+  CUDA_OK(cudaMemcpyAsync(summary.data(), d_summary.p, summary.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (n && summary[0] != ~0ull) {
+    const unsigned long long read = summary[0] >> 8;
+    const guac_status code = (guac_status)(summary[0] & 0xFF);
+    const char* why = code == GUAC_ERR_UNSORTED_READS ? "Regions must be sorted by start locus"
+                      : code == GUAC_ERR_CONTIG_ORDER ? "Regions are not sorted by contig"
+                      : code == GUAC_ERR_MISSING_MD   ? "the read has no MD tag (the callers load reads with hasMdTag = true)"
+                      : code == GUAC_ERR_INVALID_CIGAR ? "unsupported or inconsistent CIGAR (operator, zero length, or bases consumed != read length)"
+                      : code == GUAC_ERR_UNSUPPORTED  ? "unsupported read (several samples in one read set, read too long, or coordinates beyond 2^31)"
+                                                      : "contig index or coordinates out of range";
+    fail(code, "read %llu: %s", read, why);
+  }
+  out.max_ref_span = (int64_t)summary[1];
+  out.sample = n ? (int32_t)(uint32_t)summary[2] : 0;
+  std::vector<int64_t> contig_end(nc, 0);
+  std::vector<uint64_t> contig_first(nc, ~0ull), contig_last(nc, 0);
+  for (size_t c = 0; c < nc; ++c) {
+    contig_first[c] = summary[4 + c];
+    contig_last[c] = summary[4 + nc + c];
+    contig_end[c] = (int64_t)summary[4 + 2 * nc + c];
+  }
+  nvtx_pop();
+  nvtx_push("guac pack: kernels");
 
   tr.lap("header pass");
   // ---- contig geometry
@@ -303,24 +295,13 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   out.total_words = word_off;
   out.total_grans = gran_off;
 
-  // ---- H2D of the raw columns
-  cudaStream_t st = ctx->stream;
-  h2d_on(cs, out.rec, rec, n + 1);
-  h2d_on(cs, out.cig_off, cig_off, n + 1);
-  h2d_on(cs, out.md_off, md_off, n + 1);
-  h2d_on(cs, out.d_contigs, out.contigs.data(), out.contigs.size());
-  DevBuf<uint32_t> d_read_contig, conflict, gran_count;
-  h2d_on(cs, d_read_contig, read_contig, n);
-  CUDA_OK(cudaEventRecord(ctx->copy_ev[4], cs));  // the derived columns are on the device
-  if (n)
-    for (int k = chunks_before_host_pass; k < n_copy_chunks; ++k) copy_bases_chunk(k);
   out.pairs.alloc(pair_total + 8);
   out.xmask.alloc(pair_total + 8);
   out.nm.alloc(n);
   out.del_start.alloc(n);
   out.del_md.alloc(n);
   out.del_len.alloc(n);
-  if (out.has_qualities) out.qc.alloc((n ? (size_t)b->seq_off[n] : 0) + 64);
+  if (out.has_qualities) out.qc.alloc((size_t)n_bases + 64);
   CUDA_OK(cudaMemsetAsync(out.pairs.p, 0, out.pairs.bytes(), st));
   CUDA_OK(cudaMemsetAsync(out.xmask.p, 0, out.xmask.bytes(), st));
   out.trk_lo.alloc(word_off + 1);
@@ -341,10 +322,11 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     h2d(ctx, out.fasta_off, ref->base_off, (size_t)ref->n_contigs + 1);
     h2d(ctx, out.fasta, ref->bases, (size_t)ref->base_off[ref->n_contigs], 16);
   }
+  h2d(ctx, out.d_contigs, out.contigs.data(), out.contigs.size());
   CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
-  CUDA_OK(cudaStreamWaitEvent(st, ctx->copy_ev[4], 0));  // kernels below read the small raw columns and the derived ones
-  out.h2d_bytes = out.rec.bytes() + out.cig_off.bytes() * 2 + out.cigar.bytes() + out.seq_off.bytes() + out.seq.bytes() +
-                  out.qual.bytes() + out.md.bytes() + out.d_contigs.bytes() + d_read_contig.bytes() + out.fasta.bytes();
+  out.h2d_bytes = on_device ? out.d_contigs.bytes() + out.fasta.bytes()
+                            : n * (4 + 8 + 8 + 8 + 1 + 1 + (b->sample ? 4 : 0) + 8) + out.cigar.bytes() + out.seq.bytes() + out.qual.bytes() +
+                                  out.md.bytes() + out.d_contigs.bytes() + out.fasta.bytes();
 
   if (tr.on) { cudaStreamSynchronize(cs); cudaStreamSynchronize(st); }
   tr.lap("alloc + h2d");
@@ -370,8 +352,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   A.err = ctx->d_err;
   A.counters = ctx->d_counters;
 
-  CUDA_OK(cudaEventRecord(ctx->ev[0], st));
-  out.pack_launches = 0;
+  out.pack_launches = n ? 5 : 0;  // header kernel + scan
   if (n) {
     A.r_begin = 0;
     A.r_end = n;
@@ -417,6 +398,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   out.max_reads_per_granule = counters[1];
   if (n && ctx->difference_lists) settle_streams(ctx, out, counters[2], counters[3] != 0, /*was_huge=*/false);
   tr.lap("kernels");
+  nvtx_pop();
 }
 
 // ---- tiles over the requested loci -------------------------------------------------------------------------------------------
@@ -499,6 +481,8 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
   res.stats.loci_requested = requested;
   res.stats.order_sensitive_loci = reads.order_sensitive_loci;
   res.sample = reads.sample;
+  res.owner = ctx;
+  res.generation = ++ctx->generation;
   auto append_rows_past_track = [&] {  // requested loci past the end of the track hold no reads: empty pileups, reference base N
     if (prm.mode != 1 || prm.skip_empty) return;
     for (size_t i = 0; i < n_ranges; ++i) {
@@ -535,7 +519,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
   uint64_t cap_pool = kPoolDynOff + std::max<uint64_t>(65536, tile_loci / 64);
   if (counts_mode) cap_rec = std::max<uint64_t>(cap_rec, ctx->out_rec.n / sizeof(guac_locus_counts));
   cap_compact = std::max<uint64_t>(cap_compact, ctx->out_compact.n / 8);
-  cap_slow = std::max<uint64_t>(cap_slow, ctx->out_slow.n / sizeof(SlowLocus));
+  cap_slow = std::max<uint64_t>(cap_slow, ctx->out_slow.n / sizeof(SlowLocus) / 2);  // (two segments share the buffer)
   if (counts_mode) cap_pool = std::max<uint64_t>(cap_pool, ctx->out_pool.n);
   const bool streams = reads.gs_hdr.n != 0;
   // narrow counter fields (8 bits) unless the store is wide; the tile kernel reports a possible overflow and we widen
@@ -682,6 +666,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       res.general = (guac_threshold_record*)((unsigned char*)res.block + full_at);
       res.n_general = (size_t)n_rec;
       res.compact = h_compact;
+      res.d_compact = device_sorted ? (const unsigned long long*)ctx->sort_rec.p : (const unsigned long long*)ctx->out_compact.p;
       res.n_compact = (size_t)c[6];
       res.n_records = res.n_general + res.n_compact;
       res.bytes = (const uint8_t*)res.block;
@@ -825,6 +810,7 @@ void guac_ctx_destroy(guac_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->d_hist) cudaFree(ctx->d_hist);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
@@ -901,7 +887,7 @@ guac_status guac_reads_pack(guac_ctx* ctx, const guac_read_batch* batch, const g
     CUDA_OK(cudaSetDevice(ctx->device));
     std::unique_ptr<guac_reads> r(new guac_reads());
     try {
-      pack_reads(ctx, batch, ref, *r);
+      pack_reads(ctx, batch, ref, *r, false);
     } catch (...) {
       cudaStreamSynchronize(ctx->stream);  // copies from the caller's buffers may still be in flight
       throw;
@@ -909,6 +895,60 @@ guac_status guac_reads_pack(guac_ctx* ctx, const guac_read_batch* batch, const g
     *out = r.release();
   });
 }
+
+guac_status guac_reads_pack_device(guac_ctx* ctx, const guac_read_batch* device_batch, const guac_reference* ref, guac_reads** out) {
+  if (!ctx || !out) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    std::unique_ptr<guac_reads> r(new guac_reads());
+    try {
+      pack_reads(ctx, device_batch, ref, *r, true);
+    } catch (...) {
+      cudaStreamSynchronize(ctx->stream);
+      throw;
+    }
+    *out = r.release();
+  });
+}
+
+// ---- device build of the synthetic read generator (include/guac_synth.h) ---------------------------------------------------
+guac_status guac_synth_generate_device(guac_ctx* ctx, const guac_synth_params* p, guac_synth_device_batch** out) {
+  if (!ctx || !p || !out) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    std::unique_ptr<guac_synth_device_batch> b(new guac_synth_device_batch());
+    nvtx_push("guac synth (device)");
+    try {
+      synth_generate_device(ctx, *p, *b);
+    } catch (...) {
+      nvtx_pop();
+      throw;
+    }
+    nvtx_pop();
+    *out = b.release();
+  });
+}
+const guac_read_batch* guac_synth_device_batch_view(const guac_synth_device_batch* b) { return b ? &b->view : nullptr; }
+double guac_synth_device_batch_ms(const guac_synth_device_batch* b) { return b ? b->kernel_ms : 0.0; }
+void guac_synth_device_batch_free(guac_synth_device_batch* b) {
+  if (!b) return;
+  if (b->ctx) cudaSetDevice(b->ctx->device);
+  delete b;
+}
+guac_status guac_synth_device_batch_download(guac_ctx* ctx, const guac_synth_device_batch* b, int pinned, guac_synth_host_batch** out) {
+  if (!ctx || !b || !out) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    std::unique_ptr<guac_synth_host_batch> h(new guac_synth_host_batch());
+    synth_download(ctx, *b, pinned != 0, *h);
+    *out = h.release();
+  });
+}
+const guac_read_batch* guac_synth_host_batch_view(const guac_synth_host_batch* b) { return b ? &b->view : nullptr; }
+void guac_synth_host_batch_free(guac_synth_host_batch* b) { delete b; }
 
 void guac_reads_free(guac_reads* reads) {
   if (!reads) return;
@@ -1185,6 +1225,339 @@ guac_status guac_partition_loci_uniformly(int64_t tasks, const guac_locus_range*
   flush();
   *n_out = n;
   return n > max_out && out ? GUAC_ERR_INVALID_ARGUMENT : GUAC_OK;
+}
+
+// ---- depth histogram + the NCCL exchange (guac_comm.cuh) --------------------------------------------------------------------
+guac_status guac_depth_histogram(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges, size_t n_ranges, uint64_t* hist) {
+  if (!ctx || !reads || (n_ranges && !ranges)) return GUAC_ERR_INVALID_ARGUMENT;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    if (!reads->gs_hdr.n && reads->n) fail(GUAC_ERR_UNSUPPORTED, "the depth histogram reads the difference streams (GUAC_OPT_DIFFERENCE_LISTS = 1)");
+    cudaStream_t st = ctx->stream;
+    if (!ctx->d_hist) CUDA_OK(cudaMalloc((void**)&ctx->d_hist, kDepthBins * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemsetAsync(ctx->d_hist, 0, kDepthBins * sizeof(unsigned long long), st));
+    uint64_t tile_loci = 0;
+    const uint64_t requested = prepare_tiles(ctx, *reads, ranges, n_ranges, &tile_loci);
+    if (ctx->n_tiles) {
+      const size_t smem = (size_t)kHistWarps * kDepthBins * 32 * sizeof(uint32_t);
+      if (!ctx->hist_attr_done) {
+        CUDA_OK(cudaFuncSetAttribute(k_depth_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->hist_attr_done = true;
+      }
+      const int grid = (int)std::min<uint64_t>((ctx->n_tiles + kHistWarps - 1) / kHistWarps, (uint64_t)ctx->sm_count);
+      k_depth_histogram<<<grid, kHistWarps * 32, smem, st>>>(reads->view(), (const TileDesc*)ctx->tiles.p, (uint32_t)ctx->n_tiles, ctx->d_hist);
+      CUDA_OK(cudaGetLastError());
+    }
+    if (hist) {
+      CUDA_OK(cudaMemcpyAsync(hist, ctx->d_hist, kDepthBins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      hist[0] += requested - tile_loci;  // requested loci past the track hold no reads
+    } else if (requested > tile_loci) {
+      const unsigned long long extra = requested - tile_loci;
+      unsigned long long h0 = 0;
+      CUDA_OK(cudaMemcpyAsync(&h0, ctx->d_hist, 8, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      h0 += extra;
+      CUDA_OK(cudaMemcpyAsync(ctx->d_hist, &h0, 8, cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+    }
+  });
+}
+
+guac_status guac_comm_unique_id(uint8_t* id) {
+  if (!id) return GUAC_ERR_INVALID_ARGUMENT;
+  static_assert(sizeof(ncclUniqueId) <= GUAC_COMM_ID_BYTES, "ncclUniqueId fits the id buffer");
+  ncclUniqueId u;
+  if (ncclGetUniqueId(&u) != ncclSuccess) return GUAC_ERR_CUDA;
+  memset(id, 0, GUAC_COMM_ID_BYTES);
+  memcpy(id, &u, sizeof u);
+  return GUAC_OK;
+}
+
+guac_status guac_comm_create(guac_ctx* ctx, const uint8_t* id, int rank, int world, guac_comm** out) {
+  if (!ctx || !id || !out || world < 1 || rank < 0 || rank >= world) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    std::unique_ptr<guac_comm> c(new guac_comm());
+    c->ctx = ctx;
+    c->rank = rank;
+    c->world = world;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    NCCL_OK(ncclCommInitRank(&c->comm, world, u, rank));
+    c->d_sizes.alloc((size_t)6 * (world + 1));
+    CUDA_OK(cudaMallocHost((void**)&c->h_sizes, (size_t)6 * (world + 1) * sizeof(unsigned long long)));
+    *out = c.release();
+  });
+}
+
+void guac_comm_destroy(guac_comm* c) {
+  if (!c) return;
+  if (c->ctx) cudaSetDevice(c->ctx->device);
+  if (c->comm) ncclCommDestroy(c->comm);
+  if (c->h_sizes) cudaFreeHost(c->h_sizes);
+  delete c;
+}
+
+guac_status guac_result_gather(guac_comm* comm, const guac_result* local, int root, guac_result** out) {
+  if (!comm || !local || !out || root < 0 || root >= comm->world) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  guac_ctx* ctx = comm->ctx;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    if (local->kind != 0) fail(GUAC_ERR_UNSUPPORTED, "guac_result_gather takes germline-threshold results");
+    if (local->n_compact && (local->owner != ctx || local->generation != ctx->generation))
+      fail(GUAC_ERR_INVALID_ARGUMENT, "gather the result before the context runs another call (its records are sent from device memory)");
+    nvtx_push("guac gather (NCCL)");
+    cudaStream_t st = ctx->stream;
+    const int W = comm->world, me = comm->rank;
+    const size_t pool_dyn = local->n_bytes > kPoolDynOff ? local->n_bytes - kPoolDynOff : 0;
+    // 1. counts
+    unsigned long long* mine = comm->h_sizes + (size_t)6 * W;
+    mine[0] = local->n_compact; mine[1] = local->n_general; mine[2] = pool_dyn;
+    mine[3] = local->stats.loci_visited; mine[4] = local->stats.tie_loci; mine[5] = local->stats.exact_loci;
+    CUDA_OK(cudaMemcpyAsync(comm->d_sizes.p + (size_t)6 * W, mine, 6 * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    NCCL_OK(ncclAllGather(comm->d_sizes.p + (size_t)6 * W, comm->d_sizes.p, 6, ncclUint64, comm->comm, st));
+    CUDA_OK(cudaMemcpyAsync(comm->h_sizes, comm->d_sizes.p, (size_t)6 * W * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    // the local general records and allele bytes were written to pinned host memory by the exact kernel: stage them in HBM
+    const size_t gen_bytes = local->n_general * sizeof(guac_threshold_record);
+    comm->d_stage.ensure(gen_bytes + pool_dyn + 64);
+    if (gen_bytes) CUDA_OK(cudaMemcpyAsync(comm->d_stage.p, local->general, gen_bytes, cudaMemcpyHostToDevice, st));
+    if (pool_dyn) CUDA_OK(cudaMemcpyAsync(comm->d_stage.p + gen_bytes, local->bytes + kPoolDynOff, pool_dyn, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    const unsigned long long* S = comm->h_sizes;
+    std::unique_ptr<guac_result> res(new guac_result());
+    res->kind = 0;
+    res->sample = local->sample;
+    res->want_sorted = local->want_sorted;
+    res->stats = local->stats;
+    unsigned long long tot_c = 0, tot_g = 0, tot_p = 0, visited = 0, ties = 0, exact = 0;
+    for (int r = 0; r < W; ++r) { tot_c += S[6 * r]; tot_g += S[6 * r + 1]; tot_p += S[6 * r + 2]; visited += S[6 * r + 3]; ties += S[6 * r + 4]; exact += S[6 * r + 5]; }
+    // 2. records rank -> root, from device memory
+    unsigned char* recv = nullptr;
+    size_t at_c = 0, at_g = 0, at_p = 0;
+    if (me == root) {
+      at_g = (size_t)tot_c * 8;
+      at_p = at_g + (size_t)tot_g * sizeof(guac_threshold_record);
+      comm->d_recv.ensure(at_p + (size_t)tot_p + 64);
+      recv = comm->d_recv.p;
+    }
+    NCCL_OK(ncclGroupStart());
+    if (me == root) {
+      size_t oc = 0, og = 0, op = 0;
+      for (int r = 0; r < W; ++r) {
+        const size_t bc = (size_t)S[6 * r] * 8, bg = (size_t)S[6 * r + 1] * sizeof(guac_threshold_record), bp = (size_t)S[6 * r + 2];
+        if (r == me) {
+          if (bc) CUDA_OK(cudaMemcpyAsync(recv + at_c + oc, local->d_compact, bc, cudaMemcpyDeviceToDevice, st));
+          if (bg) CUDA_OK(cudaMemcpyAsync(recv + at_g + og, comm->d_stage.p, bg, cudaMemcpyDeviceToDevice, st));
+          if (bp) CUDA_OK(cudaMemcpyAsync(recv + at_p + op, comm->d_stage.p + gen_bytes, bp, cudaMemcpyDeviceToDevice, st));
+        } else {
+          if (bc) NCCL_OK(ncclRecv(recv + at_c + oc, bc, ncclUint8, r, comm->comm, st));
+          if (bg) NCCL_OK(ncclRecv(recv + at_g + og, bg, ncclUint8, r, comm->comm, st));
+          if (bp) NCCL_OK(ncclRecv(recv + at_p + op, bp, ncclUint8, r, comm->comm, st));
+        }
+        oc += bc; og += bg; op += bp;
+      }
+    } else {
+      if (local->n_compact) NCCL_OK(ncclSend(local->d_compact, local->n_compact * 8, ncclUint8, root, comm->comm, st));
+      if (gen_bytes) NCCL_OK(ncclSend(comm->d_stage.p, gen_bytes, ncclUint8, root, comm->comm, st));
+      if (pool_dyn) NCCL_OK(ncclSend(comm->d_stage.p + gen_bytes, pool_dyn, ncclUint8, root, comm->comm, st));
+    }
+    NCCL_OK(ncclGroupEnd());
+    if (me == root) {
+      // 3. one copy to the pinned block of the merged result: [allele pool][general records][compact records]
+      const size_t pool_bytes = kPoolDynOff + (size_t)tot_p;
+      const size_t full_at = (pool_bytes + 63) & ~(size_t)63;
+      const size_t compact_at = (full_at + (size_t)tot_g * sizeof(guac_threshold_record) + 63) & ~(size_t)63;
+      res->pool = ctx->pinned;
+      res->block = ctx->pinned->take(compact_at + (size_t)tot_c * 8 + 64, &res->block_bytes);
+      if (!res->block) fail(GUAC_ERR_OOM, "pinned host allocation failed");
+      unsigned char* hs = (unsigned char*)res->block;
+      memset(hs, 0, kPoolDynOff);
+      memcpy(hs, "<ALT>", 5);
+      for (int v = 0; v < 256; ++v) hs[kPoolByteOff + v] = (uint8_t)v;
+      if (tot_p) CUDA_OK(cudaMemcpyAsync(hs + kPoolDynOff, recv + at_p, (size_t)tot_p, cudaMemcpyDeviceToHost, st));
+      if (tot_g) CUDA_OK(cudaMemcpyAsync(hs + full_at, recv + at_g, (size_t)tot_g * sizeof(guac_threshold_record), cudaMemcpyDeviceToHost, st));
+      if (tot_c) CUDA_OK(cudaMemcpyAsync(hs + compact_at, recv + at_c, (size_t)tot_c * 8, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      // general records keep offsets into their own rank's pool: re-base them onto the merged pool
+      guac_threshold_record* g = (guac_threshold_record*)(hs + full_at);
+      size_t og = 0, op = 0;
+      for (int r = 0; r < W; ++r) {
+        for (size_t i = 0; i < (size_t)S[6 * r + 1]; ++i) {
+          guac_threshold_record& t = g[og + i];
+          if (t.ref_off >= kPoolDynOff) t.ref_off += (uint32_t)op;
+          if (t.alt_off >= kPoolDynOff) t.alt_off += (uint32_t)op;
+        }
+        og += (size_t)S[6 * r + 1];
+        op += (size_t)S[6 * r + 2];
+      }
+      if (kPoolDynOff + tot_p >= 0xFFFFFFF0ull) fail(GUAC_ERR_UNSUPPORTED, "merged allele pool beyond 4 GiB");
+      res->general = g;
+      res->n_general = (size_t)tot_g;
+      res->compact = (const unsigned long long*)(hs + compact_at);
+      res->n_compact = (size_t)tot_c;
+      res->n_records = res->n_general + res->n_compact;
+      res->bytes = hs;
+      res->n_bytes = pool_bytes;
+      // shards are contiguous loci ranges in rank order: the concatenation of sorted shards is sorted iff every shard was
+      bool sorted = local->compact_sorted;
+      for (size_t i = 1; sorted && i < res->n_compact; ++i) sorted = res->compact[i - 1] <= res->compact[i];
+      res->compact_sorted = sorted;
+      res->stats.records = res->n_records;
+      res->stats.loci_visited = visited;
+      res->stats.tie_loci = ties;
+      res->stats.exact_loci = exact;
+      res->stats.d2h_bytes = (size_t)tot_p + (size_t)tot_g * sizeof(guac_threshold_record) + (size_t)tot_c * 8;
+    } else {
+      CUDA_OK(cudaStreamSynchronize(st));
+      res->stats.records = 0;
+    }
+    nvtx_pop();
+    *out = res.release();
+  });
+}
+
+guac_status guac_comm_reduce_depth_histogram(guac_comm* comm, int root, uint64_t* hist) {
+  if (!comm || root < 0 || root >= comm->world) return GUAC_ERR_INVALID_ARGUMENT;
+  guac_ctx* ctx = comm->ctx;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    if (!ctx->d_hist) fail(GUAC_ERR_INVALID_ARGUMENT, "run guac_depth_histogram on this context first");
+    cudaStream_t st = ctx->stream;
+    NCCL_OK(ncclReduce(ctx->d_hist, ctx->d_hist, kDepthBins, ncclUint64, ncclSum, root, comm->comm, st));
+    if (comm->rank == root && hist) CUDA_OK(cudaMemcpyAsync(hist, ctx->d_hist, kDepthBins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  });
+}
+
+// partitionLociByApproximateDepth (DistributedUtil.scala:162-251): micro partitions by the uniform rule, regions per micro
+// partition counted on the device from the packed read sets, then the greedy assignment on the host in the reference's
+// own Double arithmetic.
+guac_status guac_partition_loci_by_approximate_depth(guac_ctx* ctx, int64_t tasks, const guac_locus_range* loci, size_t n_loci,
+                                                     int64_t accuracy, const guac_reads* const* read_sets, size_t n_read_sets,
+                                                     guac_locus_range* out, size_t max_out, size_t* n_out) {
+  if (!ctx || tasks < 1 || accuracy < 1 || (!loci && n_loci) || !read_sets || n_read_sets < 1 || !n_out) return GUAC_ERR_INVALID_ARGUMENT;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    int64_t count = 0;
+    for (size_t i = 0; i < n_loci; ++i) count += loci[i].end - loci[i].start;
+    if (count <= 0) fail(GUAC_ERR_INVALID_ARGUMENT, "assumption failed: lociUsed.count > 0");
+    // step (1): micro partitions
+    const int64_t n_micro = (accuracy * tasks < count) ? accuracy * tasks : count;
+    if (n_micro > (int64_t)0x7FFFFFF0) fail(GUAC_ERR_UNSUPPORTED, "too many micro partitions");
+    std::vector<guac_locus_range> micro((size_t)n_micro + n_loci + 8);
+    size_t n_ranges = 0;
+    if (guac_partition_loci_uniformly(n_micro, loci, n_loci, micro.data(), micro.size(), &n_ranges) != GUAC_OK)
+      fail(GUAC_ERR_INVALID_ARGUMENT, "partitionLociUniformly failed");
+    micro.resize(n_ranges);
+    // step (2): region counts, on the device.  The kernel wants each contig's ranges sorted by start.
+    std::vector<guac_locus_range> by_contig(micro);
+    std::stable_sort(by_contig.begin(), by_contig.end(), [](const guac_locus_range& a, const guac_locus_range& b) {
+      return a.contig != b.contig ? a.contig < b.contig : a.start < b.start;
+    });
+    cudaStream_t st = ctx->stream;
+    DevBuf<guac_locus_range> d_ranges;
+    DevBuf<unsigned long long> d_counts;
+    h2d(ctx, d_ranges, by_contig.data(), by_contig.size());
+    d_counts.alloc((size_t)n_micro);
+    CUDA_OK(cudaMemsetAsync(d_counts.p, 0, (size_t)n_micro * sizeof(unsigned long long), st));
+    for (size_t s = 0; s < n_read_sets; ++s) {
+      const guac_reads* rd = read_sets[s];
+      if (!rd) fail(GUAC_ERR_INVALID_ARGUMENT, "null read set");
+      const DevReads R = rd->view();
+      size_t k0 = 0;
+      while (k0 < by_contig.size()) {
+        size_t k1 = k0;
+        while (k1 < by_contig.size() && by_contig[k1].contig == by_contig[k0].contig) ++k1;
+        const int32_t c = by_contig[k0].contig;
+        if (c >= 0 && (uint32_t)c < rd->n_contigs) {
+          const ContigInfo& ci = rd->contigs[c];
+          if (ci.read_end > ci.read_begin)
+            k_micro_counts<<<grid_for(ci.read_end - ci.read_begin, 256, ctx->sm_count), 256, 0, st>>>(R, ci.read_begin, ci.read_end, d_ranges.p + k0,
+                                                                                                    (uint32_t)(k1 - k0), d_counts.p);
+        }
+        k0 = k1;
+      }
+    }
+    CUDA_OK(cudaGetLastError());
+    std::vector<unsigned long long> counts((size_t)n_micro);
+    CUDA_OK(cudaMemcpyAsync(counts.data(), d_counts.p, counts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    // step (3): the greedy assignment (:204-247)
+    auto round_double = [](double x) -> long long {  // java.lang.Math.round(double)
+      if (std::isnan(x)) return 0;
+      const double f = std::floor(x + 0.5);
+      if (f >= 9.2233720368547758e18) return INT64_MAX;
+      if (f <= -9.2233720368547758e18) return INT64_MIN;
+      return (long long)f;
+    };
+    auto round_long = [](long long v) -> long long {  // scala.math.round(Long) in Scala 2.10 = Math.round(v.toFloat): Int
+      const float f = std::floor((float)v + 0.5f);
+      if (f >= 2147483648.0f) return INT32_MAX;
+      if (f <= -2147483648.0f) return INT32_MIN;
+      return (long long)(int)f;
+    };
+    long long total = 0;
+    for (unsigned long long c : counts) total += (long long)c;
+    const double per_task = std::max(1.0, (double)total / (double)tasks);
+    double assigned = 0.0;
+    long long task = 0;
+    size_t n = 0;
+    guac_locus_range last{};
+    bool have_last = false;
+    auto put = [&](int32_t contig, int64_t start, int64_t end) {  // LociMap.Builder.put: adjacent ranges of one task coalesce
+      if (end <= start) return;
+      if (have_last && last.contig == contig && last.task == (int32_t)task && last.end == start) {
+        last.end = end;
+        return;
+      }
+      if (have_last) {
+        if (n < max_out && out) out[n] = last;
+        ++n;
+      }
+      last = guac_locus_range{contig, (int32_t)task, start, end};
+      have_last = true;
+    };
+    auto remaining = [&] { return round_double((double)(task + 1) * per_task - assigned); };
+    size_t k = 0;
+    for (long long mt = 0; mt < n_micro; ++mt) {
+      size_t k_end = k;
+      long long set_count = 0;
+      for (; k_end < micro.size() && micro[k_end].task == (int32_t)mt; ++k_end) set_count += micro[k_end].end - micro[k_end].start;
+      long long in_set = (long long)counts[(size_t)mt];
+      int64_t cursor = k < k_end ? micro[k].start : 0;  // first locus of the set not yet assigned
+      while (set_count > 0) {
+        long long take = set_count;
+        if (in_set != 0) {
+          if (remaining() == 0) task += 1;
+          if (!(remaining() > 0) || !(task < tasks)) fail(GUAC_ERR_INVALID_ARGUMENT, "partitionLociByApproximateDepth: assertion failed");
+          const double fraction = std::min(1.0, (double)remaining() / (double)in_set);
+          take = std::max<long long>(1, (long long)(fraction * (double)set_count));
+          const long long regions = round_long((long long)(fraction * (double)in_set));
+          assigned += (double)regions;
+          in_set -= regions;
+        }
+        set_count -= take;
+        while (take > 0) {  // set.take(lociToTake): the first `take` loci of the set in range order
+          const long long avail = micro[k].end - cursor;
+          const long long now = std::min(avail, take);
+          put(micro[k].contig, cursor, cursor + now);
+          cursor += now;
+          take -= now;
+          if (cursor == micro[k].end && ++k < k_end) cursor = micro[k].start;
+        }
+      }
+      k = k_end;
+    }
+    if (have_last) {
+      if (n < max_out && out) out[n] = last;
+      ++n;
+    }
+    *n_out = n;
+    if (n > max_out && out) fail(GUAC_ERR_INVALID_ARGUMENT, "output array too small: %zu ranges", n);
+  });
 }
 
 }  // extern "C"

@@ -211,6 +211,9 @@ struct guac_ctx {
   std::shared_ptr<PinnedPool> pinned = std::make_shared<PinnedPool>();
   // somatic tables (device): see guac_somatic.cuh
   double* d_tables = nullptr;
+  uint64_t generation = 0;                   // bumped by every call that reuses the output scratch
+  unsigned long long* d_hist = nullptr;      // depth histogram of the last guac_depth_histogram (GUAC_DEPTH_BINS bins)
+  bool hist_attr_done = false;
 };
 
 namespace {
@@ -454,6 +457,11 @@ struct guac_result {
   const unsigned long long* compact = nullptr;
   size_t n_compact = 0;
   bool want_sorted = true, compact_sorted = false, expanded_ready = false;
+  // the compact records as the call left them in HBM (guac_result_gather sends them from there); valid while the context
+  // has not run another call (ctx->generation)
+  const unsigned long long* d_compact = nullptr;
+  guac_ctx* owner = nullptr;
+  uint64_t generation = 0;
   std::vector<guac_threshold_record> expanded;
   // somatic / called-allele / allele-count records and the allele byte pool live in one pinned block (downloaded in place)
   std::shared_ptr<PinnedPool> pool;

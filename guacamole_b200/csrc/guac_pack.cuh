@@ -34,6 +34,138 @@ struct PackArgs {
   unsigned long long* counters;  // [0] order-sensitive loci resolved, [1] max reads per granule
 };
 
+// ---- K_header: thread per read; the per-read checks and derived columns (what SlidingWindow / MappedRead do lazily) ------------
+// Validates sortedness (windowing/SlidingWindow.scala:56, DistributedUtil.scala:662-664), CIGAR / read-length consistency
+// (reads/MappedRead.scala:87, pileup/PileupElement.scala:106) and the presence of MD tags; derives [start, end), the SIMPLE
+// flag + leading clip, the number of 32-base plane words and the per-contig read ranges.  The first failing read (lowest
+// index) wins: errors are folded with atomicMin over (read index << 8 | status).
+struct HeaderArgs {
+  uint64_t n;
+  uint32_t n_contigs;
+  const int32_t* contig;
+  const int64_t* start;
+  const uint64_t* cigar_off;
+  const uint32_t* cigar;
+  const uint64_t* seq_off;
+  const uint8_t* mapq;
+  const uint8_t* flags;
+  const int32_t* sample;            // may be null
+  const uint64_t* md_off;
+  const int64_t* contig_length;     // device copy, or null: no upper bound checked
+  ReadRec* rec;                     // pair_off is filled in after the scan of n_pairs
+  uint32_t* cig_off32;
+  uint32_t* md_off32;
+  uint32_t* read_contig;
+  uint32_t* n_pairs;
+  unsigned long long* contig_first; // [n_contigs], initialised to ~0
+  unsigned long long* contig_last;  // [n_contigs], 0
+  long long* contig_end;            // [n_contigs], 0: largest read end
+  unsigned long long* summary;      // [0] first error (~0 = none), [1] longest reference span, [2] sample of read 0
+};
+
+__global__ void __launch_bounds__(256) k_header(HeaderArgs H) {
+  const int lane = threadIdx.x & 31;
+  for (uint64_t i0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ull; i0 < H.n; i0 += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = i0 + lane;
+    int status = 0;
+    int64_t end = 0, ref_len = 0;
+    int32_t c = 0;
+    if (i < H.n) {
+      c = H.contig[i];
+      const int64_t start = H.start[i];
+      const int32_t sample0 = H.sample ? H.sample[0] : 0;
+      if (i == 0) H.summary[2] = (unsigned long long)(uint32_t)sample0;
+      const uint64_t c0 = H.cigar_off[i], c1 = H.cigar_off[i + 1];
+      const uint64_t read_len = H.seq_off[i + 1] - H.seq_off[i];
+      const bool in_range = c >= 0 && (uint32_t)c < H.n_contigs;
+      const bool run_start = i == 0 || H.contig[i - 1] != c;
+      if (!in_range) status = GUAC_ERR_INVALID_ARGUMENT;
+      else if (!run_start && start < H.start[i - 1]) status = GUAC_ERR_UNSORTED_READS;
+      else if (start < 0) status = GUAC_ERR_INVALID_ARGUMENT;
+      else if (H.sample && H.sample[i] != sample0) status = GUAC_ERR_UNSUPPORTED;
+      else if (!(H.flags[i] & GUAC_READ_HAS_MD)) status = GUAC_ERR_MISSING_MD;
+      else if (read_len > (uint64_t)kMaxReadLen) status = GUAC_ERR_UNSUPPORTED;
+      int64_t consumed = 0, lead = 0;
+      int phase = 0;  // 0 leading clips, 1 inside the aligned run, 2 trailing clips
+      bool simple = true;
+      for (uint64_t k = c0; k < c1 && status == 0; ++k) {
+        const uint32_t op = H.cigar[k] & 0xF, len = H.cigar[k] >> 4;
+        if (op > 8 || op == GUAC_CIGAR_P || len == 0) { status = GUAC_ERR_INVALID_CIGAR; break; }
+        const bool m = op == GUAC_CIGAR_M || op == GUAC_CIGAR_EQ || op == GUAC_CIGAR_X;
+        if (m || op == GUAC_CIGAR_D || op == GUAC_CIGAR_N) ref_len += len;
+        if (m || op == GUAC_CIGAR_I || op == GUAC_CIGAR_S) consumed += len;
+        if (m) {
+          if (phase == 2) simple = false;
+          phase = 1;
+        } else if (op == GUAC_CIGAR_S || op == GUAC_CIGAR_H) {
+          if (phase == 0) {
+            if (op == GUAC_CIGAR_S) lead += len;
+          } else
+            phase = 2;
+        } else {
+          simple = false;
+        }
+      }
+      if (c1 == c0) simple = false;
+      end = start + ref_len;
+      if (status == 0) {
+        if ((uint64_t)consumed != read_len) status = GUAC_ERR_INVALID_CIGAR;
+        else if (end > 0x7FFFFF00ll) status = GUAC_ERR_UNSUPPORTED;
+        else if (H.contig_length && end > H.contig_length[c]) status = GUAC_ERR_INVALID_ARGUMENT;
+      }
+      if (status == 0) {
+        if (simple && lead > 0xFFFF) simple = false;
+        const uint32_t info = (uint32_t)(simple ? (lead & 0xFFFF) : 0) | (simple ? kInfoSimple : 0) |
+                              ((H.flags[i] & GUAC_READ_POSITIVE_STRAND) ? kInfoPositive : 0) | (ref_len == 0 ? kInfoEmpty : 0) |
+                              ((uint32_t)H.mapq[i] << kInfoMapqShift);
+        H.rec[i] = ReadRec{(int32_t)start, (int32_t)end, 0u, info};
+        H.cig_off32[i] = (uint32_t)c0;
+        H.md_off32[i] = (uint32_t)H.md_off[i];
+        H.read_contig[i] = (uint32_t)c;
+        H.n_pairs[i] = (uint32_t)((read_len + 31) / 32);
+        if (run_start) {  // "Regions are not sorted by contig": a contig's reads must form one run
+          if (atomicExch(&H.contig_first[c], (unsigned long long)i) != ~0ull) status = GUAC_ERR_CONTIG_ORDER;
+          if (i > 0) {
+            const int32_t pc = H.contig[i - 1];
+            if (pc >= 0 && (uint32_t)pc < H.n_contigs) H.contig_last[pc] = i;
+          }
+        }
+        if (i + 1 == H.n) H.contig_last[c] = H.n;
+      } else {
+        H.n_pairs[i] = 0;
+      }
+      if (status) atomicMin(&H.summary[0], ((unsigned long long)i << 8) | (unsigned long long)status);
+    }
+    // largest end per contig / longest span: one atomic per warp when its reads share a contig (they are sorted by contig)
+    const bool ok = i < H.n && status == 0;
+    const int32_t c_lead = __shfl_sync(0xFFFFFFFFu, c, 0);
+    const bool uniform = __all_sync(0xFFFFFFFFu, !ok || c == c_lead) && __shfl_sync(0xFFFFFFFFu, (int)ok, 0);
+    const unsigned span = ok ? (unsigned)ref_len : 0u;
+    const unsigned max_span = __reduce_max_sync(0xFFFFFFFFu, span);
+    if (lane == 0 && max_span) atomicMax(&H.summary[1], (unsigned long long)max_span);
+    if (uniform) {
+      const unsigned max_end = __reduce_max_sync(0xFFFFFFFFu, ok ? (unsigned)end : 0u);
+      if (lane == 0) atomicMax(&H.contig_end[c_lead], (long long)max_end);
+    } else if (ok) {
+      atomicMax(&H.contig_end[c], (long long)end);
+    }
+  }
+}
+
+// rec[i].pair_off from the scan of n_pairs; rec[n] = the sentinel
+__global__ void __launch_bounds__(256) k_header_finish(ReadRec* __restrict__ rec, const uint32_t* __restrict__ pair_off, uint32_t* __restrict__ cig_off32,
+                                                       uint32_t* __restrict__ md_off32, const uint64_t* __restrict__ cigar_off, const uint64_t* __restrict__ md_off,
+                                                       uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (i < n) rec[i].pair_off = pair_off[i];
+    else {
+      rec[n] = ReadRec{0x7FFFFFFF, 0x7FFFFFFF, pair_off[n], 0u};
+      cig_off32[n] = (uint32_t)cigar_off[n];
+      md_off32[n] = (uint32_t)md_off[n];
+    }
+  }
+}
+
 // ---- K_pack_bases: ASCII bases -> (lo, hi) bit-plane pairs + non-ACGT mask (+ the qc bytes) -------------------------------
 // A CTA takes 64 consecutive reads at a time.  Their bases (and qualities) are one contiguous byte range of the raw columns:
 // it is staged into shared memory with one TMA bulk copy per column (cp.async.bulk, completion on an mbarrier).  Then
@@ -411,6 +543,28 @@ __global__ void __launch_bounds__(128) k_resolve_conflicts(PackArgs A, uint32_t 
       }
       A.trk_lo_w[ci.word_off + w] = lo;
       A.trk_hi_w[ci.word_off + w] = hi;
+    }
+  }
+}
+
+// ---- K_micro_counts: partitionLociByApproximateDepth step (2) (DistributedUtil.scala:182-195) ---------------------------------
+// thread per read of one contig: +1 for every micro partition that has a locus inside the read's [start, end).  `ranges` =
+// the micro-partition ranges of this contig sorted by start (disjoint, their micro index `task` non-decreasing); a micro
+// partition split into several ranges by gaps in the loci counts a read once (LociMap.getAll returns a Set).
+__global__ void __launch_bounds__(256) k_micro_counts(DevReads R, uint64_t r_begin, uint64_t r_end, const guac_locus_range* __restrict__ ranges,
+                                                      uint32_t n_ranges, unsigned long long* __restrict__ counts) {
+  for (uint64_t r = r_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < r_end; r += (uint64_t)gridDim.x * blockDim.x) {
+    const ReadRec rec = R.rec[r];
+    if (rec.end <= rec.start) continue;
+    uint32_t lo = 0, hi = n_ranges;  // first range that ends past the read's start
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (ranges[mid].end > (int64_t)rec.start) hi = mid; else lo = mid + 1;
+    }
+    int32_t last = -1;
+    for (uint32_t k = lo; k < n_ranges && ranges[k].start < (int64_t)rec.end; ++k) {
+      if (ranges[k].task != last) atomicAdd(&counts[ranges[k].task], 1ull);
+      last = ranges[k].task;
     }
   }
 }

@@ -518,15 +518,22 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_call_tile(DevReads R, const
         return (j & 3) == 0 ? v.x : (j & 3) == 1 ? v.y : (j & 3) == 2 ? v.z : v.w;
       };
       // per-locus sums of the four classes, byte-wise (no carry between loci while the depth is below 256)
-      const uint32_t sum4 = word(0) + word(1) + word(2) + word(3);
+      const uint32_t w0 = word(0), w1 = word(1), w2 = word(2), w3 = word(3);
+      const uint32_t sum4 = w0 + w1 + w2 + w3;
       const uint32_t st_sum = __dp4a(dd[j] & 0x0F0F0F0Fu, kOnes, 0u), en_sum = __dp4a((dd[j] >> 4) & 0x0F0F0F0Fu, kOnes, 0u);
       const uint32_t std4 = (my_std >> (4 * j)) & 0xFu, inr4 = (in_range >> (4 * j)) & 0xFu;
-      // The whole quadruple at once: every locus stays covered by at least dmin reads, so a locus whose differing elements
-      // number fewer than tq = ceil((threshold + 1) * dmin / 100) cannot hold an alternate allele that passes.
+      // The whole quadruple at once: every locus stays covered by at least dmin reads, so an allele seen fewer than
+      // tq = ceil((threshold + 1) * dmin / 100) times cannot pass the threshold there.  Byte-wise "count >= tq" over the
+      // three mismatch classes and the "other" elements (the only alleles besides the reference one): a locus with such a
+      // count is remembered — its exact depth and the full rule follow below —, every other locus yields nothing.
       const uint32_t dmin = (uint32_t)dep - en_sum;
       const uint32_t tq = (thr_plus_1 * dmin + 99u) / 100u;
-      if (std4 == 0xFu && inr4 == 0xFu && (uint32_t)dep > en_sum && (uint32_t)dep + st_sum <= 255u && tq <= 128u &&
-          ((((sum4 & 0x7F7F7F7Fu) + (128u - tq) * kOnes) | sum4) & 0x80808080u) == 0u) {
+      if (std4 == 0xFu && inr4 == 0xFu && (uint32_t)dep > en_sum && (uint32_t)dep + st_sum <= 255u && tq - 1u < 128u) {
+        const uint32_t bias = (128u - tq) * kOnes;
+        const uint32_t hit = ((((w0 & 0x7F7F7F7Fu) + bias) | w0) | (((w1 & 0x7F7F7F7Fu) + bias) | w1) | (((w2 & 0x7F7F7F7Fu) + bias) | w2) |
+                              (((w3 & 0x7F7F7F7Fu) + bias) | w3)) & 0x80808080u;
+        // bits 7, 15, 23, 31 -> bits 0..3
+        if (hit) survivors |= ((hit * 0x00204081u) >> 28) << (4 * j);
         dep += (int)st_sum - (int)en_sum;
         n_visited += 4;
         continue;

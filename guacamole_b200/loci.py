@@ -83,3 +83,19 @@ def partition_loci_uniformly(tasks: int, loci: Sequence[Range]) -> List[TaskRang
     if rc != 0:
         raise GuacError(rc, "partitionLociUniformly failed")
     return [(out[i].contig, out[i].start, out[i].end, out[i].task) for i in range(n.value)]
+
+
+def partition_loci_by_approximate_depth(ctx, tasks: int, loci: Sequence[Range], accuracy: int, *read_sets) -> List[TaskRange]:
+    """DistributedUtil.partitionLociByApproximateDepth (DistributedUtil.scala:162-251): loci assigned to tasks so that every
+    task sees about the same number of the reads packed in `read_sets` (PackedReads).  `loci` in LociSet order."""
+    from ._lib import lib
+    L = lib()
+    arr = ranges_to_c(loci)
+    handles = (C.c_void_p * len(read_sets))(*[r._h for r in read_sets])
+    total = sum(r[2] - r[1] for r in loci)
+    cap = len(loci) + 2 * int(min(int(tasks) * int(accuracy), total)) + 8
+    out = (abi.LocusRangeC * cap)()
+    n = C.c_size_t()
+    ctx._check(L.guac_partition_loci_by_approximate_depth(ctx._h, tasks, arr, len(loci), accuracy, handles, len(read_sets),
+                                                          out, cap, C.byref(n)))
+    return [(out[i].contig, out[i].start, out[i].end, out[i].task) for i in range(n.value)]

@@ -24,10 +24,10 @@ CHR20_LENGTH = 63025520
 
 class SynthParamsC(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_contigs", C.c_uint32), ("read_length", C.c_int32),
-                ("contig_length", C.POINTER(C.c_int64)), ("n_reads", C.c_uint64), ("sample", C.c_int32),
-                ("window_contig", C.c_int32), ("window_start", C.c_int64), ("window_end", C.c_int64),
+                ("contig_length", C.POINTER(C.c_int64)), ("reads_per_locus", C.c_double), ("sample", C.c_int32),
+                ("n_windows", C.c_uint32), ("windows", C.POINTER(abi.LocusRangeC)),
                 ("frac_clip", C.c_double), ("frac_ins", C.c_double), ("frac_del", C.c_double),
-                ("frac_both", C.c_double), ("n_threads", C.c_int32), ("pad_", C.c_int32)]
+                ("frac_both", C.c_double), ("n_threads", C.c_int32), ("with_qualities", C.c_int32)]
 
 
 _lib = None
@@ -91,26 +91,118 @@ class SynthBatch:
             pass
 
 
-def generate(contigs: Sequence[tuple], depth: float, read_length: int = 150, seed: int = 20261018, sample: int = 0,
-             window: Optional[tuple] = None, n_threads: int = 0, n_reads: Optional[int] = None,
-             frac_clip=0.20, frac_ins=0.009, frac_del=0.009, frac_both=0.002) -> SynthBatch:
-    """contigs: [(name, length)]; window: (contig_index, start, end) restricts the reads (and their count) to a slice."""
-    L = _load()
-    names = [c[0] for c in contigs]
+def make_params(contigs: Sequence[tuple], depth: float, read_length: int = 150, seed: int = 20261018, sample: int = 0,
+                windows: Optional[Sequence[tuple]] = None, n_threads: int = 0, with_qualities: bool = True,
+                frac_clip=0.20, frac_ins=0.009, frac_del=0.009, frac_both=0.002):
+    """guac_synth_params + the arrays it points at (keep the second value alive while the struct is in use)."""
     lengths = np.asarray([c[1] for c in contigs], dtype=np.int64)
-    if n_reads is None:
-        loci = (window[2] - window[1]) if window else int(lengths.sum())
-        n_reads = int(depth * loci / read_length)
     p = SynthParamsC()
     p.seed, p.n_contigs, p.read_length = seed, len(contigs), read_length
     p.contig_length = lengths.ctypes.data_as(C.POINTER(C.c_int64))
-    p.n_reads, p.sample = n_reads, sample
-    if window:
-        p.window_contig, p.window_start, p.window_end = window
+    p.reads_per_locus, p.sample = float(depth) / float(read_length), sample
+    keep = [lengths]
+    if windows:
+        arr = (abi.LocusRangeC * len(windows))()
+        for i, w in enumerate(windows):
+            arr[i].contig, arr[i].start, arr[i].end = int(w[0]), int(w[1]), int(w[2])
+        p.n_windows, p.windows = len(windows), arr
+        keep.append(arr)
     p.frac_clip, p.frac_ins, p.frac_del, p.frac_both = frac_clip, frac_ins, frac_del, frac_both
-    p.n_threads = n_threads
+    p.n_threads, p.with_qualities = n_threads, int(with_qualities)
+    return p, keep
+
+
+def generate(contigs: Sequence[tuple], depth: float, read_length: int = 150, seed: int = 20261018, sample: int = 0,
+             window: Optional[tuple] = None, n_threads: int = 0, windows: Optional[Sequence[tuple]] = None,
+             frac_clip=0.20, frac_ins=0.009, frac_del=0.009, frac_both=0.002) -> SynthBatch:
+    """contigs: [(name, length)]; window = (contig_index, start, end) / windows = [...] restrict the reads to those STARTING
+    there.  The reads starting at a locus do not depend on the windows: a slice holds what the whole genome would."""
+    L = _load()
+    names = [c[0] for c in contigs]
+    if window is not None:
+        windows = [window]
+    p, keep = make_params(contigs, depth, read_length, seed, sample, windows, n_threads, True, frac_clip, frac_ins, frac_del, frac_both)
     h = C.c_void_p()
     rc = L.guac_synth_generate(C.byref(p), C.byref(h))
+    del keep
     if rc != 0:
         raise RuntimeError(f"guac_synth_generate failed: {abi.STATUS_NAMES.get(rc, rc)}")
     return SynthBatch(h, names, "tumor" if sample == 1 else "normal")
+
+
+class HostBatch(SynthBatch):
+    """Host copy of a device-generated batch (guac_synth_device_batch_download); page-locked when asked for."""
+
+    def __init__(self, handle, contig_names, sample_name):
+        from ._lib import lib
+        self._h = handle
+        self.contig_names = list(contig_names)
+        self.sample_name = sample_name
+        self.c = lib().guac_synth_host_batch_view(handle).contents
+
+    def free(self):
+        if self._h:
+            from ._lib import lib
+            lib().guac_synth_host_batch_free(self._h)
+            self._h = None
+
+
+class DeviceBatch:
+    """A batch generated straight into device memory (guac_synth_generate_device): `.c` is a guac_read_batch whose column
+    pointers are DEVICE pointers — hand it to Context.pack_device."""
+
+    def __init__(self, ctx, handle, contig_names, sample_name):
+        from ._lib import lib
+        self.ctx, self._h = ctx, handle
+        self.contig_names = list(contig_names)
+        self.sample_name = sample_name
+        self.c = lib().guac_synth_device_batch_view(handle).contents
+        self.kernel_ms = float(lib().guac_synth_device_batch_ms(handle))
+
+    @property
+    def n_reads(self):
+        return int(self.c.n_reads)
+
+    def download(self, pinned: bool = False) -> HostBatch:
+        from ._lib import lib
+        h = C.c_void_p()
+        self.ctx._check(lib().guac_synth_device_batch_download(self.ctx._h, self._h, int(pinned), C.byref(h)))
+        return HostBatch(h, self.contig_names, self.sample_name)
+
+    def free(self):
+        if self._h:
+            from ._lib import lib
+            lib().guac_synth_device_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def generate_device(ctx, contigs: Sequence[tuple], depth: float, read_length: int = 150, seed: int = 20261018, sample: int = 0,
+                    windows: Optional[Sequence[tuple]] = None, with_qualities: bool = True,
+                    frac_clip=0.20, frac_ins=0.009, frac_del=0.009, frac_both=0.002) -> DeviceBatch:
+    """generate() on the device of `ctx` (a callers.Context): the same reads, byte for byte, left in HBM."""
+    from ._lib import lib
+    p, keep = make_params(contigs, depth, read_length, seed, sample, windows, 0, with_qualities, frac_clip, frac_ins, frac_del, frac_both)
+    h = C.c_void_p()
+    ctx._check(lib().guac_synth_generate_device(ctx._h, C.byref(p), C.byref(h)))
+    del keep
+    return DeviceBatch(ctx, h, [c[0] for c in contigs], "tumor" if sample == 1 else "normal")
+
+
+def shard_windows(ranges: Sequence[tuple], read_length: int = 150) -> list:
+    """Start windows of the reads that can overlap the loci `ranges` (contig, start, end[, task]) of one shard: a read
+    starting up to read_length + 40 before a range reaches into it (reads crossing a shard boundary are generated by both
+    neighbours, like the reference duplicates them across tasks, DistributedUtil.scala:585-597).  Merged per contig."""
+    out = []
+    for r in sorted((int(r[0]), int(r[1]), int(r[2])) for r in ranges):
+        s, e = max(0, r[1] - (read_length + 40)), r[2]
+        if out and out[-1][0] == r[0] and s <= out[-1][2]:
+            out[-1] = (r[0], out[-1][1], max(out[-1][2], e))
+        else:
+            out.append((r[0], s, e))
+    return out

@@ -279,6 +279,9 @@ guac_status guac_host_unregister(void* ptr);
  * CIGAR/MD consistency and quality range — the checks SlidingWindow / MappedRead do lazily. `ref` may be NULL
  * (reference bases then come from MD tags, Pileup.referenceBaseAtLocus pileup/Pileup.scala:157-165). */
 guac_status guac_reads_pack(guac_ctx* ctx, const guac_read_batch* batch, const guac_reference* ref, guac_reads** out);
+/* Same, for a batch whose column pointers are DEVICE memory of ctx's device (n_reads, n_contigs and contig_length stay on the
+ * host): no host -> device copies; the per-read checks and derived columns are computed by the same kernels either way. */
+guac_status guac_reads_pack_device(guac_ctx* ctx, const guac_read_batch* device_batch, const guac_reference* ref, guac_reads** out);
 void guac_reads_free(guac_reads* reads);
 uint64_t guac_reads_count(const guac_reads* reads);
 uint64_t guac_reads_device_bytes(const guac_reads* reads);
@@ -354,6 +357,37 @@ size_t guac_somatic_genotype_filter(const guac_somatic_record* records, size_t n
  * returns the number produced through *n_out. ------------------------------------------------------------- */
 guac_status guac_partition_loci_uniformly(int64_t tasks, const guac_locus_range* loci, size_t n_loci,
                                           guac_locus_range* out, size_t max_out, size_t* n_out);
+
+
+/* ---- loci by depth, and the path's only exchange: records + depth histograms to one rank over NCCL ------------------------
+ * Loci shard naturally (DistributedUtil.scala:537-545: a locus depends only on the reads overlapping it), so there is no
+ * collective on the data path.  What the reference does with collect / coalesce(1, shuffle = true) (Common.scala:290-293)
+ * is guac_result_gather: counts all-gathered (48 bytes per rank), every rank's records sent from device memory to the root
+ * with one group of ncclSend / ncclRecv, one device -> host copy on the root. */
+#define GUAC_DEPTH_BINS 256
+/* hist[d] = requested loci covered by exactly d reads (d < 255); hist[255] = deeper.  `hist` may be NULL: the histogram stays
+ * on the device for guac_comm_reduce_depth_histogram.  Needs GUAC_OPT_DIFFERENCE_LISTS = 1 (it reads the streams). */
+guac_status guac_depth_histogram(guac_ctx* ctx, const guac_reads* reads, const guac_locus_range* ranges, size_t n_ranges,
+                                 uint64_t* hist);
+typedef struct guac_comm guac_comm;
+#define GUAC_COMM_ID_BYTES 128
+/* One rank makes the id, the host side hands it to every rank (Spark broadcast / MPI / a file), every rank creates its
+ * communicator over its own context (one process or thread per GPU). */
+guac_status guac_comm_unique_id(uint8_t* id /* [GUAC_COMM_ID_BYTES] */);
+guac_status guac_comm_create(guac_ctx* ctx, const uint8_t* id, int rank, int world, guac_comm** out);
+void guac_comm_destroy(guac_comm* comm);
+/* Collective: every rank passes the germline-threshold result of its own loci shard (before its context runs another call);
+ * `*out` on the root holds all records in rank order — the order of the partitions —, an empty result elsewhere. */
+guac_status guac_result_gather(guac_comm* comm, const guac_result* local, int root, guac_result** out);
+/* Collective: ncclReduce(sum) of the device-resident histogram of each rank's last guac_depth_histogram; `hist` (root only) */
+guac_status guac_comm_reduce_depth_histogram(guac_comm* comm, int root, uint64_t* hist);
+
+/* partitionLociByApproximateDepth (DistributedUtil.scala:162-251; the reference's default at --partition-accuracy 250):
+ * `accuracy * tasks` uniform micro partitions, the reads of `read_sets` overlapping each counted on the device, loci then
+ * assigned to tasks so that every task sees about the same number of reads.  `loci` in LociSet order, as above. */
+guac_status guac_partition_loci_by_approximate_depth(guac_ctx* ctx, int64_t tasks, const guac_locus_range* loci, size_t n_loci,
+                                                     int64_t accuracy, const guac_reads* const* read_sets, size_t n_read_sets,
+                                                     guac_locus_range* out, size_t max_out, size_t* n_out);
 
 #ifdef __cplusplus
 }

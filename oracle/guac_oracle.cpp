@@ -1524,6 +1524,108 @@ int orc_partition_loci_uniformly(int64_t tasks, const guac_locus_range* loci, si
   });
 }
 
+// partitionLociByApproximateDepth DistributedUtil.scala:162-251.  `loci` in LociSet order (the order partitionLociUniformly
+// walks them); regions = the reads of every batch.  Restated literally: micro partitions = partitionLociUniformly(accuracy *
+// tasks), one count per (region, micro partition it overlaps) — LociMap.getAll returns a Set —, then the greedy assignment in
+// Double arithmetic.  scala.math.round applied to a Long resolves to round(Float): Int in Scala 2.10 (no Long overload):
+// kept, it only matters beyond 2^24 regions in one micro partition.
+namespace {
+long long scala_round_double(double x) {  // java.lang.Math.round(double)
+  if (std::isnan(x)) return 0;
+  double f = std::floor(x + 0.5);
+  if (f >= 9.2233720368547758e18) return INT64_MAX;
+  if (f <= -9.2233720368547758e18) return INT64_MIN;
+  return (long long)f;
+}
+long long scala_round_long(long long v) {  // math.round(v: Long) = java.lang.Math.round(v.toFloat): Int
+  float f = std::floor((float)v + 0.5f);
+  if (f >= 2147483648.0f) return INT32_MAX;
+  if (f <= -2147483648.0f) return INT32_MIN;
+  return (long long)(int)f;
+}
+}  // namespace
+
+int orc_partition_loci_by_approximate_depth(int64_t tasks, const guac_locus_range* loci, size_t n_loci, int64_t accuracy,
+                                            const guac_read_batch* const* batches, size_t n_batches, guac_locus_range* out,
+                                            size_t max_out, size_t* n_out) {
+  return guarded([&] {
+    if (tasks < 1 || accuracy < 1 || n_batches < 1) fail(GUAC_ERR_INVALID_ARGUMENT, "tasks, accuracy and the number of region sets must be >= 1");
+    int64_t count = 0;
+    for (size_t i = 0; i < n_loci; ++i) count += loci[i].end - loci[i].start;
+    if (count <= 0) fail(GUAC_ERR_INVALID_ARGUMENT, "assumption failed: lociUsed.count > 0");
+    // Step (1): micro partitions
+    const int64_t n_micro = (accuracy * tasks < count) ? accuracy * tasks : count;
+    std::vector<guac_locus_range> micro((size_t)n_micro + n_loci + 8);
+    size_t n_ranges = 0;
+    if (orc_partition_loci_uniformly(n_micro, loci, n_loci, micro.data(), micro.size(), &n_ranges) != 0) fail(GUAC_ERR_INVALID_ARGUMENT, g_last_error);
+    micro.resize(n_ranges);
+    // Step (2): regions overlapping each micro partition
+    std::vector<long long> counts((size_t)n_micro, 0);
+    for (size_t b = 0; b < n_batches; ++b) {
+      ReadSet rs;
+      load_batch(batches[b], rs);
+      for (const Read& r : rs.reads) {
+        long long last = -1;  // getAll(start, end): the SET of micro partitions with a locus in [start, end)
+        std::vector<long long> seen;
+        for (const guac_locus_range& m : micro)
+          if (m.contig == r.contig && m.start < r.end && m.end > r.start && r.end > r.start) {
+            if ((long long)m.task != last && std::find(seen.begin(), seen.end(), (long long)m.task) == seen.end()) {
+              seen.push_back(m.task);
+              counts[(size_t)m.task] += 1;
+            }
+            last = m.task;
+          }
+      }
+    }
+    // Step (3): greedy assignment
+    long long total = 0;
+    for (long long c : counts) total += c;
+    const double regions_per_task = std::max(1.0, (double)total / (double)tasks);
+    std::vector<guac_locus_range> v;
+    auto put = [&](int32_t contig, int64_t start, int64_t end, long long task) {  // LociMap.Builder.put coalesces
+      if (end <= start) return;
+      if (!v.empty() && v.back().contig == contig && v.back().task == (int32_t)task && v.back().end == start) v.back().end = end;
+      else v.push_back(guac_locus_range{contig, (int32_t)task, start, end});
+    };
+    double regions_assigned = 0.0;
+    long long task = 0;
+    auto remaining_for_task = [&]() { return scala_round_double(((double)(task + 1) * regions_per_task) - regions_assigned); };
+    size_t next_range = 0;
+    for (long long mt = 0; mt < n_micro; ++mt) {
+      // microPartitions.asInverseMap(mt): the ranges of this micro partition, in contig order
+      std::vector<guac_locus_range> set;
+      while (next_range < micro.size() && micro[next_range].task == (int32_t)mt) set.push_back(micro[next_range++]);
+      long long regions_in_set = counts[(size_t)mt];
+      auto set_count = [&]() { long long c = 0; for (auto& x : set) c += x.end - x.start; return c; };
+      while (!set.empty()) {
+        if (regions_in_set == 0) {
+          for (auto& x : set) put(x.contig, x.start, x.end, task);
+          set.clear();
+        } else {
+          if (remaining_for_task() == 0) task += 1;
+          if (!(remaining_for_task() > 0) || !(task < tasks)) fail(GUAC_ERR_INVALID_ARGUMENT, "assertion failed in partitionLociByApproximateDepth");
+          const double fraction = std::min(1.0, (double)remaining_for_task() / (double)regions_in_set);
+          long long loci_to_take = std::max<long long>(1, (long long)(fraction * (double)set_count()));
+          const long long regions_to_take = (long long)(fraction * (double)regions_in_set);
+          // set.take(lociToTake)
+          std::vector<guac_locus_range> rest;
+          for (auto& x : set) {
+            const long long len = x.end - x.start;
+            if (loci_to_take >= len) { put(x.contig, x.start, x.end, task); loci_to_take -= len; }
+            else if (loci_to_take > 0) { put(x.contig, x.start, x.start + loci_to_take, task); rest.push_back(guac_locus_range{x.contig, x.task, x.start + loci_to_take, x.end}); loci_to_take = 0; }
+            else rest.push_back(x);
+          }
+          set.swap(rest);
+          regions_assigned += (double)scala_round_long(regions_to_take);
+          regions_in_set -= scala_round_long(regions_to_take);
+        }
+      }
+    }
+    *n_out = v.size();
+    for (size_t i = 0; i < v.size() && i < max_out; ++i) out[i] = v[i];
+  });
+}
+
 double orc_phred_to_success_probability(int phred) { return phred_tables().success[phred & 255]; }
 int orc_success_probability_to_phred(double p) { return success_probability_to_phred(p); }
 

@@ -112,6 +112,10 @@ int orc_visited_loci(const guac_read_batch* a, const guac_read_batch* b, const g
 /* partitionLociUniformly DistributedUtil.scala:83-108 */
 int orc_partition_loci_uniformly(int64_t tasks, const guac_locus_range* loci, size_t n_loci, guac_locus_range* out,
                                  size_t max_out, size_t* n_out);
+/* partitionLociByApproximateDepth DistributedUtil.scala:162-251 (loci in LociSet order; regions = the reads of the batches) */
+int orc_partition_loci_by_approximate_depth(int64_t tasks, const guac_locus_range* loci, size_t n_loci, int64_t accuracy,
+                                            const guac_read_batch* const* batches, size_t n_batches, guac_locus_range* out,
+                                            size_t max_out, size_t* n_out);
 /* ADAM PhredUtils (third party, restated): */
 double orc_phred_to_success_probability(int phred);
 int orc_success_probability_to_phred(double p);

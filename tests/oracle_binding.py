@@ -338,6 +338,18 @@ def partition_loci_uniformly(tasks: int, loci) -> List[tuple]:
     return [(out[i].contig, out[i].start, out[i].end, out[i].task) for i in range(n.value)]
 
 
+def partition_loci_by_approximate_depth(tasks: int, loci, accuracy: int, *batches) -> List[tuple]:
+    """DistributedUtil.partitionLociByApproximateDepth over the reads of `batches` (ReadBatch objects)."""
+    arr = ranges_array(loci)
+    cs = [b.to_c() for b in batches]
+    ptrs = (C.c_void_p * len(cs))(*[C.cast(C.pointer(c), C.c_void_p) for c in cs])
+    out = (abi.LocusRangeC * 400000)()
+    n = C.c_size_t()
+    _check(lib().orc_partition_loci_by_approximate_depth(C.c_int64(tasks), arr, C.c_size_t(len(loci)), C.c_int64(accuracy), ptrs,
+                                                         C.c_size_t(len(cs)), out, C.c_size_t(400000), C.byref(n)))
+    return [(out[i].contig, out[i].start, out[i].end, out[i].task) for i in range(n.value)]
+
+
 def somatic_genotype_filter(raw_record, min_tumor_read_depth, max_tumor_read_depth, min_normal_read_depth,
                             min_tumor_alternate_read_depth, min_log_odds, min_vaf, min_likelihood) -> bool:
     return bool(lib().orc_somatic_genotype_filter(C.byref(raw_record), min_tumor_read_depth, max_tumor_read_depth,

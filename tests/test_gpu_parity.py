@@ -339,3 +339,80 @@ def test_by_sample_split(ctx):
     key = lambda x: (x["contig"], x["start"], x["sample"], x["ref"], x["alt"], tuple(x["gt"]))
     assert [key(x) for x in got] == [key(x) for x in want]
     assert len({x["sample"] for x in got}) == 2
+
+
+def test_partition_loci_by_approximate_depth(ctx):  # DistributedUtilSuite.scala:76-93 + the oracle on uneven depth
+    from guacamole_b200 import synth
+    from guacamole_b200.loci import partition_loci_by_approximate_depth
+    golden = ReadBatch.from_records([make_read("A" * n, f"{n}M", f"{n}", s, chr="chr1") for s, n in ((5, 1), (6, 1), (7, 1), (8, 1))])
+    reads = ctx.pack(golden)
+    got = partition_loci_by_approximate_depth(ctx, 2, [(0, 0, 100)], 100, reads)
+    reads.free()
+    assert got == [(0, 0, 7, 0), (0, 7, 100, 1)]
+    # uneven depth: a deep amplicon inside a shallow contig, two read sets, gaps in the loci
+    shallow = synth.generate([("1", 60000), ("2", 30000)], depth=6, seed=11).to_read_batch()
+    deep = synth.generate([("1", 60000), ("2", 30000)], depth=200, seed=12, window=(0, 20000, 24000)).to_read_batch()
+    loci = [(0, 0, 25000), (0, 30000, 59999), (1, 500, 29999)]
+    ra, rb = ctx.pack(shallow), ctx.pack(deep)
+    for tasks, acc in ((4, 250), (8, 13), (3, 1), (16, 1000)):
+        want = orc.partition_loci_by_approximate_depth(tasks, loci, acc, shallow, deep)
+        assert partition_loci_by_approximate_depth(ctx, tasks, loci, acc, ra, rb) == want
+    ra.free()
+    rb.free()
+
+
+def test_device_generator_equals_host_generator(ctx):
+    """The two builds of the synthetic generator produce the same bytes, a shard holds what the whole genome would, and a
+    batch packed from device memory gives the records of the same batch packed from the host."""
+    from guacamole_b200 import callers, synth
+    contigs = [("1", 300000), ("2", 120000), ("3", 900)]
+    for sample, depth in ((0, 30), (1, 45)):
+        host = synth.generate(contigs, depth=depth, seed=97, sample=sample)
+        dev = synth.generate_device(ctx, contigs, depth=depth, seed=97, sample=sample)
+        back = dev.download()
+        hb, db = host.to_read_batch(), back.to_read_batch()
+        assert len(hb.start) == len(db.start) > 50000
+        for col in ("contig", "start", "cigar_off", "cigar", "seq_off", "seq", "qual", "mapq", "flags", "md_off", "md"):
+            assert np.array_equal(getattr(hb, col), getattr(db, col)), col
+        ranges = [(0, 0, 299999), (1, 0, 119999)]
+        a = ctx.pack(hb)
+        b = ctx.pack_device(dev.c, [c[0] for c in contigs])
+        ra = callers.germline_threshold(ctx, a, ranges).genotypes()
+        rb = callers.germline_threshold(ctx, b, ranges).genotypes()
+        for g in rb:
+            g["sample"] = 0  # (to_read_batch interns the sample as index 0; the generated column carries the sample id)
+        assert ra == rb and len(ra) > 300
+        a.free()
+        b.free()
+        back.free()
+        dev.free()
+    # a shard generated alone: the reads STARTING in its windows, byte for byte
+    whole = synth.generate(contigs, depth=30, seed=97).to_read_batch()
+    windows = synth.shard_windows([(0, 250000, 300000, 1), (1, 0, 40000, 1)])
+    shard = synth.generate_device(ctx, contigs, depth=30, seed=97, windows=windows)
+    sb = shard.download().to_read_batch()
+    keep = np.zeros(len(whole.start), bool)
+    for c, s, e in windows:
+        keep |= (whole.contig == c) & (whole.start >= s) & (whole.start < e)
+    sel = whole.select(keep)
+    assert len(sb.start) == len(sel.start) > 10000
+    for col in ("contig", "start", "cigar", "seq", "qual", "mapq", "flags", "md"):
+        assert np.array_equal(getattr(sb, col), getattr(sel, col)), col
+    shard.free()
+
+
+def test_depth_histogram(ctx, difference_lists):
+    """guac_depth_histogram (the histogram the shards reduce to rank 0) against the depths of guac_pileup_counts."""
+    if not difference_lists:
+        pytest.skip("the histogram reads the difference streams")
+    from guacamole_b200 import callers, synth
+    for contigs, depth, ranges in (([("1", 70000), ("2", 9000)], 30, [(0, 100, 65000), (1, 0, 9000)]),
+                                   ([("amp", 4000)], 900, [(0, 0, 4100)])):
+        b = synth.generate(contigs, depth=depth, seed=3).to_read_batch()
+        reads = ctx.pack(b)
+        counts = callers.pileup_counts(ctx, reads, ranges, skip_empty=False).records
+        want = np.bincount(np.minimum(counts["depth"], 255), minlength=256).astype(np.uint64)
+        got = callers.depth_histogram(ctx, reads, ranges)
+        reads.free()
+        assert int(got.sum()) == sum(r[2] - r[1] for r in ranges)
+        assert np.array_equal(got, want)

@@ -174,10 +174,10 @@ def test_amplicon_shape_config5(ctx):
     H4), the per-locus element counts pass 8 bits by far, and a call's supporting elements run into the thousands (the
     AlleleEvidence medians are taken over all of them)."""
     from guacamole_b200 import synth
-    contigs = [("amp", 300)]
+    contigs = [("amp", 520)]
     tumor = synth.generate(contigs, depth=10000, seed=55, sample=1).to_read_batch()
     normal = synth.generate(contigs, depth=10000, seed=56, sample=0).to_read_batch()
-    assert_somatic_equal(ctx, tumor, normal, [(0, 0, 299)], odds=20)
+    assert_somatic_equal(ctx, tumor, normal, [(0, 0, 519)], odds=20)
     # a call whose supporting elements run into the thousands: medians / means over all 1,500 of them
     alt = [make_read("TCGGTCGA", "8M", "3A4", 0, quality_scores=[10 + (i * 7) % 50] * 8, alignment_quality=20 + (i * 11) % 41)
            for i in range(1500)]
@@ -189,11 +189,11 @@ def test_amplicon_shape_config5(ctx):
     # the same reads through germline-threshold (16-bit counter fields) and per-locus counts
     from guacamole_b200 import callers
     for b in (tumor,):
-        want = orc.germline_threshold(b, [(0, 0, 299)]).threshold()
+        want = orc.germline_threshold(b, [(0, 0, 519)]).threshold()
         reads = ctx.pack(b)
-        g = callers.germline_threshold(ctx, reads, [(0, 0, 299)]).genotypes()
-        wc = orc.pileup_counts(b, [(0, 0, 299)]).counts()
-        gc = callers.pileup_counts(ctx, reads, [(0, 0, 299)]).records
+        g = callers.germline_threshold(ctx, reads, [(0, 0, 519)]).genotypes()
+        wc = orc.pileup_counts(b, [(0, 0, 519)]).counts()
+        gc = callers.pileup_counts(ctx, reads, [(0, 0, 519)]).records
         reads.free()
         key = lambda x: (x["contig"], x["start"], x["ref"], x["alt"], x["gt"])
         assert [key(x) for x in g] == [key(x) for x in want]

@@ -235,6 +235,24 @@ def fmt(parts, name="chrM"):
     return ",".join(f"{name}:{s}-{e}={t}" for (_, s, e, t) in parts)
 
 
+def test_partition_loci_by_approximate_depth():  # DistributedUtilSuite.scala:76-93
+    from guacamole_b200.reads import ReadBatch, make_read
+    reads = ReadBatch.from_records([make_read("A" * n, f"{n}M", f"{n}", s, chr="chr1") for s, n in ((5, 1), (6, 1), (7, 1), (8, 1))])
+    got = orc.partition_loci_by_approximate_depth(2, [(0, 0, 100)], 100, reads)
+    assert fmt(got, "chr1") == "chr1:0-7=0,chr1:7-100=1"
+    # every locus is assigned exactly once, tasks ascend along the loci (result.count == lociUsed.count, :249)
+    from guacamole_b200 import synth
+    b = synth.generate([("1", 30000), ("2", 20000)], depth=12, seed=5).to_read_batch()
+    for tasks, acc in ((3, 7), (8, 250), (5, 1)):
+        parts = orc.partition_loci_by_approximate_depth(tasks, [(0, 0, 29999), (1, 100, 19999)], acc, b)
+        assert sum(e - s for _, s, e, _ in parts) == 29999 + 19899
+        assert [t for *_, t in parts] == sorted(t for *_, t in parts) and parts[-1][3] < tasks
+        ends = {}
+        for c, s, e, _ in parts:
+            assert s == ends.get(c, 0 if c == 0 else 100)
+            ends[c] = e
+
+
 def test_partition_loci_uniformly():  # :46-63
     assert fmt(orc.partition_loci_uniformly(4, [(0, 0, 16571)])) == "chrM:0-4143=0,chrM:4143-8286=1,chrM:8286-12428=2,chrM:12428-16571=3"
     assert fmt(orc.partition_loci_uniformly(3, [(0, 0, 10)])) == "chrM:0-3=0,chrM:3-7=1,chrM:7-10=2"
