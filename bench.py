@@ -3,15 +3,21 @@
 
     python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torch.distributed.run, one rank per GPU)
     python bench.py --impl reference ...                    (the reference algorithm's CPU path: the oracle, all host threads)
+    python bench.py --workload amplicon --gpus 8            (BASELINE.json configs[4]: somatic-standard, 10,000x over 1 Mb)
 
-A "step" is one pass of the hot path (K_tile + K_exact + record download) over one batch of synthetic reads.  At N = 1 the
-workload is BASELINE.json configs[1]: germline-threshold, chr20 shape (63,025,520 loci), 30x, 150 bp.  At N > 1 every rank
-holds one chr20-shaped contig of an N-contig genome (LociPartitioning assigns contiguous contig ranges to ranks; no
-data-path collective) and rank 0 gathers the variant records over NCCL — weak scaling.
-
-`value` is measured with the packed reads already resident in HBM; `e2e` goes through guac_reads_pack +
-guac_germline_threshold from (pinned) HOST buffers every step, results copied back.  `cpu_baseline` is the oracle (a C++
-restatement of the reference's Scala algorithm — there is no JVM on the box) on a bounded window of the same workload.
+A "step" is one pass of the hot path over one batch of synthetic reads, through the C ABI of include/guac.h.
+  N = 1   configs[1]: germline-threshold, chr20 shape (63,025,520 loci), 30x, 150 bp — plus a `somatic` block in the same JSON
+          line for configs[2] (somatic-standard, tumor 60x / normal 30x over the same contig).
+  N > 1   configs[3]: germline-threshold on the whole-genome shape (GRCh37 contig lengths of the reference's own
+          DistributedUtilSuite.scala:72, 3.1 G loci, 30x): partitionLociUniformly(N) cuts the loci into contiguous ranges (mid
+          contig, several contigs per rank), every rank generates the reads overlapping its ranges ON ITS DEVICE from the
+          seed (boundary reads exist on both neighbours, DistributedUtil.scala:585-597), packs and calls them; the records and
+          the depth histogram are gathered to rank 0 by the library's NCCL exchange.  Total work is fixed: strong scaling.
+`value` is measured with the packed reads resident in HBM; `e2e` goes from (pinned) HOST buffers through guac_reads_pack +
+the call (+ the NCCL gather at N > 1) to records in host memory every step — at N > 1 over a chr20-sized slice of each rank's
+shard (the whole shard would need 124 GB of pinned host memory).  `cpu_baseline` / `--impl reference` is the oracle (a C++
+restatement of the reference's Scala algorithm — there is no JVM on the box) on a bounded window of the same workload, and
+`parity_window` says whether the engine's records inside that window equal the oracle's.
 """
 import argparse
 import ctypes as C
@@ -32,6 +38,7 @@ from guacamole_b200 import abi, synth  # noqa: E402
 
 CHR20 = synth.CHR20_LENGTH
 READ_LEN = 150
+SPAN = READ_LEN + 40          # longest reference span of a generated read
 
 
 def parse_args():
@@ -40,11 +47,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="germline", choices=["germline", "somatic"])
-    ap.add_argument("--contig-length", type=int, default=CHR20)
+    ap.add_argument("--workload", default="auto", choices=["auto", "germline", "somatic", "amplicon"])
+    ap.add_argument("--contig-length", type=int, default=CHR20, help="N = 1: length of the one contig")
     ap.add_argument("--depth", type=float, default=30.0)
     ap.add_argument("--cpu-window", type=int, default=4_000_000, help="loci of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--no-somatic", action="store_true", help="N = 1: leave the configs[2] block out")
     ap.add_argument("--seed", type=int, default=20261020)
     return ap.parse_args()
 
@@ -124,9 +132,9 @@ class ClockSampler:
 
 
 def measured_traffic(kernel, n_loci, depth):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_traffic.json), scaled
-    linearly in loci when the capture was taken on a slice; None if there is no capture for this shape."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r2_traffic.json), scaled
+    linearly in loci; None if there is no capture for this shape.  (ncu cannot run inside the timed bench.)"""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if not os.path.exists(p):
         return None
     t = json.load(open(p)).get(kernel)
@@ -135,68 +143,61 @@ def measured_traffic(kernel, n_loci, depth):
     return t["traffic_bytes"] * (n_loci / t["workload_loci"])
 
 
-def algorithmic_bytes(view, n_loci):
-    """per read start 4 + ref_len 4 + 4*c + ceil(L/4) + 1 flag bytes; per locus 0.25 B of reference."""
-    n = int(view.n_reads)
-    n_ops = int(np.ctypeslib.as_array(view.cigar_off, shape=(n + 1,))[n])
-    bases = int(np.ctypeslib.as_array(view.seq_off, shape=(n + 1,))[n])
-    return n * 9 + 4 * n_ops + (bases + 3) // 4 + 0.25 * n_loci
+def genome(world, workload, contig_length):
+    """(contigs, loci in LociSet order = contigs sorted by name, LociMap.contigs) of the workload."""
+    if workload == "amplicon":
+        contigs = [("amplicon", 1_000_000 + SPAN)]
+    elif world == 1:
+        contigs = [("20", contig_length)]
+    else:
+        contigs = list(synth.GRCH37)
+    order = sorted(range(len(contigs)), key=lambda i: contigs[i][0])
+    if workload == "amplicon":
+        loci = [(0, 0, 1_000_000)]
+    else:
+        loci = [(i, 0, contigs[i][1] - 1) for i in order]   # LociSet "all" drops the last base of a contig
+    return contigs, loci
 
 
-def pinned_copy(view):
-    """Copies the generator's columns into page-locked host memory (torch pinned tensors) and returns a guac_read_batch
-    over them, so that the e2e leg's host->device copies start from pinned memory."""
-    import torch
-    n = int(view.n_reads)
-    so = np.ctypeslib.as_array(view.seq_off, shape=(n + 1,))
-    co = np.ctypeslib.as_array(view.cigar_off, shape=(n + 1,))
-    mo = np.ctypeslib.as_array(view.md_off, shape=(n + 1,))
-    keep = []
-
-    def col(ptr, count, dtype, ctype):
-        count = max(int(count), 1)
-        src = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,))
-        t = torch.empty(count, dtype=dtype, pin_memory=True)
-        t.numpy()[:] = src.view(t.numpy().dtype)
-        keep.append(t)
-        return C.cast(t.data_ptr(), C.POINTER(ctype))
-
-    b = abi.ReadBatchC()
-    b.n_reads, b.n_contigs = view.n_reads, view.n_contigs
-    b.contig_length = col(view.contig_length, view.n_contigs, torch.int64, C.c_int64)
-    b.contig = col(view.contig, n, torch.int32, C.c_int32)
-    b.start = col(view.start, n, torch.int64, C.c_int64)
-    b.cigar_off = C.cast(col(view.cigar_off, n + 1, torch.int64, C.c_int64), C.POINTER(C.c_uint64))
-    b.cigar = C.cast(col(view.cigar, co[n], torch.int32, C.c_int32), C.POINTER(C.c_uint32))
-    b.seq_off = C.cast(col(view.seq_off, n + 1, torch.int64, C.c_int64), C.POINTER(C.c_uint64))
-    b.seq = col(view.seq, so[n], torch.uint8, C.c_uint8)
-    b.qual = col(view.qual, so[n], torch.uint8, C.c_uint8)
-    b.mapq = col(view.mapq, n, torch.uint8, C.c_uint8)
-    b.flags = col(view.flags, n, torch.uint8, C.c_uint8)
-    b.sample = col(view.sample, n, torch.int32, C.c_int32)
-    b.md_off = C.cast(col(view.md_off, n + 1, torch.int64, C.c_int64), C.POINTER(C.c_uint64))
-    # c_char_p fields convert to Python bytes on access: take the raw pointer value from the struct instead
-    md_addr = C.c_void_p.from_address(C.addressof(view) + abi.ReadBatchC.md.offset).value
-    md_pinned = col(C.cast(md_addr, C.POINTER(C.c_uint8)), mo[n], torch.uint8, C.c_uint8)
-    C.c_void_p.from_address(C.addressof(b) + abi.ReadBatchC.md.offset).value = C.cast(md_pinned, C.c_void_p).value
-    return b, keep
+def algorithmic_bytes_of(n_reads, n_ops, n_bases, with_qualities):
+    """per read start 4 + ref_len 4 + 4*c + ceil(L/4) + 1 flag bytes (+ L qualities + mapq + mismatch count for
+    the likelihood callers); the 0.25 B of reference per locus is added by the caller."""
+    b = n_reads * 9 + 4 * n_ops + (n_bases + 3) // 4
+    if with_qualities:
+        b += n_bases + 3 * n_reads
+    return b
 
 
-def cpu_leg(args, steps, warmup, n_threads):
-    """The reference algorithm on host cores: oracle over a bounded window of the same workload, Spark-style loci tasks."""
+def germline_keys(res, contig=None, lo=None, hi=None):
+    """(contig, start, ref, alt, gt) of the germline records of `res` inside [lo, hi) of `contig`, sorted."""
+    recs, pool = res.records, res.bytes
+    if contig is not None:
+        recs = recs[(recs["contig"] == contig) & (recs["start"] >= lo) & (recs["start"] < hi)]
+    return sorted((int(r["contig"]), int(r["start"]), pool[int(r["ref_off"]):int(r["ref_off"]) + int(r["ref_len"])],
+                   pool[int(r["alt_off"]):int(r["alt_off"]) + int(r["alt_len"])], int(r["gt"][0]), int(r["gt"][1])) for r in recs)
+
+
+def somatic_keys(res, contig, lo, hi):
+    recs, pool = res.records, res.bytes
+    recs = recs[(recs["contig"] == contig) & (recs["start"] >= lo) & (recs["start"] < hi)]
+    return sorted((int(r["contig"]), int(r["start"]), pool[int(r["ref_off"]):int(r["ref_off"]) + int(r["ref_len"])],
+                   pool[int(r["alt_off"]):int(r["alt_off"]) + int(r["alt_len"])], int(r["tumor"]["allele_read_depth"]),
+                   int(r["tumor"]["read_depth"]), int(r["normal"]["read_depth"])) for r in recs)
+
+
+def cpu_leg(args, contigs, window, somatic, depths, steps, warmup, n_threads, keep_records=False):
+    """The reference algorithm on host cores: the oracle over the reads STARTING in `window` = (contig, start, end) of the same
+    synthetic workload (host build of the same generator), Spark-style loci tasks.  The loci [start + SPAN, end - SPAN) see
+    every read that overlaps them."""
     import oracle_binding as orc
-    somatic = args.workload == "somatic"
-    window = min(args.cpu_window // (3 if somatic else 1), args.contig_length)
-    samples = [(1, args.depth * 2), (0, args.depth)] if somatic else [(0, args.depth)]
-    sbs = [synth.generate([("20", args.contig_length)], depth=d, read_length=READ_LEN, seed=args.seed, sample=s,
-                          window=(0, 0, window)) for s, d in samples]
-    ranges = orc.partition_loci_uniformly(n_threads, [(0, 0, window - READ_LEN - 40)])
+    c, s, e = window
+    sbs = [synth.generate(contigs, depth=d, read_length=READ_LEN, seed=args.seed, sample=sm, window=(c, s, e)) for sm, d in depths]
+    lo, hi = s + (SPAN if s > 0 else 0), e - SPAN
+    ranges = orc.partition_loci_uniformly(n_threads, [(c, lo, hi)])
     arr = orc.ranges_array(ranges)
     L = orc.lib()
-    n_loci = sum(r[2] - r[1] for r in ranges)
-    times = []
-    n_rec = 0
-    for i in range(warmup + steps):
+    times, n_rec, keys = [], 0, None
+    for i in range(warmup + steps):  # straight from the generator's buffers (no numpy copy of the columns)
         h = C.c_void_p()
         t0 = time.perf_counter()
         if somatic:
@@ -209,14 +210,53 @@ def cpu_leg(args, steps, warmup, n_threads):
         dt = time.perf_counter() - t0
         if rc != 0:
             raise RuntimeError("oracle failed: " + L.orc_last_error().decode())
-        n_rec = L.orc_result_n(h)
+        n_rec = int(L.orc_result_n(h))
+        if keep_records and keys is None:
+            keys = oracle_keys(L, h, n_rec, somatic)
         L.orc_result_free(h)
         if i >= warmup:
             times.append(dt)
     sec = float(np.mean(times))
     reads = sum(sb.n_reads for sb in sbs)
-    return {"loci_per_s": n_loci / sec, "reads_per_s": reads / sec, "sec_per_step": sec, "loci": n_loci,
-            "reads": reads, "records": int(n_rec), "threads": n_threads, "window": window}
+    return {"loci_per_s": (hi - lo) / sec, "reads_per_s": reads / sec, "sec_per_step": sec, "loci": hi - lo, "reads": reads,
+            "records": n_rec, "threads": n_threads, "window": (c, lo, hi), "keys": keys}
+
+
+def oracle_keys(L, h, n_rec, somatic):
+    nb = C.c_size_t()
+    L.orc_result_bytes.restype = C.POINTER(C.c_uint8)
+    L.orc_result_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+    bp = L.orc_result_bytes(h, C.byref(nb))
+    pool = bytes((C.c_uint8 * nb.value).from_address(C.cast(bp, C.c_void_p).value)) if nb.value else b""
+    if somatic:
+        L.orc_result_somatic_records.restype = C.POINTER(abi.SomaticRecordC)
+        L.orc_result_somatic_records.argtypes = [C.c_void_p]
+        p = L.orc_result_somatic_records(h)
+        return sorted((p[k].contig, p[k].start, pool[p[k].ref_off:p[k].ref_off + p[k].ref_len],
+                       pool[p[k].alt_off:p[k].alt_off + p[k].alt_len], p[k].tumor.allele_read_depth, p[k].tumor.read_depth,
+                       p[k].normal.read_depth) for k in range(n_rec))
+    L.orc_result_threshold_records.restype = C.POINTER(abi.ThresholdRecordC)
+    L.orc_result_threshold_records.argtypes = [C.c_void_p]
+    p = L.orc_result_threshold_records(h)
+    return sorted((p[k].contig, p[k].start, pool[p[k].ref_off:p[k].ref_off + p[k].ref_len],
+                   pool[p[k].alt_off:p[k].alt_off + p[k].alt_len], p[k].gt[0], p[k].gt[1]) for k in range(n_rec))
+
+
+def cpu_baseline_block(cpu, what):
+    return {"value": cpu["loci_per_s"], "unit": "loci/s", "cores": cpu["threads"], "kind": "port",
+            "sample": f"loci {cpu['window'][1]:,}-{cpu['window'][2]:,} of contig {cpu['window'][0]} of the same {what} workload "
+                      f"({cpu['reads']:,} reads, {cpu['sec_per_step']:.1f} s per pass); C++ oracle restating the reference's Scala "
+                      "algorithm, one loci task per thread (no JVM on the box)"}
+
+
+def device_u64(ptr, index):
+    """element `index` of a device column of 8-byte elements"""
+    import torch
+    buf = C.c_uint64(0)
+    err = torch.cuda.cudart().cudaMemcpy(C.addressof(buf), C.cast(ptr, C.c_void_p).value + index * 8, 8, 2)  # device -> host
+    if int(err) != 0:
+        raise RuntimeError(f"cudaMemcpy failed: {err}")
+    return int(buf.value)
 
 
 def main():
@@ -225,26 +265,45 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_threads = os.cpu_count() or 1
-    if args.workload == "somatic":
-        wl = (f"somatic-standard, synthetic tumor/normal pair {2 * args.depth:g}x/{args.depth:g}x, chr20 shape "
-              f"({args.contig_length:,} loci), {READ_LEN} bp (BASELINE.json configs[2]) per GPU")
-    else:
+    workload = "germline" if args.workload == "auto" else args.workload
+    somatic = workload in ("somatic", "amplicon")
+    if workload == "amplicon":
+        args.depth = 10000.0
+    contigs, loci_all = genome(world, workload, args.contig_length)
+    names = [c[0] for c in contigs]
+    total_loci = sum(r[2] - r[1] for r in loci_all)
+    tumor_depth = args.depth if workload == "amplicon" else 2 * args.depth
+    if workload == "amplicon":
+        wl = (f"somatic-standard, high-depth amplicon: 10,000x tumor + 10,000x normal over 1,000,000 loci, {READ_LEN} bp "
+              f"(BASELINE.json configs[4]), loci partitioned over {world} GPU(s)")
+    elif somatic:
+        wl = (f"somatic-standard, synthetic tumor/normal pair {tumor_depth:g}x/{args.depth:g}x, chr20 shape "
+              f"({args.contig_length:,} loci), {READ_LEN} bp (BASELINE.json configs[2])")
+    elif world == 1:
         wl = (f"germline-threshold, synthetic chr20 shape ({args.contig_length:,} loci), {args.depth:g}x, {READ_LEN} bp "
-              f"(BASELINE.json configs[1]) per GPU")
-    config = {"workload": wl, "threshold_percent": 8, "loci_per_gpu": args.contig_length, "depth": args.depth, "read_length": READ_LEN,
-              "parallelism": f"loci-partitioned x{world}", "l2": "inputs larger than L2 (no flush needed)"}
+              f"(BASELINE.json configs[1]); `somatic` block: configs[2] (tumor {tumor_depth:g}x / normal {args.depth:g}x, same contig)")
+    else:
+        wl = (f"germline-threshold, synthetic whole genome {args.depth:g}x, {READ_LEN} bp: the 25 GRCh37 contigs of "
+              f"DistributedUtilSuite.scala:72 ({total_loci:,} loci), partitionLociUniformly over {world} GPUs with mid-contig cuts "
+              f"and boundary reads on both neighbours, reads generated on each device (BASELINE.json configs[3]); the e2e leg "
+              f"runs from pinned host buffers over a chr20-sized slice ({CHR20:,} loci) of every rank's shard")
+    config = {"workload": wl, "threshold_percent": 8, "total_loci": total_loci, "depth": args.depth, "read_length": READ_LEN,
+              "parallelism": f"loci-partitioned x{world} (partitionLociUniformly)", "l2": "inputs larger than L2 (no flush needed)"}
+    depths_of = lambda is_som: [(1, tumor_depth), (0, args.depth)] if is_som else [(0, args.depth)]
 
     if args.impl == "reference":
         if rank != 0:
             return
-        cpu = cpu_leg(args, max(1, args.steps), max(0, min(args.warmup, 1)), n_threads)
+        c0 = loci_all[0][0]
+        window = (c0, 0, min(args.cpu_window // (3 if somatic else 1), contigs[c0][1] - 1))
+        if workload == "amplicon":
+            window = (0, 0, 1500)
+        cpu = cpu_leg(args, contigs, window, somatic, depths_of(somatic), max(1, args.steps), max(0, min(args.warmup, 1)), n_threads)
         line = {"impl": "reference", "metric": "loci_per_sec", "value": cpu["loci_per_s"], "unit": "loci/s",
                 "reads_per_sec": cpu["reads_per_s"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": cpu["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64" if args.workload == "somatic" else "u8", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": cpu["loci_per_s"], "unit": "loci/s", "cores": cpu["threads"], "kind": "port",
-                                 "sample": f"first {cpu['window']:,} loci of the chr20-shape workload ({cpu['reads']:,} reads); "
-                                           "C++ oracle restating the reference's Scala algorithm (no JVM on the box)"},
+                "ms_per_step": cpu["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+                "vs_baseline": None, "dtype": "f64" if somatic else "u8", "data": "synthetic", "config": config,
+                "cpu_baseline": cpu_baseline_block(cpu, workload),
                 "e2e": {"value": cpu["loci_per_s"], "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
@@ -252,143 +311,232 @@ def main():
     import torch
     import torch.distributed as dist
     from guacamole_b200 import callers
-    from guacamole_b200._lib import lib
-    from guacamole_b200.distributed import gather_records, ranges_of_rank
+    from guacamole_b200.distributed import ranges_of_rank
     from guacamole_b200.loci import partition_loci_uniformly
 
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-    L = lib()
-    somatic = args.workload == "somatic"
-
-    # ---- this rank's shard: one chr20-shaped contig of a `world`-contig genome (LociPartitioning over contigs)
-    contigs = [(f"20_{r}" if world > 1 else "20", args.contig_length) for r in range(world)]
-    names = [c[0] for c in contigs]
-    loci_all = [(c, 0, args.contig_length - 1) for c in range(world)]  # LociSet "all" drops the last base of a contig
-    my_ranges = ranges_of_rank(partition_loci_uniformly(world, loci_all), rank)
-    n_loci = sum(r[2] - r[1] for r in my_ranges)
-    t_gen = time.perf_counter()
-    samples = [(1, args.depth * 2), (0, args.depth)] if somatic else [(0, args.depth)]   # tumor 60x + normal 30x
-    views, keeps, n_reads, algorithmic = [], [], 0, 0.25 * n_loci
-    for sample, depth in samples:
-        sb = synth.generate(contigs, depth=depth, read_length=READ_LEN, seed=args.seed, sample=sample,
-                            window=(rank, 0, args.contig_length))
-        n_reads += sb.n_reads
-        algorithmic += algorithmic_bytes(sb.c, 0) + ((READ_LEN + 3) * sb.n_reads if somatic else 0)
-        v, k = pinned_copy(sb.c)
-        sb.free()
-        views.append(v)
-        keeps.append(k)
-    gen_s = time.perf_counter() - t_gen
-
     ctx = callers.Context(local_rank)
-    ctx.set_option(abi.OPT_PACK_QUALITIES, 1 if somatic else 0)
-    ctx.set_option(abi.OPT_HOST_THREADS, max(1, n_threads // world))  # ranks share the box's host cores
-    packed = [ctx.pack_c(v, names) for v in views]
-    pack_ms = sum(p.pack_kernel_ms for p in packed)
+    ctx.set_option(abi.OPT_HOST_THREADS, max(1, n_threads // world))
+    comm = None
+    if world > 1:  # the library's own NCCL communicator: the id travels by the host side's broadcast
+        ids = [callers.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = callers.Comm(ctx, ids[0], rank, world)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def call(reads_list):
-        if somatic:
-            return callers.somatic_standard(ctx, reads_list[0], reads_list[1], my_ranges, odds_threshold=20, min_alignment_quality=1)
-        return callers.germline_threshold(ctx, reads_list[0], my_ranges, threshold=8)
-
-    # ---- device-resident leg
-    ctx.set_option(abi.OPT_SORT_RECORDS, 0)
-    for _ in range(args.warmup):
-        res = call(packed)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    ctx.timer_start()
-    t0 = time.perf_counter()
-    tile_ms, exact_ms, launches = 0.0, 0.0, 0
-    for _ in range(args.steps):
-        res = call(packed)
-        tile_ms += res.stats["tile_kernel_ms"]
-        exact_ms += res.stats["exact_kernel_ms"]
-        launches += res.stats["kernel_launches"]
-    dev_ms = ctx.timer_stop()
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop()
-    n_records = len(res)
-    step_ms = max(dev_ms, 0.0) / args.steps
-
-    # ---- end-to-end leg: host buffers -> pack -> call -> records on the host, every step
-    ctx.set_option(abi.OPT_SORT_RECORDS, 1)
-    e2e_steps = args.e2e_steps or min(args.steps, 5)
-    h2d = d2h = 0
-    for i in range(1 + e2e_steps):
-        if i == 1:
-            barrier()
-            t1 = time.perf_counter()
-        fresh = [ctx.pack_c(v, names) for v in views]
-        out = call(fresh)
-        h2d = sum(int(L.guac_reads_h2d_bytes(f._h)) for f in fresh) + int(out.stats["h2d_bytes"])
-        d2h = int(out.stats["d2h_bytes"])
-        for f in fresh:
-            f.free()
-    barrier()
-    e2e_ms = (time.perf_counter() - t1) * 1e3 / e2e_steps
-    assert len(out) == n_records, "e2e and resident legs disagree"
-
-    # ---- gather per-shard records to rank 0 (the path's only exchange), max-over-ranks timing
-    t = torch.tensor([step_ms, e2e_ms, float(n_records), tile_ms / args.steps, exact_ms / args.steps], device="cuda", dtype=torch.float64)
-    if world > 1:
-        mx = t.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        t_g = time.perf_counter()
-        allrec, _ = gather_records(out.records, out.bytes, dst=0, device=torch.device("cuda", local_rank))
-        torch.cuda.synchronize()
-        gather_ms = (time.perf_counter() - t_g) * 1e3
-        step_ms, e2e_ms = float(mx[0]), float(mx[1])
-        total_records = len(allrec) if rank == 0 else 0
-        tile_step_ms, exact_step_ms = float(mx[3]), float(mx[4])
-    else:
-        total_records = n_records
-        gather_ms = 0.0
-        tile_step_ms, exact_step_ms = tile_ms / args.steps, exact_ms / args.steps
-
-    if rank != 0:
+    def reduce(values, op):
+        t = torch.tensor(values, device="cuda", dtype=torch.float64)
         if world > 1:
-            dist.destroy_process_group()
-        return
+            dist.all_reduce(t, op=op)
+        return [float(x) for x in t]
 
+    my_ranges = ranges_of_rank(partition_loci_uniformly(world, loci_all), rank)
     peak, peak_src = peaks()
-    alg_bytes = algorithmic
-    total_loci = n_loci * world
-    total_reads = n_reads * world
-    value = total_loci / (step_ms * 1e-3)
-    e2e_value = total_loci / (e2e_ms * 1e-3)
-    achieved = alg_bytes / (tile_step_ms * 1e-3) / 1e9
-    line = {
-        "metric": "loci_per_sec", "value": value, "unit": "loci/s", "reads_per_sec": total_reads / (step_ms * 1e-3),
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if somatic else "u8", "data": "synthetic", "config": config,
-        "records_per_step": total_records, "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": "loci/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "pinned_host_buffers": sum(len(k) for k in keeps)},
-        "roofline": {"bound": "hbm", "kernel": "k_somatic" if somatic else "k_pileup_tile", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": measured_traffic("k_somatic" if somatic else "k_pileup_tile", n_loci, args.depth), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": tile_step_ms, "exact_kernel_ms": exact_step_ms,
-                     "whole_step_achieved_gbs": alg_bytes / (step_ms * 1e-3) / 1e9},
-        "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps, "pack_kernel_ms": pack_ms, "generate_s": gen_s,
-        "gather_ms": gather_ms,
-    }
-    if world == 1:
-        cpu = cpu_leg(args, 1, 0, n_threads)
-        line["cpu_baseline"] = {"value": cpu["loci_per_s"], "unit": "loci/s", "cores": cpu["threads"], "kind": "port",
-                                "sample": f"first {cpu['window']:,} loci of the same workload ({cpu['reads']:,} reads, "
-                                          f"{cpu['sec_per_step']:.1f} s); C++ oracle restating the reference's Scala algorithm"}
-    print(json.dumps(line), flush=True)
+
+    def run_workload(is_somatic, ranges, steps, e2e_steps, e2e_ranges, cpu_window):
+        """One workload on this rank's `ranges`: resident leg, the pack + call companion, the gather, the parity check against
+        the oracle inside `cpu_window`, the end-to-end leg over `e2e_ranges`.  Returns this rank's numbers."""
+        ctx.set_option(abi.OPT_PACK_QUALITIES, 1 if is_somatic else 0)
+        samples = depths_of(is_somatic)
+        n_loci = sum(r[2] - r[1] for r in ranges)
+        t_setup = time.perf_counter()
+        packed, n_reads, alg, gen_ms = [], 0, 0.25 * n_loci, 0.0
+        for s, d in samples:  # generated on the device, packed there (the large columns move into the read set)
+            dv = synth.generate_device(ctx, contigs, depth=d, read_length=READ_LEN, seed=args.seed, sample=s,
+                                       windows=synth.shard_windows(ranges, READ_LEN), with_qualities=is_somatic)
+            n_ops = device_u64(dv.c.cigar_off, dv.n_reads) if dv.n_reads else 0
+            n_reads += dv.n_reads
+            alg += algorithmic_bytes_of(dv.n_reads, n_ops, dv.n_reads * READ_LEN, is_somatic)
+            gen_ms += dv.kernel_ms
+            packed.append(ctx.pack_synth(dv))
+            dv.free()
+        pack_ms = sum(p.pack_kernel_ms for p in packed)
+        expand_ms = sum(p.expand_kernel_ms for p in packed)
+        setup_s = time.perf_counter() - t_setup
+
+        def call(reads_list, rngs):
+            if is_somatic:
+                return callers.somatic_standard(ctx, reads_list[0], reads_list[1], rngs, odds_threshold=20, min_alignment_quality=1)
+            return callers.germline_threshold(ctx, reads_list[0], rngs, threshold=8)
+
+        # ---- device-resident leg (records in canonical order)
+        for _ in range(args.warmup):
+            res = call(packed, ranges)
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        ctx.timer_start()
+        t0 = time.perf_counter()
+        tile_ms = exact_ms = 0.0
+        launches = 0
+        for _ in range(steps):
+            res = call(packed, ranges)
+            st = res.stats
+            tile_ms += st["tile_kernel_ms"]
+            exact_ms += st["exact_kernel_ms"]
+            launches += st["kernel_launches"]
+        dev_ms = ctx.timer_stop()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        clocks = sampler.stop()
+        out = {"n_loci": n_loci, "n_reads": n_reads, "alg": alg, "step_ms": dev_ms / steps, "tile_ms": tile_ms / steps,
+               "exact_ms": exact_ms / steps, "launches": launches, "wall_ms": wall_ms / steps, "clocks": clocks, "gen_ms": gen_ms,
+               "pack_ms": pack_ms, "expand_ms": expand_ms, "setup_s": setup_s, "records": len(res)}
+        # every kernel from the raw columns resident in HBM to the records
+        out["pack_plus_call_ms"] = pack_ms + out["tile_ms"] + out["exact_ms"]
+
+        # ---- parity: the engine's records inside the CPU window against the oracle's (the oracle's own run of the generator)
+        cpu = None
+        if cpu_window is not None:
+            cpu = cpu_leg(args, contigs, cpu_window, is_somatic, samples, 1, 0, n_threads, keep_records=True)
+            c, lo, hi = cpu["window"]
+            got = somatic_keys(res, c, lo, hi) if is_somatic else germline_keys(res, c, lo, hi)
+            out["parity_window"] = "ok" if got == cpu["keys"] else f"MISMATCH ({len(got)} engine vs {len(cpu['keys'])} oracle records)"
+            out["parity_records"] = len(got)
+            cpu["keys"] = None
+        out["cpu"] = cpu
+
+        # ---- the gather (N > 1, germline): records + depth histogram to rank 0 by the library's NCCL exchange, checked
+        if comm is not None and not is_somatic:
+            cmp, gen, _ = res.compact()
+            mine = [float(len(cmp)), float(len(gen)), float(int(gen["start"].sum()) % (1 << 40)) if len(gen) else 0.0]
+            merged = comm.gather(res, 0)
+            callers.depth_histogram(ctx, packed[0], ranges, fetch=False)
+            hist = comm.reduce_depth_histogram(0)
+            tot = reduce(mine, dist.ReduceOp.SUM)
+            if rank == 0:
+                mc, mg, _ = merged.compact()
+                ok = (len(mc) == int(tot[0]) and len(mg) == int(tot[1]) and int(mg["start"].sum()) % (1 << 40) == int(tot[2]) % (1 << 40)
+                      and bool(np.all(mc[:-1] <= mc[1:])) and int(hist.sum()) == total_loci)
+                out["gather_check"] = "ok" if ok else "MISMATCH"
+                out["total_records"] = len(merged)
+                out["mean_depth"] = float((hist.astype(np.float64) * np.arange(256)).sum() / max(1.0, float(hist.sum())))
+            del merged, cmp, gen
+        del res
+        for p in packed:
+            p.free()
+
+        # ---- end-to-end leg: (pinned) host buffers -> pack -> call (-> NCCL gather) -> records in host memory, every step
+        e2e_loci = sum(r[2] - r[1] for r in e2e_ranges)
+        hosts = []
+        for s, d in samples:
+            dv = synth.generate_device(ctx, contigs, depth=d, read_length=READ_LEN, seed=args.seed, sample=s,
+                                       windows=synth.shard_windows(e2e_ranges, READ_LEN), with_qualities=is_somatic)
+            hosts.append(dv.download(pinned=True))
+            dv.free()
+        h2d = d2h = n_touch = 0
+        t1 = time.perf_counter()
+        for i in range(1 + e2e_steps):
+            if i == 1:
+                barrier()
+                t1 = time.perf_counter()
+            fresh = [ctx.pack_c(h.c, names) for h in hosts]
+            r = call(fresh, e2e_ranges)
+            if comm is not None and not is_somatic:
+                g = comm.gather(r, 0)
+                n_touch = len(g.records) if rank == 0 else 0   # the guac_threshold_record view of every gathered record
+                d2h = int(g.stats["d2h_bytes"]) if rank == 0 else 0
+                del g
+            else:
+                n_touch = len(r.records)
+                d2h = int(r.stats["d2h_bytes"])
+            h2d = sum(f.h2d_bytes for f in fresh) + int(r.stats["h2d_bytes"])
+            del r
+            for f in fresh:
+                f.free()
+        barrier()
+        out["e2e_ms"] = (time.perf_counter() - t1) * 1e3 / e2e_steps
+        out["e2e_loci"] = e2e_loci
+        out["h2d"], out["d2h"], out["e2e_records"] = h2d, d2h, n_touch
+        for h in hosts:
+            h.free()
+        return out
+
+    def summarise(o, is_somatic, kernel):
+        """max-over-ranks timings -> one workload block"""
+        step_ms, e2e_ms, tile_ms, exact_ms, pack_ms, expand_ms, gen_ms, ppc = reduce(
+            [o["step_ms"], o["e2e_ms"], o["tile_ms"], o["exact_ms"], o["pack_ms"], o["expand_ms"], o["gen_ms"], o["pack_plus_call_ms"]],
+            dist.ReduceOp.MAX)
+        loci, reads, alg, e2e_loci, recs, h2d = reduce([o["n_loci"], o["n_reads"], o["alg"], o["e2e_loci"], o["records"], o["h2d"]], dist.ReduceOp.SUM)
+        # roofline of the dominant kernel: the slowest rank's launch against one rank's share of the algorithmic bytes
+        achieved = (alg / world) / (tile_ms * 1e-3) / 1e9
+        blk = {"value": loci / (step_ms * 1e-3), "unit": "loci/s", "reads_per_sec": reads / (step_ms * 1e-3), "ms_per_step": step_ms,
+               "loci": int(loci), "reads": int(reads), "records_per_step": int(o.get("total_records", recs)),
+               "e2e": {"value": e2e_loci / (e2e_ms * 1e-3), "unit": "loci/s", "ms_per_step": e2e_ms, "loci": int(e2e_loci),
+                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": o["d2h"], "records_read": o["e2e_records"]},
+               "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": measured_traffic(kernel, loci / world, args.depth), "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": alg / world, "kernel_ms": tile_ms, "other_kernels_ms": exact_ms,
+                            "whole_step_achieved_gbs": (alg / world) / (step_ms * 1e-3) / 1e9},
+               "pack_plus_call_ms": ppc, "pack_kernel_ms": pack_ms, "expand_kernel_ms": expand_ms, "generate_kernel_ms": gen_ms,
+               "pack_plus_call_loci_per_s": loci / (ppc * 1e-3), "gpu_launches": int(o["launches"]), "wall_ms_per_step": o["wall_ms"],
+               "clocks": o["clocks"], "setup_s": o["setup_s"]}
+        if "parity_window" in o:
+            blk["parity_window"] = o["parity_window"]
+            blk["parity_window_records"] = o["parity_records"]
+        if "gather_check" in o:
+            blk["gather_check"] = o["gather_check"]
+            blk["mean_depth"] = o["mean_depth"]
+        if o.get("cpu"):
+            blk["cpu_baseline"] = cpu_baseline_block(o["cpu"], "somatic" if is_somatic else "germline")
+        return blk
+
+    e2e_steps = args.e2e_steps or min(args.steps, 5)
+    # the e2e slice: the whole shard at N = 1; a chr20-sized prefix of the shard at N > 1
+    if world == 1 or workload == "amplicon":
+        e2e_ranges = my_ranges
+    else:
+        e2e_ranges, left = [], CHR20
+        for r in my_ranges:
+            take = min(left, r[2] - r[1])
+            if take > 0:
+                e2e_ranges.append((r[0], r[1], r[1] + take, r[3]))
+                left -= take
+    c0, s0 = my_ranges[0][0], my_ranges[0][1]
+    if rank != 0:
+        cpu_window = None
+    elif workload == "amplicon":
+        cpu_window = (0, 0, 1500)
+    else:
+        w = min(args.cpu_window // (3 if somatic else 1), my_ranges[0][2] - s0)
+        cpu_window = (c0, max(0, s0 - SPAN), s0 + w)
+    main_out = run_workload(somatic, my_ranges, args.steps, e2e_steps, e2e_ranges, cpu_window)
+    main_blk = summarise(main_out, somatic, "k_somatic" if somatic else "k_call_tile")
+    som_blk = None
+    if world == 1 and workload == "germline" and not args.no_somatic:
+        w = min(args.cpu_window // 3, my_ranges[0][2])
+        som_out = run_workload(True, my_ranges, max(1, min(args.steps, 5)), 2, my_ranges, (c0, 0, w))
+        som_blk = summarise(som_out, True, "k_somatic")
+        som_blk["workload"] = (f"somatic-standard, synthetic tumor/normal pair {tumor_depth:g}x/{args.depth:g}x, chr20 shape "
+                               f"({args.contig_length:,} loci), {READ_LEN} bp (BASELINE.json configs[2])")
+        som_blk["dtype"] = "f64"
+
+    if rank == 0:
+        line = {"metric": "loci_per_sec", "value": main_blk["value"], "unit": "loci/s", "reads_per_sec": main_blk["reads_per_sec"],
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_blk["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+                "dtype": "f64" if somatic else "u8", "data": "synthetic (generated on the device from the seed)", "config": config}
+        for k in ("records_per_step", "gpu_launches", "e2e", "roofline", "clocks", "pack_plus_call_ms", "pack_kernel_ms", "expand_kernel_ms",
+                  "generate_kernel_ms", "pack_plus_call_loci_per_s", "wall_ms_per_step", "parity_window", "parity_window_records",
+                  "gather_check", "mean_depth", "cpu_baseline", "setup_s"):
+            if k in main_blk:
+                line[k] = main_blk[k]
+        line["e2e"]["steps"] = e2e_steps
+        if som_blk:
+            line["somatic"] = som_blk
+        bad = [b[k] for b in (main_blk, som_blk or {}) for k in ("parity_window", "gather_check") if b.get(k, "ok") != "ok"]
+        print(json.dumps(line), flush=True)
+        if bad:
+            print("PARITY FAILURE: " + "; ".join(bad), file=sys.stderr, flush=True)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -15,7 +15,7 @@ EXPORTED = [
     "guac_abi_version", "guac_ctx_create", "guac_ctx_destroy", "guac_last_error", "guac_status_string",
     "guac_ctx_set_option", "guac_ctx_timer_start", "guac_ctx_timer_stop", "guac_host_register", "guac_host_unregister",
     "guac_reads_pack", "guac_reads_pack_device", "guac_reads_free", "guac_reads_count", "guac_reads_device_bytes",
-    "guac_reads_order_sensitive_loci", "guac_reads_h2d_bytes", "guac_reads_pack_kernel_ms",
+    "guac_reads_order_sensitive_loci", "guac_reads_h2d_bytes", "guac_reads_pack_kernel_ms", "guac_reads_expand_kernel_ms",
     "guac_germline_threshold", "guac_somatic_standard", "guac_germline_standard", "guac_pileup_counts",
     "guac_allele_counts", "guac_result_allele_counts",
     "guac_result_n", "guac_result_threshold_records", "guac_result_compact_records", "guac_result_somatic_records", "guac_result_counts",
@@ -82,6 +82,8 @@ def lib():
         getattr(L, f).restype = C.c_uint64
     L.guac_reads_pack_kernel_ms.argtypes = [vp]
     L.guac_reads_pack_kernel_ms.restype = C.c_double
+    L.guac_reads_expand_kernel_ms.argtypes = [vp]
+    L.guac_reads_expand_kernel_ms.restype = C.c_double
     L.guac_germline_threshold.argtypes = [vp, vp, C.POINTER(abi.LocusRangeC), C.c_size_t,
                                           C.POINTER(abi.ThresholdParamsC), C.POINTER(vp)]
     L.guac_somatic_standard.argtypes = [vp, vp, vp, C.POINTER(abi.LocusRangeC), C.c_size_t,
@@ -126,6 +128,7 @@ def lib():
     L.guac_comm_reduce_depth_histogram.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
     # device build of the synthetic generator (include/guac_synth.h)
     L.guac_synth_generate_device.argtypes = [vp, vp, C.POINTER(vp)]
+    L.guac_reads_pack_synth.argtypes = [vp, vp, C.POINTER(abi.ReferenceC), C.POINTER(vp)]
     L.guac_synth_device_batch_view.argtypes = [vp]
     L.guac_synth_device_batch_view.restype = C.POINTER(abi.ReadBatchC)
     L.guac_synth_device_batch_ms.argtypes = [vp]

@@ -91,6 +91,11 @@ class Context:
         """guac_reads_pack_device: the batch's columns already live in this context's device memory."""
         return PackedReads(self, None, None, batch_c=batch_c, contig_names=contig_names, sample_names=sample_names, on_device=True)
 
+    def pack_synth(self, device_batch) -> "PackedReads":
+        """guac_reads_pack_synth: packs a synth.DeviceBatch, taking its large columns over instead of copying them."""
+        return PackedReads(self, None, None, synth_batch=device_batch, contig_names=device_batch.contig_names,
+                           sample_names=[device_batch.sample_name])
+
     def pack(self, batch: ReadBatch, reference: Optional[Sequence[bytes]] = None) -> "PackedReads":
         return PackedReads(self, batch, reference)
 
@@ -99,11 +104,14 @@ class PackedReads:
     """guac_reads: one sample's start-sorted reads packed into the device SoA (guac_reads_pack)."""
 
     def __init__(self, ctx: Context, batch: Optional[ReadBatch], reference: Optional[Sequence[bytes]] = None,
-                 batch_c=None, contig_names=None, sample_names=None, on_device=False):
+                 batch_c=None, contig_names=None, sample_names=None, on_device=False, synth_batch=None):
         self.ctx = ctx
         self.contig_names = list(batch.contig_names if batch is not None else (contig_names or []))
         self.sample_names = list(batch.sample_names if batch is not None else (sample_names or ["default"]))
         self._h = C.c_void_p()
+        if synth_batch is not None:
+            ctx._check(lib().guac_reads_pack_synth(ctx._h, synth_batch._h, None, C.byref(self._h)))
+            return
         b = batch.to_c() if batch is not None else batch_c
         ref = None
         if reference is not None:
@@ -126,6 +134,14 @@ class PackedReads:
     @property
     def order_sensitive_loci(self) -> int:
         return int(lib().guac_reads_order_sensitive_loci(self._h))
+
+    @property
+    def expand_kernel_ms(self) -> float:
+        return float(lib().guac_reads_expand_kernel_ms(self._h))
+
+    @property
+    def h2d_bytes(self) -> int:
+        return int(lib().guac_reads_h2d_bytes(self._h))
 
     @property
     def pack_kernel_ms(self) -> float:

@@ -95,7 +95,10 @@ void settle_streams(guac_ctx* ctx, guac_reads& rd, uint64_t entries, bool field_
 }
 
 // `on_device`: the batch's column pointers are device memory of ctx's device (guac_reads_pack_device): no host -> device copies.
-void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* ref, guac_reads& out, bool on_device) {
+// `adopt`: a generated device batch whose large columns (bases, qualities, CIGARs, MD tags, base offsets) the store takes
+// over instead of copying them (guac_reads_pack_synth): the whole-genome shards would not fit twice.
+void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* ref, guac_reads& out, bool on_device,
+                guac_synth_device_batch* adopt = nullptr) {
   if (!b) fail(GUAC_ERR_INVALID_ARGUMENT, "null batch");
   const uint64_t n = b->n_reads;
   if (n >= 0xFFFFFFF0ull) fail(GUAC_ERR_UNSUPPORTED, "more than 2^32 reads in one read set: shard it");
@@ -153,9 +156,15 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   HeaderArgs H{};
   H.n = n;
   H.n_contigs = b->n_contigs;
-  bring(out.cigar, b->cigar, (size_t)n_ops, 1);
-  bring(out.seq_off, b->seq_off, n ? n + 1 : 0, n ? 0 : 1);
-  bring(out.md, b->md, (size_t)n_md, 16);
+  if (adopt && n) {
+    out.cigar.adopt(adopt->cigar);
+    out.seq_off.adopt(adopt->seq_off);
+    out.md.adopt(adopt->md);
+  } else {
+    bring(out.cigar, b->cigar, (size_t)n_ops, 1);
+    bring(out.seq_off, b->seq_off, n ? n + 1 : 0, n ? 0 : 1);
+    bring(out.md, b->md, (size_t)n_md, 16);
+  }
   if (on_device) {
     H.contig = b->contig; H.start = b->start; H.cigar_off = b->cigar_off; H.mapq = b->mapq; H.flags = b->flags;
     H.sample = b->sample; H.md_off = b->md_off;
@@ -178,11 +187,18 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     H.contig_length = d_contig_length.p;
   }
   CUDA_OK(cudaEventRecord(ctx->copy_ev[4], cs));  // the small columns are on the device
-  out.seq.alloc((size_t)n_bases + 64);
-  CUDA_OK(cudaMemsetAsync(out.seq.p + n_bases, 0, 64, cs));
-  if (need_qual) {
-    out.qual.alloc((size_t)n_bases + 64);
-    CUDA_OK(cudaMemsetAsync(out.qual.p + n_bases, 0, 64, cs));
+  const bool adopt_bases = adopt && n;
+  if (adopt_bases) {
+    if (need_qual && !adopt->qual.n) fail(GUAC_ERR_INVALID_ARGUMENT, "the generated batch holds no base qualities");
+    out.seq.adopt(adopt->seq);
+    if (need_qual) out.qual.adopt(adopt->qual);
+  } else {
+    out.seq.alloc((size_t)n_bases + 64);
+    CUDA_OK(cudaMemsetAsync(out.seq.p + n_bases, 0, 64, cs));
+    if (need_qual) {
+      out.qual.alloc((size_t)n_bases + 64);
+      CUDA_OK(cudaMemsetAsync(out.qual.p + n_bases, 0, 64, cs));
+    }
   }
   constexpr int kMaxCopyChunks = 4;
   const int n_copy_chunks = n >= 1000000 ? kMaxCopyChunks : 1;
@@ -197,7 +213,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     }
     for (int k = 0; k < n_copy_chunks; ++k) {
       const uint64_t o0 = chunk_byte[k], o1 = chunk_byte[k + 1];
-      if (o1 > o0) {
+      if (o1 > o0 && !adopt_bases) {
         CUDA_OK(cudaMemcpyAsync(out.seq.p + o0, b->seq + o0, o1 - o0, kind, cs));
         if (need_qual) CUDA_OK(cudaMemcpyAsync(out.qual.p + o0, b->qual + o0, o1 - o0, kind, cs));
       }
@@ -417,6 +433,10 @@ uint64_t build_tiles(const guac_reads& reads, const guac_locus_range* ranges, si
       td.word0 = (int32_t)(t * kWarpWords);
       td.locus_begin = (int32_t)std::max<int64_t>(s, t * kWarpLoci);
       td.locus_end = (int32_t)std::min<int64_t>(e, (t + 1) * kWarpLoci);
+      td.gran = ci.gran_off + (uint32_t)t;
+      td.trk_word = ci.word_off + (uint32_t)td.word0;
+      td.n_words = std::min<int32_t>(kWarpWords, ci.n_words - td.word0);
+      td.pad_ = 0;
       if (td.locus_end > td.locus_begin) tiles.push_back(td);
     }
   }
@@ -912,6 +932,26 @@ guac_status guac_reads_pack_device(guac_ctx* ctx, const guac_read_batch* device_
   });
 }
 
+guac_status guac_reads_pack_synth(guac_ctx* ctx, guac_synth_device_batch* batch, const guac_reference* ref, guac_reads** out) {
+  if (!ctx || !out || !batch) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    if (batch->ctx != ctx) fail(GUAC_ERR_INVALID_ARGUMENT, "the batch was generated on another context");
+    if (batch->consumed) fail(GUAC_ERR_INVALID_ARGUMENT, "the batch was already packed (its columns moved into that read set)");
+    std::unique_ptr<guac_reads> r(new guac_reads());
+    try {
+      pack_reads(ctx, &batch->view, ref, *r, true, batch);
+    } catch (...) {
+      cudaStreamSynchronize(ctx->stream);
+      throw;
+    }
+    batch->consumed = true;
+    *out = r.release();
+  });
+}
+double guac_reads_expand_kernel_ms(const guac_reads* reads) { return reads ? reads->expand_ms : 0.0; }
+
 // ---- device build of the synthetic read generator (include/guac_synth.h) ---------------------------------------------------
 guac_status guac_synth_generate_device(guac_ctx* ctx, const guac_synth_params* p, guac_synth_device_batch** out) {
   if (!ctx || !p || !out) return GUAC_ERR_INVALID_ARGUMENT;
@@ -942,6 +982,7 @@ guac_status guac_synth_device_batch_download(guac_ctx* ctx, const guac_synth_dev
   *out = nullptr;
   return guarded(ctx, [&] {
     CUDA_OK(cudaSetDevice(ctx->device));
+    if (b->consumed) fail(GUAC_ERR_INVALID_ARGUMENT, "the batch was packed with guac_reads_pack_synth: its columns moved into that read set");
     std::unique_ptr<guac_synth_host_batch> h(new guac_synth_host_batch());
     synth_download(ctx, *b, pinned != 0, *h);
     *out = h.release();

@@ -50,9 +50,8 @@ __global__ void __launch_bounds__(kHistWarps * 32) k_depth_histogram(DevReads R,
   const uint32_t n_warps = gridDim.x * kHistWarps;
   for (uint32_t tile = blockIdx.x * kHistWarps + warp; tile < n_tiles; tile += n_warps) {
     const TileDesc td = tiles[tile];
-    const ContigInfo ci = R.contigs[td.contig];
     const int tile_lo = td.word0 << 5;
-    const uint32_t g = ci.gran_off + (uint32_t)(tile_lo >> kGranuleShift);
+    const uint32_t g = td.gran;
     const GranHdr hdr = R.gs_hdr[g];
     const size_t locus0 = (size_t)g * kGranuleLoci + (size_t)lane * 32;
     const int l0 = tile_lo + (lane << 5);

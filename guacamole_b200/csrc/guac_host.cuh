@@ -119,6 +119,11 @@ struct DevBuf {
       }
     }
   }
+  void adopt(DevBuf& o) {  // takes o's allocation (o is left empty)
+    release();
+    p = o.p; n = o.n; alloc_bytes = o.alloc_bytes;
+    o.p = nullptr; o.n = 0; o.alloc_bytes = 0;
+  }
   bool ensure(size_t count) {  // grow-only; true if (re)allocated
     if (p && n >= count) return false;
     alloc(count);

@@ -55,6 +55,20 @@ struct TileDesc {
   int32_t word0;       // first word of the tile (contig-relative)
   int32_t locus_begin; // requested loci of this tile: [locus_begin, locus_end)
   int32_t locus_end;
+  uint32_t gran;       // germline tiles: the granule's global index (gs_hdr, gs_dd, gran_first) ...
+  uint32_t trk_word;   // ... the global index of its first track word ...
+  int32_t n_words;     // ... and how many of its 32 words lie inside the contig: no ContigInfo load on the hot path
+  int32_t pad_;
+};
+
+// Records and deferred loci of one granule are staged in shared memory and leave with ONE global atomic per warp and kind
+// (the counters are single addresses: a quarter of a million returning atomics on them serialise in L2).
+constexpr int kStageRecords = 32, kStageSlow = 16;
+struct EmitStage {
+  unsigned long long rec[kStageRecords];
+  unsigned long long slow[kStageSlow];   // contig << 32 | locus
+  uint32_t n_rec, n_slow;
+  uint32_t pad_[2];
 };
 
 struct CallParams {
@@ -74,22 +88,63 @@ __device__ __forceinline__ unsigned long long compact_record(int contig, int loc
          ((unsigned long long)rcode << 11) | ((unsigned long long)g0 << 9) | ((unsigned long long)g1 << 7) | ((unsigned long long)tie << 6);
 }
 
-__device__ __forceinline__ void defer_locus(DevOut& out, int contig, int locus) {
+__device__ __forceinline__ void defer_locus(DevOut& out, int contig, int locus, EmitStage* stage = nullptr) {
+  if (stage) {
+    const uint32_t k = atomicAdd(&stage->n_slow, 1u);
+    if (k < (uint32_t)kStageSlow) {
+      stage->slow[k] = ((unsigned long long)(uint32_t)contig << 32) | (uint32_t)locus;
+      return;
+    }
+  }
   const uint32_t s = (uint32_t)atomicAdd(&out.counters[out.slow_ctr], 1ull);
   if (s < out.cap_slow) out.slow[s] = SlowLocus{contig, locus};
+}
+
+__device__ __forceinline__ void emit_compact(DevOut& out, unsigned long long rec, EmitStage* stage) {
+  if (stage) {
+    const uint32_t k = atomicAdd(&stage->n_rec, 1u);
+    if (k < (uint32_t)kStageRecords) {
+      stage->rec[k] = rec;
+      return;
+    }
+  }
+  const uint32_t s = (uint32_t)atomicAdd(&out.counters[6], 1ull);
+  if (s < out.cap_compact) out.compact[s] = rec;
+}
+
+// end of a granule (whole warp): the staged records and deferred loci leave with one global atomic each
+__device__ __forceinline__ void flush_stage(DevOut& out, EmitStage* stage) {
+  __syncwarp();
+  const int lane = threadIdx.x & 31;
+  const uint32_t nr = min(stage->n_rec, (uint32_t)kStageRecords), ns = min(stage->n_slow, (uint32_t)kStageSlow);
+  if (nr) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&out.counters[6], (unsigned long long)nr);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if ((uint32_t)lane < nr && base + lane < out.cap_compact) out.compact[base + lane] = stage->rec[lane];
+  }
+  if (ns) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&out.counters[out.slow_ctr], (unsigned long long)ns);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if ((uint32_t)lane < ns && base + lane < out.cap_slow) {
+      const unsigned long long v = stage->slow[lane];
+      out.slow[base + lane] = SlowLocus{(int32_t)(v >> 32), (int32_t)(uint32_t)v};
+    }
+  }
 }
 
 // GermlineThreshold.Caller.callVariantsAtLocus (commands/GermlineThresholdCaller.scala:90-179) on the A/C/G/T counts of one
 // locus: `total` elements, of which `o` are not plain bases and m1..m3 mismatch the reference base (code rcode) by class
 // (read code ^ reference code).  Loci the counts cannot decide exactly go to the exact kernel.
 __device__ __forceinline__ void call_snv_locus(const CallParams& prm, DevOut& out, int contig, int locus, int total, int o, int m1, int m2,
-                                               int m3, int rcode, bool std_ref, bool every_covered) {
+                                               int m3, int rcode, bool std_ref, bool every_covered, EmitStage* stage = nullptr) {
   // count * 100 / total > threshold  <=>  count * 100 >= (threshold + 1) * total   (integers, no division)
   const long long bar = (long long)(prm.threshold_percent + 1) * total;
   auto passes = [&](int count) { return (long long)count * 100 >= bar; };
   // any allele made of "other" elements has count <= o: if o cannot pass the threshold the SNV counts decide alone
   if (!(std_ref && !passes(o))) {
-    defer_locus(out, contig, locus);
+    defer_locus(out, contig, locus, stage);
     return;
   }
   const int mref = total - o - m1 - m2 - m3;
@@ -121,10 +176,7 @@ __device__ __forceinline__ void call_snv_locus(const CallParams& prm, DevOut& ou
     if (v1 != v2) { ne = 1; alt0 = 1 + (v1 ? b0 : b1); g0 = GUAC_GT_REF; g1 = GUAC_GT_ALT; }
     else { ne = 2; alt0 = 1 + b0; alt1 = 1 + b1; g0 = GUAC_GT_ALT; g1 = GUAC_GT_OTHER_ALT; }
   }
-  for (int k = 0; k < ne; ++k) {
-    const uint32_t s = (uint32_t)atomicAdd(&out.counters[6], 1ull);
-    if (s < out.cap_compact) out.compact[s] = compact_record(contig, locus, rcode, k == 0 ? alt0 : alt1, g0, g1, tie);
-  }
+  for (int k = 0; k < ne; ++k) emit_compact(out, compact_record(contig, locus, rcode, k == 0 ? alt0 : alt1, g0, g1, tie), stage);
 }
 
 // ---- K_tile ---------------------------------------------------------------------------------------------------------------

@@ -219,6 +219,7 @@ struct guac_synth_device_batch {
   DevBuf<char> md;
   uint64_t n = 0, n_ops = 0, n_md = 0, n_bases = 0;
   double kernel_ms = 0;
+  bool consumed = false;  // guac_reads_pack_synth moved the large columns into a read set
   guac_read_batch view{};
 };
 
@@ -292,7 +293,13 @@ void synth_generate_device(guac_ctx* ctx, const guac_synth_params& P, guac_synth
   B.cigar.alloc(B.n_ops + 4);
   B.md.alloc(B.n_md + 16);
   B.seq.alloc(B.n_bases + 64);
-  if (P.with_qualities) B.qual.alloc(B.n_bases + 64);
+  CUDA_OK(cudaMemsetAsync(B.cigar.p + B.n_ops, 0, 4 * sizeof(uint32_t), st));
+  CUDA_OK(cudaMemsetAsync(B.md.p + B.n_md, 0, 16, st));
+  CUDA_OK(cudaMemsetAsync(B.seq.p + B.n_bases, 0, 64, st));
+  if (P.with_qualities) {
+    B.qual.alloc(B.n_bases + 64);
+    CUDA_OK(cudaMemsetAsync(B.qual.p + B.n_bases, 0, 64, st));
+  }
   if (n) {
     k_synth_write<<<grid_for(n, 128, ctx->sm_count), 128, 0, st>>>(d_T.p, n, B.start.p, B.contig.p, rank.p, B.cigar_off.p, B.md_off.p, B.seq_off.p, B.cigar.p,
                                                                    B.seq.p, P.with_qualities ? B.qual.p : nullptr, B.md.p, B.mapq.p, B.flags.p);

@@ -325,25 +325,26 @@ __global__ void __launch_bounds__(kExpandWarps * 32) k_expand(ExpandArgs A) {
 template <bool WIDE>
 struct CallSmem {
   alignas(16) uint32_t cnt[CntLayout<WIDE>::kWords + 4];  // (+ the dummy word the stream's padding entries point at)
+  EmitStage stage;
 };
 
 // the per-locus work past the cheap reject: the counts row (counts mode) or callVariantsAtLocus on the SNV alleles
 template <bool WIDE, int MODE>
-__device__ __forceinline__ void tile_call_locus(const uint32_t* cnt, const DevReads& R, const ContigInfo& ci, const TileDesc& td, const CallParams& prm,
+__device__ __forceinline__ void tile_call_locus(const uint32_t* cnt, const DevReads& R, const TileDesc& td, const CallParams& prm,
                                                 DevOut& out, const int x, const int total, const int pos_total, const bool every_covered,
-                                                const bool all_loci) {
+                                                const bool all_loci, EmitStage* stage) {
   if (total == 0 && !all_loci) return;  // callVariantsAtLocus returns nothing on an empty pileup
   using L = CntLayout<WIDE>;
   const int o = (int)L::field(cnt, x, 0), m1 = (int)L::field(cnt, x, 1), m2 = (int)L::field(cnt, x, 2), m3 = (int)L::field(cnt, x, 3);
-  const int w = td.word0 + (x >> 5), b = x & 31;
+  const int w = x >> 5, b = x & 31;
   uint32_t wl = 0, wh = 0, ws = 0;
-  if (w < ci.n_words) { wl = R.trk_lo[ci.word_off + w]; wh = R.trk_hi[ci.word_off + w]; ws = R.trk_std[ci.word_off + w]; }
+  if (w < td.n_words) { wl = R.trk_lo[td.trk_word + w]; wh = R.trk_hi[td.trk_word + w]; ws = R.trk_std[td.trk_word + w]; }
   const bool std_ref = (ws >> b) & 1u;
   const int rcode = (int)(((wl >> b) & 1u) | (((wh >> b) & 1u) << 1));
   const int locus = (td.word0 << 5) + x;
   if (MODE == 1) {
     if (!std_ref && total > 0) {
-      defer_locus(out, td.contig, locus);
+      defer_locus(out, td.contig, locus, stage);
       return;
     }
     const uint32_t s = (uint32_t)atomicAdd(&out.counters[0], 1ull);
@@ -365,7 +366,7 @@ __device__ __forceinline__ void tile_call_locus(const uint32_t* cnt, const DevRe
     }
     return;
   }
-  call_snv_locus(prm, out, td.contig, locus, total, o, m1, m2, m3, rcode, std_ref, every_covered);
+  call_snv_locus(prm, out, td.contig, locus, total, o, m1, m2, m3, rcode, std_ref, every_covered, stage);
 }
 
 __device__ __forceinline__ uint32_t pick8(const uint32_t (&v)[8], int i) {  // v[i] without dynamic register indexing
@@ -385,9 +386,8 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_call_tile(DevReads R, const
   if (tile >= n_tiles) return;  // whole warp
   CallSmem<WIDE>& S = reinterpret_cast<CallSmem<WIDE>*>(smem_raw)[threadIdx.x >> 5];
   const TileDesc td = tiles[tile];
-  const ContigInfo ci = R.contigs[td.contig];
   const int tile_lo = td.word0 << 5;
-  const uint32_t g = ci.gran_off + (uint32_t)(tile_lo >> kGranuleShift);
+  const uint32_t g = td.gran;
   const GranHdr hdr = R.gs_hdr[g];
 
   // ---- phase 0: clear the counter tile; the lane's own track word and start / end fields are requested right away
@@ -395,9 +395,9 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_call_tile(DevReads R, const
     uint4* c4 = reinterpret_cast<uint4*>(S.cnt);
     for (int i = lane; i < (int)(sizeof(S.cnt) / 16); i += 32) c4[i] = make_uint4(0u, 0u, 0u, 0u);
   }
-  const int my_word = td.word0 + lane;  // the lane owns loci [32 lane, 32 lane + 32) of the granule = one track word
-  uint32_t my_std = 0;
-  if (my_word < ci.n_words) my_std = R.trk_std[ci.word_off + my_word];
+  if (lane == 0) { S.stage.n_rec = 0; S.stage.n_slow = 0; }
+  uint32_t my_std = 0;  // the lane owns loci [32 lane, 32 lane + 32) of the granule = one track word
+  if (lane < td.n_words) my_std = R.trk_std[td.trk_word + lane];
   constexpr uint32_t kOnes = 0x01010101u;
   const size_t locus0 = (size_t)g * kGranuleLoci + (size_t)lane * 32;
   // narrow stores: the lane's 32 start / end bytes (and, in counts mode, the positive-strand ones) stay in registers;
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_call_tile(DevReads R, const
       const bool std_ref = (my_std >> kk) & 1u;
       if (!dense && differing == 0u && std_ref) continue;  // every element matches the reference: nothing to call
       if (!dense && std_ref && (unsigned long long)differing * 100ull < (unsigned long long)thr_plus_1 * (unsigned long long)(uint32_t)dep) continue;
-      tile_call_locus<WIDE, MODE>(S.cnt, R, ci, td, prm, out, x, dep, pdep, every_covered, all_loci);
+      tile_call_locus<WIDE, MODE>(S.cnt, R, td, prm, out, x, dep, pdep, every_covered, all_loci, &S.stage);
     }
   } else {
     // sparse calls over 8-bit counter fields, four consecutive loci per step.  The few loci that survive the reject are
@@ -560,11 +560,12 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_call_tile(DevReads R, const
         const uint32_t m = j < (kk >> 2) ? 0x0F0F0F0Fu : j == (kk >> 2) ? (0x0F0F0F0Fu >> (8 * (3 - (kk & 3)))) : 0u;
         d += (int)__dp4a(dd[j] & m, kOnes, 0u) - (int)__dp4a((dd[j] >> 4) & m, kOnes, 0u);
       }
-      tile_call_locus<WIDE, MODE>(S.cnt, R, ci, td, prm, out, (lane << 5) + kk, d, 0, every_covered, all_loci);
+      tile_call_locus<WIDE, MODE>(S.cnt, R, td, prm, out, (lane << 5) + kk, d, 0, every_covered, all_loci, &S.stage);
     }
   }
+  flush_stage(out, &S.stage);
   // one atomic per warp for the visited-loci counter
-  for (int o = 16; o; o >>= 1) n_visited += __shfl_xor_sync(0xFFFFFFFFu, n_visited, o);
+  n_visited = __reduce_add_sync(0xFFFFFFFFu, n_visited);
   if (lane == 0 && n_visited) atomicAdd(&out.counters[3], (unsigned long long)n_visited);
   if (overflow) atomicAdd(&out.counters[5], 1ull);
 }

@@ -288,6 +288,7 @@ uint64_t guac_reads_device_bytes(const guac_reads* reads);
 /* loci where the reads' MD-derived reference bases disagreed and the canonical rule chose one */
 uint64_t guac_reads_order_sensitive_loci(const guac_reads* reads);
 uint64_t guac_reads_h2d_bytes(const guac_reads* reads);      /* bytes guac_reads_pack copied host -> device */
+double guac_reads_expand_kernel_ms(const guac_reads* reads); /* ... of which the expansion into difference streams (k_expand) */
 double guac_reads_pack_kernel_ms(const guac_reads* reads);   /* first to last pack kernel on the compute stream (CUDA events);
                                                                  includes waiting for the chunked host -> device copies */
 

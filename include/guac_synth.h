@@ -47,6 +47,9 @@ typedef struct guac_synth_device_batch guac_synth_device_batch;
 guac_status guac_synth_generate_device(guac_ctx* ctx, const guac_synth_params* p, guac_synth_device_batch** out);
 const guac_read_batch* guac_synth_device_batch_view(const guac_synth_device_batch* b);
 double guac_synth_device_batch_ms(const guac_synth_device_batch* b);   /* device time of the generator kernels */
+/* guac_reads_pack_device that takes the batch's large columns over instead of copying them (the whole-genome shards would not
+ * fit twice); afterwards the batch can only be freed. */
+guac_status guac_reads_pack_synth(guac_ctx* ctx, guac_synth_device_batch* b, const guac_reference* ref, guac_reads** out);
 void guac_synth_device_batch_free(guac_synth_device_batch* b);
 /* Copies the columns into host memory (page-locked when `pinned`): the end-to-end bench leg starts there. */
 typedef struct guac_synth_host_batch guac_synth_host_batch;
