@@ -249,16 +249,6 @@ def cpu_baseline_block(cpu, what):
                       "algorithm, one loci task per thread (no JVM on the box)"}
 
 
-def device_u64(ptr, index):
-    """element `index` of a device column of 8-byte elements"""
-    import torch
-    buf = C.c_uint64(0)
-    err = torch.cuda.cudart().cudaMemcpy(C.addressof(buf), C.cast(ptr, C.c_void_p).value + index * 8, 8, 2)  # device -> host
-    if int(err) != 0:
-        raise RuntimeError(f"cudaMemcpy failed: {err}")
-    return int(buf.value)
-
-
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -351,9 +341,8 @@ def main():
         for s, d in samples:  # generated on the device, packed there (the large columns move into the read set)
             dv = synth.generate_device(ctx, contigs, depth=d, read_length=READ_LEN, seed=args.seed, sample=s,
                                        windows=synth.shard_windows(ranges, READ_LEN), with_qualities=is_somatic)
-            n_ops = device_u64(dv.c.cigar_off, dv.n_reads) if dv.n_reads else 0
             n_reads += dv.n_reads
-            alg += algorithmic_bytes_of(dv.n_reads, n_ops, dv.n_reads * READ_LEN, is_somatic)
+            alg += algorithmic_bytes_of(dv.n_reads, dv.n_cigar_ops, dv.n_bases, is_somatic)
             gen_ms += dv.kernel_ms
             packed.append(ctx.pack_synth(dv))
             dv.free()

@@ -133,6 +133,8 @@ def lib():
     L.guac_synth_device_batch_view.restype = C.POINTER(abi.ReadBatchC)
     L.guac_synth_device_batch_ms.argtypes = [vp]
     L.guac_synth_device_batch_ms.restype = C.c_double
+    L.guac_synth_device_batch_totals.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.guac_synth_device_batch_totals.restype = None
     L.guac_synth_device_batch_free.argtypes = [vp]
     L.guac_synth_device_batch_free.restype = None
     L.guac_synth_device_batch_download.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]

@@ -143,6 +143,7 @@ OPT_SORT_RECORDS = 1
 OPT_PACK_QUALITIES = 2
 OPT_HOST_THREADS = 3
 OPT_DIFFERENCE_LISTS = 4
+OPT_SEGMENTS = 5
 
 
 def struct_to_dict(s):

@@ -31,14 +31,21 @@ namespace {
 // ---- per-granule difference streams (k_expand, guac_tile.cuh) -------------------------------------------------------------------
 // One launch builds every granule's stream.  The stream buffer is sized from an estimate and the start / end counters are
 // stored as nibbles first: a launch that ran out of either (counters[2] / [3]) is repeated with what it asked for.
-void launch_expand(guac_ctx* ctx, guac_reads& rd, bool huge, uint64_t cap_entries) {
-  cudaStream_t st = ctx->stream;
+void alloc_streams(guac_reads& rd, uint64_t cap_entries) {
   const uint64_t grans = rd.total_grans;
   cap_entries = (cap_entries + 7) & ~7ull;
   rd.gs_hdr.alloc(grans + 1);
   rd.gs_diffs.alloc(cap_entries + 8);
   rd.gs_dd.alloc(grans * kGranuleLoci * (rd.gs_wide ? 4 : 1) + 16);
   rd.gs_dp.alloc(grans * kGranuleLoci * (rd.gs_wide ? 4 : 1) + 16);
+  rd.gs_entries = cap_entries;
+}
+
+void launch_expand(guac_ctx* ctx, guac_reads& rd, bool huge, uint64_t cap_entries, bool allocated = false) {
+  cudaStream_t st = ctx->stream;
+  const uint64_t grans = rd.total_grans;
+  if (!allocated) alloc_streams(rd, cap_entries);
+  cap_entries = rd.gs_entries;
   CUDA_OK(cudaMemsetAsync(ctx->d_counters + 2, 0, 2 * sizeof(unsigned long long), st));
   if (!grans) return;
   ExpandArgs E;
@@ -65,7 +72,6 @@ void launch_expand(guac_ctx* ctx, guac_reads& rd, bool huge, uint64_t cap_entrie
   else k_expand<false><<<ctas, kExpandWarps * 32, kExpandWarps * sizeof(ExpandSmem<false>), st>>>(E);
   CUDA_OK(cudaEventRecord(ctx->ev[3], st));
   CUDA_OK(cudaGetLastError());
-  rd.gs_entries = cap_entries;
 }
 
 // After a launch: `entries` reserved, `field_overflow` = a start / end count did not fit.  Repeats the launch until it fits.
@@ -250,9 +256,13 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   CUDA_OK(cudaStreamWaitEvent(st, ctx->copy_ev[4], 0));
   CUDA_OK(cudaEventRecord(ctx->ev[0], st));
   uint64_t pair_total = 0;
+  float header_ms = 0;
   if (n) {
     k_header<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(H);
     pair_total = device_exclusive_scan<uint32_t>(ctx, d_n_pairs.p, n, d_pair_off.p);
+    CUDA_OK(cudaEventRecord(ctx->ev[1], st));
+    CUDA_OK(cudaEventSynchronize(ctx->ev[1]));
+    CUDA_OK(cudaEventElapsedTime(&header_ms, ctx->ev[0], ctx->ev[1]));
     if (pair_total >= 0xFFFFFF00ull) fail(GUAC_ERR_UNSUPPORTED, "more than 2^37 bases in one read set: shard it");
     k_header_finish<<<grid_for(n + 1, 256, ctx->sm_count), 256, 0, st>>>(out.rec.p, d_pair_off.p, out.cig_off.p, out.md_off.p, H.cigar_off, H.md_off, n);
   } else {
@@ -318,19 +328,25 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   out.del_md.alloc(n);
   out.del_len.alloc(n);
   if (out.has_qualities) out.qc.alloc((size_t)n_bases + 64);
-  CUDA_OK(cudaMemsetAsync(out.pairs.p, 0, out.pairs.bytes(), st));
-  CUDA_OK(cudaMemsetAsync(out.xmask.p, 0, out.xmask.bytes(), st));
   out.trk_lo.alloc(word_off + 1);
   out.trk_hi.alloc(word_off + 1);
   out.trk_std.alloc(word_off + 1);
   conflict.alloc(word_off + 1);
+  out.gran_first.alloc(gran_off + 1);
+  out.gran_last.alloc(gran_off + 1);
+  gran_count.alloc(gran_off + 1);
+  if (n && ctx->difference_lists) {
+    out.gs_wide = false;
+    alloc_streams(out, (uint64_t)n * 3 + gran_off * 8 + 4096);
+  }
+  // (everything is allocated: from here to the last pack kernel the device works without waiting for the host)
+  CUDA_OK(cudaEventRecord(ctx->ev[0], st));
+  CUDA_OK(cudaMemsetAsync(out.pairs.p, 0, out.pairs.bytes(), st));
+  CUDA_OK(cudaMemsetAsync(out.xmask.p, 0, out.xmask.bytes(), st));
   CUDA_OK(cudaMemsetAsync(out.trk_lo.p, 0, out.trk_lo.bytes(), st));
   CUDA_OK(cudaMemsetAsync(out.trk_hi.p, 0, out.trk_hi.bytes(), st));
   CUDA_OK(cudaMemsetAsync(out.trk_std.p, 0, out.trk_std.bytes(), st));
   CUDA_OK(cudaMemsetAsync(conflict.p, 0, conflict.bytes(), st));
-  out.gran_first.alloc(gran_off + 1);
-  out.gran_last.alloc(gran_off + 1);
-  gran_count.alloc(gran_off + 1);
   CUDA_OK(cudaMemsetAsync(out.gran_first.p, 0xFF, out.gran_first.bytes(), st));
   CUDA_OK(cudaMemsetAsync(out.gran_last.p, 0, out.gran_last.bytes(), st));
   CUDA_OK(cudaMemsetAsync(gran_count.p, 0, gran_count.bytes(), st));
@@ -398,8 +414,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     out.pack_launches += 1;
   }
   if (n && ctx->difference_lists) {  // the track is final: every granule's reads as their differences against it
-    out.gs_wide = false;
-    launch_expand(ctx, out, /*huge=*/false, (uint64_t)n * 3 + gran_off * 8 + 4096);
+    launch_expand(ctx, out, /*huge=*/false, out.gs_entries, /*allocated=*/true);
     out.pack_launches += 1;
   }
   CUDA_OK(cudaEventRecord(ctx->ev[1], st));
@@ -409,7 +424,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   check_device_error(ctx, "guac_reads_pack");
   float ms = 0;
   CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-  out.pack_kernel_ms = ms;
+  out.pack_kernel_ms = ms + header_ms;  // header kernel + scan, then first memset to last pack kernel (waits for copy chunks included)
   out.order_sensitive_loci = counters[0];
   out.max_reads_per_granule = counters[1];
   if (n && ctx->difference_lists) settle_streams(ctx, out, counters[2], counters[3] != 0, /*was_huge=*/false);
@@ -484,6 +499,9 @@ uint64_t prepare_tiles(guac_ctx* ctx, const guac_reads& reads, const guac_locus_
       CUDA_OK(cudaMemcpyAsync(ctx->tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
     ctx->n_tiles = tiles.size();
+    ctx->tiles_in_order = true;  // are the tiles in canonical (contig, start) order?  (then so are the records laid out tile by tile)
+    for (size_t i = 1; i < tiles.size() && ctx->tiles_in_order; ++i)
+      ctx->tiles_in_order = std::make_pair(tiles[i - 1].contig, tiles[i - 1].locus_begin) < std::make_pair(tiles[i].contig, tiles[i].locus_begin);
     ctx->tiles_key_loci = tl;
     ctx->tiles_key_reads = (const void*)&reads;
     ctx->tiles_key_ranges.assign(ranges, ranges + n_ranges);
@@ -527,7 +545,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     set_all_smem_attrs();
     ctx->smem_attrs_done = true;
   }
-  cudaStream_t st = ctx->stream, st2 = ctx->stream2;
+  cudaStream_t st = ctx->stream, st2 = ctx->stream2, st3 = ctx->stream3;
   const bool counts_mode = prm.mode == 1;
   const bool dense = counts_mode || prm.emit_ref || prm.emit_no_call;
   // counts mode: rows (guac_locus_counts) in HBM, copied afterwards.  Germline mode: the tile kernel's single-base records
@@ -538,8 +556,8 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
   uint64_t cap_slow = std::max<uint64_t>(4096, tile_loci / 32);
   uint64_t cap_pool = kPoolDynOff + std::max<uint64_t>(65536, tile_loci / 64);
   if (counts_mode) cap_rec = std::max<uint64_t>(cap_rec, ctx->out_rec.n / sizeof(guac_locus_counts));
-  cap_compact = std::max<uint64_t>(cap_compact, ctx->out_compact.n / 8);
-  cap_slow = std::max<uint64_t>(cap_slow, ctx->out_slow.n / sizeof(SlowLocus) / 2);  // (two segments share the buffer)
+  cap_compact = std::max<uint64_t>(cap_compact, ctx->out_compact.n / 8 / 4);  // (up to four segments share the buffers)
+  cap_slow = std::max<uint64_t>(cap_slow, ctx->out_slow.n / sizeof(SlowLocus) / 4);
   if (counts_mode) cap_pool = std::max<uint64_t>(cap_pool, ctx->out_pool.n);
   const bool streams = reads.gs_hdr.n != 0;
   // narrow counter fields (8 bits) unless the store is wide; the tile kernel reports a possible overflow and we widen
@@ -571,70 +589,100 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       ctx->out_rec.ensure(cap_rec * sizeof(guac_locus_counts));
       if (ctx->out_pool.ensure(cap_pool)) ctx->pool_head_ready = false;
     }
-    // Germline calls over many tiles run the tile kernel in two halves: the exact kernel of the first half (second stream)
-    // walks its loci while the second half's tile kernel runs.
-    const int n_seg = (!counts_mode && ctx->n_tiles >= 8192) ? 2 : 1;
+    // After the tile kernel, the exact kernel (second stream) and the egress of the compact records (third stream) run side by
+    // side.  A call may also be cut into up to four segments of tiles (GUAC_OPT_SEGMENTS) whose side work overlaps the next
+    // segment's tile kernel; measured on B200 that interleaving costs the tile kernel more than it hides, so the default is 1.
+    const int n_seg = counts_mode ? 1 : ctx->segments;
+    const uint64_t cap_seg = counts_mode ? 8 : cap_compact;   // compact records one segment may hold (each gets the full allowance)
     ctx->out_slow.ensure((size_t)n_seg * cap_slow * sizeof(SlowLocus));
+    if (!counts_mode) {
+      ctx->out_compact.ensure((size_t)n_seg * cap_seg * 8 + 16);
+      ctx->sort_rec.ensure((size_t)(n_seg + 1) * cap_seg * 8 + 16);   // per-segment grouped records, then the contiguous copy
+    }
     CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
     DevOut out;
     out.trec = counts_mode ? (guac_threshold_record*)ctx->out_rec.p : (guac_threshold_record*)((unsigned char*)res.block + full_at);
     out.crec = (guac_locus_counts*)ctx->out_rec.p;
     out.cap_rec = (uint32_t)cap_rec;
     out.compact = (unsigned long long*)ctx->out_compact.p;
-    out.cap_compact = counts_mode ? 0u : (uint32_t)cap_compact;
+    out.cap_compact = counts_mode ? 0u : (uint32_t)cap_seg;
     out.pool = counts_mode ? ctx->out_pool.p : (uint8_t*)res.block;
     out.cap_pool = (uint32_t)cap_pool;
     out.slow = (SlowLocus*)ctx->out_slow.p;
     out.cap_slow = (uint32_t)cap_slow;
-    out.slow_ctr = 2;
+    out.slow_ctr = 8;
+    out.compact_ctr = 12;
     out.counters = ctx->d_counters;
     out.err = ctx->d_err;
     const DevReads R = reads.view();
     const TileDesc* d_tiles = (const TileDesc*)ctx->tiles.p;
-    nvtx_push("guac tile + exact kernels");
+    unsigned long long* h_compact = counts_mode ? nullptr : (unsigned long long*)((unsigned char*)res.block + compact_at);
+    unsigned long long* d_contig = counts_mode ? nullptr : (unsigned long long*)ctx->sort_rec.p + (size_t)n_seg * cap_seg;
+    // canonical order on the device: every tile sorts its own few records, the egress kernels lay the tiles out in order
+    const bool device_sort = !counts_mode && ctx->sort_records && !dense && streams;
+    const uint64_t nt_all = ctx->n_tiles;
+    if (device_sort) {
+      ctx->sort_bins.ensure(3 * (nt_all + 8));  // tile_base | tile_n | prefix
+      ctx->scan_totals.ensure((size_t)n_seg * ((nt_all + kScanChunk - 1) / kScanChunk + 2));
+      CUDA_OK(cudaMemsetAsync(ctx->sort_bins.p + (nt_all + 8), 0, (nt_all + 8) * sizeof(uint32_t), st));  // tile_n
+      out.tile_base = ctx->sort_bins.p;
+      out.tile_n = ctx->sort_bins.p + (nt_all + 8);
+    } else {
+      out.tile_base = nullptr;
+      out.tile_n = nullptr;
+    }
+    out.tile0 = 0;
+    nvtx_push("guac tile + exact kernels + record egress");
     CUDA_OK(cudaEventRecord(ctx->ev[0], st));
-    const uint64_t seg_tiles[3] = {0, n_seg == 2 ? (ctx->n_tiles / 2 + 3) & ~3ull : ctx->n_tiles, ctx->n_tiles};
+    CUDA_OK(cudaStreamWaitEvent(st3, ctx->ev[0], 0));  // (the counters are cleared)
     for (int seg = 0; seg < n_seg; ++seg) {
+      const uint64_t t0 = ((ctx->n_tiles * (uint64_t)seg / n_seg) + 3) & ~3ull, t1 = seg + 1 == n_seg ? ctx->n_tiles : ((ctx->n_tiles * (uint64_t)(seg + 1) / n_seg) + 3) & ~3ull;
       DevOut so = out;
+      so.tile0 = (uint32_t)t0;
       so.slow = out.slow + (size_t)seg * cap_slow;
-      so.slow_ctr = seg == 0 ? 2u : 8u;
-      const int nt = (int)(seg_tiles[seg + 1] - seg_tiles[seg]);
-      if (counts_mode) launch_tile<1>(streams, wide, nt, st, R, d_tiles + seg_tiles[seg], prm, so);
-      else launch_tile<0>(streams, wide, nt, st, R, d_tiles + seg_tiles[seg], prm, so);
-      // the exact kernel reads the number of deferred loci from the device counter: no host round trip in between
-      cudaEvent_t done = seg + 1 == n_seg ? ctx->ev[1] : ctx->seg_ev;
+      so.slow_ctr = 8u + (uint32_t)seg;
+      so.compact = out.compact + (size_t)seg * cap_seg;
+      so.compact_ctr = 12u + (uint32_t)seg;
+      const int nt = (int)(t1 - t0);
+      if (nt > 0) {
+        if (counts_mode) launch_tile<1>(streams, wide, nt, st, R, d_tiles + t0, prm, so);
+        else launch_tile<0>(streams, wide, nt, st, R, d_tiles + t0, prm, so);
+        launches += 1;
+      }
+      // the side streams read the segment's counters from device memory: no host round trip in between
+      cudaEvent_t done = seg + 1 == n_seg ? ctx->ev[1] : ctx->seg_ev[seg];
       CUDA_OK(cudaEventRecord(done, st));
       CUDA_OK(cudaStreamWaitEvent(st2, done, 0));
       k_exact_loci<<<ctx->sm_count * 16, kExactWarps * 32, 0, st2>>>(R, so.slow, prm, so);
-      launches += 2;
+      launches += 1;
+      if (!counts_mode) {
+        CUDA_OK(cudaStreamWaitEvent(st3, done, 0));
+        if (device_sort && nt > 0) {
+          const uint64_t n_chunks = ((uint64_t)nt + kScanChunk - 1) / kScanChunk;
+          uint64_t* totals = ctx->scan_totals.p + (size_t)seg * ((nt_all + kScanChunk - 1) / kScanChunk + 2);
+          uint32_t* prefix = ctx->sort_bins.p + 2 * (nt_all + 8) + t0;
+          k_scan_totals<<<(unsigned)n_chunks, 256, 0, st3>>>(out.tile_n + t0, (uint64_t)nt, totals);
+          k_scan_chunks<<<1, 1024, 0, st3>>>(totals, n_chunks);
+          k_scan_final<uint32_t><<<(unsigned)n_chunks, 256, 0, st3>>>(out.tile_n + t0, (uint64_t)nt, totals, prefix);
+          k_rec_gather<<<grid_for((uint64_t)nt, 256, ctx->sm_count), 256, 0, st3>>>(so.compact, out.tile_base + t0, out.tile_n + t0, prefix, (uint32_t)nt,
+                                                                                    ctx->d_counters, (uint32_t)seg, so.cap_compact, d_contig, cap_compact);
+          k_rec_to_host<<<ctx->sm_count, 256, 0, st3>>>(d_contig, ctx->d_counters, (uint32_t)seg, so.cap_compact, h_compact, cap_compact);
+          launches += 5;
+        } else {
+          k_rec_flush<<<ctx->sm_count, 256, 0, st3>>>(so.compact, ctx->d_counters, (uint32_t)seg, so.cap_compact, h_compact, d_contig, cap_compact);
+          launches += 1;
+        }
+      }
     }
     CUDA_OK(cudaEventRecord(ctx->join_ev, st2));
-    nvtx_pop();
-    nvtx_push("guac record egress");
-    bool device_sorted = false;
-    unsigned long long* h_compact = counts_mode ? nullptr : (unsigned long long*)((unsigned char*)res.block + compact_at);
-    if (!counts_mode) {
-      const unsigned long long* src = out.compact;
-      if (ctx->sort_records && !dense) {  // canonical order restored on the device (k_rec_*)
-        const uint32_t n_bins = (uint32_t)reads.total_grans;
-        ctx->sort_bins.ensure(2 * ((size_t)n_bins + 1));
-        ctx->sort_rec.ensure(cap_compact * 8 + 16);
-        uint32_t* hist = ctx->sort_bins.p;
-        uint32_t* cursor = hist + n_bins + 1;
-        unsigned long long* grouped = (unsigned long long*)ctx->sort_rec.p;
-        CUDA_OK(cudaMemsetAsync(hist, 0, ((size_t)n_bins + 1) * sizeof(uint32_t), st));
-        k_rec_hist<<<ctx->sm_count * 2, 256, 0, st>>>(R, out.compact, ctx->d_counters, out.cap_compact, hist);
-        k_rec_scan<<<1, 1024, 0, st>>>(hist, cursor, n_bins);
-        k_rec_scatter<<<ctx->sm_count * 2, 256, 0, st>>>(R, out.compact, ctx->d_counters, out.cap_compact, cursor, grouped);
-        k_rec_finish<<<grid_for(n_bins, 256, ctx->sm_count), 256, 0, st>>>(hist, n_bins, grouped, ctx->d_counters);
-        src = grouped;
-        device_sorted = true;
-        launches += 4;
-      }
-      k_rec_flush<<<ctx->sm_count * 2, 256, 0, st>>>(src, ctx->d_counters, out.cap_compact, h_compact);
-      launches += 1;
-    }
     CUDA_OK(cudaStreamWaitEvent(st, ctx->join_ev, 0));
+    if (!counts_mode) {
+      CUDA_OK(cudaEventRecord(ctx->join3_ev, st3));
+      CUDA_OK(cudaStreamWaitEvent(st, ctx->join3_ev, 0));
+    }
+    nvtx_pop();
+    nvtx_push("guac status copy");
+    const bool device_sorted = device_sort;
     CUDA_OK(cudaEventRecord(ctx->ev[2], st));
     CUDA_OK(cudaGetLastError());
     // counters and the device error word come back in one copy, one synchronisation per call
@@ -643,6 +691,15 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     CUDA_OK(cudaStreamSynchronize(st));
     nvtx_pop();
     raise_device_error(ctx, "pileup");
+    if (device_sort && c[7]) {
+      // a tile held more records than it orders in shared memory: its surplus is not part of any tile's slice.  Copy every
+      // segment's records as they are instead (still on the device); the host orders them when the view is built.
+      for (int seg = 0; seg < n_seg; ++seg)
+        k_rec_flush<<<ctx->sm_count, 256, 0, st>>>(out.compact + (size_t)seg * cap_seg, ctx->d_counters, (uint32_t)seg, (uint32_t)cap_seg, h_compact, d_contig, cap_compact);
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaStreamSynchronize(st));
+      launches += n_seg;
+    }
     float ms = 0;
     CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     tile_ms += ms;
@@ -662,10 +719,17 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       }
       continue;
     }
-    if (c[2] > cap_slow || c[8] > cap_slow || c[0] > cap_rec || c[6] > cap_compact || kPoolDynOff + c[1] > cap_pool) {
-      cap_slow = std::max<uint64_t>(cap_slow, std::max(c[2], c[8]) + std::max(c[2], c[8]) / 8 + 16);
+    unsigned long long max_slow = 0, max_seg = 0, n_compact_total = 0, n_slow_total = 0;
+    for (int sg = 0; sg < 4; ++sg) {
+      max_slow = std::max(max_slow, c[8 + sg]);
+      max_seg = std::max(max_seg, c[12 + sg]);
+      n_compact_total += c[12 + sg];
+      n_slow_total += c[8 + sg];
+    }
+    if (max_slow > cap_slow || c[0] > cap_rec || max_seg > cap_seg || n_compact_total > cap_compact || kPoolDynOff + c[1] > cap_pool) {
+      cap_slow = std::max<uint64_t>(cap_slow, max_slow + max_slow / 8 + 16);
       cap_rec = std::max<uint64_t>(cap_rec, c[0] + c[0] / 8 + 16);
-      cap_compact = std::max<uint64_t>(cap_compact, c[6] + c[6] / 8 + 16);
+      cap_compact = std::max<uint64_t>(cap_compact, n_compact_total + n_compact_total / 8 + 16);
       cap_pool = std::max<uint64_t>(cap_pool, kPoolDynOff + c[1] + c[1] / 8 + 16);
       continue;
     }
@@ -686,13 +750,13 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       res.general = (guac_threshold_record*)((unsigned char*)res.block + full_at);
       res.n_general = (size_t)n_rec;
       res.compact = h_compact;
-      res.d_compact = device_sorted ? (const unsigned long long*)ctx->sort_rec.p : (const unsigned long long*)ctx->out_compact.p;
-      res.n_compact = (size_t)c[6];
+      res.d_compact = d_contig;
+      res.n_compact = (size_t)n_compact_total;
       res.n_records = res.n_general + res.n_compact;
       res.bytes = (const uint8_t*)res.block;
       res.n_bytes = pool_bytes;
       res.want_sorted = ctx->sort_records != 0;
-      res.compact_sorted = device_sorted && c[7] == 0;
+      res.compact_sorted = device_sorted && c[7] == 0 && ctx->tiles_in_order;
       res.stats.d2h_bytes = (pool_bytes - kPoolDynOff) + n_rec * sizeof(guac_threshold_record) + res.n_compact * 8 + kStatusBytes;
     }
     res.stats.loci_visited = c[3] + (prm.skip_empty ? 0 : requested - tile_loci);  // loci past the track: empty pileups
@@ -702,7 +766,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     res.stats.tile_kernel_ms = tile_ms;
     res.stats.exact_kernel_ms = exact_ms;
     res.stats.kernel_launches = (uint64_t)launches;
-    res.stats.exact_loci = c[2] + c[8];
+    res.stats.exact_loci = n_slow_total;
     return;
   }
   fail(GUAC_ERR_CUDA, "output buffers did not converge");
@@ -805,8 +869,10 @@ guac_status guac_ctx_create(int device, guac_ctx** out) {
     CUDA_OK(cudaSetDevice(device));
     CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
-    CUDA_OK(cudaEventCreateWithFlags(&ctx->seg_ev, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ctx->join3_ev, cudaEventDisableTiming));
+    for (auto& e : ctx->seg_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (auto& e : ctx->copy_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
@@ -848,8 +914,11 @@ void guac_ctx_destroy(guac_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
-  if (ctx->seg_ev) cudaEventDestroy(ctx->seg_ev);
+  if (ctx->join3_ev) cudaEventDestroy(ctx->join3_ev);
+  for (auto& e : ctx->seg_ev)
+    if (e) cudaEventDestroy(e);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -861,6 +930,7 @@ guac_status guac_ctx_set_option(guac_ctx* ctx, int option, int64_t value) {
     case GUAC_OPT_PACK_QUALITIES: ctx->pack_qualities = value != 0; return GUAC_OK;
     case GUAC_OPT_HOST_THREADS: ctx->host_threads = value > 0 ? (int)value : 0; return GUAC_OK;
     case GUAC_OPT_DIFFERENCE_LISTS: ctx->difference_lists = value != 0; return GUAC_OK;
+    case GUAC_OPT_SEGMENTS: ctx->segments = value < 1 ? 1 : value > 4 ? 4 : (int)value; return GUAC_OK;
   }
   ctx->last_error = "unknown option";
   return GUAC_ERR_INVALID_ARGUMENT;
@@ -972,6 +1042,11 @@ guac_status guac_synth_generate_device(guac_ctx* ctx, const guac_synth_params* p
 }
 const guac_read_batch* guac_synth_device_batch_view(const guac_synth_device_batch* b) { return b ? &b->view : nullptr; }
 double guac_synth_device_batch_ms(const guac_synth_device_batch* b) { return b ? b->kernel_ms : 0.0; }
+void guac_synth_device_batch_totals(const guac_synth_device_batch* b, uint64_t* n_cigar_ops, uint64_t* n_md_bytes, uint64_t* n_bases) {
+  if (n_cigar_ops) *n_cigar_ops = b ? b->n_ops : 0;
+  if (n_md_bytes) *n_md_bytes = b ? b->n_md : 0;
+  if (n_bases) *n_bases = b ? b->n_bases : 0;
+}
 void guac_synth_device_batch_free(guac_synth_device_batch* b) {
   if (!b) return;
   if (b->ctx) cudaSetDevice(b->ctx->device);
@@ -1081,7 +1156,8 @@ static void run_allele_counts(guac_ctx* ctx, const guac_reads& reads, const guac
     out.cap_pool = (uint32_t)cap_pool;
     out.slow = nullptr;
     out.cap_slow = 0;
-    out.slow_ctr = 2;
+    out.slow_ctr = 8;
+    out.compact_ctr = 12;
     out.compact = nullptr;
     out.cap_compact = 0;
     out.counters = ctx->d_counters;

@@ -185,7 +185,8 @@ struct guac_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;       // the exact per-locus kernel of a germline call, next to the record egress on `stream`
-  cudaEvent_t join_ev = nullptr, seg_ev = nullptr;
+  cudaStream_t stream3 = nullptr;       // ... and the ordering + egress of the compact records
+  cudaEvent_t join_ev = nullptr, join3_ev = nullptr, seg_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;   // guac_reads_pack: host -> device copies, overlapped with the pack kernels
   cudaEvent_t copy_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::string last_error;
@@ -199,14 +200,16 @@ struct guac_ctx {
   int pack_qualities = 1;
   int host_threads = 0;
   int difference_lists = 1;
+  int segments = 1;
   bool smem_attrs_done = false, expand_attrs_done = false;
   // scratch kept across calls so that a repeated call neither allocates nor rebuilds its tile list
   DevBuf<unsigned char> out_rec, out_pool, out_slow, out_compact, tiles, sort_rec;
   DevBuf<uint32_t> sort_bins;
+  DevBuf<uint64_t> scan_totals;
   std::vector<guac_locus_range> tiles_key_ranges;
   const void* tiles_key_reads = nullptr;
   uint64_t tiles_key_loci = 0, n_tiles = 0;
-  bool pool_head_ready = false;
+  bool pool_head_ready = false, tiles_in_order = true;
   // pinned host staging for result downloads (grow-only)
   unsigned char* h_stage = nullptr;
   size_t h_stage_bytes = 0;

@@ -43,9 +43,15 @@ struct DevOut {
   uint32_t cap_pool;
   SlowLocus* slow;
   uint32_t cap_slow;
-  uint32_t slow_ctr;             // which counter numbers the deferred loci of this launch: 2, or 8 for the second half of a call
-  // counters: [0] general records, [1] pool bytes, [2] slow loci, [3] visited loci, [4] tie loci, [5] counter overflow,
-  // [6] compact records, [7] a granule held too many records for the device-side ordering (the host finishes the sort)
+  uint32_t slow_ctr;             // counters of this launch's segment of the call: deferred loci (8 + segment) ...
+  uint32_t compact_ctr;          // ... and compact records (12 + segment)
+  uint32_t* tile_base;           // per tile of the call: where its (sorted) compact records start in the segment's buffer ...
+  uint32_t* tile_n;              // ... and how many there are: the egress kernels put the tiles' records in tile order
+  uint32_t tile0;                // index of this launch's first tile in those arrays
+  // counters: [0] general records, [1] pool bytes, [3] visited loci, [4] tie loci, [5] counter overflow, [7] a granule held
+  // too many records for the device-side ordering (the host finishes the sort); per segment of a call (a call over many
+  // tiles runs in up to four segments so that the exact kernel and the record egress of one overlap the tile kernel of the
+  // next): [8 + s] deferred loci, [12 + s] compact records
   unsigned long long* counters;
   DevError* err;
 };
@@ -108,20 +114,37 @@ __device__ __forceinline__ void emit_compact(DevOut& out, unsigned long long rec
       return;
     }
   }
-  const uint32_t s = (uint32_t)atomicAdd(&out.counters[6], 1ull);
+  const uint32_t s = (uint32_t)atomicAdd(&out.counters[out.compact_ctr], 1ull);
   if (s < out.cap_compact) out.compact[s] = rec;
 }
 
-// end of a granule (whole warp): the staged records and deferred loci leave with one global atomic each
-__device__ __forceinline__ void flush_stage(DevOut& out, EmitStage* stage) {
+// end of a granule (whole warp): the staged records and deferred loci leave with one global atomic each.  The records of
+// the tile are put in canonical order on the way (a compact record's value orders like (contig, start, ref, alt); a tile
+// holds a handful: every lane counts the records below its own) and the tile's slice is noted for the egress kernels, which
+// lay the tiles' slices out in tile order: no sort of the whole output.
+__device__ __forceinline__ void flush_stage(DevOut& out, EmitStage* stage, uint32_t tile) {
   __syncwarp();
   const int lane = threadIdx.x & 31;
-  const uint32_t nr = min(stage->n_rec, (uint32_t)kStageRecords), ns = min(stage->n_slow, (uint32_t)kStageSlow);
+  const uint32_t n_all = stage->n_rec;
+  const uint32_t nr = min(n_all, (uint32_t)kStageRecords), ns = min(stage->n_slow, (uint32_t)kStageSlow);
+  if (n_all > (uint32_t)kStageRecords && lane == 0) out.counters[7] = 1ull;  // the surplus left unordered: the host finishes
   if (nr) {
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&out.counters[6], (unsigned long long)nr);
+    if (lane == 0) base = atomicAdd(&out.counters[out.compact_ctr], (unsigned long long)nr);
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if ((uint32_t)lane < nr && base + lane < out.cap_compact) out.compact[base + lane] = stage->rec[lane];
+    if ((uint32_t)lane < nr) {
+      const unsigned long long v = stage->rec[lane];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < nr; ++j) {
+        const unsigned long long w = stage->rec[j];
+        rank += (w < v || (w == v && j < (uint32_t)lane)) ? 1u : 0u;
+      }
+      if (base + rank < out.cap_compact) out.compact[base + rank] = v;
+    }
+    if (lane == 0 && out.tile_n) {
+      out.tile_base[out.tile0 + tile] = (uint32_t)base;
+      out.tile_n[out.tile0 + tile] = nr;
+    }
   }
   if (ns) {
     unsigned long long base = 0;
@@ -1064,95 +1087,51 @@ __global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, con
   }
 }
 
-// ---- canonical record order on the device (compact germline records) ---------------------------------------------------------
-// Records leave the tile kernel in atomic-counter order.  A compact record's numeric value orders like (contig, start, ref,
-// alt), so the canonical order is restored with a counting sort over granules — a record's granule is a monotone function of
-// (contig, start) — followed by a small insertion sort inside every granule (a granule holds a handful of sparse records),
-// and the sorted records are streamed to the pinned host block with coalesced stores.
-__device__ __forceinline__ uint32_t record_bin(const DevReads& R, unsigned long long r) {
-  return R.contigs[(uint32_t)(r >> 48)].gran_off + (uint32_t)(((uint32_t)(r >> 16)) >> kGranuleShift);
-}
-
-__global__ void __launch_bounds__(256) k_rec_hist(DevReads R, const unsigned long long* __restrict__ rec, const unsigned long long* counters,
-                                                  uint32_t cap_rec, uint32_t* __restrict__ hist) {
-  const uint32_t n = (uint32_t)min(counters[6], (unsigned long long)cap_rec);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&hist[record_bin(R, rec[i])], 1u);
-}
-
-// exclusive scan of hist[0 .. n_bins] in place (one CTA), cursor = copy of the result
-__global__ void __launch_bounds__(1024) k_rec_scan(uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, uint32_t n_bins) {
-  __shared__ uint32_t warp_sum[32];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t base = 0; base <= n_bins; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i <= n_bins ? hist[i] : 0u;
-    uint32_t incl = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_sum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      const uint32_t w = warp_sum[lane];
-      uint32_t wi = w;
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-        if (lane >= o) wi += t;
-      }
-      warp_sum[lane] = wi - w;  // exclusive
-    }
-    __syncthreads();
-    const uint32_t excl = carry + warp_sum[warp] + incl - v;
-    if (i <= n_bins) { hist[i] = excl; cursor[i] = excl; }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + v;
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(256) k_rec_scatter(DevReads R, const unsigned long long* __restrict__ rec, const unsigned long long* counters,
-                                                     uint32_t cap_rec, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ grouped) {
-  const uint32_t n = (uint32_t)min(counters[6], (unsigned long long)cap_rec);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const unsigned long long r = rec[i];
-    grouped[atomicAdd(&cursor[record_bin(R, r)], 1u)] = r;
-  }
-}
-
-// thread per granule: insertion sort of its records (starts[] = the scanned histogram).  Granules holding more records than
-// an insertion sort should see (dense outputs: emit-ref) are left to the host, which is told through counters[7].
-constexpr uint32_t kRecFinishMax = 96;
-__global__ void __launch_bounds__(256) k_rec_finish(const uint32_t* __restrict__ starts, uint32_t n_bins, unsigned long long* __restrict__ grouped,
-                                                    unsigned long long* counters) {
-  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_bins; g += gridDim.x * blockDim.x) {
-    const uint32_t lo = starts[g], hi = starts[g + 1];
-    if (hi - lo > kRecFinishMax) {
-      counters[7] = 1ull;
-      continue;
-    }
-    for (uint32_t i = lo + 1; i < hi; ++i) {
-      const unsigned long long x = grouped[i];
-      uint32_t j = i;
-      while (j > lo && x < grouped[j - 1]) {
-        grouped[j] = grouped[j - 1];
-        --j;
-      }
-      grouped[j] = x;
+// ---- record egress: the tiles' sorted slices laid out in tile order (compact germline records) ------------------------------
+// tile_n[] is scanned per segment (k_scan_* of guac_synth_device.cuh); thread per tile: its records go behind those of the
+// earlier tiles and segments (whose counts are final: the tile kernels of a call run in order), to the pinned host block of
+// the result and to the contiguous device copy the NCCL gather sends from.
+__global__ void __launch_bounds__(256) k_rec_gather(const unsigned long long* __restrict__ rec, const uint32_t* __restrict__ tile_base,
+                                                    const uint32_t* __restrict__ tile_n, const uint32_t* __restrict__ prefix, uint32_t n_tiles,
+                                                    const unsigned long long* counters, uint32_t seg, uint32_t cap_seg,
+                                                    unsigned long long* __restrict__ dev_rec, unsigned long long cap_total) {
+  unsigned long long seg_base = 0;
+  for (uint32_t j = 0; j < seg; ++j) seg_base += min(counters[12 + j], (unsigned long long)cap_seg);
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
+    const uint32_t n = tile_n[t];
+    if (!n) continue;
+    const unsigned long long dst = seg_base + prefix[t];
+    const uint32_t src = tile_base[t];
+    for (uint32_t i = 0; i < n; ++i) {
+      if (dst + i >= cap_total || src + i >= cap_seg) break;
+      dev_rec[dst + i] = rec[src + i];
     }
   }
 }
 
-// coalesced copy of the compact records to the pinned host block (16 bytes = two records per store)
-__global__ void __launch_bounds__(256) k_rec_flush(const unsigned long long* __restrict__ rec, const unsigned long long* counters, uint32_t cap_rec,
-                                                   unsigned long long* __restrict__ host_rec) {
-  const unsigned long long n16 = (min(counters[6], (unsigned long long)cap_rec) + 1) / 2;
-  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(rec);
-  uint4* dst = reinterpret_cast<uint4*>(host_rec);
-  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * blockDim.x) dst[i] = src[i];
+// coalesced copy of one segment's ordered records from the contiguous device copy to the pinned host block
+__global__ void __launch_bounds__(256) k_rec_to_host(const unsigned long long* __restrict__ dev_rec, const unsigned long long* counters, uint32_t seg,
+                                                     uint32_t cap_seg, unsigned long long* __restrict__ host_rec, unsigned long long cap_total) {
+  unsigned long long base = 0;
+  for (uint32_t j = 0; j < seg; ++j) base += min(counters[12 + j], (unsigned long long)cap_seg);
+  const unsigned long long n = min(counters[12 + seg], (unsigned long long)cap_seg);
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n && base + i < cap_total; i += (unsigned long long)gridDim.x * blockDim.x)
+    host_rec[base + i] = dev_rec[base + i];
+}
+
+// plain copy of one segment's records (no ordering asked for, or a kernel that does not note its tiles' slices)
+__global__ void __launch_bounds__(256) k_rec_flush(const unsigned long long* __restrict__ rec, const unsigned long long* counters, uint32_t seg,
+                                                   uint32_t cap_seg, unsigned long long* __restrict__ host_rec, unsigned long long* __restrict__ dev_rec,
+                                                   unsigned long long cap_total) {
+  unsigned long long base = 0;
+  for (uint32_t j = 0; j < seg; ++j) base += min(counters[12 + j], (unsigned long long)cap_seg);
+  const unsigned long long n = min(counters[12 + seg], (unsigned long long)cap_seg);
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    if (base + i >= cap_total) break;
+    const unsigned long long v = rec[i];
+    host_rec[base + i] = v;
+    dev_rec[base + i] = v;
+  }
 }
 
 // per-allele counts: one warp per requested locus of the ranges (prefix[i] = loci before range i)

@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_call_tile(DevReads R, const
       tile_call_locus<WIDE, MODE>(S.cnt, R, td, prm, out, (lane << 5) + kk, d, 0, every_covered, all_loci, &S.stage);
     }
   }
-  flush_stage(out, &S.stage);
+  flush_stage(out, &S.stage, tile);
   // one atomic per warp for the visited-loci counter
   n_visited = __reduce_add_sync(0xFFFFFFFFu, n_visited);
   if (lane == 0 && n_visited) atomicAdd(&out.counters[3], (unsigned long long)n_visited);

@@ -158,6 +158,9 @@ class DeviceBatch:
         self.sample_name = sample_name
         self.c = lib().guac_synth_device_batch_view(handle).contents
         self.kernel_ms = float(lib().guac_synth_device_batch_ms(handle))
+        ops, md, bases = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib().guac_synth_device_batch_totals(handle, C.byref(ops), C.byref(md), C.byref(bases))
+        self.n_cigar_ops, self.n_md_bytes, self.n_bases = int(ops.value), int(md.value), int(bases.value)
 
     @property
     def n_reads(self):

@@ -265,6 +265,8 @@ const char* guac_status_string(guac_status s);
                                       (every element that differs from the reference track, plus per-locus start / end
                                       counts): the germline kernels then do no per-read work.  0 = the call walks base planes
                                       and CIGARs itself (same results; the cross-check the parity tests run) */
+#define GUAC_OPT_SEGMENTS 5          /* [1] 1..4: a germline call runs in this many segments of tiles, the exact kernel and the
+                                      record egress of one overlapping the tile kernel of the next (same results) */
 guac_status guac_ctx_set_option(guac_ctx* ctx, int option, int64_t value);
 
 /* Device-side stopwatch on the context's stream (CUDA events): start, run any number of calls, stop -> elapsed ms. */

@@ -47,6 +47,8 @@ typedef struct guac_synth_device_batch guac_synth_device_batch;
 guac_status guac_synth_generate_device(guac_ctx* ctx, const guac_synth_params* p, guac_synth_device_batch** out);
 const guac_read_batch* guac_synth_device_batch_view(const guac_synth_device_batch* b);
 double guac_synth_device_batch_ms(const guac_synth_device_batch* b);   /* device time of the generator kernels */
+/* totals of the variable-length columns (the last offsets, which live on the device) */
+void guac_synth_device_batch_totals(const guac_synth_device_batch* b, uint64_t* n_cigar_ops, uint64_t* n_md_bytes, uint64_t* n_bases);
 /* guac_reads_pack_device that takes the batch's large columns over instead of copying them (the whole-genome shards would not
  * fit twice); afterwards the batch can only be freed. */
 guac_status guac_reads_pack_synth(guac_ctx* ctx, guac_synth_device_batch* b, const guac_reference* ref, guac_reads** out);
