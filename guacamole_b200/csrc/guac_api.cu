@@ -100,6 +100,54 @@ void settle_streams(guac_ctx* ctx, guac_reads& rd, uint64_t entries, bool field_
   fail(GUAC_ERR_CUDA, "difference streams did not converge");
 }
 
+// ---- per-word rows of the likelihood callers (k_expand_rows, guac_rows.cuh) -----------------------------------------------------
+void launch_rows(guac_ctx* ctx, guac_reads& rd, uint64_t cap_groups, bool allocated) {
+  cudaStream_t st = ctx->stream;
+  if (!allocated) {
+    if (cap_groups >= 0xFFFFFFF0ull) fail(GUAC_ERR_UNSUPPORTED, "row store beyond 2^32 groups: shard the read set");
+    rd.q_hdr.alloc(rd.total_words + 1);
+    rd.q_groups.alloc(cap_groups + 1);
+    rd.q_rows.alloc((cap_groups + 1) * 32);
+    rd.q_cap_groups = cap_groups;
+  }
+  CUDA_OK(cudaMemsetAsync(ctx->d_counters + 4, 0, sizeof(unsigned long long), st));
+  if (!rd.total_words) return;
+  RowsArgs A;
+  A.R = rd.view();
+  A.hdr_w = rd.q_hdr.p;
+  A.groups_w = rd.q_groups.p;
+  A.rows_w = rd.q_rows.p;
+  A.cap_groups = rd.q_cap_groups;
+  A.w_begin = 0;
+  A.w_end = (uint32_t)rd.total_words;
+  A.n_contigs = rd.n_contigs;
+  A.pad_ = 0;
+  A.counters = ctx->d_counters;
+  CUDA_OK(cudaEventRecord(ctx->ev_rows[0], st));
+  k_expand_rows<<<(unsigned)((rd.total_words + kRowsWarps - 1) / kRowsWarps), kRowsWarps * 32, 0, st>>>(A);
+  CUDA_OK(cudaEventRecord(ctx->ev_rows[1], st));
+  CUDA_OK(cudaGetLastError());
+}
+
+void settle_rows(guac_ctx* ctx, guac_reads& rd, uint64_t groups) {
+  cudaStream_t st = ctx->stream;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    if (groups <= rd.q_cap_groups) {
+      float ms = 0;
+      CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev_rows[0], ctx->ev_rows[1]));
+      rd.rows_ms = ms;
+      return;
+    }
+    launch_rows(ctx, rd, groups + groups / 16 + 64, false);
+    rd.pack_launches += 1;
+    unsigned long long c = 0;
+    CUDA_OK(cudaMemcpyAsync(&c, ctx->d_counters + 4, sizeof c, cudaMemcpyDeviceToHost, st));
+    check_device_error(ctx, "guac_reads_pack (rows)");
+    groups = c;
+  }
+  fail(GUAC_ERR_CUDA, "row store did not converge");
+}
+
 // `on_device`: the batch's column pointers are device memory of ctx's device (guac_reads_pack_device): no host -> device copies.
 // `adopt`: a generated device batch whose large columns (bases, qualities, CIGARs, MD tags, base offsets) the store takes
 // over instead of copying them (guac_reads_pack_synth): the whole-genome shards would not fit twice.
@@ -230,11 +278,11 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   DevBuf<uint32_t> d_read_contig, d_n_pairs, d_pair_off, conflict, gran_count;
   DevBuf<unsigned long long> d_summary;  // [0..2] summary, then contig_first / contig_last / contig_end
   const size_t nc = b->n_contigs;
-  d_summary.alloc(4 + 3 * nc);
+  d_summary.alloc(8 + 3 * nc);
   {
-    std::vector<unsigned long long> init(4 + 3 * nc, 0ull);
+    std::vector<unsigned long long> init(8 + 3 * nc, 0ull);
     init[0] = ~0ull;
-    for (size_t c = 0; c < nc; ++c) init[4 + c] = ~0ull;
+    for (size_t c = 0; c < nc; ++c) init[8 + c] = ~0ull;
     CUDA_OK(cudaMemcpyAsync(d_summary.p, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaStreamSynchronize(st));  // (init goes out of scope)
   }
@@ -250,9 +298,10 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   H.read_contig = d_read_contig.p;
   H.n_pairs = d_n_pairs.p;
   H.summary = d_summary.p;
-  H.contig_first = d_summary.p + 4;
-  H.contig_last = d_summary.p + 4 + nc;
-  H.contig_end = reinterpret_cast<long long*>(d_summary.p + 4 + 2 * nc);
+  H.mapq_mask = reinterpret_cast<uint32_t*>(d_summary.p + 4);
+  H.contig_first = d_summary.p + 8;
+  H.contig_last = d_summary.p + 8 + nc;
+  H.contig_end = reinterpret_cast<long long*>(d_summary.p + 8 + 2 * nc);
   CUDA_OK(cudaStreamWaitEvent(st, ctx->copy_ev[4], 0));
   CUDA_OK(cudaEventRecord(ctx->ev[0], st));
   uint64_t pair_total = 0;
@@ -271,7 +320,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     CUDA_OK(cudaMemsetAsync(out.cig_off.p, 0, 4, st));
     CUDA_OK(cudaMemsetAsync(out.md_off.p, 0, 4, st));
   }
-  std::vector<unsigned long long> summary(4 + 3 * nc);
+  std::vector<unsigned long long> summary(8 + 3 * nc);
   CUDA_OK(cudaMemcpyAsync(summary.data(), d_summary.p, summary.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   if (n && summary[0] != ~0ull) {
@@ -286,13 +335,14 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     fail(code, "read %llu: %s", read, why);
   }
   out.max_ref_span = (int64_t)summary[1];
+  memcpy(out.mapq_mask, &summary[4], sizeof out.mapq_mask);
   out.sample = n ? (int32_t)(uint32_t)summary[2] : 0;
   std::vector<int64_t> contig_end(nc, 0);
   std::vector<uint64_t> contig_first(nc, ~0ull), contig_last(nc, 0);
   for (size_t c = 0; c < nc; ++c) {
-    contig_first[c] = summary[4 + c];
-    contig_last[c] = summary[4 + nc + c];
-    contig_end[c] = (int64_t)summary[4 + 2 * nc + c];
+    contig_first[c] = summary[8 + c];
+    contig_last[c] = summary[8 + nc + c];
+    contig_end[c] = (int64_t)summary[8 + 2 * nc + c];
   }
   nvtx_pop();
   nvtx_push("guac pack: kernels");
@@ -338,6 +388,15 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   if (n && ctx->difference_lists) {
     out.gs_wide = false;
     alloc_streams(out, (uint64_t)n * 3 + gran_off * 8 + 4096);
+  }
+  const bool want_rows = n && ctx->difference_lists && out.has_qualities;
+  if (want_rows) {
+    const uint64_t cap_groups = (pair_total + 2 * n) / 4 + word_off + 1024;
+    if (cap_groups >= 0xFFFFFFF0ull) fail(GUAC_ERR_UNSUPPORTED, "row store beyond 2^32 groups: shard the read set");
+    out.q_hdr.alloc(word_off + 1);
+    out.q_groups.alloc(cap_groups + 1);
+    out.q_rows.alloc((cap_groups + 1) * 32);
+    out.q_cap_groups = cap_groups;
   }
   // (everything is allocated: from here to the last pack kernel the device works without waiting for the host)
   CUDA_OK(cudaEventRecord(ctx->ev[0], st));
@@ -417,9 +476,13 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     launch_expand(ctx, out, /*huge=*/false, out.gs_entries, /*allocated=*/true);
     out.pack_launches += 1;
   }
+  if (want_rows) {  // the likelihood callers' rows (the MD walk has located every read's first deletion: classify() uses it)
+    launch_rows(ctx, out, out.q_cap_groups, /*allocated=*/true);
+    out.pack_launches += 1;
+  }
   CUDA_OK(cudaEventRecord(ctx->ev[1], st));
   CUDA_OK(cudaGetLastError());
-  unsigned long long counters[4];
+  unsigned long long counters[5];
   CUDA_OK(cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, st));
   check_device_error(ctx, "guac_reads_pack");
   float ms = 0;
@@ -427,7 +490,13 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   out.pack_kernel_ms = ms + header_ms;  // header kernel + scan, then first memset to last pack kernel (waits for copy chunks included)
   out.order_sensitive_loci = counters[0];
   out.max_reads_per_granule = counters[1];
+  float rows_ms = 0;
+  if (want_rows) CUDA_OK(cudaEventElapsedTime(&rows_ms, ctx->ev_rows[0], ctx->ev_rows[1]));
   if (n && ctx->difference_lists) settle_streams(ctx, out, counters[2], counters[3] != 0, /*was_huge=*/false);
+  if (want_rows) {
+    if (counters[4] > out.q_cap_groups) settle_rows(ctx, out, counters[4]);
+    else out.rows_ms = rows_ms;
+  }
   tr.lap("kernels");
   nvtx_pop();
 }
@@ -881,6 +950,7 @@ guac_status guac_ctx_create(int device, guac_ctx** out) {
     CUDA_OK(cudaMemset(ctx->d_counters, 0, kStatusBytes));
     CUDA_OK(cudaMallocHost((void**)&ctx->h_counters, kStatusBytes));
     for (auto& e : ctx->ev) CUDA_OK(cudaEventCreate(&e));
+    for (auto& e : ctx->ev_rows) CUDA_OK(cudaEventCreate(&e));
     somatic_init_tables(ctx);
   });
   if (s != GUAC_OK) {
@@ -901,6 +971,8 @@ void guac_ctx_destroy(guac_ctx* ctx) {
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
   for (auto& e : ctx->ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->ev_rows)
     if (e) cudaEventDestroy(e);
   ctx->out_rec.release();
   ctx->out_pool.release();

@@ -83,6 +83,10 @@ struct DevReads {
   const uint8_t* gs_dp;       // same, positive-strand reads only
   int32_t gs_wide;            // 1: 4 bytes per locus in gs_dd / gs_dp
   int32_t pad2_;
+  // likelihood callers: per 32-locus word (all contigs, ContigInfo.word_off) the reads overlapping it as rows (guac_rows.cuh)
+  const uint2* q_hdr;         // {first group of the word, rows}; nullptr when the store holds no rows
+  const uint4* q_groups;      // per group of 4 rows: their headers (mapq | type << 8 | first lane << 10 | lanes << 15)
+  const uint32_t* q_rows;     // per group and lane: the 4 rows' bytes for the lane's locus
   const uint64_t* seq_off;
   const uint8_t* seq;
   const uint8_t* qual;

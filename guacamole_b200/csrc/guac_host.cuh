@@ -194,6 +194,7 @@ struct guac_ctx {
   DevError* d_err = nullptr;                 // = d_counters + 16
   unsigned long long* h_counters = nullptr;  // pinned mirror of the whole status block
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [4], [5]: user stopwatch
+  cudaEvent_t ev_rows[2] = {nullptr, nullptr};
   int sm_count = 148;
   // options
   int sort_records = 1;
@@ -221,7 +222,7 @@ struct guac_ctx {
   double* d_tables = nullptr;
   uint64_t generation = 0;                   // bumped by every call that reuses the output scratch
   unsigned long long* d_hist = nullptr;      // depth histogram of the last guac_depth_histogram (GUAC_DEPTH_BINS bins)
-  bool hist_attr_done = false;
+  bool hist_attr_done = false, som_attr_done = false, rows_attr_done = false;
 };
 
 namespace {
@@ -395,6 +396,14 @@ struct guac_reads {
   DevBuf<uint8_t> gs_dd, gs_dp;
   bool gs_wide = false;
   uint64_t gs_entries = 0;
+  // per 32-locus word, the overlapping reads as ROWS of (quality | base code << 6) bytes, one byte per locus of the word
+  // (k_expand_rows, guac_rows.cuh): what the likelihood kernels stream.  Empty when packed without qualities / streams.
+  DevBuf<uint2> q_hdr;
+  DevBuf<uint4> q_groups;
+  DevBuf<uint32_t> q_rows;
+  uint64_t q_cap_groups = 0;
+  double rows_ms = 0;
+  uint32_t mapq_mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double expand_ms = 0;
   DevBuf<uint64_t> seq_off, fasta_off;
   DevBuf<uint8_t> seq, qual, qc, fasta;
@@ -428,6 +437,9 @@ struct guac_reads {
     R.gs_dp = gs_dp.p;
     R.gs_wide = gs_wide ? 1 : 0;
     R.pad2_ = 0;
+    R.q_hdr = q_hdr.n ? q_hdr.p : nullptr;
+    R.q_groups = q_groups.p;
+    R.q_rows = q_rows.p;
     R.seq_off = seq_off.p;
     R.seq = seq.p;
     R.qual = qual.p;
@@ -450,7 +462,7 @@ struct guac_reads {
   }
   uint64_t device_bytes() const {
     return rec.bytes() + cig_off.bytes() + cigar.bytes() + xmask.bytes() + md_off.bytes() + trk_lo.bytes() * 3 +
-           gran_first.bytes() * 2 + pairs.bytes() + gs_hdr.bytes() + gs_diffs.bytes() + gs_dd.bytes() + gs_dp.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + qc.bytes() + md.bytes() + nm.bytes() + del_start.bytes() + del_md.bytes() + del_len.bytes() +
+           gran_first.bytes() * 2 + pairs.bytes() + gs_hdr.bytes() + gs_diffs.bytes() + gs_dd.bytes() + gs_dp.bytes() + q_hdr.bytes() + q_groups.bytes() + q_rows.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + qc.bytes() + md.bytes() + nm.bytes() + del_start.bytes() + del_md.bytes() + del_len.bytes() +
            fasta.bytes();
   }
 };

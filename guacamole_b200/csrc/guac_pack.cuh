@@ -61,10 +61,12 @@ struct HeaderArgs {
   unsigned long long* contig_last;  // [n_contigs], 0
   long long* contig_end;            // [n_contigs], 0: largest read end
   unsigned long long* summary;      // [0] first error (~0 = none), [1] longest reference span, [2] sample of read 0
+  uint32_t* mapq_mask;              // [8]: bit m set = some read has mapping quality m (sizes the somatic kernel's table)
 };
 
 __global__ void __launch_bounds__(256) k_header(HeaderArgs H) {
   const int lane = threadIdx.x & 31;
+  uint32_t mask_sent[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // (lane 0: bits of mapq_mask this warp has already set)
   for (uint64_t i0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ull; i0 < H.n; i0 += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t i = i0 + lane;
     int status = 0;
@@ -135,6 +137,17 @@ __global__ void __launch_bounds__(256) k_header(HeaderArgs H) {
         H.n_pairs[i] = 0;
       }
       if (status) atomicMin(&H.summary[0], ((unsigned long long)i << 8) | (unsigned long long)status);
+    }
+    {  // mapping qualities present: one OR per warp and 32-bit word, only for bits the warp has not set before
+      const uint32_t mq = i < H.n ? (uint32_t)H.mapq[i] : 0xFFFFFFFFu;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const uint32_t bits = __reduce_or_sync(0xFFFFFFFFu, (mq >> 5) == (uint32_t)w ? (1u << (mq & 31u)) : 0u);
+        if (lane == 0 && (bits & ~mask_sent[w])) {
+          atomicOr(&H.mapq_mask[w], bits);
+          mask_sent[w] |= bits;
+        }
+      }
     }
     // largest end per contig / longest span: one atomic per warp when its reads share a contig (they are sorted by contig)
     const bool ok = i < H.n && status == 0;

@@ -24,6 +24,7 @@
 
 #include "guac_host.cuh"
 #include "guac_pileup.cuh"
+#include "guac_rows.cuh"
 
 namespace guac {
 
@@ -594,10 +595,149 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
   }
 }
 
+// ---- the same sums from the word's ROWS (guac_rows.cuh): no per-read address arithmetic, the table in shared memory ----------
+// Shared-memory table of one CTA: for every mapping quality present in the tumor sample (and kept by the mapq filter) one row
+// of 64 (log(s + s), log((1-s) + (1-s))) pairs, s = success(quality) * success(mapq) (probabilityCorrectIncludingAlignment,
+// likelihood/Likelihood.scala:58-62); one row for the normal sample (IgnoringAlignment, :48-50).  A row's table row is
+// warp-uniform (its header holds the mapq).  Mapping qualities beyond the table's capacity and the rare general rows
+// (qualities up to 255) read the full table in global memory.
+constexpr int kSomTabRows = 56;
+struct RowTables {
+  uint8_t remap[256];            // mapq -> row of the shared-memory table, 0xFF = not resident
+  uint8_t row_mapq[kSomTabRows];
+  int32_t n_rows;
+  int32_t pad_;
+};
+struct SomSmem {
+  double2 tumor[kSomTabRows * 64];
+  double2 normal[64];
+};
+
+template <bool TUMOR>
+__device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t word, const int rcode, const bool std_ref, const SomParams& prm,
+                                            const SomSmem& T, const RowTables& rt, const double* __restrict__ tables, LaneAcc& A) {
+  const int lane = threadIdx.x & 31;
+  acc_clear(A);
+  const uint2 wh = R.q_hdr[word];
+  const uint32_t n_rows = wh.y;
+  if (n_rows == 0) return;
+  const uint32_t groups = (n_rows + 3u) >> 2;
+  const uint4* __restrict__ gh = R.q_groups + wh.x;
+  const uint32_t* __restrict__ rows = R.q_rows + (size_t)wh.x * 32 + lane;
+  const double2* __restrict__ gtab = reinterpret_cast<const double2*>(tables + (TUMOR ? kTabT : kTabN));
+  double sr1 = 0.0;
+  int n_ref = 0, any = 0;
+  unsigned long long cnt_packed = 0;  // mismatching elements: four 16-bit fields, one per base code
+  const uint32_t rc_eff = std_ref ? (uint32_t)rcode : 4u;
+  const bool fma = prm.filter_multi_allelic != 0;
+  const uint32_t min_mapq = prm.min_mapq > 0 ? (uint32_t)prm.min_mapq : 0u;
+  auto plain = [&](const uint32_t code, const double2 l) {  // one kept A/C/G/T element
+    A.t0 += l.y;
+    if (code == rc_eff) {
+      sr1 += l.x;
+      n_ref += 1;
+    } else {
+      cnt_packed += 1ull << (16 * code);
+      if (code == 0u) { A.s1[0] += l.x; A.s0[0] += l.y; }
+      else if (code == 1u) { A.s1[1] += l.x; A.s0[1] += l.y; }
+      else if (code == 2u) { A.s1[2] += l.x; A.s0[2] += l.y; }
+      else { A.s1[3] += l.x; A.s0[3] += l.y; }
+    }
+  };
+  uint4 hd = __ldg(gh);
+  uint32_t v = __ldg(rows);
+  for (uint32_t g = 0; g < groups; ++g) {
+    const uint4 hd_now = hd;
+    const uint32_t v_now = v;
+    if (g + 1 < groups) {  // the next group is on its way while this one is summed
+      hd = __ldg(gh + g + 1);
+      v = __ldg(rows + (size_t)(g + 1) * 32);
+    }
+    const uint32_t hs[4] = {hd_now.x, hd_now.y, hd_now.z, hd_now.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t h = hs[k];  // (everything read from a header is warp-uniform; a padding row is a lean row of 0 lanes)
+      const uint32_t type = (h >> 8) & 3u, mapq = h & 0xFFu;
+      const uint32_t b = (v_now >> (8 * k)) & 0xFFu;
+      if (type == kRowLean) {
+        const bool covered = (uint32_t)(lane - (int)((h >> 10) & 31u)) < ((h >> 15) & 63u);
+        any |= covered ? 1 : 0;
+        if (mapq >= min_mapq) {
+          const uint32_t r = TUMOR ? (uint32_t)rt.remap[mapq] : 0u;
+          if (!TUMOR || r != 0xFFu) {  // the table row of this read: resident in shared memory
+            const double2* __restrict__ trow = TUMOR ? &T.tumor[r * 64u] : &T.normal[0];
+            if (covered) plain(b >> 6, trow[b & 63u]);
+          } else if (covered) {
+            plain(b >> 6, __ldg(&gtab[(mapq << 8) + (b & 63u)]));
+          }
+        } else if (fma && covered) {
+          A.seen |= 1u << (b >> 6);
+        }
+      } else if (type == kRowGeneral) {  // (its quality row is the next one of the same group)
+        const uint32_t q = (v_now >> (8 * ((k + 1) & 3))) & 0xFFu;
+        const bool keep = mapq >= min_mapq;
+        if (b != kElemNone) {
+          any = 1;
+          if (keep || fma) {
+            if (b == kElemHard) {
+              A.other += 1;
+              A.hard += 1;
+            } else if (b == kElemOther) {
+              A.other += 1;  // insertion / deletion / clipped / non-ACGT element: which allele it carries is the exact kernel's
+              if (keep) {    // job, but its likelihood terms bound every genotype it can be part of (ref_leads_despite_others)
+                const double2 l = __ldg(&gtab[TUMOR ? (mapq << 8) + q : q]);
+                A.o0 += l.y;
+                A.ohet += fmax(0.0, l.y);
+                A.ohom += fmax(l.x, l.y);
+              }
+            } else {
+              const uint32_t code = b & 3u;
+              A.seen |= 1u << code;
+              if (keep) plain(code, __ldg(&gtab[TUMOR ? (mapq << 8) + q : q]));
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    A.cnt[k] = (int)((cnt_packed >> (16 * k)) & 0xFFFFu) + ((uint32_t)k == rc_eff ? n_ref : 0);
+    A.depth += A.cnt[k];
+  }
+  A.any = any;
+  A.ref_depth = std_ref ? A.cnt[rcode] : 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) A.seen |= A.cnt[k] > 0 ? (1u << k) : 0u;
+  if (n_rows > 0xFFFFu) A.other += 1;  // the packed counters hold 16 bits: deeper pileups go to the exact kernel
+  double sr0 = A.t0;  // S0 of the reference class = T0 - the other classes' S0
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sr0 -= A.s0[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool is = std_ref && k == rcode;
+    A.s1[k] += is ? sr1 : 0.0;
+    A.s0[k] += is ? sr0 : 0.0;
+  }
+}
+
 constexpr int kSomThreads = 256;
 
+// ROWS: the samples' pileup elements come from their row stores (guac_rows.cuh); otherwise every word walks its candidate
+// reads (gather_sample) — the path of stores packed without rows, and the cross-check the parity tests run.
+template <bool ROWS>
 __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads RT, DevReads RN, const TileDesc* __restrict__ tiles, SomParams prm,
-                                                        const double* __restrict__ tables, int max_span_t, int max_span_n, SomOut out) {
+                                                        const double* __restrict__ tables, RowTables rt, SomOut out) {
+  extern __shared__ __align__(16) unsigned char som_smem_raw[];
+  const SomSmem& T = *reinterpret_cast<const SomSmem*>(som_smem_raw);
+  if (ROWS) {  // the CTA's copy of the table rows it will index
+    SomSmem& Tw = *reinterpret_cast<SomSmem*>(som_smem_raw);
+    const double2* gt = reinterpret_cast<const double2*>(tables + kTabT);
+    const double2* gn = reinterpret_cast<const double2*>(tables + kTabN);
+    for (int i = threadIdx.x; i < rt.n_rows * 64; i += kSomThreads) Tw.tumor[i] = gt[((int)rt.row_mapq[i >> 6] << 8) + (i & 63)];
+    for (int i = threadIdx.x; i < 64; i += kSomThreads) Tw.normal[i] = gn[i];
+    __syncthreads();
+  }
   const TileDesc td = tiles[blockIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const ContigInfo ciT = RT.contigs[td.contig], ciN = RN.contigs[td.contig];
@@ -614,7 +754,12 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
     const int rcT = (int)((tl >> lane) & 1u) | ((int)((th >> lane) & 1u) << 1), rcN = (int)((nl >> lane) & 1u) | ((int)((nh >> lane) & 1u) << 1);
     const bool stdT = (ts >> lane) & 1u, stdN = (ns >> lane) & 1u;
     LaneAcc AT, AN;
-    gather_sample<true>(RT, td.contig, span_lo, x, rcT, stdT, prm, tables, AT);
+    if (ROWS) {
+      if (w < ciT.n_words) gather_rows<true>(RT, ciT.word_off + (uint32_t)w, rcT, stdT, prm, T, rt, tables, AT);
+      else acc_clear(AT);
+    } else {
+      gather_sample<true>(RT, td.contig, span_lo, x, rcT, stdT, prm, tables, AT);
+    }
     // The reference looks at the normal sample only where the tumor's most likely genotype holds a variant allele: decide
     // the tumor half per lane first and walk the normal reads of this word only if some lane still needs them.
     const int covT = AT.depth + AT.other;  // (filtered when no multi-allelic filter is on)
@@ -639,7 +784,12 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
     }
     if (in_req && AT.any > 0) ++n_visited;
     if (!__any_sync(0xFFFFFFFFu, need_normal)) continue;
-    gather_sample<false>(RN, td.contig, span_lo, x, rcN, stdN, prm, tables, AN);
+    if (ROWS) {
+      if (w < ciN.n_words) gather_rows<false>(RN, ciN.word_off + (uint32_t)w, rcN, stdN, prm, T, rt, tables, AN);
+      else acc_clear(AN);
+    } else {
+      gather_sample<false>(RN, td.contig, span_lo, x, rcN, stdN, prm, tables, AN);
+    }
     if (!need_normal) continue;
     if (AT.any == 0) {
       if (AN.any > 0 || !prm.skip_empty) ++n_visited;
@@ -1095,7 +1245,28 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
     out.err = ctx->d_err;
     const DevReads RT = tumor.view(), RN = normal.view();
     CUDA_OK(cudaEventRecord(ctx->ev[0], st));
-    k_somatic<<<(int)tiles.size(), kSomThreads, 0, st>>>(RT, RN, d_tiles.p, prm, ctx->d_tables, (int)tumor.max_ref_span, (int)normal.max_ref_span, out);
+    if (tumor.q_hdr.n && normal.q_hdr.n) {
+      RowTables rt;  // table rows for the tumor sample's mapping qualities that pass the filter, high ones (the common ones) first
+      memset(rt.remap, 0xFF, sizeof rt.remap);
+      memset(rt.row_mapq, 0, sizeof rt.row_mapq);
+      rt.n_rows = 0;
+      rt.pad_ = 0;
+      for (int m = 255; m >= 0; --m) {
+        const bool present = (tumor.mapq_mask[m >> 5] >> (m & 31)) & 1u;
+        if (present && m >= std::max(0, p.min_alignment_quality) && rt.n_rows < kSomTabRows) {
+          rt.remap[m] = (uint8_t)rt.n_rows;
+          rt.row_mapq[rt.n_rows++] = (uint8_t)m;
+        }
+      }
+      if (!ctx->som_attr_done) {
+        CUDA_OK(cudaFuncSetAttribute(k_somatic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SomSmem)));
+        ctx->som_attr_done = true;
+      }
+      k_somatic<true><<<(int)tiles.size(), kSomThreads, sizeof(SomSmem), st>>>(RT, RN, d_tiles.p, prm, ctx->d_tables, rt, out);
+    } else {
+      RowTables rt{};
+      k_somatic<false><<<(int)tiles.size(), kSomThreads, 0, st>>>(RT, RN, d_tiles.p, prm, ctx->d_tables, rt, out);
+    }
     CUDA_OK(cudaEventRecord(ctx->ev[1], st));
     k_somatic_exact<<<ctx->sm_count * 32, kSomExactWarps * 32, 0, st>>>(RT, RN, out.slow, prm, ctx->d_tables, out);
     k_evidence<<<ctx->sm_count * 8, kEvidenceWarps * 32, 0, st>>>(RT, RN, prm, out);

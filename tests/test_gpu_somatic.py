@@ -24,6 +24,16 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(scope="module", params=[1, 0], ids=["rows", "read-walk"], autouse=True)
+def row_store(request, ctx):
+    """Every somatic parity test runs twice: over the per-word row stores built at pack time (the default), and with the
+    likelihood kernel walking every word's candidate reads itself (stores packed without rows)."""
+    from guacamole_b200 import abi
+    ctx.set_option(abi.OPT_DIFFERENCE_LISTS, request.param)
+    yield request.param
+    ctx.set_option(abi.OPT_DIFFERENCE_LISTS, 1)
+
+
 def close(a, b):
     if isinstance(a, float) or isinstance(b, float):
         if math.isnan(a) or math.isnan(b):
