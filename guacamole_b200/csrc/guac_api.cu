@@ -123,6 +123,7 @@ void launch_rows(guac_ctx* ctx, guac_reads& rd, uint64_t cap_groups, bool alloca
   A.n_contigs = rd.n_contigs;
   A.pad_ = 0;
   A.counters = ctx->d_counters;
+  memcpy(A.mapq_mask, rd.mapq_mask, sizeof A.mapq_mask);
   CUDA_OK(cudaEventRecord(ctx->ev_rows[0], st));
   k_expand_rows<<<(unsigned)((rd.total_words + kRowsWarps - 1) / kRowsWarps), kRowsWarps * 32, 0, st>>>(A);
   CUDA_OK(cudaEventRecord(ctx->ev_rows[1], st));

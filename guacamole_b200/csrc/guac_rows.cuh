@@ -22,8 +22,10 @@ namespace guac {
 constexpr uint32_t kRowLean = 0u, kRowGeneral = 1u, kRowQuality = 2u;
 constexpr uint32_t kElemNone = 0xFFu, kElemOther = 0xFEu, kElemHard = 0xFDu, kElemPlain = 0xF8u;
 
-__device__ __forceinline__ uint32_t row_header(uint32_t mapq, uint32_t type, int lo, int len) {
-  return mapq | (type << 8) | ((uint32_t)lo << 10) | ((uint32_t)len << 15) | (1u << 21);  // (bit 21: a real row, never 0)
+// row header: mapq 7..0 | type 9..8 | first lane 14..10 | lanes 20..15 | rank of the mapq among those present, from the top, 28..21 (the row
+// of the likelihood kernel's shared-memory table); 0 = padding (a lean row of no lanes)
+__device__ __forceinline__ uint32_t row_header(uint32_t mapq, uint32_t type, int lo, int len, uint32_t rank) {
+  return mapq | (type << 8) | ((uint32_t)lo << 10) | ((uint32_t)len << 15) | (rank << 21);
 }
 
 struct RowsArgs {
@@ -36,6 +38,7 @@ struct RowsArgs {
   uint32_t n_contigs;
   uint32_t pad_;
   unsigned long long* counters;  // [4] groups reserved
+  uint32_t mapq_mask[8];         // mapping qualities present in the read set (k_header): a row's table row is its mapq's rank
 };
 
 constexpr int kRowsWarps = 8;
@@ -116,13 +119,19 @@ __global__ void __launch_bounds__(kRowsWarps * 32) k_expand_rows(RowsArgs A) {
         const int start = __shfl_sync(0xFFFFFFFFu, my.start, j), end = __shfl_sync(0xFFFFFFFFu, my.end, j);
         const uint32_t info = __shfl_sync(0xFFFFFFFFu, my.info, j);
         const uint32_t mapq = info >> kInfoMapqShift;
+        uint32_t rank = 0;  // mapping qualities present ABOVE this one (high ones are the common ones: they get the first rows)
+#pragma unroll
+        for (int wd = 0; wd < 8; ++wd) {
+          const uint32_t m = A.mapq_mask[wd];
+          rank += (uint32_t)wd > (mapq >> 5) ? __popc(m) : ((uint32_t)wd == (mapq >> 5) ? __popc(m & ~((2u << (mapq & 31u)) - 1u)) : 0u);
+        }
         if (lean) {
           const unsigned long long qa = ((unsigned long long)__shfl_sync(0xFFFFFFFFu, (uint32_t)(my_qa >> 32), j) << 32) |
                                         __shfl_sync(0xFFFFFFFFu, (uint32_t)my_qa, j);
           const int lo = max(start, span_lo) - span_lo, hi = min(end, span_lo + 32) - span_lo;
           uint32_t b = 0;
           if (lane >= lo && lane < hi) b = (uint32_t)__ldg(reinterpret_cast<const uint8_t*>((uintptr_t)(qa + (unsigned long long)(long long)x)));
-          append(row_header(mapq, kRowLean, lo, hi - lo), b);
+          append(row_header(mapq, kRowLean, lo, hi - lo, rank), b);
         } else {
           if (row & 1u) append(0u, 0u);
           uint32_t b = kElemNone, q = 0;
@@ -134,8 +143,8 @@ __global__ void __launch_bounds__(kRowsWarps * 32) k_expand_rows(RowsArgs A) {
             else b = kElemOther;
             q = (uint32_t)e.qual & 0xFFu;
           }
-          append(row_header(mapq, kRowGeneral, 0, 32), b);
-          append(row_header(mapq, kRowQuality, 0, 32), q);
+          append(row_header(mapq, kRowGeneral, 0, 32, rank), b);
+          append(row_header(mapq, kRowQuality, 0, 32, rank), q);
         }
       }
     }

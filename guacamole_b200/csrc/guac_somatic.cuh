@@ -601,11 +601,10 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
 // likelihood/Likelihood.scala:58-62); one row for the normal sample (IgnoringAlignment, :48-50).  A row's table row is
 // warp-uniform (its header holds the mapq).  Mapping qualities beyond the table's capacity and the rare general rows
 // (qualities up to 255) read the full table in global memory.
-constexpr int kSomTabRows = 56;
+constexpr int kSomTabRows = 62;
 struct RowTables {
-  uint8_t remap[256];            // mapq -> row of the shared-memory table, 0xFF = not resident
-  uint8_t row_mapq[kSomTabRows];
-  int32_t n_rows;
+  uint8_t row_mapq[kSomTabRows];  // mapping quality of the table's row r = the r-th LARGEST mapq present in the tumor sample
+  int32_t n_rows;                 // rows resident in shared memory (reads whose mapq ranks beyond them use the global table)
   int32_t pad_;
 };
 struct SomSmem {
@@ -613,10 +612,17 @@ struct SomSmem {
   double2 normal[64];
 };
 
+__device__ __forceinline__ double2 lds_double2(uint32_t shared_addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(shared_addr));
+  return v;
+}
+
 template <bool TUMOR>
 __device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t word, const int rcode, const bool std_ref, const SomParams& prm,
-                                            const SomSmem& T, const RowTables& rt, const double* __restrict__ tables, LaneAcc& A) {
-  const int lane = threadIdx.x & 31;
+                                            const uint32_t smem_table /* shared address of SomSmem */, const int n_table_rows,
+                                            const double* __restrict__ tables, LaneAcc& A) {
+  const uint32_t lane = threadIdx.x & 31u;
   acc_clear(A);
   const uint2 wh = R.q_hdr[word];
   const uint32_t n_rows = wh.y;
@@ -625,12 +631,14 @@ __device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t wo
   const uint4* __restrict__ gh = R.q_groups + wh.x;
   const uint32_t* __restrict__ rows = R.q_rows + (size_t)wh.x * 32 + lane;
   const double2* __restrict__ gtab = reinterpret_cast<const double2*>(tables + (TUMOR ? kTabT : kTabN));
+  const uint32_t tab = TUMOR ? smem_table : smem_table + (uint32_t)(kSomTabRows * 64 * sizeof(double2));
   double sr1 = 0.0;
   int n_ref = 0, any = 0;
   unsigned long long cnt_packed = 0;  // mismatching elements: four 16-bit fields, one per base code
   const uint32_t rc_eff = std_ref ? (uint32_t)rcode : 4u;
   const bool fma = prm.filter_multi_allelic != 0;
   const uint32_t min_mapq = prm.min_mapq > 0 ? (uint32_t)prm.min_mapq : 0u;
+  const uint32_t resident = TUMOR ? (uint32_t)n_table_rows : 0xFFFFu;
   auto plain = [&](const uint32_t code, const double2 l) {  // one kept A/C/G/T element
     A.t0 += l.y;
     if (code == rc_eff) {
@@ -642,6 +650,38 @@ __device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t wo
       else if (code == 1u) { A.s1[1] += l.x; A.s0[1] += l.y; }
       else if (code == 2u) { A.s1[2] += l.x; A.s0[2] += l.y; }
       else { A.s1[3] += l.x; A.s0[3] += l.y; }
+    }
+  };
+  // everything but a kept lean row whose table row is resident (rare: general rows, mapq-dropped reads, table overflow)
+  auto slow_row = [&](const uint32_t h, const uint32_t b, const uint32_t q) {
+    const uint32_t type = (h >> 8) & 3u, mapq = h & 0xFFu;
+    const bool keep = mapq >= min_mapq;
+    if (type == kRowLean) {
+      if ((lane - ((h >> 10) & 31u)) < ((h >> 15) & 63u)) {
+        any = 1;
+        if (keep) plain(b >> 6, __ldg(&gtab[TUMOR ? (mapq << 8) + (b & 63u) : (b & 63u)]));
+        else if (fma) A.seen |= 1u << (b >> 6);
+      }
+    } else if (type == kRowGeneral && b != kElemNone) {  // (its quality row is the next one of the same group)
+      any = 1;
+      if (keep || fma) {
+        if (b == kElemHard) {
+          A.other += 1;
+          A.hard += 1;
+        } else if (b == kElemOther) {
+          A.other += 1;  // insertion / deletion / clipped / non-ACGT element: which allele it carries is the exact kernel's
+          if (keep) {    // job, but its likelihood terms bound every genotype it can be part of (ref_leads_despite_others)
+            const double2 l = __ldg(&gtab[TUMOR ? (mapq << 8) + q : q]);
+            A.o0 += l.y;
+            A.ohet += fmax(0.0, l.y);
+            A.ohom += fmax(l.x, l.y);
+          }
+        } else {
+          const uint32_t code = b & 3u;
+          A.seen |= 1u << code;
+          if (keep) plain(code, __ldg(&gtab[TUMOR ? (mapq << 8) + q : q]));
+        }
+      }
     }
   };
   uint4 hd = __ldg(gh);
@@ -656,47 +696,17 @@ __device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t wo
     const uint32_t hs[4] = {hd_now.x, hd_now.y, hd_now.z, hd_now.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const uint32_t h = hs[k];  // (everything read from a header is warp-uniform; a padding row is a lean row of 0 lanes)
-      const uint32_t type = (h >> 8) & 3u, mapq = h & 0xFFu;
+      const uint32_t h = hs[k];  // (everything read from a header is warp-uniform; a padding row is a lean row of no lanes)
       const uint32_t b = (v_now >> (8 * k)) & 0xFFu;
-      if (type == kRowLean) {
-        const bool covered = (uint32_t)(lane - (int)((h >> 10) & 31u)) < ((h >> 15) & 63u);
-        any |= covered ? 1 : 0;
-        if (mapq >= min_mapq) {
-          const uint32_t r = TUMOR ? (uint32_t)rt.remap[mapq] : 0u;
-          if (!TUMOR || r != 0xFFu) {  // the table row of this read: resident in shared memory
-            const double2* __restrict__ trow = TUMOR ? &T.tumor[r * 64u] : &T.normal[0];
-            if (covered) plain(b >> 6, trow[b & 63u]);
-          } else if (covered) {
-            plain(b >> 6, __ldg(&gtab[(mapq << 8) + (b & 63u)]));
-          }
-        } else if (fma && covered) {
-          A.seen |= 1u << (b >> 6);
-        }
-      } else if (type == kRowGeneral) {  // (its quality row is the next one of the same group)
-        const uint32_t q = (v_now >> (8 * ((k + 1) & 3))) & 0xFFu;
-        const bool keep = mapq >= min_mapq;
-        if (b != kElemNone) {
+      const uint32_t rank = h >> 21;
+      if ((h & 0x300u) == 0u && (h & 0xFFu) >= min_mapq && rank < resident) {  // the common row
+        const bool covered = (lane - ((h >> 10) & 31u)) < ((h >> 15) & 63u);
+        if (covered) {
           any = 1;
-          if (keep || fma) {
-            if (b == kElemHard) {
-              A.other += 1;
-              A.hard += 1;
-            } else if (b == kElemOther) {
-              A.other += 1;  // insertion / deletion / clipped / non-ACGT element: which allele it carries is the exact kernel's
-              if (keep) {    // job, but its likelihood terms bound every genotype it can be part of (ref_leads_despite_others)
-                const double2 l = __ldg(&gtab[TUMOR ? (mapq << 8) + q : q]);
-                A.o0 += l.y;
-                A.ohet += fmax(0.0, l.y);
-                A.ohom += fmax(l.x, l.y);
-              }
-            } else {
-              const uint32_t code = b & 3u;
-              A.seen |= 1u << code;
-              if (keep) plain(code, __ldg(&gtab[TUMOR ? (mapq << 8) + q : q]));
-            }
-          }
+          plain(b >> 6, lds_double2(tab + (TUMOR ? rank * 1024u : 0u) + (b & 63u) * 16u));
         }
+      } else {
+        slow_row(h, b, (v_now >> (8 * ((k + 1) & 3))) & 0xFFu);
       }
     }
   }
@@ -729,7 +739,7 @@ template <bool ROWS>
 __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads RT, DevReads RN, const TileDesc* __restrict__ tiles, SomParams prm,
                                                         const double* __restrict__ tables, RowTables rt, SomOut out) {
   extern __shared__ __align__(16) unsigned char som_smem_raw[];
-  const SomSmem& T = *reinterpret_cast<const SomSmem*>(som_smem_raw);
+  const uint32_t smem_table = (uint32_t)__cvta_generic_to_shared(som_smem_raw);
   if (ROWS) {  // the CTA's copy of the table rows it will index
     SomSmem& Tw = *reinterpret_cast<SomSmem*>(som_smem_raw);
     const double2* gt = reinterpret_cast<const double2*>(tables + kTabT);
@@ -755,7 +765,7 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
     const bool stdT = (ts >> lane) & 1u, stdN = (ns >> lane) & 1u;
     LaneAcc AT, AN;
     if (ROWS) {
-      if (w < ciT.n_words) gather_rows<true>(RT, ciT.word_off + (uint32_t)w, rcT, stdT, prm, T, rt, tables, AT);
+      if (w < ciT.n_words) gather_rows<true>(RT, ciT.word_off + (uint32_t)w, rcT, stdT, prm, smem_table, rt.n_rows, tables, AT);
       else acc_clear(AT);
     } else {
       gather_sample<true>(RT, td.contig, span_lo, x, rcT, stdT, prm, tables, AT);
@@ -785,7 +795,7 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
     if (in_req && AT.any > 0) ++n_visited;
     if (!__any_sync(0xFFFFFFFFu, need_normal)) continue;
     if (ROWS) {
-      if (w < ciN.n_words) gather_rows<false>(RN, ciN.word_off + (uint32_t)w, rcN, stdN, prm, T, rt, tables, AN);
+      if (w < ciN.n_words) gather_rows<false>(RN, ciN.word_off + (uint32_t)w, rcN, stdN, prm, smem_table, rt.n_rows, tables, AN);
       else acc_clear(AN);
     } else {
       gather_sample<false>(RN, td.contig, span_lo, x, rcN, stdN, prm, tables, AN);
@@ -1246,18 +1256,12 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
     const DevReads RT = tumor.view(), RN = normal.view();
     CUDA_OK(cudaEventRecord(ctx->ev[0], st));
     if (tumor.q_hdr.n && normal.q_hdr.n) {
-      RowTables rt;  // table rows for the tumor sample's mapping qualities that pass the filter, high ones (the common ones) first
-      memset(rt.remap, 0xFF, sizeof rt.remap);
+      RowTables rt;  // the table's row r belongs to the r-th largest mapping quality present in the tumor sample
       memset(rt.row_mapq, 0, sizeof rt.row_mapq);
       rt.n_rows = 0;
       rt.pad_ = 0;
-      for (int m = 255; m >= 0; --m) {
-        const bool present = (tumor.mapq_mask[m >> 5] >> (m & 31)) & 1u;
-        if (present && m >= std::max(0, p.min_alignment_quality) && rt.n_rows < kSomTabRows) {
-          rt.remap[m] = (uint8_t)rt.n_rows;
-          rt.row_mapq[rt.n_rows++] = (uint8_t)m;
-        }
-      }
+      for (int m = 255; m >= 0 && rt.n_rows < kSomTabRows; --m)
+        if ((tumor.mapq_mask[m >> 5] >> (m & 31)) & 1u) rt.row_mapq[rt.n_rows++] = (uint8_t)m;
       if (!ctx->som_attr_done) {
         CUDA_OK(cudaFuncSetAttribute(k_somatic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SomSmem)));
         ctx->som_attr_done = true;
