@@ -101,22 +101,29 @@ void settle_streams(guac_ctx* ctx, guac_reads& rd, uint64_t entries, bool field_
 }
 
 // ---- per-word rows of the likelihood callers (k_expand_rows, guac_rows.cuh) -----------------------------------------------------
-void launch_rows(guac_ctx* ctx, guac_reads& rd, uint64_t cap_groups, bool allocated) {
+void alloc_rows(guac_reads& rd, uint64_t cap_pairs, uint64_t cap_groups) {
+  if (cap_pairs >= 0xFFFFFFF0ull || cap_groups >= 0xFFFFFFF0ull) fail(GUAC_ERR_UNSUPPORTED, "row store beyond 2^32 entries: shard the read set");
+  rd.q_hdr.alloc(rd.total_words + 1);
+  rd.q_depth.alloc(rd.total_words * 32 + 32);
+  rd.q_cols.alloc((cap_pairs + 1) * 32 * 4);  // (blocks of eight columns: 16 bytes per locus)
+  rd.q_groups.alloc(cap_groups + 1);
+  rd.q_rows.alloc((cap_groups + 1) * 32);
+  rd.q_cap_pairs = cap_pairs;
+  rd.q_cap_groups = cap_groups;
+}
+
+void launch_rows(guac_ctx* ctx, guac_reads& rd) {
   cudaStream_t st = ctx->stream;
-  if (!allocated) {
-    if (cap_groups >= 0xFFFFFFF0ull) fail(GUAC_ERR_UNSUPPORTED, "row store beyond 2^32 groups: shard the read set");
-    rd.q_hdr.alloc(rd.total_words + 1);
-    rd.q_groups.alloc(cap_groups + 1);
-    rd.q_rows.alloc((cap_groups + 1) * 32);
-    rd.q_cap_groups = cap_groups;
-  }
-  CUDA_OK(cudaMemsetAsync(ctx->d_counters + 4, 0, sizeof(unsigned long long), st));
+  CUDA_OK(cudaMemsetAsync(ctx->d_counters + 4, 0, 2 * sizeof(unsigned long long), st));
   if (!rd.total_words) return;
   RowsArgs A;
   A.R = rd.view();
   A.hdr_w = rd.q_hdr.p;
+  A.depth_w = rd.q_depth.p;
+  A.cols_w = rd.q_cols.p;
   A.groups_w = rd.q_groups.p;
   A.rows_w = rd.q_rows.p;
+  A.cap_pairs = rd.q_cap_pairs;
   A.cap_groups = rd.q_cap_groups;
   A.w_begin = 0;
   A.w_end = (uint32_t)rd.total_words;
@@ -130,21 +137,23 @@ void launch_rows(guac_ctx* ctx, guac_reads& rd, uint64_t cap_groups, bool alloca
   CUDA_OK(cudaGetLastError());
 }
 
-void settle_rows(guac_ctx* ctx, guac_reads& rd, uint64_t groups) {
+void settle_rows(guac_ctx* ctx, guac_reads& rd, uint64_t pairs, uint64_t groups) {
   cudaStream_t st = ctx->stream;
   for (int attempt = 0; attempt < 4; ++attempt) {
-    if (groups <= rd.q_cap_groups) {
+    if (pairs <= rd.q_cap_pairs && groups <= rd.q_cap_groups) {
       float ms = 0;
       CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev_rows[0], ctx->ev_rows[1]));
       rd.rows_ms = ms;
       return;
     }
-    launch_rows(ctx, rd, groups + groups / 16 + 64, false);
+    alloc_rows(rd, std::max<uint64_t>(rd.q_cap_pairs, pairs + pairs / 16 + 64), std::max<uint64_t>(rd.q_cap_groups, groups + groups / 16 + 64));
+    launch_rows(ctx, rd);
     rd.pack_launches += 1;
-    unsigned long long c = 0;
-    CUDA_OK(cudaMemcpyAsync(&c, ctx->d_counters + 4, sizeof c, cudaMemcpyDeviceToHost, st));
+    unsigned long long c[2] = {0, 0};
+    CUDA_OK(cudaMemcpyAsync(c, ctx->d_counters + 4, sizeof c, cudaMemcpyDeviceToHost, st));
     check_device_error(ctx, "guac_reads_pack (rows)");
-    groups = c;
+    pairs = c[0];
+    groups = c[1];
   }
   fail(GUAC_ERR_CUDA, "row store did not converge");
 }
@@ -391,13 +400,9 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     alloc_streams(out, (uint64_t)n * 3 + gran_off * 8 + 4096);
   }
   const bool want_rows = n && ctx->difference_lists && out.has_qualities;
-  if (want_rows) {
-    const uint64_t cap_groups = (pair_total + 2 * n) / 4 + word_off + 1024;
-    if (cap_groups >= 0xFFFFFFF0ull) fail(GUAC_ERR_UNSUPPORTED, "row store beyond 2^32 groups: shard the read set");
-    out.q_hdr.alloc(word_off + 1);
-    out.q_groups.alloc(cap_groups + 1);
-    out.q_rows.alloc((cap_groups + 1) * 32);
-    out.q_cap_groups = cap_groups;
+  if (want_rows) {  // column pairs: ~1.3 slots per base (a word's columns run to its deepest locus); rows: the few general reads
+    out.total_words = word_off;
+    alloc_rows(out, (uint64_t)((double)n_bases * 1.3 / 256.0) + word_off + 1024, n / 4 + 1024);
   }
   // (everything is allocated: from here to the last pack kernel the device works without waiting for the host)
   CUDA_OK(cudaEventRecord(ctx->ev[0], st));
@@ -478,12 +483,12 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     out.pack_launches += 1;
   }
   if (want_rows) {  // the likelihood callers' rows (the MD walk has located every read's first deletion: classify() uses it)
-    launch_rows(ctx, out, out.q_cap_groups, /*allocated=*/true);
+    launch_rows(ctx, out);
     out.pack_launches += 1;
   }
   CUDA_OK(cudaEventRecord(ctx->ev[1], st));
   CUDA_OK(cudaGetLastError());
-  unsigned long long counters[5];
+  unsigned long long counters[6];
   CUDA_OK(cudaMemcpyAsync(counters, ctx->d_counters, sizeof counters, cudaMemcpyDeviceToHost, st));
   check_device_error(ctx, "guac_reads_pack");
   float ms = 0;
@@ -495,7 +500,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   if (want_rows) CUDA_OK(cudaEventElapsedTime(&rows_ms, ctx->ev_rows[0], ctx->ev_rows[1]));
   if (n && ctx->difference_lists) settle_streams(ctx, out, counters[2], counters[3] != 0, /*was_huge=*/false);
   if (want_rows) {
-    if (counters[4] > out.q_cap_groups) settle_rows(ctx, out, counters[4]);
+    if (counters[4] > out.q_cap_pairs || counters[5] > out.q_cap_groups) settle_rows(ctx, out, counters[4], counters[5]);
     else out.rows_ms = rows_ms;
   }
   tr.lap("kernels");

@@ -84,9 +84,11 @@ struct DevReads {
   int32_t gs_wide;            // 1: 4 bytes per locus in gs_dd / gs_dp
   int32_t pad2_;
   // likelihood callers: per 32-locus word (all contigs, ContigInfo.word_off) the reads overlapping it as rows (guac_rows.cuh)
-  const uint2* q_hdr;         // {first group of the word, rows}; nullptr when the store holds no rows
-  const uint4* q_groups;      // per group of 4 rows: their headers (mapq | type << 8 | first lane << 10 | lanes << 15)
-  const uint32_t* q_rows;     // per group and lane: the 4 rows' bytes for the lane's locus
+  const uint4* q_hdr;         // {first column pair, columns, first row group, rows | highest rank << 24}; nullptr: no such store
+  const uint16_t* q_depth;    // per locus: plain elements (all mapping qualities)
+  const uint32_t* q_cols;     // per (block of 8 columns, lane): eight 16-bit elements (quality | class << 6 | mapq rank << 8)
+  const uint4* q_groups;      // general rows, per group of 4: their headers (mapq | type << 8)
+  const uint32_t* q_rows;     // ... and per group and lane: the 4 rows' bytes for the lane's locus
   const uint64_t* seq_off;
   const uint8_t* seq;
   const uint8_t* qual;

@@ -398,10 +398,10 @@ struct guac_reads {
   uint64_t gs_entries = 0;
   // per 32-locus word, the overlapping reads as ROWS of (quality | base code << 6) bytes, one byte per locus of the word
   // (k_expand_rows, guac_rows.cuh): what the likelihood kernels stream.  Empty when packed without qualities / streams.
-  DevBuf<uint2> q_hdr;
-  DevBuf<uint4> q_groups;
-  DevBuf<uint32_t> q_rows;
-  uint64_t q_cap_groups = 0;
+  DevBuf<uint4> q_hdr, q_groups;
+  DevBuf<uint16_t> q_depth;
+  DevBuf<uint32_t> q_cols, q_rows;
+  uint64_t q_cap_pairs = 0, q_cap_groups = 0;
   double rows_ms = 0;
   uint32_t mapq_mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double expand_ms = 0;
@@ -438,6 +438,8 @@ struct guac_reads {
     R.gs_wide = gs_wide ? 1 : 0;
     R.pad2_ = 0;
     R.q_hdr = q_hdr.n ? q_hdr.p : nullptr;
+    R.q_depth = q_depth.p;
+    R.q_cols = q_cols.p;
     R.q_groups = q_groups.p;
     R.q_rows = q_rows.p;
     R.seq_off = seq_off.p;
@@ -462,7 +464,7 @@ struct guac_reads {
   }
   uint64_t device_bytes() const {
     return rec.bytes() + cig_off.bytes() + cigar.bytes() + xmask.bytes() + md_off.bytes() + trk_lo.bytes() * 3 +
-           gran_first.bytes() * 2 + pairs.bytes() + gs_hdr.bytes() + gs_diffs.bytes() + gs_dd.bytes() + gs_dp.bytes() + q_hdr.bytes() + q_groups.bytes() + q_rows.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + qc.bytes() + md.bytes() + nm.bytes() + del_start.bytes() + del_md.bytes() + del_len.bytes() +
+           gran_first.bytes() * 2 + pairs.bytes() + gs_hdr.bytes() + gs_diffs.bytes() + gs_dd.bytes() + gs_dp.bytes() + q_hdr.bytes() + q_depth.bytes() + q_cols.bytes() + q_groups.bytes() + q_rows.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + qc.bytes() + md.bytes() + nm.bytes() + del_start.bytes() + del_md.bytes() + del_len.bytes() +
            fasta.bytes();
   }
 };

@@ -1,18 +1,21 @@
-// guac_rows.cuh — the likelihood callers' view of a read set: per 32-locus word, the overlapping reads as ROWS.
+// guac_rows.cuh — the likelihood callers' view of a read set: per 32-locus word, the pileup TRANSPOSED.
 //
 // Likelihood.likelihoodsOfAllPossibleGenotypesFromPileup (likelihood/Likelihood.scala:99-113, 149-201) needs, per locus, every
-// overlapping element's base and quality (and its read's mapping quality): 1 byte per (read, locus).  Walking the reads from
-// the loci (k_somatic's gather_sample) costs ~60 instructions and two dependent loads per (read, word).  K_expand_rows does
-// that walk ONCE, at pack time — the CIGAR expansion of PileupElement.advanceToLocus / alignment
-// (pileup/PileupElement.scala:68-248) — and leaves, per word, one row per overlapping read in read order:
-//   lean rows      (one M/=/X run between clips, A/C/G/T bases, qualities < 64 — 98 % of the reads): 32 bytes, byte l =
-//                  quality | base code << 6 of the read's base at locus l of the word;
-//   general rows   (reads with insertions / deletions / skips / non-ACGT bases / wide qualities), two rows each: the element
-//                  class per locus (0xF8 | base code = plain base, 0xFE = an element that is not a plain base, 0xFD = an
-//                  element the exact kernel must report an error for, 0xFF = no element) and its qualityScore.
-// Rows are stored four to a group: per group one uint4 of row headers (mapq | type << 8 | first lane << 10 | lanes << 15, the
-// same for every locus: a row's table row is warp-uniform) and per lane one 32-bit word holding the lane's four bytes, so the
-// likelihood kernel streams 128 coalesced bytes per four reads and does no per-read address arithmetic at all.
+// overlapping element's base and quality and its read's mapping quality.  Walking the reads from the loci (k_somatic's
+// gather_sample) costs ~60 instructions and two dependent loads per (read, word).  K_expand_rows does that walk ONCE, at pack
+// time — the CIGAR expansion of PileupElement.advanceToLocus / alignment (pileup/PileupElement.scala:68-248) — and leaves,
+// per word:
+//   columns   the plain elements (A/C/G/T bases of reads that are one M/=/X run between clips, qualities < 64: 98 % of all
+//             elements) of every locus, in read order, 16 bits each: quality | (base code ^ reference code) << 6 | rank of
+//             the read's mapping quality among those present (from the top) << 8.  Column k of the word holds the k-th
+//             element of each of its 32 loci; loci with fewer elements are filled with a sentinel that reads a zero row of
+//             the likelihood table.  Two columns per 32-bit word per locus: the likelihood kernel streams 128 coalesced bytes
+//             per two columns and does nothing per element but one table look-up and two additions;
+//   depth     the number of plain elements per locus (u16);
+//   rows      the other reads (insertions / deletions / skips / non-ACGT bases / wide qualities), two rows of 32 bytes each:
+//             the element class per locus (0xF8 | base code = plain base, 0xFE = an element that is not a plain base, 0xFD =
+//             an element the exact kernel must report an error for, 0xFF = no element) and its qualityScore; four rows to a
+//             group with one uint4 of row headers (mapq | type << 8).
 #pragma once
 
 #include "guac_pileup.cuh"
@@ -22,26 +25,36 @@ namespace guac {
 constexpr uint32_t kRowLean = 0u, kRowGeneral = 1u, kRowQuality = 2u;
 constexpr uint32_t kElemNone = 0xFFu, kElemOther = 0xFEu, kElemHard = 0xFDu, kElemPlain = 0xF8u;
 
-// row header: mapq 7..0 | type 9..8 | first lane 14..10 | lanes 20..15 | rank of the mapq among those present, from the top, 28..21 (the row
-// of the likelihood kernel's shared-memory table); 0 = padding (a lean row of no lanes)
-__device__ __forceinline__ uint32_t row_header(uint32_t mapq, uint32_t type, int lo, int len, uint32_t rank) {
-  return mapq | (type << 8) | ((uint32_t)lo << 10) | ((uint32_t)len << 15) | (rank << 21);
-}
+constexpr uint32_t kRankZero = 63u;        // rank of the sentinel element: the all-zero row of the likelihood table
+constexpr uint32_t kMaxRank = 62u;         // reads whose mapping quality ranks at or beyond this take the general rows
+constexpr uint32_t kSentinel = kRankZero << 8;
 
 struct RowsArgs {
   DevReads R;
-  uint2* hdr_w;
+  uint4* hdr_w;                // per word: {first column pair, columns, first row group, rows | highest rank << 24}
+  uint16_t* depth_w;           // per locus: plain elements
+  uint32_t* cols_w;            // per (block of eight columns, lane): 16 bytes
   uint4* groups_w;
   uint32_t* rows_w;
-  unsigned long long cap_groups;
+  unsigned long long cap_pairs, cap_groups;
   uint32_t w_begin, w_end;     // global word indices this launch covers
   uint32_t n_contigs;
   uint32_t pad_;
-  unsigned long long* counters;  // [4] groups reserved
-  uint32_t mapq_mask[8];         // mapping qualities present in the read set (k_header): a row's table row is its mapq's rank
+  unsigned long long* counters;  // [4] column blocks reserved, [5] row groups reserved
+  uint32_t mapq_mask[8];         // mapping qualities present in the read set (k_header)
 };
 
 constexpr int kRowsWarps = 8;
+
+__device__ __forceinline__ uint32_t mapq_rank(const uint32_t (&mask)[8], uint32_t mapq) {  // mapping qualities present above this one
+  uint32_t rank = 0;
+#pragma unroll
+  for (int wd = 0; wd < 8; ++wd) {
+    const uint32_t m = mask[wd];
+    rank += (uint32_t)wd > (mapq >> 5) ? __popc(m) : ((uint32_t)wd == (mapq >> 5) ? __popc(m & ~((2u << (mapq & 31u)) - 1u)) : 0u);
+  }
+  return rank;
+}
 
 __global__ void __launch_bounds__(kRowsWarps * 32) k_expand_rows(RowsArgs A) {
   const DevReads& R = A.R;
@@ -66,33 +79,42 @@ __global__ void __launch_bounds__(kRowsWarps * 32) k_expand_rows(RowsArgs A) {
     last = R.gran_last[ci.gran_off + g];
   }
   if (first == 0xFFFFFFFFu) {
-    if (lane == 0) A.hdr_w[W] = make_uint2(0u, 0u);
+    if (lane == 0) A.hdr_w[W] = make_uint4(0u, 0u, 0u, 0u);
+    A.depth_w[(size_t)W * 32 + lane] = 0;
     return;
   }
   narrow_candidates(R, first, last, span_lo, span_lo + 32);
   constexpr uint32_t kLeanMask = kInfoSimple | kInfoHasExc | kInfoWideQ;
+  const uint32_t rcode = ((R.trk_lo[W] >> lane) & 1u) | (((R.trk_hi[W] >> lane) & 1u) << 1);  // this locus' reference code
 
-  uint32_t n_rows = 0;
-  unsigned long long goff = 0;
-  bool fits = false;
+  uint32_t depth = 0, n_cols = 0, max_rank = 0, n_rows = 0;
+  unsigned long long coff = 0, goff = 0;
   uint32_t acc = 0, hacc[4] = {0u, 0u, 0u, 0u};
   for (int pass = 0; pass < 2; ++pass) {
-    uint32_t row = 0;
+    uint32_t row = 0, k = 0, pend[4] = {0u, 0u, 0u, 0u};
+    auto put = [&](uint32_t elem) {  // this lane's next column element; eight columns (16 bytes per locus) leave together
+      const uint32_t j = k & 7u;
+      const uint32_t v = elem << (16 * (j & 1u));
+      pend[0] = (j >> 1) == 0u ? (j & 1u ? pend[0] | v : v) : pend[0];
+      pend[1] = (j >> 1) == 1u ? (j & 1u ? pend[1] | v : v) : pend[1];
+      pend[2] = (j >> 1) == 2u ? (j & 1u ? pend[2] | v : v) : pend[2];
+      pend[3] = (j >> 1) == 3u ? (j & 1u ? pend[3] | v : v) : pend[3];
+      if (j == 7u) reinterpret_cast<uint4*>(A.cols_w)[((size_t)coff + (k >> 3)) * 32 + lane] = make_uint4(pend[0], pend[1], pend[2], pend[3]);
+      ++k;
+    };
     auto append = [&](uint32_t header, uint32_t byte) {  // warp-uniform call; `byte` per lane
-      if (pass == 1 && fits) {
-        const uint32_t k = row & 3u;
-        acc |= (byte & 0xFFu) << (8 * k);
-        hacc[0] = k == 0 ? header : hacc[0];
-        hacc[1] = k == 1 ? header : hacc[1];
-        hacc[2] = k == 2 ? header : hacc[2];
-        hacc[3] = k == 3 ? header : hacc[3];
-        if (k == 3u) {
-          const size_t grp = (size_t)goff + (row >> 2);
-          A.rows_w[grp * 32 + lane] = acc;
-          if (lane == 0) A.groups_w[grp] = make_uint4(hacc[0], hacc[1], hacc[2], hacc[3]);
-          acc = 0;
-          hacc[0] = hacc[1] = hacc[2] = hacc[3] = 0u;
-        }
+      const uint32_t j = row & 3u;
+      acc |= (byte & 0xFFu) << (8 * j);
+      hacc[0] = j == 0 ? header : hacc[0];
+      hacc[1] = j == 1 ? header : hacc[1];
+      hacc[2] = j == 2 ? header : hacc[2];
+      hacc[3] = j == 3 ? header : hacc[3];
+      if (j == 3u) {
+        const size_t grp = (size_t)goff + (row >> 2);
+        A.rows_w[grp * 32 + lane] = acc;
+        if (lane == 0) A.groups_w[grp] = make_uint4(hacc[0], hacc[1], hacc[2], hacc[3]);
+        acc = 0;
+        hacc[0] = hacc[1] = hacc[2] = hacc[3] = 0u;
       }
       ++row;
     };
@@ -101,7 +123,8 @@ __global__ void __launch_bounds__(kRowsWarps * 32) k_expand_rows(RowsArgs A) {
       ReadRec my{0, 0, 0, 0};
       if (mine < last) my = R.rec[mine];
       const bool overlaps = mine < last && my.start < span_lo + 32 && my.end > span_lo && my.end > my.start;
-      const bool lean_mine = overlaps && (my.info & kLeanMask) == kInfoSimple;
+      const uint32_t my_rank = overlaps ? mapq_rank(A.mapq_mask, my.info >> kInfoMapqShift) : 0u;
+      const bool lean_mine = overlaps && (my.info & kLeanMask) == kInfoSimple && my_rank < kMaxRank;
       uint32_t ov = __ballot_sync(0xFFFFFFFFu, overlaps);
       const uint32_t ov_lean = __ballot_sync(0xFFFFFFFFu, lean_mine);
       unsigned long long my_qa = 0;
@@ -111,31 +134,30 @@ __global__ void __launch_bounds__(kRowsWarps * 32) k_expand_rows(RowsArgs A) {
         const int j = __ffs(ov) - 1;
         ov &= ov - 1;
         const bool lean = (ov_lean >> j) & 1u;
-        if (pass == 0) {
-          if (!lean && (row & 1u)) ++row;  // a general read's two rows share a group: pad to an even row
-          row += lean ? 1u : 2u;
-          continue;
-        }
         const int start = __shfl_sync(0xFFFFFFFFu, my.start, j), end = __shfl_sync(0xFFFFFFFFu, my.end, j);
-        const uint32_t info = __shfl_sync(0xFFFFFFFFu, my.info, j);
-        const uint32_t mapq = info >> kInfoMapqShift;
-        uint32_t rank = 0;  // mapping qualities present ABOVE this one (high ones are the common ones: they get the first rows)
-#pragma unroll
-        for (int wd = 0; wd < 8; ++wd) {
-          const uint32_t m = A.mapq_mask[wd];
-          rank += (uint32_t)wd > (mapq >> 5) ? __popc(m) : ((uint32_t)wd == (mapq >> 5) ? __popc(m & ~((2u << (mapq & 31u)) - 1u)) : 0u);
+        const uint32_t rank = __shfl_sync(0xFFFFFFFFu, my_rank, j);
+        const bool covered = x >= start && x < end;
+        if (pass == 0) {
+          if (lean) {
+            depth += covered ? 1u : 0u;
+            max_rank = max(max_rank, rank);
+          } else {
+            row += 2u;
+          }
+          continue;
         }
         if (lean) {
           const unsigned long long qa = ((unsigned long long)__shfl_sync(0xFFFFFFFFu, (uint32_t)(my_qa >> 32), j) << 32) |
                                         __shfl_sync(0xFFFFFFFFu, (uint32_t)my_qa, j);
-          const int lo = max(start, span_lo) - span_lo, hi = min(end, span_lo + 32) - span_lo;
-          uint32_t b = 0;
-          if (lane >= lo && lane < hi) b = (uint32_t)__ldg(reinterpret_cast<const uint8_t*>((uintptr_t)(qa + (unsigned long long)(long long)x)));
-          append(row_header(mapq, kRowLean, lo, hi - lo, rank), b);
+          if (covered) {
+            const uint32_t b = (uint32_t)__ldg(reinterpret_cast<const uint8_t*>((uintptr_t)(qa + (unsigned long long)(long long)x)));
+            put((b & 63u) | ((((b >> 6) ^ rcode) & 3u) << 6) | (rank << 8));
+          }
         } else {
-          if (row & 1u) append(0u, 0u);
+          const uint32_t info = __shfl_sync(0xFFFFFFFFu, my.info, j);
+          const uint32_t mapq = info >> kInfoMapqShift;
           uint32_t b = kElemNone, q = 0;
-          if (x >= start && x < end) {
+          if (covered) {
             Elem e;
             const int rc = classify(R, (uint64_t)(base + j), x, (uint8_t)'N', e);
             if (rc || e.kind == kNone) b = kElemHard;
@@ -143,23 +165,34 @@ __global__ void __launch_bounds__(kRowsWarps * 32) k_expand_rows(RowsArgs A) {
             else b = kElemOther;
             q = (uint32_t)e.qual & 0xFFu;
           }
-          append(row_header(mapq, kRowGeneral, 0, 32, rank), b);
-          append(row_header(mapq, kRowQuality, 0, 32, rank), q);
+          append(mapq | (kRowGeneral << 8), b);
+          append(mapq | (kRowQuality << 8), q);
         }
       }
     }
     if (pass == 0) {
       n_rows = row;
-      const uint32_t groups = (n_rows + 3u) >> 2;
-      if (lane == 0) goff = atomicAdd(&A.counters[4], (unsigned long long)groups);
+      n_cols = __reduce_max_sync(0xFFFFFFFFu, depth);
+      max_rank = __reduce_max_sync(0xFFFFFFFFu, max_rank);
+      const uint32_t pairs = (n_cols + 7u) >> 3, groups = (n_rows + 3u) >> 2;  // (blocks of eight columns)
+      if (lane == 0) {
+        coff = atomicAdd(&A.counters[4], (unsigned long long)pairs);
+        goff = atomicAdd(&A.counters[5], (unsigned long long)groups);
+      }
+      coff = __shfl_sync(0xFFFFFFFFu, coff, 0);
       goff = __shfl_sync(0xFFFFFFFFu, goff, 0);
-      fits = goff + groups <= A.cap_groups;  // (else the host grows the buffers and packs the rows again)
-      if (lane == 0) A.hdr_w[W] = make_uint2((uint32_t)goff, n_rows);
-      if (!fits || n_rows == 0) return;
-    } else if (row & 3u) {  // the last, partial group
-      const size_t grp = (size_t)goff + (row >> 2);
-      A.rows_w[grp * 32 + lane] = acc;
-      if (lane == 0) A.groups_w[grp] = make_uint4(hacc[0], hacc[1], hacc[2], hacc[3]);
+      const bool fits = coff + pairs <= A.cap_pairs && goff + groups <= A.cap_groups;  // (else the host grows the buffers and repeats)
+      if (lane == 0) A.hdr_w[W] = make_uint4((uint32_t)coff, n_cols, (uint32_t)goff, n_rows | (max_rank << 24));
+      A.depth_w[(size_t)W * 32 + lane] = (uint16_t)min(depth, 0xFFFFu);
+      if (!fits || (n_cols == 0 && n_rows == 0)) return;
+    } else {
+      const uint32_t slots = ((n_cols + 7u) >> 3) << 3;  // loci with fewer elements: sentinels up to the word's last block of columns
+      while (k < slots) put(kSentinel);
+      if (row & 3u) {  // the last, partial group of rows
+        const size_t grp = (size_t)goff + (row >> 2);
+        A.rows_w[grp * 32 + lane] = acc;
+        if (lane == 0) A.groups_w[grp] = make_uint4(hacc[0], hacc[1], hacc[2], hacc[3]);
+      }
     }
   }
 }

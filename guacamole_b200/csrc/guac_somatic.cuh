@@ -595,21 +595,23 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
   }
 }
 
-// ---- the same sums from the word's ROWS (guac_rows.cuh): no per-read address arithmetic, the table in shared memory ----------
-// Shared-memory table of one CTA: for every mapping quality present in the tumor sample (and kept by the mapq filter) one row
-// of 64 (log(s + s), log((1-s) + (1-s))) pairs, s = success(quality) * success(mapq) (probabilityCorrectIncludingAlignment,
-// likelihood/Likelihood.scala:58-62); one row for the normal sample (IgnoringAlignment, :48-50).  A row's table row is
-// warp-uniform (its header holds the mapq).  Mapping qualities beyond the table's capacity and the rare general rows
-// (qualities up to 255) read the full table in global memory.
-constexpr int kSomTabRows = 62;
+// ---- the same sums from the word's transposed pileup (guac_rows.cuh): no per-read work, the table in shared memory -------------
+// Shared-memory table of one CTA.  Tumor: 64 rows of 64 (log(s + s), log((1-s) + (1-s))) pairs, s = success(quality) *
+// success(mapq) (probabilityCorrectIncludingAlignment, likelihood/Likelihood.scala:58-62): row r belongs to the r-th largest
+// mapping quality present in the tumor sample; rows of mapping qualities below --min-mapq, the unused rows and row 63 (the
+// sentinel's) are ZERO, so dropped reads and the padding of short columns add nothing — no test per element.  Normal:
+// the one row of probabilityCorrectIgnoringAlignment (:48-50), and a zero row for its dropped reads.
+constexpr int kSomTabRows = 64;
 struct RowTables {
-  uint8_t row_mapq[kSomTabRows];  // mapping quality of the table's row r = the r-th LARGEST mapq present in the tumor sample
-  int32_t n_rows;                 // rows resident in shared memory (reads whose mapq ranks beyond them use the global table)
+  uint8_t row_mapq[kSomTabRows];  // mapping quality of the tumor table's row r
+  int32_t n_rows;                 // rows in use (< kMaxRank)
+  int32_t n_keep_tumor;           // ranks below this pass the mapq filter ...
+  int32_t n_keep_normal;          // ... same for the normal sample's ranks
   int32_t pad_;
 };
 struct SomSmem {
   double2 tumor[kSomTabRows * 64];
-  double2 normal[64];
+  double2 normal[2 * 64];
 };
 
 __device__ __forceinline__ double2 lds_double2(uint32_t shared_addr) {
@@ -620,51 +622,94 @@ __device__ __forceinline__ double2 lds_double2(uint32_t shared_addr) {
 
 template <bool TUMOR>
 __device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t word, const int rcode, const bool std_ref, const SomParams& prm,
-                                            const uint32_t smem_table /* shared address of SomSmem */, const int n_table_rows,
+                                            const uint32_t smem_table /* shared address of SomSmem */, const RowTables& rt,
                                             const double* __restrict__ tables, LaneAcc& A) {
   const uint32_t lane = threadIdx.x & 31u;
   acc_clear(A);
-  const uint2 wh = R.q_hdr[word];
-  const uint32_t n_rows = wh.y;
-  if (n_rows == 0) return;
-  const uint32_t groups = (n_rows + 3u) >> 2;
-  const uint4* __restrict__ gh = R.q_groups + wh.x;
-  const uint32_t* __restrict__ rows = R.q_rows + (size_t)wh.x * 32 + lane;
+  const uint4 wh = R.q_hdr[word];
+  const uint32_t n_cols = wh.y, n_rows = wh.w & 0xFFFFFFu, max_rank = wh.w >> 24;
+  const uint32_t depth_all = R.q_depth[(size_t)word * 32 + lane];
   const double2* __restrict__ gtab = reinterpret_cast<const double2*>(tables + (TUMOR ? kTabT : kTabN));
   const uint32_t tab = TUMOR ? smem_table : smem_table + (uint32_t)(kSomTabRows * 64 * sizeof(double2));
+  const uint32_t n_keep = (uint32_t)(TUMOR ? rt.n_keep_tumor : rt.n_keep_normal);
+  const uint32_t min_mapq = prm.min_mapq > 0 ? (uint32_t)prm.min_mapq : 0u;
+  const bool fma = prm.filter_multi_allelic != 0;
   double sr1 = 0.0;
-  int n_ref = 0, any = 0;
+  int any = depth_all != 0u ? 1 : 0;
+  uint32_t dropped = 0;
   unsigned long long cnt_packed = 0;  // mismatching elements: four 16-bit fields, one per base code
   const uint32_t rc_eff = std_ref ? (uint32_t)rcode : 4u;
-  const bool fma = prm.filter_multi_allelic != 0;
-  const uint32_t min_mapq = prm.min_mapq > 0 ? (uint32_t)prm.min_mapq : 0u;
-  const uint32_t resident = TUMOR ? (uint32_t)n_table_rows : 0xFFFFu;
-  auto plain = [&](const uint32_t code, const double2 l) {  // one kept A/C/G/T element
-    A.t0 += l.y;
-    if (code == rc_eff) {
-      sr1 += l.x;
-      n_ref += 1;
-    } else {
-      cnt_packed += 1ull << (16 * code);
-      if (code == 0u) { A.s1[0] += l.x; A.s0[0] += l.y; }
-      else if (code == 1u) { A.s1[1] += l.x; A.s0[1] += l.y; }
-      else if (code == 2u) { A.s1[2] += l.x; A.s0[2] += l.y; }
-      else { A.s1[3] += l.x; A.s0[3] += l.y; }
-    }
+  // an element that does not carry the reference base (rare)
+  auto non_ref = [&](const uint32_t cls, const uint32_t rank, const double2 l) {
+    if (rank >= n_keep) return;  // dropped by the mapq filter (its table row is zero: nothing was added to T0 either)
+    const uint32_t code = cls ^ (uint32_t)rcode;
+    cnt_packed += 1ull << (16 * code);
+    if (code == 0u) { A.s1[0] += l.x; A.s0[0] += l.y; }
+    else if (code == 1u) { A.s1[1] += l.x; A.s0[1] += l.y; }
+    else if (code == 2u) { A.s1[2] += l.x; A.s0[2] += l.y; }
+    else { A.s1[3] += l.x; A.s0[3] += l.y; }
   };
-  // everything but a kept lean row whose table row is resident (rare: general rows, mapq-dropped reads, table overflow)
-  auto slow_row = [&](const uint32_t h, const uint32_t b, const uint32_t q) {
-    const uint32_t type = (h >> 8) & 3u, mapq = h & 0xFFu;
-    const bool keep = mapq >= min_mapq;
-    if (type == kRowLean) {
-      if ((lane - ((h >> 10) & 31u)) < ((h >> 15) & 63u)) {
-        any = 1;
-        if (keep) plain(b >> 6, __ldg(&gtab[TUMOR ? (mapq << 8) + (b & 63u) : (b & 63u)]));
-        else if (fma) A.seen |= 1u << (b >> 6);
+  if (n_cols) {
+    const uint32_t blocks = (n_cols + 7u) >> 3;  // eight columns = 16 bytes per locus per load
+    const uint4* __restrict__ cp = reinterpret_cast<const uint4*>(R.q_cols) + (size_t)wh.x * 32 + lane;
+    const bool check = max_rank >= n_keep;  // (warp-uniform) some read of this word fails the mapq filter
+    const uint32_t ref_mask = std_ref ? 0xC0u : 0u;  // (no reference class at a locus whose reference base is not A/C/G/T)
+    uint4 v = __ldg(cp), v_next = v;
+    if (blocks > 1) v_next = __ldg(cp + 32);
+    for (uint32_t p = 0; p < blocks; ++p) {
+      const uint4 v_now = v;
+      v = v_next;
+      if (p + 2 < blocks) v_next = __ldg(cp + (size_t)(p + 2) * 32);  // two blocks are on their way while this one is summed
+      const uint32_t w4[4] = {v_now.x, v_now.y, v_now.z, v_now.w};
+      // the hot loop: per element one table look-up and two additions; elements that do not carry the reference base (a
+      // percent of them) are only noted here
+      uint32_t rare = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t e = (j & 1) ? (w4[j >> 1] >> 16) : (w4[j >> 1] & 0xFFFFu);
+        const uint32_t rank = e >> 8;
+        const double2 l = lds_double2(tab + (TUMOR ? rank * 1024u : (rank < n_keep ? 0u : 1024u)) + (e & 63u) * 16u);
+        A.t0 += l.y;
+        const bool is_ref = (e & 0xC0u) == 0u && ref_mask != 0u;
+        sr1 += is_ref ? l.x : 0.0;
+        rare |= is_ref ? 0u : (1u << j);
       }
-    } else if (type == kRowGeneral && b != kElemNone) {  // (its quality row is the next one of the same group)
-      any = 1;
-      if (keep || fma) {
+      if (check) {  // (rare words) elements dropped by the mapq filter: n_keep <= rank < the sentinel's
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t wj = j < 2 ? w4[0] : j < 4 ? w4[1] : j < 6 ? w4[2] : w4[3];
+          const uint32_t rank = ((j & 1) ? (wj >> 16) : (wj & 0xFFFFu)) >> 8;
+          dropped += (rank - n_keep) < (kRankZero - n_keep) ? 1u : 0u;
+        }
+      }
+      while (rare) {  // (divergent, rare)
+        const int j = __ffs(rare) - 1;
+        rare &= rare - 1;
+        const uint32_t wj = j < 2 ? w4[0] : j < 4 ? w4[1] : j < 6 ? w4[2] : w4[3];
+        const uint32_t e = (j & 1) ? (wj >> 16) : (wj & 0xFFFFu);
+        const uint32_t rank = e >> 8;
+        non_ref((e >> 6) & 3u, rank, lds_double2(tab + (TUMOR ? rank * 1024u : (rank < n_keep ? 0u : 1024u)) + (e & 63u) * 16u));
+      }
+    }
+  }
+  // the general rows (reads with insertions / deletions / skips / non-ACGT bases / wide qualities): a class row + a quality row each
+  if (n_rows) {
+    const uint32_t groups = (n_rows + 3u) >> 2;
+    const uint4* __restrict__ gh = R.q_groups + wh.z;
+    const uint32_t* __restrict__ rows = R.q_rows + (size_t)wh.z * 32 + lane;
+    for (uint32_t g = 0; g < groups; ++g) {
+      const uint4 hd = __ldg(gh + g);
+      const uint32_t v = __ldg(rows + (size_t)g * 32);
+      const uint32_t hs[4] = {hd.x, hd.y, hd.z, hd.w};
+#pragma unroll
+      for (int k = 0; k < 4; k += 2) {
+        const uint32_t h = hs[k];
+        if (((h >> 8) & 3u) != kRowGeneral) continue;  // (padding of the last group)
+        const uint32_t mapq = h & 0xFFu, b = (v >> (8 * k)) & 0xFFu, q = (v >> (8 * (k + 1))) & 0xFFu;
+        const bool keep = mapq >= min_mapq;
+        if (b == kElemNone) continue;
+        any = 1;
+        if (!keep && !fma) continue;
         if (b == kElemHard) {
           A.other += 1;
           A.hard += 1;
@@ -676,50 +721,41 @@ __device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t wo
             A.ohet += fmax(0.0, l.y);
             A.ohom += fmax(l.x, l.y);
           }
-        } else {
+        } else if (keep) {  // a plain base of a general read
           const uint32_t code = b & 3u;
-          A.seen |= 1u << code;
-          if (keep) plain(code, __ldg(&gtab[TUMOR ? (mapq << 8) + q : q]));
+          const double2 l = __ldg(&gtab[TUMOR ? (mapq << 8) + q : q]);
+          A.t0 += l.y;
+          if (code == rc_eff) {
+            sr1 += l.x;
+            dropped -= 1u;  // (counted as a kept element: the reference count below is kept elements - the other classes)
+          } else {
+            cnt_packed += 1ull << (16 * code);
+            if (code == 0u) { A.s1[0] += l.x; A.s0[0] += l.y; }
+            else if (code == 1u) { A.s1[1] += l.x; A.s0[1] += l.y; }
+            else if (code == 2u) { A.s1[2] += l.x; A.s0[2] += l.y; }
+            else { A.s1[3] += l.x; A.s0[3] += l.y; }
+            dropped -= 1u;
+          }
         }
-      }
-    }
-  };
-  uint4 hd = __ldg(gh);
-  uint32_t v = __ldg(rows);
-  for (uint32_t g = 0; g < groups; ++g) {
-    const uint4 hd_now = hd;
-    const uint32_t v_now = v;
-    if (g + 1 < groups) {  // the next group is on its way while this one is summed
-      hd = __ldg(gh + g + 1);
-      v = __ldg(rows + (size_t)(g + 1) * 32);
-    }
-    const uint32_t hs[4] = {hd_now.x, hd_now.y, hd_now.z, hd_now.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t h = hs[k];  // (everything read from a header is warp-uniform; a padding row is a lean row of no lanes)
-      const uint32_t b = (v_now >> (8 * k)) & 0xFFu;
-      const uint32_t rank = h >> 21;
-      if ((h & 0x300u) == 0u && (h & 0xFFu) >= min_mapq && rank < resident) {  // the common row
-        const bool covered = (lane - ((h >> 10) & 31u)) < ((h >> 15) & 63u);
-        if (covered) {
-          any = 1;
-          plain(b >> 6, lds_double2(tab + (TUMOR ? rank * 1024u : 0u) + (b & 63u) * 16u));
-        }
-      } else {
-        slow_row(h, b, (v_now >> (8 * ((k + 1) & 3))) & 0xFFu);
       }
     }
   }
+  // kept plain elements = all of the locus - the dropped ones (+ the general reads' plain bases, entered as negative drops)
+  const int kept = (int)depth_all - (int)dropped;
+  int others = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) others += (int)((cnt_packed >> (16 * k)) & 0xFFFFu);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    A.cnt[k] = (int)((cnt_packed >> (16 * k)) & 0xFFFFu) + ((uint32_t)k == rc_eff ? n_ref : 0);
+    A.cnt[k] = (int)((cnt_packed >> (16 * k)) & 0xFFFFu) + ((uint32_t)k == rc_eff ? kept - others : 0);
     A.depth += A.cnt[k];
   }
+  if (!std_ref) A.depth = kept;  // (no reference class: every element sits in a mismatch class; only the totals matter, the locus is deferred)
   A.any = any;
   A.ref_depth = std_ref ? A.cnt[rcode] : 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) A.seen |= A.cnt[k] > 0 ? (1u << k) : 0u;
-  if (n_rows > 0xFFFFu) A.other += 1;  // the packed counters hold 16 bits: deeper pileups go to the exact kernel
+  if (n_cols + n_rows > 0xFFFFu) A.other += 1;  // the packed counters hold 16 bits: deeper pileups go to the exact kernel
   double sr0 = A.t0;  // S0 of the reference class = T0 - the other classes' S0
 #pragma unroll
   for (int k = 0; k < 4; ++k) sr0 -= A.s0[k];
@@ -740,12 +776,14 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
                                                         const double* __restrict__ tables, RowTables rt, SomOut out) {
   extern __shared__ __align__(16) unsigned char som_smem_raw[];
   const uint32_t smem_table = (uint32_t)__cvta_generic_to_shared(som_smem_raw);
-  if (ROWS) {  // the CTA's copy of the table rows it will index
+  if (ROWS) {  // the CTA's copy of the table: kept mapping qualities' rows, zero rows for everything else
     SomSmem& Tw = *reinterpret_cast<SomSmem*>(som_smem_raw);
     const double2* gt = reinterpret_cast<const double2*>(tables + kTabT);
     const double2* gn = reinterpret_cast<const double2*>(tables + kTabN);
-    for (int i = threadIdx.x; i < rt.n_rows * 64; i += kSomThreads) Tw.tumor[i] = gt[((int)rt.row_mapq[i >> 6] << 8) + (i & 63)];
-    for (int i = threadIdx.x; i < 64; i += kSomThreads) Tw.normal[i] = gn[i];
+    const int live = min(rt.n_rows, rt.n_keep_tumor);
+    for (int i = threadIdx.x; i < kSomTabRows * 64; i += kSomThreads)
+      Tw.tumor[i] = (i >> 6) < live ? gt[((int)rt.row_mapq[i >> 6] << 8) + (i & 63)] : make_double2(0.0, 0.0);
+    for (int i = threadIdx.x; i < 128; i += kSomThreads) Tw.normal[i] = i < 64 ? gn[i] : make_double2(0.0, 0.0);
     __syncthreads();
   }
   const TileDesc td = tiles[blockIdx.x];
@@ -765,7 +803,7 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
     const bool stdT = (ts >> lane) & 1u, stdN = (ns >> lane) & 1u;
     LaneAcc AT, AN;
     if (ROWS) {
-      if (w < ciT.n_words) gather_rows<true>(RT, ciT.word_off + (uint32_t)w, rcT, stdT, prm, smem_table, rt.n_rows, tables, AT);
+      if (w < ciT.n_words) gather_rows<true>(RT, ciT.word_off + (uint32_t)w, rcT, stdT, prm, smem_table, rt, tables, AT);
       else acc_clear(AT);
     } else {
       gather_sample<true>(RT, td.contig, span_lo, x, rcT, stdT, prm, tables, AT);
@@ -784,7 +822,9 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
       else if (covT > 0 && !tumor_all_match) {
         if (!tumor_exact && AT.other > 0) tumor_exact = !ref_leads_despite_others(AT, rcT);
         if (tumor_exact) need_normal = true;
-        else if (AT.other == 0) {
+        else if (AT.other == 0 && !ref_leads_despite_others(AT, rcT)) {
+          // (the same exact bound first, on the raw sums: at most loci with a mismatching read or two the homozygous-reference
+          // genotype leads every other one clearly, and the ten likelihoods below are never formed)
           SnvAlleles sT;
           snv_compact(AT, sT);
           variant = snv_tumor_most_likely(sT, AT.ref_depth, rcT, prm, &c1, &c2, &tumor_l);
@@ -795,7 +835,7 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
     if (in_req && AT.any > 0) ++n_visited;
     if (!__any_sync(0xFFFFFFFFu, need_normal)) continue;
     if (ROWS) {
-      if (w < ciN.n_words) gather_rows<false>(RN, ciN.word_off + (uint32_t)w, rcN, stdN, prm, smem_table, rt.n_rows, tables, AN);
+      if (w < ciN.n_words) gather_rows<false>(RN, ciN.word_off + (uint32_t)w, rcN, stdN, prm, smem_table, rt, tables, AN);
       else acc_clear(AN);
     } else {
       gather_sample<false>(RN, td.contig, span_lo, x, rcN, stdN, prm, tables, AN);
@@ -1257,11 +1297,15 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
     CUDA_OK(cudaEventRecord(ctx->ev[0], st));
     if (tumor.q_hdr.n && normal.q_hdr.n) {
       RowTables rt;  // the table's row r belongs to the r-th largest mapping quality present in the tumor sample
-      memset(rt.row_mapq, 0, sizeof rt.row_mapq);
-      rt.n_rows = 0;
-      rt.pad_ = 0;
-      for (int m = 255; m >= 0 && rt.n_rows < kSomTabRows; --m)
-        if ((tumor.mapq_mask[m >> 5] >> (m & 31)) & 1u) rt.row_mapq[rt.n_rows++] = (uint8_t)m;
+      memset(&rt, 0, sizeof rt);
+      const int min_q = std::max(0, p.min_alignment_quality);
+      for (int m = 255; m >= 0; --m) {
+        if ((tumor.mapq_mask[m >> 5] >> (m & 31)) & 1u) {
+          if (rt.n_rows < (int)kMaxRank) rt.row_mapq[rt.n_rows++] = (uint8_t)m;
+          if (m >= min_q) rt.n_keep_tumor += 1;
+        }
+        if (((normal.mapq_mask[m >> 5] >> (m & 31)) & 1u) && m >= min_q) rt.n_keep_normal += 1;
+      }
       if (!ctx->som_attr_done) {
         CUDA_OK(cudaFuncSetAttribute(k_somatic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SomSmem)));
         ctx->som_attr_done = true;
