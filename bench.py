@@ -149,8 +149,8 @@ def genome(world, workload, contig_length):
         contigs = [("amplicon", 1_000_000 + SPAN)]
     elif world == 1:
         contigs = [("20", contig_length)]
-    else:
-        contigs = list(synth.GRCH37)
+    else:  # the sequence dictionary in name order, so that LociSet order (contigs by name) and contig index order agree
+        contigs = sorted(synth.GRCH37, key=lambda c: c[0])
     order = sorted(range(len(contigs)), key=lambda i: contigs[i][0])
     if workload == "amplicon":
         loci = [(0, 0, 1_000_000)]

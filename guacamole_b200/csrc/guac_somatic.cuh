@@ -1065,7 +1065,8 @@ __device__ bool elem_is_allele(const DevReads& R, const Elem& e, uint8_t ref_bas
 // The statistics AlleleEvidence needs are over small integers (mapping quality 0..255, element quality 0..255, mismatches per
 // read): one histogram each in shared memory gives exact medians at any depth (breeze median = sort + middle element(s))
 // and the means as integer sums (breeze's running mean agrees with sum / n to an ulp).
-constexpr int kNmBins = 2048;  // reads with more MD mismatches than this are not supported by K_evidence
+constexpr int kNmBins = 512;   // reads with more MD mismatches than this are not supported by K_evidence (small histograms:
+                               // more warps per SM, and the kernel lives on memory latency)
 
 struct EvidenceSmem {
   int hmq[256], hbq[256], hnm[kNmBins];
@@ -1181,7 +1182,7 @@ __device__ void evidence_sample(const DevReads& R, int contig, int locus, const 
   __syncwarp();
 }
 
-constexpr int kEvidenceWarps = 2;
+constexpr int kEvidenceWarps = 4;
 
 __global__ void __launch_bounds__(kEvidenceWarps * 32) k_evidence(DevReads RT, DevReads RN, SomParams prm, SomOut out) {
   __shared__ EvidenceSmem sm[kEvidenceWarps];
@@ -1317,7 +1318,7 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
     }
     CUDA_OK(cudaEventRecord(ctx->ev[1], st));
     k_somatic_exact<<<ctx->sm_count * 32, kSomExactWarps * 32, 0, st>>>(RT, RN, out.slow, prm, ctx->d_tables, out);
-    k_evidence<<<ctx->sm_count * 8, kEvidenceWarps * 32, 0, st>>>(RT, RN, prm, out);
+    k_evidence<<<ctx->sm_count * 12, kEvidenceWarps * 32, 0, st>>>(RT, RN, prm, out);
     CUDA_OK(cudaEventRecord(ctx->ev[2], st));
     CUDA_OK(cudaGetLastError());
     unsigned long long* c = ctx->h_counters;

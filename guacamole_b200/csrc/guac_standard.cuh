@@ -258,7 +258,7 @@ void run_standard(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range
     k_standard<<<(int)tiles.size(), kSomThreads, 0, st>>>(R, d_tiles.p, prm, ctx->d_tables, out);
     CUDA_OK(cudaEventRecord(ctx->ev[1], st));
     k_standard_exact<<<ctx->sm_count * 32, kSomExactWarps * 32, 0, st>>>(R, out.slow, prm, ctx->d_tables, out);
-    k_standard_evidence<<<ctx->sm_count * 8, kEvidenceWarps * 32, 0, st>>>(R, prm_unfiltered, out);
+    k_standard_evidence<<<ctx->sm_count * 12, kEvidenceWarps * 32, 0, st>>>(R, prm_unfiltered, out);
     CUDA_OK(cudaEventRecord(ctx->ev[2], st));
     CUDA_OK(cudaGetLastError());
     unsigned long long* c = ctx->h_counters;
