@@ -16,7 +16,7 @@ EXPORTED = [
     "guac_ctx_set_option", "guac_ctx_timer_start", "guac_ctx_timer_stop", "guac_host_register", "guac_host_unregister",
     "guac_reads_pack", "guac_reads_pack_device", "guac_reads_free", "guac_reads_count", "guac_reads_device_bytes",
     "guac_reads_order_sensitive_loci", "guac_reads_h2d_bytes", "guac_reads_pack_kernel_ms", "guac_reads_expand_kernel_ms",
-    "guac_germline_threshold", "guac_somatic_standard", "guac_germline_standard", "guac_pileup_counts",
+    "guac_germline_threshold", "guac_somatic_standard", "guac_somatic_standard_filtered", "guac_germline_standard", "guac_pileup_counts",
     "guac_allele_counts", "guac_result_allele_counts",
     "guac_result_n", "guac_result_threshold_records", "guac_result_compact_records", "guac_result_somatic_records", "guac_result_counts",
     "guac_result_called_alleles",
@@ -88,6 +88,8 @@ def lib():
                                           C.POINTER(abi.ThresholdParamsC), C.POINTER(vp)]
     L.guac_somatic_standard.argtypes = [vp, vp, vp, C.POINTER(abi.LocusRangeC), C.c_size_t,
                                         C.POINTER(abi.SomaticParamsC), C.POINTER(vp)]
+    L.guac_somatic_standard_filtered.argtypes = [vp, vp, vp, C.POINTER(abi.LocusRangeC), C.c_size_t,
+                                                 C.POINTER(abi.SomaticParamsC), C.POINTER(abi.SomaticFilterParamsC), C.POINTER(vp)]
     L.guac_germline_standard.argtypes = [vp, vp, C.POINTER(abi.LocusRangeC), C.c_size_t,
                                          C.POINTER(abi.StandardParamsC), C.POINTER(vp)]
     L.guac_allele_counts.argtypes = [vp, vp, C.POINTER(abi.LocusRangeC), C.c_size_t, C.POINTER(vp)]

@@ -303,14 +303,30 @@ def germline_threshold(ctx: Context, reads: PackedReads, loci_partitions, thresh
 
 def somatic_standard(ctx: Context, tumor: PackedReads, normal: PackedReads, loci_partitions, odds_threshold: int = 20,
                      min_alignment_quality: int = 1, filter_multi_allelic: bool = False,
-                     max_read_depth: int = 2 ** 31 - 1, skip_empty: bool = True) -> Result:
-    """pileupFlatMapTwoRDDs(tumor, normal, lociPartitions, skipEmpty, findPotentialVariantAtLocus(...))."""
+                     max_read_depth: int = 2 ** 31 - 1, skip_empty: bool = True, filters: Optional[dict] = None) -> Result:
+    """pileupFlatMapTwoRDDs(tumor, normal, lociPartitions, skipEmpty, findPotentialVariantAtLocus(...)).  `filters`: the
+    keyword arguments of somatic_genotype_filter — the post-call genotype filters (SomaticStandardCaller.scala:125-151) then
+    run on the device, and only the records that pass come back (guac_somatic_standard_filtered)."""
     arr, n = _ranges(loci_partitions)
     prm = abi.SomaticParamsC(odds_threshold, min_alignment_quality, int(filter_multi_allelic), max_read_depth,
                              int(skip_empty))
     h = C.c_void_p()
-    ctx._check(lib().guac_somatic_standard(ctx._h, tumor._h, normal._h, arr, n, C.byref(prm), C.byref(h)))
+    if filters is None:
+        ctx._check(lib().guac_somatic_standard(ctx._h, tumor._h, normal._h, arr, n, C.byref(prm), C.byref(h)))
+    else:
+        fp = _filter_params(**filters)
+        ctx._check(lib().guac_somatic_standard_filtered(ctx._h, tumor._h, normal._h, arr, n, C.byref(prm), C.byref(fp), C.byref(h)))
     return Result(h, "somatic")
+
+
+def _filter_params(min_tumor_read_depth=0, max_tumor_read_depth=2 ** 31 - 1, min_normal_read_depth=0,
+                   min_tumor_alternate_read_depth=0, min_lod=0, min_likelihood=0, min_vaf=0,
+                   min_average_mapping_quality=0, min_average_base_quality=0, max_median_mismatches=2 ** 31 - 1,
+                   seq_overload=False):
+    return abi.SomaticFilterParamsC(min_tumor_read_depth, max_tumor_read_depth, min_normal_read_depth,
+                                    min_tumor_alternate_read_depth, min_lod, min_likelihood, min_vaf,
+                                    min_average_mapping_quality, min_average_base_quality, max_median_mismatches,
+                                    int(seq_overload), 0)
 
 
 def germline_threshold_by_sample(ctx: Context, batch: ReadBatch, loci_partitions, reference: Optional[Sequence[bytes]] = None,

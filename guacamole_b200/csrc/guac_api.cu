@@ -1199,6 +1199,20 @@ guac_status guac_somatic_standard(guac_ctx* ctx, const guac_reads* tumor, const 
   });
 }
 
+guac_status guac_somatic_standard_filtered(guac_ctx* ctx, const guac_reads* tumor, const guac_reads* normal, const guac_locus_range* ranges,
+                                           size_t n_ranges, const guac_somatic_params* params, const guac_somatic_filter_params* filters,
+                                           guac_result** out) {
+  if (!ctx || !tumor || !normal || !params || !filters || !out || (n_ranges && !ranges)) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    std::unique_ptr<guac_result> res(new guac_result());
+    res->kind = 1;
+    run_somatic(ctx, *tumor, *normal, ranges, n_ranges, *params, *res, filters);
+    *out = res.release();
+  });
+}
+
 // pileupFlatMap(reads, ranges, true, pileupToAlleleCounts): the exact per-element walk over every requested locus
 static void run_allele_counts(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* ranges, size_t n_ranges, guac_result& res) {
   cudaStream_t st = ctx->stream;
@@ -1357,24 +1371,7 @@ size_t guac_somatic_genotype_filter(const guac_somatic_record* g, size_t n, cons
   if (!g || !p || !keep) return 0;
   size_t kept = 0;
   for (size_t i = 0; i < n; ++i) {
-    const guac_allele_evidence& t = g[i].tumor;
-    const guac_allele_evidence& nrm = g[i].normal;
-    // SomaticReadDepthFilter.withinReadDepthRange: min inclusive, max exclusive; the normal side has no upper bound
-    bool ok = t.read_depth >= p->min_tumor_read_depth && t.read_depth < p->max_tumor_read_depth &&
-              nrm.read_depth >= p->min_normal_read_depth && nrm.read_depth < 0x7FFFFFFF;
-    if (p->min_tumor_alternate_read_depth > 0) ok = ok && t.allele_read_depth >= p->min_tumor_alternate_read_depth;
-    const float vaf = (float)t.allele_read_depth / (float)t.read_depth;  // AlleleEvidence.variantAlleleFrequency (Float)
-    ok = ok && ((double)vaf * 100.0 > (double)p->min_vaf);
-    ok = ok && g[i].phred_scaled_somatic_likelihood >= p->min_likelihood;
-    if (!p->seq_overload) {
-      ok = ok && g[i].somatic_log_odds > (double)p->min_lod;
-      ok = ok && t.mean_mapping_quality >= (double)p->min_average_mapping_quality &&
-           nrm.mean_mapping_quality >= (double)p->min_average_mapping_quality;
-      // SomaticAverageBaseQualityFilter compares meanMappingQuality (sic) against the base-quality bound
-      ok = ok && t.mean_mapping_quality >= (double)p->min_average_base_quality &&
-           nrm.mean_mapping_quality >= (double)p->min_average_base_quality;
-      ok = ok && t.median_mismatches_per_read <= (double)p->max_median_mismatches;
-    }
+    const bool ok = somatic_filter_keep(g[i], *p);
     keep[i] = ok ? 1 : 0;
     kept += ok ? 1 : 0;
   }

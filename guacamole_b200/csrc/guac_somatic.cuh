@@ -1209,6 +1209,43 @@ __global__ void __launch_bounds__(kEvidenceWarps * 32) k_evidence(DevReads RT, D
 
 }  // namespace guac
 
+// ---- post-call filters in the epilogue: SomaticGenotypeFilter over the finished records, on the device, so that
+// filtered records never cross PCIe (filters/SomaticGenotypeFilter.scala:30-335, called from SomaticStandardCaller.scala:125-151)
+namespace guac {
+
+// SomaticReadDepthFilter (:69-75, upper bound exclusive, filters/GenotypeFilter.scala:63), SomaticAlternateReadDepthFilter
+// (:107-110), SomaticVAFFilter (:142-145, Float VAF), SomaticMinimumLikelihoodFilter (:38-41), and in the full overload
+// SomaticLogOddsFilter (:176-179), SomaticAverageMappingQualityFilter (:210-214), SomaticAverageBaseQualityFilter (:194-198 —
+// compares the MAPPING quality, kept as is), SomaticMedianMismatchFilter (:228-231)
+__host__ __device__ inline bool somatic_filter_keep(const guac_somatic_record& g, const guac_somatic_filter_params& p) {
+  const guac_allele_evidence& t = g.tumor;
+  const guac_allele_evidence& nrm = g.normal;
+  bool ok = t.read_depth >= p.min_tumor_read_depth && t.read_depth < p.max_tumor_read_depth && nrm.read_depth >= p.min_normal_read_depth &&
+            nrm.read_depth < 0x7FFFFFFF;
+  if (p.min_tumor_alternate_read_depth > 0) ok = ok && t.allele_read_depth >= p.min_tumor_alternate_read_depth;
+  const float vaf = (float)t.allele_read_depth / (float)t.read_depth;  // AlleleEvidence.variantAlleleFrequency (Float)
+  ok = ok && ((double)vaf * 100.0 > (double)p.min_vaf);
+  ok = ok && g.phred_scaled_somatic_likelihood >= p.min_likelihood;
+  if (!p.seq_overload) {
+    ok = ok && g.somatic_log_odds > (double)p.min_lod;
+    ok = ok && t.mean_mapping_quality >= (double)p.min_average_mapping_quality && nrm.mean_mapping_quality >= (double)p.min_average_mapping_quality;
+    ok = ok && t.mean_mapping_quality >= (double)p.min_average_base_quality && nrm.mean_mapping_quality >= (double)p.min_average_base_quality;
+    ok = ok && t.median_mismatches_per_read <= (double)p.max_median_mismatches;
+  }
+  return ok;
+}
+
+// thread per finished record: the ones that pass every filter are compacted into `kept` (counters[6])
+__global__ void __launch_bounds__(256) k_somatic_filter(SomOut out, guac_somatic_filter_params p, guac_somatic_record* __restrict__ kept) {
+  const uint32_t n = (uint32_t)min(out.counters[0], (unsigned long long)out.cap_rec);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const guac_somatic_record r = out.rec[i];
+    if (somatic_filter_keep(r, p)) kept[atomicAdd(&out.counters[6], 1ull)] = r;
+  }
+}
+
+}  // namespace guac
+
 // ---- host side ------------------------------------------------------------------------------------------------------------------------
 namespace {
 
@@ -1246,7 +1283,7 @@ void somatic_init_tables(guac_ctx* ctx) {
 }
 
 void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& normal, const guac_locus_range* ranges, size_t n_ranges,
-                 const guac_somatic_params& p, guac_result& res) {
+                 const guac_somatic_params& p, guac_result& res, const guac_somatic_filter_params* filters = nullptr) {
   if (tumor.n_contigs != normal.n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "tumor and normal samples have different sequence dictionaries");
   if (!tumor.has_qualities || !normal.has_qualities) fail(GUAC_ERR_UNSUPPORTED, "somatic-standard needs reads packed with base qualities");
   cudaStream_t st = ctx->stream;
@@ -1319,6 +1356,13 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
     CUDA_OK(cudaEventRecord(ctx->ev[1], st));
     k_somatic_exact<<<ctx->sm_count * 32, kSomExactWarps * 32, 0, st>>>(RT, RN, out.slow, prm, ctx->d_tables, out);
     k_evidence<<<ctx->sm_count * 12, kEvidenceWarps * 32, 0, st>>>(RT, RN, prm, out);
+    const guac_somatic_record* d_final = out.rec;
+    if (filters) {  // the post-call genotype filters, before anything crosses PCIe
+      ctx->sort_rec.ensure(cap_rec * sizeof(guac_somatic_record));
+      k_somatic_filter<<<ctx->sm_count * 2, 256, 0, st>>>(out, *filters, (guac_somatic_record*)ctx->sort_rec.p);
+      d_final = (const guac_somatic_record*)ctx->sort_rec.p;
+      res.stats.kernel_launches += 1;
+    }
     CUDA_OK(cudaEventRecord(ctx->ev[2], st));
     CUDA_OK(cudaGetLastError());
     unsigned long long* c = ctx->h_counters;
@@ -1336,7 +1380,7 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
       cap_pool = std::max<uint64_t>(cap_pool, kPoolDynOff + c[1] + c[1] / 8 + 16);
       continue;
     }
-    const uint64_t n_rec = c[0];
+    const uint64_t n_rec = filters ? c[6] : c[0];
     const size_t pool_bytes = (size_t)(kPoolDynOff + c[1]), rec_bytes = (size_t)(n_rec * sizeof(guac_somatic_record));
     const size_t rec_at = (pool_bytes + 63) & ~(size_t)63;
     res.pool = ctx->pinned;
@@ -1345,7 +1389,7 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
     unsigned char* hs = (unsigned char*)res.block;
     unsigned char* hrec = hs + rec_at;
     CUDA_OK(cudaMemcpyAsync(hs, ctx->out_pool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
-    if (n_rec) CUDA_OK(cudaMemcpyAsync(hrec, ctx->out_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
+    if (n_rec) CUDA_OK(cudaMemcpyAsync(hrec, d_final, rec_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
     res.stats.d2h_bytes = pool_bytes + rec_bytes + 64;
     res.records = hrec;

@@ -352,7 +352,12 @@ typedef struct guac_somatic_filter_params {   /* SomaticGenotypeFilterArguments 
   int32_t seq_overload;                    /* 1: the Seq[...] overload (:310-335: depth, VAF, likelihood, alternate depth only) */
   int32_t pad_;
 } guac_somatic_filter_params;
-/* keep[i] = 1 if records[i] passes every filter; returns the number kept. */
+/* pileupFlatMapTwoRDDs(...findPotentialVariantAtLocus...) followed by the genotype filters of SomaticStandardCaller.scala:125-151,
+ * applied on the device in the caller kernels' epilogue: records that fail a filter never cross PCIe. */
+guac_status guac_somatic_standard_filtered(guac_ctx* ctx, const guac_reads* tumor, const guac_reads* normal,
+                                           const guac_locus_range* ranges, size_t n_ranges, const guac_somatic_params* params,
+                                           const guac_somatic_filter_params* filters, guac_result** out);
+/* The same predicates over records already on the host: keep[i] = 1 if records[i] passes every filter; returns the number kept. */
 size_t guac_somatic_genotype_filter(const guac_somatic_record* records, size_t n, const guac_somatic_filter_params* params,
                                     uint8_t* keep);
 

@@ -209,3 +209,40 @@ def test_amplicon_shape_config5(ctx):
         assert [key(x) for x in g] == [key(x) for x in want]
         assert gc["depth"].tolist() == wc["depth"].tolist() and gc["reference_depth"].tolist() == wc["reference_depth"].tolist()
         assert int(gc["depth"].max()) > 9000
+
+
+# ---- SomaticStandardCallerSuite.scala:82-115 through the engine, genotype filters applied on the device -----------------------
+SUITE_FILTERS = dict(min_tumor_read_depth=8, max_tumor_read_depth=200, min_normal_read_depth=4, min_tumor_alternate_read_depth=3,
+                     min_lod=120, min_vaf=5, min_likelihood=70, seq_overload=True)
+SUITE_LOCI = [
+    ("tumor.chr20.tough", "normal.chr20.tough", "20",
+     [42999694, 25031215, 44061033, 45175149, 755754, 1843813, 3555766, 3868620, 9896926, 14017900, 17054263, 35951019, 50472935,
+      51858471, 58201903, 7087895, 19772181, 30430960, 32150541, 42186626, 44973412, 46814443, 52311925, 53774355, 57280858, 62262870], []),
+    ("synthetic.challenge.set1.tumor.v2.withMDTags.chr2.syn1fp", "synthetic.challenge.set1.normal.v2.withMDTags.chr2.syn1fp", "2",
+     [], [216094721, 3529313, 8789794, 104043280, 104175801, 126651101, 241901237, 57270796, 120757852]),
+    ("synthetic.challenge.set1.tumor.v2.withMDTags.chr2.complexvar", "synthetic.challenge.set1.normal.v2.withMDTags.chr2.complexvar", "2",
+     [82949713, 130919744], [148487667, 134307261, 90376213, 3638733, 109347468]),
+    ("tumor.chr20.simplefp", "normal.chr20.simplefp", "20", [], [26211835, 29652479, 54495768, 13046318, 25939088]),
+]
+
+
+@pytest.mark.parametrize("tumor_name,normal_name,contig,positive,negative", SUITE_LOCI)
+def test_suite_decisions_with_device_filters(ctx, tumor_name, normal_name, contig, positive, negative):
+    """The reference's 28 "variant found" and 19 "no variant" loci: findPotentialVariantAtLocus(odds 120) followed by
+    SomaticGenotypeFilter(Seq(...), 8, 200, 4, 3, 120, 5, 70), the filters running in the engine's epilogue
+    (guac_somatic_standard_filtered); the surviving records equal the host-side filter over the unfiltered call."""
+    from guacamole_b200 import callers
+    t, n = tn(tumor_name, normal_name)
+    c = t.contig_names.index(contig)
+    loci = sorted(positive + negative)
+    ranges = [(c, p, p + 1) for p in loci]
+    rt, rn = ctx.pack(t), ctx.pack(n)
+    kept = callers.somatic_standard(ctx, rt, rn, ranges, odds_threshold=120, min_alignment_quality=1, filters=SUITE_FILTERS)
+    everything = callers.somatic_standard(ctx, rt, rn, ranges, odds_threshold=120, min_alignment_quality=1)
+    rt.free()
+    rn.free()
+    found = {int(r["start"]) for r in kept.records}
+    assert found == set(positive), (sorted(found), sorted(positive))
+    mask = callers.somatic_genotype_filter(everything.records, **SUITE_FILTERS)
+    assert [g["start"] for g in kept.genotypes()] == [g["start"] for g, m in zip(everything.genotypes(), mask) if m]
+    assert len(kept) <= len(everything)
