@@ -565,6 +565,7 @@ uint64_t prepare_tiles(guac_ctx* ctx, const guac_reads& reads, const guac_locus_
   uint64_t requested = 0;
   for (size_t i = 0; i < n_ranges; ++i) requested += (uint64_t)std::max<int64_t>(0, ranges[i].end - ranges[i].start);
   if (!same) {
+    check_ranges_disjoint(ranges, n_ranges);
     std::vector<TileDesc> tiles;
     build_tiles(reads, ranges, n_ranges, tiles);
     uint64_t tl = 0;
@@ -1223,6 +1224,7 @@ static void run_allele_counts(guac_ctx* ctx, const guac_reads& reads, const guac
     if (r.start < 0 || r.end < r.start) fail(GUAC_ERR_INVALID_ARGUMENT, "locus range %zu: bad bounds", i);
     prefix[i + 1] = prefix[i] + (unsigned long long)(r.end - r.start);
   }
+  check_ranges_disjoint(ranges, n_ranges);
   const uint64_t requested = prefix[n_ranges];
   res.stats.reads_total = reads.n;
   res.stats.loci_requested = requested;

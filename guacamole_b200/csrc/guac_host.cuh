@@ -373,6 +373,21 @@ void sort_records_canonical(Rec* recs, size_t n, TieLess tie_less) {
   }
 }
 
+// The reference's LociSet merges overlapping ranges; here they are the caller's to merge: overlapping input would visit loci
+// twice and return duplicate records, so it is refused (GUAC_ERR_INVALID_ARGUMENT, as include/guac.h says).
+void check_ranges_disjoint(const guac_locus_range* ranges, size_t n_ranges) {
+  std::vector<std::tuple<int32_t, int64_t, int64_t>> v;
+  v.reserve(n_ranges);
+  for (size_t i = 0; i < n_ranges; ++i)
+    if (ranges[i].end > ranges[i].start) v.emplace_back(ranges[i].contig, ranges[i].start, ranges[i].end);
+  bool sorted = true;
+  for (size_t i = 1; i < v.size() && sorted; ++i) sorted = v[i - 1] <= v[i];
+  if (!sorted) std::sort(v.begin(), v.end());
+  for (size_t i = 1; i < v.size(); ++i)
+    if (std::get<0>(v[i]) == std::get<0>(v[i - 1]) && std::get<1>(v[i]) < std::get<2>(v[i - 1]))
+      fail(GUAC_ERR_INVALID_ARGUMENT, "loci ranges overlap (contig %d near locus %lld): merge them first", std::get<0>(v[i]), (long long)std::get<1>(v[i]));
+}
+
 int grid_for(uint64_t n, int block, int sm_count) {
   uint64_t g = (n + block - 1) / block;
   uint64_t cap = (uint64_t)sm_count * 32;

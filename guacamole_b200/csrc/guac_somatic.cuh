@@ -581,7 +581,10 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
   A.ref_depth = std_ref ? A.cnt[rcode] : 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) A.seen |= A.cnt[k] > 0 ? (1u << k) : 0u;
-  if (n_word_reads > 0xFFFFu) A.other += 1;  // the packed counters hold 16 bits: deeper pileups go to the exact kernel
+  if (n_word_reads > 0xFFFFu) {  // the packed counters hold 16 bits and may have wrapped: the exact kernel decides this word's
+    A.other += 1;                // loci, whatever the bounds computed from the wrapped counts would say
+    A.hard += 1;
+  }
   // S0 of the reference class = T0 - the other classes' S0 (every kept plain element is in exactly one class)
   double sr0 = A.t0;
 #pragma unroll
@@ -755,7 +758,10 @@ __device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t wo
   A.ref_depth = std_ref ? A.cnt[rcode] : 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) A.seen |= A.cnt[k] > 0 ? (1u << k) : 0u;
-  if (n_cols + n_rows > 0xFFFFu) A.other += 1;  // the packed counters hold 16 bits: deeper pileups go to the exact kernel
+  if (n_cols + n_rows > 0xFFFFu) {  // the packed counters (and the u16 depths) hold 16 bits: the exact kernel decides this
+    A.other += 1;                   // word's loci, whatever the bounds computed from wrapped counts would say
+    A.hard += 1;
+  }
   double sr0 = A.t0;  // S0 of the reference class = T0 - the other classes' S0
 #pragma unroll
   for (int k = 0; k < 4; ++k) sr0 -= A.s0[k];
@@ -1288,6 +1294,7 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
   if (!tumor.has_qualities || !normal.has_qualities) fail(GUAC_ERR_UNSUPPORTED, "somatic-standard needs reads packed with base qualities");
   cudaStream_t st = ctx->stream;
   // tiles over the union of both tracks: a locus past one sample's track simply holds no reads of that sample
+  check_ranges_disjoint(ranges, n_ranges);
   std::vector<TileDesc> tiles;
   uint64_t requested = 0;
   for (size_t i = 0; i < n_ranges; ++i) {

@@ -206,6 +206,7 @@ void run_standard(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range
                   guac_result& res) {
   if (!reads.has_qualities) fail(GUAC_ERR_UNSUPPORTED, "germline-standard needs reads packed with base qualities");
   cudaStream_t st = ctx->stream;
+  check_ranges_disjoint(ranges, n_ranges);
   std::vector<TileDesc> tiles;
   uint64_t requested = 0;
   for (size_t i = 0; i < n_ranges; ++i) {

@@ -57,6 +57,8 @@ def gather_records(records: np.ndarray, pool: bytes, dst: int = 0, group=None, d
     for r in range(world):
         n_rec_bytes, n_pool = int(all_sizes[r][0]), int(all_sizes[r][1])
         a = gathered[0][r][:n_rec_bytes].cpu().numpy().view(records.dtype).copy()
+        if base + n_pool >= 2 ** 32:
+            raise OverflowError("merged allele pools exceed the 32-bit offsets of the records: gather fewer ranks at a time")
         if len(a):
             a["ref_off"] += base
             a["alt_off"] += base

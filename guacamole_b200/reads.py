@@ -219,7 +219,10 @@ class ReadBatch:
 
     # ---- C view -----------------------------------------------------------------------------------------------------
     def to_c(self) -> abi.ReadBatchC:
-        """A guac_read_batch pointing at this batch's arrays (keep `self` alive while it is in use)."""
+        """A guac_read_batch pointing at this batch's arrays (keep `self` alive while it is in use).  The arrays the last call
+        pinned are released first: repeated packs of one batch do not pile references up."""
+        self._keep.clear()
+
         def ptr(a, t):
             a = np.ascontiguousarray(a)
             self._keep.append(a)

@@ -30,7 +30,10 @@ def vcf_lines(genotypes: Iterable[dict], contig_names: Sequence[str], sample_nam
     """Body lines (no header), sorted by (contig index, position, ref, alt).  `genotypes` = Result.genotypes()."""
     rows: Dict[tuple, Dict[int, Dict[str, str]]] = {}
     for g in genotypes:
-        alt = g["alt"] if g["alt"] else "<DEL>" if g["ref"] else "."  # an empty alternate has no VCF spelling of its own
+        # An empty alternate (a locus INSIDE a deletion: the reference's MidDeletion allele, ref = the deleted base, alt = "")
+        # is spelt with VCF 4.2's own allele for "missing due to an upstream deletion": "*".  (The deletion itself is the
+        # record at its anchor locus, REF = anchor + deleted bases.)  The reference does not pin the VCF text (SURVEY 8c).
+        alt = g["alt"] if g["alt"] else "*" if g["ref"] else "."
         if g["alt"] == "<ALT>":  # the symbolic allele of emit_ref / emit_no_call records
             alt = "."
         key = (g["contig"], g["start"], g["ref"] or "N", alt)
@@ -56,7 +59,6 @@ def write_vcf(path: str, genotypes: Iterable[dict], contig_names: Sequence[str],
         for i, name in enumerate(contig_names):
             ln = f",length={int(contig_lengths[i])}" if len(contig_lengths) > i else ""
             fh.write(f"##contig=<ID={name}{ln}>\n")
-        fh.write('##ALT=<ID=DEL,Description="Deleted base(s): the alternate allele is empty">\n')
         fh.write('##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">\n')
         fh.write('##FORMAT=<ID=GQ,Number=1,Type=Integer,Description="Phred-scaled genotype quality">\n')
         fh.write('##FORMAT=<ID=DP,Number=1,Type=Integer,Description="Read depth">\n')

@@ -416,3 +416,18 @@ def test_depth_histogram(ctx, difference_lists):
         reads.free()
         assert int(got.sum()) == sum(r[2] - r[1] for r in ranges)
         assert np.array_equal(got, want)
+
+
+def test_overlapping_ranges_are_refused(ctx):
+    """LociSet merges overlapping ranges; the C ABI asks the caller to (include/guac.h): overlapping input is refused."""
+    from guacamole_b200 import callers
+    from guacamole_b200._lib import GuacError
+    b = ReadBatch.from_records(UNIT_SETS["het_snv"]).sorted()
+    reads = ctx.pack(b)
+    for fn in (lambda r: callers.germline_threshold(ctx, reads, r), lambda r: callers.pileup_counts(ctx, reads, r),
+               lambda r: callers.allele_counts(ctx, reads, r)):
+        with pytest.raises(GuacError) as e:
+            fn([(0, 0, 6), (0, 4, 9)])
+        assert e.value.code == abi.ERR_INVALID_ARGUMENT
+        assert len(fn([(0, 4, 9), (0, 0, 4)])) > 0   # unordered but disjoint is fine
+    reads.free()

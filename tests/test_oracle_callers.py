@@ -428,7 +428,7 @@ def test_vcf_writer_on_chrm(tmp_path):
     # called alleles carry GQ / DP / AD; an empty alternate is spelled <DEL>
     dele = ReadBatch.from_records([make_read("TCGTCGA", "3M1D4M", "3^A4", 0)] * 3).sorted()
     cl = vcf.vcf_lines([dict(g, gt=(0, 1)) for g in orc.germline_standard(dele, [(0, 0, 64)]).called()], dele.contig_names, dele.sample_names)
-    assert [ln.split("\t")[1:5] for ln in cl] == [["3", ".", "GA", "G"], ["4", ".", "A", "<DEL>"]]
+    assert [ln.split("\t")[1:5] for ln in cl] == [["3", ".", "GA", "G"], ["4", ".", "A", "*"]]
     assert cl[0].split("\t")[8] == "GT:GQ:DP:AD" and cl[0].split("\t")[9] == "0/1:100:3:0,3"
 
 
