@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--depth", type=float, default=30.0)
     ap.add_argument("--cpu-window", type=int, default=4_000_000, help="loci of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--e2e-wide", dest="e2e_compact", action="store_false",
+                    help="end-to-end leg from the wide guac_read_batch (ASCII bases, 64-bit columns) instead of guac_read_batch_v2")
     ap.add_argument("--no-somatic", action="store_true", help="N = 1: leave the configs[2] block out")
     ap.add_argument("--seed", type=int, default=20261020)
     return ap.parse_args()
@@ -418,15 +420,20 @@ def main():
         for s, d in samples:
             dv = synth.generate_device(ctx, contigs, depth=d, read_length=READ_LEN, seed=args.seed, sample=s,
                                        windows=synth.shard_windows(e2e_ranges, READ_LEN), with_qualities=is_somatic)
-            hosts.append(dv.download(pinned=True))
+            wide = dv.download(pinned=not args.e2e_compact)
             dv.free()
+            if args.e2e_compact:  # what a shim fills straight from BAM records: 4-bit bases, 32-bit starts / offsets (guac_read_batch_v2)
+                hosts.append(callers.CompactBatch(wide.c, pinned=True, fixed_length=True))
+                wide.free()
+            else:
+                hosts.append(wide)
         h2d = d2h = n_touch = 0
         t1 = time.perf_counter()
         for i in range(1 + e2e_steps):
             if i == 1:
                 barrier()
                 t1 = time.perf_counter()
-            fresh = [ctx.pack_c(h.c, names) for h in hosts]
+            fresh = [ctx.pack_v2(h, names) if args.e2e_compact else ctx.pack_c(h.c, names) for h in hosts]
             r = call(fresh, e2e_ranges)
             if comm is not None and not is_somatic:
                 g = comm.gather(r, 0)
@@ -459,7 +466,8 @@ def main():
         blk = {"value": loci / (step_ms * 1e-3), "unit": "loci/s", "reads_per_sec": reads / (step_ms * 1e-3), "ms_per_step": step_ms,
                "loci": int(loci), "reads": int(reads), "records_per_step": int(o.get("total_records", recs)),
                "e2e": {"value": e2e_loci / (e2e_ms * 1e-3), "unit": "loci/s", "ms_per_step": e2e_ms, "loci": int(e2e_loci),
-                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": o["d2h"], "records_read": o["e2e_records"]},
+                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": o["d2h"], "records_read": o["e2e_records"],
+                       "input": "guac_read_batch_v2 (4-bit bases, 32-bit columns)" if args.e2e_compact else "guac_read_batch (ASCII bases, 64-bit columns)"},
                "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": measured_traffic(kernel, loci / world, args.depth), "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": alg / world, "kernel_ms": tile_ms, "other_kernels_ms": exact_ms,

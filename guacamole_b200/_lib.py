@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libguac_b200.so")
 EXPORTED = [
     "guac_abi_version", "guac_ctx_create", "guac_ctx_destroy", "guac_last_error", "guac_status_string",
     "guac_ctx_set_option", "guac_ctx_timer_start", "guac_ctx_timer_stop", "guac_host_register", "guac_host_unregister",
-    "guac_reads_pack", "guac_reads_pack_device", "guac_reads_free", "guac_reads_count", "guac_reads_device_bytes",
+    "guac_reads_pack", "guac_reads_pack_device", "guac_reads_pack_v2", "guac_read_batch_compact", "guac_host_batch_v2_view",
+    "guac_host_batch_v2_bytes", "guac_host_batch_v2_free", "guac_reads_free", "guac_reads_count", "guac_reads_device_bytes",
     "guac_reads_order_sensitive_loci", "guac_reads_h2d_bytes", "guac_reads_pack_kernel_ms", "guac_reads_expand_kernel_ms",
     "guac_germline_threshold", "guac_somatic_standard", "guac_somatic_standard_filtered", "guac_germline_standard", "guac_pileup_counts",
     "guac_allele_counts", "guac_result_allele_counts",
@@ -76,6 +77,14 @@ def lib():
     L.guac_reads_pack.argtypes = [vp, C.POINTER(abi.ReadBatchC), C.POINTER(abi.ReferenceC), C.POINTER(vp)]
     L.guac_reads_free.argtypes = [vp]
     L.guac_reads_pack_device.argtypes = [vp, C.POINTER(abi.ReadBatchC), C.POINTER(abi.ReferenceC), C.POINTER(vp)]
+    L.guac_reads_pack_v2.argtypes = [vp, C.POINTER(abi.ReadBatchV2C), C.POINTER(abi.ReferenceC), C.POINTER(vp)]
+    L.guac_read_batch_compact.argtypes = [C.POINTER(abi.ReadBatchC), C.c_int, C.c_int, C.POINTER(vp)]
+    L.guac_host_batch_v2_view.argtypes = [vp]
+    L.guac_host_batch_v2_view.restype = C.POINTER(abi.ReadBatchV2C)
+    L.guac_host_batch_v2_bytes.argtypes = [vp]
+    L.guac_host_batch_v2_bytes.restype = C.c_uint64
+    L.guac_host_batch_v2_free.argtypes = [vp]
+    L.guac_host_batch_v2_free.restype = None
     L.guac_reads_free.restype = None
     for f in ("guac_reads_count", "guac_reads_device_bytes", "guac_reads_order_sensitive_loci", "guac_reads_h2d_bytes"):
         getattr(L, f).argtypes = [vp]

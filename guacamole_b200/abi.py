@@ -60,6 +60,29 @@ class ReadBatchC(C.Structure):
     ]
 
 
+class ReadBatchV2C(C.Structure):
+    """guac_read_batch_v2: the columns at their BAM width (4-bit bases, 32-bit starts and offsets)."""
+    _fields_ = [
+        ("n_reads", C.c_uint64),
+        ("n_contigs", C.c_uint32),
+        ("read_length", C.c_uint32),
+        ("contig_length", C.POINTER(C.c_int64)),
+        ("contig_read_off", C.POINTER(C.c_uint64)),
+        ("start", C.POINTER(C.c_int32)),
+        ("cigar_off", C.POINTER(C.c_uint32)),
+        ("cigar", C.POINTER(C.c_uint32)),
+        ("seq_off", C.POINTER(C.c_uint32)),
+        ("seq4", C.POINTER(C.c_uint8)),
+        ("qual", C.POINTER(C.c_uint8)),
+        ("mapq", C.POINTER(C.c_uint8)),
+        ("flags", C.POINTER(C.c_uint8)),
+        ("md_off", C.POINTER(C.c_uint32)),
+        ("md", C.c_char_p),
+        ("sample", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 class ReferenceC(C.Structure):
     _fields_ = [
         ("n_contigs", C.c_uint32),

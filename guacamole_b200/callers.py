@@ -91,6 +91,10 @@ class Context:
         """guac_reads_pack_device: the batch's columns already live in this context's device memory."""
         return PackedReads(self, None, None, batch_c=batch_c, contig_names=contig_names, sample_names=sample_names, on_device=True)
 
+    def pack_v2(self, compact: "CompactBatch", contig_names=None, sample_names=None, reference=None) -> "PackedReads":
+        """guac_reads_pack_v2: a compact host batch (4-bit bases, 32-bit columns), widened on the device."""
+        return PackedReads(self, None, reference, batch_c=compact.c, contig_names=contig_names, sample_names=sample_names, v2=True)
+
     def pack_synth(self, device_batch) -> "PackedReads":
         """guac_reads_pack_synth: packs a synth.DeviceBatch, taking its large columns over instead of copying them."""
         return PackedReads(self, None, None, synth_batch=device_batch, contig_names=device_batch.contig_names,
@@ -100,11 +104,41 @@ class Context:
         return PackedReads(self, batch, reference)
 
 
+class CompactBatch:
+    """guac_host_batch_v2: a read batch converted to the compact columns (guac_read_batch_compact).  `source` is a ReadBatch or
+    a guac_read_batch (ctypes); it is only read during the conversion."""
+
+    def __init__(self, source, pinned: bool = False, fixed_length: bool = True):
+        self._h = C.c_void_p()
+        self.contig_names = list(getattr(source, "contig_names", []) or [])
+        self.sample_names = list(getattr(source, "sample_names", []) or ["default"])
+        b = source.to_c() if hasattr(source, "to_c") else source
+        rc = lib().guac_read_batch_compact(C.byref(b), int(pinned), int(fixed_length), C.byref(self._h))
+        if rc != abi.OK:
+            raise GuacError(rc, lib().guac_status_string(rc).decode())
+        self.c = lib().guac_host_batch_v2_view(self._h).contents
+
+    @property
+    def h2d_bytes(self) -> int:
+        return int(lib().guac_host_batch_v2_bytes(self._h))
+
+    def free(self):
+        if self._h:
+            lib().guac_host_batch_v2_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class PackedReads:
     """guac_reads: one sample's start-sorted reads packed into the device SoA (guac_reads_pack)."""
 
     def __init__(self, ctx: Context, batch: Optional[ReadBatch], reference: Optional[Sequence[bytes]] = None,
-                 batch_c=None, contig_names=None, sample_names=None, on_device=False, synth_batch=None):
+                 batch_c=None, contig_names=None, sample_names=None, on_device=False, synth_batch=None, v2=False):
         self.ctx = ctx
         self.contig_names = list(batch.contig_names if batch is not None else (contig_names or []))
         self.sample_names = list(batch.sample_names if batch is not None else (sample_names or ["default"]))
@@ -120,7 +154,7 @@ class PackedReads:
             data = np.frombuffer(b"".join(reference) or b"\0", dtype=np.uint8).copy()
             ref = abi.ReferenceC(len(reference), offs.ctypes.data_as(C.POINTER(C.c_uint64)),
                                  data.ctypes.data_as(C.POINTER(C.c_uint8)))
-        pack = lib().guac_reads_pack_device if on_device else lib().guac_reads_pack
+        pack = lib().guac_reads_pack_v2 if v2 else lib().guac_reads_pack_device if on_device else lib().guac_reads_pack
         ctx._check(pack(ctx._h, C.byref(b), C.byref(ref) if ref is not None else None, C.byref(self._h)))
 
     @property

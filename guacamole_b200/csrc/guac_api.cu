@@ -23,6 +23,7 @@
 #include "guac_standard.cuh"
 #include "guac_synth_device.cuh"
 #include "guac_comm.cuh"
+#include "guac_batch2.cuh"
 #include "../../include/guac_synth.h"
 
 namespace {
@@ -161,13 +162,33 @@ void settle_rows(guac_ctx* ctx, guac_reads& rd, uint64_t pairs, uint64_t groups)
 // `on_device`: the batch's column pointers are device memory of ctx's device (guac_reads_pack_device): no host -> device copies.
 // `adopt`: a generated device batch whose large columns (bases, qualities, CIGARs, MD tags, base offsets) the store takes
 // over instead of copying them (guac_reads_pack_synth): the whole-genome shards would not fit twice.
+// `b2`: the compact host batch (guac_reads_pack_v2): its columns are copied as they are and widened on the device, on the copy
+// stream (guac_batch2.cuh); `b` is then ignored.
 void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* ref, guac_reads& out, bool on_device,
-                guac_synth_device_batch* adopt = nullptr) {
+                guac_synth_device_batch* adopt = nullptr, const guac_read_batch_v2* b2 = nullptr) {
+  guac_read_batch shell{};
+  if (b2) {  // (the column pointers of `shell` stay null: every use below is behind !b2)
+    shell.n_reads = b2->n_reads;
+    shell.n_contigs = b2->n_contigs;
+    shell.contig_length = b2->contig_length;
+    b = &shell;
+    on_device = false;
+  }
   if (!b) fail(GUAC_ERR_INVALID_ARGUMENT, "null batch");
   const uint64_t n = b->n_reads;
   if (n >= 0xFFFFFFF0ull) fail(GUAC_ERR_UNSUPPORTED, "more than 2^32 reads in one read set: shard it");
   const bool need_qual = ctx->pack_qualities != 0;
-  if (n && (!b->contig || !b->start || !b->cigar_off || !b->seq_off || !b->seq || (need_qual && !b->qual) || !b->mapq || !b->flags || !b->md_off))
+  if (b2) {
+    if (n && (!b2->contig_read_off || !b2->start || !b2->cigar_off || (!b2->seq_off && !b2->read_length) || !b2->seq4 || (need_qual && !b2->qual) ||
+              !b2->mapq || !b2->flags || !b2->md_off))
+      fail(GUAC_ERR_INVALID_ARGUMENT, "null column in read batch");
+    if (n) {
+      if (b2->contig_read_off[0] != 0 || b2->contig_read_off[b2->n_contigs] != n) fail(GUAC_ERR_INVALID_ARGUMENT, "contig_read_off does not span the batch");
+      for (uint32_t c = 0; c < b2->n_contigs; ++c)
+        if (b2->contig_read_off[c] > b2->contig_read_off[c + 1]) fail(GUAC_ERR_CONTIG_ORDER, "contig_read_off descends at contig %u", c);
+      if (b2->read_length && (uint64_t)b2->read_length * n >= 0xFFFFFFFF00ull) fail(GUAC_ERR_UNSUPPORTED, "more than 2^37 bases in one read set: shard it");
+    }
+  } else if (n && (!b->contig || !b->start || !b->cigar_off || !b->seq_off || !b->seq || (need_qual && !b->qual) || !b->mapq || !b->flags || !b->md_off))
     fail(GUAC_ERR_INVALID_ARGUMENT, "null column in read batch");
   out.ctx = ctx;
   out.n = n;
@@ -178,8 +199,8 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   Trace tr("pack");
   nvtx_push("guac pack: copies + header kernel");
   cudaStream_t cs = ctx->copy_stream, st = ctx->stream;
-  CUDA_OK(cudaEventRecord(ctx->copy_ev[5], st));  // buffers handed back by earlier calls may still be in use there
-  CUDA_OK(cudaStreamWaitEvent(cs, ctx->copy_ev[5], 0));
+  CUDA_OK(cudaEventRecord(ctx->copy_ev[9], st));  // buffers handed back by earlier calls may still be in use there
+  CUDA_OK(cudaStreamWaitEvent(cs, ctx->copy_ev[9], 0));
   struct DrainOnError {  // a failed pack must not leave copies from the caller's buffers in flight
     guac_ctx* c;
     int pending = std::uncaught_exceptions();
@@ -200,6 +221,9 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
       CUDA_OK(cudaMemcpyAsync(&n_md, b->md_off + n, 8, cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaMemcpyAsync(&n_bases, b->seq_off + n, 8, cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
+    } else if (b2) {
+      n_ops = b2->cigar_off[n]; n_md = b2->md_off[n];
+      n_bases = b2->read_length ? (uint64_t)b2->read_length * n : (uint64_t)b2->seq_off[n];
     } else {
       n_ops = b->cigar_off[n]; n_md = b->md_off[n]; n_bases = b->seq_off[n];
     }
@@ -220,7 +244,16 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   HeaderArgs H{};
   H.n = n;
   H.n_contigs = b->n_contigs;
-  if (adopt && n) {
+  DevBuf<int32_t> t2_start;
+  DevBuf<uint32_t> t2_cigar_off, t2_seq_off, t2_md_off;
+  DevBuf<unsigned long long> t2_contig_off;
+  DevBuf<uint8_t> t2_seq4;
+  if (b2) {
+    bring(out.cigar, b2->cigar, (size_t)n_ops, 1);
+    bring(out.md, b2->md, (size_t)n_md, 16);
+    out.seq_off.alloc(n + 1);
+    if (!n) CUDA_OK(cudaMemsetAsync(out.seq_off.p, 0, sizeof(uint64_t), cs));
+  } else if (adopt && n) {
     out.cigar.adopt(adopt->cigar);
     out.seq_off.adopt(adopt->seq_off);
     out.md.adopt(adopt->md);
@@ -232,6 +265,36 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   if (on_device) {
     H.contig = b->contig; H.start = b->start; H.cigar_off = b->cigar_off; H.mapq = b->mapq; H.flags = b->flags;
     H.sample = b->sample; H.md_off = b->md_off;
+  } else if (b2 && n) {
+    bring(t2_start, b2->start, n, 0);
+    bring(t2_cigar_off, b2->cigar_off, n + 1, 0);
+    bring(t2_md_off, b2->md_off, n + 1, 0);
+    if (!b2->read_length) bring(t2_seq_off, b2->seq_off, n + 1, 0);
+    bring(t2_contig_off, reinterpret_cast<const unsigned long long*>(b2->contig_read_off), (size_t)b2->n_contigs + 1, 0);
+    bring(t_mapq, b2->mapq, n, 0);
+    bring(t_flags, b2->flags, n, 0);
+    t_contig.alloc(n);
+    t_start.alloc(n);
+    t_cigar_off.alloc(n + 1);
+    t_md_off.alloc(n + 1);
+    WidenArgs W{};
+    W.n = n;
+    W.n_contigs = b2->n_contigs;
+    W.read_length = b2->read_length;
+    W.contig_read_off = t2_contig_off.p;
+    W.start = t2_start.p;
+    W.cigar_off = t2_cigar_off.p;
+    W.seq_off = b2->read_length ? nullptr : t2_seq_off.p;
+    W.md_off = t2_md_off.p;
+    W.contig_w = t_contig.p;
+    W.start_w = reinterpret_cast<long long*>(t_start.p);
+    W.cigar_off_w = reinterpret_cast<unsigned long long*>(t_cigar_off.p);
+    W.seq_off_w = reinterpret_cast<unsigned long long*>(out.seq_off.p);
+    W.md_off_w = reinterpret_cast<unsigned long long*>(t_md_off.p);
+    k_widen_header<<<grid_for(n + 1, 256, ctx->sm_count), 256, 0, cs>>>(W);
+    CUDA_OK(cudaGetLastError());
+    H.contig = t_contig.p; H.start = t_start.p; H.cigar_off = t_cigar_off.p; H.mapq = t_mapq.p; H.flags = t_flags.p;
+    H.sample = nullptr; H.md_off = t_md_off.p;
   } else if (n) {
     bring(t_contig, b->contig, n, 0);
     bring(t_start, b->start, n, 0);
@@ -250,7 +313,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     CUDA_OK(cudaMemcpyAsync(d_contig_length.p, b->contig_length, b->n_contigs * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
     H.contig_length = d_contig_length.p;
   }
-  CUDA_OK(cudaEventRecord(ctx->copy_ev[4], cs));  // the small columns are on the device
+  CUDA_OK(cudaEventRecord(ctx->copy_ev[8], cs));  // the small columns are on the device
   const bool adopt_bases = adopt && n;
   if (adopt_bases) {
     if (need_qual && !adopt->qual.n) fail(GUAC_ERR_INVALID_ARGUMENT, "the generated batch holds no base qualities");
@@ -263,8 +326,9 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
       out.qual.alloc((size_t)n_bases + 64);
       CUDA_OK(cudaMemsetAsync(out.qual.p + n_bases, 0, 64, cs));
     }
+    if (b2) t2_seq4.alloc((size_t)(n_bases + 1) / 2 + 64);
   }
-  constexpr int kMaxCopyChunks = 4;
+  constexpr int kMaxCopyChunks = 8;
   const int n_copy_chunks = n >= 1000000 ? kMaxCopyChunks : 1;
   uint64_t chunk_read[kMaxCopyChunks + 1], chunk_byte[kMaxCopyChunks + 1];
   for (int k = 0; k <= n_copy_chunks; ++k) chunk_read[k] = n * (uint64_t)k / (uint64_t)n_copy_chunks;
@@ -272,12 +336,20 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     if (on_device) {  // (fixed offsets cannot be assumed: fetch the few chunk boundaries)
       for (int k = 0; k <= n_copy_chunks; ++k) CUDA_OK(cudaMemcpyAsync(&chunk_byte[k], b->seq_off + chunk_read[k], 8, cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
+    } else if (b2) {
+      for (int k = 0; k <= n_copy_chunks; ++k)
+        chunk_byte[k] = b2->read_length ? chunk_read[k] * (uint64_t)b2->read_length : (uint64_t)b2->seq_off[chunk_read[k]];
     } else {
       for (int k = 0; k <= n_copy_chunks; ++k) chunk_byte[k] = b->seq_off[chunk_read[k]];
     }
     for (int k = 0; k < n_copy_chunks; ++k) {
       const uint64_t o0 = chunk_byte[k], o1 = chunk_byte[k + 1];
-      if (o1 > o0 && !adopt_bases) {
+      if (o1 > o0 && b2) {  // the chunk's nibbles (whole bytes: a byte shared with a neighbour travels twice), widened where they land
+        const uint64_t q0 = o0 >> 1, q1 = (o1 + 1) >> 1;
+        CUDA_OK(cudaMemcpyAsync(t2_seq4.p + q0, b2->seq4 + q0, q1 - q0, kind, cs));
+        k_unpack_bases<<<(unsigned)std::min<uint64_t>(((o1 - o0) / 32 + 256) / 256, (uint64_t)ctx->sm_count * 8), 256, 0, cs>>>(t2_seq4.p, out.seq.p, o0, o1);
+        if (need_qual) CUDA_OK(cudaMemcpyAsync(out.qual.p + o0, b2->qual + o0, o1 - o0, kind, cs));
+      } else if (o1 > o0 && !adopt_bases) {
         CUDA_OK(cudaMemcpyAsync(out.seq.p + o0, b->seq + o0, o1 - o0, kind, cs));
         if (need_qual) CUDA_OK(cudaMemcpyAsync(out.qual.p + o0, b->qual + o0, o1 - o0, kind, cs));
       }
@@ -312,7 +384,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   H.contig_first = d_summary.p + 8;
   H.contig_last = d_summary.p + 8 + nc;
   H.contig_end = reinterpret_cast<long long*>(d_summary.p + 8 + 2 * nc);
-  CUDA_OK(cudaStreamWaitEvent(st, ctx->copy_ev[4], 0));
+  CUDA_OK(cudaStreamWaitEvent(st, ctx->copy_ev[8], 0));
   CUDA_OK(cudaEventRecord(ctx->ev[0], st));
   uint64_t pair_total = 0;
   float header_ms = 0;
@@ -346,7 +418,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   }
   out.max_ref_span = (int64_t)summary[1];
   memcpy(out.mapq_mask, &summary[4], sizeof out.mapq_mask);
-  out.sample = n ? (int32_t)(uint32_t)summary[2] : 0;
+  out.sample = b2 ? b2->sample : n ? (int32_t)(uint32_t)summary[2] : 0;
   std::vector<int64_t> contig_end(nc, 0);
   std::vector<uint64_t> contig_first(nc, ~0ull), contig_last(nc, 0);
   for (size_t c = 0; c < nc; ++c) {
@@ -422,6 +494,8 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   h2d(ctx, out.d_contigs, out.contigs.data(), out.contigs.size());
   CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
   out.h2d_bytes = on_device ? out.d_contigs.bytes() + out.fasta.bytes()
+                  : b2      ? n * (4 + 4 + 4 + (b2->read_length ? 0 : 4) + 1 + 1) + out.cigar.bytes() + (n_bases + 1) / 2 + out.qual.bytes() + out.md.bytes() +
+                                  out.d_contigs.bytes() + out.fasta.bytes()
                             : n * (4 + 8 + 8 + 8 + 1 + 1 + (b->sample ? 4 : 0) + 8) + out.cigar.bytes() + out.seq.bytes() + out.qual.bytes() +
                                   out.md.bytes() + out.d_contigs.bytes() + out.fasta.bytes();
 
@@ -463,13 +537,13 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
       const uint64_t nr = A.r_end - A.r_begin;
       CUDA_OK(cudaStreamWaitEvent(st, ctx->copy_ev[k], 0));
       k_pack_bases<<<(int)std::min<uint64_t>((nr + kPackReads - 1) / kPackReads, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(A);
-      k_md_track<0><<<grid_for(nr, 128, ctx->sm_count), 128, 0, st>>>(A);
+      k_md_track<<<grid_for(nr, 128, ctx->sm_count), 128, 0, st>>>(A);
       out.pack_launches += 2;
     }
     A.r_begin = 0;
     A.r_end = n;
     if (!ref) {
-      k_md_track<1><<<grid_for(n, 128, ctx->sm_count), 128, 0, st>>>(A);
+      k_track_finish<<<grid_for(word_off, 256, ctx->sm_count), 256, 0, st>>>(A, (uint32_t)word_off);
       k_resolve_conflicts<<<grid_for(word_off, 128, ctx->sm_count), 128, 0, st>>>(A, b->n_contigs);
       out.pack_launches += 2;
     }
@@ -1064,6 +1138,38 @@ guac_status guac_reads_pack(guac_ctx* ctx, const guac_read_batch* batch, const g
     *out = r.release();
   });
 }
+
+guac_status guac_reads_pack_v2(guac_ctx* ctx, const guac_read_batch_v2* batch, const guac_reference* ref, guac_reads** out) {
+  if (!ctx || !out || !batch) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    std::unique_ptr<guac_reads> r(new guac_reads());
+    try {
+      pack_reads(ctx, nullptr, ref, *r, false, nullptr, batch);
+    } catch (...) {
+      cudaStreamSynchronize(ctx->copy_stream);  // copies from the caller's buffers may still be in flight
+      cudaStreamSynchronize(ctx->stream);
+      throw;
+    }
+    *out = r.release();
+  });
+}
+
+guac_status guac_read_batch_compact(const guac_read_batch* batch, int pinned, int fixed_length, guac_host_batch_v2** out) {
+  if (!batch || !out) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  return guarded(nullptr, [&] {
+    std::unique_ptr<guac_host_batch_v2> h(new guac_host_batch_v2());
+    h->pinned = pinned != 0;
+    compact_batch(*batch, fixed_length != 0, *h);
+    *out = h.release();
+  });
+}
+
+const guac_read_batch_v2* guac_host_batch_v2_view(const guac_host_batch_v2* b) { return b ? &b->view : nullptr; }
+uint64_t guac_host_batch_v2_bytes(const guac_host_batch_v2* b) { return b ? b->bytes : 0; }
+void guac_host_batch_v2_free(guac_host_batch_v2* b) { delete b; }
 
 guac_status guac_reads_pack_device(guac_ctx* ctx, const guac_read_batch* device_batch, const guac_reference* ref, guac_reads** out) {
   if (!ctx || !out) return GUAC_ERR_INVALID_ARGUMENT;

@@ -188,7 +188,7 @@ struct guac_ctx {
   cudaStream_t stream3 = nullptr;       // ... and the ordering + egress of the compact records
   cudaEvent_t join_ev = nullptr, join3_ev = nullptr, seg_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;   // guac_reads_pack: host -> device copies, overlapped with the pack kernels
-  cudaEvent_t copy_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t copy_ev[10] = {};  // [0..7] chunks of bases on the device, [8] small columns there, [9] compute stream caught up
   std::string last_error;
   unsigned long long* d_counters = nullptr;  // 16 counters, then the DevError (kStatusBytes)
   DevError* d_err = nullptr;                 // = d_counters + 16

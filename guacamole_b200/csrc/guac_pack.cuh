@@ -12,7 +12,7 @@ namespace guac {
 
 struct PackArgs {
   DevReads R;            // const view
-  uint64_t r_begin, r_end;  // reads this launch handles (k_pack_bases, k_md_track<0>: launched per chunk of the host -> device copy)
+  uint64_t r_begin, r_end;  // reads this launch handles (k_pack_bases, k_md_track: launched per chunk of the host -> device copy)
   ReadRec* rec_w;        // writable aliases
   uint2* pairs_w;
   uint32_t* xmask_w;
@@ -389,8 +389,9 @@ __global__ void k_granule_max(PackArgs A, uint32_t n_grans) {
 }
 
 // ---- K_md_track: thread per read; MD-derived reference bases -> the per-contig reference track ---------------------------
-// MODE 0 builds (OR-merge, exact when all reads agree), MODE 1 verifies and marks the loci where they do not.
-template <int MODE>
+// Each bit of a locus' 2-bit base code is OR-merged into one of TWO planes — "some read says 1" (trk_lo / trk_hi) and "some read
+// says 0" (kept in trk_std / conflict until k_track_finish) — so that one walk both builds the track and finds the loci where
+// the reads' MD tags disagree (a bit that is set in both planes of a pair); k_track_finish derives the final planes.
 struct TrackVisitor {
   const PackArgs& A;
   const ContigInfo& ci;
@@ -406,14 +407,10 @@ struct TrackVisitor {
     if (ref_pos < 0 || ref_pos >= ci.length || !is_std_base(ch)) return;
     const uint32_t w = ci.word_off + (uint32_t)(ref_pos >> 5), bit = 1u << (ref_pos & 31);
     const uint32_t code = base_code(ch);
-    if (MODE == 0) {
-      if ((code & 1u) && !(A.trk_lo_w[w] & bit)) atomicOr(&A.trk_lo_w[w], bit);
-      if ((code & 2u) && !(A.trk_hi_w[w] & bit)) atomicOr(&A.trk_hi_w[w], bit);
-      if (!(A.trk_std_w[w] & bit)) atomicOr(&A.trk_std_w[w], bit);
-    } else {
-      uint32_t lo = (A.trk_lo_w[w] & bit) ? 1u : 0u, hi = (A.trk_hi_w[w] & bit) ? 2u : 0u;
-      if ((lo | hi) != code) atomicOr(&A.conflict_w[w], bit);
-    }
+    uint32_t* lo_plane = (code & 1u) ? A.trk_lo_w : A.trk_std_w;
+    uint32_t* hi_plane = (code & 2u) ? A.trk_hi_w : A.conflict_w;
+    if (!(lo_plane[w] & bit)) atomicOr(&lo_plane[w], bit);
+    if (!(hi_plane[w] & bit)) atomicOr(&hi_plane[w], bit);
   }
   __device__ bool run(int ref_pos, int read_pos, int k) {
     // k aligned bases whose reference base equals the read base: word-parallel merge of the read's planes
@@ -435,17 +432,14 @@ struct TrackVisitor {
       uint32_t bits = bit_range(ref_pos - wbase, ref_pos + k - wbase) & ~__funnelshift_r(xa, xb, sh);
       if (wbase + 32 > ci.length) bits &= bit_range(0, ci.length - wbase);
       const uint32_t lo = __funnelshift_r(pa.x, pb.x, sh) & bits, hi = __funnelshift_r(pa.y, pb.y, sh) & bits;
+      const uint32_t lo0 = bits & ~lo, hi0 = bits & ~hi;
       pa = pb;
       xa = xb;
       const uint32_t gw = ci.word_off + (uint32_t)w;
-      if (MODE == 0) {
-        if ((A.trk_lo_w[gw] & lo) != lo) atomicOr(&A.trk_lo_w[gw], lo);
-        if ((A.trk_hi_w[gw] & hi) != hi) atomicOr(&A.trk_hi_w[gw], hi);
-        if ((A.trk_std_w[gw] & bits) != bits) atomicOr(&A.trk_std_w[gw], bits);
-      } else {
-        const uint32_t diff = bits & ((lo ^ A.trk_lo_w[gw]) | (hi ^ A.trk_hi_w[gw]));
-        if (diff) atomicOr(&A.conflict_w[gw], diff);
-      }
+      if ((A.trk_lo_w[gw] & lo) != lo) atomicOr(&A.trk_lo_w[gw], lo);
+      if ((A.trk_hi_w[gw] & hi) != hi) atomicOr(&A.trk_hi_w[gw], hi);
+      if ((A.trk_std_w[gw] & lo0) != lo0) atomicOr(&A.trk_std_w[gw], lo0);
+      if ((A.conflict_w[gw] & hi0) != hi0) atomicOr(&A.conflict_w[gw], hi0);
     }
     return true;
   }
@@ -456,29 +450,34 @@ struct TrackVisitor {
   }
   __device__ bool deleted(int ref_pos, uint8_t ch, int md_pos) {
     put_base(ref_pos, ch);
-    if (MODE == 0) {  // remember the read's first deletion for the exact per-locus path
-      if (del_first < 0) { del_first = ref_pos; del_md_pos = md_pos; del_n = 1; }
-      else if (ref_pos == del_first + del_n && md_pos == del_md_pos + del_n) ++del_n;
-    }
+    // remember the read's first deletion for the exact per-locus path
+    if (del_first < 0) { del_first = ref_pos; del_md_pos = md_pos; del_n = 1; }
+    else if (ref_pos == del_first + del_n && md_pos == del_md_pos + del_n) ++del_n;
     return true;
   }
   __device__ bool skipped(int, int) { return true; }
 };
 
-template <int MODE>
 __global__ void __launch_bounds__(128) k_md_track(PackArgs A) {
   for (uint64_t r = A.r_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < A.r_end; r += (uint64_t)gridDim.x * blockDim.x) {
     const ContigInfo ci = A.R.contigs[A.read_contig[r]];
     const ReadRec rec = A.R.rec[r];
-    TrackVisitor<MODE> v(A, ci, r, rec.pair_off, (rec.info & kInfoHasExc) != 0);
+    TrackVisitor v(A, ci, r, rec.pair_off, (rec.info & kInfoHasExc) != 0);
     int rc = md_walk(A.R, r, v);
     if (rc) report_error(A.err, rc, r);
-    if (MODE == 0) {
-      A.nm_w[r] = (uint16_t)min(v.n_mismatch, 65535);
-      A.del_start_w[r] = v.del_first;
-      A.del_md_w[r] = (uint32_t)v.del_md_pos;
-      A.del_len_w[r] = (uint16_t)min(v.del_n, 65535);
-    }
+    A.nm_w[r] = (uint16_t)min(v.n_mismatch, 65535);
+    A.del_start_w[r] = v.del_first;
+    A.del_md_w[r] = (uint32_t)v.del_md_pos;
+    A.del_len_w[r] = (uint16_t)min(v.del_n, 65535);
+  }
+}
+
+// thread per track word: the "says 0" planes become the standard-base plane and the plane of disagreeing loci
+__global__ void __launch_bounds__(256) k_track_finish(PackArgs A, uint32_t n_words) {
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
+    const uint32_t lo1 = A.trk_lo_w[w], hi1 = A.trk_hi_w[w], lo0 = A.trk_std_w[w], hi0 = A.conflict_w[w];
+    A.trk_std_w[w] = lo1 | lo0;
+    A.conflict_w[w] = (lo1 & lo0) | (hi1 & hi0);
   }
 }
 

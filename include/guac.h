@@ -87,6 +87,32 @@ typedef struct guac_read_batch {
   const char* md;                /* MD tag strings, not NUL-terminated                                           */
 } guac_read_batch;
 
+/* The same reads in the compact form they have in a BAM record (what Read.fromSAMRecord, reads/Read.scala:217-291, decodes
+ * FROM): half the bytes of guac_read_batch cross PCIe.  Bases are 4-bit codes into "=ACMGRSVTWYHKDBN" (SAM spec 4.2.3),
+ * packed back to back over the whole batch: base g (= seq_off[i] + j for base j of read i) is the HIGH nibble of
+ * seq4[g / 2] when g is even, the low nibble when odd.  Starts are 32-bit, offsets 32-bit (a batch holds fewer than 2^32
+ * bases, CIGAR ops and MD bytes: split larger ones), reads of one contig are one run of the batch (contig_read_off) and the
+ * batch holds one sample.  Bases outside the sixteen letters (lower case, '.', ...) need guac_read_batch. */
+typedef struct guac_read_batch_v2 {
+  uint64_t n_reads;
+  uint32_t n_contigs;
+  uint32_t read_length;            /* != 0: every read holds exactly this many bases; seq_off is then ignored (may be NULL) */
+  const int64_t* contig_length;    /* [n_contigs] or NULL                                                           */
+  const uint64_t* contig_read_off; /* [n_contigs + 1] reads of contig c are [off[c], off[c+1]); off[n_contigs] = n  */
+  const int32_t* start;            /* [n] 0-based inclusive, ascending within a contig                              */
+  const uint32_t* cigar_off;       /* [n+1]                                                                         */
+  const uint32_t* cigar;           /* BAM-encoded ops                                                               */
+  const uint32_t* seq_off;         /* [n+1] in bases (or NULL with read_length)                                     */
+  const uint8_t* seq4;             /* (bases + 1) / 2 bytes                                                         */
+  const uint8_t* qual;             /* one byte per base, numeric phred; NULL allowed when GUAC_OPT_PACK_QUALITIES=0 */
+  const uint8_t* mapq;             /* [n]                                                                           */
+  const uint8_t* flags;            /* [n] GUAC_READ_* bits                                                          */
+  const uint32_t* md_off;          /* [n+1]                                                                         */
+  const char* md;
+  int32_t sample;                  /* the batch's sample index                                                      */
+  int32_t reserved;
+} guac_read_batch_v2;
+
 /* optional FASTA-derived reference (ReferenceGenome.getReferenceBase, DistributedUtil.scala:266) */
 typedef struct guac_reference {
   uint32_t n_contigs;
@@ -284,6 +310,18 @@ guac_status guac_reads_pack(guac_ctx* ctx, const guac_read_batch* batch, const g
 /* Same, for a batch whose column pointers are DEVICE memory of ctx's device (n_reads, n_contigs and contig_length stay on the
  * host): no host -> device copies; the per-read checks and derived columns are computed by the same kernels either way. */
 guac_status guac_reads_pack_device(guac_ctx* ctx, const guac_read_batch* device_batch, const guac_reference* ref, guac_reads** out);
+/* Same as guac_reads_pack for the compact batch: the columns cross PCIe as they are and are widened on the device (the
+ * nibbles to the ASCII bases the store keeps, chunk by chunk underneath the copies); identical store, identical records. */
+guac_status guac_reads_pack_v2(guac_ctx* ctx, const guac_read_batch_v2* batch, const guac_reference* ref, guac_reads** out);
+/* Host-side conversion guac_read_batch -> guac_read_batch_v2 (what a JVM shim does straight from SAMRecord; here for tests,
+ * the C driver and the bench).  `pinned` != 0 page-locks the buffers.  GUAC_ERR_INVALID_ARGUMENT when a base is outside
+ * "=ACMGRSVTWYHKDBN", the reads hold several samples or are not grouped by contig; GUAC_ERR_UNSUPPORTED when an offset or a
+ * start needs more than 32 bits.  `fixed_length` != 0 stores read_length instead of seq_off when every read has that many bases. */
+typedef struct guac_host_batch_v2 guac_host_batch_v2;
+guac_status guac_read_batch_compact(const guac_read_batch* batch, int pinned, int fixed_length, guac_host_batch_v2** out);
+const guac_read_batch_v2* guac_host_batch_v2_view(const guac_host_batch_v2* b);
+uint64_t guac_host_batch_v2_bytes(const guac_host_batch_v2* b);   /* bytes guac_reads_pack_v2 will copy for it (with qualities) */
+void guac_host_batch_v2_free(guac_host_batch_v2* b);
 void guac_reads_free(guac_reads* reads);
 uint64_t guac_reads_count(const guac_reads* reads);
 uint64_t guac_reads_device_bytes(const guac_reads* reads);

@@ -154,3 +154,31 @@ def test_plain_c_consumer_builds_and_runs(tmp_path):
     r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "abi_driver ok" in r.stdout
+
+
+def test_compact_batch_conversion():
+    """guac_read_batch_compact (host only): the columns at BAM width hold what the wide batch held."""
+    from guacamole_b200 import callers
+    from guacamole_b200.reads import ReadBatch, make_read
+    recs = [make_read("TCGATCGAN", "9M", "9", 1, chr="a"), make_read("=CMGRSVTWYHKDBNAA", "17M", "17", 4, chr="a", alignment_quality=7),
+            make_read("ACG", "3M", "3", 2, chr="c", is_positive_strand=False)]
+    b = ReadBatch.from_records(recs, contig_names=["a", "b", "c"])
+    cb = callers.CompactBatch(b, fixed_length=True)
+    v = cb.c
+    assert v.n_reads == 3 and v.n_contigs == 3 and v.read_length == 0  # (unequal lengths: the offsets stay)
+    assert [v.contig_read_off[i] for i in range(4)] == [0, 2, 2, 3]
+    assert [v.start[i] for i in range(3)] == [int(x) for x in b.start]
+    assert [v.seq_off[i] for i in range(4)] == [0, 9, 26, 29]
+    letters = "=ACMGRSVTWYHKDBN"
+    bases = "".join(letters[(v.seq4[g >> 1] >> (0 if g & 1 else 4)) & 15] for g in range(29))
+    assert bases == "TCGATCGAN" + "=CMGRSVTWYHKDBNAA" + "ACG"
+    assert [v.mapq[i] for i in range(3)] == [30, 7, 30] and [v.flags[i] for i in range(3)] == [int(x) for x in b.flags]
+    assert [v.qual[i] for i in range(29)] == [int(x) for x in b.qual]
+    assert cb.h2d_bytes == 3 * (4 + 4 + 4 + 4 + 1 + 1) + 3 * 4 + 15 + 29 + int(b.md_off[-1])
+    cb.free()
+    same = ReadBatch.from_records([make_read("ACGT", "4M", "4", 1), make_read("ACGA", "4M", "3T0", 2)])
+    cb = callers.CompactBatch(same, fixed_length=True)
+    assert cb.c.read_length == 4 and not cb.c.seq_off
+    cb.free()
+    with pytest.raises(callers.GuacError):
+        callers.CompactBatch(ReadBatch.from_records([make_read("ACgT", "4M", "4", 1)]))

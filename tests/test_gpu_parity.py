@@ -307,15 +307,15 @@ def test_allele_counts_and_variant_loci(ctx):  # VariantSupport / V
 
 
 def test_chunked_pack_above_a_million_reads(ctx):
-    """guac_reads_pack copies the bases of >= 1,000,000 reads in four chunks and runs k_pack_bases / k_md_track<0> per chunk
-    as they land: parity in windows around the chunk boundaries (reads n/4, n/2, 3n/4) and at both ends."""
+    """guac_reads_pack copies the bases of >= 1,000,000 reads in eight chunks and runs k_pack_bases / k_md_track per chunk
+    as they land: parity in windows around chunk boundaries (reads n/8, n/4, n/2, 3n/4) and at both ends."""
     from guacamole_b200 import synth
     L = 5_300_000
     b = synth.generate([("20", L)], depth=30, seed=4242, sample=0).to_read_batch()
     assert len(b) >= 1_000_000
     ranges = [(0, 0, 30_000)]
-    for k in (1, 2, 3):
-        s = int(b.start[len(b) * k // 4])
+    for k in (1, 2, 4, 6):
+        s = int(b.start[len(b) * k // 8])
         ranges.append((0, max(0, s - 20_000), s + 20_000))
     ranges.append((0, L - 30_000, L - 1))
     assert_threshold_equal(ctx, b, ranges)
@@ -431,3 +431,71 @@ def test_overlapping_ranges_are_refused(ctx):
         assert e.value.code == abi.ERR_INVALID_ARGUMENT
         assert len(fn([(0, 4, 9), (0, 0, 4)])) > 0   # unordered but disjoint is fine
     reads.free()
+
+
+def _same_results(ctx, batch, ranges, reference=None):
+    """The compact batch (guac_reads_pack_v2) packs into the same store as the wide one: identical results."""
+    from guacamole_b200 import callers
+    wide = ctx.pack(batch, reference)
+    cb = callers.CompactBatch(batch, fixed_length=True)
+    compact = ctx.pack_v2(cb, batch.contig_names, batch.sample_names, reference=reference)
+    assert compact.n_reads == wide.n_reads
+    assert compact.h2d_bytes < wide.h2d_bytes or len(batch) == 0
+    n = 0
+    for thr, emit in ((8, False), (0, True)):
+        a = callers.germline_threshold(ctx, wide, ranges, threshold=thr, emit_ref=emit, emit_no_call=emit)
+        b = callers.germline_threshold(ctx, compact, ranges, threshold=thr, emit_ref=emit, emit_no_call=emit)
+        # (general records pool their allele strings in the order the warps finish: compare the decoded records)
+        assert a.genotypes() == b.genotypes() and a.stats["loci_visited"] == b.stats["loci_visited"]
+        n += len(a)
+    a, b = callers.pileup_counts(ctx, wide, ranges), callers.pileup_counts(ctx, compact, ranges)
+    assert np.array_equal(a.records, b.records)
+    a, b = callers.germline_standard(ctx, wide, ranges), callers.germline_standard(ctx, compact, ranges)
+    assert a.genotypes() == b.genotypes()  # (allele strings are pooled in the order the warps finish: compare the decoded records)
+    wide.free()
+    compact.free()
+    cb.free()
+    return n
+
+
+@pytest.mark.parametrize("name", sorted(UNIT_SETS))
+def test_compact_batch_unit_sets(ctx, name):
+    b = ReadBatch.from_records(UNIT_SETS[name]).sorted()
+    assert _same_results(ctx, b, [(0, 0, 6000)]) > 0
+
+
+def test_compact_batch_real_and_synthetic(ctx):
+    from guacamole_b200 import callers, synth
+    from guacamole_b200._lib import GuacError
+    chrm = load_golden("chrM.sorted").filtered(non_duplicate=True, passed_qc=True, has_md=True).sorted()
+    assert _same_results(ctx, chrm, [(chrm.contig_names.index("chrM"), 0, 16571)]) >= 138
+    # several contigs (one of them empty), reads of unequal length (seq_off stays), above the chunked-copy limit
+    contigs = [("1", 2_700_000), ("2", 900), ("4", 2_600_000)]
+    b = synth.generate(contigs, depth=30, seed=515, sample=0).to_read_batch()
+    assert len(b) >= 1_000_000
+    ranges = [(0, 0, 40_000), (0, 2_650_000, 2_700_000), (1, 0, 900), (2, 0, 50_000), (2, 2_560_000, 2_600_000)]
+    for k in (1, 2, 3):
+        i = len(b) * k // 4
+        s, c = int(b.start[i]), int(b.contig[i])
+        ranges.append((c, s + 60_000, s + 90_000) if k == 2 and c == 0 else (c, max(50_000, s - 15_000), s + 15_000))
+    ranges = [r for r in ranges if r[2] > r[1]]
+    assert _same_results(ctx, b, ranges) > 300
+    reference = [bytes(np.random.default_rng(3).choice(np.frombuffer(b"ACGT", np.uint8), n).tobytes()) for _, n in contigs[:2]]
+    small = synth.generate(contigs[1:2] + contigs[1:2], depth=20, seed=5, sample=0).to_read_batch()
+    assert _same_results(ctx, small, [(0, 0, 900), (1, 0, 900)], reference=[reference[1], reference[1]]) > 0
+    # what the compact form cannot hold is refused by the converter, not mangled
+    lower = ReadBatch.from_records([make_read("acgtACGT", "8M", "8", 1)])
+    with pytest.raises(GuacError) as e:
+        callers.CompactBatch(lower)
+    assert e.value.code == abi.ERR_INVALID_ARGUMENT
+    two = ReadBatch.from_records([make_read("ACGT", "4M", "4", 1, sample="a"), make_read("ACGT", "4M", "4", 2, sample="b")])
+    with pytest.raises(GuacError) as e:
+        callers.CompactBatch(two)
+    assert e.value.code == abi.ERR_INVALID_ARGUMENT
+    empty = callers.CompactBatch(ReadBatch.from_records([], contig_names=["1"]))
+    r = ctx.pack_v2(empty, ["1"], ["s"])
+    assert r.n_reads == 0 and len(callers.germline_threshold(ctx, r, [(0, 0, 100)])) == 0
+    # a contig without reads between two that have some
+    gap = ReadBatch.from_records([make_read("TCGATCGA", "8M", "8", 1, chr="a"), make_read("GCGATCGA", "8M", "0T7", 1, chr="a"),
+                                  make_read("GCGATCGA", "8M", "0T7", 3, chr="c")], contig_names=["a", "b", "c"])
+    assert _same_results(ctx, gap, [(0, 0, 50), (1, 0, 50), (2, 0, 50)]) > 0

@@ -246,3 +246,19 @@ def test_suite_decisions_with_device_filters(ctx, tumor_name, normal_name, conti
     mask = callers.somatic_genotype_filter(everything.records, **SUITE_FILTERS)
     assert [g["start"] for g in kept.genotypes()] == [g["start"] for g, m in zip(everything.genotypes(), mask) if m]
     assert len(kept) <= len(everything)
+
+
+def test_compact_batch_somatic(ctx):
+    """guac_reads_pack_v2 (4-bit bases, 32-bit columns) gives the store of guac_reads_pack: byte-identical somatic records."""
+    from guacamole_b200 import callers
+    t, n = tn(*FIXTURES[0][:2])
+    c = t.contig_names.index(FIXTURES[0][2])
+    hi = int(max(t.end().max(), n.end().max())) + 10
+    wide = [ctx.pack(t), ctx.pack(n)]
+    cbs = [callers.CompactBatch(t, fixed_length=False), callers.CompactBatch(n)]
+    compact = [ctx.pack_v2(cbs[0], t.contig_names, t.sample_names), ctx.pack_v2(cbs[1], n.contig_names, n.sample_names)]
+    a = callers.somatic_standard(ctx, wide[0], wide[1], [(c, 0, hi)], odds_threshold=20)
+    b = callers.somatic_standard(ctx, compact[0], compact[1], [(c, 0, hi)], odds_threshold=20)
+    assert len(a) > 20 and a.genotypes() == b.genotypes()
+    for r in wide + compact:
+        r.free()
