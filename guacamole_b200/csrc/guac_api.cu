@@ -191,6 +191,7 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   } else if (n && (!b->contig || !b->start || !b->cigar_off || !b->seq_off || !b->seq || (need_qual && !b->qual) || !b->mapq || !b->flags || !b->md_off))
     fail(GUAC_ERR_INVALID_ARGUMENT, "null column in read batch");
   out.ctx = ctx;
+  out.device = ctx->device;
   out.n = n;
   out.n_contigs = b->n_contigs;
   if (b->n_contigs == 0 && n) fail(GUAC_ERR_INVALID_ARGUMENT, "reads without contigs");
@@ -474,7 +475,8 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   const bool want_rows = n && ctx->difference_lists && out.has_qualities;
   if (want_rows) {  // column pairs: ~1.3 slots per base (a word's columns run to its deepest locus); rows: the few general reads
     out.total_words = word_off;
-    alloc_rows(out, (uint64_t)((double)n_bases * 1.3 / 256.0) + word_off + 1024, n / 4 + 1024);
+    // (at most one partly filled block per word that holds reads: a sparse read set over a large dictionary pays for its reads)
+    alloc_rows(out, (uint64_t)((double)n_bases * 1.3 / 256.0) + std::min<uint64_t>(word_off, n * 8) + 1024, n / 4 + 1024);
   }
   // (everything is allocated: from here to the last pack kernel the device works without waiting for the host)
   CUDA_OK(cudaEventRecord(ctx->ev[0], st));
@@ -632,7 +634,7 @@ void set_all_smem_attrs() {
 
 // the tile list of (reads, ranges) is cached in the context: a repeated call does not rebuild or re-upload it
 uint64_t prepare_tiles(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* ranges, size_t n_ranges, uint64_t* tile_loci) {
-  bool same = ctx->tiles_key_reads == (const void*)&reads && ctx->tiles_key_ranges.size() == n_ranges;
+  bool same = ctx->tiles_key_reads == reads.id && ctx->tiles_key_ranges.size() == n_ranges;
   for (size_t i = 0; same && i < n_ranges; ++i)
     same = ctx->tiles_key_ranges[i].contig == ranges[i].contig && ctx->tiles_key_ranges[i].start == ranges[i].start &&
            ctx->tiles_key_ranges[i].end == ranges[i].end;
@@ -653,7 +655,7 @@ uint64_t prepare_tiles(guac_ctx* ctx, const guac_reads& reads, const guac_locus_
     for (size_t i = 1; i < tiles.size() && ctx->tiles_in_order; ++i)
       ctx->tiles_in_order = std::make_pair(tiles[i - 1].contig, tiles[i - 1].locus_begin) < std::make_pair(tiles[i].contig, tiles[i].locus_begin);
     ctx->tiles_key_loci = tl;
-    ctx->tiles_key_reads = (const void*)&reads;
+    ctx->tiles_key_reads = reads.id;
     ctx->tiles_key_ranges.assign(ranges, ranges + n_ranges);
   }
   *tile_loci = ctx->tiles_key_loci;
@@ -1234,7 +1236,7 @@ void guac_synth_device_batch_totals(const guac_synth_device_batch* b, uint64_t* 
 }
 void guac_synth_device_batch_free(guac_synth_device_batch* b) {
   if (!b) return;
-  if (b->ctx) cudaSetDevice(b->ctx->device);
+  cudaSetDevice(b->device);
   delete b;
 }
 guac_status guac_synth_device_batch_download(guac_ctx* ctx, const guac_synth_device_batch* b, int pinned, guac_synth_host_batch** out) {
@@ -1253,10 +1255,7 @@ void guac_synth_host_batch_free(guac_synth_host_batch* b) { delete b; }
 
 void guac_reads_free(guac_reads* reads) {
   if (!reads) return;
-  if (reads->ctx) {
-    cudaSetDevice(reads->ctx->device);
-    if (reads->ctx->tiles_key_reads == (const void*)reads) reads->ctx->tiles_key_reads = nullptr;
-  }
+  cudaSetDevice(reads->device);  // (ids are never reused: a tile list cached for this read set can never match another one)
   delete reads;
 }
 uint64_t guac_reads_count(const guac_reads* reads) { return reads ? reads->n : 0; }
@@ -1581,6 +1580,7 @@ guac_status guac_comm_create(guac_ctx* ctx, const uint8_t* id, int rank, int wor
     CUDA_OK(cudaSetDevice(ctx->device));
     std::unique_ptr<guac_comm> c(new guac_comm());
     c->ctx = ctx;
+    c->device = ctx->device;
     c->rank = rank;
     c->world = world;
     ncclUniqueId u;
@@ -1594,7 +1594,7 @@ guac_status guac_comm_create(guac_ctx* ctx, const uint8_t* id, int rank, int wor
 
 void guac_comm_destroy(guac_comm* c) {
   if (!c) return;
-  if (c->ctx) cudaSetDevice(c->ctx->device);
+  cudaSetDevice(c->device);
   if (c->comm) ncclCommDestroy(c->comm);
   if (c->h_sizes) cudaFreeHost(c->h_sizes);
   delete c;

@@ -24,6 +24,7 @@
 
 struct guac_comm {
   guac_ctx* ctx = nullptr;
+  int device = 0;
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   DevBuf<unsigned long long> d_sizes;      // [6 * world] after the all-gather, + 6 for the local row

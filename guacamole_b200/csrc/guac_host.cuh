@@ -2,6 +2,7 @@
 // results.  (Internal; the public contract is include/guac.h.)
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -208,7 +209,7 @@ struct guac_ctx {
   DevBuf<uint32_t> sort_bins;
   DevBuf<uint64_t> scan_totals;
   std::vector<guac_locus_range> tiles_key_ranges;
-  const void* tiles_key_reads = nullptr;
+  uint64_t tiles_key_reads = 0;  // guac_reads::id of the cached tile list (0 = none)
   uint64_t tiles_key_loci = 0, n_tiles = 0;
   bool pool_head_ready = false, tiles_in_order = true;
   // pinned host staging for result downloads (grow-only)
@@ -227,9 +228,19 @@ struct guac_ctx {
 
 namespace {
 
+// GUAC_DEBUG_STALE=1: report a CUDA error some call left pending (cudaGetLastError is otherwise only consulted after launches)
+// An error some earlier runtime call of this thread left pending (ours or another library's: the runtime's error state is per
+// thread, not per library) must not be blamed on the first launch that asks: it is cleared on entry to every API call.
+inline void report_stale_error(const char* when) {
+  static const bool on = getenv("GUAC_DEBUG_STALE") != nullptr;
+  const cudaError_t e = cudaGetLastError();
+  if (on && e != cudaSuccess) fprintf(stderr, "[guac] pending CUDA error %s an API call: %s\n", when, cudaGetErrorString(e));
+}
+
 template <typename F>
 guac_status guarded(guac_ctx* ctx, F&& f) {
   try {
+    report_stale_error("before");
     f();
     return GUAC_OK;
   } catch (const StatusError& e) {
@@ -397,8 +408,15 @@ int grid_for(uint64_t n, int block, int sm_count) {
 }  // namespace
 
 // ---- packed read store ---------------------------------------------------------------------------------------------------
+inline uint64_t next_object_id() {
+  static std::atomic<uint64_t> counter{0};
+  return ++counter;
+}
+
 struct guac_reads {
-  guac_ctx* ctx = nullptr;
+  guac_ctx* ctx = nullptr;      // (never dereferenced when the read set is freed: a context may be destroyed first)
+  int device = 0;
+  uint64_t id = next_object_id();
   uint64_t n = 0;
   uint32_t n_contigs = 0;
   int32_t sample = 0;

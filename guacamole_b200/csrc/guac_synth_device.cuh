@@ -210,6 +210,7 @@ uint64_t device_exclusive_scan(guac_ctx* ctx, const uint32_t* in, uint64_t n, Ou
 
 struct guac_synth_device_batch {
   guac_ctx* ctx = nullptr;
+  int device = 0;
   std::vector<int64_t> contig_length;
   DevBuf<int64_t> start;
   DevBuf<int32_t> contig, sample;
@@ -243,6 +244,7 @@ void synth_generate_device(guac_ctx* ctx, const guac_synth_params& P, guac_synth
   if (!P.contig_length || P.n_contigs == 0 || (P.n_windows && !P.windows) || !gsynth::build_tables(P, T)) fail(GUAC_ERR_INVALID_ARGUMENT, "bad generator parameters");
   cudaStream_t st = ctx->stream;
   B.ctx = ctx;
+  B.device = ctx->device;
   B.contig_length.assign(P.contig_length, P.contig_length + P.n_contigs);
   const std::vector<guac_locus_range> windows = gsynth::start_windows(P);
   std::vector<SynthWin> wins;

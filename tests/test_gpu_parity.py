@@ -451,7 +451,7 @@ def _same_results(ctx, batch, ranges, reference=None):
     a, b = callers.pileup_counts(ctx, wide, ranges), callers.pileup_counts(ctx, compact, ranges)
     assert np.array_equal(a.records, b.records)
     a, b = callers.germline_standard(ctx, wide, ranges), callers.germline_standard(ctx, compact, ranges)
-    assert a.genotypes() == b.genotypes()  # (allele strings are pooled in the order the warps finish: compare the decoded records)
+    assert repr(a.genotypes()) == repr(b.genotypes())  # (repr: NaN fields compare equal; allele strings are pooled in the order the warps finish: compare the decoded records)
     wide.free()
     compact.free()
     cb.free()

@@ -259,6 +259,6 @@ def test_compact_batch_somatic(ctx):
     compact = [ctx.pack_v2(cbs[0], t.contig_names, t.sample_names), ctx.pack_v2(cbs[1], n.contig_names, n.sample_names)]
     a = callers.somatic_standard(ctx, wide[0], wide[1], [(c, 0, hi)], odds_threshold=20)
     b = callers.somatic_standard(ctx, compact[0], compact[1], [(c, 0, hi)], odds_threshold=20)
-    assert len(a) > 20 and a.genotypes() == b.genotypes()
+    assert len(a) > 20 and repr(a.genotypes()) == repr(b.genotypes())  # (repr: NaN evidence fields compare equal)
     for r in wide + compact:
         r.free()
