@@ -15,7 +15,8 @@ EXPORTED = [
     "guac_abi_version", "guac_ctx_create", "guac_ctx_destroy", "guac_last_error", "guac_status_string",
     "guac_ctx_set_option", "guac_ctx_timer_start", "guac_ctx_timer_stop", "guac_host_register", "guac_host_unregister",
     "guac_reads_pack", "guac_reads_pack_device", "guac_reads_pack_v2", "guac_read_batch_compact", "guac_host_batch_v2_view",
-    "guac_host_batch_v2_bytes", "guac_host_batch_v2_free", "guac_reads_free", "guac_reads_count", "guac_reads_device_bytes",
+    "guac_host_batch_v2_bytes", "guac_host_batch_v2_free", "guac_bam_load", "guac_bam_last_error", "guac_host_batch_v2_contig_name",
+    "guac_host_batch_v2_sample_name", "guac_host_batch_v2_decode_stats", "guac_reads_free", "guac_reads_count", "guac_reads_device_bytes",
     "guac_reads_order_sensitive_loci", "guac_reads_h2d_bytes", "guac_reads_pack_kernel_ms", "guac_reads_expand_kernel_ms",
     "guac_germline_threshold", "guac_somatic_standard", "guac_somatic_standard_filtered", "guac_germline_standard", "guac_pileup_counts",
     "guac_allele_counts", "guac_result_allele_counts",
@@ -83,6 +84,14 @@ def lib():
     L.guac_host_batch_v2_view.restype = C.POINTER(abi.ReadBatchV2C)
     L.guac_host_batch_v2_bytes.argtypes = [vp]
     L.guac_host_batch_v2_bytes.restype = C.c_uint64
+    L.guac_bam_load.argtypes = [C.c_char_p, C.POINTER(abi.BamOptionsC), C.POINTER(vp)]
+    L.guac_bam_last_error.restype = C.c_char_p
+    L.guac_host_batch_v2_contig_name.argtypes = [vp, C.c_uint32]
+    L.guac_host_batch_v2_contig_name.restype = C.c_char_p
+    L.guac_host_batch_v2_sample_name.argtypes = [vp]
+    L.guac_host_batch_v2_sample_name.restype = C.c_char_p
+    L.guac_host_batch_v2_decode_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.guac_host_batch_v2_decode_stats.restype = C.c_double
     L.guac_host_batch_v2_free.argtypes = [vp]
     L.guac_host_batch_v2_free.restype = None
     L.guac_reads_free.restype = None

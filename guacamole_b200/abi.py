@@ -83,6 +83,12 @@ class ReadBatchV2C(C.Structure):
     ]
 
 
+class BamOptionsC(C.Structure):
+    _fields_ = [("n_threads", C.c_int32), ("non_duplicate", C.c_int32), ("passed_qc", C.c_int32), ("has_md_tag", C.c_int32),
+                ("is_paired", C.c_int32), ("with_qualities", C.c_int32), ("pinned", C.c_int32), ("reserved", C.c_int32),
+                ("sample", C.c_char_p)]
+
+
 class ReferenceC(C.Structure):
     _fields_ = [
         ("n_contigs", C.c_uint32),

@@ -110,6 +110,8 @@ class CompactBatch:
 
     def __init__(self, source, pinned: bool = False, fixed_length: bool = True):
         self._h = C.c_void_p()
+        if source is None:  # (from_bam fills the handle in)
+            return
         self.contig_names = list(getattr(source, "contig_names", []) or [])
         self.sample_names = list(getattr(source, "sample_names", []) or ["default"])
         b = source.to_c() if hasattr(source, "to_c") else source
@@ -117,6 +119,52 @@ class CompactBatch:
         if rc != abi.OK:
             raise GuacError(rc, lib().guac_status_string(rc).decode())
         self.c = lib().guac_host_batch_v2_view(self._h).contents
+
+    @classmethod
+    def from_bam(cls, path: str, non_duplicate=False, passed_qc=False, has_md_tag=False, is_paired=False, with_qualities=True,
+                 pinned=False, sample: Optional[str] = None, n_threads: int = 0) -> "CompactBatch":
+        """guac_bam_load: a BAM file decoded on host threads straight into the compact columns (no GPU needed)."""
+        self = cls(None)
+        opt = abi.BamOptionsC(n_threads, int(non_duplicate), int(passed_qc), int(has_md_tag), int(is_paired), int(with_qualities),
+                              int(pinned), 0, sample.encode() if sample is not None else None)
+        rc = lib().guac_bam_load(path.encode(), C.byref(opt), C.byref(self._h))
+        if rc != abi.OK:
+            raise GuacError(rc, lib().guac_bam_last_error().decode())
+        self.c = lib().guac_host_batch_v2_view(self._h).contents
+        self.contig_names = [lib().guac_host_batch_v2_contig_name(self._h, i).decode() for i in range(self.c.n_contigs)]
+        self.sample_names = [lib().guac_host_batch_v2_sample_name(self._h).decode()]
+        return self
+
+    @property
+    def decode_stats(self) -> dict:
+        st = (C.c_uint64 * 4)()
+        ms = lib().guac_host_batch_v2_decode_stats(self._h, st)
+        return {"file_bytes": int(st[0]), "inflated_bytes": int(st[1]), "records_in_file": int(st[2]), "reads": int(st[3]), "decode_ms": float(ms)}
+
+    def to_read_batch(self) -> ReadBatch:
+        """The wide ReadBatch holding the same reads (tests; examples)."""
+        v, n = self.c, int(self.c.n_reads)
+        arr = lambda p, k, dt: np.ctypeslib.as_array(p, shape=(max(int(k), 1),))[:int(k)].astype(dt) if k else np.zeros(0, dt)
+        cigar_off, md_off = arr(v.cigar_off, n + 1, np.uint64), arr(v.md_off, n + 1, np.uint64)
+        seq_off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(v.read_length)) if v.read_length else arr(v.seq_off, n + 1, np.uint64)
+        if n == 0:
+            cigar_off = md_off = seq_off = np.zeros(1, np.uint64)
+        n_bases = int(seq_off[-1])
+        packed = arr(v.seq4, (n_bases + 1) // 2, np.uint8)
+        nib = np.empty(2 * len(packed), np.uint8)
+        nib[0::2], nib[1::2] = packed >> 4, packed & 15
+        seq = np.frombuffer(b"=ACMGRSVTWYHKDBN", np.uint8)[nib[:n_bases]]
+        off = [int(v.contig_read_off[i]) for i in range(v.n_contigs + 1)] if n else [0] * (v.n_contigs + 1)
+        contig = np.zeros(n, np.int32)
+        for ci in range(v.n_contigs):
+            contig[off[ci]:off[ci + 1]] = ci
+        lengths = np.asarray([int(v.contig_length[i]) for i in range(v.n_contigs)], np.int64) if v.contig_length else None
+        md = np.frombuffer(C.string_at(v.md, int(md_off[-1])), np.uint8).copy() if int(md_off[-1]) else np.zeros(0, np.uint8)
+        return ReadBatch(contig_names=list(self.contig_names), sample_names=list(self.sample_names), contig=contig,
+                         start=arr(v.start, n, np.int64), cigar_off=cigar_off, cigar=arr(v.cigar, int(cigar_off[-1]), np.uint32),
+                         seq_off=seq_off, seq=seq.copy(), qual=arr(v.qual, n_bases, np.uint8) if v.qual else np.zeros(n_bases, np.uint8),
+                         mapq=arr(v.mapq, n, np.uint8), flags=arr(v.flags, n, np.uint8), sample=np.zeros(n, np.int32), md_off=md_off, md=md,
+                         contig_lengths=lengths)
 
     @property
     def h2d_bytes(self) -> int:

@@ -24,6 +24,7 @@
 #include "guac_synth_device.cuh"
 #include "guac_comm.cuh"
 #include "guac_batch2.cuh"
+#include "guac_bam.cuh"
 #include "../../include/guac_synth.h"
 
 namespace {
@@ -1172,6 +1173,37 @@ guac_status guac_read_batch_compact(const guac_read_batch* batch, int pinned, in
 const guac_read_batch_v2* guac_host_batch_v2_view(const guac_host_batch_v2* b) { return b ? &b->view : nullptr; }
 uint64_t guac_host_batch_v2_bytes(const guac_host_batch_v2* b) { return b ? b->bytes : 0; }
 void guac_host_batch_v2_free(guac_host_batch_v2* b) { delete b; }
+
+static thread_local std::string tl_bam_error;
+guac_status guac_bam_load(const char* path, const guac_bam_options* options, guac_host_batch_v2** out) {
+  if (!path || !out) return GUAC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  guac_bam_options opt{};
+  if (options) opt = *options;
+  try {
+    std::unique_ptr<guac_host_batch_v2> h(new guac_host_batch_v2());
+    h->pinned = opt.pinned != 0;
+    bam_load(path, opt, *h);
+    *out = h.release();
+    return GUAC_OK;
+  } catch (const StatusError& e) {
+    tl_bam_error = e.msg;
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    tl_bam_error = "host allocation failed";
+    return GUAC_ERR_OOM;
+  }
+}
+const char* guac_bam_last_error(void) { return tl_bam_error.c_str(); }
+const char* guac_host_batch_v2_contig_name(const guac_host_batch_v2* b, uint32_t contig) {
+  return b && contig < b->contig_names.size() ? b->contig_names[contig].c_str() : "";
+}
+const char* guac_host_batch_v2_sample_name(const guac_host_batch_v2* b) { return b ? b->sample_name.c_str() : ""; }
+double guac_host_batch_v2_decode_stats(const guac_host_batch_v2* b, uint64_t stats[4]) {
+  if (!b) return 0;
+  if (stats) { stats[0] = b->file_bytes; stats[1] = b->inflated_bytes; stats[2] = b->records_in_file; stats[3] = b->view.n_reads; }
+  return b->decode_ms;
+}
 
 guac_status guac_reads_pack_device(guac_ctx* ctx, const guac_read_batch* device_batch, const guac_reference* ref, guac_reads** out) {
   if (!ctx || !out) return GUAC_ERR_INVALID_ARGUMENT;

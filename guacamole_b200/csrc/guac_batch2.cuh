@@ -95,6 +95,11 @@ struct guac_host_batch_v2 {
   bool pinned = false;
   uint64_t bytes = 0;
   guac_read_batch_v2 view{};
+  // guac_bam_load: the file's sequence dictionary, the sample of the kept reads, and what the decode cost
+  std::vector<std::string> contig_names;
+  std::string sample_name = "default";
+  uint64_t file_bytes = 0, inflated_bytes = 0, records_in_file = 0;
+  double decode_ms = 0;
   ~guac_host_batch_v2() {
     for (void* p : blocks) {
       if (pinned) cudaFreeHost(p);

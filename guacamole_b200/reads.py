@@ -429,3 +429,58 @@ def load_bam(path: str) -> ReadBatch:
 
 def load_reads(path: str) -> ReadBatch:
     return load_bam(path) if path.endswith(".bam") else load_sam(path)
+
+
+def write_bam(batch: ReadBatch, path: str, read_groups: Optional[dict] = None, block_bytes: int = 0xFF00, level: int = 6) -> None:
+    """Write the batch as a BAM file (BGZF members of `block_bytes` uncompressed bytes, SAM spec 4.1 / 4.2): the test and
+    bench input of guac_bam_load.  Samples other than "default" get one read group each (ID = SM = sample name)."""
+    import zlib
+    names = list(batch.contig_names)
+    lengths = [int(x) for x in batch.contig_lengths] if batch.contig_lengths is not None else [0] * len(names)
+    ends = batch.end() if len(batch) else np.zeros(0, np.int64)
+    for c in range(len(names)):
+        if lengths[c] <= 0:
+            sel = batch.contig == c
+            lengths[c] = int(ends[sel].max()) + 1 if sel.any() else 1
+    text = "@HD\tVN:1.4\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in zip(names, lengths))
+    text += "".join(f"@RG\tID:{s}\tSM:{s}\n" for s in batch.sample_names if s != "default")
+    out = bytearray(b"BAM\x01" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(names)))
+    for n, l in zip(names, lengths):
+        out += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l)
+    code = np.full(256, 15, np.uint8)
+    for k, ch in enumerate(b"=ACMGRSVTWYHKDBN"):
+        code[ch] = k
+    for i in range(len(batch)):
+        co, ce = int(batch.cigar_off[i]), int(batch.cigar_off[i + 1])
+        so, se = int(batch.seq_off[i]), int(batch.seq_off[i + 1])
+        mo, me = int(batch.md_off[i]), int(batch.md_off[i + 1])
+        f = int(batch.flags[i])
+        flag = (0 if f & abi.READ_POSITIVE_STRAND else 0x10) | (0x400 if f & abi.READ_DUPLICATE else 0) | \
+               (0x200 if f & abi.READ_FAILED_QC else 0) | (0x1 if f & abi.READ_PAIRED else 0)
+        name = b"r%d\0" % i
+        nib = code[batch.seq[so:se]]
+        if len(nib) & 1:
+            nib = np.append(nib, np.uint8(0))
+        packed = ((nib[0::2] << 4) | nib[1::2]).astype(np.uint8).tobytes()
+        aux = b""
+        if f & abi.READ_HAS_MD:
+            aux += b"MDZ" + batch.md[mo:me].tobytes() + b"\0"
+        sample = batch.sample_names[int(batch.sample[i])] if len(batch.sample_names) else "default"
+        if sample != "default":
+            aux += b"RGZ" + sample.encode() + b"\0"
+        aux += b"NMi" + struct.pack("<i", 0)
+        body = struct.pack("<iiBBHHHiiii", int(batch.contig[i]), int(batch.start[i]), len(name), int(batch.mapq[i]), 4680, ce - co, flag,
+                           se - so, -1, -1, 0) + name + batch.cigar[co:ce].astype("<u4").tobytes() + packed + \
+            batch.qual[so:se].tobytes() + aux
+        out += struct.pack("<i", len(body)) + body
+
+    def member(chunk: bytes) -> bytes:
+        z = zlib.compressobj(level, zlib.DEFLATED, -15)
+        data = z.compress(chunk) + z.flush()
+        head = b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(data) + 25)
+        return head + data + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk))
+
+    with open(path, "wb") as fh:
+        for a in range(0, len(out), block_bytes):
+            fh.write(member(bytes(out[a:a + block_bytes])))
+        fh.write(member(b""))

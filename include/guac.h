@@ -322,6 +322,30 @@ guac_status guac_read_batch_compact(const guac_read_batch* batch, int pinned, in
 const guac_read_batch_v2* guac_host_batch_v2_view(const guac_host_batch_v2* b);
 uint64_t guac_host_batch_v2_bytes(const guac_host_batch_v2* b);   /* bytes guac_reads_pack_v2 will copy for it (with qualities) */
 void guac_host_batch_v2_free(guac_host_batch_v2* b);
+
+/* BAM file -> compact batch on host threads: the BGZF members are inflated in parallel, the records filtered (mapped reads
+ * only, then Read.InputFilters reads/Read.scala:88-136) and written in parallel straight into the columns guac_reads_pack_v2
+ * copies — the 4-bit bases and the CIGAR words are the record's own bytes.  Replaces Read.fromSAMRecord / loadReadsFromBAM
+ * (reads/Read.scala:217-291, 368-451) for this path.  Reads come out sorted by (contig index, start) (file order among equals;
+ * a coordinate-sorted file is taken as it is).  One sample per batch: `sample` selects the reads whose @RG SM equals it
+ * ("default" = reads without a read group); NULL requires the kept reads to share one.  No GPU needed. */
+typedef struct guac_bam_options {
+  int32_t n_threads;      /* 0 = all hardware threads */
+  int32_t non_duplicate;  /* drop SAM flag 0x400 */
+  int32_t passed_qc;      /* drop SAM flag 0x200 */
+  int32_t has_md_tag;     /* drop reads without an MD tag */
+  int32_t is_paired;      /* drop reads without SAM flag 0x1 */
+  int32_t with_qualities; /* 0: the qual column stays NULL (germline-threshold does not read it) */
+  int32_t pinned;         /* page-lock the columns */
+  int32_t reserved;
+  const char* sample;
+} guac_bam_options;
+guac_status guac_bam_load(const char* path, const guac_bam_options* options, guac_host_batch_v2** out);
+const char* guac_bam_last_error(void);                                  /* message of this thread's last failed guac_bam_load */
+const char* guac_host_batch_v2_contig_name(const guac_host_batch_v2* b, uint32_t contig);
+const char* guac_host_batch_v2_sample_name(const guac_host_batch_v2* b);
+/* [0] file bytes, [1] inflated bytes, [2] records in the file, [3] reads kept; returns the decode time in milliseconds */
+double guac_host_batch_v2_decode_stats(const guac_host_batch_v2* b, uint64_t stats[4]);
 void guac_reads_free(guac_reads* reads);
 uint64_t guac_reads_count(const guac_reads* reads);
 uint64_t guac_reads_device_bytes(const guac_reads* reads);
