@@ -86,7 +86,7 @@ struct DevReads {
   // likelihood callers: per 32-locus word (all contigs, ContigInfo.word_off) the reads overlapping it as rows (guac_rows.cuh)
   const uint4* q_hdr;         // {first column pair, columns, first row group, rows | highest rank << 24}; nullptr: no such store
   const uint16_t* q_depth;    // per locus: plain elements (all mapping qualities)
-  const uint32_t* q_cols;     // per (block of 8 columns, lane): eight 16-bit elements (quality | class << 6 | mapq rank << 8)
+  const uint32_t* q_cols;     // per (block of 8 columns, lane): eight 16-bit elements (class | quality << 4 | mapq rank << 10)
   const uint4* q_groups;      // general rows, per group of 4: their headers (mapq | type << 8)
   const uint32_t* q_rows;     // ... and per group and lane: the 4 rows' bytes for the lane's locus
   const uint64_t* seq_off;

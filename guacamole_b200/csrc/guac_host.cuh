@@ -14,6 +14,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -323,19 +324,42 @@ struct Trace {  // GUAC_TRACE=1 prints host-side phase times (diagnostics only)
 // Canonical record order (contig, start, then `tie_less` among equal loci): LSD radix sort of (key, index) words on the
 // bits of the (contig, start) key that actually vary, 13 bits per pass (one contig of up to 67 M loci: two passes over
 // 8-byte words), one gather of the records, groups of equal keys finished with the full comparator.
+// f(begin, end) over contiguous slices of [0, n) on up to `max_threads` host threads (the caller's included); slices shorter
+// than `grain` are not worth a thread
+template <typename F>
+void host_parallel(size_t n, size_t grain, unsigned max_threads, F&& f) {
+  const unsigned n_thr = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(max_threads, std::max(1u, std::thread::hardware_concurrency())), n / std::max<size_t>(grain, 1)));
+  if (n_thr <= 1) { f((size_t)0, n); return; }
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < n_thr; ++t) pool.emplace_back([&f, n, n_thr, t] { f(n * t / n_thr, n * (t + 1) / n_thr); });
+  f((size_t)0, n / n_thr);
+  for (std::thread& th : pool) th.join();
+}
+
 template <typename Rec, typename TieLess>
 void sort_records_canonical(Rec* recs, size_t n, TieLess tie_less) {
   if (n < 2) return;
-  bool fits = true;
+  constexpr unsigned kThreads = 8;
+  const size_t grain = std::max<size_t>(1, (size_t)(1u << 20) / sizeof(Rec));  // a megabyte of records per thread at least
   int ib = 1;  // bits of a record index
   while (((n - 1) >> ib) != 0) ++ib;
+  std::mutex mu;
+  bool fits = true;
   uint64_t kmin = ~0ull, kmax = 0;
-  for (size_t i = 0; i < n && fits; ++i) {
-    fits = recs[i].contig >= 0 && recs[i].contig < 65536 && recs[i].start >= 0 && recs[i].start < (1ll << 32);
-    const uint64_t k = ((uint64_t)recs[i].contig << 32) | (uint64_t)recs[i].start;
-    kmin = std::min(kmin, k);
-    kmax = std::max(kmax, k);
-  }
+  host_parallel(n, grain, kThreads, [&](size_t b, size_t e) {
+    bool ok = true;
+    uint64_t lo = ~0ull, hi = 0;
+    for (size_t i = b; i < e && ok; ++i) {
+      ok = recs[i].contig >= 0 && recs[i].contig < 65536 && recs[i].start >= 0 && recs[i].start < (1ll << 32);
+      const uint64_t k = ((uint64_t)recs[i].contig << 32) | (uint64_t)recs[i].start;
+      lo = std::min(lo, k);
+      hi = std::max(hi, k);
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    fits = fits && ok;
+    kmin = std::min(kmin, lo);
+    kmax = std::max(kmax, hi);
+  });
   int bits = 0;
   while (fits && bits < 64 && ((kmax - kmin) >> bits) != 0) ++bits;
   if (!fits || bits + ib > 64) {  // (key - kmin) and the record index must share one 64-bit word
@@ -346,15 +370,17 @@ void sort_records_canonical(Rec* recs, size_t n, TieLess tie_less) {
     });
     return;
   }
-  bool sorted = true;  // device order is often already canonical for small outputs
   static thread_local std::vector<uint64_t> v, v2;  // scratch kept between calls: no page faults on the hot path
   static thread_local std::vector<unsigned char> tmp_bytes;
   if (v.size() < n) { v.resize(n); v2.resize(n); }
-  for (size_t i = 0; i < n; ++i) {
-    const uint64_t k = (((uint64_t)recs[i].contig << 32) | (uint64_t)recs[i].start) - kmin;
-    v[i] = (k << ib) | (uint64_t)i;
-    if (i && (v[i] >> ib) < (v[i - 1] >> ib)) sorted = false;
+  {
+    uint64_t* keys = v.data();  // (a thread_local is per thread: the workers get the caller's array through a plain pointer)
+    host_parallel(n, grain, kThreads, [&, keys](size_t b, size_t e) {
+      for (size_t i = b; i < e; ++i) keys[i] = (((((uint64_t)recs[i].contig << 32) | (uint64_t)recs[i].start) - kmin) << ib) | (uint64_t)i;
+    });
   }
+  bool sorted = true;  // device order is often already canonical for small outputs
+  for (size_t i = 1; i < n && sorted; ++i) sorted = (v[i] >> ib) >= (v[i - 1] >> ib);
   if (!sorted) {
     constexpr int kDigit = 13;
     std::vector<uint32_t> count((1u << kDigit) + 1);
@@ -369,14 +395,16 @@ void sort_records_canonical(Rec* recs, size_t n, TieLess tie_less) {
   if (tmp_bytes.size() < n * sizeof(Rec)) tmp_bytes.resize(n * sizeof(Rec));
   Rec* tmp = reinterpret_cast<Rec*>(tmp_bytes.data());
   const uint64_t imask = (1ull << ib) - 1;
-  for (size_t i = 0; i < n; ++i) tmp[i] = recs[v[i] & imask];
-  for (size_t i = 0; i < n;) {
+  const uint64_t* order = v.data();
+  if (!sorted) host_parallel(n, grain, kThreads, [&, order](size_t b, size_t e) { for (size_t i = b; i < e; ++i) tmp[i] = recs[order[i] & imask]; });
+  Rec* cur = sorted ? recs : tmp;
+  for (size_t i = 0; i < n;) {  // records of one locus: the full comparator
     size_t j = i + 1;
     while (j < n && (v[j] >> ib) == (v[i] >> ib)) ++j;
-    if (j - i > 1) std::sort(tmp + i, tmp + j, tie_less);
+    if (j - i > 1) std::sort(cur + i, cur + j, tie_less);
     i = j;
   }
-  memcpy(recs, tmp, n * sizeof(Rec));
+  if (!sorted) host_parallel(n, grain, kThreads, [&](size_t b, size_t e) { memcpy(recs + b, tmp + b, (e - b) * sizeof(Rec)); });
   if (n > (1u << 22)) {  // dense outputs: do not keep gigabytes of scratch around
     std::vector<uint64_t>().swap(v);
     std::vector<uint64_t>().swap(v2);

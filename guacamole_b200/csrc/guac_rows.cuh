@@ -6,8 +6,9 @@
 // time — the CIGAR expansion of PileupElement.advanceToLocus / alignment (pileup/PileupElement.scala:68-248) — and leaves,
 // per word:
 //   columns   the plain elements (A/C/G/T bases of reads that are one M/=/X run between clips, qualities < 64: 98 % of all
-//             elements) of every locus, in read order, 16 bits each: quality | (base code ^ reference code) << 6 | rank of
-//             the read's mapping quality among those present (from the top) << 8.  Column k of the word holds the k-th
+//             elements) of every locus, in read order, 16 bits each: (base code ^ reference code) | quality << 4 | rank of
+//             the read's mapping quality among those present (from the top) << 10 — bits 15..4 are the element's byte offset
+//             in the likelihood table (64 rows of 64 double2).  Column k of the word holds the k-th
 //             element of each of its 32 loci; loci with fewer elements are filled with a sentinel that reads a zero row of
 //             the likelihood table.  Two columns per 32-bit word per locus: the likelihood kernel streams 128 coalesced bytes
 //             per two columns and does nothing per element but one table look-up and two additions;
@@ -27,7 +28,7 @@ constexpr uint32_t kElemNone = 0xFFu, kElemOther = 0xFEu, kElemHard = 0xFDu, kEl
 
 constexpr uint32_t kRankZero = 63u;        // rank of the sentinel element: the all-zero row of the likelihood table
 constexpr uint32_t kMaxRank = 62u;         // reads whose mapping quality ranks at or beyond this take the general rows
-constexpr uint32_t kSentinel = kRankZero << 8;
+constexpr uint32_t kSentinel = kRankZero << 10;
 
 struct RowsArgs {
   DevReads R;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(kRowsWarps * 32) k_expand_rows(RowsArgs A) {
                                         __shfl_sync(0xFFFFFFFFu, (uint32_t)my_qa, j);
           if (covered) {
             const uint32_t b = (uint32_t)__ldg(reinterpret_cast<const uint8_t*>((uintptr_t)(qa + (unsigned long long)(long long)x)));
-            put((b & 63u) | ((((b >> 6) ^ rcode) & 3u) << 6) | (rank << 8));
+            put(((b & 63u) << 4) | (((b >> 6) ^ rcode) & 3u) | (rank << 10));
           }
         } else {
           const uint32_t info = __shfl_sync(0xFFFFFFFFu, my.info, j);

@@ -578,7 +578,7 @@ __device__ void gather_sample(const DevReads& R, int contig, int span_lo, int x,
     A.depth += A.cnt[k];
   }
   A.any += A.depth;  // (only any > 0 matters: the lean loop's elements all count towards the depth)
-  A.ref_depth = std_ref ? A.cnt[rcode] : 0;
+  A.ref_depth = !std_ref ? 0 : rcode == 0 ? A.cnt[0] : rcode == 1 ? A.cnt[1] : rcode == 2 ? A.cnt[2] : A.cnt[3];  // (no dynamic index: A stays in registers)
 #pragma unroll
   for (int k = 0; k < 4; ++k) A.seen |= A.cnt[k] > 0 ? (1u << k) : 0u;
   if (n_word_reads > 0xFFFFu) {  // the packed counters hold 16 bits and may have wrapped: the exact kernel decides this word's
@@ -656,7 +656,12 @@ __device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t wo
     const uint32_t blocks = (n_cols + 7u) >> 3;  // eight columns = 16 bytes per locus per load
     const uint4* __restrict__ cp = reinterpret_cast<const uint4*>(R.q_cols) + (size_t)wh.x * 32 + lane;
     const bool check = max_rank >= n_keep;  // (warp-uniform) some read of this word fails the mapq filter
-    const uint32_t ref_mask = std_ref ? 0xC0u : 0u;  // (no reference class at a locus whose reference base is not A/C/G/T)
+    const uint32_t nostd = std_ref ? 0u : 1u;  // (no reference class at a locus whose reference base is not A/C/G/T)
+    // byte offset of an element's table entry: bits 15..4 of the element are (rank, quality).  The normal sample's table has
+    // two rows: the probabilities ignoring the mapping quality, and zeros for dropped reads and the sentinel.
+    auto entry = [&](const uint32_t e) -> uint32_t {
+      return TUMOR ? (e & 0xFFF0u) : (e & 0x03F0u) + (((e >> 10) & 63u) < n_keep ? 0u : 1024u);
+    };
     uint4 v = __ldg(cp), v_next = v;
     if (blocks > 1) v_next = __ldg(cp + 32);
     for (uint32_t p = 0; p < blocks; ++p) {
@@ -664,34 +669,48 @@ __device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t wo
       v = v_next;
       if (p + 2 < blocks) v_next = __ldg(cp + (size_t)(p + 2) * 32);  // two blocks are on their way while this one is summed
       const uint32_t w4[4] = {v_now.x, v_now.y, v_now.z, v_now.w};
-      // the hot loop: per element one table look-up and two additions; elements that do not carry the reference base (a
-      // percent of them) are only noted here
-      uint32_t rare = 0;
+      // the hot loop: per element one table look-up and two additions, the second one only for elements that carry the
+      // reference base (class 0); the others (a percent of them) are handled below
+      if (!nostd) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t e = (j & 1) ? (w4[j >> 1] >> 16) : (w4[j >> 1] & 0xFFFFu);
-        const uint32_t rank = e >> 8;
-        const double2 l = lds_double2(tab + (TUMOR ? rank * 1024u : (rank < n_keep ? 0u : 1024u)) + (e & 63u) * 16u);
-        A.t0 += l.y;
-        const bool is_ref = (e & 0xC0u) == 0u && ref_mask != 0u;
-        sr1 += is_ref ? l.x : 0.0;
-        rare |= is_ref ? 0u : (1u << j);
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t e = (j & 1) ? (w4[j >> 1] >> 16) : w4[j >> 1];  // (even elements: the upper half word is masked off below)
+          const double2 l = lds_double2(tab + entry(e));
+          A.t0 += l.y;
+          asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p add.f64 %0, %0, %1;\n\t}" : "+d"(sr1) : "d"(l.x), "r"(e & 3u));  // a predicated add, no select
+        }
+      } else {  // (rare lanes) every element is of a mismatch class
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t wj = j < 2 ? w4[0] : j < 4 ? w4[1] : j < 6 ? w4[2] : w4[3];
+          const uint32_t e = ((j & 1) ? (wj >> 16) : wj) & 0xFFFFu;
+          const double2 l = lds_double2(tab + entry(e));
+          A.t0 += l.y;
+          non_ref(e & 3u, e >> 10, l);
+        }
       }
       if (check) {  // (rare words) elements dropped by the mapq filter: n_keep <= rank < the sentinel's
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
           const uint32_t wj = j < 2 ? w4[0] : j < 4 ? w4[1] : j < 6 ? w4[2] : w4[3];
-          const uint32_t rank = ((j & 1) ? (wj >> 16) : (wj & 0xFFFFu)) >> 8;
+          const uint32_t rank = (((j & 1) ? (wj >> 16) : wj) >> 10) & 63u;
           dropped += (rank - n_keep) < (kRankZero - n_keep) ? 1u : 0u;
         }
       }
-      while (rare) {  // (divergent, rare)
-        const int j = __ffs(rare) - 1;
-        rare &= rare - 1;
-        const uint32_t wj = j < 2 ? w4[0] : j < 4 ? w4[1] : j < 6 ? w4[2] : w4[3];
-        const uint32_t e = (j & 1) ? (wj >> 16) : (wj & 0xFFFFu);
-        const uint32_t rank = e >> 8;
-        non_ref((e >> 6) & 3u, rank, lds_double2(tab + (TUMOR ? rank * 1024u : (rank < n_keep ? 0u : 1024u)) + (e & 63u) * 16u));
+      if (!nostd && (((w4[0] | w4[1]) | (w4[2] | w4[3])) & 0x00030003u)) {  // (divergent, rare) some element is not of class 0
+        uint32_t rare = 0;  // bit j: element j's class is not 0
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t m = (w4[k] | (w4[k] >> 1)) & 0x00010001u;
+          rare |= ((m | (m >> 15)) & 3u) << (2 * k);
+        }
+        while (rare) {
+          const int j = __ffs(rare) - 1;
+          rare &= rare - 1;
+          const uint32_t wj = j < 2 ? w4[0] : j < 4 ? w4[1] : j < 6 ? w4[2] : w4[3];
+          const uint32_t e = ((j & 1) ? (wj >> 16) : wj) & 0xFFFFu;
+          non_ref(e & 3u, e >> 10, lds_double2(tab + entry(e)));
+        }
       }
     }
   }
@@ -755,7 +774,7 @@ __device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t wo
   }
   if (!std_ref) A.depth = kept;  // (no reference class: every element sits in a mismatch class; only the totals matter, the locus is deferred)
   A.any = any;
-  A.ref_depth = std_ref ? A.cnt[rcode] : 0;
+  A.ref_depth = !std_ref ? 0 : rcode == 0 ? A.cnt[0] : rcode == 1 ? A.cnt[1] : rcode == 2 ? A.cnt[2] : A.cnt[3];  // (no dynamic index: A stays in registers)
 #pragma unroll
   for (int k = 0; k < 4; ++k) A.seen |= A.cnt[k] > 0 ? (1u << k) : 0u;
   if (n_cols + n_rows > 0xFFFFu) {  // the packed counters (and the u16 depths) hold 16 bits: the exact kernel decides this
@@ -1293,6 +1312,7 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
   if (tumor.n_contigs != normal.n_contigs) fail(GUAC_ERR_INVALID_ARGUMENT, "tumor and normal samples have different sequence dictionaries");
   if (!tumor.has_qualities || !normal.has_qualities) fail(GUAC_ERR_UNSUPPORTED, "somatic-standard needs reads packed with base qualities");
   cudaStream_t st = ctx->stream;
+  Trace tr("somatic");
   // tiles over the union of both tracks: a locus past one sample's track simply holds no reads of that sample
   check_ranges_disjoint(ranges, n_ranges);
   std::vector<TileDesc> tiles;
@@ -1319,6 +1339,7 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
   DevBuf<TileDesc> d_tiles;
   h2d(ctx, d_tiles, tiles.data(), tiles.size());
   res.stats.h2d_bytes = d_tiles.bytes();
+  tr.lap("tiles");
   uint64_t cap_rec = std::max<uint64_t>(4096, tile_loci / 256), cap_slow = std::max<uint64_t>(4096, tile_loci / 8);
   uint64_t cap_pool = kPoolDynOff + std::max<uint64_t>(65536, tile_loci / 64);
   SomParams prm{p.odds_threshold, p.min_alignment_quality, p.filter_multi_allelic, p.max_read_depth, p.skip_empty, tumor.sample};
@@ -1375,6 +1396,7 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
     unsigned long long* c = ctx->h_counters;
     CUDA_OK(cudaMemcpyAsync(c, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     check_device_error(ctx, "somatic-standard");
+    tr.lap("kernels");
     float ms0 = 0, ms1 = 0;
     CUDA_OK(cudaEventElapsedTime(&ms0, ctx->ev[0], ctx->ev[1]));
     CUDA_OK(cudaEventElapsedTime(&ms1, ctx->ev[1], ctx->ev[2]));
@@ -1398,6 +1420,7 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
     CUDA_OK(cudaMemcpyAsync(hs, ctx->out_pool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
     if (n_rec) CUDA_OK(cudaMemcpyAsync(hrec, d_final, rec_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
+    tr.lap("d2h");
     res.stats.d2h_bytes = pool_bytes + rec_bytes + 64;
     res.records = hrec;
     res.n_records = (size_t)n_rec;
@@ -1415,6 +1438,7 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
         return a.alt_len < b.alt_len;
       });
     }
+    tr.lap("sort");
     res.stats.loci_visited = c[3];
     res.stats.records = n_rec;
     res.stats.exact_loci = c[2];

@@ -10,7 +10,7 @@ from guacamole_b200 import abi, callers, synth  # noqa: E402
 length = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 calls = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 ctx = callers.Context(0)
-ctx.set_option(abi.OPT_SORT_RECORDS, 0)
+ctx.set_option(abi.OPT_SORT_RECORDS, int(os.environ.get("GUAC_SORT", "0")))
 t = synth.generate([("20", length)], depth=60, seed=20261021, sample=1)
 n = synth.generate([("20", length)], depth=30, seed=20261021, sample=0)
 rt, rn = ctx.pack_c(t.c, ["20"]), ctx.pack_c(n.c, ["20"])
