@@ -40,6 +40,7 @@ void alloc_streams(guac_reads& rd, uint64_t cap_entries) {
   rd.gs_diffs.alloc(cap_entries + 8);
   rd.gs_dd.alloc(grans * kGranuleLoci * (rd.gs_wide ? 4 : 1) + 16);
   rd.gs_dp.alloc(grans * kGranuleLoci * (rd.gs_wide ? 4 : 1) + 16);
+  rd.gs_imp.alloc(grans * (kGranuleLoci / 32) + 32);
   rd.gs_entries = cap_entries;
 }
 
@@ -56,6 +57,7 @@ void launch_expand(guac_ctx* ctx, guac_reads& rd, bool huge, uint64_t cap_entrie
   E.diffs_w = rd.gs_diffs.p;
   E.dd_w = rd.gs_dd.p;
   E.dp_w = rd.gs_dp.p;
+  E.imp_w = rd.gs_imp.p;
   E.cap_diffs = cap_entries;
   E.g_begin = 0;
   E.g_end = (uint32_t)grans;
@@ -132,6 +134,7 @@ void launch_rows(guac_ctx* ctx, guac_reads& rd) {
   A.n_contigs = rd.n_contigs;
   A.pad_ = 0;
   A.counters = ctx->d_counters;
+  A.err = ctx->d_err;
   memcpy(A.mapq_mask, rd.mapq_mask, sizeof A.mapq_mask);
   CUDA_OK(cudaEventRecord(ctx->ev_rows[0], st));
   k_expand_rows<<<(unsigned)((rd.total_words + kRowsWarps - 1) / kRowsWarps), kRowsWarps * 32, 0, st>>>(A);
@@ -775,11 +778,11 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     const bool device_sort = !counts_mode && ctx->sort_records && !dense && streams;
     const uint64_t nt_all = ctx->n_tiles;
     if (device_sort) {
-      ctx->sort_bins.ensure(3 * (nt_all + 8));  // tile_base | tile_n | prefix
-      ctx->scan_totals.ensure((size_t)n_seg * ((nt_all + kScanChunk - 1) / kScanChunk + 2));
-      CUDA_OK(cudaMemsetAsync(ctx->sort_bins.p + (nt_all + 8), 0, (nt_all + 8) * sizeof(uint32_t), st));  // tile_n
+      const uint64_t nt_pad = (nt_all + 11) & ~3ull;  // (tile_n is read 16 bytes at a time; the segments start at multiples of 4)
+      ctx->sort_bins.ensure(2 * nt_pad);  // tile_base | tile_n
+      CUDA_OK(cudaMemsetAsync(ctx->sort_bins.p + nt_pad, 0, nt_pad * sizeof(uint32_t), st));  // tile_n
       out.tile_base = ctx->sort_bins.p;
-      out.tile_n = ctx->sort_bins.p + (nt_all + 8);
+      out.tile_n = ctx->sort_bins.p + nt_pad;
     } else {
       out.tile_base = nullptr;
       out.tile_n = nullptr;
@@ -806,21 +809,17 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       cudaEvent_t done = seg + 1 == n_seg ? ctx->ev[1] : ctx->seg_ev[seg];
       CUDA_OK(cudaEventRecord(done, st));
       CUDA_OK(cudaStreamWaitEvent(st2, done, 0));
-      k_exact_loci<<<ctx->sm_count * 16, kExactWarps * 32, 0, st2>>>(R, so.slow, prm, so);
+      // (8 CTAs per SM: all of them resident at once with room left for the egress kernels' 256-thread blocks next to them —
+      // a grid that is not resident in full keeps every later launch waiting, whatever its stream)
+      k_exact_loci<<<ctx->sm_count * 8, kExactWarps * 32, 0, st2>>>(R, so.slow, prm, so);
       launches += 1;
       if (!counts_mode) {
         CUDA_OK(cudaStreamWaitEvent(st3, done, 0));
         if (device_sort && nt > 0) {
-          const uint64_t n_chunks = ((uint64_t)nt + kScanChunk - 1) / kScanChunk;
-          uint64_t* totals = ctx->scan_totals.p + (size_t)seg * ((nt_all + kScanChunk - 1) / kScanChunk + 2);
-          uint32_t* prefix = ctx->sort_bins.p + 2 * (nt_all + 8) + t0;
-          k_scan_totals<<<(unsigned)n_chunks, 256, 0, st3>>>(out.tile_n + t0, (uint64_t)nt, totals);
-          k_scan_chunks<<<1, 1024, 0, st3>>>(totals, n_chunks);
-          k_scan_final<uint32_t><<<(unsigned)n_chunks, 256, 0, st3>>>(out.tile_n + t0, (uint64_t)nt, totals, prefix);
-          k_rec_gather<<<grid_for((uint64_t)nt, 256, ctx->sm_count), 256, 0, st3>>>(so.compact, out.tile_base + t0, out.tile_n + t0, prefix, (uint32_t)nt,
-                                                                                    ctx->d_counters, (uint32_t)seg, so.cap_compact, d_contig, cap_compact);
+          k_rec_gather<<<(unsigned)(((uint64_t)nt + 255) / 256), 256, 0, st3>>>(so.compact, out.tile_base + t0, out.tile_n + t0, (uint32_t)nt, ctx->d_counters,
+                                                                               (uint32_t)seg, so.cap_compact, d_contig, cap_compact);
           k_rec_to_host<<<ctx->sm_count, 256, 0, st3>>>(d_contig, ctx->d_counters, (uint32_t)seg, so.cap_compact, h_compact, cap_compact);
-          launches += 5;
+          launches += 2;
         } else {
           k_rec_flush<<<ctx->sm_count, 256, 0, st3>>>(so.compact, ctx->d_counters, (uint32_t)seg, so.cap_compact, h_compact, d_contig, cap_compact);
           launches += 1;

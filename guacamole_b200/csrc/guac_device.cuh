@@ -81,6 +81,8 @@ struct DevReads {
   const uint16_t* gs_diffs;   // CntLayout::slot_code(locus offset, class) entries, 16-byte aligned per granule
   const uint8_t* gs_dd;       // per locus of every granule: starts | ends << 4 (narrow) or u32 starts | ends << 16 (wide)
   const uint8_t* gs_dp;       // same, positive-strand reads only
+  const uint32_t* gs_imp;     // per 32 loci of every granule: loci holding an element that is neither a plain base nor a
+                              //   mid-deletion element carrying the track's base (only those need the exact per-locus walk)
   int32_t gs_wide;            // 1: 4 bytes per locus in gs_dd / gs_dp
   int32_t pad2_;
   // likelihood callers: per 32-locus word (all contigs, ContigInfo.word_off) the reads overlapping it as rows (guac_rows.cuh)

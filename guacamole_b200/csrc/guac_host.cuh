@@ -455,6 +455,7 @@ struct guac_reads {
   DevBuf<GranHdr> gs_hdr;             // per-granule difference streams (k_expand); empty when packed without them
   DevBuf<uint16_t> gs_diffs;
   DevBuf<uint8_t> gs_dd, gs_dp;
+  DevBuf<uint32_t> gs_imp;
   bool gs_wide = false;
   uint64_t gs_entries = 0;
   // per 32-locus word, the overlapping reads as ROWS of (quality | base code << 6) bytes, one byte per locus of the word
@@ -496,6 +497,7 @@ struct guac_reads {
     R.gs_diffs = gs_diffs.p;
     R.gs_dd = gs_dd.p;
     R.gs_dp = gs_dp.p;
+    R.gs_imp = gs_imp.p;
     R.gs_wide = gs_wide ? 1 : 0;
     R.pad2_ = 0;
     R.q_hdr = q_hdr.n ? q_hdr.p : nullptr;
@@ -525,7 +527,7 @@ struct guac_reads {
   }
   uint64_t device_bytes() const {
     return rec.bytes() + cig_off.bytes() + cigar.bytes() + xmask.bytes() + md_off.bytes() + trk_lo.bytes() * 3 +
-           gran_first.bytes() * 2 + pairs.bytes() + gs_hdr.bytes() + gs_diffs.bytes() + gs_dd.bytes() + gs_dp.bytes() + q_hdr.bytes() + q_depth.bytes() + q_cols.bytes() + q_groups.bytes() + q_rows.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + qc.bytes() + md.bytes() + nm.bytes() + del_start.bytes() + del_md.bytes() + del_len.bytes() +
+           gran_first.bytes() * 2 + pairs.bytes() + gs_hdr.bytes() + gs_diffs.bytes() + gs_dd.bytes() + gs_dp.bytes() + gs_imp.bytes() + q_hdr.bytes() + q_depth.bytes() + q_cols.bytes() + q_groups.bytes() + q_rows.bytes() + seq_off.bytes() + seq.bytes() + qual.bytes() + qc.bytes() + md.bytes() + nm.bytes() + del_start.bytes() + del_md.bytes() + del_len.bytes() +
            fasta.bytes();
   }
 };

@@ -161,19 +161,25 @@ __device__ __forceinline__ void flush_stage(DevOut& out, EmitStage* stage, uint3
 // locus: `total` elements, of which `o` are not plain bases and m1..m3 mismatch the reference base (code rcode) by class
 // (read code ^ reference code).  Loci the counts cannot decide exactly go to the exact kernel.
 __device__ __forceinline__ void call_snv_locus(const CallParams& prm, DevOut& out, int contig, int locus, int total, int o, int m1, int m2,
-                                               int m3, int rcode, bool std_ref, bool every_covered, EmitStage* stage = nullptr) {
+                                               int m3, int rcode, bool std_ref, bool every_covered, bool pure = false, EmitStage* stage = nullptr) {
   // count * 100 / total > threshold  <=>  count * 100 >= (threshold + 1) * total   (integers, no division)
   const long long bar = (long long)(prm.threshold_percent + 1) * total;
   auto passes = [&](int count) { return (long long)count * 100 >= bar; };
-  // any allele made of "other" elements has count <= o: if o cannot pass the threshold the SNV counts decide alone
-  if (!(std_ref && !passes(o))) {
+  // any allele made of "other" elements has count <= o: if o cannot pass the threshold the SNV counts decide alone.  `pure`:
+  // every "other" element of the locus is a MidDeletion element carrying the reference base (k_expand) — ONE allele,
+  // (reference base, ""), which precedes every single-base allele in Allele.compare order (equal ref, shorter alt).
+  const bool del = passes(o);
+  if (!std_ref || (del && !(pure && o > 0))) {
     defer_locus(out, contig, locus, stage);
     return;
   }
   const int mref = total - o - m1 - m2 - m3;
-  if (!every_covered && !passes(max(m1, max(m2, m3)))) return;  // no alternate allele passes
-  // alleles in Allele.compare order (= base code order), stable-sorted by descending count: keep the best three
+  if (!del && !every_covered && !passes(max(m1, max(m2, m3)))) return;  // no alternate allele passes
+  // alleles in Allele.compare order (= the deletion allele, then base code order), stable-sorted by descending count: keep
+  // the best three
+  constexpr int kDel = 4;
   int c0 = -1, c1 = -1, c2 = -1, b0 = 0, b1 = 0, n = 0;
+  if (del) { c0 = o; b0 = kDel; n = 1; }
 #pragma unroll
   for (int code = 0; code < 4; ++code) {
     const int cls = code ^ rcode;
@@ -186,6 +192,17 @@ __device__ __forceinline__ void call_snv_locus(const CallParams& prm, DevOut& ou
     }
   }
   const uint32_t tie = (n >= 3 && c1 == c2) ? 1u : 0u;
+  if (del && (b0 == kDel || (n >= 2 && b1 == kDel))) {
+    // the deletion allele is one of the two leading alleles.  Next to the reference allele: "heterozygous deletion", no
+    // genotype (GermlineThresholdCaller.scala:146-149) — by far the commonest case.  Alone or next to an alternate base
+    // its record carries an empty allele string: the exact kernel writes it.
+    if (n >= 2 && (b0 == kDel ? b1 : b0) == rcode) {
+      if (tie) atomicAdd(&out.counters[4], 1ull);
+      return;
+    }
+    defer_locus(out, contig, locus, stage);
+    return;
+  }
   if (tie) atomicAdd(&out.counters[4], 1ull);
   int ne = 0, alt0 = 0, alt1 = 0;  // alt: 0 = "<ALT>", 1 + base code otherwise
   uint32_t g0 = 0, g1 = 0;
@@ -1088,24 +1105,50 @@ __global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, con
 }
 
 // ---- record egress: the tiles' sorted slices laid out in tile order (compact germline records) ------------------------------
-// tile_n[] is scanned per segment (k_scan_* of guac_synth_device.cuh); thread per tile: its records go behind those of the
-// earlier tiles and segments (whose counts are final: the tile kernels of a call run in order), to the pinned host block of
-// the result and to the contiguous device copy the NCCL gather sends from.
+// One block per 256 tiles of a segment: the block sums tile_n[] of every earlier tile itself (a few hundred kilobytes from L2;
+// no scan kernels in front of it: the whole egress is two small launches that fit next to the exact kernel) and scans its
+// own 256 counts; thread per tile: its records go behind those of the earlier tiles and segments (whose counts are final: the
+// tile kernels of a call run in order), to the contiguous device copy that k_rec_to_host and the NCCL gather send from.
 __global__ void __launch_bounds__(256) k_rec_gather(const unsigned long long* __restrict__ rec, const uint32_t* __restrict__ tile_base,
-                                                    const uint32_t* __restrict__ tile_n, const uint32_t* __restrict__ prefix, uint32_t n_tiles,
+                                                    const uint32_t* __restrict__ tile_n, uint32_t n_tiles,
                                                     const unsigned long long* counters, uint32_t seg, uint32_t cap_seg,
                                                     unsigned long long* __restrict__ dev_rec, unsigned long long cap_total) {
+  __shared__ unsigned long long warp_sum[8];
+  __shared__ uint32_t warp_n[8];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   unsigned long long seg_base = 0;
   for (uint32_t j = 0; j < seg; ++j) seg_base += min(counters[12 + j], (unsigned long long)cap_seg);
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
-    const uint32_t n = tile_n[t];
-    if (!n) continue;
-    const unsigned long long dst = seg_base + prefix[t];
-    const uint32_t src = tile_base[t];
-    for (uint32_t i = 0; i < n; ++i) {
-      if (dst + i >= cap_total || src + i >= cap_seg) break;
-      dev_rec[dst + i] = rec[src + i];
+  const uint32_t t0 = blockIdx.x * 256u;  // (a multiple of 4: tile_n is read 16 bytes at a time; the host aligns it)
+  unsigned long long before = 0;
+  {
+    const uint4* n4 = reinterpret_cast<const uint4*>(tile_n);
+    for (uint32_t i = threadIdx.x; i < t0 / 4u; i += 256u) {
+      const uint4 v = __ldg(n4 + i);
+      before += (unsigned long long)v.x + v.y + v.z + v.w;
     }
+    for (int o = 16; o; o >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, o);
+  }
+  const uint32_t t = t0 + threadIdx.x;
+  const uint32_t n = t < n_tiles ? tile_n[t] : 0u;
+  uint32_t incl = n;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= (uint32_t)o) incl += u;
+  }
+  if (lane == 31u) warp_n[warp] = incl;
+  if (lane == 0u) warp_sum[warp] = before;
+  __syncthreads();
+  unsigned long long dst = seg_base + (incl - n);
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    dst += warp_sum[w];
+    if ((uint32_t)w < warp) dst += warp_n[w];
+  }
+  if (!n) return;
+  const uint32_t src = tile_base[t];
+  for (uint32_t i = 0; i < n; ++i) {
+    if (dst + i >= cap_total || src + i >= cap_seg) break;
+    dev_rec[dst + i] = rec[src + i];
   }
 }
 

@@ -11,7 +11,10 @@
 //             in the likelihood table (64 rows of 64 double2).  Column k of the word holds the k-th
 //             element of each of its 32 loci; loci with fewer elements are filled with a sentinel that reads a zero row of
 //             the likelihood table.  Two columns per 32-bit word per locus: the likelihood kernel streams 128 coalesced bytes
-//             per two columns and does nothing per element but one table look-up and two additions;
+//             per two columns and does nothing per element but one table look-up and two additions.  Elements that carry
+//             the reference base fill a locus' column from the FRONT, the mismatching ones (a percent) from the BACK, the
+//             sentinels sit in between: only the word's last block(s) of columns — how many is in the header — can hold an
+//             element whose class is not 0, every other block is summed without looking at the class bits;
 //   depth     the number of plain elements per locus (u16);
 //   rows      the other reads (insertions / deletions / skips / non-ACGT bases / wide qualities), two rows of 32 bytes each:
 //             the element class per locus (0xF8 | base code = plain base, 0xFE = an element that is not a plain base, 0xFD =
@@ -29,10 +32,20 @@ constexpr uint32_t kElemNone = 0xFFu, kElemOther = 0xFEu, kElemHard = 0xFDu, kEl
 constexpr uint32_t kRankZero = 63u;        // rank of the sentinel element: the all-zero row of the likelihood table
 constexpr uint32_t kMaxRank = 62u;         // reads whose mapping quality ranks at or beyond this take the general rows
 constexpr uint32_t kSentinel = kRankZero << 10;
+constexpr uint32_t kSentinel2 = kSentinel | (kSentinel << 16);
+constexpr uint32_t kRareAll = 255u;        // header value: "any block may hold a mismatching element"
+
+// halfword j (0..7) of a block of eight column elements held in four registers (no dynamic register index)
+__device__ __forceinline__ void set_half(uint32_t (&p)[4], uint32_t j, uint32_t elem) {
+  const uint32_t sh = 16u * (j & 1u), keep = ~(0xFFFFu << sh), v = elem << sh;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = (j >> 1) == (uint32_t)i ? ((p[i] & keep) | v) : p[i];
+}
 
 struct RowsArgs {
   DevReads R;
-  uint4* hdr_w;                // per word: {first column pair, columns, first row group, rows | highest rank << 24}
+  uint4* hdr_w;                // per word: {first column block, columns | trailing blocks with mismatches << 24, first row group,
+                               //            rows | highest rank << 24}
   uint16_t* depth_w;           // per locus: plain elements
   uint32_t* cols_w;            // per (block of eight columns, lane): 16 bytes
   uint4* groups_w;
@@ -43,6 +56,7 @@ struct RowsArgs {
   uint32_t pad_;
   unsigned long long* counters;  // [4] column blocks reserved, [5] row groups reserved
   uint32_t mapq_mask[8];         // mapping qualities present in the read set (k_header)
+  DevError* err;
 };
 
 constexpr int kRowsWarps = 8;
@@ -87,21 +101,34 @@ __global__ void __launch_bounds__(kRowsWarps * 32) k_expand_rows(RowsArgs A) {
   narrow_candidates(R, first, last, span_lo, span_lo + 32);
   constexpr uint32_t kLeanMask = kInfoSimple | kInfoHasExc | kInfoWideQ;
   const uint32_t rcode = ((R.trk_lo[W] >> lane) & 1u) | (((R.trk_hi[W] >> lane) & 1u) << 1);  // this locus' reference code
+  const bool std_ref = (R.trk_std[W] >> lane) & 1u;  // (no reference class without a standard reference base: all elements in front)
 
-  uint32_t depth = 0, n_cols = 0, max_rank = 0, n_rows = 0;
+  uint32_t depth = 0, n_cols = 0, max_rank = 0, n_rows = 0, slots = 0;
   unsigned long long coff = 0, goff = 0;
   uint32_t acc = 0, hacc[4] = {0u, 0u, 0u, 0u};
   for (int pass = 0; pass < 2; ++pass) {
-    uint32_t row = 0, k = 0, pend[4] = {0u, 0u, 0u, 0u};
-    auto put = [&](uint32_t elem) {  // this lane's next column element; eight columns (16 bytes per locus) leave together
-      const uint32_t j = k & 7u;
-      const uint32_t v = elem << (16 * (j & 1u));
-      pend[0] = (j >> 1) == 0u ? (j & 1u ? pend[0] | v : v) : pend[0];
-      pend[1] = (j >> 1) == 1u ? (j & 1u ? pend[1] | v : v) : pend[1];
-      pend[2] = (j >> 1) == 2u ? (j & 1u ? pend[2] | v : v) : pend[2];
-      pend[3] = (j >> 1) == 3u ? (j & 1u ? pend[3] | v : v) : pend[3];
-      if (j == 7u) reinterpret_cast<uint4*>(A.cols_w)[((size_t)coff + (k >> 3)) * 32 + lane] = make_uint4(pend[0], pend[1], pend[2], pend[3]);
-      ++k;
+    uint32_t row = 0, kf = 0, kb = 0;
+    uint32_t pf[4] = {kSentinel2, kSentinel2, kSentinel2, kSentinel2}, pb[4] = {kSentinel2, kSentinel2, kSentinel2, kSentinel2};
+    uint4* const blocks_w = reinterpret_cast<uint4*>(A.cols_w) + (size_t)coff * 32 + lane;
+    // this lane's next column element: reference-class elements from the front, the others from the back; a block of eight
+    // columns (16 bytes per locus) leaves when it is full
+    auto put = [&](uint32_t elem) {
+      if ((elem & 3u) == 0u || !std_ref) {
+        set_half(pf, kf & 7u, elem);
+        if ((kf & 7u) == 7u) {
+          blocks_w[(size_t)(kf >> 3) * 32] = make_uint4(pf[0], pf[1], pf[2], pf[3]);
+          pf[0] = pf[1] = pf[2] = pf[3] = kSentinel2;
+        }
+        ++kf;
+      } else {
+        const uint32_t pos = slots - 1u - kb;
+        set_half(pb, pos & 7u, elem);
+        if ((pos & 7u) == 0u) {
+          blocks_w[(size_t)(pos >> 3) * 32] = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+          pb[0] = pb[1] = pb[2] = pb[3] = kSentinel2;
+        }
+        ++kb;
+      }
     };
     auto append = [&](uint32_t header, uint32_t byte) {  // warp-uniform call; `byte` per lane
       const uint32_t j = row & 3u;
@@ -176,6 +203,8 @@ __global__ void __launch_bounds__(kRowsWarps * 32) k_expand_rows(RowsArgs A) {
       n_cols = __reduce_max_sync(0xFFFFFFFFu, depth);
       max_rank = __reduce_max_sync(0xFFFFFFFFu, max_rank);
       const uint32_t pairs = (n_cols + 7u) >> 3, groups = (n_rows + 3u) >> 2;  // (blocks of eight columns)
+      slots = pairs << 3;
+      if (n_cols > 0xFFFFFFu) { report_error(A.err, GUAC_ERR_UNSUPPORTED, (unsigned long long)W); return; }
       if (lane == 0) {
         coff = atomicAdd(&A.counters[4], (unsigned long long)pairs);
         goff = atomicAdd(&A.counters[5], (unsigned long long)groups);
@@ -183,12 +212,32 @@ __global__ void __launch_bounds__(kRowsWarps * 32) k_expand_rows(RowsArgs A) {
       coff = __shfl_sync(0xFFFFFFFFu, coff, 0);
       goff = __shfl_sync(0xFFFFFFFFu, goff, 0);
       const bool fits = coff + pairs <= A.cap_pairs && goff + groups <= A.cap_groups;  // (else the host grows the buffers and repeats)
-      if (lane == 0) A.hdr_w[W] = make_uint4((uint32_t)coff, n_cols, (uint32_t)goff, n_rows | (max_rank << 24));
+      if (lane == 0) A.hdr_w[W] = make_uint4((uint32_t)coff, n_cols | (kRareAll << 24), (uint32_t)goff, n_rows | (max_rank << 24));
       A.depth_w[(size_t)W * 32 + lane] = (uint16_t)min(depth, 0xFFFFu);
       if (!fits || (n_cols == 0 && n_rows == 0)) return;
     } else {
-      const uint32_t slots = ((n_cols + 7u) >> 3) << 3;  // loci with fewer elements: sentinels up to the word's last block of columns
-      while (k < slots) put(kSentinel);
+      // the free positions [kf, slots - kb) of this lane's column hold sentinels: the two partial blocks (one, where front and
+      // back meet inside a block) and the whole blocks in between
+      const uint32_t free_lo = kf, free_hi = slots - kb;
+      const bool part_f = (free_lo & 7u) != 0u, part_b = (free_hi & 7u) != 0u;
+      if (part_f && part_b && (free_lo >> 3) == (free_hi >> 3)) {
+        const uint32_t nf = free_lo & 7u;  // halfwords below nf come from the front block, the others from the back block
+        uint32_t m[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t lo = (uint32_t)(2 * i) < nf ? pf[i] : pb[i], hi = (uint32_t)(2 * i + 1) < nf ? pf[i] : pb[i];
+          m[i] = (lo & 0xFFFFu) | (hi & 0xFFFF0000u);
+        }
+        blocks_w[(size_t)(free_lo >> 3) * 32] = make_uint4(m[0], m[1], m[2], m[3]);
+      } else {
+        if (part_f) blocks_w[(size_t)(free_lo >> 3) * 32] = make_uint4(pf[0], pf[1], pf[2], pf[3]);
+        if (part_b) blocks_w[(size_t)(free_hi >> 3) * 32] = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+      }
+      for (uint32_t b = (free_lo + 7u) >> 3; b < (free_hi >> 3); ++b) blocks_w[(size_t)b * 32] = make_uint4(kSentinel2, kSentinel2, kSentinel2, kSentinel2);
+      // trailing blocks that hold an element of a mismatch class on some lane
+      const uint32_t max_back = __reduce_max_sync(0xFFFFFFFFu, kb);
+      const uint32_t rare_blocks = max_back ? (slots >> 3) - ((slots - max_back) >> 3) : 0u;
+      if (lane == 0) A.hdr_w[W] = make_uint4((uint32_t)coff, n_cols | (min(rare_blocks, kRareAll) << 24), (uint32_t)goff, n_rows | (max_rank << 24));
       if (row & 3u) {  // the last, partial group of rows
         const size_t grp = (size_t)goff + (row >> 2);
         A.rows_w[grp * 32 + lane] = acc;

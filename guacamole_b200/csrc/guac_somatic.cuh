@@ -615,6 +615,7 @@ struct RowTables {
 struct SomSmem {
   double2 tumor[kSomTabRows * 64];
   double2 normal[2 * 64];
+  uint4 hdr[kTileWords];   // the tumor sample's word headers of this CTA's tile
 };
 
 __device__ __forceinline__ double2 lds_double2(uint32_t shared_addr) {
@@ -623,14 +624,31 @@ __device__ __forceinline__ double2 lds_double2(uint32_t shared_addr) {
   return v;
 }
 
+// L2 prefetch of everything gather_rows streams for one word (its header is known already): the kernel handles a word in about
+// the time of two DRAM round trips, so the word after this one is requested while this one is summed
+__device__ __forceinline__ void prefetch_rows(const DevReads& R, const uint32_t word, const uint4 wh) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t blocks = ((wh.y & 0xFFFFFFu) + 7u) >> 3, groups = ((wh.w & 0xFFFFFFu) + 3u) >> 2;
+  const uint4* cp = reinterpret_cast<const uint4*>(R.q_cols) + (size_t)wh.x * 32 + lane;
+  if ((lane & 1u) == 0u)  // (one request per 32-byte sector)
+    for (uint32_t b = 0; b < blocks; ++b) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp + (size_t)b * 32));
+  if (lane < 2u) asm volatile("prefetch.global.L2 [%0];" ::"l"(R.q_depth + (size_t)word * 32 + lane * 16));
+  if (lane < groups) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(R.q_groups + wh.z + lane));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(R.q_rows + ((size_t)wh.z + lane) * 32));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(R.q_rows + ((size_t)wh.z + lane) * 32 + 16));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(R.q_rows + ((size_t)wh.z + lane) * 32 + 24));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(R.q_rows + ((size_t)wh.z + lane) * 32 + 8));
+  }
+}
+
 template <bool TUMOR>
-__device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t word, const int rcode, const bool std_ref, const SomParams& prm,
+__device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t word, const uint4 wh, const int rcode, const bool std_ref, const SomParams& prm,
                                             const uint32_t smem_table /* shared address of SomSmem */, const RowTables& rt,
                                             const double* __restrict__ tables, LaneAcc& A) {
   const uint32_t lane = threadIdx.x & 31u;
   acc_clear(A);
-  const uint4 wh = R.q_hdr[word];
-  const uint32_t n_cols = wh.y, n_rows = wh.w & 0xFFFFFFu, max_rank = wh.w >> 24;
+  const uint32_t n_cols = wh.y & 0xFFFFFFu, n_rows = wh.w & 0xFFFFFFu, max_rank = wh.w >> 24;
   const uint32_t depth_all = R.q_depth[(size_t)word * 32 + lane];
   const double2* __restrict__ gtab = reinterpret_cast<const double2*>(tables + (TUMOR ? kTabT : kTabN));
   const uint32_t tab = TUMOR ? smem_table : smem_table + (uint32_t)(kSomTabRows * 64 * sizeof(double2));
@@ -662,6 +680,10 @@ __device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t wo
     auto entry = [&](const uint32_t e) -> uint32_t {
       return TUMOR ? (e & 0xFFF0u) : (e & 0x03F0u) + (((e >> 10) & 63u) < n_keep ? 0u : 1024u);
     };
+    // Elements of a mismatch class sit in the word's last blocks only (k_expand_rows fills a column with reference-class
+    // elements from the front, the others from the back): every block before `first_rare` is summed without a class test.
+    const uint32_t rare_blocks = wh.y >> 24;
+    const uint32_t first_rare = rare_blocks >= kRareAll ? 0u : blocks - min(rare_blocks, blocks);
     uint4 v = __ldg(cp), v_next = v;
     if (blocks > 1) v_next = __ldg(cp + 32);
     for (uint32_t p = 0; p < blocks; ++p) {
@@ -669,17 +691,8 @@ __device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t wo
       v = v_next;
       if (p + 2 < blocks) v_next = __ldg(cp + (size_t)(p + 2) * 32);  // two blocks are on their way while this one is summed
       const uint32_t w4[4] = {v_now.x, v_now.y, v_now.z, v_now.w};
-      // the hot loop: per element one table look-up and two additions, the second one only for elements that carry the
-      // reference base (class 0); the others (a percent of them) are handled below
-      if (!nostd) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t e = (j & 1) ? (w4[j >> 1] >> 16) : w4[j >> 1];  // (even elements: the upper half word is masked off below)
-          const double2 l = lds_double2(tab + entry(e));
-          A.t0 += l.y;
-          asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p add.f64 %0, %0, %1;\n\t}" : "+d"(sr1) : "d"(l.x), "r"(e & 3u));  // a predicated add, no select
-        }
-      } else {  // (rare lanes) every element is of a mismatch class
+      const bool tail = p >= first_rare;  // (warp-uniform)
+      if (nostd) {  // (rare lanes) every element is of a mismatch class
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
           const uint32_t wj = j < 2 ? w4[0] : j < 4 ? w4[1] : j < 6 ? w4[2] : w4[3];
@@ -688,28 +701,48 @@ __device__ __forceinline__ void gather_rows(const DevReads& R, const uint32_t wo
           A.t0 += l.y;
           non_ref(e & 3u, e >> 10, l);
         }
-      }
-      if (check) {  // (rare words) elements dropped by the mapq filter: n_keep <= rank < the sentinel's
-#pragma unroll 1
+      } else if (!tail) {
+        // the hot loop: per element one table look-up and two additions (every element here carries the reference base or is
+        // the sentinel, whose table row is zero)
+#pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint32_t wj = j < 2 ? w4[0] : j < 4 ? w4[1] : j < 6 ? w4[2] : w4[3];
-          const uint32_t rank = (((j & 1) ? (wj >> 16) : wj) >> 10) & 63u;
-          dropped += (rank - n_keep) < (kRankZero - n_keep) ? 1u : 0u;
+          const uint32_t e = (j & 1) ? (w4[j >> 1] >> 16) : w4[j >> 1];  // (even elements: the upper half word is masked off below)
+          const double2 l = lds_double2(tab + entry(e));
+          A.t0 += l.y;
+          sr1 += l.x;
+        }
+      } else {
+        // the word's last block(s): the second addition only for elements of class 0, the others are handled below
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t e = (j & 1) ? (w4[j >> 1] >> 16) : w4[j >> 1];
+          const double2 l = lds_double2(tab + entry(e));
+          A.t0 += l.y;
+          asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p add.f64 %0, %0, %1;\n\t}" : "+d"(sr1) : "d"(l.x), "r"(e & 3u));  // a predicated add, no select
+        }
+        if (((w4[0] | w4[1]) | (w4[2] | w4[3])) & 0x00030003u) {  // (divergent) some element of this lane is not of class 0
+          uint32_t rare = 0;  // bit j: element j's class is not 0
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t m = (w4[k] | (w4[k] >> 1)) & 0x00010001u;
+            rare |= ((m | (m >> 15)) & 3u) << (2 * k);
+          }
+          while (rare) {
+            const int j = __ffs(rare) - 1;
+            rare &= rare - 1;
+            const uint32_t wj = j < 2 ? w4[0] : j < 4 ? w4[1] : j < 6 ? w4[2] : w4[3];
+            const uint32_t e = ((j & 1) ? (wj >> 16) : wj) & 0xFFFFu;
+            non_ref(e & 3u, e >> 10, lds_double2(tab + entry(e)));
+          }
         }
       }
-      if (!nostd && (((w4[0] | w4[1]) | (w4[2] | w4[3])) & 0x00030003u)) {  // (divergent, rare) some element is not of class 0
-        uint32_t rare = 0;  // bit j: element j's class is not 0
+      if (check) {  // (rare words) elements dropped by the mapq filter: n_keep <= rank < the sentinel's.  Two elements per word:
+        // bit 6 of (rank + 64 - n_keep) says rank >= n_keep, bit 6 of (rank + 1) says rank == 63
+        const uint32_t ge = (64u - n_keep) * 0x00010001u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t m = (w4[k] | (w4[k] >> 1)) & 0x00010001u;
-          rare |= ((m | (m >> 15)) & 3u) << (2 * k);
-        }
-        while (rare) {
-          const int j = __ffs(rare) - 1;
-          rare &= rare - 1;
-          const uint32_t wj = j < 2 ? w4[0] : j < 4 ? w4[1] : j < 6 ? w4[2] : w4[3];
-          const uint32_t e = ((j & 1) ? (wj >> 16) : wj) & 0xFFFFu;
-          non_ref(e & 3u, e >> 10, lds_double2(tab + entry(e)));
+          const uint32_t r2 = (w4[k] >> 10) & 0x003F003Fu;
+          dropped += __popc((r2 + ge) & ~(r2 + 0x00010001u) & 0x00400040u);
         }
       }
     }
@@ -809,11 +842,17 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
     for (int i = threadIdx.x; i < kSomTabRows * 64; i += kSomThreads)
       Tw.tumor[i] = (i >> 6) < live ? gt[((int)rt.row_mapq[i >> 6] << 8) + (i & 63)] : make_double2(0.0, 0.0);
     for (int i = threadIdx.x; i < 128; i += kSomThreads) Tw.normal[i] = i < 64 ? gn[i] : make_double2(0.0, 0.0);
-    __syncthreads();
   }
   const TileDesc td = tiles[blockIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const ContigInfo ciT = RT.contigs[td.contig], ciN = RN.contigs[td.contig];
+  if (ROWS) {
+    SomSmem& Tw = *reinterpret_cast<SomSmem*>(som_smem_raw);
+    for (int i = threadIdx.x; i < kTileWords; i += kSomThreads)
+      Tw.hdr[i] = td.word0 + i < ciT.n_words ? RT.q_hdr[ciT.word_off + (uint32_t)(td.word0 + i)] : make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+  }
+  const uint4* const tile_hdr = reinterpret_cast<const SomSmem*>(som_smem_raw)->hdr;
   uint32_t n_visited = 0;
   for (int wi = warp; wi < kTileWords; wi += kSomThreads / 32) {
     const int w = td.word0 + wi;
@@ -828,7 +867,9 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
     const bool stdT = (ts >> lane) & 1u, stdN = (ns >> lane) & 1u;
     LaneAcc AT, AN;
     if (ROWS) {
-      if (w < ciT.n_words) gather_rows<true>(RT, ciT.word_off + (uint32_t)w, rcT, stdT, prm, smem_table, rt, tables, AT);
+      const int wn = wi + kSomThreads / 32;  // this warp's next word
+      if (wn < kTileWords && td.word0 + wn < ciT.n_words) prefetch_rows(RT, ciT.word_off + (uint32_t)(td.word0 + wn), tile_hdr[wn]);
+      if (w < ciT.n_words) gather_rows<true>(RT, ciT.word_off + (uint32_t)w, tile_hdr[wi], rcT, stdT, prm, smem_table, rt, tables, AT);
       else acc_clear(AT);
     } else {
       gather_sample<true>(RT, td.contig, span_lo, x, rcT, stdT, prm, tables, AT);
@@ -860,7 +901,7 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
     if (in_req && AT.any > 0) ++n_visited;
     if (!__any_sync(0xFFFFFFFFu, need_normal)) continue;
     if (ROWS) {
-      if (w < ciN.n_words) gather_rows<false>(RN, ciN.word_off + (uint32_t)w, rcN, stdN, prm, smem_table, rt, tables, AN);
+      if (w < ciN.n_words) gather_rows<false>(RN, ciN.word_off + (uint32_t)w, RN.q_hdr[ciN.word_off + (uint32_t)w], rcN, stdN, prm, smem_table, rt, tables, AN);
       else acc_clear(AN);
     } else {
       gather_sample<false>(RN, td.contig, span_lo, x, rcN, stdN, prm, tables, AN);

@@ -64,6 +64,7 @@ struct ExpandArgs {
   uint16_t* diffs_w;
   uint8_t* dd_w;
   uint8_t* dp_w;
+  uint32_t* imp_w;
   unsigned long long cap_diffs;    // entries gs_diffs can hold
   uint32_t g_begin, g_end;         // granules (global index) this launch covers
   uint32_t n_contigs;
@@ -79,6 +80,7 @@ struct ExpandSmem {
   using Word = typename std::conditional<HUGE, unsigned long long, uint32_t>::type;
   Word st[kCntWords], en[kCntWords];
   uint32_t ref_lo[kWarpWords], ref_hi[kWarpWords], ref_std[kWarpWords];
+  uint32_t imp[kWarpWords];  // loci with an "other" element that is not a mid-deletion element carrying the track's base
   alignas(16) uint16_t stage[kStageCap];
   uint32_t cursor;
   uint32_t pad_[3];
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32) k_expand(ExpandArgs A) {
     S.ref_lo[lane] = in ? R.trk_lo[ci.word_off + w] : 0u;
     S.ref_hi[lane] = in ? R.trk_hi[ci.word_off + w] : 0u;
     S.ref_std[lane] = in ? R.trk_std[ci.word_off + w] : 0u;
+    S.imp[lane] = 0u;
   }
   if (lane == 0) S.cursor = 0;
   uint32_t first = R.gran_first[g], last = R.gran_last[g];
@@ -130,10 +133,39 @@ __global__ void __launch_bounds__(kExpandWarps * 32) k_expand(ExpandArgs A) {
     if (direct) direct[slot] = e;
     else if (slot < (uint32_t)kStageCap) S.stage[slot] = e;
   };
+  auto impure = [&](int x) {  // (idempotent: the second walk of a deep granule sets the same bits)
+    const uint32_t bit = 1u << (x & 31);
+    if (!(S.imp[x >> 5] & bit)) atomicOr(&S.imp[x >> 5], bit);
+  };
   auto other = [&](int lo, int hi) {  // reference positions [lo, hi) of this lane's read hold elements that are not plain bases
     lo = max(lo, tile_lo);
     hi = min(hi, tile_hi);
-    for (int p = lo; p < hi; ++p) append(p - tile_lo, 0u);
+    for (int p = lo; p < hi; ++p) {
+      append(p - tile_lo, 0u);
+      impure(p - tile_lo);
+    }
+  };
+  // deleted loci [lo, hi) of read r: MidDeletion elements, allele (deleted base, "") (PileupElement.scala:121-123).  Where the
+  // deleted base of the MD tag is the track's base, all such elements of the locus are ONE allele and k_call_tile decides the
+  // locus from its counters; anything else (no cached tag offset, a non-standard or disagreeing base) marks the locus impure.
+  auto deleted = [&](uint32_t r, int lo, int hi) {
+    lo = max(lo, tile_lo);
+    hi = min(hi, tile_hi);
+    if (lo >= hi) return;
+    const int d0 = R.del_start[r], dn = (int)R.del_len[r];
+    const char* md = R.md + R.md_off[r] + R.del_md[r];
+    for (int p = lo; p < hi; ++p) {
+      const int x = p - tile_lo;
+      append(x, 0u);
+      bool same = false;
+      if (d0 >= 0 && p >= d0 && p < d0 + dn) {
+        const uint8_t ch = (uint8_t)md[p - d0];
+        const uint32_t w = (uint32_t)x >> 5, b = (uint32_t)x & 31u;
+        same = is_std_base(ch) && ((S.ref_std[w] >> b) & 1u) &&
+               base_code(ch) == (((S.ref_lo[w] >> b) & 1u) | (((S.ref_hi[w] >> b) & 1u) << 1));
+      }
+      if (!same) impure(x);
+    }
   };
   // one plain M/=/X run [seg_ref, seg_ref + seg_len) whose first base is read base seg_read
   auto segment = [&](const ReadRec& rec, int seg_ref, int seg_read, int seg_len, bool has_exc) {
@@ -163,6 +195,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32) k_expand(ExpandArgs A) {
       pa = pb;
       xa = xb;
       uint32_t d = x | y | oth;
+      if (oth && (S.imp[w] & oth) != oth) atomicOr(&S.imp[w], oth);  // a non-ACGT read base is its own allele
       while (d) {
         const int b = __ffs(d) - 1;
         d &= d - 1;
@@ -202,8 +235,11 @@ __global__ void __launch_bounds__(kExpandWarps * 32) k_expand(ExpandArgs A) {
         segment(rec, seg_ref, seg_read, seg_len, has_exc);
         ref_pos += len;
         read_pos += len;
-      } else if (op == GUAC_CIGAR_D || op == GUAC_CIGAR_N) {
-        other(ref_pos, ref_pos + len);  // mid-deletion / skipped loci
+      } else if (op == GUAC_CIGAR_D) {
+        deleted(r, ref_pos, ref_pos + len);
+        ref_pos += len;
+      } else if (op == GUAC_CIGAR_N) {
+        other(ref_pos, ref_pos + len);  // skipped loci
         ref_pos += len;
       } else if (op == GUAC_CIGAR_I) {
         if (ref_pos == 0 && rec.start == 0) skip_first = true;
@@ -270,6 +306,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32) k_expand(ExpandArgs A) {
   constexpr Word HMASK = ((Word)1 << HB) - 1;
   bool overflow = false;
   const size_t locus0 = (size_t)g * kGranuleLoci + (size_t)lane * 32;
+  A.imp_w[(size_t)g * kWarpWords + lane] = S.imp[lane];
   if (!wide) {
     uint32_t wd[8], wp[8];
 #pragma unroll
@@ -332,7 +369,7 @@ struct CallSmem {
 template <bool WIDE, int MODE>
 __device__ __forceinline__ void tile_call_locus(const uint32_t* cnt, const DevReads& R, const TileDesc& td, const CallParams& prm,
                                                 DevOut& out, const int x, const int total, const int pos_total, const bool every_covered,
-                                                const bool all_loci, EmitStage* stage) {
+                                                const bool all_loci, const bool pure, EmitStage* stage) {
   if (total == 0 && !all_loci) return;  // callVariantsAtLocus returns nothing on an empty pileup
   using L = CntLayout<WIDE>;
   const int o = (int)L::field(cnt, x, 0), m1 = (int)L::field(cnt, x, 1), m2 = (int)L::field(cnt, x, 2), m3 = (int)L::field(cnt, x, 3);
@@ -366,7 +403,7 @@ __device__ __forceinline__ void tile_call_locus(const uint32_t* cnt, const DevRe
     }
     return;
   }
-  call_snv_locus(prm, out, td.contig, locus, total, o, m1, m2, m3, rcode, std_ref, every_covered, stage);
+  call_snv_locus(prm, out, td.contig, locus, total, o, m1, m2, m3, rcode, std_ref, every_covered, pure, stage);
 }
 
 __device__ __forceinline__ uint32_t pick8(const uint32_t (&v)[8], int i) {  // v[i] without dynamic register indexing
@@ -474,7 +511,10 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_call_tile(DevReads R, const
   const uint32_t in_range = bit_range(td.locus_begin - l0, td.locus_end - l0);
   uint32_t n_visited = 0;
   bool overflow = false;
+  // the lane's word of the impure mask, read only where a locus gets that far (nothing of it is kept live across the scan)
+  auto imp_word = [&]() { return __ldg(R.gs_imp + (size_t)__ldg(&tiles[tile].gran) * kWarpWords + lane); };
   if (WIDE || dense) {
+    const uint32_t my_imp = MODE == 0 ? imp_word() : 0xFFFFFFFFu;
     // the general loop, one locus at a time: deep pileups (wide stores) and the dense outputs (counts, emit-ref / emit-no-call)
 #pragma unroll 1
     for (int kk = 0; kk < 32; ++kk) {
@@ -498,7 +538,7 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_call_tile(DevReads R, const
       const bool std_ref = (my_std >> kk) & 1u;
       if (!dense && differing == 0u && std_ref) continue;  // every element matches the reference: nothing to call
       if (!dense && std_ref && (unsigned long long)differing * 100ull < (unsigned long long)thr_plus_1 * (unsigned long long)(uint32_t)dep) continue;
-      tile_call_locus<WIDE, MODE>(S.cnt, R, td, prm, out, x, dep, pdep, every_covered, all_loci, &S.stage);
+      tile_call_locus<WIDE, MODE>(S.cnt, R, td, prm, out, x, dep, pdep, every_covered, all_loci, !((my_imp >> kk) & 1u), &S.stage);
     }
   } else {
     // sparse calls over 8-bit counter fields, four consecutive loci per step.  The few loci that survive the reject are
@@ -551,6 +591,7 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_call_tile(DevReads R, const
         survivors |= 1u << (4 * j + k);
       }
     }
+    const uint32_t my_imp = survivors ? imp_word() : 0u;
     while (survivors) {
       const int kk = __ffs(survivors) - 1;
       survivors &= survivors - 1;
@@ -560,7 +601,7 @@ __global__ void __launch_bounds__(kTileThreads, 8) k_call_tile(DevReads R, const
         const uint32_t m = j < (kk >> 2) ? 0x0F0F0F0Fu : j == (kk >> 2) ? (0x0F0F0F0Fu >> (8 * (3 - (kk & 3)))) : 0u;
         d += (int)__dp4a(dd[j] & m, kOnes, 0u) - (int)__dp4a((dd[j] >> 4) & m, kOnes, 0u);
       }
-      tile_call_locus<WIDE, MODE>(S.cnt, R, td, prm, out, (lane << 5) + kk, d, 0, every_covered, all_loci, &S.stage);
+      tile_call_locus<WIDE, MODE>(S.cnt, R, td, prm, out, (lane << 5) + kk, d, 0, every_covered, all_loci, !((my_imp >> kk) & 1u), &S.stage);
     }
   }
   flush_stage(out, &S.stage, tile);
