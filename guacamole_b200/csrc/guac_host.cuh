@@ -209,6 +209,8 @@ struct guac_ctx {
   DevBuf<unsigned char> out_rec, out_pool, out_slow, out_compact, tiles, sort_rec;
   DevBuf<uint32_t> sort_bins;
   DevBuf<uint64_t> scan_totals;
+  DevBuf<uint32_t> ord_u32;             // device-side canonical ordering of the likelihood callers' records (guac_order.cuh)
+  DevBuf<unsigned char> ord_out;
   std::vector<guac_locus_range> tiles_key_ranges;
   uint64_t tiles_key_reads = 0;  // guac_reads::id of the cached tile list (0 = none)
   uint64_t tiles_key_loci = 0, n_tiles = 0;

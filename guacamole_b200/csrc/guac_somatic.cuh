@@ -25,6 +25,7 @@
 #include "guac_host.cuh"
 #include "guac_pileup.cuh"
 #include "guac_rows.cuh"
+#include "guac_order.cuh"
 
 namespace guac {
 
@@ -830,8 +831,8 @@ constexpr int kSomThreads = 256;
 // ROWS: the samples' pileup elements come from their row stores (guac_rows.cuh); otherwise every word walks its candidate
 // reads (gather_sample) — the path of stores packed without rows, and the cross-check the parity tests run.
 template <bool ROWS>
-__global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads RT, DevReads RN, const TileDesc* __restrict__ tiles, SomParams prm,
-                                                        const double* __restrict__ tables, RowTables rt, SomOut out) {
+__global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads RT, DevReads RN, const TileDesc* __restrict__ tiles, uint32_t n_tiles,
+                                                        SomParams prm, const double* __restrict__ tables, RowTables rt, SomOut out) {
   extern __shared__ __align__(16) unsigned char som_smem_raw[];
   const uint32_t smem_table = (uint32_t)__cvta_generic_to_shared(som_smem_raw);
   if (ROWS) {  // the CTA's copy of the table: kept mapping qualities' rows, zero rows for everything else
@@ -843,17 +844,20 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
       Tw.tumor[i] = (i >> 6) < live ? gt[((int)rt.row_mapq[i >> 6] << 8) + (i & 63)] : make_double2(0.0, 0.0);
     for (int i = threadIdx.x; i < 128; i += kSomThreads) Tw.normal[i] = i < 64 ? gn[i] : make_double2(0.0, 0.0);
   }
-  const TileDesc td = tiles[blockIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint4* const tile_hdr = reinterpret_cast<const SomSmem*>(som_smem_raw)->hdr;
+  uint32_t n_visited = 0;
+  // a CTA stays for many tiles (the grid is what fits the device at once): its copy of the table is built once
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const TileDesc td = tiles[tile];
   const ContigInfo ciT = RT.contigs[td.contig], ciN = RN.contigs[td.contig];
   if (ROWS) {
     SomSmem& Tw = *reinterpret_cast<SomSmem*>(som_smem_raw);
+    __syncthreads();  // (every warp is done with the previous tile's headers; the first time: the table is complete)
     for (int i = threadIdx.x; i < kTileWords; i += kSomThreads)
       Tw.hdr[i] = td.word0 + i < ciT.n_words ? RT.q_hdr[ciT.word_off + (uint32_t)(td.word0 + i)] : make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
   }
-  const uint4* const tile_hdr = reinterpret_cast<const SomSmem*>(som_smem_raw)->hdr;
-  uint32_t n_visited = 0;
   for (int wi = warp; wi < kTileWords; wi += kSomThreads / 32) {
     const int w = td.word0 + wi;
     const int span_lo = w << 5, x = span_lo + lane;
@@ -925,6 +929,7 @@ __global__ void __launch_bounds__(kSomThreads, GUAC_SOM_MINB) k_somatic(DevReads
     const double normal_variants_total = snv_normal_variants_total(sN, rcN);
     emit_somatic(avT, snv_entry(c1, 0), snv_entry(c2, 0), tumor_l, normal_variants_total, td.contig, x, prm, out);
   }
+  }  // tiles
   for (int o = 16; o; o >>= 1) n_visited += __shfl_xor_sync(0xFFFFFFFFu, n_visited, o);
   if (lane == 0 && n_visited) atomicAdd(&out.counters[3], (unsigned long long)n_visited);
 }
@@ -1417,10 +1422,11 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
         CUDA_OK(cudaFuncSetAttribute(k_somatic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SomSmem)));
         ctx->som_attr_done = true;
       }
-      k_somatic<true><<<(int)tiles.size(), kSomThreads, sizeof(SomSmem), st>>>(RT, RN, d_tiles.p, prm, ctx->d_tables, rt, out);
+      const int grid = (int)std::min<size_t>(tiles.size(), (size_t)ctx->sm_count * GUAC_SOM_MINB);
+      k_somatic<true><<<grid, kSomThreads, sizeof(SomSmem), st>>>(RT, RN, d_tiles.p, (uint32_t)tiles.size(), prm, ctx->d_tables, rt, out);
     } else {
       RowTables rt{};
-      k_somatic<false><<<(int)tiles.size(), kSomThreads, 0, st>>>(RT, RN, d_tiles.p, prm, ctx->d_tables, rt, out);
+      k_somatic<false><<<(int)tiles.size(), kSomThreads, 0, st>>>(RT, RN, d_tiles.p, (uint32_t)tiles.size(), prm, ctx->d_tables, rt, out);
     }
     CUDA_OK(cudaEventRecord(ctx->ev[1], st));
     k_somatic_exact<<<ctx->sm_count * 32, kSomExactWarps * 32, 0, st>>>(RT, RN, out.slow, prm, ctx->d_tables, out);
@@ -1458,8 +1464,13 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
     if (!res.block) fail(GUAC_ERR_OOM, "pinned host allocation of %zu bytes failed", rec_at + rec_bytes + 64);
     unsigned char* hs = (unsigned char*)res.block;
     unsigned char* hrec = hs + rec_at;
+    // canonical order on the device (guac_order.cuh): the records cross PCIe in the order the caller sees them
+    const unsigned char* d_sorted = (const unsigned char*)d_final;
+    if (ctx->sort_records) d_sorted = device_order_records(ctx, tumor, d_sorted, (uint32_t)sizeof(guac_somatic_record), n_rec, ctx->out_pool.p);
+    const bool device_sorted = d_sorted != (const unsigned char*)d_final || n_rec < 2;
+    if (d_sorted != (const unsigned char*)d_final) res.stats.kernel_launches += 7;
     CUDA_OK(cudaMemcpyAsync(hs, ctx->out_pool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
-    if (n_rec) CUDA_OK(cudaMemcpyAsync(hrec, d_final, rec_bytes, cudaMemcpyDeviceToHost, st));
+    if (n_rec) CUDA_OK(cudaMemcpyAsync(hrec, d_sorted, rec_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
     tr.lap("d2h");
     res.stats.d2h_bytes = pool_bytes + rec_bytes + 64;
@@ -1467,7 +1478,7 @@ void run_somatic(guac_ctx* ctx, const guac_reads& tumor, const guac_reads& norma
     res.n_records = (size_t)n_rec;
     res.bytes = hs;
     res.n_bytes = pool_bytes;
-    if (ctx->sort_records) {
+    if (ctx->sort_records && !device_sorted) {
       const uint8_t* pool = hs;
       guac_somatic_record* first = (guac_somatic_record*)hrec;
       sort_records_canonical(first, (size_t)n_rec, [pool](const guac_somatic_record& a, const guac_somatic_record& b) {

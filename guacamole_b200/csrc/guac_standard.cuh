@@ -285,15 +285,19 @@ void run_standard(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range
     if (!res.block) fail(GUAC_ERR_OOM, "pinned host allocation of %zu bytes failed", rec_at + rec_bytes + 64);
     unsigned char* hs = (unsigned char*)res.block;
     unsigned char* hrec = hs + rec_at;
+    const unsigned char* d_sorted = ctx->out_rec.p;  // canonical order on the device (guac_order.cuh)
+    if (ctx->sort_records) d_sorted = device_order_records(ctx, reads, d_sorted, (uint32_t)sizeof(guac_called_allele), n_rec, ctx->out_pool.p);
+    const bool device_sorted = d_sorted != ctx->out_rec.p || n_rec < 2;
+    if (d_sorted != ctx->out_rec.p) res.stats.kernel_launches += 7;
     CUDA_OK(cudaMemcpyAsync(hs, ctx->out_pool.p, pool_bytes, cudaMemcpyDeviceToHost, st));
-    if (n_rec) CUDA_OK(cudaMemcpyAsync(hrec, ctx->out_rec.p, rec_bytes, cudaMemcpyDeviceToHost, st));
+    if (n_rec) CUDA_OK(cudaMemcpyAsync(hrec, d_sorted, rec_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
     res.stats.d2h_bytes = pool_bytes + rec_bytes + 64;
     res.records = hrec;
     res.n_records = (size_t)n_rec;
     res.bytes = hs;
     res.n_bytes = pool_bytes;
-    if (ctx->sort_records) {
+    if (ctx->sort_records && !device_sorted) {
       const uint8_t* pool = hs;
       guac_called_allele* first = (guac_called_allele*)hrec;
       sort_records_canonical(first, (size_t)n_rec, [pool](const guac_called_allele& a, const guac_called_allele& b) {
