@@ -173,6 +173,7 @@ OPT_PACK_QUALITIES = 2
 OPT_HOST_THREADS = 3
 OPT_DIFFERENCE_LISTS = 4
 OPT_SEGMENTS = 5
+OPT_TRIM_CACHE = 6
 
 
 def struct_to_dict(s):

@@ -443,6 +443,10 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
     int64_t len = b->contig_length ? b->contig_length[c] : contig_end[c];
     if (ref) len = std::max<int64_t>(len, (int64_t)(ref->base_off[c + 1] - ref->base_off[c]));
     if (len > 0x7FFFFF00ll) fail(GUAC_ERR_UNSUPPORTED, "contig longer than 2^31");
+    // Without a FASTA reference nothing is known about the loci behind a contig's last read (no pileup, reference base N:
+    // exactly what the loci past the track yield): the track, the granule index and the by-locus stores end with the reads,
+    // so a shard of a whole-genome dictionary pays for the loci it covers, not for 3 G loci of empty arrays.
+    if (!ref) len = std::min<int64_t>(len, (std::max<int64_t>(contig_end[c], 0) + kGranuleLoci - 1) / kGranuleLoci * kGranuleLoci);
     ci.read_begin = contig_first[c] == ~0ull ? 0 : contig_first[c];
     ci.read_end = contig_first[c] == ~0ull ? 0 : contig_last[c];
     ci.length = (int32_t)len;
@@ -777,9 +781,10 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     // canonical order on the device: every tile sorts its own few records, the egress kernels lay the tiles out in order
     const bool device_sort = !counts_mode && ctx->sort_records && !dense && streams;
     const uint64_t nt_all = ctx->n_tiles;
+    const uint64_t nt_pad = (nt_all + 11) & ~3ull;  // (tile_n is read 16 bytes at a time; the segments start at multiples of 4)
     if (device_sort) {
-      const uint64_t nt_pad = (nt_all + 11) & ~3ull;  // (tile_n is read 16 bytes at a time; the segments start at multiples of 4)
-      ctx->sort_bins.ensure(2 * nt_pad);  // tile_base | tile_n
+      ctx->sort_bins.ensure(3 * nt_pad);  // tile_base | tile_n | prefix (calls over more than 64 K tiles)
+      ctx->scan_totals.ensure((size_t)n_seg * ((nt_all + kScanChunk - 1) / kScanChunk + 2));
       CUDA_OK(cudaMemsetAsync(ctx->sort_bins.p + nt_pad, 0, nt_pad * sizeof(uint32_t), st));  // tile_n
       out.tile_base = ctx->sort_bins.p;
       out.tile_n = ctx->sort_bins.p + nt_pad;
@@ -816,8 +821,19 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       if (!counts_mode) {
         CUDA_OK(cudaStreamWaitEvent(st3, done, 0));
         if (device_sort && nt > 0) {
-          k_rec_gather<<<(unsigned)(((uint64_t)nt + 255) / 256), 256, 0, st3>>>(so.compact, out.tile_base + t0, out.tile_n + t0, (uint32_t)nt, ctx->d_counters,
-                                                                               (uint32_t)seg, so.cap_compact, d_contig, cap_compact);
+          const uint32_t* block_before = nullptr;
+          if ((uint64_t)nt > 65536) {  // (the in-kernel sums are quadratic in the number of tiles)
+            const uint64_t n_chunks = ((uint64_t)nt + kScanChunk - 1) / kScanChunk;
+            uint64_t* totals = ctx->scan_totals.p + (size_t)seg * ((nt_all + kScanChunk - 1) / kScanChunk + 2);
+            uint32_t* prefix = ctx->sort_bins.p + 2 * nt_pad + t0;
+            k_scan_totals<<<(unsigned)n_chunks, 256, 0, st3>>>(out.tile_n + t0, (uint64_t)nt, totals);
+            k_scan_chunks<<<1, 1024, 0, st3>>>(totals, n_chunks);
+            k_scan_final<uint32_t><<<(unsigned)n_chunks, 256, 0, st3>>>(out.tile_n + t0, (uint64_t)nt, totals, prefix);
+            block_before = prefix;
+            launches += 3;
+          }
+          k_rec_gather<<<(unsigned)(((uint64_t)nt + 255) / 256), 256, 0, st3>>>(so.compact, out.tile_base + t0, out.tile_n + t0, block_before, (uint32_t)nt,
+                                                                               ctx->d_counters, (uint32_t)seg, so.cap_compact, d_contig, cap_compact);
           k_rec_to_host<<<ctx->sm_count, 256, 0, st3>>>(d_contig, ctx->d_counters, (uint32_t)seg, so.cap_compact, h_compact, cap_compact);
           launches += 2;
         } else {
@@ -1086,6 +1102,11 @@ guac_status guac_ctx_set_option(guac_ctx* ctx, int option, int64_t value) {
     case GUAC_OPT_HOST_THREADS: ctx->host_threads = value > 0 ? (int)value : 0; return GUAC_OK;
     case GUAC_OPT_DIFFERENCE_LISTS: ctx->difference_lists = value != 0; return GUAC_OK;
     case GUAC_OPT_SEGMENTS: ctx->segments = value < 1 ? 1 : value > 4 ? 4 : (int)value; return GUAC_OK;
+    case GUAC_OPT_TRIM_CACHE:
+      cudaSetDevice(ctx->device);
+      cudaStreamSynchronize(ctx->stream);
+      tl_dev_cache.trim();
+      return GUAC_OK;
   }
   ctx->last_error = "unknown option";
   return GUAC_ERR_INVALID_ARGUMENT;

@@ -1106,11 +1106,11 @@ __global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, con
 
 // ---- record egress: the tiles' sorted slices laid out in tile order (compact germline records) ------------------------------
 // One block per 256 tiles of a segment: the block sums tile_n[] of every earlier tile itself (a few hundred kilobytes from L2;
-// no scan kernels in front of it: the whole egress is two small launches that fit next to the exact kernel) and scans its
-// own 256 counts; thread per tile: its records go behind those of the earlier tiles and segments (whose counts are final: the
+// no scan kernels in front of it: the whole egress is two small launches that fit next to the exact kernel; beyond 64 K
+// tiles the host runs the three scan kernels first and passes the prefix) and scans its own 256 counts; thread per tile: its records go behind those of the earlier tiles and segments (whose counts are final: the
 // tile kernels of a call run in order), to the contiguous device copy that k_rec_to_host and the NCCL gather send from.
 __global__ void __launch_bounds__(256) k_rec_gather(const unsigned long long* __restrict__ rec, const uint32_t* __restrict__ tile_base,
-                                                    const uint32_t* __restrict__ tile_n, uint32_t n_tiles,
+                                                    const uint32_t* __restrict__ tile_n, const uint32_t* __restrict__ block_before, uint32_t n_tiles,
                                                     const unsigned long long* counters, uint32_t seg, uint32_t cap_seg,
                                                     unsigned long long* __restrict__ dev_rec, unsigned long long cap_total) {
   __shared__ unsigned long long warp_sum[8];
@@ -1120,7 +1120,9 @@ __global__ void __launch_bounds__(256) k_rec_gather(const unsigned long long* __
   for (uint32_t j = 0; j < seg; ++j) seg_base += min(counters[12 + j], (unsigned long long)cap_seg);
   const uint32_t t0 = blockIdx.x * 256u;  // (a multiple of 4: tile_n is read 16 bytes at a time; the host aligns it)
   unsigned long long before = 0;
-  {
+  if (block_before) {  // calls over very many tiles (a whole-genome shard): the per-block sums were scanned beforehand
+    before = block_before[t0];
+  } else {
     const uint4* n4 = reinterpret_cast<const uint4*>(tile_n);
     for (uint32_t i = threadIdx.x; i < t0 / 4u; i += 256u) {
       const uint4 v = __ldg(n4 + i);
@@ -1136,7 +1138,7 @@ __global__ void __launch_bounds__(256) k_rec_gather(const unsigned long long* __
     if (lane >= (uint32_t)o) incl += u;
   }
   if (lane == 31u) warp_n[warp] = incl;
-  if (lane == 0u) warp_sum[warp] = before;
+  if (lane == 0u) warp_sum[warp] = block_before ? (warp == 0u ? before : 0ull) : before;
   __syncthreads();
   unsigned long long dst = seg_base + (incl - n);
 #pragma unroll

@@ -293,6 +293,8 @@ const char* guac_status_string(guac_status s);
                                       and CIGARs itself (same results; the cross-check the parity tests run) */
 #define GUAC_OPT_SEGMENTS 5          /* [1] 1..4: a germline call runs in this many segments of tiles, the exact kernel and the
                                       record egress of one overlapping the tile kernel of the next (same results) */
+#define GUAC_OPT_TRIM_CACHE 6        /* (an action, any value) hand the device buffers cached from freed read sets / results back
+                                      * to the driver now: between workloads of very different shapes on one context */
 guac_status guac_ctx_set_option(guac_ctx* ctx, int option, int64_t value);
 
 /* Device-side stopwatch on the context's stream (CUDA events): start, run any number of calls, stop -> elapsed ms. */
