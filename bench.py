@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--e2e-wide", dest="e2e_compact", action="store_false",
                     help="end-to-end leg from the wide guac_read_batch (ASCII bases, 64-bit columns) instead of guac_read_batch_v2")
+    ap.add_argument("--no-pack-overlap", action="store_true", help="GUAC_OPT_PACK_OVERLAP = 0 (A/B of the chunk-wise pack finish)")
     ap.add_argument("--no-somatic", action="store_true", help="N = 1: leave the configs[2] block out")
     ap.add_argument("--seed", type=int, default=20261020)
     return ap.parse_args()
@@ -177,6 +178,29 @@ def germline_keys(res, contig=None, lo=None, hi=None):
         recs = recs[(recs["contig"] == contig) & (recs["start"] >= lo) & (recs["start"] < hi)]
     return sorted((int(r["contig"]), int(r["start"]), pool[int(r["ref_off"]):int(r["ref_off"]) + int(r["ref_len"])],
                    pool[int(r["alt_off"]):int(r["alt_off"]) + int(r["alt_len"])], int(r["gt"][0]), int(r["gt"][1])) for r in recs)
+
+
+def record_digest(res, somatic):
+    """Order-independent fingerprint of a whole result (every record's locus, alleles and genotype / depths): the end-to-end leg
+    must hand back exactly what the device-resident leg did."""
+    import hashlib
+    recs, pool = res.records, np.frombuffer(res.bytes, dtype=np.uint8) if not isinstance(res.bytes, np.ndarray) else res.bytes
+    if len(recs) == 0:
+        return "empty"
+    cols = [recs["contig"].astype(np.int64), recs["start"].astype(np.int64), recs["ref_len"].astype(np.int64), recs["alt_len"].astype(np.int64)]
+    # first and last allele bytes stand in for the strings (the lengths are in the key as well)
+    for off, ln in (("ref_off", "ref_len"), ("alt_off", "alt_len")):
+        o, l = recs[off].astype(np.int64), recs[ln].astype(np.int64)
+        cols.append(np.where(l > 0, pool[np.minimum(o, len(pool) - 1)], 0).astype(np.int64))
+        cols.append(np.where(l > 0, pool[np.minimum(o + np.maximum(l, 1) - 1, len(pool) - 1)], 0).astype(np.int64))
+    if somatic:
+        cols += [recs["tumor"]["allele_read_depth"].astype(np.int64), recs["tumor"]["read_depth"].astype(np.int64),
+                 recs["normal"]["read_depth"].astype(np.int64)]
+    else:
+        cols += [recs["gt"][:, 0].astype(np.int64), recs["gt"][:, 1].astype(np.int64)]
+    m = np.stack(cols, axis=1)
+    m = m[np.lexsort(m.T[::-1])]
+    return f"{len(recs)}:" + hashlib.sha256(np.ascontiguousarray(m).tobytes()).hexdigest()[:16]
 
 
 def somatic_keys(res, contig, lo, hi):
@@ -312,6 +336,8 @@ def main():
     torch.cuda.set_device(local_rank)
     ctx = callers.Context(local_rank)
     ctx.set_option(abi.OPT_HOST_THREADS, max(1, n_threads // world))
+    if args.no_pack_overlap:
+        ctx.set_option(abi.OPT_PACK_OVERLAP, 0)
     comm = None
     if world > 1:  # the library's own NCCL communicator: the id travels by the host side's broadcast
         ids = [callers.Comm.unique_id() if rank == 0 else None]
@@ -382,6 +408,7 @@ def main():
                "pack_ms": pack_ms, "expand_ms": expand_ms, "setup_s": setup_s, "records": len(res)}
         # every kernel from the raw columns resident in HBM to the records
         out["pack_plus_call_ms"] = pack_ms + out["tile_ms"] + out["exact_ms"]
+        resident_digest = record_digest(res, is_somatic) if e2e_ranges == ranges else None
 
         # ---- parity: the engine's records inside the CPU window against the oracle's (the oracle's own run of the generator)
         cpu = None
@@ -429,6 +456,7 @@ def main():
             else:
                 hosts.append(wide)
         h2d = d2h = n_touch = 0
+        e2e_digest = None
         t1 = time.perf_counter()
         e2e_warm = max(3, args.warmup)  # (untimed: the pinned-block and device-buffer caches settle over the first few packs)
         for i in range(e2e_warm + e2e_steps):
@@ -460,7 +488,16 @@ def main():
         barrier()
         out["e2e_ms"] = (time.perf_counter() - t1) * 1e3 / e2e_steps
         out["e2e_loci"] = e2e_loci
+        if resident_digest is not None and comm is None:  # one more step, untimed, whose records are fingerprinted
+            fresh = [ctx.pack_v2(h, names) if args.e2e_compact else ctx.pack_c(h.c, names) for h in hosts]
+            r = call(fresh, e2e_ranges)
+            e2e_digest = record_digest(r, is_somatic)
+            del r
+            for f in fresh:
+                f.free()
         out["h2d"], out["d2h"], out["e2e_records"] = h2d, d2h, n_touch
+        if resident_digest is not None and e2e_digest is not None:  # the end-to-end leg returns the resident leg's records, all of them
+            out["e2e_check"] = "ok" if e2e_digest == resident_digest else f"MISMATCH ({e2e_digest} vs {resident_digest})"
         for h in hosts:
             h.free()
         return out
@@ -488,6 +525,8 @@ def main():
         if "parity_window" in o:
             blk["parity_window"] = o["parity_window"]
             blk["parity_window_records"] = o["parity_records"]
+        if "e2e_check" in o:
+            blk["e2e_check"] = o["e2e_check"]
         if "gather_check" in o:
             blk["gather_check"] = o["gather_check"]
             blk["mean_depth"] = o["mean_depth"]
@@ -532,13 +571,13 @@ def main():
                 "dtype": "f64" if somatic else "u8", "data": "synthetic (generated on the device from the seed)", "config": config}
         for k in ("records_per_step", "gpu_launches", "e2e", "roofline", "clocks", "pack_plus_call_ms", "pack_kernel_ms", "expand_kernel_ms",
                   "generate_kernel_ms", "pack_plus_call_loci_per_s", "wall_ms_per_step", "parity_window", "parity_window_records",
-                  "gather_check", "mean_depth", "cpu_baseline", "setup_s"):
+                  "e2e_check", "gather_check", "mean_depth", "cpu_baseline", "setup_s"):
             if k in main_blk:
                 line[k] = main_blk[k]
         line["e2e"]["steps"] = e2e_steps
         if som_blk:
             line["somatic"] = som_blk
-        bad = [b[k] for b in (main_blk, som_blk or {}) for k in ("parity_window", "gather_check") if b.get(k, "ok") != "ok"]
+        bad = [b[k] for b in (main_blk, som_blk or {}) for k in ("parity_window", "e2e_check", "gather_check") if b.get(k, "ok") != "ok"]
         print(json.dumps(line), flush=True)
         if bad:
             print("PARITY FAILURE: " + "; ".join(bad), file=sys.stderr, flush=True)

@@ -174,6 +174,7 @@ OPT_HOST_THREADS = 3
 OPT_DIFFERENCE_LISTS = 4
 OPT_SEGMENTS = 5
 OPT_TRIM_CACHE = 6
+OPT_PACK_OVERLAP = 7
 
 
 def struct_to_dict(s):

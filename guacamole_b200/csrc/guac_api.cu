@@ -44,13 +44,17 @@ void alloc_streams(guac_reads& rd, uint64_t cap_entries) {
   rd.gs_entries = cap_entries;
 }
 
-void launch_expand(guac_ctx* ctx, guac_reads& rd, bool huge, uint64_t cap_entries, bool allocated = false) {
+// [g_begin, g_end): the granules of this launch (guac_reads_pack expands the granules behind a copy chunk's last read while
+// the next chunk is still on the bus); `first` / `last`: clears the counters / closes the timing of a series of launches
+void launch_expand(guac_ctx* ctx, guac_reads& rd, bool huge, uint64_t cap_entries, bool allocated = false, uint64_t g_begin = 0,
+                   uint64_t g_end = ~0ull, bool first = true, bool last = true) {
   cudaStream_t st = ctx->stream;
   const uint64_t grans = rd.total_grans;
   if (!allocated) alloc_streams(rd, cap_entries);
   cap_entries = rd.gs_entries;
-  CUDA_OK(cudaMemsetAsync(ctx->d_counters + 2, 0, 2 * sizeof(unsigned long long), st));
+  if (first) CUDA_OK(cudaMemsetAsync(ctx->d_counters + 2, 0, 2 * sizeof(unsigned long long), st));
   if (!grans) return;
+  g_end = std::min<uint64_t>(g_end, grans);
   ExpandArgs E;
   E.R = rd.view();
   E.hdr_w = rd.gs_hdr.p;
@@ -59,22 +63,24 @@ void launch_expand(guac_ctx* ctx, guac_reads& rd, bool huge, uint64_t cap_entrie
   E.dp_w = rd.gs_dp.p;
   E.imp_w = rd.gs_imp.p;
   E.cap_diffs = cap_entries;
-  E.g_begin = 0;
-  E.g_end = (uint32_t)grans;
+  E.g_begin = (uint32_t)g_begin;
+  E.g_end = (uint32_t)g_end;
   E.n_contigs = rd.n_contigs;
   E.wide = rd.gs_wide ? 1 : 0;
   E.counters = ctx->d_counters;
   E.err = ctx->d_err;
-  const int ctas = (int)((grans + kExpandWarps - 1) / kExpandWarps);
+  const int ctas = (int)((g_end - std::min(g_begin, g_end) + kExpandWarps - 1) / kExpandWarps);
   if (!ctx->expand_attrs_done) {
     CUDA_OK(cudaFuncSetAttribute(k_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kExpandWarps * sizeof(ExpandSmem<false>))));
     CUDA_OK(cudaFuncSetAttribute(k_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kExpandWarps * sizeof(ExpandSmem<true>))));
     ctx->expand_attrs_done = true;
   }
-  CUDA_OK(cudaEventRecord(ctx->ev[2], st));
-  if (huge) k_expand<true><<<ctas, kExpandWarps * 32, kExpandWarps * sizeof(ExpandSmem<true>), st>>>(E);
-  else k_expand<false><<<ctas, kExpandWarps * 32, kExpandWarps * sizeof(ExpandSmem<false>), st>>>(E);
-  CUDA_OK(cudaEventRecord(ctx->ev[3], st));
+  if (first) CUDA_OK(cudaEventRecord(ctx->ev[2], st));
+  if (ctas > 0) {
+    if (huge) k_expand<true><<<ctas, kExpandWarps * 32, kExpandWarps * sizeof(ExpandSmem<true>), st>>>(E);
+    else k_expand<false><<<ctas, kExpandWarps * 32, kExpandWarps * sizeof(ExpandSmem<false>), st>>>(E);
+  }
+  if (last) CUDA_OK(cudaEventRecord(ctx->ev[3], st));
   CUDA_OK(cudaGetLastError());
 }
 
@@ -116,10 +122,12 @@ void alloc_rows(guac_reads& rd, uint64_t cap_pairs, uint64_t cap_groups) {
   rd.q_cap_groups = cap_groups;
 }
 
-void launch_rows(guac_ctx* ctx, guac_reads& rd) {
+void launch_rows(guac_ctx* ctx, guac_reads& rd, uint64_t w_begin = 0, uint64_t w_end = ~0ull, bool first = true, bool last = true) {
   cudaStream_t st = ctx->stream;
-  CUDA_OK(cudaMemsetAsync(ctx->d_counters + 4, 0, 2 * sizeof(unsigned long long), st));
+  if (first) CUDA_OK(cudaMemsetAsync(ctx->d_counters + 4, 0, 2 * sizeof(unsigned long long), st));
   if (!rd.total_words) return;
+  w_end = std::min<uint64_t>(w_end, rd.total_words);
+  w_begin = std::min(w_begin, w_end);
   RowsArgs A;
   A.R = rd.view();
   A.hdr_w = rd.q_hdr.p;
@@ -129,16 +137,16 @@ void launch_rows(guac_ctx* ctx, guac_reads& rd) {
   A.rows_w = rd.q_rows.p;
   A.cap_pairs = rd.q_cap_pairs;
   A.cap_groups = rd.q_cap_groups;
-  A.w_begin = 0;
-  A.w_end = (uint32_t)rd.total_words;
+  A.w_begin = (uint32_t)w_begin;
+  A.w_end = (uint32_t)w_end;
   A.n_contigs = rd.n_contigs;
   A.pad_ = 0;
   A.counters = ctx->d_counters;
   A.err = ctx->d_err;
   memcpy(A.mapq_mask, rd.mapq_mask, sizeof A.mapq_mask);
-  CUDA_OK(cudaEventRecord(ctx->ev_rows[0], st));
-  k_expand_rows<<<(unsigned)((rd.total_words + kRowsWarps - 1) / kRowsWarps), kRowsWarps * 32, 0, st>>>(A);
-  CUDA_OK(cudaEventRecord(ctx->ev_rows[1], st));
+  if (first) CUDA_OK(cudaEventRecord(ctx->ev_rows[0], st));
+  if (w_end > w_begin) k_expand_rows<<<(unsigned)((w_end - w_begin + kRowsWarps - 1) / kRowsWarps), kRowsWarps * 32, 0, st>>>(A);
+  if (last) CUDA_OK(cudaEventRecord(ctx->ev_rows[1], st));
   CUDA_OK(cudaGetLastError());
 }
 
@@ -534,12 +542,19 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
   A.counters = ctx->d_counters;
 
   out.pack_launches = n ? 5 : 0;  // header kernel + scan
+  bool finished = false;  // the by-locus stores were built chunk by chunk
   if (n) {
     A.r_begin = 0;
     A.r_end = n;
     k_granule_index<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(A);
     k_granule_max<<<grid_for(gran_off, 256, ctx->sm_count), 256, 0, st>>>(A, (uint32_t)gran_off);
     out.pack_launches += 2;
+    // Reads are sorted by start: once a copy chunk's reads went through the MD walk, the track in front of the next chunk's
+    // first read is final, and so are its granules' streams and its words' rows.  They are built right away, underneath the
+    // copy of the following chunks; what remains after the last chunk has landed is an eighth of the work.
+    const bool finish_by_chunk = !ref && !on_device && n_copy_chunks > 1 && ctx->pack_overlap;
+    uint64_t g_done = 0, w_done = 0;
+    bool first_finish = true;
     for (int k = 0; k < n_copy_chunks; ++k) {  // bases -> planes and the MD walk, chunk by chunk as the copies land
       A.r_begin = chunk_read[k];
       A.r_end = chunk_read[k + 1];
@@ -549,24 +564,59 @@ void pack_reads(guac_ctx* ctx, const guac_read_batch* b, const guac_reference* r
       k_pack_bases<<<(int)std::min<uint64_t>((nr + kPackReads - 1) / kPackReads, (uint64_t)ctx->sm_count * 8), 256, 0, st>>>(A);
       k_md_track<<<grid_for(nr, 128, ctx->sm_count), 128, 0, st>>>(A);
       out.pack_launches += 2;
+      if (!finish_by_chunk) continue;
+      const bool last_chunk = chunk_read[k + 1] >= n;
+      uint64_t g_end = gran_off, w_end = word_off;
+      if (!last_chunk) {  // the granule of the next chunk's first read
+        const uint64_t r = chunk_read[k + 1];
+        uint32_t c = 0;
+        int64_t s0 = 0;
+        if (b2) {
+          c = (uint32_t)(std::upper_bound(b2->contig_read_off, b2->contig_read_off + b2->n_contigs + 1, r) - b2->contig_read_off - 1);
+          s0 = b2->start[r];
+        } else {
+          c = (uint32_t)b->contig[r];
+          s0 = b->start[r];
+        }
+        const ContigInfo& ci = out.contigs[std::min<uint32_t>(c, b->n_contigs - 1)];
+        const uint64_t lg = std::min<uint64_t>((uint64_t)std::max<int64_t>(s0, 0) >> kGranuleShift, (uint64_t)ci.n_grans);
+        g_end = (uint64_t)ci.gran_off + lg;
+        w_end = (uint64_t)ci.word_off + std::min<uint64_t>(lg * (kGranuleLoci / 32), (uint64_t)ci.n_words);
+      }
+      if (g_end <= g_done && !last_chunk) continue;
+      k_track_finish<<<grid_for(w_end - w_done + 1, 256, ctx->sm_count), 256, 0, st>>>(A, (uint32_t)w_done, (uint32_t)w_end);
+      k_resolve_conflicts<<<grid_for(w_end - w_done + 1, 128, ctx->sm_count), 128, 0, st>>>(A, b->n_contigs, (uint32_t)w_done, (uint32_t)w_end);
+      out.pack_launches += 2;
+      if (ctx->difference_lists) {
+        launch_expand(ctx, out, /*huge=*/false, out.gs_entries, /*allocated=*/true, g_done, g_end, first_finish, last_chunk);
+        out.pack_launches += 1;
+      }
+      if (want_rows) {
+        launch_rows(ctx, out, w_done, w_end, first_finish, last_chunk);
+        out.pack_launches += 1;
+      }
+      first_finish = false;
+      g_done = g_end;
+      w_done = w_end;
     }
     A.r_begin = 0;
     A.r_end = n;
-    if (!ref) {
-      k_track_finish<<<grid_for(word_off, 256, ctx->sm_count), 256, 0, st>>>(A, (uint32_t)word_off);
-      k_resolve_conflicts<<<grid_for(word_off, 128, ctx->sm_count), 128, 0, st>>>(A, b->n_contigs);
+    if (!ref && !finish_by_chunk) {
+      k_track_finish<<<grid_for(word_off, 256, ctx->sm_count), 256, 0, st>>>(A, 0u, (uint32_t)word_off);
+      k_resolve_conflicts<<<grid_for(word_off, 128, ctx->sm_count), 128, 0, st>>>(A, b->n_contigs, 0u, (uint32_t)word_off);
       out.pack_launches += 2;
     }
+    finished = finish_by_chunk;
   }
   if (ref) {
     k_fasta_track<<<grid_for(word_off, 256, ctx->sm_count), 256, 0, st>>>(A, b->n_contigs);
     out.pack_launches += 1;
   }
-  if (n && ctx->difference_lists) {  // the track is final: every granule's reads as their differences against it
+  if (n && ctx->difference_lists && !finished) {  // the track is final: every granule's reads as their differences against it
     launch_expand(ctx, out, /*huge=*/false, out.gs_entries, /*allocated=*/true);
     out.pack_launches += 1;
   }
-  if (want_rows) {  // the likelihood callers' rows (the MD walk has located every read's first deletion: classify() uses it)
+  if (want_rows && !finished) {  // the likelihood callers' rows (the MD walk has located every read's first deletion: classify() uses it)
     launch_rows(ctx, out);
     out.pack_launches += 1;
   }
@@ -1102,6 +1152,7 @@ guac_status guac_ctx_set_option(guac_ctx* ctx, int option, int64_t value) {
     case GUAC_OPT_HOST_THREADS: ctx->host_threads = value > 0 ? (int)value : 0; return GUAC_OK;
     case GUAC_OPT_DIFFERENCE_LISTS: ctx->difference_lists = value != 0; return GUAC_OK;
     case GUAC_OPT_SEGMENTS: ctx->segments = value < 1 ? 1 : value > 4 ? 4 : (int)value; return GUAC_OK;
+    case GUAC_OPT_PACK_OVERLAP: ctx->pack_overlap = value != 0; return GUAC_OK;
     case GUAC_OPT_TRIM_CACHE:
       cudaSetDevice(ctx->device);
       cudaStreamSynchronize(ctx->stream);

@@ -204,6 +204,7 @@ struct guac_ctx {
   int host_threads = 0;
   int difference_lists = 1;
   int segments = 1;
+  bool pack_overlap = true;
   bool smem_attrs_done = false, expand_attrs_done = false;
   // scratch kept across calls so that a repeated call neither allocates nor rebuilds its tile list
   DevBuf<unsigned char> out_rec, out_pool, out_slow, out_compact, tiles, sort_rec;

@@ -473,8 +473,8 @@ __global__ void __launch_bounds__(128) k_md_track(PackArgs A) {
 }
 
 // thread per track word: the "says 0" planes become the standard-base plane and the plane of disagreeing loci
-__global__ void __launch_bounds__(256) k_track_finish(PackArgs A, uint32_t n_words) {
-  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) k_track_finish(PackArgs A, uint32_t w_begin, uint32_t w_end) {
+  for (uint32_t w = w_begin + blockIdx.x * blockDim.x + threadIdx.x; w < w_end; w += gridDim.x * blockDim.x) {
     const uint32_t lo1 = A.trk_lo_w[w], hi1 = A.trk_hi_w[w], lo0 = A.trk_std_w[w], hi0 = A.conflict_w[w];
     A.trk_std_w[w] = lo1 | lo0;
     A.conflict_w[w] = (lo1 & lo0) | (hi1 & hi0);
@@ -521,10 +521,12 @@ struct BaseAtVisitor {
 // ---- K_resolve_conflicts: thread per track word.  Canonical rule for loci where the reads' MD tags disagree (SURVEY
 // H1a): the standard base given by the overlapping read with the smallest end, earliest read on ties — what
 // Pileup.referenceBaseAtLocus sees first in the sliding window's heap order on a single-task run. ---------------------
-__global__ void __launch_bounds__(128) k_resolve_conflicts(PackArgs A, uint32_t n_contigs) {
+__global__ void __launch_bounds__(128) k_resolve_conflicts(PackArgs A, uint32_t n_contigs, uint32_t w_begin, uint32_t w_end) {  // global words [w_begin, w_end)
   for (uint32_t c = 0; c < n_contigs; ++c) {
     const ContigInfo ci = A.R.contigs[c];
-    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < ci.n_words; w += gridDim.x * blockDim.x) {
+    if (ci.word_off >= w_end || ci.word_off + (uint32_t)ci.n_words <= w_begin) continue;
+    const int w_first = (int)(max(ci.word_off, w_begin) - ci.word_off), w_last = (int)(min(ci.word_off + (uint32_t)ci.n_words, w_end) - ci.word_off);
+    for (int w = w_first + blockIdx.x * blockDim.x + threadIdx.x; w < w_last; w += gridDim.x * blockDim.x) {
       uint32_t conf = A.conflict_w[ci.word_off + w];
       if (!conf) continue;
       uint32_t lo = A.trk_lo_w[ci.word_off + w], hi = A.trk_hi_w[ci.word_off + w];

@@ -295,6 +295,10 @@ const char* guac_status_string(guac_status s);
                                       record egress of one overlapping the tile kernel of the next (same results) */
 #define GUAC_OPT_TRIM_CACHE 6        /* (an action, any value) hand the device buffers cached from freed read sets / results back
                                       * to the driver now: between workloads of very different shapes on one context */
+#define GUAC_OPT_PACK_OVERLAP 7      /* [1] guac_reads_pack of a large host batch finishes the reference track and the by-locus
+                                      stores copy chunk by copy chunk (reads are start-sorted: everything in front of the next
+                                      chunk's first read is final), underneath the copies still on the bus.  0 = after the last
+                                      chunk, in one launch each (same store) */
 guac_status guac_ctx_set_option(guac_ctx* ctx, int option, int64_t value);
 
 /* Device-side stopwatch on the context's stream (CUDA events): start, run any number of calls, stop -> elapsed ms. */

@@ -320,6 +320,28 @@ def test_chunked_pack_above_a_million_reads(ctx):
     ranges.append((0, L - 30_000, L - 1))
     assert_threshold_equal(ctx, b, ranges)
     assert_counts_equal(ctx, b, ranges)
+    # the by-locus stores finished chunk by chunk underneath the copies (GUAC_OPT_PACK_OVERLAP, the default) and in one launch
+    # after the last chunk: the same records over every locus, from the wide and from the compact batch
+    from guacamole_b200 import abi, callers
+    whole = [(0, 0, L - 1)]
+    got = {}
+    for overlap in (1, 0):
+        ctx.set_option(abi.OPT_PACK_OVERLAP, overlap)
+        try:
+            for compact in (False, True):
+                host = callers.CompactBatch(b, pinned=False, fixed_length=False) if compact else None
+                reads = ctx.pack_v2(host, b.contig_names) if compact else ctx.pack(b)
+                res = callers.germline_threshold(ctx, reads, whole, threshold=8)
+                got[(overlap, compact)] = res.genotypes()
+                del res
+                reads.free()
+                if host is not None:
+                    host.free()
+        finally:
+            ctx.set_option(abi.OPT_PACK_OVERLAP, 1)
+    assert len(got[(1, False)]) > 1000
+    for k, v in got.items():
+        assert v == got[(1, False)], k
 
 
 def test_by_sample_split(ctx):
