@@ -774,6 +774,10 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
   bool wide = streams ? reads.gs_wide : reads.max_reads_per_granule >= 2048;
   double tile_ms = 0, exact_ms = 0;
   int launches = 0;
+  static const bool x_tl = getenv("GUAC_TRACE") != nullptr;
+  cudaEvent_t* xe = ctx->trace_ev;
+  if (x_tl && !xe[0])
+    for (int i = 0; i < 5; ++i) CUDA_OK(cudaEventCreate(&xe[i]));
   for (int attempt = 0; attempt < 8; ++attempt) {
     if (cap_rec >= 0xFFFFFFF0ull || cap_compact >= 0xFFFFFFF0ull || cap_slow >= 0xFFFFFFF0ull || cap_pool >= 0xFFFFFFF0ull)
       fail(GUAC_ERR_UNSUPPORTED, "too many output records for one call: split the loci ranges");
@@ -795,6 +799,8 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       memcpy(hs, "<ALT>", 5);
       for (int v = 0; v < 256; ++v) hs[kPoolByteOff + v] = (uint8_t)v;
       ctx->out_compact.ensure(cap_compact * 8 + 16);
+      ctx->out_rec.ensure(cap_rec * sizeof(guac_threshold_record) + 16);  // the exact kernel's general records and allele bytes:
+      if (ctx->out_pool.ensure(cap_pool + 16)) ctx->pool_head_ready = false;  // HBM first, one coalesced copy to the block
     } else {
       ctx->out_rec.ensure(cap_rec * sizeof(guac_locus_counts));
       if (ctx->out_pool.ensure(cap_pool)) ctx->pool_head_ready = false;
@@ -811,12 +817,12 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     }
     CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
     DevOut out;
-    out.trec = counts_mode ? (guac_threshold_record*)ctx->out_rec.p : (guac_threshold_record*)((unsigned char*)res.block + full_at);
+    out.trec = (guac_threshold_record*)ctx->out_rec.p;
     out.crec = (guac_locus_counts*)ctx->out_rec.p;
     out.cap_rec = (uint32_t)cap_rec;
     out.compact = (unsigned long long*)ctx->out_compact.p;
     out.cap_compact = counts_mode ? 0u : (uint32_t)cap_seg;
-    out.pool = counts_mode ? ctx->out_pool.p : (uint8_t*)res.block;
+    out.pool = ctx->out_pool.p;
     out.cap_pool = (uint32_t)cap_pool;
     out.slow = (SlowLocus*)ctx->out_slow.p;
     out.cap_slow = (uint32_t)cap_slow;
@@ -824,6 +830,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     out.compact_ctr = 12;
     out.counters = ctx->d_counters;
     out.err = ctx->d_err;
+    out.work = ctx->d_counters + kStatusBytes / sizeof(unsigned long long);  // (zero at rest: the exact kernel resets its tickets itself)
     const DevReads R = reads.view();
     const TileDesc* d_tiles = (const TileDesc*)ctx->tiles.p;
     unsigned long long* h_compact = counts_mode ? nullptr : (unsigned long long*)((unsigned char*)res.block + compact_at);
@@ -866,7 +873,6 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       CUDA_OK(cudaStreamWaitEvent(st2, done, 0));
       // (8 CTAs per SM: all of them resident at once with room left for the egress kernels' 256-thread blocks next to them —
       // a grid that is not resident in full keeps every later launch waiting, whatever its stream)
-      k_exact_loci<<<ctx->sm_count * 8, kExactWarps * 32, 0, st2>>>(R, so.slow, prm, so);
       launches += 1;
       if (!counts_mode) {
         CUDA_OK(cudaStreamWaitEvent(st3, done, 0));
@@ -882,14 +888,28 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
             block_before = prefix;
             launches += 3;
           }
+          if (x_tl) cudaEventRecord(xe[2], st3);
           k_rec_gather<<<(unsigned)(((uint64_t)nt + 255) / 256), 256, 0, st3>>>(so.compact, out.tile_base + t0, out.tile_n + t0, block_before, (uint32_t)nt,
                                                                                ctx->d_counters, (uint32_t)seg, so.cap_compact, d_contig, cap_compact);
+          if (x_tl) cudaEventRecord(xe[3], st3);
           k_rec_to_host<<<ctx->sm_count, 256, 0, st3>>>(d_contig, ctx->d_counters, (uint32_t)seg, so.cap_compact, h_compact, cap_compact);
+          if (x_tl) cudaEventRecord(xe[4], st3);
           launches += 2;
         } else {
           k_rec_flush<<<ctx->sm_count, 256, 0, st3>>>(so.compact, ctx->d_counters, (uint32_t)seg, so.cap_compact, h_compact, d_contig, cap_compact);
           launches += 1;
         }
+      }
+      // (after the egress kernels in launch order, and 7 CTAs of 56 registers per SM: the egress kernels' 256-thread blocks find
+      // room next to them.  With 8 the register file was full and the record gather waited for the exact kernel to drain:
+      // 90 us instead of 15.)
+      if (x_tl) cudaEventRecord(xe[0], st2);
+      k_exact_loci<<<ctx->sm_count * 7, kExactWarps * 32, 0, st2>>>(R, so.slow, prm, so);
+      if (x_tl) cudaEventRecord(xe[1], st2);
+      if (!counts_mode && seg + 1 == n_seg) {  // (the segments' exact kernels run in order on st2 and share the buffers)
+        k_general_to_host<<<8, 256, 0, st2>>>(ctx->d_counters, (const uint4*)ctx->out_rec.p, ctx->out_pool.p, (uint4*)((unsigned char*)res.block + full_at),
+                                              (uint8_t*)res.block, (uint32_t)cap_rec, (uint32_t)cap_pool);
+        launches += 1;
       }
     }
     CUDA_OK(cudaEventRecord(ctx->join_ev, st2));
@@ -909,6 +929,14 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     CUDA_OK(cudaStreamSynchronize(st));
     nvtx_pop();
     raise_device_error(ctx, "pileup");
+    if (x_tl && !counts_mode && device_sort) {  // (GUAC_TRACE) the side streams' kernels relative to the start of the call
+      float t[8] = {0};
+      cudaEventElapsedTime(&t[0], ctx->ev[0], ctx->ev[1]);
+      for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[1 + i], ctx->ev[0], xe[i]);
+      cudaEventElapsedTime(&t[6], ctx->ev[0], ctx->ev[2]);
+      fprintf(stderr, "[guac timeline] tile end %.1f us | exact %.1f..%.1f | gather %.1f..%.1f | to_host ..%.1f | joined %.1f\n", t[0] * 1e3, t[1] * 1e3,
+              t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3, t[6] * 1e3);
+    }
     if (device_sort && c[7]) {
       // a tile held more records than it orders in shared memory: its surplus is not part of any tile's slice.  Copy every
       // segment's records as they are instead (still on the device); the host orders them when the view is built.
@@ -1094,7 +1122,8 @@ guac_status guac_ctx_create(int device, guac_ctx** out) {
     CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (auto& e : ctx->copy_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
-    CUDA_OK(cudaMalloc((void**)&ctx->d_counters, kStatusBytes));
+    CUDA_OK(cudaMalloc((void**)&ctx->d_counters, kStatusBytes + 8 * sizeof(unsigned long long)));  // status block + the exact kernel's tickets
+    CUDA_OK(cudaMemset(ctx->d_counters, 0, kStatusBytes + 8 * sizeof(unsigned long long)));
     ctx->d_err = reinterpret_cast<DevError*>(ctx->d_counters + 16);
     CUDA_OK(cudaMemset(ctx->d_counters, 0, kStatusBytes));
     CUDA_OK(cudaMallocHost((void**)&ctx->h_counters, kStatusBytes));
@@ -1136,6 +1165,8 @@ void guac_ctx_destroy(guac_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
   if (ctx->join3_ev) cudaEventDestroy(ctx->join3_ev);
+  for (auto& e : ctx->trace_ev)
+    if (e) cudaEventDestroy(e);
   for (auto& e : ctx->seg_ev)
     if (e) cudaEventDestroy(e);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);

@@ -189,6 +189,7 @@ struct guac_ctx {
   cudaStream_t stream2 = nullptr;       // the exact per-locus kernel of a germline call, next to the record egress on `stream`
   cudaStream_t stream3 = nullptr;       // ... and the ordering + egress of the compact records
   cudaEvent_t join_ev = nullptr, join3_ev = nullptr, seg_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t trace_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // GUAC_TRACE: the side streams' kernels of a germline call
   cudaStream_t copy_stream = nullptr;   // guac_reads_pack: host -> device copies, overlapped with the pack kernels
   cudaEvent_t copy_ev[10] = {};  // [0..7] chunks of bases on the device, [8] small columns there, [9] compute stream caught up
   std::string last_error;

@@ -53,6 +53,7 @@ struct DevOut {
   // tiles runs in up to four segments so that the exact kernel and the record egress of one overlap the tile kernel of the
   // next): [8 + s] deferred loci, [12 + s] compact records
   unsigned long long* counters;
+  unsigned long long* work;      // k_exact_loci: per segment a ticket counter and the number of warps that are through (self-resetting)
   DevError* err;
 };
 
@@ -695,29 +696,75 @@ __device__ long md_deleted_offset(const DevReads& R, uint64_t r, int pos) {
   return -1;
 }
 
+// Everything classify() needs to know about a read before it can look at a base: one round of independent loads (the exact
+// kernels are chains of dependent DRAM round trips, ~1.5 us each; a warp decides one locus, so the length of the chain is the
+// kernel's duration).
+struct ReadMeta {
+  ReadRec rec;
+  uint64_t seq0, seq1;      // seq_off[r], seq_off[r + 1]
+  uint32_t cig0, cig1;      // cig_off[r], cig_off[r + 1]
+  uint32_t op[4];           // the first four CIGAR operators (whatever follows a short CIGAR's last one: never looked at)
+  int32_t del_start;        // the read's first deletion (k_md_track): -1 = none
+  uint32_t del_len, del_md, md0, md1;
+};
+
+__device__ __forceinline__ ReadMeta load_read_meta(const DevReads& R, const uint64_t r) {
+  ReadMeta M;
+  const uint4 rc = __ldg(reinterpret_cast<const uint4*>(R.rec + r));
+  M.seq0 = __ldg(R.seq_off + r);
+  M.seq1 = __ldg(R.seq_off + r + 1);
+  M.cig0 = __ldg(R.cig_off + r);
+  M.cig1 = __ldg(R.cig_off + r + 1);
+  M.del_start = __ldg(R.del_start + r);
+  M.del_len = __ldg(R.del_len + r);
+  M.del_md = __ldg(R.del_md + r);
+  M.md0 = __ldg(R.md_off + r);
+  M.md1 = __ldg(R.md_off + r + 1);
+  M.rec.start = (int32_t)rc.x;
+  M.rec.end = (int32_t)rc.y;
+  M.rec.pair_off = rc.z;
+  M.rec.info = rc.w;
+  const uint32_t n = M.cig1 - M.cig0;  // (second round, still before any decision)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) M.op[i] = (uint32_t)i < n ? __ldg(R.cigar + M.cig0 + i) : 0u;
+  return M;
+}
+
+// offset into R.md of the deleted base at reference position `pos`: the first deletion from the preloaded cache, any other
+// through the walk
+__device__ __forceinline__ long md_deleted_offset_meta(const DevReads& R, const uint64_t r, const ReadMeta& M, const int pos) {
+  if (M.del_start < 0) return -1;
+  if (pos >= M.del_start && pos < M.del_start + (int)M.del_len) return (long)(M.md0 + M.del_md + (uint32_t)(pos - M.del_start));
+  return md_deleted_offset(R, r, pos);
+}
+
 // PileupElement(read, locus, referenceBase) + alignment + qualityScore  (pileup/PileupElement.scala:68-171, 220-274)
-__device__ __noinline__ int classify(const DevReads& R, uint64_t r, int locus, uint8_t ref_base, Elem& e) {
-  const ReadRec rec = R.rec[r];
-  const uint8_t* seq = R.seq + R.seq_off[r];
-  const uint8_t* qual = R.qual ? R.qual + R.seq_off[r] : nullptr;  // absent when packed without qualities
+__device__ __forceinline__ int classify_meta(const DevReads& R, const uint64_t r, const ReadMeta& M, const int locus, const uint8_t ref_base, Elem& e) {
+  const ReadRec rec = M.rec;
+  const uint8_t* seq = R.seq + M.seq0;
+  const uint8_t* qual = R.qual ? R.qual + M.seq0 : nullptr;  // absent when packed without qualities
   e.kind = kNone;
   if ((rec.info & kInfoSimple) && locus >= rec.start && locus < rec.end) {
     // one M/=/X run between clips: the element is a plain base, no CIGAR walk needed
     const int rp = (int)(rec.info & kInfoLeadMask) + (locus - rec.start);
-    e.base = seq[rp];
-    e.qual = qual ? (int)(int8_t)qual[rp] : 0;
+    e.base = __ldg(seq + rp);
+    e.qual = qual ? (int)(int8_t)__ldg(qual + rp) : 0;
     e.kind = (e.base == ref_base) ? kMatch : kMismatch;
     e.len = 1;
     return 0;
   }
-  const uint32_t c0 = R.cig_off[r], c1 = R.cig_off[r + 1];
-  const int read_len = (int)(R.seq_off[r + 1] - R.seq_off[r]);
+  const uint32_t c0 = M.cig0, c1 = M.cig1;
+  const int read_len = (int)(M.seq1 - M.seq0);
   const int mapq = (int)(rec.info >> kInfoMapqShift);
   int ref_pos = rec.start, read_pos = 0;
-  e.kind = kNone;
+  auto op_at = [&](const uint32_t c) -> uint32_t {
+    const uint32_t i = c - c0;
+    return i == 0u ? M.op[0] : i == 1u ? M.op[1] : i == 2u ? M.op[2] : i == 3u ? M.op[3] : __ldg(R.cigar + c);
+  };
   for (uint32_t c = c0; c < c1; ++c) {
-    const uint32_t op = R.cigar[c] & 0xF;
-    const int len = (int)(R.cigar[c] >> 4);
+    const uint32_t word = op_at(c);
+    const uint32_t op = word & 0xF;
+    const int len = (int)(word >> 4);
     const int ref_len = op_consumes_ref(op) ? len : 0;
     const bool here = ref_pos <= locus && locus < ref_pos + ref_len;
     const bool stay_on_insertion = !here && locus == 0 && op == GUAC_CIGAR_I;  // insertion at the start of a contig
@@ -730,14 +777,15 @@ __device__ __noinline__ int classify(const DevReads& R, uint64_t r, int locus, u
     const int rp = read_pos + ((here && op_consumes_read(op)) ? idx : 0);
     const bool is_final = idx == len - 1;
     const bool has_next = c + 1 < c1;
-    const uint32_t next_op = is_final ? (has_next ? (R.cigar[c + 1] & 0xF) : 0xFFu) : op;
-    const int next_len = has_next ? (int)(R.cigar[c + 1] >> 4) : 0;
+    const uint32_t next_word = has_next ? op_at(c + 1) : 0u;
+    const uint32_t next_op = is_final ? (has_next ? (next_word & 0xF) : 0xFFu) : op;
+    const int next_len = has_next ? (int)(next_word >> 4) : 0;
     auto insertion = [&](int ins_len) {
       int from = min(max(rp, 0), read_len), until = min(rp + ins_len + 1, read_len);
       if (until <= from) return (int)GUAC_ERR_INVALID_CIGAR;
       e.kind = kInsertion;
       e.len = until - from;
-      e.ptr = R.seq_off[r] + from;
+      e.ptr = M.seq0 + from;
       int q = 255;
       for (int k = from; k < until; ++k) q = min(q, qual ? (int)(int8_t)qual[k] : 0);
       e.qual = q;
@@ -748,14 +796,19 @@ __device__ __noinline__ int classify(const DevReads& R, uint64_t r, int locus, u
     if (op == GUAC_CIGAR_I && next_op != 0xFFu && ref_pos == 0) return insertion(len);
     if (op == GUAC_CIGAR_I) return GUAC_ERR_INVALID_CIGAR;
     if (op_is_match_like(op) && next_op == GUAC_CIGAR_D) {
-      long off = md_deleted_offset(R, r, locus + 1);
+      long off = md_deleted_offset_meta(R, r, M, locus + 1);
       if (off < 0 || rp < 0 || rp >= read_len) return GUAC_ERR_MISSING_MD;
       // all next_len deleted bases must be present in the tag: they follow contiguously (the tag was upper-cased at pack
       // time; '^' or a digit in between is what a second walk to the last deleted base would also trip over)
-      if ((uint64_t)off + (uint64_t)next_len > (uint64_t)R.md_off[r + 1]) return GUAC_ERR_MISSING_MD;
-      for (int i = 1; i < next_len; ++i) {
-        const char ch = R.md[off + i];
-        if (ch < 'A' || ch > 'Z') return GUAC_ERR_MISSING_MD;
+      if ((uint64_t)off + (uint64_t)next_len > (uint64_t)M.md1) return GUAC_ERR_MISSING_MD;
+      for (int i = 1; i < next_len; i += 8) {  // (eight bytes per round trip)
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const char ch = i + j < next_len ? __ldg(R.md + off + i + j) : 'A';
+          ok = ok && ch >= 'A' && ch <= 'Z';
+        }
+        if (!ok) return GUAC_ERR_MISSING_MD;
       }
       e.kind = kDeletion;
       e.len = next_len;
@@ -765,7 +818,7 @@ __device__ __noinline__ int classify(const DevReads& R, uint64_t r, int locus, u
       return 0;
     }
     if (op == GUAC_CIGAR_D) {
-      long off = md_deleted_offset(R, r, locus);
+      long off = md_deleted_offset_meta(R, r, M, locus);
       if (off < 0) return GUAC_ERR_MISSING_MD;
       e.kind = kMidDeletion;
       e.base = (uint8_t)R.md[off];
@@ -788,6 +841,21 @@ __device__ __noinline__ int classify(const DevReads& R, uint64_t r, int locus, u
     return 0;
   }
   return 0;
+}
+
+// (one copy of the walk per kernel that calls it from several places)
+__device__ __noinline__ int classify(const DevReads& R, uint64_t r, int locus, uint8_t ref_base, Elem& e) {
+  const ReadRec rec = R.rec[r];
+  if ((rec.info & kInfoSimple) && locus >= rec.start && locus < rec.end) {  // (the likelihood kernels' common case: two loads)
+    const uint64_t at = R.seq_off[r] + (uint64_t)((int)(rec.info & kInfoLeadMask) + (locus - rec.start));
+    e.base = R.seq[at];
+    e.qual = R.qual ? (int)(int8_t)R.qual[at] : 0;
+    e.kind = (e.base == ref_base) ? kMatch : kMismatch;
+    e.len = 1;
+    return 0;
+  }
+  const ReadMeta M = load_read_meta(R, r);
+  return classify_meta(R, r, M, locus, ref_base, e);
 }
 
 // ---- allele table of one locus ---------------------------------------------------------------------------------------------
@@ -829,8 +897,24 @@ struct AlleleView {
     if (ek == 0 || ek == 4) return a.base == e.base;
     if (ek == 5) return true;
     if (a.len != e.len) return false;
-    if (ek == 2) { for (int i = 0; i < a.len; ++i) if (R.seq[a.ptr + i] != R.seq[e.ptr + i]) return false; return true; }
-    for (int i = 0; i < a.len; ++i) if (R.md[a.ptr + i] != R.md[e.ptr + i]) return false;
+    if (ek == 2) return bytes_equal(R.seq + a.ptr, R.seq + e.ptr, a.len);
+    return bytes_equal(reinterpret_cast<const uint8_t*>(R.md) + a.ptr, reinterpret_cast<const uint8_t*>(R.md) + e.ptr, a.len);
+  }
+  // eight bytes of each side per round trip (a byte-by-byte loop with an early exit is one dependent load per byte)
+  __device__ static bool bytes_equal(const uint8_t* __restrict__ x, const uint8_t* __restrict__ y, const int n) {
+    for (int i = 0; i < n; i += 8) {
+      uint8_t a[8], b[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool in = i + j < n;
+        a[j] = in ? __ldg(x + i + j) : (uint8_t)0;
+        b[j] = in ? __ldg(y + i + j) : (uint8_t)0;
+      }
+      bool eq = true;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) eq = eq && a[j] == b[j];
+      if (!eq) return false;
+    }
     return true;
   }
   // Allele.compare: java String.compareTo on ref, then alt (bytes widened by Byte.toChar)
@@ -874,6 +958,12 @@ struct OverlapWalker {
       : ring(r), src(first), last(last_), head(0), tail(0), locus(l) {
     if (first == 0xFFFFFFFFu) src = last = 0;
     else narrow_candidates(R, src, last, l, l + 1);
+    // the scan below is one dependent load per 32 candidates: ask for the second and third round's records now
+    const uint32_t lane = threadIdx.x & 31u;
+    if ((lane & 1u) == 0u) {  // (two 16-byte records per sector)
+      if (src + 32u + lane < last) asm volatile("prefetch.global.L2 [%0];" ::"l"(R.rec + src + 32u + lane));
+      if (src + 64u + lane < last) asm volatile("prefetch.global.L2 [%0];" ::"l"(R.rec + src + 64u + lane));
+    }
   }
   // warp-uniform; false when no read is left.  Lanes with valid == true hold one overlapping read each.
   __device__ bool next(const DevReads& R, uint32_t& r, ReadRec& rec, bool& valid) {
@@ -909,13 +999,19 @@ constexpr int kExactWarps = 4;
 __device__ void exact_locus(const DevReads& R, const int contig, const int locus, const CallParams& prm, DevOut& out, AlleleEntry* tab, uint32_t* ring) {
   const int lane = threadIdx.x & 31;
   const ContigInfo ci = R.contigs[contig];
-  bool std_ref;
-  const uint8_t ref_base = reference_base_of(R, ci, contig, locus, &std_ref);
+  // the track word and the granule's candidate range: five independent loads, one round trip
+  const uint32_t tw = ci.word_off + (uint32_t)(locus >> 5), gi = ci.gran_off + (uint32_t)(locus >> kGranuleShift);
+  const uint32_t t_std = __ldg(R.trk_std + tw), t_lo = __ldg(R.trk_lo + tw), t_hi = __ldg(R.trk_hi + tw);
+  const uint32_t first = __ldg(R.gran_first + gi), last = __ldg(R.gran_last + gi);
+  const int tb = locus & 31;
+  uint8_t ref_base = code_base(((t_lo >> tb) & 1u) | (((t_hi >> tb) & 1u) << 1));
+  if (!((t_std >> tb) & 1u)) {  // reference_base_of: no read offers a standard base here
+    bool std_ref;
+    ref_base = reference_base_of(R, ci, contig, locus, &std_ref);
+  }
   AlleleView av{R, ref_base};
   int na = 0, total = 0, pos_depth = 0, ref_depth = 0;
   int bc[4] = {0, 0, 0, 0};
-  const int g = locus >> kGranuleShift;
-  const uint32_t first = R.gran_first[ci.gran_off + g], last = R.gran_last[ci.gran_off + g];
   if (first == 0xFFFFFFFFu) return;
   OverlapWalker walk(R, ring, first, last, locus);
   uint32_t r;
@@ -929,7 +1025,8 @@ __device__ void exact_locus(const DevReads& R, const int contig, const int locus
     e.ptr = 0;
     int rc = 0;
     if (valid) {
-      rc = classify(R, r, locus, ref_base, e);
+      const ReadMeta M = load_read_meta(R, r);
+      rc = classify_meta(R, r, M, locus, ref_base, e);
       if (rc == 0 && e.kind == kNone) rc = GUAC_ERR_INVALID_CIGAR;
     }
     if (__any_sync(0xFFFFFFFFu, rc != 0)) {
@@ -1052,8 +1149,14 @@ __device__ void exact_locus(const DevReads& R, const int contig, const int locus
       int rl = av.ref_len(*a), al = av.alt_len(*a);
       uint32_t o = pool_alloc(out, (uint32_t)(rl + al));
       if ((unsigned long long)o + rl + al <= out.cap_pool) {
-        for (int i = 0; i < rl; ++i) out.pool[o + i] = av.ref_at(*a, i);
-        for (int i = 0; i < al; ++i) out.pool[o + rl + i] = av.alt_at(*a, i);
+        for (int i = 0; i < rl + al; i += 8) {  // (the loads of eight bytes before their stores: one round trip per eight)
+          uint8_t v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = i + j < rl ? av.ref_at(*a, i + j) : i + j < rl + al ? av.alt_at(*a, i + j - rl) : (uint8_t)0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (i + j < rl + al) out.pool[o + i + j] = v[j];
+        }
       }
       rcd.ref_off = o; rcd.ref_len = (uint16_t)rl; rcd.alt_off = o + rl; rcd.alt_len = (uint16_t)al;
     }
@@ -1098,9 +1201,21 @@ __global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, con
   __shared__ uint32_t rings[kExactWarps][64];
   const uint32_t n_loci = (uint32_t)min(out.counters[out.slow_ctr], (unsigned long long)out.cap_slow);
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t t = warp; t < n_loci; t += n_warps) {
+  // A locus is a chain of dependent round trips: 15 us for a plain one, four times that where a dozen reads carry a long
+  // insertion or deletion, and a warp decides one or two of them.  The first comes by warp index, every further one from a
+  // ticket counter, so that the warps that drew short loci take the rest (the counter and the count of warps that are
+  // through reset themselves: the last warp out zeroes both).
+  unsigned long long* ticket = out.work + 2 * (out.slow_ctr - 8u);
+  for (uint32_t t = warp; t < n_loci;) {
     exact_locus(R, loci[t].contig, loci[t].locus, prm, out, tabs[threadIdx.x >> 5], rings[threadIdx.x >> 5]);
     __syncwarp();
+    unsigned long long k = 0;
+    if ((threadIdx.x & 31) == 0) k = atomicAdd(ticket, 1ull);
+    t = n_warps + (uint32_t)__shfl_sync(0xFFFFFFFFu, (uint32_t)k, 0);
+  }
+  if ((threadIdx.x & 31) == 0 && atomicAdd(ticket + 1, 1ull) + 1ull == (unsigned long long)n_warps) {  // the last warp out
+    ticket[0] = 0ull;
+    ticket[1] = 0ull;
   }
 }
 
@@ -1162,6 +1277,23 @@ __global__ void __launch_bounds__(256) k_rec_to_host(const unsigned long long* _
   const unsigned long long n = min(counters[12 + seg], (unsigned long long)cap_seg);
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n && base + i < cap_total; i += (unsigned long long)gridDim.x * blockDim.x)
     host_rec[base + i] = dev_rec[base + i];
+}
+
+// the exact kernel's general records and allele bytes, HBM -> the pinned block of the result in 16-byte stores.  (The exact
+// kernel used to write them to host memory itself: one PCIe write per allele byte from a single lane, which is what a locus
+// with a long insertion spent most of its time on, and which slowed k_rec_to_host next to it to half its speed.)
+__global__ void __launch_bounds__(256) k_general_to_host(const unsigned long long* counters, const uint4* __restrict__ d_rec, const uint8_t* __restrict__ d_pool,
+                                                         uint4* __restrict__ h_rec, uint8_t* __restrict__ h_pool, uint32_t cap_rec, uint32_t cap_pool) {
+  static_assert(sizeof(guac_threshold_record) == 32, "two 16-byte stores per general record");
+  static_assert(kPoolDynOff % 8 == 0, "the dynamic part of the pool is copied in 8-byte words");
+  const unsigned long long n16 = 2ull * min(counters[0], (unsigned long long)cap_rec);
+  const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x, nth = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = tid; i < n16; i += nth) h_rec[i] = d_rec[i];
+  const unsigned long long pool_end = min((unsigned long long)kPoolDynOff + counters[1], (unsigned long long)cap_pool);
+  const unsigned long long n8 = (pool_end - kPoolDynOff + 7ull) / 8ull;  // (both buffers are padded past cap_pool)
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(d_pool + kPoolDynOff);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(h_pool + kPoolDynOff);
+  for (unsigned long long i = tid; i < n8; i += nth) dst[i] = src[i];
 }
 
 // plain copy of one segment's records (no ordering asked for, or a kernel that does not note its tiles' slices)
