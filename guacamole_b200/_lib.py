@@ -8,7 +8,7 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libguac_b200.so")
+LIB_PATH = os.environ.get("GUAC_B200_LIBRARY") or os.path.join(_HERE, "libguac_b200.so")  # (override: A/B of two builds on one box)
 
 # every symbol include/guac.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTED = [

@@ -843,19 +843,101 @@ __device__ __forceinline__ int classify_meta(const DevReads& R, const uint64_t r
   return 0;
 }
 
-// (one copy of the walk per kernel that calls it from several places)
+// The likelihood kernels' copy (one per kernel, called from several places): they classify ninety reads per locus and are
+// bound by the number of loads, not by their latency — every load only where it is needed.
+// PileupElement(read, locus, referenceBase) + alignment + qualityScore  (pileup/PileupElement.scala:68-171, 220-274)
 __device__ __noinline__ int classify(const DevReads& R, uint64_t r, int locus, uint8_t ref_base, Elem& e) {
   const ReadRec rec = R.rec[r];
-  if ((rec.info & kInfoSimple) && locus >= rec.start && locus < rec.end) {  // (the likelihood kernels' common case: two loads)
-    const uint64_t at = R.seq_off[r] + (uint64_t)((int)(rec.info & kInfoLeadMask) + (locus - rec.start));
-    e.base = R.seq[at];
-    e.qual = R.qual ? (int)(int8_t)R.qual[at] : 0;
+  const uint8_t* seq = R.seq + R.seq_off[r];
+  const uint8_t* qual = R.qual ? R.qual + R.seq_off[r] : nullptr;  // absent when packed without qualities
+  e.kind = kNone;
+  if ((rec.info & kInfoSimple) && locus >= rec.start && locus < rec.end) {
+    // one M/=/X run between clips: the element is a plain base, no CIGAR walk needed
+    const int rp = (int)(rec.info & kInfoLeadMask) + (locus - rec.start);
+    e.base = seq[rp];
+    e.qual = qual ? (int)(int8_t)qual[rp] : 0;
     e.kind = (e.base == ref_base) ? kMatch : kMismatch;
     e.len = 1;
     return 0;
   }
-  const ReadMeta M = load_read_meta(R, r);
-  return classify_meta(R, r, M, locus, ref_base, e);
+  const uint32_t c0 = R.cig_off[r], c1 = R.cig_off[r + 1];
+  const int read_len = (int)(R.seq_off[r + 1] - R.seq_off[r]);
+  const int mapq = (int)(rec.info >> kInfoMapqShift);
+  int ref_pos = rec.start, read_pos = 0;
+  e.kind = kNone;
+  for (uint32_t c = c0; c < c1; ++c) {
+    const uint32_t op = R.cigar[c] & 0xF;
+    const int len = (int)(R.cigar[c] >> 4);
+    const int ref_len = op_consumes_ref(op) ? len : 0;
+    const bool here = ref_pos <= locus && locus < ref_pos + ref_len;
+    const bool stay_on_insertion = !here && locus == 0 && op == GUAC_CIGAR_I;  // insertion at the start of a contig
+    if (!here && !stay_on_insertion) {
+      if (op_consumes_read(op)) read_pos += len;
+      ref_pos += ref_len;
+      continue;
+    }
+    const int idx = here ? locus - ref_pos : 0;
+    const int rp = read_pos + ((here && op_consumes_read(op)) ? idx : 0);
+    const bool is_final = idx == len - 1;
+    const bool has_next = c + 1 < c1;
+    const uint32_t next_op = is_final ? (has_next ? (R.cigar[c + 1] & 0xF) : 0xFFu) : op;
+    const int next_len = has_next ? (int)(R.cigar[c + 1] >> 4) : 0;
+    auto insertion = [&](int ins_len) {
+      int from = min(max(rp, 0), read_len), until = min(rp + ins_len + 1, read_len);
+      if (until <= from) return (int)GUAC_ERR_INVALID_CIGAR;
+      e.kind = kInsertion;
+      e.len = until - from;
+      e.ptr = R.seq_off[r] + from;
+      int q = 255;
+      for (int k = from; k < until; ++k) q = min(q, qual ? (int)(int8_t)qual[k] : 0);
+      e.qual = q;
+      e.base = seq[from];
+      return 0;
+    };
+    if ((op == GUAC_CIGAR_M || op == GUAC_CIGAR_EQ) && next_op == GUAC_CIGAR_I) return insertion(next_len);
+    if (op == GUAC_CIGAR_I && next_op != 0xFFu && ref_pos == 0) return insertion(len);
+    if (op == GUAC_CIGAR_I) return GUAC_ERR_INVALID_CIGAR;
+    if (op_is_match_like(op) && next_op == GUAC_CIGAR_D) {
+      long off = md_deleted_offset(R, r, locus + 1);
+      if (off < 0 || rp < 0 || rp >= read_len) return GUAC_ERR_MISSING_MD;
+      // all next_len deleted bases must be present in the tag: they follow contiguously (the tag was upper-cased at pack
+      // time; '^' or a digit in between is what a second walk to the last deleted base would also trip over)
+      if ((uint64_t)off + (uint64_t)next_len > (uint64_t)R.md_off[r + 1]) return GUAC_ERR_MISSING_MD;
+      for (int i = 1; i < next_len; ++i) {
+        const char ch = R.md[off + i];
+        if (ch < 'A' || ch > 'Z') return GUAC_ERR_MISSING_MD;
+      }
+      e.kind = kDeletion;
+      e.len = next_len;
+      e.ptr = (uint64_t)off;
+      e.qual = qual ? (int)(int8_t)qual[rp] : 0;
+      e.base = ref_base;
+      return 0;
+    }
+    if (op == GUAC_CIGAR_D) {
+      long off = md_deleted_offset(R, r, locus);
+      if (off < 0) return GUAC_ERR_MISSING_MD;
+      e.kind = kMidDeletion;
+      e.base = (uint8_t)R.md[off];
+      e.qual = mapq;
+      e.len = 0;
+      return 0;
+    }
+    if (next_op == GUAC_CIGAR_D) return GUAC_ERR_INVALID_CIGAR;  // deletion preceded by a non-match operator
+    if (op_is_match_like(op)) {
+      if (rp < 0 || rp >= read_len) return GUAC_ERR_INVALID_CIGAR;
+      e.base = seq[rp];
+      e.qual = qual ? (int)(int8_t)qual[rp] : 0;
+      e.kind = (e.base == ref_base) ? kMatch : kMismatch;
+      e.len = 1;
+      return 0;
+    }
+    e.kind = kClipped;  // N (S and H have no reference length)
+    e.qual = mapq;
+    e.len = 0;
+    return 0;
+  }
+  return 0;
 }
 
 // ---- allele table of one locus ---------------------------------------------------------------------------------------------
@@ -872,6 +954,7 @@ struct AlleleEntry {
 struct AlleleView {
   const DevReads& R;
   uint8_t ref_base;
+  bool batched = false;  // same(): eight bytes per round trip (the germline exact kernel, where a locus' latency is what counts)
   __device__ int ref_len(const AlleleEntry& a) const { return a.kind == 3 ? 1 + a.len : (a.kind == 5 ? 0 : 1); }
   __device__ int alt_len(const AlleleEntry& a) const { return a.kind == 2 ? a.len : (a.kind == 4 || a.kind == 5 ? 0 : 1); }
   __device__ uint8_t ref_at(const AlleleEntry& a, int i) const {
@@ -897,8 +980,13 @@ struct AlleleView {
     if (ek == 0 || ek == 4) return a.base == e.base;
     if (ek == 5) return true;
     if (a.len != e.len) return false;
-    if (ek == 2) return bytes_equal(R.seq + a.ptr, R.seq + e.ptr, a.len);
-    return bytes_equal(reinterpret_cast<const uint8_t*>(R.md) + a.ptr, reinterpret_cast<const uint8_t*>(R.md) + e.ptr, a.len);
+    if (batched) {
+      if (ek == 2) return bytes_equal(R.seq + a.ptr, R.seq + e.ptr, a.len);
+      return bytes_equal(reinterpret_cast<const uint8_t*>(R.md) + a.ptr, reinterpret_cast<const uint8_t*>(R.md) + e.ptr, a.len);
+    }
+    if (ek == 2) { for (int i = 0; i < a.len; ++i) if (R.seq[a.ptr + i] != R.seq[e.ptr + i]) return false; return true; }
+    for (int i = 0; i < a.len; ++i) if (R.md[a.ptr + i] != R.md[e.ptr + i]) return false;
+    return true;
   }
   // eight bytes of each side per round trip (a byte-by-byte loop with an early exit is one dependent load per byte)
   __device__ static bool bytes_equal(const uint8_t* __restrict__ x, const uint8_t* __restrict__ y, const int n) {
@@ -954,13 +1042,15 @@ struct OverlapWalker {
   uint32_t src, last;
   uint32_t head, tail;
   int locus;
-  __device__ OverlapWalker(const DevReads& R, uint32_t* r, uint32_t first, uint32_t last_, int l)
+  __device__ OverlapWalker(const DevReads& R, uint32_t* r, uint32_t first, uint32_t last_, int l, bool ahead = false)
       : ring(r), src(first), last(last_), head(0), tail(0), locus(l) {
     if (first == 0xFFFFFFFFu) src = last = 0;
     else narrow_candidates(R, src, last, l, l + 1);
     // the scan below is one dependent load per 32 candidates: ask for the second and third round's records now
+    // (the germline exact kernel only: a warp decides one locus there and the chain's length is the kernel's duration; the
+    // likelihood kernels keep dozens of loci per warp in flight and are slower with the extra requests)
     const uint32_t lane = threadIdx.x & 31u;
-    if ((lane & 1u) == 0u) {  // (two 16-byte records per sector)
+    if (ahead && (lane & 1u) == 0u) {  // (two 16-byte records per sector)
       if (src + 32u + lane < last) asm volatile("prefetch.global.L2 [%0];" ::"l"(R.rec + src + 32u + lane));
       if (src + 64u + lane < last) asm volatile("prefetch.global.L2 [%0];" ::"l"(R.rec + src + 64u + lane));
     }
@@ -1009,11 +1099,11 @@ __device__ void exact_locus(const DevReads& R, const int contig, const int locus
     bool std_ref;
     ref_base = reference_base_of(R, ci, contig, locus, &std_ref);
   }
-  AlleleView av{R, ref_base};
+  AlleleView av{R, ref_base, /*batched=*/true};
   int na = 0, total = 0, pos_depth = 0, ref_depth = 0;
   int bc[4] = {0, 0, 0, 0};
   if (first == 0xFFFFFFFFu) return;
-  OverlapWalker walk(R, ring, first, last, locus);
+  OverlapWalker walk(R, ring, first, last, locus, /*ahead=*/true);
   uint32_t r;
   ReadRec rec;
   bool valid;
