@@ -521,3 +521,26 @@ def test_compact_batch_real_and_synthetic(ctx):
     gap = ReadBatch.from_records([make_read("TCGATCGA", "8M", "8", 1, chr="a"), make_read("GCGATCGA", "8M", "0T7", 1, chr="a"),
                                   make_read("GCGATCGA", "8M", "0T7", 3, chr="c")], contig_names=["a", "b", "c"])
     assert _same_results(ctx, gap, [(0, 0, 50), (1, 0, 50), (2, 0, 50)]) > 0
+
+
+@pytest.mark.gpu
+def test_call_segments_and_repeated_calls(ctx):
+    """GUAC_OPT_SEGMENTS cuts a germline call into up to four segments of tiles whose exact kernels share the general-record
+    buffers and draw their loci from per-segment ticket counters (which reset themselves): the same records as one segment,
+    equal to the oracle's, call after call on one context (indel-rich reads so that the exact kernel has work in every segment)."""
+    from guacamole_b200 import abi, callers, synth
+    L = 1_000_000
+    b = synth.generate([("20", L)], depth=30, seed=977, sample=0, frac_ins=0.03, frac_del=0.03).to_read_batch()
+    ranges = [(0, 0, L - 1)]
+    want = orc.germline_threshold(b, ranges, orc.threshold_params(8)).threshold()
+    reads = ctx.pack(b)
+    try:
+        for seg in (1, 2, 3, 4, 1):
+            ctx.set_option(abi.OPT_SEGMENTS, seg)
+            for _ in range(2):
+                got = callers.germline_threshold(ctx, reads, ranges, threshold=8)
+                assert got.stats["exact_loci"] > 50
+                assert got.genotypes() == want, seg
+    finally:
+        ctx.set_option(abi.OPT_SEGMENTS, 1)
+        reads.free()
