@@ -67,6 +67,10 @@ struct HeaderArgs {
 __global__ void __launch_bounds__(256) k_header(HeaderArgs H) {
   const int lane = threadIdx.x & 31;
   uint32_t mask_sent[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // (lane 0: bits of mapq_mask this warp has already set)
+  // Largest end per contig and longest span: running maxima of the warp over its iterations, sent when the contig changes and
+  // at the end (one same-address atomic per warp and iteration was most of this kernel's 1.5 ms on a chr20 read set)
+  unsigned span_sent = 0, run_end = 0;
+  int32_t run_contig = -1;
   for (uint64_t i0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ull; i0 < H.n; i0 += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t i = i0 + lane;
     int status = 0;
@@ -155,14 +159,25 @@ __global__ void __launch_bounds__(256) k_header(HeaderArgs H) {
     const bool uniform = __all_sync(0xFFFFFFFFu, !ok || c == c_lead) && __shfl_sync(0xFFFFFFFFu, (int)ok, 0);
     const unsigned span = ok ? (unsigned)ref_len : 0u;
     const unsigned max_span = __reduce_max_sync(0xFFFFFFFFu, span);
-    if (lane == 0 && max_span) atomicMax(&H.summary[1], (unsigned long long)max_span);
+    if (lane == 0 && max_span > span_sent) {
+      atomicMax(&H.summary[1], (unsigned long long)max_span);
+      span_sent = max_span;
+    }
     if (uniform) {
       const unsigned max_end = __reduce_max_sync(0xFFFFFFFFu, ok ? (unsigned)end : 0u);
-      if (lane == 0) atomicMax(&H.contig_end[c_lead], (long long)max_end);
+      if (lane == 0) {
+        if (run_contig != c_lead) {
+          if (run_contig >= 0) atomicMax(&H.contig_end[run_contig], (long long)run_end);
+          run_contig = c_lead;
+          run_end = 0;
+        }
+        run_end = max(run_end, max_end);
+      }
     } else if (ok) {
       atomicMax(&H.contig_end[c], (long long)end);
     }
   }
+  if (lane == 0 && run_contig >= 0) atomicMax(&H.contig_end[run_contig], (long long)run_end);
 }
 
 // rec[i].pair_off from the scan of n_pairs; rec[n] = the sentinel

@@ -44,6 +44,7 @@ if what in ("germline", "both"):
     ctx.set_option(abi.OPT_PACK_QUALITIES, 0)
     dv = synth.generate_device(ctx, contigs, depth=30, seed=20261020, sample=0, with_qualities=False)
     reads = ctx.pack_synth(dv)
+    print("germline pack_kernel_ms", round(reads.pack_kernel_ms, 3), "expand", round(reads.expand_kernel_ms, 3), flush=True)
     timed(lambda: callers.germline_threshold(ctx, reads, ranges, threshold=8), False)
     reads.free()
     ctx.set_option(abi.OPT_TRIM_CACHE, 1)
