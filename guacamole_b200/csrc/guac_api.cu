@@ -842,7 +842,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
     if (device_sort) {
       ctx->sort_bins.ensure(3 * nt_pad);  // tile_base | tile_n | prefix (calls over more than 64 K tiles)
       ctx->scan_totals.ensure((size_t)n_seg * ((nt_all + kScanChunk - 1) / kScanChunk + 2));
-      CUDA_OK(cudaMemsetAsync(ctx->sort_bins.p + nt_pad, 0, nt_pad * sizeof(uint32_t), st));  // tile_n
+      // (tile_n needs no clearing: every tile of the call writes its count, k_call_tile's flush_stage)
       out.tile_base = ctx->sort_bins.p;
       out.tile_n = ctx->sort_bins.p + nt_pad;
     } else {

@@ -142,11 +142,9 @@ __device__ __forceinline__ void flush_stage(DevOut& out, EmitStage* stage, uint3
       }
       if (base + rank < out.cap_compact) out.compact[base + rank] = v;
     }
-    if (lane == 0 && out.tile_n) {
-      out.tile_base[out.tile0 + tile] = (uint32_t)base;
-      out.tile_n[out.tile0 + tile] = nr;
-    }
+    if (lane == 0 && out.tile_n) out.tile_base[out.tile0 + tile] = (uint32_t)base;
   }
+  if (lane == 0 && out.tile_n) out.tile_n[out.tile0 + tile] = nr;  // (every tile, also 0: the array is not cleared between calls)
   if (ns) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(&out.counters[out.slow_ctr], (unsigned long long)ns);
