@@ -871,8 +871,6 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
       cudaEvent_t done = seg + 1 == n_seg ? ctx->ev[1] : ctx->seg_ev[seg];
       CUDA_OK(cudaEventRecord(done, st));
       CUDA_OK(cudaStreamWaitEvent(st2, done, 0));
-      // (8 CTAs per SM: all of them resident at once with room left for the egress kernels' 256-thread blocks next to them —
-      // a grid that is not resident in full keeps every later launch waiting, whatever its stream)
       launches += 1;
       if (!counts_mode) {
         CUDA_OK(cudaStreamWaitEvent(st3, done, 0));
@@ -900,11 +898,11 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
           launches += 1;
         }
       }
-      // (after the egress kernels in launch order, and 7 CTAs of 56 registers per SM: the egress kernels' 256-thread blocks find
-      // room next to them.  With 8 the register file was full and the record gather waited for the exact kernel to drain:
-      // 90 us instead of 15.)
+      // (after the egress kernels in launch order, and 8 CTAs of 48 registers per SM: the egress kernels' 256-thread blocks find
+      // room next to them.  At 56 registers the register file was full and the record gather waited for the exact kernel to
+      // drain — 90 us instead of 16; from 10 CTAs per SM on k_rec_to_host is starved the same way.)
       if (x_tl) cudaEventRecord(xe[0], st2);
-      k_exact_loci<<<ctx->sm_count * 7, kExactWarps * 32, 0, st2>>>(R, so.slow, prm, so);
+      k_exact_loci<<<ctx->sm_count * 8, kExactWarps * 32, 0, st2>>>(R, so.slow, prm, so);
       if (x_tl) cudaEventRecord(xe[1], st2);
       if (!counts_mode && seg + 1 == n_seg) {  // (the segments' exact kernels run in order on st2 and share the buffers)
         k_general_to_host<<<8, 256, 0, st2>>>(ctx->d_counters, (const uint4*)ctx->out_rec.p, ctx->out_pool.p, (uint4*)((unsigned char*)res.block + full_at),
