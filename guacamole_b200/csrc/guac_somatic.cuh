@@ -1255,7 +1255,7 @@ __device__ void evidence_sample(const DevReads& R, int contig, int locus, const 
 
 constexpr int kEvidenceWarps = 4;
 
-__global__ void __launch_bounds__(kEvidenceWarps * 32) k_evidence(DevReads RT, DevReads RN, SomParams prm, SomOut out) {
+__global__ void __launch_bounds__(kEvidenceWarps * 32, 8) k_evidence(DevReads RT, DevReads RN, SomParams prm, SomOut out) {
   __shared__ EvidenceSmem sm[kEvidenceWarps];
   EvidenceSmem& S = sm[threadIdx.x >> 5];
   const uint32_t n_rec = (uint32_t)min(out.counters[0], (unsigned long long)out.cap_rec);
