@@ -182,3 +182,28 @@ def test_compact_batch_conversion():
     cb.free()
     with pytest.raises(callers.GuacError):
         callers.CompactBatch(ReadBatch.from_records([make_read("ACgT", "4M", "4", 1)]))
+
+
+def test_python_constants_mirror_the_header():
+    """Every integer constant of include/guac.h that guacamole_b200/abi.py mirrors (status codes, read flags, context options,
+    the ABI version) carries the header's value: the two are edited by hand."""
+    import re
+    text = open(os.path.join(ROOT, "include", "guac.h")).read()
+    header = {}
+    for name, value in re.findall(r"^#define\s+GUAC_([A-Z0-9_]+)\s+(0x[0-9A-Fa-f]+|\d+)u?\b", text, flags=re.M):
+        header[name] = int(value, 0)
+    for name, value in re.findall(r"^\s*GUAC_(OK|ERR_[A-Z_]+)\s*=\s*(\d+)", text, flags=re.M):
+        header[name] = int(value)
+    checked = 0
+    for name, value in header.items():
+        mirror = getattr(abi, name, None)
+        if mirror is None and name == "ABI_VERSION":
+            mirror = abi.GUAC_ABI_VERSION
+        if mirror is None:
+            continue
+        assert mirror == value, (name, mirror, value)
+        checked += 1
+    assert checked >= 25, checked
+    for name in ("OPT_SORT_RECORDS", "OPT_PACK_QUALITIES", "OPT_HOST_THREADS", "OPT_DIFFERENCE_LISTS", "OPT_SEGMENTS", "OPT_TRIM_CACHE",
+                 "OPT_PACK_OVERLAP"):
+        assert name in header and getattr(abi, name) == header[name], name
