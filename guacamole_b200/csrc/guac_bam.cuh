@@ -19,6 +19,7 @@
 #include <thread>
 
 #include "guac_batch2.cuh"
+#include "guac_inflate.h"
 
 namespace {
 
@@ -106,17 +107,22 @@ void bam_load(const char* path, const guac_bam_options& opt, guac_host_batch_v2&
   // nature) as soon as the member holding the next length word is done, so the walk hides underneath the inflate.
   std::unique_ptr<std::atomic<uint8_t>[]> done(new std::atomic<uint8_t>[members.size() + 1]);
   for (size_t k = 0; k <= members.size(); ++k) done[k].store(0, std::memory_order_relaxed);
-  std::atomic<size_t> next{0};
+  std::atomic<size_t> next{0}, n_fast{0};
   std::atomic<int> bad{0};
+  const bool use_fast_inflate = getenv("GUAC_BAM_ZLIB_ONLY") == nullptr;  // (A/B and the fallback's test)
   std::vector<std::thread> inflaters;
   for (unsigned t = 0; t < n_thr; ++t)
     inflaters.emplace_back([&] {
       z_stream zs;
       memset(&zs, 0, sizeof zs);
       const bool ok = inflateInit2(&zs, -15) == Z_OK;
+      std::unique_ptr<guac_inflate::Tables> tables(new guac_inflate::Tables);
       for (size_t k; (k = next.fetch_add(1)) < members.size();) {
         const Member& mb = members[k];
-        if (ok) {
+        // the member's own decoder first (guac_inflate.h: 2 - 3 x zlib on BGZF members); whatever it refuses goes through zlib
+        if (use_fast_inflate && guac_inflate::inflate_member(file.p + mb.c_off, mb.c_len, raw.get() + mb.u_off, mb.u_len, *tables)) {
+          n_fast.fetch_add(1, std::memory_order_relaxed);
+        } else if (ok) {
           inflateReset(&zs);
           zs.next_in = const_cast<Bytef*>(file.p + mb.c_off);
           zs.avail_in = mb.c_len;
@@ -208,6 +214,7 @@ void bam_load(const char* path, const guac_bam_options& opt, guac_host_batch_v2&
   if (bad) fail(GUAC_ERR_INVALID_ARGUMENT, "%s: corrupt BGZF member", path);
   const uint64_t n_rec = recs.size();
   lap("inflate + record walk");
+  if (trace) fprintf(stderr, "[guac bam] members %zu, of which %zu through guac_inflate\n", members.size(), n_fast.load());
 
   // ---- pass A: fields, tags, filters
   std::atomic<int> bad_record{0};
