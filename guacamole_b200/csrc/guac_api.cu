@@ -760,7 +760,7 @@ void run_pileup(guac_ctx* ctx, const guac_reads& reads, const guac_locus_range* 
   const bool dense = counts_mode || prm.emit_ref || prm.emit_no_call;
   // counts mode: rows (guac_locus_counts) in HBM, copied afterwards.  Germline mode: the tile kernel's single-base records
   // are compact (8 bytes) in HBM, ordered on the device and streamed to the pinned host block of the result; the exact
-  // kernel's few general records and their allele bytes are written to that block directly (unified addressing).
+  // kernel's few general records and their allele bytes are staged in HBM as well and copied there by k_general_to_host.
   uint64_t cap_rec = counts_mode ? tile_loci + 16 : std::max<uint64_t>(4096, tile_loci / 256);
   uint64_t cap_compact = counts_mode ? 8 : (dense ? tile_loci + tile_loci / 8 + 16 : std::max<uint64_t>(4096, tile_loci / 64));
   uint64_t cap_slow = std::max<uint64_t>(4096, tile_loci / 32);

@@ -1281,9 +1281,9 @@ __device__ void exact_locus(const DevReads& R, const int contig, const int locus
 }
 
 
-// grid-stride over the loci the tile kernel deferred; their number is read from the device counter (no host round trip).
-// In germline mode out.trec / out.pool point into the pinned host block of the result (unified addressing): the few general
-// records and their allele bytes are written there directly.
+// The loci the tile kernel deferred; their number is read from the device counter (no host round trip).  out.trec / out.pool
+// are device buffers in every mode: in germline mode k_general_to_host copies the few general records and their allele bytes
+// to the pinned host block of the result afterwards.
 __global__ void __launch_bounds__(kExactWarps * 32) k_exact_loci(DevReads R, const SlowLocus* __restrict__ loci, CallParams prm, DevOut out) {
   __shared__ AlleleEntry tabs[kExactWarps][kMaxAlleles];
   __shared__ uint32_t rings[kExactWarps][64];
