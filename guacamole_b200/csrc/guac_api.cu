@@ -1042,7 +1042,23 @@ void expand_threshold_records(guac_result& r) {
     if (c != 0) return c < 0;
     return a.alt_len < b.alt_len;
   };
-  if (r.want_sorted) std::sort(gen.begin(), gen.end(), less_general);
+  if (r.want_sorted && gen.size() > 1) {
+    // (contig, start) as one integer first — the exact kernel hands its records out in ticket order, and a comparator that
+    // looks at allele bytes for every pair was half of this function's time —, the full order only inside a locus' own records
+    std::vector<std::pair<unsigned long long, uint32_t>> keyed(gen.size());
+    for (size_t q = 0; q < gen.size(); ++q)
+      keyed[q] = {(((unsigned long long)(uint32_t)gen[q].contig) << 32) | (unsigned long long)(uint32_t)gen[q].start, (uint32_t)q};
+    std::sort(keyed.begin(), keyed.end());
+    std::vector<guac_threshold_record> ordered(gen.size());
+    for (size_t q = 0; q < gen.size(); ++q) ordered[q] = gen[keyed[q].second];
+    for (size_t a = 0; a < ordered.size();) {
+      size_t b = a + 1;
+      while (b < ordered.size() && keyed[b].first == keyed[a].first) ++b;
+      if (b - a > 1) std::sort(ordered.begin() + (ptrdiff_t)a, ordered.begin() + (ptrdiff_t)b, less_general);
+      a = b;
+    }
+    gen.swap(ordered);
+  }
   r.expanded.resize(r.n_records);
   auto widen = [&](unsigned long long v) {
     guac_threshold_record t;
