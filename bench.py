@@ -17,7 +17,9 @@ A "step" is one pass of the hot path over one batch of synthetic reads, through 
 the call (+ the NCCL gather at N > 1) to records in host memory every step — at N > 1 over a chr20-sized slice of each rank's
 shard (the whole shard would need 124 GB of pinned host memory).  `cpu_baseline` / `--impl reference` is the oracle (a C++
 restatement of the reference's Scala algorithm — there is no JVM on the box) on a bounded window of the same workload, and
-`parity_window` says whether the engine's records inside that window equal the oracle's.
+`parity_window` says whether the engine's records inside that window equal the oracle's; `e2e_check` whether the end-to-end
+leg handed back exactly the resident leg's records (an order-independent fingerprint of all of them); `gather_check` (N > 1)
+whether rank 0's gathered set is the concatenation of the ranks' sets.  Any of them failing exits non-zero after the line.
 """
 import argparse
 import ctypes as C
@@ -564,6 +566,7 @@ def main():
                                f"({args.contig_length:,} loci), {READ_LEN} bp (BASELINE.json configs[2])")
         som_blk["dtype"] = "f64"
 
+    failed = False
     if rank == 0:
         line = {"metric": "loci_per_sec", "value": main_blk["value"], "unit": "loci/s", "reads_per_sec": main_blk["reads_per_sec"],
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_blk["ms_per_step"],
@@ -581,10 +584,13 @@ def main():
         print(json.dumps(line), flush=True)
         if bad:
             print("PARITY FAILURE: " + "; ".join(bad), file=sys.stderr, flush=True)
+            failed = True
     if comm is not None:
         comm.close()
     if world > 1:
         dist.destroy_process_group()
+    if failed:  # (after the line: a number whose records differ from the oracle's is not a result)
+        sys.exit(1)
 
 
 if __name__ == "__main__":
