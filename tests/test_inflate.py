@@ -42,3 +42,41 @@ def test_bam_loader_same_reads_with_and_without_own_inflate(tmp_path, monkeypatc
         assert (va == vb).all(), col
     a.free()
     b.free()
+
+
+def test_bam_loader_on_corrupt_members(tmp_path, monkeypatch):
+    """Bytes flipped inside BGZF members: the loader fails with an error or — where the damage is harmless to the deflate
+    stream — returns what it returns through zlib; it never crashes and the two paths never disagree."""
+    import numpy as np
+    from guacamole_b200._lib import GuacError
+    want = load_golden("chrM.sorted")
+    path = str(tmp_path / "x.bam")
+    write_bam(want, path, level=6, block_bytes=8192)
+    raw = bytearray(open(path, "rb").read())
+    rng = np.random.default_rng(5)
+    outcomes = set()
+    for trial in range(12):
+        bad = bytearray(raw)
+        for _ in range(3):
+            at = int(rng.integers(400, len(bad) - 64))  # (behind the header's members, in front of the EOF marker)
+            bad[at] ^= 1 << int(rng.integers(0, 8))
+        p2 = str(tmp_path / f"bad{trial}.bam")
+        open(p2, "wb").write(bytes(bad))
+        res = []
+        for zlib_only in (False, True):
+            if zlib_only:
+                monkeypatch.setenv("GUAC_BAM_ZLIB_ONLY", "1")
+            else:
+                monkeypatch.delenv("GUAC_BAM_ZLIB_ONLY", raising=False)
+            try:
+                cb = callers.CompactBatch.from_bam(p2, n_threads=2)
+                rb = cb.to_read_batch()
+                res.append(("ok", len(rb), bytes(np.asarray(rb.seq)[:2000]), bytes(np.asarray(rb.start).tobytes()[:2000])))
+                cb.free()
+            except (GuacError, ValueError, RuntimeError) as e:
+                res.append(("error",))
+        assert res[0][0] == res[1][0], (trial, res[0][0], res[1][0])
+        if res[0][0] == "ok":
+            assert res[0] == res[1], trial
+        outcomes.add(res[0][0])
+    assert "error" in outcomes  # (most flips break a member)
