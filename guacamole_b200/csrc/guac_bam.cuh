@@ -276,40 +276,92 @@ void bam_load(const char* path, const guac_bam_options& opt, guac_host_batch_v2&
     auto it = std::find(samples.begin(), samples.end(), std::string(opt.sample));
     want_sample = it == samples.end() ? (std::string(opt.sample) == "default" ? -1 : -3) : (int)(it - samples.begin());
   }
-  std::vector<uint32_t> kept;
-  kept.reserve(n_rec);
+  // Selection and offsets, slice by slice on all threads (a serial pass over the records is a cache miss per record: a third of
+  // a second for a chr20 at 30x): per slice the kept records, their sizes, whether they are in (contig, start) order and of one
+  // sample; the slices' sums are scanned, then every slice writes its part of `kept` and of the offset columns.
+  if (n_rec >= 0xFFFFFFFFull) fail(GUAC_ERR_UNSUPPORTED, "%s: more than 2^32 records", path);
+  struct Slice {
+    uint64_t kept = 0, cig = 0, seq = 0, md = 0;
+    int sample = -2;          // of its kept reads (-2: none kept)
+    bool mixed = false, sorted = true;
+    int32_t first_ref = 0, first_pos = 0, last_ref = 0, last_pos = 0;
+  };
+  const unsigned n_sl = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(n_thr, n_rec));
+  std::vector<Slice> sl(n_sl);
+  parallel_for(n_thr, n_rec, [&](unsigned t, uint64_t b, uint64_t e) {
+    Slice z;
+    for (uint64_t i = b; i < e; ++i) {
+      BamRec& r = recs[i];
+      if (!r.keep) continue;
+      if (want_sample != -2 && r.sample != want_sample) { r.keep = 0; continue; }
+      if (z.sample == -2) z.sample = r.sample;
+      else if (z.sample != r.sample) z.mixed = true;
+      if (z.kept == 0) { z.first_ref = r.ref_id; z.first_pos = r.pos; }
+      else if (z.last_ref > r.ref_id || (z.last_ref == r.ref_id && z.last_pos > r.pos)) z.sorted = false;
+      z.last_ref = r.ref_id;
+      z.last_pos = r.pos;
+      z.kept += 1;
+      z.cig += r.n_cigar;
+      z.seq += r.l_seq;
+      z.md += r.md_len;
+    }
+    sl[t] = z;
+  });
   int seen_sample = -2;
   bool sorted = true;
-  for (uint64_t i = 0; i < n_rec; ++i) {
-    BamRec& r = recs[i];
-    if (!r.keep) continue;
-    if (want_sample != -2 && r.sample != want_sample) { r.keep = 0; continue; }
-    if (seen_sample == -2) seen_sample = r.sample;
-    else if (seen_sample != r.sample) fail(GUAC_ERR_INVALID_ARGUMENT, "%s holds reads of several samples: name one in guac_bam_options.sample", path);
-    if (!kept.empty()) {
-      const BamRec& q = recs[kept.back()];
-      if (q.ref_id > r.ref_id || (q.ref_id == r.ref_id && q.pos > r.pos)) sorted = false;
+  std::vector<uint64_t> base_kept(n_sl + 1, 0), base_cig(n_sl + 1, 0), base_seq(n_sl + 1, 0), base_md(n_sl + 1, 0);
+  {
+    const Slice* before = nullptr;
+    for (unsigned t = 0; t < n_sl; ++t) {
+      const Slice& z = sl[t];
+      base_kept[t + 1] = base_kept[t] + z.kept;
+      base_cig[t + 1] = base_cig[t] + z.cig;
+      base_seq[t + 1] = base_seq[t] + z.seq;
+      base_md[t + 1] = base_md[t] + z.md;
+      if (!z.kept) continue;
+      if (z.mixed || (seen_sample != -2 && seen_sample != z.sample))
+        fail(GUAC_ERR_INVALID_ARGUMENT, "%s holds reads of several samples: name one in guac_bam_options.sample", path);
+      seen_sample = z.sample;
+      sorted = sorted && z.sorted;
+      if (before && (before->last_ref > z.first_ref || (before->last_ref == z.first_ref && before->last_pos > z.first_pos))) sorted = false;
+      before = &z;
     }
-    if (i >= 0xFFFFFFFFull) fail(GUAC_ERR_UNSUPPORTED, "%s: more than 2^32 records", path);
-    kept.push_back((uint32_t)i);
   }
-  if (!sorted)  // (contig index, start), file order among equals: what sortBy(start) inside a task gives the reference
+  const uint64_t n = base_kept[n_sl];
+  if (base_cig[n_sl] >= 0xFFFFFFFFull || base_seq[n_sl] >= 0xFFFFFFFFull || base_md[n_sl] >= 0xFFFFFFFFull)
+    fail(GUAC_ERR_UNSUPPORTED, "%s: the compact batch holds fewer than 2^32 bases, CIGAR ops and MD bytes: load it by region / sample", path);
+  std::vector<uint32_t> kept(n);
+  std::vector<uint64_t> o_cig(n + 1, 0), o_seq(n + 1, 0), o_md(n + 1, 0);
+  parallel_for(n_thr, n_rec, [&](unsigned t, uint64_t b, uint64_t e) {
+    uint64_t k = base_kept[t], c = base_cig[t], q = base_seq[t], m = base_md[t];
+    for (uint64_t i = b; i < e; ++i) {
+      const BamRec& r = recs[i];
+      if (!r.keep) continue;
+      kept[k] = (uint32_t)i;
+      o_cig[k] = c;
+      o_seq[k] = q;
+      o_md[k] = m;
+      c += r.n_cigar;
+      q += r.l_seq;
+      m += r.md_len;
+      ++k;
+    }
+  });
+  o_cig[n] = base_cig[n_sl];
+  o_seq[n] = base_seq[n_sl];
+  o_md[n] = base_md[n_sl];
+  if (!sorted) {  // (contig index, start), file order among equals: what sortBy(start) inside a task gives the reference
     std::stable_sort(kept.begin(), kept.end(), [&](uint32_t a, uint32_t b) {
       return recs[a].ref_id != recs[b].ref_id ? recs[a].ref_id < recs[b].ref_id : recs[a].pos < recs[b].pos;
     });
-  const uint64_t n = kept.size();
-  H.sample_name = seen_sample >= 0 ? samples[(size_t)seen_sample] : std::string("default");
-
-  // ---- offsets
-  std::vector<uint64_t> o_cig(n + 1, 0), o_seq(n + 1, 0), o_md(n + 1, 0);
-  for (uint64_t k = 0; k < n; ++k) {
-    const BamRec& r = recs[kept[k]];
-    o_cig[k + 1] = o_cig[k] + r.n_cigar;
-    o_seq[k + 1] = o_seq[k] + r.l_seq;
-    o_md[k + 1] = o_md[k] + r.md_len;
+    for (uint64_t k = 0; k < n; ++k) {  // (the offsets follow the new order)
+      const BamRec& r = recs[kept[k]];
+      o_cig[k + 1] = o_cig[k] + r.n_cigar;
+      o_seq[k + 1] = o_seq[k] + r.l_seq;
+      o_md[k + 1] = o_md[k] + r.md_len;
+    }
   }
-  if (o_cig[n] >= 0xFFFFFFFFull || o_seq[n] >= 0xFFFFFFFFull || o_md[n] >= 0xFFFFFFFFull)
-    fail(GUAC_ERR_UNSUPPORTED, "%s: the compact batch holds fewer than 2^32 bases, CIGAR ops and MD bytes: load it by region / sample", path);
+  H.sample_name = seen_sample >= 0 ? samples[(size_t)seen_sample] : std::string("default");
   const uint64_t n_bases = o_seq[n];
   lap("select + offsets");
   bool fixed = n > 0;
